@@ -1,0 +1,210 @@
+/*
+ * zs_b200.h — C ABI of the B200 (sm_100a) stochastic-node hot path.
+ *
+ * This is the drop-in boundary for ZhuSuan-PyTorch's multi-particle path.  The
+ * reference has no FFI of its own (it is pure Python over torch); every entry
+ * point below replaces one Python function of the reference, cited as
+ * `file:line` relative to the reference tree.  INTEGRATION.md shows the ctypes
+ * stub a reference maintainer would add at each of those sites.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing here synchronises (except the `*_host` convenience calls);
+ *   - `dtype` is ZS_F32 or ZS_F64 (the reference's log_floating_dtypes,
+ *     zhusuan/distributions/utils.py:5); all tensor arguments of one call share it;
+ *   - return value: ZS_OK (0) or a negative ZS_ERR_* code; zs_strerror() names
+ *     it, zs_last_error() returns the CUDA error string of the calling thread;
+ *   - no global mutable state besides that thread-local error string.
+ *
+ * Tensor layout ("particle rows")
+ *   A stochastic node's value is viewed as [K, M, E], contiguous, where
+ *     K = n_particles (the reference's leading `n_samples` axis, base.py:138-140),
+ *     M = the batch rows that survive the event reduction,
+ *     E = the trailing event elements that are summed (group_ndims axes,
+ *         base.py:175-176, and trailing reduce_sum_dims, stochastic_tensor.py:164-165).
+ *   Each operand carries a layout mode:
+ *     ZS_FULL   [K, M, E]   one value per element
+ *     ZS_KBCAST [M, E]      broadcast over particles — replaces `.repeat([K,1,..])`
+ *                           (normal.py:94-95,115-116; bernoulli.py:75,90)
+ *     ZS_SCALAR [1]         one value for everything
+ *   Log-prob outputs are [K, M].
+ */
+#ifndef ZS_B200_H
+#define ZS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS_ABI_VERSION 1
+
+typedef void* zs_stream_t; /* cudaStream_t */
+
+enum { ZS_F32 = 0, ZS_F64 = 1 };
+enum { ZS_FULL = 0, ZS_KBCAST = 1, ZS_SCALAR = 2 };
+enum { ZS_EST_SGVB = 0, ZS_EST_VIMCO = 1 };
+
+enum {
+    ZS_OK = 0,
+    ZS_ERR_ARG = -1,         /* null pointer / negative size / bad enum          */
+    ZS_ERR_DTYPE = -2,       /* dtype not ZS_F32 / ZS_F64                        */
+    ZS_ERR_CUDA = -3,        /* a CUDA runtime call or launch failed             */
+    ZS_ERR_NO_DEVICE = -4,   /* no sm_100 device visible                         */
+    ZS_ERR_WORKSPACE = -5,   /* caller workspace too small (see *_workspace())   */
+    ZS_ERR_UNSUPPORTED = -6, /* shape outside what this entry point handles      */
+    ZS_ERR_ALIGN = -7        /* pointer not aligned as the entry point requires  */
+};
+
+/* ---- library info ------------------------------------------------------- */
+int zs_abi_version(void);
+const char* zs_strerror(int code);
+const char* zs_last_error(void);
+/* SM count and compute capability of the current device. */
+int zs_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- Philox4x32-10 counter RNG ------------------------------------------
+ * Element i of a call uses counter (i/4 lo, i/4 hi, offset lo, offset hi), key
+ * (seed lo, seed hi), word i%4.  Results do not depend on the launch geometry.
+ * Replaces the CPU-side torch.normal / torch.bernoulli + H2D copies at
+ * normal.py:104, bernoulli.py:79, SGLD.py:51, SGHMC.py:27,33,34.               */
+int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_philox_normal(int dtype, void* out, int64_t n, double mean, double std, uint64_t seed, uint64_t offset,
+                     zs_stream_t stream);
+/* raw 32-bit words (n must be a multiple of 4); used by the bit-exact RNG tests */
+int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream);
+
+/* ---- Normal stochastic node ----------------------------------------------
+ * zs_normal_sample: z[K,N] = mean + std * eps      (Normal._sample, normal.py:89-107)
+ *   eps_in  != NULL : injected noise [K,N] (parity mode; replaces torch.normal(0,1,size))
+ *   eps_in  == NULL : eps drawn from Philox(seed, offset), Box-Muller
+ *   eps_out != NULL : the noise used is also written there
+ *   N = M*E elements per particle; mean/std modes ZS_FULL|ZS_KBCAST|ZS_SCALAR.
+ * The same call serves the non-reparameterised branch (torch.normal(mean,std),
+ * normal.py:101-102): the value is identical, only autograd differs.            */
+int zs_normal_sample(int dtype, void* z, const void* mean, int mean_mode, const void* std, int std_mode,
+                     const void* eps_in, void* eps_out, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
+                     zs_stream_t stream);
+/* Pathwise gradient of the sample: dmean = sum_k dz, dstd = sum_k dz*eps (sums only
+ * over broadcast axes).  eps == NULL regenerates the noise from (seed, offset).
+ * dmean / dstd may be NULL.  SCALAR-mode grads are not produced here (host sums).  */
+int zs_normal_sample_bwd(int dtype, void* dmean, int mean_mode, void* dstd, int std_mode, const void* dz,
+                         const void* eps, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
+                         zs_stream_t stream);
+
+/* out[K,M] = sum_e ( c - log(std) - 0.5*exp(-2 log std)*(x-mean)^2 )
+ * Normal._log_prob (normal.py:109-126) + Distribution.log_prob's group_ndims sum
+ * (base.py:175-176) + StochasticTensor's trailing reduce_sum_dims
+ * (stochastic_tensor.py:164-165).                                               */
+int zs_normal_logprob_fwd(int dtype, void* out, const void* x, int x_mode, const void* mean, int mean_mode,
+                          const void* std, int std_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+/* Backward of the above for upstream g[K,M].  Any of dx/dmean/dstd may be NULL.
+ * Each gradient has the layout of its operand: FULL is written elementwise, KBCAST
+ * is summed over K in-kernel.  SCALAR gradients are not supported (pass NULL; the
+ * host expands the operand instead).                                            */
+int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const void* g, const void* x, int x_mode,
+                          const void* mean, int mean_mode, const void* std, int std_mode, int64_t K, int64_t M,
+                          int64_t E, zs_stream_t stream);
+
+/* ---- Bernoulli stochastic node -------------------------------------------
+ * out[K,N] = (u < probs) as float, u ~ Philox uniform   (Bernoulli._sample,
+ * bernoulli.py:72-82); u_in != NULL injects the uniforms (parity mode).         */
+int zs_bernoulli_sample(int dtype, void* out, const void* probs, int probs_mode, const void* u_in, int64_t K,
+                        int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+/* out[K,M] = sum_e ( x*log(p+1e-8) + (1-x)*log((1-p)+1e-8) )
+ * Bernoulli._log_prob (bernoulli.py:84-95) + the same event sums as above.      */
+int zs_bernoulli_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* probs, int probs_mode,
+                            int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+/* dprobs = g*( x/(p+1e-8) - (1-x)/((1-p)+1e-8) ), dx = g*(log(p+1e-8)-log((1-p)+1e-8)). */
+int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, const void* x, int x_mode,
+                            const void* probs, int probs_mode, int64_t K, int64_t M, int64_t E,
+                            zs_stream_t stream);
+
+/* ---- Categorical stochastic node (absent from the reference: parity unpinned;
+ * API modelled on bernoulli.py) --------------------------------
+ * logits [K|1, M, C]; value = class index stored as float/double in x[K,M].     */
+int zs_categorical_sample(int dtype, void* out, const void* logits, int logits_mode, const void* u_in, int64_t K,
+                          int64_t M, int64_t C, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_categorical_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* logits, int logits_mode,
+                              int64_t K, int64_t M, int64_t C, zs_stream_t stream);
+int zs_categorical_logpmf_bwd(int dtype, void* dlogits, const void* g, const void* x, int x_mode,
+                              const void* logits, int logits_mode, int64_t K, int64_t M, int64_t C,
+                              zs_stream_t stream);
+
+/* ---- multi-particle objectives over log-weights [K,B] ----------------------
+ * One launch computes the objective AND its gradient wrt logp and logq.
+ *   estimator ZS_EST_SGVB : ImportanceWeightedObjective.sgvb + compute_iw_term
+ *       (importance_weighted_objective.py:16-25,102-132)
+ *   estimator ZS_EST_VIMCO: ImportanceWeightedObjective.vimco (:134-191), the
+ *       [B,K,K] leave-one-out tensor replaced by O(K) per-column sums.
+ * log w = logp - logq (+ logp_extra when not NULL, a second generator term [K,B]).
+ * cost[B]   = per-column surrogate cost (cost_b); the scalar loss is mean_b cost_b.
+ * dlogp/dlogq [K,B] = d(sum_b cost_b * grad_scale)/d(logp|logq); pass
+ *   grad_scale = 1/B_global to get the gradient of the mean.  Either may be NULL. */
+int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlogq, const void* logp,
+                    const void* logq, const void* logp_extra, int64_t K, int64_t B, double grad_scale,
+                    zs_stream_t stream);
+/* log_mean_exp over the leading axis of [K,B] -> [B]   (zhusuan/utils.py:6-21)    */
+int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, zs_stream_t stream);
+/* backward: dx[K,B] = g[B] * softmax_k(x)                                          */
+int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64_t K, int64_t B,
+                        zs_stream_t stream);
+
+/* ---- fused resident-column kernel: Bernoulli likelihood + objective, fwd+bwd --
+ * For every batch column b the K particle rows probs[:, b, :] are staged ONCE in
+ * shared memory (bulk async copies), their log-pmf at x[b,:] is reduced, combined
+ * with the rest of the log-weight, the estimator weights are formed, and dprobs is
+ * produced from the resident rows — probs is read from HBM once, dprobs written once.
+ *   logp_other[K,B] = sum of the other generator log-probs (may be NULL = 0)
+ *   logq[K,B]       = variational log-prob (may be NULL = 0 for SGVB; required for VIMCO)
+ *   log w = logpx + logp_other - logq
+ *   cost[B], dprobs[K,B,X], dlogp[K,B] (= gradient wrt every generator log-prob term),
+ *   dlogq[K,B]; logpx_out[K,B] optional copy of the likelihood term.
+ * Requires f32, X % 4 == 0, 16-byte aligned probs/dprobs/x and
+ * zs_iw_bernoulli_fused_smem_bytes(K,X) <= device opt-in shared memory; otherwise
+ * returns ZS_ERR_UNSUPPORTED and the caller uses the two-pass entry points.         */
+int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X);
+int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq,
+                          float* logpx_out, const float* probs, const float* x, const float* logp_other,
+                          const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                          zs_stream_t stream);
+
+/* ---- SG-MCMC updates across parallel chains (in place, one pass) -------------
+ * noise != NULL injects the already-scaled Gaussian term (parity mode); otherwise
+ * it is drawn from Philox(seed, offset) inside the kernel.
+ * SGLD._update (SGLD.py:42-54):  w += 0.5*lr*g + N(0, lr)                          */
+int zs_sgld_step(int dtype, void* w, const void* g, const void* noise, int64_t n, double lr, uint64_t seed,
+                 uint64_t offset, zs_stream_t stream);
+/* PSGLD._update (SGLD.py:67-82): aux = decay*aux + (1-decay) g^2; G = 1/(eps+sqrt(aux));
+ * w += 0.5*lr*G*g + N(0, lr*G).  noise_unit != NULL injects UNIT normals.          */
+int zs_psgld_step(int dtype, void* w, void* aux, const void* g, const void* noise_unit, int64_t n, double lr,
+                  double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream);
+/* SGHMC._update (SGHMC.py:25-56).
+ *   zs_sghmc_pre : optional velocity resample v ~ N(0, lr) (resample != 0; v_noise
+ *                  injects it) and, for second_order, the half step w += 0.5 v.
+ *   zs_sghmc_post: first order  v = (1-alpha) v + lr g + n ; w += v
+ *                  second order v = d (d v + lr g + n), d = exp(-alpha/2) ; w += 0.5 v
+ *                  n ~ N(0, 2(alpha-beta) lr) (noise injects it).                   */
+int zs_sghmc_pre(int dtype, void* w, void* v, const void* v_noise, int64_t n, double lr, int resample,
+                 int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_sghmc_post(int dtype, void* w, void* v, const void* g, const void* noise, int64_t n, double lr, double alpha,
+                  double beta, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
+
+/* ---- host-buffer convenience call (end-to-end measurement) ----
+ * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers:
+ * copies probs/x/logp_other/logq to the device, runs zs_iw_bernoulli_fused (or the
+ * two-pass kernels), copies cost/dprobs/dlogp/dlogq back and synchronises.
+ * `ws` is a caller-owned device workspace of zs_iw_step_host_workspace() bytes.     */
+int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X);
+int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
+                    const float* probs_host, const float* x_host, const float* logp_other_host,
+                    const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
+                    int64_t ws_bytes, zs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZS_B200_H */

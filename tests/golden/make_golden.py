@@ -1,0 +1,382 @@
+"""Generate tests/golden/*.npz by running the REAL reference (thuwzy/ZhuSuan-PyTorch).
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Each fixture holds seeded inputs plus the reference's outputs and autograd gradients, in float32
+and float64.  Noise is injected by patching torch.normal / torch.bernoulli, so the fixtures pin
+the oracle (tests/test_oracle_golden.py) and the CUDA kernels (tests/test_gpu_parity.py) on
+identical inputs.  Nothing here is imported by the product.
+"""
+import math
+import os
+import sys
+from unittest import mock
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ZS_REFERENCE", "/root/reference")
+if REF not in sys.path:
+    sys.path.insert(0, REF)
+
+import zhusuan  # noqa: E402  (the reference)
+from zhusuan.distributions import Bernoulli, Normal  # noqa: E402
+from zhusuan.framework import BayesianNet  # noqa: E402
+from zhusuan.variational import ELBO, ImportanceWeightedObjective  # noqa: E402
+from zhusuan import mcmc  # noqa: E402
+
+assert os.path.realpath(zhusuan.__file__).startswith(os.path.realpath(REF)), zhusuan.__file__
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+DT = {"f32": torch.float32, "f64": torch.float64}
+
+
+def t(a, dtype, grad=False):
+    x = torch.tensor(np.asarray(a), dtype=dtype)
+    x.requires_grad_(grad)
+    return x
+
+
+def npy(x):
+    return None if x is None else x.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    arrs = {k: v for k, v in arrs.items() if v is not None}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrs.items()})
+
+
+# --------------------------------------------------------------------------- distributions
+def gen_normal():
+    rng = np.random.RandomState(11)
+    cases = {
+        # q(z|x): params [B,Z] broadcast over K particles, event sum over Z (iwae.py:102-120)
+        "kbcast": dict(x=(5, 6, 8), mean=(6, 8), std=(6, 8), event=1),
+        # prior on observed z with same-shaped params
+        "full": dict(x=(4, 3, 8), mean=(4, 3, 8), std=(4, 3, 8), event=1),
+        # BNN y-likelihood: mean [K,B], scalar std, y [B]  (bnn_vi.py:55-60)
+        "ylik": dict(x=(7,), mean=(5, 7), std=(1,), event=0),
+        # BNN weights: group_ndims=2 over [n_out, n_in+1]  (bnn_vi.py:32-38)
+        "group2": dict(x=(6, 5, 9), mean=(5, 9), std=(5, 9), event=2),
+    }
+    out = {}
+    for cname, c in cases.items():
+        x64 = rng.standard_normal(c["x"])
+        mean64 = 0.5 * rng.standard_normal(c["mean"])
+        std64 = np.exp(0.3 * rng.standard_normal(c["std"]))
+        for dn, dt in DT.items():
+            x, mean, std = t(x64, dt, True), t(mean64, dt, True), t(std64, dt, True)
+            dist = Normal(mean=mean, std=std, group_ndims=c["event"] if cname == "group2" else 0)
+            lp = dist.log_prob(x)
+            if cname in ("kbcast", "full"):
+                lp = lp.sum(-1)
+            g64 = np.random.RandomState(3).standard_normal(tuple(lp.shape))
+            g = t(g64, dt)
+            dx, dmean, dstd = torch.autograd.grad(lp, [x, mean, std], grad_outputs=g)
+            p = "%s_%s_" % (cname, dn)
+            out.update({p + "x": npy(x), p + "mean": npy(mean), p + "std": npy(std), p + "g": npy(g),
+                        p + "out": npy(lp), p + "dx": npy(dx), p + "dmean": npy(dmean), p + "dstd": npy(dstd)})
+    save("normal_logprob", **out)
+
+
+def gen_bernoulli():
+    rng = np.random.RandomState(12)
+    cases = {
+        # likelihood: probs [K,B,X], observed x [B,X] broadcast, event sum over X (iwae.py:73-81)
+        "lik": dict(x=(6, 16), probs=(4, 6, 16), binary=True),
+        # real-valued observations (load_mnist_realval)
+        "lik_real": dict(x=(6, 16), probs=(4, 6, 16), binary=False),
+        # Bernoulli latents: probs [B,Z] broadcast over K, samples [K,B,Z]
+        "latent": dict(x=(5, 6, 8), probs=(6, 8), binary=True),
+    }
+    out = {}
+    for cname, c in cases.items():
+        probs64 = 1.0 / (1.0 + np.exp(-2.0 * rng.standard_normal(c["probs"])))
+        # exercise the +1e-8 guards: exact 0 / 1 and tiny probabilities
+        flat = probs64.reshape(-1)
+        flat[0], flat[1], flat[2], flat[3] = 0.0, 1.0, 1e-9, 1.0 - 1e-7
+        x64 = (rng.uniform(size=c["x"]) < 0.5).astype(np.float64) if c["binary"] else rng.uniform(size=c["x"])
+        if c["binary"]:
+            # keep log(0 + 1e-8) finite-gradient corner but make x agree there so values stay finite
+            pass
+        for dn, dt in DT.items():
+            probs, x = t(probs64, dt, True), t(x64, dt)
+            dist = Bernoulli(probs=probs)
+            lp = dist.log_prob(x).sum(-1)
+            g = t(np.random.RandomState(4).standard_normal(tuple(lp.shape)), dt)
+            (dprobs,) = torch.autograd.grad(lp, [probs], grad_outputs=g)
+            p = "%s_%s_" % (cname, dn)
+            out.update({p + "x": npy(x), p + "probs": npy(probs), p + "g": npy(g), p + "out": npy(lp),
+                        p + "dprobs": npy(dprobs)})
+    save("bernoulli_logpmf", **out)
+
+
+# --------------------------------------------------------------------------- objectives
+class _Dummy(torch.nn.Module):
+    pass
+
+
+def gen_objectives():
+    rng = np.random.RandomState(13)
+    out = {}
+    shapes = {"kb": (10, 7), "k50": (50, 33), "k1d": (12,), "dominant": (6, 4)}
+    for sname, shp in shapes.items():
+        logp64 = -90.0 + 6.0 * rng.standard_normal(shp)
+        logq64 = 25.0 + 3.0 * rng.standard_normal(shp)
+        if sname == "dominant":
+            logp64[2] += 60.0  # one particle carries ~all the weight: LOO arg-max branch
+        for dn, dt in DT.items():
+            for est in ("sgvb", "vimco"):
+                logp, logq = t(logp64, dt, True), t(logq64, dt, True)
+                obj = ImportanceWeightedObjective(_Dummy(), _Dummy(), axis=0, estimator=est)
+                loss = getattr(obj, est)(logp, logq, True)
+                dlp, dlq = torch.autograd.grad(loss, [logp, logq])
+                p = "%s_%s_%s_" % (sname, est, dn)
+                out.update({p + "logp": npy(logp), p + "logq": npy(logq), p + "loss": npy(loss),
+                            p + "dlogp": npy(dlp), p + "dlogq": npy(dlq)})
+                if est == "sgvb":
+                    per = obj.sgvb(logp, logq, False)
+                    out[p + "cost"] = npy(per)
+            # ELBO.sgvb (elbo.py:134-161) and log_mean_exp (zhusuan/utils.py:6-21)
+            logp, logq = t(logp64, dt, True), t(logq64, dt, True)
+            elbo = ELBO(_Dummy(), _Dummy(), estimator="sgvb")
+            loss = elbo.sgvb(logp, logq, True)
+            dlp, dlq = torch.autograd.grad(loss, [logp, logq])
+            p = "%s_elbo_%s_" % (sname, dn)
+            out.update({p + "loss": npy(loss), p + "dlogp": npy(dlp), p + "dlogq": npy(dlq)})
+            lw = t(logp64 - logq64, dt, True)
+            lme = zhusuan.log_mean_exp(lw, 0)
+            (dlw,) = torch.autograd.grad(lme.sum(), [lw])
+            p = "%s_lme_%s_" % (sname, dn)
+            out.update({p + "x": npy(lw), p + "out": npy(lme), p + "dx": npy(dlw)})
+    save("objectives", **out)
+
+
+def gen_reinforce():
+    """ELBO.reinforce (elbo.py:163-238): three consecutive calls so the moving-mean state is pinned."""
+    rng = np.random.RandomState(14)
+    out = {}
+    for dn, dt in DT.items():
+        elbo = ELBO(_Dummy(), _Dummy(), estimator="reinforce")
+        for step in range(3):
+            logp64 = -90.0 + 6.0 * rng.standard_normal((10, 7))
+            logq64 = 25.0 + 3.0 * rng.standard_normal((10, 7))
+            logp, logq = t(logp64, torch.float32, True), t(logq64, torch.float32, True)
+            loss = elbo.reinforce(logp, logq, True)
+            dlp, dlq = torch.autograd.grad(loss, [logp, logq])
+            p = "%s_s%d_" % (dn, step)
+            out.update({p + "logp": npy(logp), p + "logq": npy(logq), p + "loss": npy(loss), p + "dlogp": npy(dlp),
+                        p + "dlogq": npy(dlq), p + "moving_mean": npy(elbo.moving_mean.clone()),
+                        p + "local_step": npy(elbo.local_step.clone())})
+        break  # buffers are float32 in the reference regardless of input dtype
+    save("reinforce", **out)
+
+
+# --------------------------------------------------------------------------- end-to-end IW path
+class _Gen(BayesianNet):
+    """Generator with the decoder output given as a leaf (the path boundary of SURVEY.md §8d)."""
+
+    def __init__(self, probs, K, latent):
+        super().__init__()
+        self.probs, self.K, self.latent = probs, K, latent
+
+    def forward(self, observed):
+        self.observe(observed)
+        B, Z = self.observed["z"].shape[1:]
+        if self.latent == "normal":
+            self.normal("z", mean=torch.zeros([B, Z], dtype=self.probs.dtype), std=torch.ones([B, Z], dtype=self.probs.dtype),
+                        is_reparameterized=False, n_samples=self.K, reduce_sum_dims=[2])
+        else:
+            self.bernoulli("z", probs=0.5 * torch.ones([B, Z], dtype=self.probs.dtype), n_samples=self.K,
+                           reduce_sum_dims=[2])
+        self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
+        return self
+
+
+class _Var(BayesianNet):
+    def __init__(self, a, b, K, latent, reparam):
+        super().__init__()
+        self.a, self.b, self.K, self.latent, self.reparam = a, b, K, latent, reparam
+
+    def forward(self, observed):
+        self.observe(observed)
+        if self.latent == "normal":
+            self.sn(Normal(mean=self.a, logstd=self.b, is_reparameterized=self.reparam), name="z", n_samples=self.K,
+                    reduce_sum_dims=[2])
+        else:
+            self.sn(Bernoulli(probs=self.a), name="z", n_samples=self.K, reduce_sum_dims=[2])
+        return self
+
+
+def gen_iw_path():
+    rng = np.random.RandomState(15)
+    K, B, Z, X = 6, 5, 4, 12
+    out = {"K": np.int64(K), "B": np.int64(B), "Z": np.int64(Z), "X": np.int64(X)}
+    mean64 = 0.5 * rng.standard_normal((B, Z))
+    logstd64 = 0.3 * rng.standard_normal((B, Z))
+    pq64 = 1.0 / (1.0 + np.exp(-rng.standard_normal((B, Z))))
+    probs64 = 1.0 / (1.0 + np.exp(-2.0 * rng.standard_normal((K, B, X))))
+    x64 = (rng.uniform(size=(B, X)) < 0.5).astype(np.float64)
+    eps64 = rng.standard_normal((K, B, Z))
+    u64 = rng.uniform(size=(K, B, Z))
+    out.update(mean=mean64, logstd=logstd64, probs_q=pq64, probs=probs64, x=x64, eps=eps64, u=u64)
+
+    for dn, dt in DT.items():
+        for est, latent in (("sgvb", "normal"), ("vimco", "normal"), ("vimco", "bernoulli")):
+            probs = t(probs64, dt, True)
+            if latent == "normal":
+                a, b = t(mean64, dt, True), t(logstd64, dt, True)
+            else:
+                a, b = t(pq64, dt, True), None
+            eps, u = t(eps64, dt), t(u64, dt)
+
+            def fake_normal(*args, **kw):
+                if "size" in kw:  # reparameterised draw: torch.normal(0., 1., size=shape)  (normal.py:104)
+                    return eps.clone()
+                m, s = args[0], args[1]  # non-reparameterised: torch.normal(mean, std)  (normal.py:102)
+                return (m + s * eps).detach()
+
+            def fake_bernoulli(p, *args, **kw):
+                return (u < p).to(p.dtype)
+
+            gen = _Gen(probs, K, latent)
+            var = _Var(a, b, K, latent, reparam=(est == "sgvb"))
+            obj = ImportanceWeightedObjective(gen, var, axis=0, estimator=est)
+            with mock.patch("torch.normal", fake_normal), mock.patch("torch.bernoulli", fake_bernoulli):
+                loss = obj({"x": t(x64, dt)})
+            leaves = [probs, a] + ([b] if b is not None else [])
+            grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+            p = "%s_%s_%s_" % (est, latent, dn)
+            out[p + "loss"] = npy(loss)
+            out[p + "dprobs"] = npy(grads[0])
+            out[p + "da"] = npy(grads[1])
+            if b is not None:
+                out[p + "db"] = npy(grads[2])
+            out[p + "z"] = npy(var.nodes["z"].dist.sample_cache)
+            out[p + "logq"] = npy(var.nodes["z"].log_prob())
+            out[p + "logpz"] = npy(gen.nodes["z"].log_prob())
+            out[p + "logpx"] = npy(gen.nodes["x"].log_prob())
+    save("iw_path", **out)
+
+
+# --------------------------------------------------------------------------- VAE ELBO (cfg 1 shapes, small)
+def gen_elbo_path():
+    rng = np.random.RandomState(16)
+    B, Z, X = 6, 4, 12
+    mean64 = 0.5 * rng.standard_normal((B, Z))
+    std64 = np.exp(0.3 * rng.standard_normal((B, Z)))
+    probs64 = 1.0 / (1.0 + np.exp(-2.0 * rng.standard_normal((B, X))))
+    x64 = (rng.uniform(size=(B, X)) < 0.5).astype(np.float64)
+    eps64 = rng.standard_normal((B, Z))
+    out = dict(mean=mean64, std=std64, probs=probs64, x=x64, eps=eps64)
+
+    class G(BayesianNet):
+        def __init__(self, probs):
+            super().__init__()
+            self.probs = probs
+
+        def forward(self, observed):
+            self.observe(observed)
+            dt = self.probs.dtype
+            self.normal("z", mean=torch.zeros([B, Z], dtype=dt), std=torch.ones([B, Z], dtype=dt),
+                        reduce_mean_dims=[0], reduce_sum_dims=[1])
+            self.bernoulli("x", probs=self.probs, reduce_mean_dims=[0], reduce_sum_dims=[1])
+            return self
+
+    class V(BayesianNet):
+        def __init__(self, m, s):
+            super().__init__()
+            self.m, self.s = m, s
+
+        def forward(self, observed):
+            self.observe(observed)
+            self.normal("z", mean=self.m, std=self.s, reduce_mean_dims=[0], reduce_sum_dims=[1])
+            return self
+
+    for dn, dt in DT.items():
+        m, s, probs = t(mean64, dt, True), t(std64, dt, True), t(probs64, dt, True)
+        eps = t(eps64, dt)
+        with mock.patch("torch.normal", lambda *a, **k: eps.clone()):
+            loss = ELBO(G(probs), V(m, s))({"x": t(x64, dt)})
+        dm, ds, dp = torch.autograd.grad(loss, [m, s, probs])
+        out.update({dn + "_loss": npy(loss), dn + "_dmean": npy(dm), dn + "_dstd": npy(ds), dn + "_dprobs": npy(dp)})
+    save("elbo_path", **out)
+
+
+# --------------------------------------------------------------------------- SG-MCMC
+class _Well(BayesianNet):
+    """Quadratic-quartic log joint over one latent 'x' (test/mcmc/test_mcmc.py:24-37 without its noise)."""
+
+    def __init__(self, x0):
+        super().__init__()
+        self.nodes["x"] = type("N", (), {"tensor": x0})()
+
+    def forward(self, observed):
+        self.observe(observed)
+        return self
+
+    def _log_joint(self, use_cache=False):
+        x = self.observed["x"]
+        return (2 * torch.pow(x, 2) - torch.pow(x, 4)).sum()
+
+
+def gen_sgmcmc():
+    rng = np.random.RandomState(17)
+    n, steps = 64, 4
+    out = {"n": np.int64(n), "steps": np.int64(steps)}
+    x0_64 = 0.7 * rng.standard_normal(n)
+    noise64 = rng.standard_normal((steps + 1, 2, n))  # per step: [velocity-resample, gaussian] unit draws
+    out.update(x0=x0_64, unit_noise=noise64)
+    samplers = {
+        "sgld": lambda: mcmc.SGLD(learning_rate=0.01),
+        "psgld": lambda: mcmc.PSGLD(learning_rate=0.01),
+        "sghmc1": lambda: mcmc.SGHMC(learning_rate=0.01, n_iter_resample_v=2, friction=0.3, variance_estimate=0.02,
+                                     second_order=False),
+        "sghmc2": lambda: mcmc.SGHMC(learning_rate=0.01, n_iter_resample_v=2, friction=0.3, variance_estimate=0.02,
+                                     second_order=True),
+    }
+    for sname, mk in samplers.items():
+        for dn, dt in (("f32", torch.float32),):
+            sampler = mk()
+            x0 = t(x0_64, dt, True)
+            model = _Well(x0)
+            calls = []
+            state = {"step": 0, "j": 0}
+
+            def fake_normal(*args, **kw):
+                # every torch.normal call of one update consumes the next unit draw of that step
+                mean = kw.get("mean", args[0] if len(args) > 0 else 0.0)
+                std = kw.get("std", args[1] if len(args) > 1 else 1.0)
+                unit = torch.tensor(noise64[state["step"], state["j"] % 2], dtype=torch.float32)
+                state["j"] += 1
+                if torch.is_tensor(std):
+                    r = mean + std * unit.to(std.dtype)
+                else:
+                    r = torch.tensor(mean, dtype=torch.float32) + torch.tensor(std, dtype=torch.float32) * unit
+                calls.append((state["step"], float(std) if not torch.is_tensor(std) else -1.0))
+                return r
+
+            traj = []
+            with mock.patch("torch.normal", fake_normal):
+                sampler.sample(model, {}, True)  # resample=True: no update (SGMCMC.py:39-52)
+                for s in range(steps):
+                    state["step"], state["j"] = s, 0
+                    w = sampler.sample(model, {}, False)["x"]
+                    traj.append(npy(w).copy())
+            out[sname + "_" + dn + "_traj"] = np.stack(traj)
+            out[sname + "_" + dn + "_calls"] = np.array(calls, dtype=np.float64)
+    save("sgmcmc", **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_normal()
+    gen_bernoulli()
+    gen_objectives()
+    gen_reinforce()
+    gen_iw_path()
+    gen_elbo_path()
+    gen_sgmcmc()

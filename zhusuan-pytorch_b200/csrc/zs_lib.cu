@@ -1,0 +1,69 @@
+// Library plumbing: version, error strings, device info.
+#include <stdio.h>
+#include <string.h>
+
+#include "zs_common.cuh"
+
+namespace zs {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* where, cudaError_t e) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+void set_last_error_msg(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return 148;  // B200; only used to size grids
+    }
+    cached = n;
+    return n;
+}
+
+}  // namespace zs
+
+extern "C" {
+
+int zs_abi_version(void) { return ZS_ABI_VERSION; }
+
+const char* zs_strerror(int code) {
+    switch (code) {
+        case ZS_OK: return "ok";
+        case ZS_ERR_ARG: return "invalid argument";
+        case ZS_ERR_DTYPE: return "unsupported dtype (float32 / float64 only)";
+        case ZS_ERR_CUDA: return "CUDA error";
+        case ZS_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case ZS_ERR_WORKSPACE: return "workspace too small";
+        case ZS_ERR_UNSUPPORTED: return "shape not supported by this entry point";
+        case ZS_ERR_ALIGN: return "pointer alignment";
+        default: return "unknown error";
+    }
+}
+
+const char* zs_last_error(void) { return zs::g_last_error; }
+
+int zs_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        zs::set_last_error("cudaGetDevice", e);
+        (void)cudaGetLastError();
+        return ZS_ERR_NO_DEVICE;
+    }
+    int n = 0, ma = 0, mi = 0;
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm_count) *sm_count = n;
+    if (cc_major) *cc_major = ma;
+    if (cc_minor) *cc_minor = mi;
+    return ZS_OK;
+}
+
+}  // extern "C"

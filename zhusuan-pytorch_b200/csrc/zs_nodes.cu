@@ -1,0 +1,679 @@
+// Stochastic-node kernels: sample and log-prob (forward / backward) for Normal and Bernoulli
+// over the [K, M, E] particle-row view described in include/zs_b200.h.
+//
+// Replaces (reference file:line):
+//   Normal._sample        zhusuan/distributions/normal.py:89-107
+//   Normal._log_prob      zhusuan/distributions/normal.py:109-126
+//   Bernoulli._sample     zhusuan/distributions/bernoulli.py:72-82
+//   Bernoulli._log_prob   zhusuan/distributions/bernoulli.py:84-95
+//   Distribution.log_prob zhusuan/distributions/base.py:161-178      (group_ndims sum)
+//   StochasticTensor.log_prob  zhusuan/framework/stochastic_tensor.py:160-181 (trailing sums)
+// The `.repeat([K,1,...])` of the parameters is replaced by the ZS_KBCAST operand mode, the
+// CPU-side RNG + H2D copy by in-kernel Philox, and the ~8 (fwd) / ~12 (bwd) elementwise aten
+// kernels plus the event-axis reduction by one pass each.
+#include "zs_common.cuh"
+#include "zs_philox.cuh"
+
+namespace zs {
+
+// ---------------------------------------------------------------------------
+// operand addressing
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Operand {
+    const T* p;
+    int mode;
+    // base pointer of row r = k*M + m (E elements); SCALAR rows are handled by the caller
+    __device__ __forceinline__ const T* row(int64_t r, int64_t m, int64_t E) const {
+        return mode == ZS_FULL ? p + r * E : p + m * E;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// per-element math
+// ---------------------------------------------------------------------------
+template <typename T>
+struct NormalOp {
+    // normal.py:122: a 0-d float64 tensor, rounded to the operand dtype when combined
+    static __device__ __forceinline__ T c() { return (T)(-0.9189385332046727); }
+    static __device__ __forceinline__ T term(T x, T mean, T std) {
+        T logstd = Real<T>::log(std);
+        T prec = Real<T>::exp(T(-2) * logstd);
+        T d = x - mean;
+        return (c() - logstd) - (T(0.5) * prec) * (d * d);
+    }
+    static __device__ __forceinline__ T finish(T acc) { return acc; }
+    // autograd of the expression above, same association order
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(T g, T x, T mean, T std, T& dx, T& dmean, T& dstd) {
+        T logstd = Real<T>::log(std);
+        T prec = Real<T>::exp(T(-2) * logstd);
+        T d = x - mean;
+        T dd = -(g * (T(0.5) * prec)) * (T(2) * d);
+        dx = dd;
+        dmean = -dd;
+        T dprec = -(g * (d * d)) * T(0.5);
+        T dlogstd = -g + (dprec * prec) * T(-2);
+        dstd = dlogstd / std;
+    }
+};
+
+template <typename T>
+struct BernoulliOp;
+
+template <>
+struct BernoulliOp<float> {
+    // accumulate in log2 units on the SFU, scale by ln2 once per row
+    static __device__ __forceinline__ float term(float x, float p, float) {
+        float a = p + 1e-8f;
+        float b = (1.0f - p) + 1e-8f;
+        return x * fast_log2(a) + (1.0f - x) * fast_log2(b);
+    }
+    static __device__ __forceinline__ float finish(float acc) { return acc * 0.6931471805599453f; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(float g, float x, float p, float, float& dx, float& dp, float& unused) {
+        float a = p + 1e-8f;
+        float b = (1.0f - p) + 1e-8f;
+        dp = __fdividef(g * x, a) - __fdividef(g * (1.0f - x), b);
+        if (NEED_X) dx = g * ((fast_log2(a) - fast_log2(b)) * 0.6931471805599453f);
+        unused = 0.f;
+    }
+};
+template <>
+struct BernoulliOp<double> {
+    static __device__ __forceinline__ double term(double x, double p, double) {
+        return x * ::log(p + 1e-8) + (1.0 - x) * ::log((1.0 - p) + 1e-8);
+    }
+    static __device__ __forceinline__ double finish(double acc) { return acc; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(double g, double x, double p, double, double& dx, double& dp,
+                                                double& unused) {
+        double a = p + 1e-8, b = (1.0 - p) + 1e-8;
+        dp = (g * x) / a - (g * (1.0 - x)) / b;
+        if (NEED_X) dx = g * (::log(a) - ::log(b));
+        unused = 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// forward: out[r] = finish( sum_e term(x, a, b) ),  LPR lanes cooperate on a row
+// ---------------------------------------------------------------------------
+template <typename T, typename Op, int LPR, bool VEC>
+__global__ void __launch_bounds__(256) k_rows_fwd(T* __restrict__ out, Operand<T> x, Operand<T> a, Operand<T> b,
+                                                  int64_t K, int64_t M, int64_t E) {
+    constexpr int VN = Pack<T>::N;
+    const int lane = threadIdx.x % LPR;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ngrp = (int64_t)gridDim.x * blockDim.x / LPR;
+    const int64_t R = K * M;
+    const T xs = x.mode == ZS_SCALAR ? x.p[0] : T(0);
+    const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
+    const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
+    const bool hasb = b.p != nullptr;
+
+    for (int64_t base = 0; base < R; base += ngrp) {
+        const int64_t r = base + grp;
+        const bool valid = r < R;
+        T acc = T(0);
+        if (valid) {
+            const int64_t m = r % M;
+            const T* xr = x.row(r, m, E);
+            const T* ar = a.row(r, m, E);
+            const T* br = hasb ? b.row(r, m, E) : nullptr;
+            if (VEC) {
+                const int64_t nv = E / VN;
+#pragma unroll 4
+                for (int64_t v = lane; v < nv; v += LPR) {
+                    Pack<T> px, pa, pb;
+                    if (x.mode == ZS_SCALAR) {
+#pragma unroll
+                        for (int j = 0; j < VN; ++j) px.v[j] = xs;
+                    } else if (x.mode == ZS_FULL) {
+                        px = ld_pack_stream(xr + v * VN);
+                    } else {
+                        px = ld_pack(xr + v * VN);
+                    }
+                    if (a.mode == ZS_SCALAR) {
+#pragma unroll
+                        for (int j = 0; j < VN; ++j) pa.v[j] = as;
+                    } else if (a.mode == ZS_FULL) {
+                        pa = ld_pack_stream(ar + v * VN);
+                    } else {
+                        pa = ld_pack(ar + v * VN);
+                    }
+                    if (!hasb || b.mode == ZS_SCALAR) {
+#pragma unroll
+                        for (int j = 0; j < VN; ++j) pb.v[j] = bs;
+                    } else if (b.mode == ZS_FULL) {
+                        pb = ld_pack_stream(br + v * VN);
+                    } else {
+                        pb = ld_pack(br + v * VN);
+                    }
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+                }
+            } else {
+                for (int64_t e = lane; e < E; e += LPR) {
+                    T xv = x.mode == ZS_SCALAR ? xs : xr[e];
+                    T av = a.mode == ZS_SCALAR ? as : ar[e];
+                    T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
+                    acc += Op::term(xv, av, bv);
+                }
+            }
+        }
+        acc = group_sum<LPR>(acc);
+        if (valid && lane == 0) out[r] = Op::finish(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward, no reduction over K: every requested gradient has a FULL operand
+// ---------------------------------------------------------------------------
+template <typename T, typename Op, int LPR, bool VEC>
+__global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restrict__ da, T* __restrict__ db,
+                                                  const T* __restrict__ g, Operand<T> x, Operand<T> a, Operand<T> b,
+                                                  int64_t K, int64_t M, int64_t E) {
+    constexpr int VN = Pack<T>::N;
+    const int lane = threadIdx.x % LPR;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ngrp = (int64_t)gridDim.x * blockDim.x / LPR;
+    const int64_t R = K * M;
+    const T xs = x.mode == ZS_SCALAR ? x.p[0] : T(0);
+    const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
+    const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
+    const bool hasb = b.p != nullptr;
+
+    for (int64_t r = grp; r < R; r += ngrp) {
+        const int64_t m = r % M;
+        const T gv = g[r];
+        const T* xr = x.row(r, m, E);
+        const T* ar = a.row(r, m, E);
+        const T* br = hasb ? b.row(r, m, E) : nullptr;
+        T* dxr = dx ? dx + r * E : nullptr;
+        T* dar = da ? da + r * E : nullptr;
+        T* dbr = db ? db + r * E : nullptr;
+        if (VEC) {
+            const int64_t nv = E / VN;
+#pragma unroll 2
+            for (int64_t v = lane; v < nv; v += LPR) {
+                Pack<T> px, pa, pb, ox, oa, ob;
+                if (x.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) px.v[j] = xs;
+                } else if (x.mode == ZS_FULL) {
+                    px = ld_pack_stream(xr + v * VN);
+                } else {
+                    px = ld_pack(xr + v * VN);
+                }
+                if (a.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) pa.v[j] = as;
+                } else if (a.mode == ZS_FULL) {
+                    pa = ld_pack_stream(ar + v * VN);
+                } else {
+                    pa = ld_pack(ar + v * VN);
+                }
+                if (!hasb || b.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) pb.v[j] = bs;
+                } else if (b.mode == ZS_FULL) {
+                    pb = ld_pack_stream(br + v * VN);
+                } else {
+                    pb = ld_pack(br + v * VN);
+                }
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    if (dx)
+                        Op::template grad<true>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                    else
+                        Op::template grad<false>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                }
+                if (dxr) st_pack_stream(dxr + v * VN, ox);
+                if (dar) st_pack_stream(dar + v * VN, oa);
+                if (dbr) st_pack_stream(dbr + v * VN, ob);
+            }
+        } else {
+            for (int64_t e = lane; e < E; e += LPR) {
+                T xv = x.mode == ZS_SCALAR ? xs : xr[e];
+                T av = a.mode == ZS_SCALAR ? as : ar[e];
+                T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
+                T ox, oa, ob;
+                if (dx)
+                    Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
+                else
+                    Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+                if (dxr) dxr[e] = ox;
+                if (dar) dar[e] = oa;
+                if (dbr) dbr[e] = ob;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward with a sum over particles for KBCAST operands.
+// block = (32 flat (m,e) elements) x (8 particle slices); fixed-order cross-slice sum.
+// ---------------------------------------------------------------------------
+constexpr int KR_X = 32, KR_Y = 8;
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(KR_X* KR_Y) k_kreduce_bwd(T* __restrict__ dx, T* __restrict__ da, T* __restrict__ db,
+                                                             const T* __restrict__ g, Operand<T> x, Operand<T> a,
+                                                             Operand<T> b, int64_t K, int64_t M, int64_t E) {
+    const int64_t ME = M * E;
+    const int64_t n = (int64_t)blockIdx.x * KR_X + threadIdx.x;
+    const bool valid = n < ME;
+    const int64_t m = valid ? n / E : 0;
+    const bool hasb = b.p != nullptr;
+    T sx = T(0), sa = T(0), sb = T(0);
+    if (valid) {
+        const T xs = x.mode == ZS_SCALAR ? x.p[0] : T(0);
+        const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
+        const T bs = (hasb && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
+#pragma unroll 4
+        for (int64_t k = threadIdx.y; k < K; k += KR_Y) {
+            const int64_t f = k * ME + n;
+            T gv = g[k * M + m];
+            T xv = x.mode == ZS_FULL ? x.p[f] : (x.mode == ZS_KBCAST ? x.p[n] : xs);
+            T av = a.mode == ZS_FULL ? a.p[f] : (a.mode == ZS_KBCAST ? a.p[n] : as);
+            T bv = !hasb ? T(0) : (b.mode == ZS_FULL ? b.p[f] : (b.mode == ZS_KBCAST ? b.p[n] : bs));
+            T ox, oa, ob;
+            if (dx)
+                Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
+            else
+                Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+            if (dx) {
+                if (x.mode == ZS_FULL) dx[f] = ox; else sx += ox;
+            }
+            if (da) {
+                if (a.mode == ZS_FULL) da[f] = oa; else sa += oa;
+            }
+            if (db) {
+                if (b.mode == ZS_FULL) db[f] = ob; else sb += ob;
+            }
+        }
+    }
+    __shared__ T red[3][KR_Y][KR_X + 1];
+    red[0][threadIdx.y][threadIdx.x] = sx;
+    red[1][threadIdx.y][threadIdx.x] = sa;
+    red[2][threadIdx.y][threadIdx.x] = sb;
+    __syncthreads();
+    if (threadIdx.y == 0 && valid) {
+        T tx = T(0), ta = T(0), tb = T(0);
+#pragma unroll
+        for (int s = 0; s < KR_Y; ++s) {
+            tx += red[0][s][threadIdx.x];
+            ta += red[1][s][threadIdx.x];
+            tb += red[2][s][threadIdx.x];
+        }
+        if (dx && x.mode == ZS_KBCAST) dx[n] = tx;
+        if (da && a.mode == ZS_KBCAST) da[n] = ta;
+        if (db && hasb && b.mode == ZS_KBCAST) db[n] = tb;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sampling
+// ---------------------------------------------------------------------------
+// Normal: z = mean + std*eps over [K,N]; 4 consecutive elements per thread (one Philox call).
+template <typename T, bool ALIGNED4>
+__global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const T* __restrict__ mean, int mm,
+                                                       const T* __restrict__ std, int sm, const T* __restrict__ eps_in,
+                                                       T* __restrict__ eps_out, int64_t K, int64_t N, uint64_t seed,
+                                                       uint64_t offset) {
+    const int64_t total = K * N;
+    const int64_t nq = (total + 3) / 4;
+    const T ms = mm == ZS_SCALAR ? mean[0] : T(0);
+    const T ss = sm == ZS_SCALAR ? std[0] : T(0);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float e4[4];
+        if (!eps_in) philox_normal4((uint64_t)q, offset, seed, e4);
+        const int64_t i0 = q * 4;
+        // ALIGNED4: N % 4 == 0, so the 4 elements share a particle and are contiguous in [N]
+        int64_t n0 = ALIGNED4 ? (i0 % N) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j;
+            if (i < total) {
+                const int64_t n = ALIGNED4 ? n0 + j : i % N;
+                T e = eps_in ? eps_in[i] : (T)e4[j];
+                T mv = mm == ZS_FULL ? mean[i] : (mm == ZS_KBCAST ? mean[n] : ms);
+                T sv = sm == ZS_FULL ? std[i] : (sm == ZS_KBCAST ? std[n] : ss);
+                z[i] = mv + sv * e;
+                if (eps_out) eps_out[i] = e;
+            }
+        }
+    }
+}
+
+// pathwise backward of the sample: dmean = sum_k dz ; dstd = sum_k dz*eps (KBCAST), elementwise (FULL)
+template <typename T>
+__global__ void __launch_bounds__(KR_X* KR_Y) k_normal_sample_bwd(T* __restrict__ dmean, int mm, T* __restrict__ dstd,
+                                                                   int sm, const T* __restrict__ dz,
+                                                                   const T* __restrict__ eps, int64_t K, int64_t N,
+                                                                   uint64_t seed, uint64_t offset) {
+    const int64_t n = (int64_t)blockIdx.x * KR_X + threadIdx.x;
+    const bool valid = n < N;
+    T sm_acc = T(0), ss_acc = T(0);
+    if (valid) {
+#pragma unroll 4
+        for (int64_t k = threadIdx.y; k < K; k += KR_Y) {
+            const int64_t i = k * N + n;
+            T d = dz[i];
+            T e;
+            if (eps) {
+                e = eps[i];
+            } else {
+                float e4[4];
+                philox_normal4((uint64_t)(i >> 2), offset, seed, e4);
+                e = (T)e4[i & 3];
+            }
+            if (dmean) {
+                if (mm == ZS_FULL) dmean[i] = d; else sm_acc += d;
+            }
+            if (dstd) {
+                if (sm == ZS_FULL) dstd[i] = d * e; else ss_acc += d * e;
+            }
+        }
+    }
+    __shared__ T red[2][KR_Y][KR_X + 1];
+    red[0][threadIdx.y][threadIdx.x] = sm_acc;
+    red[1][threadIdx.y][threadIdx.x] = ss_acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && valid) {
+        T tm = T(0), ts = T(0);
+#pragma unroll
+        for (int s = 0; s < KR_Y; ++s) {
+            tm += red[0][s][threadIdx.x];
+            ts += red[1][s][threadIdx.x];
+        }
+        if (dmean && mm == ZS_KBCAST) dmean[n] = tm;
+        if (dstd && sm == ZS_KBCAST) dstd[n] = ts;
+    }
+}
+
+template <typename T, bool ALIGNED4>
+__global__ void __launch_bounds__(256) k_bernoulli_sample(T* __restrict__ out, const T* __restrict__ probs, int pm,
+                                                          const T* __restrict__ u_in, int64_t K, int64_t N,
+                                                          uint64_t seed, uint64_t offset) {
+    const int64_t total = K * N;
+    const int64_t nq = (total + 3) / 4;
+    const T ps = pm == ZS_SCALAR ? probs[0] : T(0);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float u4[4];
+        if (!u_in) philox_uniform4((uint64_t)q, offset, seed, u4);
+        const int64_t i0 = q * 4;
+        int64_t n0 = ALIGNED4 ? (i0 % N) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j;
+            if (i < total) {
+                const int64_t n = ALIGNED4 ? n0 + j : i % N;
+                T u = u_in ? u_in[i] : (T)u4[j];
+                T pv = pm == ZS_FULL ? probs[i] : (pm == ZS_KBCAST ? probs[n] : ps);
+                out[i] = u < pv ? T(1) : T(0);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_philox_fill(T* __restrict__ out, int64_t n, T mean, T std, int normal,
+                                                     uint64_t seed, uint64_t offset) {
+    const int64_t nq = (n + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float v4[4];
+        if (normal)
+            philox_normal4((uint64_t)q, offset, seed, v4);
+        else
+            philox_uniform4((uint64_t)q, offset, seed, v4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = q * 4 + j;
+            if (i < n) out[i] = normal ? mean + std * (T)v4[j] : (T)v4[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_philox_raw(uint32_t* __restrict__ out, int64_t nq, uint64_t seed,
+                                                    uint64_t offset) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        Philox4 r = philox4x32_10((uint64_t)q, offset, seed);
+        out[4 * q + 0] = r.x;
+        out[4 * q + 1] = r.y;
+        out[4 * q + 2] = r.z;
+        out[4 * q + 3] = r.w;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------
+template <typename T>
+static bool vec_ok(const Operand<T>& o, int64_t E) {
+    if (o.p == nullptr || o.mode == ZS_SCALAR) return true;
+    return aligned16(o.p) && (E % Pack<T>::N == 0);
+}
+
+template <typename T, typename Op, int LPR>
+static int launch_rows_fwd(T* out, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K, int64_t M, int64_t E,
+                           cudaStream_t st) {
+    const int64_t R = K * M;
+    const int rows_per_block = 256 / LPR;
+    const int grid = grid_for(R, rows_per_block, 256);
+    const bool vec = LPR == 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N;
+    if (vec)
+        k_rows_fwd<T, Op, LPR, true><<<grid, 256, 0, st>>>(out, x, a, b, K, M, E);
+    else
+        k_rows_fwd<T, Op, LPR, false><<<grid, 256, 0, st>>>(out, x, a, b, K, M, E);
+    ZS_LAUNCH_CHECK("k_rows_fwd");
+    return ZS_OK;
+}
+
+template <typename T, typename Op>
+static int dispatch_rows_fwd(T* out, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K, int64_t M, int64_t E,
+                             cudaStream_t st) {
+    if (K * M == 0) return ZS_OK;
+    if (E <= 2) return launch_rows_fwd<T, Op, 1>(out, x, a, b, K, M, E, st);
+    if (E <= 48) return launch_rows_fwd<T, Op, 8>(out, x, a, b, K, M, E, st);
+    return launch_rows_fwd<T, Op, 32>(out, x, a, b, K, M, E, st);
+}
+
+template <typename T, typename Op, int LPR>
+static int launch_rows_bwd(T* dx, T* da, T* db, const T* g, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K,
+                           int64_t M, int64_t E, cudaStream_t st) {
+    const int64_t R = K * M;
+    const int rows_per_block = 256 / LPR;
+    const int grid = grid_for(R, rows_per_block, 256);
+    const bool vec = LPR == 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N &&
+                     aligned16(dx) && aligned16(da) && aligned16(db);
+    if (vec)
+        k_rows_bwd<T, Op, LPR, true><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E);
+    else
+        k_rows_bwd<T, Op, LPR, false><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E);
+    ZS_LAUNCH_CHECK("k_rows_bwd");
+    return ZS_OK;
+}
+
+template <typename T, typename Op>
+static int dispatch_bwd(T* dx, T* da, T* db, const T* g, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K,
+                        int64_t M, int64_t E, cudaStream_t st) {
+    if (K * M * E == 0) return ZS_OK;
+    const bool hasb = b.p != nullptr;
+    // SCALAR gradients are the host's job (it expands the operand); reject them here
+    if ((dx && x.mode == ZS_SCALAR) || (da && a.mode == ZS_SCALAR) || (db && hasb && b.mode == ZS_SCALAR)) {
+        set_last_error_msg("SCALAR-mode gradients are not produced by the kernels; expand the operand");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    const bool needs_kreduce =
+        (dx && x.mode == ZS_KBCAST) || (da && a.mode == ZS_KBCAST) || (db && hasb && b.mode == ZS_KBCAST);
+    if (needs_kreduce) {
+        const int64_t ME = M * E;
+        dim3 block(KR_X, KR_Y);
+        const int64_t grid = (ME + KR_X - 1) / KR_X;
+        ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+        k_kreduce_bwd<T, Op><<<(unsigned)grid, block, 0, st>>>(dx, da, db, g, x, a, b, K, M, E);
+        ZS_LAUNCH_CHECK("k_kreduce_bwd");
+        return ZS_OK;
+    }
+    if (E <= 2) return launch_rows_bwd<T, Op, 1>(dx, da, db, g, x, a, b, K, M, E, st);
+    if (E <= 48) return launch_rows_bwd<T, Op, 8>(dx, da, db, g, x, a, b, K, M, E, st);
+    return launch_rows_bwd<T, Op, 32>(dx, da, db, g, x, a, b, K, M, E, st);
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+#define ZS_DTYPE_SWITCH(dtype, ...)              \
+    if ((dtype) == ZS_F32) {                     \
+        using T = float;                         \
+        __VA_ARGS__                              \
+    } else if ((dtype) == ZS_F64) {              \
+        using T = double;                        \
+        __VA_ARGS__                              \
+    } else {                                     \
+        set_last_error_msg("dtype must be ZS_F32 or ZS_F64"); \
+        return ZS_ERR_DTYPE;                     \
+    }
+
+extern "C" {
+
+int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(out != nullptr && n >= 0 && n % 4 == 0, ZS_ERR_ARG);
+    if (n == 0) return ZS_OK;
+    k_philox_raw<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(out, n / 4, seed, offset);
+    ZS_LAUNCH_CHECK("k_philox_raw");
+    return ZS_OK;
+}
+
+int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(out != nullptr && n >= 0, ZS_ERR_ARG);
+    if (n == 0) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        k_philox_fill<T><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>((T*)out, n, T(0), T(1), 0, seed,
+                                                                                     offset);
+    })
+    ZS_LAUNCH_CHECK("k_philox_fill");
+    return ZS_OK;
+}
+
+int zs_philox_normal(int dtype, void* out, int64_t n, double mean, double std, uint64_t seed, uint64_t offset,
+                     zs_stream_t stream) {
+    ZS_REQUIRE(out != nullptr && n >= 0, ZS_ERR_ARG);
+    if (n == 0) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        k_philox_fill<T><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>((T*)out, n, (T)mean, (T)std, 1,
+                                                                                     seed, offset);
+    })
+    ZS_LAUNCH_CHECK("k_philox_fill");
+    return ZS_OK;
+}
+
+int zs_normal_sample(int dtype, void* z, const void* mean, int mean_mode, const void* std, int std_mode,
+                     const void* eps_in, void* eps_out, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
+                     zs_stream_t stream) {
+    ZS_REQUIRE(z && mean && std && K >= 0 && N >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
+    if (K * N == 0) return ZS_OK;
+    const int grid = grid_for((K * N + 3) / 4, 256);
+    ZS_DTYPE_SWITCH(dtype, {
+        if (N % 4 == 0)
+            k_normal_sample<T, true><<<grid, 256, 0, as_stream(stream)>>>(
+                (T*)z, (const T*)mean, mean_mode, (const T*)std, std_mode, (const T*)eps_in, (T*)eps_out, K, N, seed,
+                offset);
+        else
+            k_normal_sample<T, false><<<grid, 256, 0, as_stream(stream)>>>(
+                (T*)z, (const T*)mean, mean_mode, (const T*)std, std_mode, (const T*)eps_in, (T*)eps_out, K, N, seed,
+                offset);
+    })
+    ZS_LAUNCH_CHECK("k_normal_sample");
+    return ZS_OK;
+}
+
+int zs_normal_sample_bwd(int dtype, void* dmean, int mean_mode, void* dstd, int std_mode, const void* dz,
+                         const void* eps, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(dz && K >= 0 && N >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
+    if ((dmean && mean_mode == ZS_SCALAR) || (dstd && std_mode == ZS_SCALAR)) {
+        set_last_error_msg("SCALAR-mode gradients are not produced by the kernels; expand the operand");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    if (K * N == 0 || (!dmean && !dstd)) return ZS_OK;
+    dim3 block(KR_X, KR_Y);
+    const int64_t grid = (N + KR_X - 1) / KR_X;
+    ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+    ZS_DTYPE_SWITCH(dtype, {
+        k_normal_sample_bwd<T><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+            (T*)dmean, mean_mode, (T*)dstd, std_mode, (const T*)dz, (const T*)eps, K, N, seed, offset);
+    })
+    ZS_LAUNCH_CHECK("k_normal_sample_bwd");
+    return ZS_OK;
+}
+
+int zs_normal_logprob_fwd(int dtype, void* out, const void* x, int x_mode, const void* mean, int mean_mode,
+                          const void* std, int std_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(out && x && mean && std && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_rows_fwd<T, NormalOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                 Operand<T>{(const T*)mean, mean_mode},
+                                                 Operand<T>{(const T*)std, std_mode}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const void* g, const void* x, int x_mode,
+                          const void* mean, int mean_mode, const void* std, int std_mode, int64_t K, int64_t M,
+                          int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(g && x && mean && std && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
+    if (!dx && !dmean && !dstd) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_bwd<T, NormalOp<T>>((T*)dx, (T*)dmean, (T*)dstd, (const T*)g, Operand<T>{(const T*)x, x_mode},
+                                            Operand<T>{(const T*)mean, mean_mode},
+                                            Operand<T>{(const T*)std, std_mode}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_bernoulli_sample(int dtype, void* out, const void* probs, int probs_mode, const void* u_in, int64_t K,
+                        int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(out && probs && K >= 0 && N >= 0 && valid_mode(probs_mode), ZS_ERR_ARG);
+    if (K * N == 0) return ZS_OK;
+    const int grid = grid_for((K * N + 3) / 4, 256);
+    ZS_DTYPE_SWITCH(dtype, {
+        if (N % 4 == 0)
+            k_bernoulli_sample<T, true><<<grid, 256, 0, as_stream(stream)>>>((T*)out, (const T*)probs, probs_mode,
+                                                                              (const T*)u_in, K, N, seed, offset);
+        else
+            k_bernoulli_sample<T, false><<<grid, 256, 0, as_stream(stream)>>>((T*)out, (const T*)probs, probs_mode,
+                                                                               (const T*)u_in, K, N, seed, offset);
+    })
+    ZS_LAUNCH_CHECK("k_bernoulli_sample");
+    return ZS_OK;
+}
+
+int zs_bernoulli_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* probs, int probs_mode,
+                            int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(out && x && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(probs_mode), ZS_ERR_ARG);
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_rows_fwd<T, BernoulliOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                    Operand<T>{(const T*)probs, probs_mode},
+                                                    Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, const void* x, int x_mode,
+                            const void* probs, int probs_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(g && x && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(probs_mode), ZS_ERR_ARG);
+    if (!dx && !dprobs) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_bwd<T, BernoulliOp<T>>((T*)dx, (T*)dprobs, (T*)nullptr, (const T*)g,
+                                               Operand<T>{(const T*)x, x_mode},
+                                               Operand<T>{(const T*)probs, probs_mode},
+                                               Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
+    })
+}
+
+}  // extern "C"

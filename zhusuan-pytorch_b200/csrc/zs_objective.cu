@@ -1,0 +1,268 @@
+// Multi-particle objectives over log-weights [K,B], forward + backward in one launch.
+//
+// Replaces (reference file:line):
+//   compute_iw_term                      zhusuan/variational/importance_weighted_objective.py:16-25
+//   ImportanceWeightedObjective.sgvb     zhusuan/variational/importance_weighted_objective.py:102-132
+//   ImportanceWeightedObjective.vimco    zhusuan/variational/importance_weighted_objective.py:134-191
+//   log_mean_exp                         zhusuan/utils.py:6-21
+// The reference materialises a [B,K,K] tensor for the VIMCO leave-one-out baseline (:184-186) and
+// runs ~40 aten kernels; here each batch column is reduced over its K particles with O(K) work:
+//   x_k = logp_k - logq_k, m = max x, e_k = exp(x_k - m), S = sum e, wt_k = e_k / S
+//   sgvb : cost = -sum wt_k x_k ;              dlogp = -wt,  dlogq = +wt
+//   vimco: mu_k = (sum_j x_j - x_k)/(K-1)      (log geometric mean of the other weights)
+//          sig_k = L - loo_k = -log1p( (exp(mu_k - m) - e_k) / S )
+//          cost = -sum logq_k sig_k - sum wt_k x_k ;  dlogp = -wt, dlogq = wt - sig
+// sig is formed without the reference's L - loo cancellation, so it is at least as accurate as the
+// reference's fp32 result.
+#include "zs_common.cuh"
+
+namespace zs {
+
+constexpr int OBJ_THREADS = 256;
+
+// deterministic reduction across the k-slices (threadIdx.y) of one column (threadIdx.x)
+template <typename T, typename F>
+__device__ __forceinline__ T slice_reduce(T v, T* sm, int cols, int slices, F f) {
+    sm[threadIdx.y * cols + threadIdx.x] = v;
+    __syncthreads();
+    // tree over slices, fixed order
+    for (int s = 1; s < slices; s <<= 1) {
+        if ((threadIdx.y % (2 * s)) == 0 && threadIdx.y + s < slices)
+            sm[threadIdx.y * cols + threadIdx.x] =
+                f(sm[threadIdx.y * cols + threadIdx.x], sm[(threadIdx.y + s) * cols + threadIdx.x]);
+        __syncthreads();
+    }
+    T r = sm[threadIdx.x];
+    __syncthreads();
+    return r;
+}
+
+template <typename T>
+struct Top2 {
+    T m1, m2;
+    long long i1;
+};
+
+template <typename T, int EST>
+__global__ void __launch_bounds__(OBJ_THREADS)
+    k_iw_objective(T* __restrict__ cost, T* __restrict__ dlogp, T* __restrict__ dlogq, const T* __restrict__ logp,
+                   const T* __restrict__ logq, const T* __restrict__ extra, int64_t K, int64_t B, T gscale, int cols,
+                   int slices) {
+    extern __shared__ unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);               // [slices*cols]
+    long long* smi = reinterpret_cast<long long*>(sm + OBJ_THREADS);  // [slices*cols]
+    const int64_t b = (int64_t)blockIdx.x * cols + threadIdx.x;
+    const bool valid = b < B;
+    const T NEG_INF = -INFINITY;
+
+    // pass 1: max (and, for VIMCO, second max excluding the first argmax, and sum of x)
+    T m1 = NEG_INF, m2 = NEG_INF, sumx = T(0);
+    long long i1 = -1;
+    if (valid) {
+        for (int64_t k = threadIdx.y; k < K; k += slices) {
+            T x = logp[k * B + b] - logq[k * B + b] + (extra ? extra[k * B + b] : T(0));
+            if (EST == ZS_EST_VIMCO) sumx += x;
+            if (x > m1 || i1 < 0) {
+                m2 = m1;
+                m1 = x;
+                i1 = k;
+            } else if (x > m2) {
+                m2 = x;
+            }
+        }
+    }
+    // merge (m1,i1,m2) across slices: smallest index wins ties so the result is order independent
+    {
+        sm[threadIdx.y * cols + threadIdx.x] = m1;
+        smi[threadIdx.y * cols + threadIdx.x] = i1;
+        __syncthreads();
+        T gm = NEG_INF;
+        long long gi = -1;
+        for (int s = 0; s < slices; ++s) {
+            T v = sm[s * cols + threadIdx.x];
+            long long vi = smi[s * cols + threadIdx.x];
+            if (vi >= 0 && (gi < 0 || v > gm || (v == gm && vi < gi))) {
+                gm = v;
+                gi = vi;
+            }
+        }
+        __syncthreads();
+        if (EST == ZS_EST_VIMCO) {
+            // second max = max over all elements except index gi
+            T cand = (i1 == gi) ? m2 : m1;
+            m2 = slice_reduce(cand, sm, cols, slices, [](T a, T c) { return a > c ? a : c; });
+            sumx = slice_reduce(sumx, sm, cols, slices, [](T a, T c) { return a + c; });
+        }
+        m1 = gm;
+        i1 = gi;
+    }
+
+    // pass 2: S = sum exp(x - m) ; VIMCO also S2 = sum_{k != argmax} exp(x - m2)
+    T S = T(0), S2 = T(0);
+    if (valid) {
+        for (int64_t k = threadIdx.y; k < K; k += slices) {
+            T x = logp[k * B + b] - logq[k * B + b] + (extra ? extra[k * B + b] : T(0));
+            S += Real<T>::exp(x - m1);
+            if (EST == ZS_EST_VIMCO && k != i1) S2 += Real<T>::exp(x - m2);
+        }
+    }
+    S = slice_reduce(S, sm, cols, slices, [](T a, T c) { return a + c; });
+    if (EST == ZS_EST_VIMCO) S2 = slice_reduce(S2, sm, cols, slices, [](T a, T c) { return a + c; });
+
+    // pass 3: weights, learning signal, cost and gradients
+    T c_acc = T(0);
+    if (valid) {
+        const T invS = T(1) / S;
+        const T km1 = (T)(K - 1);
+        for (int64_t k = threadIdx.y; k < K; k += slices) {
+            const T lq = logq[k * B + b];
+            const T x = logp[k * B + b] - lq + (extra ? extra[k * B + b] : T(0));
+            const T e = Real<T>::exp(x - m1);
+            const T wt = e / S;
+            c_acc -= wt * x;
+            T gq = wt;
+            if (EST == ZS_EST_VIMCO) {
+                const T mu = (sumx - x) / km1;
+                T sig;
+                if (k == i1 && (m1 - m2) > T(1)) {
+                    // the arg-max row: S - e would cancel, re-centre on the second max
+                    T Sloo = S2 + Real<T>::exp(mu - m2);
+                    sig = (m1 - m2) + (Real<T>::log(S) - Real<T>::log(Sloo));
+                } else {
+                    T t = (Real<T>::exp(mu - m1) - e) * invS;
+                    sig = -log1p(t);
+                }
+                c_acc -= lq * sig;
+                gq = wt - sig;
+            }
+            if (dlogp) dlogp[k * B + b] = -wt * gscale;
+            if (dlogq) dlogq[k * B + b] = gq * gscale;
+        }
+    }
+    c_acc = slice_reduce(c_acc, sm, cols, slices, [](T a, T c) { return a + c; });
+    if (valid && threadIdx.y == 0 && cost) cost[b] = c_acc;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(OBJ_THREADS)
+    k_log_mean_exp(T* __restrict__ out, const T* __restrict__ g, const T* __restrict__ x, int64_t K, int64_t B,
+                   int cols, int slices) {
+    extern __shared__ unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    const int64_t b = (int64_t)blockIdx.x * cols + threadIdx.x;
+    const bool valid = b < B;
+    T m = -INFINITY;
+    if (valid)
+        for (int64_t k = threadIdx.y; k < K; k += slices) m = fmax(m, x[k * B + b]);
+    m = slice_reduce(m, sm, cols, slices, [](T a, T c) { return a > c ? a : c; });
+    T S = T(0);
+    if (valid)
+        for (int64_t k = threadIdx.y; k < K; k += slices) S += Real<T>::exp(x[k * B + b] - m);
+    S = slice_reduce(S, sm, cols, slices, [](T a, T c) { return a + c; });
+    if (!BWD) {
+        // zhusuan/utils.py:18-19: log(mean(exp(x - max))) + max
+        if (valid && threadIdx.y == 0) out[b] = Real<T>::log(S / (T)K) + m;
+    } else if (valid) {
+        const T gb = g[b];
+        for (int64_t k = threadIdx.y; k < K; k += slices) out[k * B + b] = gb * (Real<T>::exp(x[k * B + b] - m) / S);
+    }
+}
+
+static void column_geometry(int64_t B, int& cols, int& slices) {
+    cols = 1;
+    while (cols < 32 && cols < B) cols <<= 1;
+    slices = OBJ_THREADS / cols;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" {
+
+int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlogq, const void* logp,
+                    const void* logq, const void* logp_extra, int64_t K, int64_t B, double grad_scale,
+                    zs_stream_t stream) {
+    ZS_REQUIRE(logp && logq && K >= 1 && B >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && K < 2), ZS_ERR_ARG);
+    if (B == 0) return ZS_OK;
+    int cols, slices;
+    column_geometry(B, cols, slices);
+    dim3 block(cols, slices);
+    const int64_t grid = (B + cols - 1) / cols;
+    ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == ZS_F32) {
+        const size_t smem = OBJ_THREADS * (sizeof(float) + sizeof(long long));
+        if (estimator == ZS_EST_SGVB)
+            k_iw_objective<float, ZS_EST_SGVB><<<(unsigned)grid, block, smem, st>>>(
+                (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
+                (float)grad_scale, cols, slices);
+        else
+            k_iw_objective<float, ZS_EST_VIMCO><<<(unsigned)grid, block, smem, st>>>(
+                (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
+                (float)grad_scale, cols, slices);
+    } else if (dtype == ZS_F64) {
+        const size_t smem = OBJ_THREADS * (sizeof(double) + sizeof(long long));
+        if (estimator == ZS_EST_SGVB)
+            k_iw_objective<double, ZS_EST_SGVB><<<(unsigned)grid, block, smem, st>>>(
+                (double*)cost, (double*)dlogp, (double*)dlogq, (const double*)logp, (const double*)logq, (const double*)logp_extra, K, B,
+                grad_scale, cols, slices);
+        else
+            k_iw_objective<double, ZS_EST_VIMCO><<<(unsigned)grid, block, smem, st>>>(
+                (double*)cost, (double*)dlogp, (double*)dlogq, (const double*)logp, (const double*)logq, (const double*)logp_extra, K, B,
+                grad_scale, cols, slices);
+    } else {
+        set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+        return ZS_ERR_DTYPE;
+    }
+    ZS_LAUNCH_CHECK("k_iw_objective");
+    return ZS_OK;
+}
+
+static int lme_launch(int dtype, bool bwd, void* out, const void* g, const void* x, int64_t K, int64_t B,
+                      zs_stream_t stream) {
+    ZS_REQUIRE(out && x && K >= 1 && B >= 0, ZS_ERR_ARG);
+    if (B == 0) return ZS_OK;
+    int cols, slices;
+    column_geometry(B, cols, slices);
+    dim3 block(cols, slices);
+    const int64_t grid = (B + cols - 1) / cols;
+    ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == ZS_F32) {
+        const size_t smem = OBJ_THREADS * sizeof(float);
+        if (bwd)
+            k_log_mean_exp<float, true><<<(unsigned)grid, block, smem, st>>>((float*)out, (const float*)g,
+                                                                              (const float*)x, K, B, cols, slices);
+        else
+            k_log_mean_exp<float, false><<<(unsigned)grid, block, smem, st>>>((float*)out, nullptr, (const float*)x,
+                                                                               K, B, cols, slices);
+    } else if (dtype == ZS_F64) {
+        const size_t smem = OBJ_THREADS * sizeof(double);
+        if (bwd)
+            k_log_mean_exp<double, true><<<(unsigned)grid, block, smem, st>>>((double*)out, (const double*)g,
+                                                                               (const double*)x, K, B, cols, slices);
+        else
+            k_log_mean_exp<double, false><<<(unsigned)grid, block, smem, st>>>((double*)out, nullptr,
+                                                                                (const double*)x, K, B, cols, slices);
+    } else {
+        set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+        return ZS_ERR_DTYPE;
+    }
+    ZS_LAUNCH_CHECK("k_log_mean_exp");
+    return ZS_OK;
+}
+
+int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, zs_stream_t stream) {
+    return lme_launch(dtype, false, out, nullptr, x, K, B, stream);
+}
+
+int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64_t K, int64_t B,
+                        zs_stream_t stream) {
+    ZS_REQUIRE(g != nullptr, ZS_ERR_ARG);
+    return lme_launch(dtype, true, dx, g, x, K, B, stream);
+}
+
+}  // extern "C"

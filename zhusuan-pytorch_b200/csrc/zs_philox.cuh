@@ -1,0 +1,66 @@
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11) and the uniform / normal
+// conversions used by every sampling kernel.  Element i of a call draws word i%4 of
+// Philox(counter = (i/4 lo, i/4 hi, offset lo, offset hi), key = (seed lo, seed hi)), so the
+// stream is a pure function of (seed, offset, i): independent of launch geometry and of how
+// particles / chains are sharded over ranks.  oracle/zs_oracle_impl.h restates it bit-exactly.
+#pragma once
+#include <stdint.h>
+
+namespace zs {
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t index, uint64_t offset, uint64_t seed) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
+    uint32_t c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// u in [0,1): 24 random bits.  P(u < p) == p up to 2^-24 for the Bernoulli draw.
+__host__ __device__ __forceinline__ float u01_closed_open(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-8f; }
+// u in (0,1): safe under log()
+__host__ __device__ __forceinline__ float u01_open(uint32_t r) {
+    return (float)(r >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+}
+
+#ifdef __CUDACC__
+// Box-Muller on two words -> two standard normals.
+__device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
+    float u1 = u01_open(r0), u2 = u01_open(r1);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+// the four standard normals of element group q (elements 4q .. 4q+3)
+__device__ __forceinline__ void philox_normal4(uint64_t q, uint64_t offset, uint64_t seed, float out[4]) {
+    Philox4 r = philox4x32_10(q, offset, seed);
+    box_muller(r.x, r.y, out[0], out[1]);
+    box_muller(r.z, r.w, out[2], out[3]);
+}
+__device__ __forceinline__ void philox_uniform4(uint64_t q, uint64_t offset, uint64_t seed, float out[4]) {
+    Philox4 r = philox4x32_10(q, offset, seed);
+    out[0] = u01_closed_open(r.x);
+    out[1] = u01_closed_open(r.y);
+    out[2] = u01_closed_open(r.z);
+    out[3] = u01_closed_open(r.w);
+}
+#endif
+
+}  // namespace zs

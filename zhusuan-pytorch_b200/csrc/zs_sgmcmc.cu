@@ -1,0 +1,271 @@
+// SG-MCMC parameter updates across parallel chains: one fused, in-place pass per update with the
+// Gaussian term drawn in-register from Philox (or injected for parity tests).
+//
+// Replaces (reference file:line):
+//   SGLD._update   zhusuan/mcmc/SGLD.py:42-54    w += 0.5*lr*g + N(0, lr)
+//   PSGLD._update  zhusuan/mcmc/SGLD.py:67-82    RMSprop-preconditioned SGLD
+//   SGHMC._update  zhusuan/mcmc/SGHMC.py:25-56   first / second order, velocity resampling
+// The reference draws every noise tensor on the CPU and copies it to the device
+// (SGLD.py:51, SGHMC.py:27,33,34) and runs 3-6 elementwise kernels per tensor.
+// Scalar coefficients are rounded exactly as the reference's Python does: SGLD.lr is a float32
+// 0-d tensor (SGLD.py:20), SGHMC.lr / alpha / beta are Python floats cast to the tensor dtype.
+#include "zs_common.cuh"
+#include "zs_philox.cuh"
+
+namespace zs {
+
+template <typename T>
+struct Quad {
+    T v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ Quad<T> ld4(const T* p);
+template <>
+__device__ __forceinline__ Quad<float> ld4<float>(const float* p) {
+    Pack<float> a = ld_pack(p);
+    return Quad<float>{{a.v[0], a.v[1], a.v[2], a.v[3]}};
+}
+template <>
+__device__ __forceinline__ Quad<double> ld4<double>(const double* p) {
+    Pack<double> a = ld_pack(p), b = ld_pack(p + 2);
+    return Quad<double>{{a.v[0], a.v[1], b.v[0], b.v[1]}};
+}
+__device__ __forceinline__ void st4(float* p, const Quad<float>& q) {
+    Pack<float> a{{q.v[0], q.v[1], q.v[2], q.v[3]}};
+    st_pack(p, a);
+}
+__device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
+    Pack<double> a{{q.v[0], q.v[1]}}, b{{q.v[2], q.v[3]}};
+    st_pack(p, a);
+    st_pack(p + 2, b);
+}
+
+// Generic driver: Body::apply(i-th element state...) over n elements, 4 per thread.
+// VEC requires 16-byte aligned pointers; the last n%4 elements always take the scalar path.
+template <typename T, typename Body, bool VEC>
+__global__ void __launch_bounds__(256) k_chain_update(Body body, int64_t n, uint64_t seed, uint64_t offset) {
+    const int64_t nq = (n + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        float xi[4] = {0.f, 0.f, 0.f, 0.f};
+        if (body.needs_rng()) philox_normal4((uint64_t)q, offset, seed, xi);
+        const int64_t i0 = q * 4;
+        if (VEC && i0 + 4 <= n) {
+            body.vec(i0, xi);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < n) body.one(i0 + j, xi[j]);
+        }
+    }
+}
+
+template <typename T>
+struct SgldBody {
+    T* w;
+    const T* g;
+    const T* noise;  // already scaled, or null
+    T half_lr;       // (T)(0.5f * (float)lr)
+    float std;       // sqrt(lr)
+    __device__ bool needs_rng() const { return noise == nullptr; }
+    __device__ __forceinline__ T upd(T wv, T gv, T e) const { return (wv + half_lr * gv) + e; }
+    __device__ void one(int64_t i, float xi) const {
+        T e = noise ? noise[i] : (T)(std * xi);
+        w[i] = upd(w[i], g[i], e);
+    }
+    __device__ void vec(int64_t i, const float* xi) const {
+        Quad<T> wv = ld4(w + i), gv = ld4(g + i), ev;
+        if (noise) ev = ld4(noise + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv.v[j] = upd(wv.v[j], gv.v[j], noise ? ev.v[j] : (T)(std * xi[j]));
+        st4(w + i, wv);
+    }
+};
+
+template <typename T>
+struct PsgldBody {
+    T* w;
+    T* aux;
+    const T* g;
+    const T* unit;  // unit normals or null
+    T decay, one_m_decay, eps, lr, half_lr;
+    __device__ bool needs_rng() const { return unit == nullptr; }
+    __device__ __forceinline__ void upd(T& wv, T& av, T gv, T xi) const {
+        av = decay * av + one_m_decay * (gv * gv);
+        T G = T(1) / (eps + Real<T>::sqrt(av));
+        T e = Real<T>::sqrt(lr * G) * xi;
+        wv = (wv + (half_lr * G) * gv) + e;
+    }
+    __device__ void one(int64_t i, float xi) const {
+        T wv = w[i], av = aux[i];
+        upd(wv, av, g[i], unit ? unit[i] : (T)xi);
+        w[i] = wv;
+        aux[i] = av;
+    }
+    __device__ void vec(int64_t i, const float* xi) const {
+        Quad<T> wv = ld4(w + i), av = ld4(aux + i), gv = ld4(g + i), uv;
+        if (unit) uv = ld4(unit + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) upd(wv.v[j], av.v[j], gv.v[j], unit ? uv.v[j] : (T)xi[j]);
+        st4(w + i, wv);
+        st4(aux + i, av);
+    }
+};
+
+template <typename T>
+struct SghmcPreBody {
+    T* w;
+    T* v;
+    const T* v_noise;  // injected resampled velocity, or null
+    float std;         // sqrt(lr)
+    int resample, second_order;
+    __device__ bool needs_rng() const { return resample && v_noise == nullptr; }
+    __device__ __forceinline__ void upd(T& wv, T& vv, T fresh) const {
+        if (resample) vv = fresh;
+        if (second_order) wv = wv + T(0.5) * vv;
+    }
+    __device__ void one(int64_t i, float xi) const {
+        T wv = w[i], vv = v[i];
+        upd(wv, vv, v_noise ? v_noise[i] : (T)(std * xi));
+        if (resample) v[i] = vv;
+        if (second_order) w[i] = wv;
+    }
+    __device__ void vec(int64_t i, const float* xi) const {
+        Quad<T> wv = ld4(w + i), vv = ld4(v + i), nv;
+        if (v_noise) nv = ld4(v_noise + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], v_noise ? nv.v[j] : (T)(std * xi[j]));
+        if (resample) st4(v + i, vv);
+        if (second_order) st4(w + i, wv);
+    }
+};
+
+template <typename T>
+struct SghmcPostBody {
+    T* w;
+    T* v;
+    const T* g;
+    const T* noise;  // already scaled, or null
+    T one_m_alpha, lr, decay_half;
+    float std;  // sqrt(2 (alpha-beta) lr)
+    int second_order;
+    __device__ bool needs_rng() const { return noise == nullptr; }
+    __device__ __forceinline__ void upd(T& wv, T& vv, T gv, T n) const {
+        if (!second_order) {
+            vv = (one_m_alpha * vv + lr * gv) + n;
+            wv = wv + vv;
+        } else {
+            vv = decay_half * ((decay_half * vv + lr * gv) + n);
+            wv = wv + T(0.5) * vv;
+        }
+    }
+    __device__ void one(int64_t i, float xi) const {
+        T wv = w[i], vv = v[i];
+        upd(wv, vv, g[i], noise ? noise[i] : (T)(std * xi));
+        w[i] = wv;
+        v[i] = vv;
+    }
+    __device__ void vec(int64_t i, const float* xi) const {
+        Quad<T> wv = ld4(w + i), vv = ld4(v + i), gv = ld4(g + i), nv;
+        if (noise) nv = ld4(noise + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], gv.v[j], noise ? nv.v[j] : (T)(std * xi[j]));
+        st4(w + i, wv);
+        st4(v + i, vv);
+    }
+};
+
+template <typename T, typename Body>
+static int launch_chain(Body body, int64_t n, bool vec, uint64_t seed, uint64_t offset, cudaStream_t st,
+                        const char* name) {
+    if (n == 0) return ZS_OK;
+    const int grid = grid_for((n + 3) / 4, 256, 64);
+    if (vec)
+        k_chain_update<T, Body, true><<<grid, 256, 0, st>>>(body, n, seed, offset);
+    else
+        k_chain_update<T, Body, false><<<grid, 256, 0, st>>>(body, n, seed, offset);
+    ZS_LAUNCH_CHECK(name);
+    return ZS_OK;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" {
+
+int zs_sgld_step(int dtype, void* w, const void* g, const void* noise, int64_t n, double lr, uint64_t seed,
+                 uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+    const float lr_f = (float)lr;
+    const float std = (float)sqrt((double)lr_f);
+    const bool vec = aligned16(w) && aligned16(g) && aligned16(noise);
+    if (dtype == ZS_F32) {
+        SgldBody<float> b{(float*)w, (const float*)g, (const float*)noise, 0.5f * lr_f, std};
+        return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sgld");
+    } else if (dtype == ZS_F64) {
+        SgldBody<double> b{(double*)w, (const double*)g, (const double*)noise, (double)(0.5f * lr_f), std};
+        return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sgld");
+    }
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_psgld_step(int dtype, void* w, void* aux, const void* g, const void* noise_unit, int64_t n, double lr,
+                  double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w && aux && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+    const float lr_f = (float)lr;
+    const bool vec = aligned16(w) && aligned16(g) && aligned16(aux) && aligned16(noise_unit);
+    if (dtype == ZS_F32) {
+        PsgldBody<float> b{(float*)w,      (float*)aux,           (const float*)g, (const float*)noise_unit,
+                           (float)decay,   (float)(1.0 - decay),  (float)epsilon,  lr_f,
+                           0.5f * lr_f};
+        return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "psgld");
+    } else if (dtype == ZS_F64) {
+        PsgldBody<double> b{(double*)w, (double*)aux, (const double*)g, (const double*)noise_unit,
+                            decay,      1.0 - decay,  epsilon,          (double)lr_f,
+                            (double)(0.5f * lr_f)};
+        return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "psgld");
+    }
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_sghmc_pre(int dtype, void* w, void* v, const void* v_noise, int64_t n, double lr, int resample,
+                 int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w && v && n >= 0 && lr >= 0, ZS_ERR_ARG);
+    if (!resample && !second_order) return ZS_OK;
+    const float std = (float)sqrt(lr);
+    const bool vec = aligned16(w) && aligned16(v) && aligned16(v_noise);
+    if (dtype == ZS_F32) {
+        SghmcPreBody<float> b{(float*)w, (float*)v, (const float*)v_noise, std, resample, second_order};
+        return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sghmc_pre");
+    } else if (dtype == ZS_F64) {
+        SghmcPreBody<double> b{(double*)w, (double*)v, (const double*)v_noise, std, resample, second_order};
+        return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sghmc_pre");
+    }
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_sghmc_post(int dtype, void* w, void* v, const void* g, const void* noise, int64_t n, double lr, double alpha,
+                  double beta, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w && v && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(alpha - beta >= 0, ZS_ERR_ARG);
+    const float std = (float)sqrt(2.0 * (alpha - beta) * lr);
+    const double dh = exp(-0.5 * alpha);
+    const bool vec = aligned16(w) && aligned16(v) && aligned16(g) && aligned16(noise);
+    if (dtype == ZS_F32) {
+        SghmcPostBody<float> b{(float*)w, (float*)v, (const float*)g, (const float*)noise, (float)(1.0 - alpha),
+                               (float)lr, (float)dh, std,             second_order};
+        return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sghmc_post");
+    } else if (dtype == ZS_F64) {
+        SghmcPostBody<double> b{(double*)w, (double*)v, (const double*)g, (const double*)noise, 1.0 - alpha,
+                                lr,         dh,         std,              second_order};
+        return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sghmc_post");
+    }
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+}  // extern "C"
