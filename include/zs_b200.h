@@ -147,6 +147,9 @@ int zs_categorical_logpmf_bwd(int dtype, void* dlogits, const void* g, const voi
 int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlogq, const void* logp,
                     const void* logq, const void* logp_extra, int64_t K, int64_t B, double grad_scale,
                     zs_stream_t stream);
+/* buf[n] *= *scale_dev, a no-op launch when *scale_dev == 1: applies the upstream gradient of the
+ * scalar loss to gradients the fused kernels computed for a unit upstream gradient.          */
+int zs_scale_inplace(int dtype, void* buf, int64_t n, const void* scale_dev, zs_stream_t stream);
 /* log_mean_exp over the leading axis of [K,B] -> [B]   (zhusuan/utils.py:6-21)    */
 int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, zs_stream_t stream);
 /* backward: dx[K,B] = g[B] * softmax_k(x)                                          */
@@ -172,26 +175,30 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
                           zs_stream_t stream);
 
-/* ---- SG-MCMC updates across parallel chains (in place, one pass) -------------
+/* ---- SG-MCMC updates across parallel chains (one pass) -----------------------
+ * w_out receives the updated chain state and may alias w (in place); the reference
+ * returns a fresh leaf tensor per step (SGLD.py:52-54), which costs the same bytes.
+ * Velocity / preconditioner state (v, aux) is always updated in place.
  * noise != NULL injects the already-scaled Gaussian term (parity mode); otherwise
  * it is drawn from Philox(seed, offset) inside the kernel.
  * SGLD._update (SGLD.py:42-54):  w += 0.5*lr*g + N(0, lr)                          */
-int zs_sgld_step(int dtype, void* w, const void* g, const void* noise, int64_t n, double lr, uint64_t seed,
-                 uint64_t offset, zs_stream_t stream);
+int zs_sgld_step(int dtype, void* w_out, const void* w, const void* g, const void* noise, int64_t n, double lr,
+                 uint64_t seed, uint64_t offset, zs_stream_t stream);
 /* PSGLD._update (SGLD.py:67-82): aux = decay*aux + (1-decay) g^2; G = 1/(eps+sqrt(aux));
  * w += 0.5*lr*G*g + N(0, lr*G).  noise_unit != NULL injects UNIT normals.          */
-int zs_psgld_step(int dtype, void* w, void* aux, const void* g, const void* noise_unit, int64_t n, double lr,
-                  double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_psgld_step(int dtype, void* w_out, const void* w, void* aux, const void* g, const void* noise_unit, int64_t n,
+                  double lr, double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream);
 /* SGHMC._update (SGHMC.py:25-56).
  *   zs_sghmc_pre : optional velocity resample v ~ N(0, lr) (resample != 0; v_noise
  *                  injects it) and, for second_order, the half step w += 0.5 v.
  *   zs_sghmc_post: first order  v = (1-alpha) v + lr g + n ; w += v
  *                  second order v = d (d v + lr g + n), d = exp(-alpha/2) ; w += 0.5 v
  *                  n ~ N(0, 2(alpha-beta) lr) (noise injects it).                   */
-int zs_sghmc_pre(int dtype, void* w, void* v, const void* v_noise, int64_t n, double lr, int resample,
-                 int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
-int zs_sghmc_post(int dtype, void* w, void* v, const void* g, const void* noise, int64_t n, double lr, double alpha,
-                  double beta, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_sghmc_pre(int dtype, void* w_out, const void* w, void* v, const void* v_noise, int64_t n, double lr,
+                 int resample, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g, const void* noise, int64_t n,
+                  double lr, double alpha, double beta, int second_order, uint64_t seed, uint64_t offset,
+                  zs_stream_t stream);
 
 /* ---- host-buffer convenience call (end-to-end measurement) ----
  * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers:

@@ -1,0 +1,576 @@
+"""GPU parity tests: every C-ABI entry point (through the ctypes binding) against the CPU oracle and
+the reference-generated golden fixtures.  Tolerances (fp32): 1e-5 relative, normwise
+(atol = 1e-5 * max|ref|) unless a test states otherwise; fp64: 1e-11."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from zhusuan import _backend as be  # noqa: E402
+
+DEV = "cuda"
+FULL, KBCAST, SCALAR = be.FULL, be.KBCAST, be.SCALAR
+
+
+def dev(a, dt=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dt is not None:
+        t = t.to(dt)
+    return t.to(DEV).contiguous()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, ref, rtol=1e-5, what=""):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    scale = max(np.abs(ref).max(), 1e-30)
+    np.testing.assert_allclose(a, ref, rtol=rtol, atol=rtol * scale, err_msg=what)
+
+
+def rtol_of(dt):
+    return 1e-5 if dt in (np.float32, torch.float32) else 1e-11
+
+
+def mode_of(a, K, N):
+    if a.size == 1 and K * N != 1:
+        return SCALAR
+    if a.size == N and K != 1:
+        return KBCAST
+    return FULL
+
+
+# ----------------------------------------------------------------------------- RNG
+def test_philox_bit_exact(oracle):
+    for seed, offset, n in [(0, 0, 64), (12345678901234, 987654321098, 4096), (2 ** 63 + 5, 2 ** 40 + 3, 1024)]:
+        got = host(be.philox_raw(n, seed, offset, DEV)).view(np.uint32)
+        assert np.array_equal(got, oracle.philox_raw(n, seed, offset))
+
+
+def test_philox_uniform_normal(oracle):
+    from scipy import stats
+    n = 1 << 20
+    u = host(be.philox_uniform(n, torch.float32, 3, 5, DEV))
+    assert np.array_equal(u, oracle.philox_uniform(n, 3, 5))  # integer -> float conversion is exact
+    z = host(be.philox_normal(n, torch.float32, 0.0, 1.0, 3, 6, DEV))
+    zo = oracle.philox_normal(n, 3, 6)
+    np.testing.assert_allclose(z, zo, rtol=0, atol=2e-5)  # Box-Muller in fp32: CUDA vs glibc libm
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+    assert stats.kstest(z[:200000], "norm").pvalue > 1e-3
+    assert abs(stats.skew(z)) < 0.01 and abs(stats.kurtosis(z)) < 0.02
+    z64 = host(be.philox_normal(1001, torch.float64, 1.0, 2.0, 3, 6, DEV))
+    np.testing.assert_allclose(z64, 1.0 + 2.0 * zo[:1001].astype(np.float64), atol=1e-4)
+
+
+# ----------------------------------------------------------------------------- Normal
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,N,mm,sm", [(5, 48, KBCAST, KBCAST), (3, 10, FULL, FULL), (4, 7, KBCAST, SCALAR),
+                                        (50, 4096, KBCAST, KBCAST), (1, 33, FULL, FULL)])
+def test_normal_sample_injected(oracle, dt, K, N, mm, sm):
+    rng = np.random.RandomState(1)
+    shp = {FULL: (K, N), KBCAST: (N,), SCALAR: (1,)}
+    mean = rng.standard_normal(shp[mm]).astype(dt)
+    std = np.exp(0.3 * rng.standard_normal(shp[sm])).astype(dt)
+    eps = rng.standard_normal((K, N)).astype(dt)
+    z = be.normal_sample(dev(mean), mm, dev(std), sm, K, N, eps_in=dev(eps))
+    close(host(z), oracle.normal_sample(mean, std, eps, K, N), rtol_of(dt))
+    # pathwise backward
+    dz = rng.standard_normal((K, N)).astype(dt)
+    if sm != SCALAR:
+        dmean, dstd = be.normal_sample_bwd(dev(dz), dev(mean), mm, dev(std), sm, K, N, eps=dev(eps))
+        om, os_ = oracle.normal_sample_bwd(dz, eps, mean, std, K, N)
+        close(host(dmean), om, rtol_of(dt))
+        close(host(dstd), os_, rtol_of(dt))
+
+
+def test_normal_sample_philox_statistics(oracle):
+    """CPU and GPU RNG streams differ from torch's, so the sampler is validated statistically
+    (moments + KS) and for self-consistency (eps_out, regenerated noise in backward)."""
+    from scipy import stats
+    K, N = 50, 40960
+    mean = torch.linspace(-1, 1, N, device=DEV)
+    std = torch.linspace(0.5, 2.0, N, device=DEV)
+    eps = torch.empty((K, N), device=DEV)
+    z = be.normal_sample(mean, KBCAST, std, KBCAST, K, N, eps_out=eps, seed=11, offset=4)
+    torch.testing.assert_close(z, mean + std * eps, rtol=1e-6, atol=1e-6)
+    e = host(eps).ravel()
+    assert abs(e.mean()) < 3e-3 and abs(e.std() - 1) < 3e-3
+    assert stats.kstest(e[::7], "norm").pvalue > 1e-3
+    # standardised samples are N(0,1) per coordinate
+    zs = host((z - mean) / std)
+    assert np.abs(zs.mean(0)).max() < 0.8 and abs(zs.var(0).mean() - 1) < 0.02
+    # the stream is a pure function of (seed, offset): same call -> same bits, other offset -> other bits
+    z2 = be.normal_sample(mean, KBCAST, std, KBCAST, K, N, seed=11, offset=4)
+    assert torch.equal(z, z2)
+    z3 = be.normal_sample(mean, KBCAST, std, KBCAST, K, N, seed=11, offset=8)
+    assert not torch.equal(z, z3)
+    # matches the oracle's restatement of the same Philox / Box-Muller stream
+    np.testing.assert_allclose(e[:4096], oracle.philox_normal(4096, 11, 4), atol=2e-5)
+    # backward regenerates the noise instead of storing it
+    dz = torch.randn((K, N), device=DEV)
+    dm1, ds1 = be.normal_sample_bwd(dz, mean, KBCAST, std, KBCAST, K, N, eps=eps)
+    dm2, ds2 = be.normal_sample_bwd(dz, mean, KBCAST, std, KBCAST, K, N, eps=None, seed=11, offset=4)
+    assert torch.equal(dm1, dm2) and torch.equal(ds1, ds2)
+
+
+def _normal_case(g, case, dn):
+    p = "%s_%s_" % (case, dn)
+    x, mean, std, up = g[p + "x"], g[p + "mean"], g[p + "std"], g[p + "g"]
+    if case == "ylik":
+        K, M, E = mean.shape[0], mean.shape[1], 1
+    elif case == "group2":
+        K, M, E = x.shape[0], 1, x.shape[1] * x.shape[2]
+    else:
+        K, M, E = x.shape
+    return p, x, mean, std, up, K, M, E
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("case", ["kbcast", "full", "ylik", "group2"])
+def test_normal_logprob_golden(golden, case, dn):
+    """Against the real reference's outputs and autograd gradients (tests/golden/make_golden.py)."""
+    g = golden("normal_logprob")
+    p, x, mean, std, up, K, M, E = _normal_case(g, case, dn)
+    rt = 1e-5 if dn == "f32" else 1e-11
+    xm, mm, sm = mode_of(x, K, M * E), mode_of(mean, K, M * E), mode_of(std, K, M * E)
+    out = be.normal_logprob_fwd(dev(x), xm, dev(mean), mm, dev(std), sm, K, M, E)
+    close(host(out).reshape(g[p + "out"].shape), g[p + "out"], rt)
+    stdd = dev(std)
+    if sm == SCALAR:  # SCALAR gradients: the host expands the operand (here to KBCAST) and sums
+        stdd = stdd.expand(M * E).contiguous()
+        sm = KBCAST
+    dx, dmean, dstd = be.normal_logprob_bwd(dev(up), dev(x), xm, dev(mean), mm, stdd, sm, K, M, E, True, True, True)
+    close(host(dx).reshape(g[p + "dx"].shape), g[p + "dx"], rt)
+    close(host(dmean).reshape(g[p + "dmean"].shape), g[p + "dmean"], rt)
+    dstd = host(dstd)
+    if g[p + "dstd"].size == 1:
+        dstd = dstd.sum(keepdims=True)
+    close(dstd.reshape(g[p + "dstd"].shape), g[p + "dstd"], rt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,M,E,xm,mm,sm", [
+    (50, 256, 40, FULL, KBCAST, KBCAST),     # q(z|x) at cfg-2 shapes
+    (50, 256, 40, FULL, FULL, FULL),
+    (7, 33, 5, FULL, KBCAST, FULL),          # ragged: E not a multiple of 4 -> scalar path
+    (100, 1000, 1, KBCAST, FULL, SCALAR),    # BNN y-likelihood (bnn_vi.py:55-60)
+    (100, 1, 4550, FULL, KBCAST, KBCAST),    # BNN weights, group_ndims=2 (bnn_vi.py:32-38)
+    (1, 128, 40, FULL, FULL, FULL),          # K = 1 (cfg 1)
+    (3, 2, 131, FULL, KBCAST, KBCAST),
+])
+def test_normal_logprob_oracle(oracle, dt, K, M, E, xm, mm, sm):
+    rng = np.random.RandomState(2)
+    shp = {FULL: (K, M, E), KBCAST: (M, E), SCALAR: (1,)}
+    x = rng.standard_normal(shp[xm]).astype(dt)
+    mean = (0.5 * rng.standard_normal(shp[mm])).astype(dt)
+    std = np.exp(0.3 * rng.standard_normal(shp[sm])).astype(dt)
+    up = rng.standard_normal((K, M)).astype(dt)
+    out = be.normal_logprob_fwd(dev(x), xm, dev(mean), mm, dev(std), sm, K, M, E)
+    close(host(out), oracle.normal_logprob_fwd(x, mean, std, K, M, E), rtol_of(dt))
+    need_std = sm != SCALAR
+    dx, dmean, dstd = be.normal_logprob_bwd(dev(up), dev(x), xm, dev(mean), mm, dev(std), sm, K, M, E, True, True,
+                                            need_std)
+    # fp64 oracle on the same inputs is the yard-stick for sums over K (order differs)
+    ox, om, os_ = oracle.normal_logprob_bwd(up.astype(np.float64), x.astype(np.float64), mean.astype(np.float64),
+                                            std.astype(np.float64), K, M, E)
+    close(host(dx), ox, rtol_of(dt))
+    close(host(dmean), om, rtol_of(dt))
+    if need_std:
+        close(host(dstd), os_, rtol_of(dt))
+
+
+def test_scalar_gradient_is_rejected():
+    x = torch.randn(4, 3, device=DEV)
+    with pytest.raises(be.BackendError):
+        be.normal_logprob_bwd(torch.ones(4, 3, device=DEV), x, FULL, x, FULL, torch.ones(1, device=DEV), SCALAR, 4, 3,
+                              1, False, False, True)
+
+
+# ----------------------------------------------------------------------------- Bernoulli
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("case", ["lik", "lik_real", "latent"])
+def test_bernoulli_golden(golden, case, dn):
+    g = golden("bernoulli_logpmf")
+    p = "%s_%s_" % (case, dn)
+    x, probs, up = g[p + "x"], g[p + "probs"], g[p + "g"]
+    K, M, E = probs.shape if case != "latent" else x.shape
+    rt = 1e-5 if dn == "f32" else 1e-11
+    xm, pm = mode_of(x, K, M * E), mode_of(probs, K, M * E)
+    out = be.bernoulli_logpmf_fwd(dev(x), xm, dev(probs), pm, K, M, E)
+    close(host(out), g[p + "out"], rt)
+    _, dprobs = be.bernoulli_logpmf_bwd(dev(up), dev(x), xm, dev(probs), pm, K, M, E, False, True)
+    close(host(dprobs), g[p + "dprobs"], rt)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,M,E,xm,pm,binary", [
+    (50, 64, 784, KBCAST, FULL, True),     # likelihood at cfg-2 row size
+    (50, 64, 784, KBCAST, FULL, False),    # real-valued pixels
+    (50, 256, 40, FULL, KBCAST, True),     # Bernoulli latents (cfg 3)
+    (5, 9, 13, FULL, FULL, True),          # ragged
+    (1, 128, 784, FULL, FULL, True),       # cfg 1
+    (4, 100, 1, FULL, FULL, True),
+])
+def test_bernoulli_oracle(oracle, dt, K, M, E, xm, pm, binary):
+    rng = np.random.RandomState(3)
+    shp = {FULL: (K, M, E), KBCAST: (M, E)}
+    probs = (1 / (1 + np.exp(-2 * rng.standard_normal(shp[pm])))).astype(dt)
+    probs.reshape(-1)[:4] = [0.0, 1.0, 1e-9, 1 - 1e-7]
+    x = rng.uniform(size=shp[xm])
+    x = ((x < 0.5) if binary else x).astype(dt)
+    up = rng.standard_normal((K, M)).astype(dt)
+    out = be.bernoulli_logpmf_fwd(dev(x), xm, dev(probs), pm, K, M, E)
+    close(host(out), oracle.bernoulli_logpmf_fwd(x, probs, K, M, E), rtol_of(dt))
+    dx, dprobs = be.bernoulli_logpmf_bwd(dev(up), dev(x), xm, dev(probs), pm, K, M, E, xm == FULL, True)
+    odx, odp = oracle.bernoulli_logpmf_bwd(up.astype(np.float64), x.astype(np.float64), probs.astype(np.float64), K,
+                                           M, E, need_dx=True)
+    close(host(dprobs), odp, rtol_of(dt))
+    if xm == FULL:
+        close(host(dx), odx, 3e-5 if dt == np.float32 else 1e-11)  # log via MUFU: abs err 2^-22 near 1
+
+
+def test_bernoulli_sample(oracle):
+    from scipy import stats
+    K, N = 50, 4096
+    probs = np.random.RandomState(4).uniform(size=N).astype(np.float32)
+    probs[:3] = [0.0, 1.0, 0.5]
+    u = np.random.RandomState(5).uniform(size=(K, N)).astype(np.float32)
+    got = be.bernoulli_sample(dev(probs), KBCAST, K, N, u_in=dev(u))
+    assert np.array_equal(host(got), oracle.bernoulli_sample(probs, u, K, N))  # bit-exact
+    s = host(be.bernoulli_sample(dev(probs), KBCAST, 2000, N, seed=9, offset=12))
+    assert set(np.unique(s)) <= {0.0, 1.0} and s.dtype == np.float32
+    assert s[:, 0].sum() == 0 and s[:, 1].sum() == 2000
+    z = (s.mean(0) - probs)[3:] / np.sqrt(probs[3:] * (1 - probs[3:]) / 2000 + 1e-12)
+    assert np.abs(z).max() < 5.5 and abs(z.mean()) < 0.1 and abs(z.std() - 1) < 0.1
+    # uniforms match the oracle's Philox stream exactly
+    uu = oracle.philox_uniform(N, 9, 12)
+    assert np.array_equal(s[0], (uu < probs).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- objectives
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("shape", ["kb", "k50", "k1d", "dominant"])
+@pytest.mark.parametrize("est", ["sgvb", "vimco"])
+def test_iw_objective_golden(oracle, golden, shape, est, dn):
+    g = golden("objectives")
+    p = "%s_%s_%s_" % (shape, est, dn)
+    logp, logq = g[p + "logp"], g[p + "logq"]
+    lp2, lq2 = (logp[:, None], logq[:, None]) if logp.ndim == 1 else (logp, logq)
+    K, B = lp2.shape
+    code = be.SGVB if est == "sgvb" else be.VIMCO
+    cost, dlp, dlq = be.iw_objective(code, dev(lp2), dev(lq2), 1.0 / B)
+    rt = 1e-5 if dn == "f32" else 1e-11
+    close(host(cost).mean(), g[p + "loss"], rt)
+    if est == "sgvb":
+        close(host(cost).reshape(g[p + "cost"].shape), g[p + "cost"], rt)
+        close(host(dlp).reshape(logp.shape), g[p + "dlogp"], rt)
+        close(host(dlq).reshape(logp.shape), g[p + "dlogq"], rt)
+    else:
+        # fp32 VIMCO: the reference forms the learning signal as L - control_variate, a difference of
+        # two O(100) numbers, so ITS fp32 gradients carry ~1e-4 relative noise.  The kernel forms the
+        # same quantity without that cancellation; it must match the float64 reference run on the same
+        # inputs to 1e-5, and sit at least as close to it as the fp32 reference does.
+        g64 = {k: g[p.replace("f32", "f64") + k] for k in ("dlogp", "dlogq")}
+        close(host(dlp).reshape(logp.shape), g64["dlogp"], rt)
+        close(host(dlq).reshape(logp.shape), g64["dlogq"], rt)
+        if dn == "f32":
+            err_ours = np.abs(host(dlq).reshape(logp.shape) - g64["dlogq"]).max()
+            err_ref = np.abs(g[p + "dlogq"].astype(np.float64) - g64["dlogq"]).max()
+            assert err_ours <= err_ref + 1e-9
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,B", [(50, 1024), (2, 5), (10000, 1), (64, 100), (33, 31), (1000, 3)])
+@pytest.mark.parametrize("est", ["sgvb", "vimco"])
+def test_iw_objective_oracle(oracle, dt, K, B, est):
+    rng = np.random.RandomState(6)
+    logp = (-540 + 12 * rng.standard_normal((K, B))).astype(dt)
+    logq = (30 + 4 * rng.standard_normal((K, B))).astype(dt)
+    if B > 2:
+        logp[K // 2, 1] += 200  # a dominant particle
+        logp[:, 2] = logp[0, 2]  # ties
+        logq[:, 2] = logq[0, 2]
+    code = be.SGVB if est == "sgvb" else be.VIMCO
+    cost, dlp, dlq = be.iw_objective(code, dev(logp), dev(logq), 1.0 / B)
+    ocode = oracle.SGVB if est == "sgvb" else oracle.VIMCO
+    oc, olp, olq = oracle.iw_objective(ocode, logp.astype(np.float64), logq.astype(np.float64))
+    rt = rtol_of(dt)
+    close(host(cost), oc, rt)
+    close(host(dlp), olp, rt)
+    close(host(dlq), olq, rt)
+
+
+def test_iw_objective_extra_term(oracle):
+    rng = np.random.RandomState(7)
+    K, B = 20, 17
+    a, b, c = [rng.standard_normal((K, B)).astype(np.float32) * 5 for _ in range(3)]
+    for code in (be.SGVB, be.VIMCO):
+        c1 = be.iw_objective(code, dev(a), dev(b), 1.0, extra=dev(c))
+        c2 = be.iw_objective(code, dev(a + c), dev(b), 1.0)
+        for u, v in zip(c1, c2):
+            close(host(u), host(v), 2e-6)
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("shape", ["kb", "k50", "dominant"])
+def test_log_mean_exp(golden, shape, dn):
+    g = golden("objectives")
+    p = "%s_lme_%s_" % (shape, dn)
+    x = dev(g[p + "x"])
+    rt = 1e-5 if dn == "f32" else 1e-11
+    close(host(be.log_mean_exp(x)), g[p + "out"], rt)
+    close(host(be.log_mean_exp_bwd(torch.ones(x.shape[1], dtype=x.dtype, device=DEV), x)), g[p + "dx"], rt)
+
+
+# ----------------------------------------------------------------------------- fused resident-column kernel
+def _fused_inputs(K, B, X, binary=True, seed=8):
+    rng = np.random.RandomState(seed)
+    probs = (1 / (1 + np.exp(-2 * rng.standard_normal((K, B, X))))).astype(np.float32)
+    probs.reshape(-1)[:4] = [0.0, 1.0, 1e-9, 1 - 1e-7]
+    x = rng.uniform(size=(B, X))
+    x = ((x < 0.5) if binary else x).astype(np.float32)
+    other = (-55 + 5 * rng.standard_normal((K, B))).astype(np.float32)
+    logq = (30 + 4 * rng.standard_normal((K, B))).astype(np.float32)
+    return probs, x, other, logq
+
+
+@pytest.mark.parametrize("K,B,X", [(50, 64, 784), (8, 3, 16), (25, 300, 100), (64, 150, 784), (10, 1, 4),
+                                    (16, 149, 128)])
+@pytest.mark.parametrize("est", ["sgvb", "vimco"])
+@pytest.mark.parametrize("binary", [True, False])
+def test_fused_vs_oracle(oracle, K, B, X, est, binary):
+    probs, x, other, logq = _fused_inputs(K, B, X, binary)
+    code = be.SGVB if est == "sgvb" else be.VIMCO
+    r = be.iw_bernoulli_fused(code, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B, want_logpx=True)
+    assert r is not None, "fused kernel refused a supported shape"
+    ocode = oracle.SGVB if est == "sgvb" else oracle.VIMCO
+    # stage-wise yard-stick: float64 oracle on the same fp32 inputs
+    o = oracle.iw_bernoulli_step(ocode, probs.astype(np.float64), x.astype(np.float64), other.astype(np.float64),
+                                 logq.astype(np.float64))
+    close(host(r["logpx"]), o["logpx"], 1e-5, "logpx")
+    close(host(r["cost"]).mean(), o["cost"].mean(), 1e-5, "loss")
+    # Gradients depend on the fp32 log-weights through exp(): |logpx| ~ 500 has ulp 6e-5, so weights
+    # computed from ANY fp32 logpx (the reference's included) carry ~1e-4 relative noise
+    # (SURVEY.md §8c tolerance budget).  Compare against the oracle fed the kernel's own logpx.
+    lpx = host(r["logpx"]).astype(np.float64)
+    oc, olp, olq = oracle.iw_objective(ocode, lpx + other.astype(np.float64), logq.astype(np.float64))
+    close(host(r["cost"]), oc, 1e-5, "cost")
+    close(host(r["dlogp"]), olp, 1e-5, "dlogp")
+    close(host(r["dlogq"]), olq, 1e-5, "dlogq")
+    odp = oracle.bernoulli_logpmf_bwd(olp, x.astype(np.float64), probs.astype(np.float64), K, B, X)
+    close(host(r["dprobs"]), odp, 1e-5, "dprobs")
+    # and end to end against the all-float64 run, at the budget the reference's own fp32 meets
+    close(host(r["dprobs"]), o["dprobs"], 3e-4, "dprobs e2e")
+
+
+def test_fused_golden_path(golden):
+    """The reference's own IW step (K=6 < 8 falls to the two-pass kernels; K is tiled up to 12 here)."""
+    g = golden("iw_path")
+    probs, x = g["probs"].astype(np.float32), g["x"].astype(np.float32)
+    p = "sgvb_normal_f32_"
+    K, B, X = probs.shape
+    # duplicating every particle leaves loss unchanged and halves each particle's gradient
+    probs2 = np.concatenate([probs, probs], 0)
+    other2 = np.concatenate([g[p + "logpz"]] * 2, 0).astype(np.float32)
+    logq2 = np.concatenate([g[p + "logq"]] * 2, 0).astype(np.float32)
+    r = be.iw_bernoulli_fused(be.SGVB, dev(probs2), dev(x), dev(other2), dev(logq2), 1.0 / B)
+    assert r is not None
+    close(host(r["cost"]).mean(), g[p + "loss"], 1e-5)
+    close(2 * host(r["dprobs"])[:K], g[p + "dprobs"], 1e-4)
+
+
+def test_fused_full_size_properties(oracle):
+    """BASELINE config 2 size (K=50, B=1024, X=784): fused == two-pass kernels == oracle."""
+    K, B, X = 50, 1024, 784
+    probs, x, other, logq = _fused_inputs(K, B, X, True, seed=9)
+    dp, dx, do, dq = dev(probs), dev(x), dev(other), dev(logq)
+    for code, ocode in ((be.SGVB, oracle.SGVB), (be.VIMCO, oracle.VIMCO)):
+        r = be.iw_bernoulli_fused(code, dp, dx, do, dq, 1.0 / B, want_logpx=True)
+        assert r is not None
+        lpx = be.bernoulli_logpmf_fwd(dx, KBCAST, dp, FULL, K, B, X)
+        torch.testing.assert_close(r["logpx"], lpx, rtol=2e-6, atol=1e-3)
+        cost, dlp, dlq = be.iw_objective(code, r["logpx"], dq, 1.0 / B, extra=do)
+        torch.testing.assert_close(r["cost"], cost, rtol=1e-5, atol=1e-3)
+        torch.testing.assert_close(r["dlogp"], dlp, rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(r["dlogq"], dlq, rtol=1e-5, atol=1e-9)
+        _, dprobs = be.bernoulli_logpmf_bwd(dlp, dx, KBCAST, dp, FULL, K, B, X, False, True)
+        torch.testing.assert_close(r["dprobs"], dprobs, rtol=1e-5, atol=1e-9)
+        # size-independent properties: softmax weights sum to one per column, cost is finite
+        assert torch.allclose(-r["dlogp"].sum(0) * B, torch.ones(B, device=DEV), atol=1e-5)
+        assert torch.isfinite(r["cost"]).all() and torch.isfinite(r["dprobs"]).all()
+        o = oracle.iw_bernoulli_step(ocode, probs, x, other, logq)
+        close(host(r["cost"]).mean(), o["cost"].mean(), 1e-5)
+        close(host(r["logpx"]), o["logpx"], 1e-5)
+
+
+def test_fused_invalid_probs_give_nan():
+    K, B, X = 8, 2, 16
+    probs, x, other, logq = _fused_inputs(K, B, X)
+    probs[3, 1, 5] = 1.5
+    r = be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), dev(other), dev(logq), 1.0, want_logpx=True)
+    lp = host(r["logpx"])
+    assert np.isnan(lp[3, 1]) and np.isfinite(np.delete(lp.ravel(), 3 * B + 1)).all()
+
+
+def test_fused_unsupported_shapes_return_none():
+    probs, x, other, logq = _fused_inputs(4, 3, 16)
+    assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # K < 8
+    probs, x, other, logq = _fused_inputs(8, 3, 18)
+    assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # X % 4
+    probs, x, other, logq = _fused_inputs(100, 2, 784)
+    assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # does not fit smem
+
+
+def test_iw_step_host(oracle):
+    K, B, X = 50, 96, 784
+    probs, x, other, logq = _fused_inputs(K, B, X)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    hp, hx, ho, hq = pin(probs), pin(x), pin(other), pin(logq)
+    cost = torch.empty(B).pin_memory()
+    dprobs = torch.empty(K, B, X).pin_memory()
+    dlp, dlq = torch.empty(K, B).pin_memory(), torch.empty(K, B).pin_memory()
+    ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
+    for code, ocode in ((be.SGVB, oracle.SGVB), (be.VIMCO, oracle.VIMCO)):
+        be.iw_step_host(code, cost, dprobs, dlp, dlq, hp, hx, ho, hq, K, B, X, 1.0 / B, ws)
+        r = be.iw_bernoulli_fused(code, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B)
+        assert np.array_equal(cost.numpy(), host(r["cost"]))
+        assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
+        assert np.array_equal(dlq.numpy(), host(r["dlogq"]))
+    # a shape the fused kernel refuses goes through the two-pass kernels
+    K, B, X = 5, 7, 18
+    probs, x, other, logq = _fused_inputs(K, B, X)
+    cost = torch.empty(B).pin_memory()
+    dprobs = torch.empty(K, B, X).pin_memory()
+    ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
+    be.iw_step_host(be.VIMCO, cost, dprobs, None, None, pin(probs), pin(x), pin(other), pin(logq), K, B, X, 1.0 / B, ws)
+    o = oracle.iw_bernoulli_step(oracle.VIMCO, probs.astype(np.float64), x.astype(np.float64),
+                                 other.astype(np.float64), logq.astype(np.float64))
+    close(cost.numpy(), o["cost"], 1e-5)
+    close(dprobs.numpy(), o["dprobs"], 1e-4)
+
+
+# ----------------------------------------------------------------------------- SG-MCMC
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [4710000 // 10, 1027, 3])
+def test_sgmcmc_injected(oracle, dt, n):
+    rng = np.random.RandomState(10)
+    w, g, v = [rng.standard_normal(n).astype(dt) for _ in range(3)]
+    noise = (0.1 * rng.standard_normal(n)).astype(dt)
+    unit = rng.standard_normal(n).astype(dt)
+    rt = 1e-6 if dt == np.float32 else 1e-13
+    lr = 0.01
+    wd = dev(w)
+    w1 = be.sgld_step(wd, dev(g), lr, noise=dev(noise))
+    close(host(w1), oracle.sgld_step(w, g, noise, lr), rt)
+    assert np.array_equal(host(wd), w)  # out of place by default ...
+    be.sgld_step(wd, dev(g), lr, noise=dev(noise), out=wd)  # ... and in place on request
+    assert torch.equal(wd, w1)
+
+    wd, ad = dev(w), dev(np.abs(v))
+    w1 = be.psgld_step(wd, ad, dev(g), lr, 0.9, 1e-3, noise_unit=dev(unit))
+    ow, oa = oracle.psgld_step(w, np.abs(v), g, unit, lr)
+    close(host(w1), ow, rt * 10)
+    close(host(ad), oa, rt * 10)
+
+    for second in (False, True):
+        for resample in (False, True):
+            wd, vd = dev(w), dev(v)
+            w1 = be.sghmc_pre(wd, vd, lr, resample, second, v_noise=dev(noise) if resample else None)
+            ow, ov = oracle.sghmc_pre(w, v, noise, resample, second)
+            close(host(w1), ow, rt)
+            close(host(vd), ov, rt)
+            w2 = be.sghmc_post(w1, vd, dev(g), lr, 0.3, 0.02, second, noise=dev(noise))
+            ow, ov = oracle.sghmc_post(ow, ov, g, noise, lr, 0.3, second)
+            close(host(w2), ow, rt)
+            close(host(vd), ov, rt)
+
+
+@pytest.mark.parametrize("name", ["sgld", "psgld", "sghmc1", "sghmc2"])
+def test_sgmcmc_golden_trajectories(golden, name):
+    """The reference's samplers stepped 4 times with recorded noise (tests/golden/make_golden.py)."""
+    from test_oracle_golden import _replay_sgmcmc
+
+    class GpuSteps:
+        @staticmethod
+        def sgld_step(w, g, noise, lr):
+            return host(be.sgld_step(dev(w), dev(g), lr, noise=dev(noise)))
+
+        @staticmethod
+        def psgld_step(w, aux, g, unit, lr):
+            ad = dev(aux)
+            w1 = be.psgld_step(dev(w), ad, dev(g), lr, 0.9, 1e-3, noise_unit=dev(unit))
+            return host(w1), host(ad)
+
+        @staticmethod
+        def sghmc_pre(w, v, v_noise, resample, second):
+            vd = dev(v)
+            w1 = be.sghmc_pre(dev(w), vd, 0.01, resample, second, v_noise=None if v_noise is None else dev(v_noise))
+            return host(w1), host(vd)
+
+        @staticmethod
+        def sghmc_post(w, v, g, noise, lr, alpha, second):
+            vd = dev(v)
+            w1 = be.sghmc_post(dev(w), vd, dev(g), lr, alpha, 0.02, second, noise=dev(noise))
+            return host(w1), host(vd)
+
+    g = golden("sgmcmc")
+    traj = _replay_sgmcmc(GpuSteps, g, name)
+    np.testing.assert_allclose(traj, g[name + "_f32_traj"], rtol=2e-5, atol=2e-6)
+
+
+def test_sgmcmc_philox_noise_statistics():
+    from scipy import stats
+    n, lr = 1 << 20, 0.01
+    w = torch.zeros(n, device=DEV)
+    e = host(be.sgld_step(w, torch.zeros(n, device=DEV), lr, seed=5, offset=16))
+    assert abs(e.mean()) < 5e-4 and abs(e.std() / np.sqrt(lr) - 1) < 5e-3
+    assert stats.kstest(e[::5] / np.sqrt(lr), "norm").pvalue > 1e-3
+    # velocity resample + noise of SGHMC
+    w, v = torch.zeros(n, device=DEV), torch.ones(n, device=DEV)
+    be.sghmc_pre(w, v, lr, True, False, seed=5, offset=20)
+    assert abs(host(v).std() / np.sqrt(lr) - 1) < 5e-3
+    v0 = v.clone()
+    w1 = be.sghmc_post(w, v, torch.zeros(n, device=DEV), lr, 0.3, 0.02, False, seed=5, offset=24)
+    inj = host(v - (1 - 0.3) * v0)
+    assert abs(inj.std() / np.sqrt(2 * (0.3 - 0.02) * lr) - 1) < 5e-3
+    assert torch.equal(w1, v)
+
+
+def test_scale_inplace():
+    buf = torch.randn(1000003, device=DEV)
+    ref = buf.clone()
+    be.scale_inplace(buf, torch.ones(1, device=DEV))
+    assert torch.equal(buf, ref)
+    be.scale_inplace(buf, torch.full((1,), 0.25, device=DEV))
+    assert torch.equal(buf, ref * 0.25)
+
+
+# ----------------------------------------------------------------------------- Categorical (parity unpinned)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,M,C,lm", [(5, 33, 10, KBCAST), (4, 20, 100, FULL), (50, 64, 7, KBCAST), (1, 9, 3, FULL)])
+def test_categorical(oracle, dt, K, M, C, lm):
+    rng = np.random.RandomState(11)
+    logits = (2 * rng.standard_normal((K, M, C) if lm == FULL else (M, C))).astype(dt)
+    x = rng.randint(0, C, size=(K, M)).astype(dt)
+    up = rng.standard_normal((K, M)).astype(dt)
+    out = be.categorical_logpmf_fwd(dev(x), FULL, dev(logits), lm, K, M, C)
+    close(host(out), oracle.categorical_logpmf_fwd(x, logits, K, M, C), rtol_of(dt))
+    d = be.categorical_logpmf_bwd(dev(up), dev(x), FULL, dev(logits), lm, K, M, C)
+    close(host(d), oracle.categorical_logpmf_bwd(up.astype(np.float64), x.astype(np.float64),
+                                                 logits.astype(np.float64), K, M, C), rtol_of(dt))
+    u = rng.uniform(size=(K, M)).astype(dt)
+    s = be.categorical_sample(dev(logits), lm, K, M, C, u_in=dev(u))
+    so = oracle.categorical_sample(logits, u, K, M, C)
+    assert (host(s) == so).mean() > 0.999  # ties at cumulative-sum boundaries may round differently
+
+
+def test_categorical_sample_statistics():
+    M, C, K = 4, 6, 40000
+    logits = torch.randn(M, C, device=DEV)
+    s = host(be.categorical_sample(logits, KBCAST, K, M, C, seed=3, offset=28))
+    p = torch.softmax(logits, -1).cpu().numpy()
+    for m in range(M):
+        freq = np.bincount(s[:, m].astype(int), minlength=C) / K
+        assert np.abs(freq - p[m]).max() < 0.012

@@ -60,24 +60,25 @@ struct FusedSmemLayout {
     __host__ __device__ size_t rest_off() const { return lpx_off() + (size_t)2 * Kpad * 4; }
     __host__ __device__ size_t lq_off() const { return rest_off() + (size_t)Kpad * 4; }
     __host__ __device__ size_t g_off() const { return lq_off() + (size_t)Kpad * 4; }
-    __host__ __device__ size_t xw_off() const { return g_off() + (size_t)Kpad * 4; }
-    __host__ __device__ size_t bar_off() const { return (xw_off() + (size_t)Kpad * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xw_off() const { return (g_off() + (size_t)Kpad * 4 + 15) & ~(size_t)15; }  // double[Kpad]
+    __host__ __device__ size_t bar_off() const { return (xw_off() + (size_t)Kpad * 8 + 15) & ~(size_t)15; }
     __host__ __device__ size_t total() const { return bar_off() + (size_t)(K + 2) * 8; }
 };
 
 // One warp turns the K log-weights of a column into cost, weights and gradients (all in smem/regs).
+// As in k_iw_objective, log w and its centring are carried in double (K values: negligible work).
 template <int EST>
 __device__ __forceinline__ void warp_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
-                                               const float* s_rest, const float* s_lq, float* s_xw, float* s_g,
+                                               const float* s_other, const float* s_lq, double* s_xw, float* s_g,
                                                float gscale, float* __restrict__ cost, float* __restrict__ dlogp,
                                                float* __restrict__ dlogq, float* __restrict__ logpx_out) {
     const unsigned FULL = 0xffffffffu;
-    float m1 = -INFINITY, m2 = -INFINITY, sumx = 0.f;
+    double m1 = -INFINITY, m2 = -INFINITY, sumd = 0.0;
     int i1 = -1;
     for (int k = lane; k < K; k += 32) {
-        float xv = s_lpx[k] + s_rest[k];
+        // same association as k_iw_objective: (logp - logq) + extra
+        double xv = ((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k];
         s_xw[k] = xv;
-        sumx += xv;
         if (xv > m1 || i1 < 0) {
             m2 = m1; m1 = xv; i1 = k;
         } else if (xv > m2) {
@@ -86,45 +87,51 @@ __device__ __forceinline__ void warp_objective(int lane, int K, int64_t B, int64
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        float om1 = __shfl_xor_sync(FULL, m1, o), om2 = __shfl_xor_sync(FULL, m2, o);
+        double om1 = __shfl_xor_sync(FULL, m1, o), om2 = __shfl_xor_sync(FULL, m2, o);
         int oi1 = __shfl_xor_sync(FULL, i1, o);
         bool other = (oi1 >= 0) && (i1 < 0 || om1 > m1 || (om1 == m1 && oi1 < i1));
-        float loser = other ? m1 : om1;
-        m2 = fmaxf(loser, fmaxf(m2, om2));
+        double loser = other ? m1 : om1;
+        m2 = fmax(loser, fmax(m2, om2));
         m1 = other ? om1 : m1;
         i1 = other ? oi1 : i1;
     }
-    if (EST == ZS_EST_VIMCO) sumx = warp_sum(sumx);
+    const float gap = (float)(m1 - m2);
 
     float S = 0.f, S2 = 0.f;
     for (int k = lane; k < K; k += 32) {
-        float xv = s_xw[k];
-        S += expf(xv - m1);
-        if (EST == ZS_EST_VIMCO && k != i1) S2 += expf(xv - m2);
+        double xv = s_xw[k];
+        S += expf((float)(xv - m1));
+        if (EST == ZS_EST_VIMCO) {
+            sumd += xv - m1;
+            if (k != i1) S2 += expf((float)(xv - m2));
+        }
     }
     S = warp_sum(S);
-    if (EST == ZS_EST_VIMCO) S2 = warp_sum(S2);
+    if (EST == ZS_EST_VIMCO) {
+        S2 = warp_sum(S2);
+        sumd = warp_sum(sumd);
+    }
 
-    float c_acc = 0.f;
+    double c_acc = 0.0;
     const float invS = 1.0f / S;
-    const float km1 = (float)(K - 1);
+    const double km1 = (double)(K - 1);
     for (int k = lane; k < K; k += 32) {
-        const float xv = s_xw[k];
-        const float e = expf(xv - m1);
+        const double xv = s_xw[k];
+        const float e = expf((float)(xv - m1));
         const float wt = e / S;
-        c_acc -= wt * xv;
+        c_acc -= (double)wt * xv;
         float gq = wt;
         if (EST == ZS_EST_VIMCO) {
             const float lq = s_lq[k];
-            const float mu = (sumx - xv) / km1;
+            const float mu_m = (float)((sumd - (xv - m1)) / km1);
             float sig;
-            if (k == i1 && (m1 - m2) > 1.0f) {
-                float Sloo = S2 + expf(mu - m2);
-                sig = (m1 - m2) + (logf(S) - logf(Sloo));
+            if (k == i1 && gap > 1.0f) {
+                float Sloo = S2 + expf(mu_m + gap);
+                sig = gap + (logf(S) - logf(Sloo));
             } else {
-                sig = -log1pf((expf(mu - m1) - e) * invS);
+                sig = -log1pf((expf(mu_m) - e) * invS);
             }
-            c_acc -= lq * sig;
+            c_acc -= (double)lq * (double)sig;
             gq = wt - sig;
         }
         const float gp = -wt * gscale;
@@ -134,7 +141,7 @@ __device__ __forceinline__ void warp_objective(int lane, int K, int64_t B, int64
         if (logpx_out) logpx_out[(int64_t)k * B + b] = s_lpx[k];
     }
     c_acc = warp_sum(c_acc);
-    if (lane == 0 && cost) cost[b] = c_acc;
+    if (lane == 0 && cost) cost[b] = (float)c_acc;
 }
 
 template <int EST>
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(1024, 1)
     float* s_rest = reinterpret_cast<float*>(smem + L.rest_off());
     float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
     float* s_g = reinterpret_cast<float*>(smem + L.g_off());
-    float* s_xw = reinterpret_cast<float*>(smem + L.xw_off());
+    double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
     uint64_t* bar_row = reinterpret_cast<uint64_t*>(smem + L.bar_off());
     uint64_t* bar_x = bar_row + K;
 
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(1024, 1)
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
             float o = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
             float q = logq ? logq[(int64_t)k * B + b] : 0.f;
-            s_rest[k] = o - q;
+            s_rest[k] = o;
             s_lq[k] = q;
         }
 

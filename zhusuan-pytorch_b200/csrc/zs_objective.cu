@@ -43,25 +43,31 @@ struct Top2 {
     long long i1;
 };
 
+// Log-weights are formed and centred in double: |log w| is O(100-1000), where fp32 has an ulp of
+// ~6e-5 that exp() would turn into ~1e-4 relative noise on every weight (the reference's own fp32
+// noise floor).  Only the small centred difference is rounded to T before exp().
 template <typename T, int EST>
 __global__ void __launch_bounds__(OBJ_THREADS)
     k_iw_objective(T* __restrict__ cost, T* __restrict__ dlogp, T* __restrict__ dlogq, const T* __restrict__ logp,
                    const T* __restrict__ logq, const T* __restrict__ extra, int64_t K, int64_t B, T gscale, int cols,
                    int slices) {
+    using A = double;
     extern __shared__ unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw);               // [slices*cols]
+    A* sm = reinterpret_cast<A*>(smem_raw);                           // [slices*cols]
     long long* smi = reinterpret_cast<long long*>(sm + OBJ_THREADS);  // [slices*cols]
     const int64_t b = (int64_t)blockIdx.x * cols + threadIdx.x;
     const bool valid = b < B;
-    const T NEG_INF = -INFINITY;
+    const A NEG_INF = -INFINITY;
+    auto logw = [&](int64_t k) -> A {
+        return ((A)logp[k * B + b] - (A)logq[k * B + b]) + (extra ? (A)extra[k * B + b] : A(0));
+    };
 
-    // pass 1: max (and, for VIMCO, second max excluding the first argmax, and sum of x)
-    T m1 = NEG_INF, m2 = NEG_INF, sumx = T(0);
+    // pass 1: max (and, for VIMCO, second max excluding the first argmax)
+    A m1 = NEG_INF, m2 = NEG_INF, sumd = A(0);
     long long i1 = -1;
     if (valid) {
         for (int64_t k = threadIdx.y; k < K; k += slices) {
-            T x = logp[k * B + b] - logq[k * B + b] + (extra ? extra[k * B + b] : T(0));
-            if (EST == ZS_EST_VIMCO) sumx += x;
+            A x = logw(k);
             if (x > m1 || i1 < 0) {
                 m2 = m1;
                 m1 = x;
@@ -76,10 +82,10 @@ __global__ void __launch_bounds__(OBJ_THREADS)
         sm[threadIdx.y * cols + threadIdx.x] = m1;
         smi[threadIdx.y * cols + threadIdx.x] = i1;
         __syncthreads();
-        T gm = NEG_INF;
+        A gm = NEG_INF;
         long long gi = -1;
         for (int s = 0; s < slices; ++s) {
-            T v = sm[s * cols + threadIdx.x];
+            A v = sm[s * cols + threadIdx.x];
             long long vi = smi[s * cols + threadIdx.x];
             if (vi >= 0 && (gi < 0 || v > gm || (v == gm && vi < gi))) {
                 gm = v;
@@ -89,58 +95,67 @@ __global__ void __launch_bounds__(OBJ_THREADS)
         __syncthreads();
         if (EST == ZS_EST_VIMCO) {
             // second max = max over all elements except index gi
-            T cand = (i1 == gi) ? m2 : m1;
-            m2 = slice_reduce(cand, sm, cols, slices, [](T a, T c) { return a > c ? a : c; });
-            sumx = slice_reduce(sumx, sm, cols, slices, [](T a, T c) { return a + c; });
+            A cand = (i1 == gi) ? m2 : m1;
+            m2 = slice_reduce(cand, sm, cols, slices, [](A a, A c) { return a > c ? a : c; });
         }
         m1 = gm;
         i1 = gi;
     }
+    const T gap = (T)(m1 - m2);
 
-    // pass 2: S = sum exp(x - m) ; VIMCO also S2 = sum_{k != argmax} exp(x - m2)
-    T S = T(0), S2 = T(0);
+    // pass 2: S = sum exp(x - m) ; VIMCO also S2 = sum_{k != argmax} exp(x - m2) and sum (x - m):
+    // the leave-one-out mean is only ever needed relative to m, and summing the centred values
+    // keeps its rounding error ~|spread|*eps instead of ~K*|log w|*eps
+    A S_a = A(0), S2_a = A(0);
     if (valid) {
         for (int64_t k = threadIdx.y; k < K; k += slices) {
-            T x = logp[k * B + b] - logq[k * B + b] + (extra ? extra[k * B + b] : T(0));
-            S += Real<T>::exp(x - m1);
-            if (EST == ZS_EST_VIMCO && k != i1) S2 += Real<T>::exp(x - m2);
+            A x = logw(k);
+            S_a += (A)Real<T>::exp((T)(x - m1));
+            if (EST == ZS_EST_VIMCO) {
+                sumd += x - m1;
+                if (k != i1) S2_a += (A)Real<T>::exp((T)(x - m2));
+            }
         }
     }
-    S = slice_reduce(S, sm, cols, slices, [](T a, T c) { return a + c; });
-    if (EST == ZS_EST_VIMCO) S2 = slice_reduce(S2, sm, cols, slices, [](T a, T c) { return a + c; });
+    const T S = (T)slice_reduce(S_a, sm, cols, slices, [](A a, A c) { return a + c; });
+    T S2 = T(0);
+    if (EST == ZS_EST_VIMCO) {
+        S2 = (T)slice_reduce(S2_a, sm, cols, slices, [](A a, A c) { return a + c; });
+        sumd = slice_reduce(sumd, sm, cols, slices, [](A a, A c) { return a + c; });
+    }
 
     // pass 3: weights, learning signal, cost and gradients
-    T c_acc = T(0);
+    A c_acc = A(0);
     if (valid) {
         const T invS = T(1) / S;
-        const T km1 = (T)(K - 1);
+        const A km1 = (A)(K - 1);
         for (int64_t k = threadIdx.y; k < K; k += slices) {
             const T lq = logq[k * B + b];
-            const T x = logp[k * B + b] - lq + (extra ? extra[k * B + b] : T(0));
-            const T e = Real<T>::exp(x - m1);
+            const A x = logw(k);
+            const T e = Real<T>::exp((T)(x - m1));
             const T wt = e / S;
-            c_acc -= wt * x;
+            c_acc -= (A)wt * x;
             T gq = wt;
             if (EST == ZS_EST_VIMCO) {
-                const T mu = (sumx - x) / km1;
+                const T mu_m = (T)((sumd - (x - m1)) / km1);  // LOO mean of log w, minus m
                 T sig;
-                if (k == i1 && (m1 - m2) > T(1)) {
+                if (k == i1 && gap > T(1)) {
                     // the arg-max row: S - e would cancel, re-centre on the second max
-                    T Sloo = S2 + Real<T>::exp(mu - m2);
-                    sig = (m1 - m2) + (Real<T>::log(S) - Real<T>::log(Sloo));
+                    T Sloo = S2 + Real<T>::exp(mu_m + gap);
+                    sig = gap + (Real<T>::log(S) - Real<T>::log(Sloo));
                 } else {
-                    T t = (Real<T>::exp(mu - m1) - e) * invS;
+                    T t = (Real<T>::exp(mu_m) - e) * invS;
                     sig = -log1p(t);
                 }
-                c_acc -= lq * sig;
+                c_acc -= (A)lq * (A)sig;
                 gq = wt - sig;
             }
             if (dlogp) dlogp[k * B + b] = -wt * gscale;
             if (dlogq) dlogq[k * B + b] = gq * gscale;
         }
     }
-    c_acc = slice_reduce(c_acc, sm, cols, slices, [](T a, T c) { return a + c; });
-    if (valid && threadIdx.y == 0 && cost) cost[b] = c_acc;
+    c_acc = slice_reduce(c_acc, sm, cols, slices, [](A a, A c) { return a + c; });
+    if (valid && threadIdx.y == 0 && cost) cost[b] = (T)c_acc;
 }
 
 template <typename T, bool BWD>
@@ -166,6 +181,25 @@ __global__ void __launch_bounds__(OBJ_THREADS)
         const T gb = g[b];
         for (int64_t k = threadIdx.y; k < K; k += slices) out[k * B + b] = gb * (Real<T>::exp(x[k * B + b] - m) / S);
     }
+}
+
+// buf *= *scale, skipped entirely when *scale == 1 (the usual loss.backward() case): lets a fused
+// forward+backward kernel hand out gradients computed for a unit upstream gradient without a host
+// sync and without a second pass over them.
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ buf, int64_t n, const T* __restrict__ scale) {
+    const T s = *scale;
+    if (s == T(1)) return;
+    constexpr int VN = Pack<T>::N;
+    const int64_t nv = n / VN;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
+        Pack<T> p = ld_pack(buf + v * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) p.v[j] *= s;
+        st_pack(buf + v * VN, p);
+    }
+    for (int64_t i = nv * VN + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= s;
 }
 
 static void column_geometry(int64_t B, int& cols, int& slices) {
@@ -194,7 +228,7 @@ int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlo
     ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
     cudaStream_t st = as_stream(stream);
     if (dtype == ZS_F32) {
-        const size_t smem = OBJ_THREADS * (sizeof(float) + sizeof(long long));
+        const size_t smem = OBJ_THREADS * (sizeof(double) + sizeof(long long));
         if (estimator == ZS_EST_SGVB)
             k_iw_objective<float, ZS_EST_SGVB><<<(unsigned)grid, block, smem, st>>>(
                 (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
@@ -252,6 +286,23 @@ static int lme_launch(int dtype, bool bwd, void* out, const void* g, const void*
         return ZS_ERR_DTYPE;
     }
     ZS_LAUNCH_CHECK("k_log_mean_exp");
+    return ZS_OK;
+}
+
+int zs_scale_inplace(int dtype, void* buf, int64_t n, const void* scale_dev, zs_stream_t stream) {
+    ZS_REQUIRE(buf && scale_dev && n >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(aligned16(buf), ZS_ERR_ALIGN);
+    if (n == 0) return ZS_OK;
+    const int grid = grid_for(n / 4 + 1, 256, 8);
+    if (dtype == ZS_F32)
+        k_scale_inplace<float><<<grid, 256, 0, as_stream(stream)>>>((float*)buf, n, (const float*)scale_dev);
+    else if (dtype == ZS_F64)
+        k_scale_inplace<double><<<grid, 256, 0, as_stream(stream)>>>((double*)buf, n, (const double*)scale_dev);
+    else {
+        set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+        return ZS_ERR_DTYPE;
+    }
+    ZS_LAUNCH_CHECK("k_scale_inplace");
     return ZS_OK;
 }
 

@@ -1,4 +1,4 @@
-// SG-MCMC parameter updates across parallel chains: one fused, in-place pass per update with the
+// SG-MCMC parameter updates across parallel chains: one fused pass per update (w_out may alias w) with the
 // Gaussian term drawn in-register from Philox (or injected for parity tests).
 //
 // Replaces (reference file:line):
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) k_chain_update(Body body, int64_t n, uint
 
 template <typename T>
 struct SgldBody {
-    T* w;
+    T* wo;
+    const T* w;
     const T* g;
     const T* noise;  // already scaled, or null
     T half_lr;       // (T)(0.5f * (float)lr)
@@ -71,20 +72,21 @@ struct SgldBody {
     __device__ __forceinline__ T upd(T wv, T gv, T e) const { return (wv + half_lr * gv) + e; }
     __device__ void one(int64_t i, float xi) const {
         T e = noise ? noise[i] : (T)(std * xi);
-        w[i] = upd(w[i], g[i], e);
+        wo[i] = upd(w[i], g[i], e);
     }
     __device__ void vec(int64_t i, const float* xi) const {
         Quad<T> wv = ld4(w + i), gv = ld4(g + i), ev;
         if (noise) ev = ld4(noise + i);
 #pragma unroll
         for (int j = 0; j < 4; ++j) wv.v[j] = upd(wv.v[j], gv.v[j], noise ? ev.v[j] : (T)(std * xi[j]));
-        st4(w + i, wv);
+        st4(wo + i, wv);
     }
 };
 
 template <typename T>
 struct PsgldBody {
-    T* w;
+    T* wo;
+    const T* w;
     T* aux;
     const T* g;
     const T* unit;  // unit normals or null
@@ -99,7 +101,7 @@ struct PsgldBody {
     __device__ void one(int64_t i, float xi) const {
         T wv = w[i], av = aux[i];
         upd(wv, av, g[i], unit ? unit[i] : (T)xi);
-        w[i] = wv;
+        wo[i] = wv;
         aux[i] = av;
     }
     __device__ void vec(int64_t i, const float* xi) const {
@@ -107,14 +109,15 @@ struct PsgldBody {
         if (unit) uv = ld4(unit + i);
 #pragma unroll
         for (int j = 0; j < 4; ++j) upd(wv.v[j], av.v[j], gv.v[j], unit ? uv.v[j] : (T)xi[j]);
-        st4(w + i, wv);
+        st4(wo + i, wv);
         st4(aux + i, av);
     }
 };
 
 template <typename T>
 struct SghmcPreBody {
-    T* w;
+    T* wo;
+    const T* w;
     T* v;
     const T* v_noise;  // injected resampled velocity, or null
     float std;         // sqrt(lr)
@@ -128,7 +131,7 @@ struct SghmcPreBody {
         T wv = w[i], vv = v[i];
         upd(wv, vv, v_noise ? v_noise[i] : (T)(std * xi));
         if (resample) v[i] = vv;
-        if (second_order) w[i] = wv;
+        if (second_order) wo[i] = wv;
     }
     __device__ void vec(int64_t i, const float* xi) const {
         Quad<T> wv = ld4(w + i), vv = ld4(v + i), nv;
@@ -136,13 +139,14 @@ struct SghmcPreBody {
 #pragma unroll
         for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], v_noise ? nv.v[j] : (T)(std * xi[j]));
         if (resample) st4(v + i, vv);
-        if (second_order) st4(w + i, wv);
+        if (second_order) st4(wo + i, wv);
     }
 };
 
 template <typename T>
 struct SghmcPostBody {
-    T* w;
+    T* wo;
+    const T* w;
     T* v;
     const T* g;
     const T* noise;  // already scaled, or null
@@ -162,7 +166,7 @@ struct SghmcPostBody {
     __device__ void one(int64_t i, float xi) const {
         T wv = w[i], vv = v[i];
         upd(wv, vv, g[i], noise ? noise[i] : (T)(std * xi));
-        w[i] = wv;
+        wo[i] = wv;
         v[i] = vv;
     }
     __device__ void vec(int64_t i, const float* xi) const {
@@ -170,7 +174,7 @@ struct SghmcPostBody {
         if (noise) nv = ld4(noise + i);
 #pragma unroll
         for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], gv.v[j], noise ? nv.v[j] : (T)(std * xi[j]));
-        st4(w + i, wv);
+        st4(wo + i, wv);
         st4(v + i, vv);
     }
 };
@@ -194,35 +198,35 @@ using namespace zs;
 
 extern "C" {
 
-int zs_sgld_step(int dtype, void* w, const void* g, const void* noise, int64_t n, double lr, uint64_t seed,
-                 uint64_t offset, zs_stream_t stream) {
-    ZS_REQUIRE(w && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+int zs_sgld_step(int dtype, void* w_out, const void* w, const void* g, const void* noise, int64_t n, double lr,
+                 uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w_out && w && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
     const float lr_f = (float)lr;
     const float std = (float)sqrt((double)lr_f);
-    const bool vec = aligned16(w) && aligned16(g) && aligned16(noise);
+    const bool vec = aligned16(w_out) && aligned16(w) && aligned16(g) && aligned16(noise);
     if (dtype == ZS_F32) {
-        SgldBody<float> b{(float*)w, (const float*)g, (const float*)noise, 0.5f * lr_f, std};
+        SgldBody<float> b{(float*)w_out, (const float*)w, (const float*)g, (const float*)noise, 0.5f * lr_f, std};
         return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sgld");
     } else if (dtype == ZS_F64) {
-        SgldBody<double> b{(double*)w, (const double*)g, (const double*)noise, (double)(0.5f * lr_f), std};
+        SgldBody<double> b{(double*)w_out, (const double*)w, (const double*)g, (const double*)noise, (double)(0.5f * lr_f), std};
         return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sgld");
     }
     set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
     return ZS_ERR_DTYPE;
 }
 
-int zs_psgld_step(int dtype, void* w, void* aux, const void* g, const void* noise_unit, int64_t n, double lr,
-                  double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream) {
-    ZS_REQUIRE(w && aux && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+int zs_psgld_step(int dtype, void* w_out, const void* w, void* aux, const void* g, const void* noise_unit, int64_t n,
+                  double lr, double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w_out && w && aux && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
     const float lr_f = (float)lr;
-    const bool vec = aligned16(w) && aligned16(g) && aligned16(aux) && aligned16(noise_unit);
+    const bool vec = aligned16(w_out) && aligned16(w) && aligned16(g) && aligned16(aux) && aligned16(noise_unit);
     if (dtype == ZS_F32) {
-        PsgldBody<float> b{(float*)w,      (float*)aux,           (const float*)g, (const float*)noise_unit,
+        PsgldBody<float> b{(float*)w_out, (const float*)w,      (float*)aux,           (const float*)g, (const float*)noise_unit,
                            (float)decay,   (float)(1.0 - decay),  (float)epsilon,  lr_f,
                            0.5f * lr_f};
         return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "psgld");
     } else if (dtype == ZS_F64) {
-        PsgldBody<double> b{(double*)w, (double*)aux, (const double*)g, (const double*)noise_unit,
+        PsgldBody<double> b{(double*)w_out, (const double*)w, (double*)aux, (const double*)g, (const double*)noise_unit,
                             decay,      1.0 - decay,  epsilon,          (double)lr_f,
                             (double)(0.5f * lr_f)};
         return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "psgld");
@@ -231,36 +235,37 @@ int zs_psgld_step(int dtype, void* w, void* aux, const void* g, const void* nois
     return ZS_ERR_DTYPE;
 }
 
-int zs_sghmc_pre(int dtype, void* w, void* v, const void* v_noise, int64_t n, double lr, int resample,
-                 int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream) {
-    ZS_REQUIRE(w && v && n >= 0 && lr >= 0, ZS_ERR_ARG);
+int zs_sghmc_pre(int dtype, void* w_out, const void* w, void* v, const void* v_noise, int64_t n, double lr,
+                 int resample, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(w_out && w && v && n >= 0 && lr >= 0, ZS_ERR_ARG);
     if (!resample && !second_order) return ZS_OK;
     const float std = (float)sqrt(lr);
-    const bool vec = aligned16(w) && aligned16(v) && aligned16(v_noise);
+    const bool vec = aligned16(w_out) && aligned16(w) && aligned16(v) && aligned16(v_noise);
     if (dtype == ZS_F32) {
-        SghmcPreBody<float> b{(float*)w, (float*)v, (const float*)v_noise, std, resample, second_order};
+        SghmcPreBody<float> b{(float*)w_out, (const float*)w, (float*)v, (const float*)v_noise, std, resample, second_order};
         return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sghmc_pre");
     } else if (dtype == ZS_F64) {
-        SghmcPreBody<double> b{(double*)w, (double*)v, (const double*)v_noise, std, resample, second_order};
+        SghmcPreBody<double> b{(double*)w_out, (const double*)w, (double*)v, (const double*)v_noise, std, resample, second_order};
         return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sghmc_pre");
     }
     set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
     return ZS_ERR_DTYPE;
 }
 
-int zs_sghmc_post(int dtype, void* w, void* v, const void* g, const void* noise, int64_t n, double lr, double alpha,
-                  double beta, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream) {
-    ZS_REQUIRE(w && v && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
+int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g, const void* noise, int64_t n,
+                  double lr, double alpha, double beta, int second_order, uint64_t seed, uint64_t offset,
+                  zs_stream_t stream) {
+    ZS_REQUIRE(w_out && w && v && g && n >= 0 && lr >= 0, ZS_ERR_ARG);
     ZS_REQUIRE(alpha - beta >= 0, ZS_ERR_ARG);
     const float std = (float)sqrt(2.0 * (alpha - beta) * lr);
     const double dh = exp(-0.5 * alpha);
-    const bool vec = aligned16(w) && aligned16(v) && aligned16(g) && aligned16(noise);
+    const bool vec = aligned16(w_out) && aligned16(w) && aligned16(v) && aligned16(g) && aligned16(noise);
     if (dtype == ZS_F32) {
-        SghmcPostBody<float> b{(float*)w, (float*)v, (const float*)g, (const float*)noise, (float)(1.0 - alpha),
+        SghmcPostBody<float> b{(float*)w_out, (const float*)w, (float*)v, (const float*)g, (const float*)noise, (float)(1.0 - alpha),
                                (float)lr, (float)dh, std,             second_order};
         return launch_chain<float>(b, n, vec, seed, offset, as_stream(stream), "sghmc_post");
     } else if (dtype == ZS_F64) {
-        SghmcPostBody<double> b{(double*)w, (double*)v, (const double*)g, (const double*)noise, 1.0 - alpha,
+        SghmcPostBody<double> b{(double*)w_out, (const double*)w, (double*)v, (const double*)g, (const double*)noise, 1.0 - alpha,
                                 lr,         dh,         std,              second_order};
         return launch_chain<double>(b, n, vec, seed, offset, as_stream(stream), "sghmc_post");
     }

@@ -1,0 +1,384 @@
+"""Host-side glue between the reference-shaped Python API and the C-ABI kernels.
+
+Responsibilities (all host logic, no math):
+  * view a broadcast problem as the [K, M, E] particle-row layout of include/zs_b200.h and classify
+    every operand as FULL / KBCAST / SCALAR (what the reference does with `.repeat`, normal.py:94-95,
+    115-116; bernoulli.py:75,90);
+  * wrap each kernel pair in a torch.autograd.Function so the reference's autograd contract holds;
+  * move CPU tensors to the current CUDA device and results back to the caller's device (the
+    reference's tests feed CPU tensors); there is no CPU implementation to fall back to.
+"""
+import torch
+
+from . import _backend as be
+from . import _rng
+
+FULL, KBCAST, SCALAR = be.FULL, be.KBCAST, be.SCALAR
+
+
+def _prod(xs):
+    p = 1
+    for v in xs:
+        p *= int(v)
+    return p
+
+
+def compute_device():
+    be.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_compute(t):
+    """Differentiable move to the CUDA device the kernels run on."""
+    if t.is_cuda:
+        return t
+    return t.to(compute_device())
+
+
+def back_home(t, home):
+    return t if t.device == home else t.to(home)
+
+
+# --------------------------------------------------------------------------------------------
+# layout
+# --------------------------------------------------------------------------------------------
+class Layout(object):
+    """[K, M, E] view of the broadcast of `shapes` with the last `n_event` axes summed."""
+
+    def __init__(self, shapes, n_event):
+        S = tuple(torch.broadcast_shapes(*shapes))
+        if n_event > len(S):
+            raise ValueError("cannot reduce %d event axes of a %d-d value" % (n_event, len(S)))
+        self.S = S
+        self.lead = S[:len(S) - n_event]
+        self.E = _prod(S[len(S) - n_event:])
+        self.k_axis = len(self.lead) > 0
+        self.K = int(self.lead[0]) if self.k_axis else 1
+        self.M = _prod(self.lead[1:]) if self.k_axis else 1
+
+    def canon(self, t):
+        """Return (contiguous tensor, mode) for an operand broadcastable to S.  Differentiable."""
+        S = self.S
+        if t.numel() == 1 and _prod(S) != 1 and not t.requires_grad:
+            return t.reshape(1).contiguous(), SCALAR
+        pad = (1,) * (len(S) - t.dim()) + tuple(t.shape)
+        if pad == S:
+            return t.contiguous(), FULL
+        if self.k_axis and self.K > 1 and pad[0] == 1:
+            # broadcast over particles; any further broadcasting inside a particle is materialised
+            return t.reshape(pad[1:]).expand(S[1:]).contiguous(), KBCAST
+        return t.expand(S).contiguous(), FULL
+
+
+# --------------------------------------------------------------------------------------------
+# Normal
+# --------------------------------------------------------------------------------------------
+class _NormalLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, std, modes, K, M, E):
+        out = be.normal_logprob_fwd(x, modes[0], mean, modes[1], std, modes[2], K, M, E)
+        ctx.save_for_backward(x, mean, std)
+        ctx.cfg = (modes, K, M, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, std = ctx.saved_tensors
+        modes, K, M, E = ctx.cfg
+        nx, nm, ns = ctx.needs_input_grad[:3]
+        dx, dmean, dstd = be.normal_logprob_bwd(g.contiguous(), x, modes[0], mean, modes[1], std, modes[2], K, M, E,
+                                                nx, nm, ns)
+        return dx, dmean, dstd, None, None, None, None
+
+
+def normal_log_prob(x, mean, std, n_event):
+    """sum over the last n_event axes of the Normal log-density (normal.py:109-126 + base.py:175-176)."""
+    home = x.device
+    x, mean, std = to_compute(x), to_compute(mean), to_compute(std)
+    L = Layout([x.shape, mean.shape, std.shape], n_event)
+    if _prod(L.S) == 0:
+        return back_home(torch.zeros(L.lead, dtype=x.dtype, device=x.device), home)
+    (xc, xm), (mc, mm), (sc, sm) = L.canon(x), L.canon(mean), L.canon(std)
+    out = _NormalLogProb.apply(xc, mc, sc, (xm, mm, sm), L.K, L.M, L.E)
+    return back_home(out.reshape(L.lead), home)
+
+
+class _NormalSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, std, modes, K, N, eps_in):
+        if eps_in is not None:
+            seed, offset = 0, 0
+        else:
+            seed, offset = _rng.next_philox(mean.device)
+        z = be.normal_sample(mean, modes[0], std, modes[1], K, N, eps_in=eps_in, seed=seed, offset=offset)
+        ctx.save_for_backward(mean, std, eps_in)
+        ctx.cfg = (modes, K, N, seed, offset)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        mean, std, eps = ctx.saved_tensors
+        modes, K, N, seed, offset = ctx.cfg
+        nm, ns = ctx.needs_input_grad[:2]
+        dmean, dstd = be.normal_sample_bwd(dz.contiguous(), mean, modes[0], std, modes[1], K, N, eps=eps, seed=seed,
+                                           offset=offset, need_mean=nm, need_std=ns)
+        return dmean, dstd, None, None, None, None
+
+
+def normal_sample(mean, std, n_samples, reparameterized):
+    """Normal._sample (normal.py:89-107): [n_samples] + mean.shape (no leading axis for n_samples 1).
+
+    The noise has the shape of `mean` (as in the reference, :90-104); injected noise, when present,
+    replaces it (see _rng.inject)."""
+    home = mean.device
+    mean, std = to_compute(mean), to_compute(std)
+    K = int(n_samples)
+    base = tuple(mean.shape)
+    out_shape = ((K,) if K > 1 else ()) + base
+    N = _prod(base)
+    eps_in = _rng.take_injected("normal")
+    if eps_in is not None:
+        eps_in = to_compute(eps_in).to(mean.dtype).reshape(K, N).contiguous()
+    fits = tuple(torch.broadcast_shapes(base, std.shape)) == base
+    if not fits or N == 0:
+        # std broadcasts the mean (e.g. mean [1,3], std [2,1]): rare, composed from a noise draw
+        if eps_in is None:
+            seed, offset = _rng.next_philox(mean.device)
+            eps_in = be.philox_normal(K * N, mean.dtype, 0.0, 1.0, seed, offset, mean.device)
+        eps = eps_in.reshape(out_shape)
+        z = (mean.unsqueeze(0) + std.unsqueeze(0) * eps) if K > 1 else (mean + std * eps)
+        z = z if reparameterized else z.detach()
+        return back_home(z, home)
+    L = Layout([out_shape], 0)
+    L.k_axis, L.K, L.M = K > 1, K, N  # the particle axis is the sample axis
+    L.S = out_shape
+    (mc, mm), (sc, sm) = L.canon(mean), L.canon(std)
+    if K == 1:
+        mm = FULL if mm != SCALAR else mm
+    if reparameterized:
+        z = _NormalSample.apply(mc, sc, (mm, sm), K, N, eps_in)
+    else:
+        with torch.no_grad():
+            z = _NormalSample.apply(mc.detach(), sc.detach(), (mm, sm), K, N, eps_in)
+    return back_home(z.reshape(out_shape), home)
+
+
+# --------------------------------------------------------------------------------------------
+# Bernoulli
+# --------------------------------------------------------------------------------------------
+class _BernoulliLogPmf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, probs, modes, K, M, E):
+        out = be.bernoulli_logpmf_fwd(x, modes[0], probs, modes[1], K, M, E)
+        ctx.save_for_backward(x, probs)
+        ctx.cfg = (modes, K, M, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, probs = ctx.saved_tensors
+        modes, K, M, E = ctx.cfg
+        nx, np_ = ctx.needs_input_grad[:2]
+        dx, dprobs = be.bernoulli_logpmf_bwd(g.contiguous(), x, modes[0], probs, modes[1], K, M, E, nx, np_)
+        return dx, dprobs, None, None, None, None
+
+
+def bernoulli_log_prob(x, probs, n_event):
+    """sum over the last n_event axes of x*log(p+1e-8) + (1-x)*log(1-p+1e-8) (bernoulli.py:84-95)."""
+    home = probs.device
+    x, probs = to_compute(x), to_compute(probs)
+    L = Layout([x.shape, probs.shape], n_event)
+    if _prod(L.S) == 0:
+        return back_home(torch.zeros(L.lead, dtype=probs.dtype, device=probs.device), home)
+    (xc, xm), (pc, pm) = L.canon(x), L.canon(probs)
+    if pm == SCALAR:  # the kernels take probs as FULL / KBCAST only when it needs no gradient either way
+        pc, pm = probs.expand(L.S).contiguous(), FULL
+    out = _BernoulliLogPmf.apply(xc, pc, (xm, pm), L.K, L.M, L.E)
+    return back_home(out.reshape(L.lead), home)
+
+
+def bernoulli_sample(probs, n_samples):
+    """Bernoulli._sample (bernoulli.py:72-82): float samples, [n_samples] + probs.shape."""
+    home = probs.device
+    probs = to_compute(probs).detach()
+    K = int(n_samples)
+    base = tuple(probs.shape)
+    out_shape = ((K,) if K > 1 else ()) + base
+    N = _prod(base)
+    if N == 0:
+        return back_home(torch.zeros(out_shape, dtype=probs.dtype, device=probs.device), home)
+    u_in = _rng.take_injected("uniform")
+    seed = offset = 0
+    if u_in is not None:
+        u_in = to_compute(u_in).to(probs.dtype).reshape(K, N).contiguous()
+    else:
+        seed, offset = _rng.next_philox(probs.device)
+    out = be.bernoulli_sample(probs.contiguous(), KBCAST if K > 1 else FULL, K, N, u_in=u_in, seed=seed,
+                              offset=offset)
+    return back_home(out.reshape(out_shape), home)
+
+
+# --------------------------------------------------------------------------------------------
+# Categorical (not in the reference; see distributions/categorical.py)
+# --------------------------------------------------------------------------------------------
+class _CategoricalLogPmf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, logits, modes, K, M, C):
+        out = be.categorical_logpmf_fwd(x, modes[0], logits, modes[1], K, M, C)
+        ctx.save_for_backward(x, logits)
+        ctx.cfg = (modes, K, M, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, logits = ctx.saved_tensors
+        modes, K, M, C = ctx.cfg
+        d = be.categorical_logpmf_bwd(g.contiguous(), x, modes[0], logits, modes[1], K, M, C)
+        return None, d, None, None, None, None
+
+
+def categorical_log_prob(x, logits):
+    """log_softmax(logits)[x]; x has shape (...,) + logits.shape[:-1] (or broadcastable to it)."""
+    home = logits.device
+    x, logits = to_compute(x), to_compute(logits)
+    C = int(logits.shape[-1])
+    L = Layout([x.shape, logits.shape[:-1]], 0)
+    if _prod(L.S) == 0:
+        return back_home(torch.zeros(L.S, dtype=logits.dtype, device=logits.device), home)
+    xc, xm = L.canon(x.to(logits.dtype))
+    lpad = (1,) * (len(L.S) - (logits.dim() - 1)) + tuple(logits.shape[:-1])
+    if lpad == L.S:
+        lc, lm = logits.contiguous(), FULL
+    elif L.K > 1 and lpad[0] == 1:
+        lc, lm = logits.reshape(lpad[1:] + (C,)).expand(L.S[1:] + (C,)).contiguous(), KBCAST
+    else:
+        lc, lm = logits.expand(L.S + (C,)).contiguous(), FULL
+    out = _CategoricalLogPmf.apply(xc, lc, (xm, lm), L.K, L.M, C)
+    return back_home(out.reshape(L.S), home)
+
+
+def categorical_sample(logits, n_samples):
+    home = logits.device
+    logits = to_compute(logits).detach().contiguous()
+    K = int(n_samples)
+    base = tuple(logits.shape[:-1])
+    C = int(logits.shape[-1])
+    out_shape = ((K,) if K > 1 else ()) + base
+    M = _prod(base)
+    if M == 0:
+        return back_home(torch.zeros(out_shape, dtype=logits.dtype, device=logits.device), home)
+    u_in = _rng.take_injected("uniform")
+    seed = offset = 0
+    if u_in is not None:
+        u_in = to_compute(u_in).to(logits.dtype).reshape(K, M).contiguous()
+    else:
+        seed, offset = _rng.next_philox(logits.device)
+    out = be.categorical_sample(logits, KBCAST if K > 1 else FULL, K, M, C, u_in=u_in, seed=seed, offset=offset)
+    return back_home(out.reshape(out_shape), home)
+
+
+# --------------------------------------------------------------------------------------------
+# objectives
+# --------------------------------------------------------------------------------------------
+class _IWObjective(torch.autograd.Function):
+    """cost (scalar mean or per column) of the IW-SGVB / VIMCO surrogate with its gradient computed in
+    the same launch (importance_weighted_objective.py:16-25,102-191)."""
+
+    @staticmethod
+    def forward(ctx, logp, logq, estimator, reduce_mean):
+        K, B = logp.shape
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        cost, dlp, dlq = be.iw_objective(estimator, logp, logq, (1.0 / B) if reduce_mean else 1.0, need_grads=need)
+        ctx.save_for_backward(dlp, dlq)
+        ctx.reduce_mean = reduce_mean
+        return cost.mean() if reduce_mean else cost
+
+    @staticmethod
+    def backward(ctx, g):
+        dlp, dlq = ctx.saved_tensors
+        if not ctx.reduce_mean:
+            g = g.reshape(1, -1)
+        return (dlp * g if ctx.needs_input_grad[0] else None, dlq * g if ctx.needs_input_grad[1] else None, None, None)
+
+
+def iw_objective(logp, logq, axis, estimator, reduce_mean):
+    """logp/logq: same-shaped tensors; `axis` is the particle axis.  Returns the surrogate cost
+    (0-d if reduce_mean else the shape of logp without `axis`)."""
+    home = logp.device
+    logp, logq = torch.broadcast_tensors(to_compute(logp), to_compute(logq))
+    nd = logp.dim()
+    ax = axis % nd if nd > 0 else 0
+    lp = logp.movedim(ax, 0) if nd > 0 else logp.reshape(1)
+    lq = logq.movedim(ax, 0) if nd > 0 else logq.reshape(1)
+    rest = tuple(lp.shape[1:])
+    K = int(lp.shape[0])
+    lp2, lq2 = lp.reshape(K, -1).contiguous(), lq.reshape(K, -1).contiguous()
+    out = _IWObjective.apply(lp2, lq2, estimator, bool(reduce_mean))
+    if not reduce_mean:
+        out = out.reshape(rest)
+    return back_home(out, home)
+
+
+class _LogMeanExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return be.log_mean_exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return be.log_mean_exp_bwd(g.contiguous(), x)
+
+
+def log_mean_exp(x, dim, keepdims):
+    home = x.device
+    x = to_compute(x)
+    nd = x.dim()
+    ax = dim % nd
+    xm = x.movedim(ax, 0)
+    rest = tuple(xm.shape[1:])
+    out = _LogMeanExp.apply(xm.reshape(xm.shape[0], -1).contiguous()).reshape(rest)
+    if keepdims:
+        out = out.unsqueeze(ax)
+    return back_home(out, home)
+
+
+class _IWBernoulliFused(torch.autograd.Function):
+    """Bernoulli likelihood + IW objective, forward and backward in ONE launch (zs_fused_iw.cu).
+    The gradients are computed for a unit upstream gradient; backward applies the actual upstream
+    scalar with zs_scale_inplace, which is a no-op launch for the usual loss.backward()."""
+
+    @staticmethod
+    def forward(ctx, probs, x, logp_other, logq, estimator):
+        K, B, X = probs.shape
+        r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, 1.0 / B,
+                                  need_dprobs=ctx.needs_input_grad[0])
+        if r is None:
+            raise be.BackendError("fused IW kernel refused a shape fused_supported() accepted")
+        ctx.grads = (r["dprobs"], r["dlogp"], r["dlogq"])
+        return r["cost"].mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            raise RuntimeError("the fused IW objective hands its gradient buffers to autograd and can be "
+                               "back-propagated once; set zhusuan.variational.FUSED = False for retain_graph")
+        dprobs, dlp, dlq = ctx.grads
+        ctx.grads = None
+        g1 = g.reshape(1).contiguous()
+        if dprobs is not None:
+            be.scale_inplace(dprobs, g1)
+        return (dprobs, None,
+                dlp * g if ctx.needs_input_grad[2] else None,
+                dlq * g if ctx.needs_input_grad[3] else None,
+                None)
+
+
+def iw_bernoulli_fused(probs, x, logp_other, logq, estimator):
+    """probs [K,B,X] (CUDA, float32), x [B,X], logp_other / logq [K,B] or None -> scalar loss."""
+    probs = probs.contiguous()
+    x = x.to(probs.dtype).contiguous()
+    lo = None if logp_other is None else logp_other.contiguous()
+    lq = None if logq is None else logq.contiguous()
+    return _IWBernoulliFused.apply(probs, x, lo, lq, estimator)

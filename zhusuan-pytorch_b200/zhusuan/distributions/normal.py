@@ -1,0 +1,63 @@
+"""Univariate Normal — drop-in for zhusuan/distributions/normal.py of the reference.
+
+sample  : one kernel (Philox + Box-Muller + mean + std*eps), parameters broadcast over particles
+          instead of `.repeat`ed (reference :89-107 draws eps on the CPU and copies it over);
+log_prob: one kernel for the log-density and its event-axis sum (reference :109-126 + base.py:175-176).
+"""
+import torch
+
+from zhusuan.distributions.base import Distribution
+from zhusuan.distributions.utils import assert_same_log_float_dtype, check_broadcast
+from zhusuan import _ops
+
+__all__ = ['Normal']
+
+
+class Normal(Distribution):
+    """Normal(mean, std | logstd).  Exactly one of `std` / `logstd` must be given."""
+
+    def __init__(self, mean=0., std=None, logstd=None, dtype=None, is_continuous=True, is_reparameterized=True,
+                 group_ndims=0, device=torch.device('cpu'), **kwargs):
+        self._mean = torch.as_tensor(mean, dtype=dtype).to(device)
+        if (logstd is None) == (std is None):
+            raise ValueError("Either `std` or `logstd` should be passed. It is not allowed "
+                             "that both are specified or both are not.")
+        if std is None:
+            # std = exp(logstd) is what the reference stores (:56); log_prob takes its log again (:121)
+            self._std = torch.exp(torch.as_tensor(logstd, dtype=dtype)).to(device)
+        else:
+            self._std = torch.as_tensor(std, dtype=dtype).to(device)
+        check_broadcast(self._std, self._mean)
+        dtype = assert_same_log_float_dtype([(self._mean, "Normal.mean"), (self._std, "Normal.std")])
+        super(Normal, self).__init__(dtype=dtype, is_continuous=is_continuous,
+                                     is_reparameterized=is_reparameterized, group_ndims=group_ndims,
+                                     device=device, **kwargs)
+
+    @property
+    def mean(self):
+        return self._mean
+
+    @property
+    def std(self):
+        return self._std
+
+    @property
+    def logstd(self):
+        return torch.log(self._std)
+
+    def _batch_shape(self):
+        return torch.broadcast_shapes(self._mean.shape, self._std.shape)
+
+    def _sample(self, n_samples=1):
+        z = _ops.normal_sample(self._mean, self._std, n_samples, self.is_reparameterized)
+        self.sample_cache = z
+        return z
+
+    def _log_prob_event(self, given, n_event):
+        return _ops.normal_log_prob(self._given(given), self._mean, self._std, n_event)
+
+    def _log_prob(self, sample=None):
+        return _ops.normal_log_prob(self._given(sample), self._mean, self._std, 0)
+
+    def _prob(self, given):
+        return torch.exp(self._log_prob(given))
