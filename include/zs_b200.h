@@ -46,7 +46,7 @@ typedef void* zs_stream_t; /* cudaStream_t */
 
 enum { ZS_F32 = 0, ZS_F64 = 1 };
 enum { ZS_FULL = 0, ZS_KBCAST = 1, ZS_SCALAR = 2 };
-enum { ZS_EST_SGVB = 0, ZS_EST_VIMCO = 1 };
+enum { ZS_EST_SGVB = 0, ZS_EST_VIMCO = 1, ZS_EST_ELBO = 2 };
 
 enum {
     ZS_OK = 0,
@@ -140,6 +140,8 @@ int zs_categorical_logpmf_bwd(int dtype, void* dlogits, const void* g, const voi
  *       (importance_weighted_objective.py:16-25,102-132)
  *   estimator ZS_EST_VIMCO: ImportanceWeightedObjective.vimco (:134-191), the
  *       [B,K,K] leave-one-out tensor replaced by O(K) per-column sums.
+ *   estimator ZS_EST_ELBO : ELBO.sgvb (elbo.py:134-161), cost_b = -mean_k(logp - logq)
+ *       (zs_iw_objective only).
  * log w = logp - logq (+ logp_extra when not NULL, a second generator term [K,B]).
  * cost[B]   = per-column surrogate cost (cost_b); the scalar loss is mean_b cost_b.
  * dlogp/dlogq [K,B] = d(sum_b cost_b * grad_scale)/d(logp|logq); pass
@@ -174,6 +176,10 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
                           zs_stream_t stream);
+
+/* Debug hook: device buffer (grid*40 int64) that the fused kernel fills with clock64() phase
+ * timestamps of each CTA's first 8 columns; NULL (default) disables tracing. */
+int zs_debug_set_trace(void* device_buffer);
 
 /* ---- SG-MCMC updates across parallel chains (one pass) -----------------------
  * w_out receives the updated chain state and may alias w (in place); the reference

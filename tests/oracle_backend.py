@@ -1,0 +1,177 @@
+"""TEST-ONLY stand-in for zhusuan._backend built on the CPU oracle.
+
+`install(monkeypatch)` replaces the ctypes entry points of the product's backend with oracle-based
+implementations on CPU tensors, so the host logic of the package (layouts, autograd wiring,
+StochasticTensor / BayesianNet semantics, objective assembly, sampler state machines) can be tested in
+the CPU container.  The product never imports this module; `-m gpu` tests run the same scenarios
+against the real kernels.
+"""
+import numpy as np
+import torch
+
+from oracle import zs_oracle as O
+
+FULL, KBCAST, SCALAR = 0, 1, 2
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _t(a, like):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(like.dtype)
+
+
+def normal_sample(mean, mean_mode, std, std_mode, K, N, eps_in=None, eps_out=None, seed=0, offset=0):
+    if eps_in is None:
+        eps = O.philox_normal(K * N, seed, offset).astype(_np(mean).dtype).reshape(K, N)
+    else:
+        eps = _np(eps_in).reshape(K, N)
+    if eps_out is not None:
+        eps_out.copy_(_t(eps, mean))
+    return _t(O.normal_sample(_np(mean), _np(std), eps, K, N), mean)
+
+
+def normal_sample_bwd(dz, mean_like, mean_mode, std_like, std_mode, K, N, eps=None, seed=0, offset=0,
+                      need_mean=True, need_std=True):
+    e = O.philox_normal(K * N, seed, offset).astype(_np(dz).dtype).reshape(K, N) if eps is None else _np(eps).reshape(K, N)
+    dm, ds = O.normal_sample_bwd(_np(dz).reshape(K, N), e, _np(mean_like), _np(std_like), K, N)
+    return (_t(dm, dz) if need_mean else None), (_t(ds, dz) if need_std else None)
+
+
+def normal_logprob_fwd(x, xm, mean, mm, std, sm, K, M, E):
+    return _t(O.normal_logprob_fwd(_np(x), _np(mean), _np(std), K, M, E), x)
+
+
+def normal_logprob_bwd(g, x, xm, mean, mm, std, sm, K, M, E, need_x, need_mean, need_std):
+    dx, dm, ds = O.normal_logprob_bwd(_np(g), _np(x), _np(mean), _np(std), K, M, E)
+    return (_t(dx, x) if need_x else None, _t(dm, x) if need_mean else None, _t(ds, x) if need_std else None)
+
+
+def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0):
+    u = O.philox_uniform(K * N, seed, offset).astype(_np(probs).dtype).reshape(K, N) if u_in is None else _np(u_in)
+    return _t(O.bernoulli_sample(_np(probs), u.reshape(K, N), K, N), probs)
+
+
+def bernoulli_logpmf_fwd(x, xm, probs, pm, K, M, E):
+    return _t(O.bernoulli_logpmf_fwd(_np(x), _np(probs), K, M, E), probs)
+
+
+def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs):
+    dx, dp = O.bernoulli_logpmf_bwd(_np(g), _np(x), _np(probs), K, M, E, need_dx=True)
+    return (_t(dx, probs) if need_x else None, _t(dp, probs) if need_probs else None)
+
+
+def categorical_sample(logits, lm, K, M, C, u_in=None, seed=0, offset=0):
+    u = O.philox_uniform(K * M, seed, offset).astype(_np(logits).dtype) if u_in is None else _np(u_in)
+    return _t(O.categorical_sample(_np(logits), u.reshape(K, M), K, M, C), logits)
+
+
+def categorical_logpmf_fwd(x, xm, logits, lm, K, M, C):
+    return _t(O.categorical_logpmf_fwd(_np(x), _np(logits), K, M, C), logits)
+
+
+def categorical_logpmf_bwd(g, x, xm, logits, lm, K, M, C):
+    return _t(O.categorical_logpmf_bwd(_np(g), _np(x), _np(logits), K, M, C), logits)
+
+
+def iw_objective(estimator, logp, logq, grad_scale, extra=None, need_grads=True):
+    lp = _np(logp) + (0 if extra is None else _np(extra))
+    K, B = lp.shape
+    if estimator == 2:  # ELBO
+        x = lp.astype(np.float64) - _np(logq)
+        cost = (-x.mean(0)).astype(lp.dtype)
+        g = np.full((K, B), grad_scale / K, lp.dtype)
+        return _t(cost, logp), _t(-g, logp), _t(g, logp)
+    cost, dlp, dlq = O.iw_objective(estimator, lp, _np(logq), grad_scale)
+    return _t(cost, logp), _t(dlp, logp), _t(dlq, logp)
+
+
+def log_mean_exp(x):
+    return _t(O.log_mean_exp(_np(x)), x)
+
+
+def log_mean_exp_bwd(g, x):
+    xn = _np(x).astype(np.float64)
+    w = np.exp(xn - xn.max(0, keepdims=True))
+    return _t(_np(g)[None, :] * w / w.sum(0, keepdims=True), x)
+
+
+def fused_supported(K, X, dtype):
+    return dtype == torch.float32 and X % 4 == 0 and 8 <= K <= 4096 and K * X * 4 <= 200 * 1024
+
+
+def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False, out=None):
+    r = O.iw_bernoulli_step(estimator, _np(probs), _np(x), _np(logp_other), _np(logq), grad_scale,
+                            need_dprobs=need_dprobs)
+    return dict(cost=_t(r["cost"], probs), dprobs=_t(r["dprobs"], probs) if need_dprobs else None,
+                dlogp=_t(r["dlogp"], probs), dlogq=_t(r["dlogq"], probs),
+                logpx=_t(r["logpx"], probs) if want_logpx else None)
+
+
+def scale_inplace(buf, scale_dev):
+    if float(scale_dev) != 1.0:
+        buf.mul_(scale_dev)
+
+
+def philox_normal(n, dtype, mean, std, seed, offset, device):
+    return torch.from_numpy(O.philox_normal(n, seed, offset, mean, std)).to(dtype)
+
+
+def sgld_step(w, g, lr, noise=None, seed=0, offset=0, out=None):
+    if noise is None:
+        noise = philox_normal(w.numel(), w.dtype, 0.0, float(np.float32(np.sqrt(np.float64(np.float32(lr))))), seed,
+                              offset, None).reshape(w.shape)
+    return _t(O.sgld_step(_np(w), _np(g), _np(noise), lr), w)
+
+
+def psgld_step(w, aux, g, lr, decay, epsilon, noise_unit=None, seed=0, offset=0, out=None):
+    if noise_unit is None:
+        noise_unit = philox_normal(w.numel(), w.dtype, 0.0, 1.0, seed, offset, None).reshape(w.shape)
+    nw, na = O.psgld_step(_np(w), _np(aux), _np(g), _np(noise_unit), lr, decay, epsilon)
+    aux.copy_(_t(na, w))
+    return _t(nw, w)
+
+
+def sghmc_pre(w, v, lr, resample, second_order, v_noise=None, seed=0, offset=0, out=None):
+    if not resample and not second_order:
+        return w
+    if resample and v_noise is None:
+        v_noise = philox_normal(w.numel(), w.dtype, 0.0, float(np.float32(np.sqrt(lr))), seed, offset, None).reshape(w.shape)
+    nw, nv = O.sghmc_pre(_np(w), _np(v), _np(v_noise), resample, second_order)
+    v.copy_(_t(nv, w))
+    return _t(nw, w) if second_order else w
+
+
+def sghmc_post(w, v, g, lr, alpha, beta, second_order, noise=None, seed=0, offset=0, out=None):
+    if noise is None:
+        std = float(np.float32(np.sqrt(2.0 * (alpha - beta) * lr)))
+        noise = philox_normal(w.numel(), w.dtype, 0.0, std, seed, offset, None).reshape(w.shape)
+    nw, nv = O.sghmc_post(_np(w), _np(v), _np(g), _np(noise), lr, alpha, second_order)
+    v.copy_(_t(nv, w))
+    return _t(nw, w)
+
+
+_counter = {"off": 0}
+
+
+def _next_philox(device):
+    _counter["off"] += 4
+    return 1234, _counter["off"]
+
+
+def install(monkeypatch):
+    """Patch the product's backend / device helpers with the CPU stand-ins above."""
+    from zhusuan import _backend, _ops, _rng
+    for name in ("normal_sample", "normal_sample_bwd", "normal_logprob_fwd", "normal_logprob_bwd", "bernoulli_sample",
+                 "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "categorical_sample", "categorical_logpmf_fwd",
+                 "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
+                 "iw_bernoulli_fused", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
+                 "sghmc_post"):
+        monkeypatch.setattr(_backend, name, globals()[name])
+    monkeypatch.setattr(_backend, "require_cuda", lambda: None)
+    monkeypatch.setattr(_backend, "on_compute_device", lambda t: True)
+    monkeypatch.setattr(_ops, "to_compute", lambda t: t)
+    monkeypatch.setattr(_ops, "compute_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(_rng, "next_philox", _next_philox)
+    _counter["off"] = 0

@@ -1,0 +1,718 @@
+"""API-level tests of the drop-in `zhusuan` package: the reference's public surface
+(zhusuan.distributions / framework / variational / mcmc) with the reference's behaviour.
+
+Every test runs in two modes:
+  * `oracle` — CPU container: the ctypes backend is replaced by the CPU oracle (tests/oracle_backend.py)
+    so the package's host logic is exercised without a GPU;
+  * `cuda`   — B200 (`-m gpu`): the real kernels, CUDA tensors;
+  * `cuda-host` — B200: CPU tensors in, results back on the CPU (the reference's tests feed CPU tensors).
+Scenarios mirror the reference's test strategy: constructor errors, shapes, dtypes,
+known answers from scipy, reparameterisation gradients, analytic-KL checks of the objectives,
+golden fixtures produced by the real reference with injected noise, and the double-well sampler test.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+import zhusuan
+import zhusuan.mcmc
+import zhusuan.variational
+from zhusuan import _rng
+from zhusuan.distributions import Bernoulli, Categorical, Normal
+from zhusuan.framework import BayesianNet, StochasticTensor
+from zhusuan.variational import ELBO, ImportanceWeightedObjective
+
+MODES = [pytest.param("oracle"), pytest.param("cuda", marks=pytest.mark.gpu),
+         pytest.param("cuda-host", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=MODES)
+def dev(request, monkeypatch):
+    mode = request.param
+    if mode == "oracle":
+        import oracle_backend
+        oracle_backend.install(monkeypatch)
+        return torch.device("cpu")
+    return torch.device("cuda") if mode == "cuda" else torch.device("cpu")
+
+
+def T(a, dev, dtype=torch.float32, grad=False):
+    t = torch.tensor(np.asarray(a), dtype=dtype, device=dev)
+    t.requires_grad_(grad)
+    return t
+
+
+def close(a, ref, rtol=1e-5):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    ref = ref.detach().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+    a, ref = a.astype(np.float64), ref.astype(np.float64)
+    np.testing.assert_allclose(a, ref, rtol=rtol, atol=rtol * max(np.abs(ref).max(), 1e-30))
+
+
+# ============================================================================ distributions
+def test_constructor_errors():
+    with pytest.raises(ValueError, match="Either.*should be passed"):
+        Normal(mean=0.)
+    with pytest.raises(ValueError, match="Either.*should be passed"):
+        Normal(mean=0., std=1., logstd=0.)
+    with pytest.raises(RuntimeError):
+        Normal(mean=torch.zeros(2, 3), std=torch.ones(4))
+    with pytest.raises(ValueError, match="Either.*should be passed"):
+        Bernoulli()
+    with pytest.raises(TypeError, match="must have a dtype in"):
+        Bernoulli(logits=torch.zeros(3, dtype=torch.int32))
+    with pytest.raises(TypeError, match="must have a dtype in"):
+        Normal(mean=torch.zeros(3, dtype=torch.float16), std=torch.ones(3, dtype=torch.float16))
+    with pytest.raises(ValueError, match="non-negative"):
+        Normal(mean=0., std=1., group_ndims=-1)
+    # unknown kwargs are swallowed (reference base.py:77); check_numerics is accepted and ignored
+    Normal(mean=0., std=1., check_numerics=True, reparameterize=True, reduce_mean_dims=[0])
+
+
+def test_bernoulli_parameterisations():
+    b = Bernoulli(0.)
+    assert b.dtype == torch.float32 and float(b.probs) == 0.5
+    p = torch.tensor([0.2, 0.7])
+    close(Bernoulli(probs=p).logits, torch.log(p / (1 - p)))
+    lg = torch.tensor([-1.0, 2.0], dtype=torch.float64)
+    assert Bernoulli(logits=lg).dtype == torch.float64
+    close(Bernoulli(logits=lg).probs, torch.sigmoid(lg))
+    assert not Bernoulli(probs=p).is_reparameterized and Normal(0., 1.).is_reparameterized
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_normal_shapes_and_values(dev, dtype):
+    # sample shapes, incl. the reference's broadcasting case mean [1,3] + std [2,1], n=2 -> [2,2,3]
+    n = Normal(mean=torch.zeros(1, 3, dtype=dtype, device=dev), std=torch.ones(2, 1, dtype=dtype, device=dev))
+    assert tuple(n.batch_shape) == (2, 3)
+    assert tuple(n.sample(2).shape) == (2, 2, 3) and tuple(n.sample().shape) == (2, 3)
+    n = Normal(mean=torch.zeros(4, 5, dtype=dtype, device=dev), logstd=torch.zeros(4, 5, dtype=dtype, device=dev))
+    s = n.sample(7)
+    assert tuple(s.shape) == (7, 4, 5) and s.dtype == dtype and s.device.type == dev.type
+    assert tuple(n.sample(1).shape) == (4, 5) and tuple(n.sample(None).shape) == (4, 5)  # no particle axis
+    assert n.sample_cache is not None
+    # log_prob broadcasting and known answers (scipy, as test/distributions/test_normal.py:92-126)
+    rng = np.random.RandomState(0)
+    mean, logstd, x = rng.standard_normal((2, 3)), 0.5 * rng.standard_normal((2, 3)), rng.standard_normal((5, 2, 3))
+    n = Normal(mean=T(mean, dev, dtype), logstd=T(logstd, dev, dtype))
+    lp = n.log_prob(T(x, dev, dtype))
+    assert tuple(lp.shape) == (5, 2, 3) and lp.dtype == dtype
+    close(lp, stats.norm.logpdf(x, mean, np.exp(logstd)), 1e-5 if dtype == torch.float32 else 1e-7)
+    close(n.prob(T(x, dev, dtype)), stats.norm.pdf(x, mean, np.exp(logstd)), 1e-5)
+    g1 = Normal(mean=T(mean, dev, dtype), logstd=T(logstd, dev, dtype), group_ndims=1)
+    close(g1.log_prob(T(x, dev, dtype)), stats.norm.logpdf(x, mean, np.exp(logstd)).sum(-1), 1e-5)
+    g2 = Normal(mean=T(mean, dev, dtype), logstd=T(logstd, dev, dtype), group_ndims=2)
+    assert tuple(g2.log_prob(T(x, dev, dtype)).shape) == (5,)
+    close(n.logstd, logstd, 1e-5)
+
+
+def test_normal_reparameterisation_gradients(dev):
+    """test/distributions/test_normal.py:65-84: gradients reach the parameters through the sample
+    iff the distribution is reparameterised."""
+    mean = torch.zeros(3, 4, device=dev, requires_grad=True)
+    std = torch.ones(3, 4, device=dev, requires_grad=True)
+    z = Normal(mean=mean, std=std).sample(6)
+    gm, gs = torch.autograd.grad(z.sum() + (z * z).sum(), [mean, std])
+    assert gm.abs().sum() > 0 and gs.abs().sum() > 0
+    close(gm, (1 + 2 * z).sum(0))
+    z2 = Normal(mean=mean, std=std, is_reparameterized=False).sample(6)
+    assert not z2.requires_grad
+    # the score-function path: log_prob of a detached sample still differentiates wrt the parameters
+    lp = Normal(mean=mean, std=std, is_reparameterized=False).log_prob(z2)
+    gm2, = torch.autograd.grad(lp.sum(), [mean])
+    close(gm2, ((z2 - mean) / std ** 2).sum(0), 1e-4)
+
+
+def test_normal_sampler_statistics(dev):
+    mean = torch.tensor([[-2.0, 0.0, 3.0]], device=dev)
+    std = torch.tensor([[0.5, 1.0, 2.0]], device=dev)
+    s = Normal(mean=mean, std=std).sample(40000).cpu().numpy()[:, 0, :]
+    for j in range(3):
+        m, sd = float(mean[0, j]), float(std[0, j])
+        assert abs(s[:, j].mean() - m) < 4 * sd / math.sqrt(40000) + 1e-3
+        assert abs(s[:, j].std() / sd - 1) < 0.02
+        assert stats.kstest((s[:, j] - m) / sd, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(s[:, 0], s[:, 1])[0, 1]) < 0.03  # coordinates are independent
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_bernoulli_shapes_and_values(dev, dtype):
+    rng = np.random.RandomState(1)
+    logits = rng.standard_normal((2, 3))
+    probs = 1 / (1 + np.exp(-logits))
+    b = Bernoulli(logits=T(logits, dev, dtype))
+    s = b.sample(5)
+    assert tuple(s.shape) == (5, 2, 3) and s.dtype == dtype and tuple(b.sample().shape) == (2, 3)
+    assert set(np.unique(s.cpu().numpy())) <= {0.0, 1.0}
+    x = (rng.uniform(size=(4, 2, 3)) < 0.5).astype(np.float64)
+    lp = b.log_prob(T(x, dev, dtype))
+    assert tuple(lp.shape) == (4, 2, 3)
+    close(lp, stats.bernoulli.logpmf(x, probs), 1e-5)  # test/distributions/test_bernoulli.py:56-72
+    b1 = Bernoulli(probs=T(probs, dev, dtype), group_ndims=1)
+    close(b1.log_prob(T(x, dev, dtype)), stats.bernoulli.logpmf(x, probs).sum(-1), 1e-5)
+    # log_prob(None) evaluates at the cached sample (reference Q2)
+    s = b.sample(3)
+    close(b.log_prob(None), b.log_prob(s))
+    # gradient wrt probs
+    p = T(probs, dev, dtype, grad=True)
+    (g,) = torch.autograd.grad(Bernoulli(probs=p).log_prob(T(x, dev, dtype)).sum(), [p])
+    close(g, (x / (probs + 1e-8) - (1 - x) / (1 - probs + 1e-8)).sum(0), 1e-5)
+
+
+def test_bernoulli_sampler_statistics(dev):
+    p = torch.tensor([0.0, 0.1, 0.5, 0.9, 1.0], device=dev)
+    s = Bernoulli(probs=p).sample(40000).cpu().numpy()
+    f = s.mean(0)
+    assert f[0] == 0 and f[4] == 1
+    assert np.abs(f[1:4] - np.array([0.1, 0.5, 0.9])).max() < 0.01
+
+
+def test_categorical(dev):
+    rng = np.random.RandomState(2)
+    logits = T(rng.standard_normal((3, 5)), dev, grad=True)
+    c = Categorical(logits=logits)
+    assert tuple(c.batch_shape) == (3,) and c.n_categories == 5 and not c.is_reparameterized
+    s = c.sample(7)
+    assert tuple(s.shape) == (7, 3) and s.dtype == torch.float32
+    lp = c.log_prob(s)
+    ref = torch.log_softmax(logits, -1).unsqueeze(0).expand(7, 3, 5).gather(-1, s.long().unsqueeze(-1)).squeeze(-1)
+    close(lp, ref, 1e-5)
+    (g,) = torch.autograd.grad(lp.sum(), [logits])
+    (gr,) = torch.autograd.grad(ref.sum(), [logits])
+    close(g, gr, 1e-5)
+    freq = np.bincount(Categorical(logits=logits[0].detach()).sample(30000).cpu().numpy().astype(int), minlength=5)
+    close(freq / 30000.0, torch.softmax(logits[0], -1), 0.03)
+    with pytest.raises(ValueError, match="Either"):
+        Categorical()
+
+
+# ============================================================================ framework
+class _Net(BayesianNet):
+    def __init__(self, K, dev, dtype=torch.float32):
+        super().__init__(device=dev)
+        self.K, self.dt = K, dtype
+
+    def forward(self, observed):
+        self.observe(observed)
+        d = self.device
+        z = self.normal("z", mean=torch.zeros(4, 3, dtype=self.dt, device=d),
+                        std=torch.ones(4, 3, dtype=self.dt, device=d), n_samples=self.K, reduce_sum_dims=[2])
+        self.cache["z_seen"] = z
+        self.bernoulli("x", probs=torch.sigmoid(z), reduce_sum_dims=[-1])
+        return self
+
+
+def test_bayesian_net_protocol(dev):
+    net = _Net(5, dev)
+    assert net(dict()) is net and set(net.nodes) == {"z", "x"} and isinstance(net.nodes["z"], StochasticTensor)
+    z1, z2 = net.nodes["z"].tensor, net.nodes["z"].tensor
+    assert tuple(z1.shape) == (5, 4, 3) and not torch.equal(z1, z2)  # unobserved: a NEW draw per access (Q1)
+    assert tuple(net.nodes["z"].shape) == (5, 4, 3)
+    zobs = torch.zeros(5, 4, 3, device=dev)
+    net({"z": zobs})
+    assert net.nodes["z"].tensor is zobs and net.observed["z"] is zobs and net.cache["z_seen"] is zobs
+    assert net.nodes["z"].dist.sample_cache is zobs
+    lp = net.nodes["z"].log_prob()
+    assert tuple(lp.shape) == (5, 4)
+    close(lp, torch.full((5, 4), 3 * -0.9189385332))
+    xobs = torch.ones(4, 3, device=dev)
+    net({"z": zobs, "x": xobs})
+    lj = net.log_joint()
+    assert tuple(lj.shape) == (5, 4)
+    close(lj, torch.full((5, 4), 3 * -0.9189385332 + 3 * math.log(0.5)), 1e-5)
+    assert net.log_joint(use_cache=True) is net._log_joint_cache
+    # registered by name or by instance; unknown names fail loudly
+    net.stochastic_node("Normal", "a", mean=0., std=1.)
+    net.sn(Bernoulli(probs=torch.tensor(0.3)), "b", n_samples=4)
+    assert tuple(net.nodes["b"].tensor.shape) == (4,)
+    with pytest.raises(NotImplementedError):
+        net.stochastic_node("Gamma", "g", alpha=1., beta=1.)
+    with pytest.raises(ValueError):
+        net.stochastic_node(3, "c")
+    with pytest.raises(ValueError):
+        net.normal(3, mean=0., std=1.)
+
+
+@pytest.mark.parametrize("plan", [
+    dict(group_ndims=0, reduce_mean_dims=None, reduce_sum_dims=[2]),
+    dict(group_ndims=1, reduce_mean_dims=None, reduce_sum_dims=None),
+    dict(group_ndims=0, reduce_mean_dims=[0], reduce_sum_dims=[2]),
+    dict(group_ndims=0, reduce_mean_dims=[0, 1], reduce_sum_dims=None, multiplier=456),
+    dict(group_ndims=2, reduce_mean_dims=[0], reduce_sum_dims=None),
+    dict(group_ndims=0, reduce_mean_dims=[1], reduce_sum_dims=[0]),
+    dict(group_ndims=0, reduce_mean_dims=None, reduce_sum_dims=[1, 2]),
+    dict(group_ndims=0, reduce_mean_dims=None, reduce_sum_dims=None),
+])
+def test_stochastic_tensor_reductions(dev, plan):
+    """StochasticTensor.log_prob = group_ndims sum -> mean dims -> sum dims -> squeeze -> multiplier
+    (reference stochastic_tensor.py:160-181), whichever part of it the kernel absorbs."""
+    rng = np.random.RandomState(3)
+    mean, std, x = rng.standard_normal((4, 6)), np.exp(0.2 * rng.standard_normal((4, 6))), rng.standard_normal((5, 4, 6))
+    net = BayesianNet(device=dev)
+    net.observe({"w": T(x, dev)})
+    kw = {k: v for k, v in plan.items() if k != "group_ndims"}
+    net.normal("w", mean=T(mean, dev), std=T(std, dev), group_ndims=plan["group_ndims"], n_samples=5, **kw)
+    got = net.nodes["w"].log_prob()
+    ref = torch.tensor(stats.norm.logpdf(x, mean, std))
+    g = plan["group_ndims"]
+    if g:
+        ref = ref.sum(list(range(-g, 0)))
+    dims = []
+    if plan.get("reduce_mean_dims"):
+        ref = ref.mean(plan["reduce_mean_dims"], keepdim=True)
+        dims += plan["reduce_mean_dims"]
+    if plan.get("reduce_sum_dims"):
+        ref = ref.sum(plan["reduce_sum_dims"], keepdim=True)
+        dims += plan["reduce_sum_dims"]
+    for d in sorted(dims, reverse=True):
+        ref = ref.squeeze(d)
+    if plan.get("multiplier"):
+        ref = ref * plan["multiplier"]
+    assert tuple(got.shape) == tuple(ref.shape)
+    close(got, ref, 1e-5)
+
+
+# ============================================================================ objectives
+def _kl(m1, s1, m2, s2):
+    return torch.log(s2 / s1) + (s1 ** 2 + (m1 - m2) ** 2) / (2 * s2 ** 2) - 0.5
+
+
+class _GenNode(object):
+    """Duck-typed node, as the reference's tests plant them (test_elbo.py:23-66, test_iw.py:23-66)."""
+
+    def __init__(self, mean, std, dev):
+        self.mean, self.std, self.dev, self.observed = mean, std, dev, {}
+
+    def log_prob(self):
+        return Normal(mean=self.mean, std=self.std).log_prob(self.observed["x"])
+
+
+class _GenNet(BayesianNet):
+    def __init__(self, mean, std, dev):
+        super().__init__()
+        self._nodes["test"] = _GenNode(mean, std, dev)
+
+    def forward(self, observed):
+        self._nodes["test"].observed = dict(observed)
+        return self
+
+
+class _VarNode(object):
+    def __init__(self, samples, log_q):
+        self.tensor, self._lq = samples, log_q
+
+    def log_prob(self):
+        return self._lq
+
+
+class _VarNet(BayesianNet):
+    def __init__(self, samples, log_q):
+        super().__init__()
+        self._nodes["x"] = _VarNode(samples, log_q)
+
+    def forward(self, observed):
+        return self
+
+
+def test_elbo_against_analytic_kl(dev):
+    """-ELBO of q=N(0,1) against p=N(m,s) equals KL(q||p); test/variational/test_elbo.py:78-121."""
+    rng = np.random.RandomState(1)
+    eps = T(rng.standard_normal(100000), dev)
+    logq = T(stats.norm.logpdf(eps.cpu().numpy()), dev)
+    for m, s in ((0., 1.), (2., 3.)):
+        model = ELBO(_GenNet(torch.tensor(m, device=dev), torch.tensor(s, device=dev), dev), _VarNet(eps, logq))
+        kl = float(_kl(torch.tensor(0.), torch.tensor(1.), torch.tensor(m), torch.tensor(s)))
+        assert abs(float(model({})) - kl) < 1e-2
+    # sgvb gradients wrt the variational parameters vs the analytic KL gradients
+    mu = torch.tensor(2., device=dev, requires_grad=True)
+    sigma = torch.tensor(3., device=dev, requires_grad=True)
+    x = eps * sigma + mu
+    logq = Normal(mean=mu, std=sigma).log_prob(x)
+    for m, s in ((0., 1.), (2., 3.)):
+        model = ELBO(_GenNet(torch.tensor(m, device=dev), torch.tensor(s, device=dev), dev), _VarNet(x, logq))
+        grads = torch.autograd.grad(model({}), [mu, sigma], retain_graph=True)
+        true = torch.autograd.grad(_kl(mu, sigma, torch.tensor(m, device=dev), torch.tensor(s, device=dev)), [mu, sigma])
+        np.testing.assert_allclose([float(g) for g in grads], [float(g) for g in true], rtol=1e-2, atol=1e-2)
+    with pytest.raises(NotImplementedError):
+        ELBO(None, None, estimator="nope")
+
+
+def test_iw_objective_properties(dev):
+    """K=1 reduces to the ELBO; the bound tightens with K; VIMCO and SGVB gradients agree in
+    expectation (test/variational/test_iw.py:78-175)."""
+    rng = np.random.RandomState(1)
+    n1 = T(rng.standard_normal((1, 1000)), dev)
+    n3 = T(rng.standard_normal(10000), dev)
+    for m, s in ((0., 1.), (2., 3.)):
+        gm, gs = torch.tensor(m, device=dev), torch.tensor(s, device=dev)
+        kl = float(_kl(torch.tensor(0.), torch.tensor(1.), torch.tensor(m), torch.tensor(s)))
+        lb1 = -float(ImportanceWeightedObjective(_GenNet(gm, gs, dev), _VarNet(n1, T(stats.norm.logpdf(n1.cpu().numpy()), dev)),
+                                                 axis=0)({}))
+        assert abs(lb1 + kl) < 6e-2
+        lb3 = -float(ImportanceWeightedObjective(_GenNet(gm, gs, dev), _VarNet(n3, T(stats.norm.logpdf(n3.cpu().numpy()), dev)),
+                                                 axis=0)({}))
+        assert lb3 > -kl - 1e-6
+    mu = torch.tensor(2., device=dev, requires_grad=True)
+    sigma = torch.tensor(3., device=dev, requires_grad=True)
+    x = n3 * sigma + mu
+    norm = Normal(mean=mu, std=sigma)
+    logq = norm.log_prob(x)
+    xv = (n3 * sigma + mu).detach()
+    logqv = norm.log_prob(xv)
+    for m, s, thr in ((0., 1., 1e-2), (2., 3., 1e-6)):
+        gm, gs = torch.tensor(m, device=dev), torch.tensor(s, device=dev)
+        sg = ImportanceWeightedObjective(_GenNet(gm, gs, dev), _VarNet(x, logq), axis=0, estimator="sgvb")
+        vi = ImportanceWeightedObjective(_GenNet(gm, gs, dev), _VarNet(xv, logqv), axis=0, estimator="vimco")
+        g_vi = [float(g) for g in torch.autograd.grad(vi({}), [mu, sigma], retain_graph=True)]
+        g_sg = [float(g) for g in torch.autograd.grad(sg({}), [mu, sigma], retain_graph=True)]
+        np.testing.assert_allclose(g_vi, g_sg, rtol=thr, atol=thr)
+    with pytest.raises(ValueError, match="axis"):
+        ImportanceWeightedObjective(None, None)
+    with pytest.raises(NotImplementedError):
+        ImportanceWeightedObjective(None, None, axis=0, estimator="nope")
+    obj = ImportanceWeightedObjective(None, None, axis=0, estimator="vimco")
+    with pytest.raises(ValueError, match="multi-sample"):
+        obj.vimco(torch.zeros(1, 4, device=dev), torch.zeros(1, 4, device=dev))
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("shape", ["kb", "k50", "k1d", "dominant"])
+def test_objective_methods_against_reference_goldens(dev, golden, shape, dn):
+    """sgvb / vimco / ELBO.sgvb / log_mean_exp called on raw tensors, as recorded from the reference."""
+    g = golden("objectives")
+    dt = torch.float32 if dn == "f32" else torch.float64
+    rt = 1e-5 if dn == "f32" else 1e-10
+    for est in ("sgvb", "vimco"):
+        p = "%s_%s_%s_" % (shape, est, dn)
+        lp, lq = T(g[p + "logp"], dev, dt, True), T(g[p + "logq"], dev, dt, True)
+        obj = ImportanceWeightedObjective(None, None, axis=0, estimator=est)
+        loss = getattr(obj, est)(lp, lq, True)
+        assert loss.dim() == 0 and loss.dtype == dt and loss.device.type == dev.type
+        close(loss, g[p + "loss"], rt)
+        dlp, dlq = torch.autograd.grad(loss, [lp, lq])
+        ref = g if est == "sgvb" else {k.replace("f32", "f64") if False else k: v for k, v in g.items()}
+        if est == "sgvb":
+            close(dlp, g[p + "dlogp"], rt)
+            close(dlq, g[p + "dlogq"], rt)
+            close(obj.sgvb(lp, lq, False), g[p + "cost"], rt)
+        else:  # compare with the float64 reference run (see tests/test_gpu_kernels.py on fp32 VIMCO noise)
+            p64 = "%s_%s_f64_" % (shape, est)
+            close(dlp, g[p64 + "dlogp"], rt)
+            close(dlq, g[p64 + "dlogq"], rt)
+    p = "%s_elbo_%s_" % (shape, dn)
+    ps = "%s_sgvb_%s_" % (shape, dn)
+    lp, lq = T(g[ps + "logp"], dev, dt, True), T(g[ps + "logq"], dev, dt, True)
+    loss = ELBO(None, None).sgvb(lp, lq, True)
+    close(loss, g[p + "loss"], rt)
+    dlp, dlq = torch.autograd.grad(loss, [lp, lq])
+    close(dlp, g[p + "dlogp"], rt)
+    close(dlq, g[p + "dlogq"], rt)
+    close(ELBO(None, None).sgvb(lp, lq, False), -(g[ps + "logp"] - g[ps + "logq"]), rt)
+    p = "%s_lme_%s_" % (shape, dn)
+    xx = T(g[p + "x"], dev, dt, True)
+    out = zhusuan.log_mean_exp(xx, 0)
+    close(out, g[p + "out"], rt)
+    (dx,) = torch.autograd.grad(out.sum(), [xx])
+    close(dx, g[p + "dx"], rt)
+    assert tuple(zhusuan.log_mean_exp(xx, 0, keepdims=True).shape) == (1,) + tuple(xx.shape[1:])
+
+
+def test_reinforce_against_reference_golden(dev, golden):
+    g = golden("reinforce")
+    elbo = ELBO(None, None, estimator="reinforce").to(dev)
+    assert set(elbo.state_dict()) == {"moving_mean", "local_step"}
+    for step in range(3):
+        p = "f32_s%d_" % step
+        lp, lq = T(g[p + "logp"], dev, grad=True), T(g[p + "logq"], dev, grad=True)
+        loss = elbo.reinforce(lp, lq, True)
+        close(loss, g[p + "loss"], 1e-5)
+        dlp, dlq = torch.autograd.grad(loss, [lp, lq])
+        close(dlp, g[p + "dlogp"], 1e-5)
+        close(dlq, g[p + "dlogq"], 1e-4)
+        close(elbo.moving_mean, g[p + "moving_mean"], 1e-5)
+        assert int(elbo.local_step) == int(g[p + "local_step"])
+
+
+class _PathGen(BayesianNet):
+    def __init__(self, probs, K, latent):
+        super().__init__(device=probs.device)
+        self.probs, self.K, self.latent = probs, K, latent
+
+    def forward(self, observed):
+        self.observe(observed)
+        B, Z = self.observed["z"].shape[1:]
+        dt, d = self.probs.dtype, self.probs.device
+        if self.latent == "normal":
+            self.normal("z", mean=torch.zeros([B, Z], dtype=dt, device=d), std=torch.ones([B, Z], dtype=dt, device=d),
+                        is_reparameterized=False, n_samples=self.K, reduce_sum_dims=[2])
+        else:
+            self.bernoulli("z", probs=0.5 * torch.ones([B, Z], dtype=dt, device=d), n_samples=self.K,
+                           reduce_sum_dims=[2])
+        self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
+        return self
+
+
+class _PathVar(BayesianNet):
+    def __init__(self, a, b, K, latent, reparam):
+        super().__init__(device=a.device)
+        self.a, self.b, self.K, self.latent, self.reparam = a, b, K, latent, reparam
+
+    def forward(self, observed):
+        self.observe(observed)
+        if self.latent == "normal":
+            self.sn(Normal(mean=self.a, logstd=self.b, is_reparameterized=self.reparam), name="z", n_samples=self.K,
+                    reduce_sum_dims=[2])
+        else:
+            self.sn(Bernoulli(probs=self.a), name="z", n_samples=self.K, reduce_sum_dims=[2])
+        return self
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("est,latent", [("sgvb", "normal"), ("vimco", "normal"), ("vimco", "bernoulli")])
+def test_iw_path_against_reference_golden(dev, golden, est, latent, dn):
+    """The whole hot path through the public API — sample, log q, log p(z), log p(x|z), objective,
+    backward — against the reference run with the SAME injected noise (make_golden.py:gen_iw_path).
+    `.tensor` is read twice per step in the reference (Q1), so the noise is injected twice."""
+    g = golden("iw_path")
+    dt = torch.float32 if dn == "f32" else torch.float64
+    K = int(g["K"])
+    p = "%s_%s_%s_" % (est, latent, dn)
+    probs = T(g["probs"], dev, dt, True)
+    if latent == "normal":
+        a, b = T(g["mean"], dev, dt, True), T(g["logstd"], dev, dt, True)
+        inj = dict(normal=[T(g["eps"], dev, dt)] * 2)
+    else:
+        a, b = T(g["probs_q"], dev, dt, True), None
+        inj = dict(uniform=[T(g["u"], dev, dt)] * 2)
+    gen, var = _PathGen(probs, K, latent), _PathVar(a, b, K, latent, est == "sgvb")
+    obj = ImportanceWeightedObjective(gen, var, axis=0, estimator=est)
+    with _rng.inject(**inj):
+        loss = obj({"x": T(g["x"], dev, dt)})
+    rt = 1e-5 if dn == "f32" else 1e-10
+    close(loss, g[p + "loss"], rt)
+    close(var.nodes["z"].dist.sample_cache, g[p + "z"], rt)
+    close(var.nodes["z"].log_prob(), g[p + "logq"], rt)
+    close(gen.nodes["z"].log_prob(), g[p + "logpz"], rt)
+    close(gen.nodes["x"].log_prob(), g[p + "logpx"], rt)
+    leaves = [probs, a] + ([b] if b is not None else [])
+    grads = torch.autograd.grad(loss, leaves)
+    # fp32: gradients go through exp(log w) with |log w| ~ 30: 4e-5 covers one ulp of the log-weights
+    gt = 4e-5 if dn == "f32" else 1e-10
+    ref = {k: g[(p if est == "sgvb" or dn == "f64" else p.replace("f32", "f64")) + k] for k in ("dprobs", "da")}
+    close(grads[0], ref["dprobs"], gt)
+    close(grads[1], ref["da"], gt)
+    if b is not None:
+        close(grads[2], g[(p if est == "sgvb" or dn == "f64" else p.replace("f32", "f64")) + "db"], gt)
+
+
+def test_elbo_path_against_reference_golden(dev, golden):
+    """VAE ELBO (config 1 shapes, reduce_mean_dims=[0], reduce_sum_dims=[1]) vs the reference."""
+    g = golden("elbo_path")
+    B, Z = g["mean"].shape
+
+    class G(BayesianNet):
+        def __init__(self, probs):
+            super().__init__(device=probs.device)
+            self.probs = probs
+
+        def forward(self, observed):
+            self.observe(observed)
+            d = self.probs.device
+            self.normal("z", mean=torch.zeros([B, Z], device=d), std=torch.ones([B, Z], device=d),
+                        reduce_mean_dims=[0], reduce_sum_dims=[1])
+            self.bernoulli("x", probs=self.probs, reduce_mean_dims=[0], reduce_sum_dims=[1])
+            return self
+
+    class V(BayesianNet):
+        def __init__(self, m, s):
+            super().__init__(device=m.device)
+            self.m, self.s = m, s
+
+        def forward(self, observed):
+            self.observe(observed)
+            self.normal("z", mean=self.m, std=self.s, reduce_mean_dims=[0], reduce_sum_dims=[1])
+            return self
+
+    m, s, probs = T(g["mean"], dev, grad=True), T(g["std"], dev, grad=True), T(g["probs"], dev, grad=True)
+    with _rng.inject(normal=[T(g["eps"], dev)] * 2):
+        loss = ELBO(G(probs), V(m, s))({"x": T(g["x"], dev)})
+    assert loss.dim() == 0
+    close(loss, g["f32_loss"], 1e-5)
+    dm, ds, dp = torch.autograd.grad(loss, [m, s, probs])
+    close(dm, g["f32_dmean"], 1e-5)
+    close(ds, g["f32_dstd"], 1e-5)
+    close(dp, g["f32_dprobs"], 1e-5)
+
+
+@pytest.mark.parametrize("est,latent", [("sgvb", "normal"), ("vimco", "bernoulli")])
+def test_fused_route_matches_two_pass_route(dev, est, latent):
+    """K >= 8 with a [K,B,X] Bernoulli likelihood takes the fused kernel; its loss and gradients must
+    equal those of the general route (zhusuan.variational.FUSED = False) on the same noise."""
+    if dev.type == "cpu" and torch.cuda.is_available():
+        pytest.skip("the fused route needs device-resident probabilities")
+    rng = np.random.RandomState(5)
+    K, B, Z, X = 10, 7, 4, 16
+    x = T((rng.uniform(size=(B, X)) < 0.5).astype(np.float32), dev)
+    results = []
+    for fused in (True, False):
+        zhusuan.variational.FUSED = fused
+        try:
+            probs = T(1 / (1 + np.exp(-rng.RandomState(6).standard_normal((K, B, X)))) if False else
+                      1 / (1 + np.exp(-np.random.RandomState(6).standard_normal((K, B, X)))), dev, grad=True)
+            if latent == "normal":
+                a = T(0.3 * np.random.RandomState(7).standard_normal((B, Z)), dev, grad=True)
+                b = T(0.1 * np.random.RandomState(8).standard_normal((B, Z)), dev, grad=True)
+                inj = dict(normal=[T(np.random.RandomState(9).standard_normal((K, B, Z)), dev)] * 2)
+            else:
+                a, b = T(np.random.RandomState(7).uniform(0.2, 0.8, size=(B, Z)), dev, grad=True), None
+                inj = dict(uniform=[T(np.random.RandomState(9).uniform(size=(K, B, Z)), dev)] * 2)
+            obj = ImportanceWeightedObjective(_PathGen(probs, K, latent), _PathVar(a, b, K, latent, est == "sgvb"),
+                                              axis=0, estimator=est)
+            with _rng.inject(**inj):
+                loss = obj({"x": x})
+            scale = 1.0 if fused else 1.0
+            (loss * 3.0).backward()  # a non-unit upstream gradient exercises zs_scale_inplace
+            results.append((loss.detach(), probs.grad.clone(), a.grad.clone(), None if b is None else b.grad.clone()))
+        finally:
+            zhusuan.variational.FUSED = True
+    for u, v in zip(*results):
+        if u is not None:
+            close(u, v, 2e-5)
+
+
+def test_fused_backward_runs_once(dev):
+    if dev.type == "cpu" and torch.cuda.is_available():
+        pytest.skip("the fused route needs device-resident probabilities")
+    K, B, Z, X = 8, 3, 2, 8
+    probs = torch.rand(K, B, X, device=dev).clamp(0.05, 0.95).requires_grad_()
+    a = torch.zeros(B, Z, device=dev, requires_grad=True)
+    b = torch.zeros(B, Z, device=dev, requires_grad=True)
+    obj = ImportanceWeightedObjective(_PathGen(probs, K, "normal"), _PathVar(a, b, K, "normal", True), axis=0)
+    loss = obj({"x": torch.ones(B, X, device=dev)})
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="once"):
+        loss.backward()
+
+
+def test_vimco_rejects_reparameterised_latents(dev):
+    K, B, Z, X = 4, 3, 2, 8
+    probs = torch.rand(K, B, X, device=dev)
+    a, b = torch.zeros(B, Z, device=dev), torch.zeros(B, Z, device=dev)
+    obj = ImportanceWeightedObjective(_PathGen(probs, K, "normal"), _PathVar(a, b, K, "normal", True), axis=0,
+                                      estimator="vimco")
+    with pytest.raises(ValueError, match="is_reparameterized must be false"):
+        obj({"x": torch.ones(B, X, device=dev)})
+
+
+# ============================================================================ SG-MCMC
+class _Well(BayesianNet):
+    """2x^2 - x^4 double well over one latent (test/mcmc/test_mcmc.py:24-37)."""
+
+    def __init__(self, x0, noise_std=0.0):
+        super().__init__()
+        self.nodes["x"] = type("N", (), {"tensor": x0})()
+        self.noise_std = noise_std
+
+    def forward(self, observed):
+        self.observe(observed)
+        return self
+
+    def _log_joint(self, use_cache=False):
+        x = self.observed["x"]
+        res = 2 * torch.pow(x, 2) - torch.pow(x, 4)
+        if self.noise_std:
+            res = res + self.noise_std * torch.randn_like(x)
+        return res.sum()
+
+
+def _sampler(name):
+    m = zhusuan.mcmc
+    return {"sgld": lambda: m.SGLD(learning_rate=0.01), "psgld": lambda: m.PSGLD(learning_rate=0.01),
+            "sghmc1": lambda: m.SGHMC(learning_rate=0.01, n_iter_resample_v=2, friction=0.3, variance_estimate=0.02,
+                                      second_order=False),
+            "sghmc2": lambda: m.SGHMC(learning_rate=0.01, n_iter_resample_v=2, friction=0.3, variance_estimate=0.02,
+                                      second_order=True)}[name]()
+
+
+@pytest.mark.parametrize("name", ["sgld", "psgld", "sghmc1", "sghmc2"])
+def test_sgmcmc_against_reference_trajectories(dev, golden, name):
+    """Four updates of each sampler with the noise the reference consumed (make_golden.py:gen_sgmcmc)."""
+    g = golden("sgmcmc")
+    unit, calls = g["unit_noise"].astype(np.float32), g[name + "_f32_calls"]
+    sampler = _sampler(name)
+    x0 = T(g["x0"], dev, grad=True)
+    model = _Well(x0)
+    out = sampler.sample(model, {}, True)
+    assert out["x"] is x0 and sampler.t == 1  # resample=True: no update, pre-detach draws (Q13)
+    for s in range(int(g["steps"])):
+        stds = calls[calls[:, 0] == s][:, 1]
+        # the reference's torch.normal(mean=0, std=s, size) calls of this update, in order; PSGLD's
+        # tensor-std call (recorded as -1) takes unit normals
+        inj = [T(unit[s, j % 2] * (np.float32(sd) if sd >= 0 else np.float32(1.0)), dev) for j, sd in enumerate(stds)]
+        with _rng.inject(normal=inj):
+            w = sampler.sample(model, {}, False)["x"]
+        assert w.requires_grad and w.is_leaf and w.device.type == dev.type
+        np.testing.assert_allclose(w.detach().cpu().numpy(), g[name + "_f32_traj"][s], rtol=2e-5, atol=2e-6)
+    assert sampler.t == 1 + int(g["steps"])
+
+
+@pytest.mark.parametrize("name,bound", [("sgld", 0.023), ("psgld", 0.088), ("sghmc1", 0.016), ("sghmc2", 0.016)])
+def test_sgmcmc_double_well(dev, name, bound):
+    """100 chains on the double well with N(0,2) gradient noise; KDE of the samples against the true
+    density, with the reference's own error bounds (test/mcmc/test_mcmc.py:74-107)."""
+    if dev.type == "cpu" and torch.cuda.is_available():
+        pytest.skip("host-shuttle mode is covered by the trajectory test")
+    n_iters = 8000 if dev.type == "cuda" else 3000
+    m = zhusuan.mcmc
+    sampler = {"sgld": lambda: m.SGLD(learning_rate=0.01), "psgld": lambda: m.PSGLD(learning_rate=0.01),
+               "sghmc1": lambda: m.SGHMC(learning_rate=0.01, n_iter_resample_v=50, friction=0.3,
+                                         variance_estimate=0.02, second_order=False),
+               "sghmc2": lambda: m.SGHMC(learning_rate=0.01, n_iter_resample_v=50, friction=0.3,
+                                         variance_estimate=0.02, second_order=True)}[name]()
+    torch.manual_seed(0)
+    x = torch.zeros([100], device=dev, requires_grad=True)
+    model = _Well(x, noise_std=2.0)
+    samples = []
+    burn = n_iters * 2 // 3
+    for t in range(n_iters):
+        xs = sampler.sample(model, {}, t == 0)["x"]
+        if t >= burn and t % 50 == 0:
+            samples.append(xs.detach().cpu().numpy().copy())
+    samples = np.array(samples).reshape(-1)
+    assert not np.isnan(samples).any()
+    xs = np.linspace(-3, 3, 1000)
+    pdf = np.exp(2 * xs ** 2 - xs ** 4)
+    pdf = pdf / pdf.mean() / 6
+    err = np.abs(stats.gaussian_kde(samples)(xs) - pdf).mean()
+    assert err < (bound if dev.type == "cuda" else 2.5 * bound), err
+
+
+def test_sghmc_multiple_latents(dev):
+    """The reference raises for differently-shaped latents (shared gaussian_term, SGHMC.py:34); the
+    B200 build draws one term per variable."""
+
+    class Two(BayesianNet):
+        def __init__(self, d):
+            super().__init__(device=d)
+
+        def forward(self, observed):
+            self.observe(observed)
+            d = self.device
+            self.normal("a", mean=torch.zeros(3, 4, device=d), std=torch.ones(3, 4, device=d), n_samples=5,
+                        group_ndims=2, reduce_mean_dims=[0])
+            self.normal("b", mean=torch.zeros(2, device=d), std=torch.ones(2, device=d), n_samples=5, group_ndims=1,
+                        reduce_mean_dims=[0])
+            return self
+
+    net = Two(dev)
+    for second in (False, True):
+        s = zhusuan.mcmc.SGHMC(learning_rate=1e-2, second_order=second)
+        w = s.sample(net, {}, True)
+        assert set(w) == {"a", "b"}
+        for _ in range(3):
+            w = s.sample(net, {}, False)
+        assert tuple(w["a"].shape) == (5, 3, 4) and tuple(w["b"].shape) == (5, 2)
+        assert torch.isfinite(w["a"]).all() and w["a"].requires_grad

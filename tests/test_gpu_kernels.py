@@ -414,13 +414,20 @@ def test_fused_invalid_probs_give_nan():
     assert np.isnan(lp[3, 1]) and np.isfinite(np.delete(lp.ravel(), 3 * B + 1)).all()
 
 
-def test_fused_unsupported_shapes_return_none():
-    probs, x, other, logq = _fused_inputs(4, 3, 16)
-    assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # K < 8
+def test_fused_shape_coverage(oracle):
+    """X % 4 != 0 is refused (callers use the two-pass kernels); small K and columns far larger than
+    shared memory are handled (the ring streams rows, it does not keep a column resident)."""
     probs, x, other, logq = _fused_inputs(8, 3, 18)
     assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # X % 4
-    probs, x, other, logq = _fused_inputs(100, 2, 784)
-    assert be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), None, None, 1.0) is None  # does not fit smem
+    for K, B, X in [(4, 3, 16), (2, 5, 8), (100, 6, 784), (7, 9, 4096), (200, 3, 2048)]:
+        probs, x, other, logq = _fused_inputs(K, B, X)
+        r = be.iw_bernoulli_fused(be.VIMCO, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B, want_logpx=True)
+        assert r is not None
+        o = oracle.iw_bernoulli_step(oracle.VIMCO, probs.astype(np.float64), x.astype(np.float64),
+                                     other.astype(np.float64), logq.astype(np.float64))
+        close(host(r["logpx"]), o["logpx"], 1e-5)
+        close(host(r["cost"]).mean(), o["cost"].mean(), 1e-5)
+        close(host(r["dprobs"]), o["dprobs"], 3e-4)
 
 
 def test_iw_step_host(oracle):

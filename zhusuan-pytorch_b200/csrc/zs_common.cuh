@@ -55,17 +55,19 @@ template <typename T>
 __device__ __forceinline__ Pack<T> ld_pack(const T* p) {
     return *reinterpret_cast<const Pack<T>*>(p);
 }
-// streaming (read-once) load: do not keep the line in L1
+// streaming (read-once) load: do not keep the line in L1.  NOT volatile: the compiler must be free
+// to hoist and batch these loads (several in flight per warp); a volatile asm pins each load behind
+// the previous load's consumers and leaves the kernel latency-bound (profiles/r1_notes.md).
 __device__ __forceinline__ Pack<float> ld_pack_stream(const float* p) {
     Pack<float> r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
                  : "l"(p));
     return r;
 }
 __device__ __forceinline__ Pack<double> ld_pack_stream(const double* p) {
     Pack<double> r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
     return r;
 }
 template <typename T>

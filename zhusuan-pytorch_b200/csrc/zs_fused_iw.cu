@@ -17,11 +17,24 @@
 //            of the CTA's next column, so next-column loads overlap this column's stores.
 // HBM traffic per particle-sample: 4X read + 4X write (+ [K,B] scalars) instead of 8X + 4X for the
 // two-pass form; the unfused entry points remain as the general fallback.
+#include <stdlib.h>
+
 #include "zs_common.cuh"
 
 namespace zs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 128-bit shared-memory load.  Written as asm because the compiler otherwise scalarises the float4 into
+// four LDS.32 whose lane stride of 16 B is a 4-way bank conflict (profiles/r1_notes.md).  volatile keeps
+// it ordered after the mbarrier wait that publishes the slot.
+__device__ __forceinline__ float4 lds128(const float4* p) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "r"(smem_u32(p)));
+    return r;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -296,6 +309,543 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column-fused variant that keeps the in-flight columns in L2 instead of shared memory.
+// A CTA walks batch columns; phase A streams the K rows of its column from HBM and reduces their
+// log-pmf, warp 0 forms the weights, phase B RE-READS the same rows — now L2 hits, the 126 MB L2
+// holds every in-flight column (CTAs * K*X*4 bytes, 46 MB at 2 CTAs/SM) — and writes dprobs.
+// HBM traffic equals the shared-memory variant (probs once, dprobs once) but several CTAs per SM sit
+// in different phases, so loads, math and stores overlap by thread-level parallelism and there is no
+// K*X shared-memory limit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// not volatile: loads of read-only data may be hoisted and batched by the compiler
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_hint(float* p, const float4& v, uint64_t) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+constexpr int COLF_ROW_WARPS_MAX = 12;                         // row-owning warps per CTA
+constexpr int COLF_MAX_THREADS = (COLF_ROW_WARPS_MAX + 1) * 32;  // + one objective warp
+constexpr int COLF_BATCH = 4;                                  // float4 loads in flight per lane
+constexpr int COLF_MIN_CTAS = 3;
+
+// log-pmf contribution of 4 elements (log2 units) / their dprobs; binary x needs one SFU op per element
+template <bool BINARY>
+__device__ __forceinline__ float lpmf4(const float4& p, const float4& xx, float& mn) {
+    if (BINARY) {
+        float a, b, acc;
+        a = p.x + 1e-8f; b = (1.0f - p.x) + 1e-8f; mn = fminf(mn, fminf(a, b)); acc = fast_log2(xx.x == 1.f ? a : b);
+        a = p.y + 1e-8f; b = (1.0f - p.y) + 1e-8f; mn = fminf(mn, fminf(a, b)); acc += fast_log2(xx.y == 1.f ? a : b);
+        a = p.z + 1e-8f; b = (1.0f - p.z) + 1e-8f; mn = fminf(mn, fminf(a, b)); acc += fast_log2(xx.z == 1.f ? a : b);
+        a = p.w + 1e-8f; b = (1.0f - p.w) + 1e-8f; mn = fminf(mn, fminf(a, b)); acc += fast_log2(xx.w == 1.f ? a : b);
+        return acc;
+    }
+    float acc = xx.x * fast_log2(p.x + 1e-8f) + (1.0f - xx.x) * fast_log2((1.0f - p.x) + 1e-8f);
+    acc += xx.y * fast_log2(p.y + 1e-8f) + (1.0f - xx.y) * fast_log2((1.0f - p.y) + 1e-8f);
+    acc += xx.z * fast_log2(p.z + 1e-8f) + (1.0f - xx.z) * fast_log2((1.0f - p.z) + 1e-8f);
+    acc += xx.w * fast_log2(p.w + 1e-8f) + (1.0f - xx.w) * fast_log2((1.0f - p.w) + 1e-8f);
+    return acc;
+}
+template <bool BINARY>
+__device__ __forceinline__ float4 dprobs4(const float4& p, const float4& xx, float g) {
+    float4 o;
+    if (BINARY) {
+        const float ng = -g;
+        o.x = (xx.x == 1.f ? g : ng) * fast_rcp(xx.x == 1.f ? p.x + 1e-8f : (1.0f - p.x) + 1e-8f);
+        o.y = (xx.y == 1.f ? g : ng) * fast_rcp(xx.y == 1.f ? p.y + 1e-8f : (1.0f - p.y) + 1e-8f);
+        o.z = (xx.z == 1.f ? g : ng) * fast_rcp(xx.z == 1.f ? p.z + 1e-8f : (1.0f - p.z) + 1e-8f);
+        o.w = (xx.w == 1.f ? g : ng) * fast_rcp(xx.w == 1.f ? p.w + 1e-8f : (1.0f - p.w) + 1e-8f);
+    } else {
+        o.x = (g * xx.x) * fast_rcp(p.x + 1e-8f) - (g * (1.0f - xx.x)) * fast_rcp((1.0f - p.x) + 1e-8f);
+        o.y = (g * xx.y) * fast_rcp(p.y + 1e-8f) - (g * (1.0f - xx.y)) * fast_rcp((1.0f - p.y) + 1e-8f);
+        o.z = (g * xx.z) * fast_rcp(p.z + 1e-8f) - (g * (1.0f - xx.z)) * fast_rcp((1.0f - p.z) + 1e-8f);
+        o.w = (g * xx.w) * fast_rcp(p.w + 1e-8f) - (g * (1.0f - xx.w)) * fast_rcp((1.0f - p.w) + 1e-8f);
+    }
+    return o;
+}
+
+template <bool BINARY>
+__device__ __forceinline__ float row_logpmf(const float4* __restrict__ p4, const float4* __restrict__ x4, int X4,
+                                            int lane, uint64_t pol) {
+    float acc = 0.f, mn = 1.0f;
+    for (int v0 = lane; v0 < X4; v0 += 32 * COLF_BATCH) {
+        float4 p[COLF_BATCH];
+#pragma unroll
+        for (int u = 0; u < COLF_BATCH; ++u) {
+            const int v = v0 + 32 * u;
+            p[u] = ldg_hint(p4 + (v < X4 ? v : v0), pol);  // always in bounds: p[] stays in registers
+        }
+#pragma unroll
+        for (int u = 0; u < COLF_BATCH; ++u) {
+            const int v = v0 + 32 * u;
+            if (v < X4) acc += lpmf4<BINARY>(p[u], lds128(x4 + v), mn);
+        }
+    }
+    if (BINARY && mn < 0.f) acc = __int_as_float(0x7fc00000);  // a negative log argument is NaN in the reference
+    return acc;
+}
+
+template <bool BINARY>
+__device__ __forceinline__ void row_dprobs(float* __restrict__ drow, const float4* __restrict__ p4,
+                                           const float4* __restrict__ x4, int X4, int lane, float g, uint64_t pol) {
+    for (int v0 = lane; v0 < X4; v0 += 32 * COLF_BATCH) {
+        float4 p[COLF_BATCH];
+#pragma unroll
+        for (int u = 0; u < COLF_BATCH; ++u) {
+            const int v = v0 + 32 * u;
+            p[u] = ldg_hint(p4 + (v < X4 ? v : v0), pol);
+        }
+#pragma unroll
+        for (int u = 0; u < COLF_BATCH; ++u) {
+            const int v = v0 + 32 * u;
+            if (v < X4) stg_hint(drow + 4 * v, dprobs4<BINARY>(p[u], lds128(x4 + v), g), pol);
+        }
+    }
+}
+
+// Objective warp: turns the K log-weights of a column into cost, dlogp, dlogq (global) — off the
+// critical path of the row warps.  Same math as k_iw_objective; reciprocal instead of IEEE division.
+template <int EST>
+__device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
+                                               const float* s_other, const float* s_lq, double* s_xw, float gscale,
+                                               float* __restrict__ cost, float* __restrict__ dlogp,
+                                               float* __restrict__ dlogq, float* __restrict__ logpx_out) {
+    const unsigned FULL = 0xffffffffu;
+    // log-weights in double; max in float (any value within an ulp of the max stabilises exp)
+    float mf = -INFINITY;
+    for (int k = lane; k < K; k += 32) {
+        double xv = ((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k];
+        s_xw[k] = xv;
+        mf = fmaxf(mf, (float)xv);
+    }
+    mf = warp_max(mf);
+    const double m1 = (double)mf;
+    float S = 0.f;
+    double sumd = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double d = s_xw[k] - m1;
+        S += expf((float)d);
+        if (EST == ZS_EST_VIMCO) sumd += d;
+    }
+    S = warp_sum(S);
+    const float invS = fast_rcp(S) * (2.0f - S * fast_rcp(S));  // one Newton step: ~1 ulp
+    float gap = 0.f, S2 = 0.f;  // gap = m1 - (second max), S2 = sum_{k != argmax} exp(x_k - second max)
+    int i1 = -1;
+    if (EST == ZS_EST_VIMCO) {
+        sumd = warp_sum(sumd);
+        // arg-max (smallest index among ties) and second max, needed only for the arg-max row
+        double best = -INFINITY;
+        for (int k = lane; k < K; k += 32)
+            if (s_xw[k] > best) { best = s_xw[k]; i1 = k; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(FULL, best, o);
+            int oi = __shfl_xor_sync(FULL, i1, o);
+            if (oi >= 0 && (i1 < 0 || ob > best || (ob == best && oi < i1))) { best = ob; i1 = oi; }
+        }
+        double m2 = -INFINITY;
+        for (int k = lane; k < K; k += 32)
+            if (k != i1) m2 = fmax(m2, s_xw[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m2 = fmax(m2, __shfl_xor_sync(FULL, m2, o));
+        gap = (float)(m1 - m2);
+        if (gap > 1.0f) {
+            for (int k = lane; k < K; k += 32)
+                if (k != i1) S2 += expf((float)(s_xw[k] - m2));
+            S2 = warp_sum(S2);
+        }
+    }
+    double c_acc = 0.0;
+    const double km1 = (double)(K - 1);
+    for (int k = lane; k < K; k += 32) {
+        const double xv = s_xw[k];
+        const float e = expf((float)(xv - m1));
+        const float wt = e * invS;
+        c_acc -= (double)wt * xv;
+        float gq = wt;
+        if (EST == ZS_EST_VIMCO) {
+            const float lq = s_lq[k];
+            const float mu_m = (float)((sumd - (xv - m1)) / km1);
+            float sig;
+            if (k == i1 && gap > 1.0f) {
+                // the arg-max row: S - e would cancel, re-centre on the second max (mu_m is relative to m1)
+                const float Sloo = S2 + expf(mu_m + gap);
+                sig = gap + (logf(S) - logf(Sloo));
+            } else {
+                sig = -log1pf((expf(mu_m) - e) * invS);
+            }
+            c_acc -= (double)lq * (double)sig;
+            gq = wt - sig;
+        }
+        if (dlogp) dlogp[(int64_t)k * B + b] = -wt * gscale;
+        if (dlogq) dlogq[(int64_t)k * B + b] = gq * gscale;
+        if (logpx_out) logpx_out[(int64_t)k * B + b] = s_lpx[k];
+    }
+    c_acc = warp_sum(c_acc);
+    if (lane == 0 && cost) cost[b] = (float)c_acc;
+}
+
+// Every row warp needs only max and sum-exp of the column to weight its own rows.
+__device__ __forceinline__ void colf_max_sumexp(int lane, int K, const float* s_lpx, const float* s_other,
+                                                const float* s_lq, double& m1, float& invS) {
+    float mf = -INFINITY;
+    for (int k = lane; k < K; k += 32)
+        mf = fmaxf(mf, (float)(((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k]));
+    mf = warp_max(mf);
+    m1 = (double)mf;
+    float S = 0.f;
+    for (int k = lane; k < K; k += 32)
+        S += expf((float)((((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k]) - m1));
+    S = warp_sum(S);
+    invS = fast_rcp(S) * (2.0f - S * fast_rcp(S));
+}
+
+template <int EST, bool TRACE>
+__global__ void __launch_bounds__(COLF_MAX_THREADS, COLF_MIN_CTAS)
+    k_iw_bernoulli_colfused(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
+                            float* __restrict__ dlogq, float* __restrict__ logpx_out,
+                            const float* __restrict__ probs, const float* __restrict__ x,
+                            const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B,
+                            int X, float gscale, long long* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int Kpad = (K + 3) & ~3;
+    float* s_x = reinterpret_cast<float*>(smem);                      // [3][X]    x rows, by column % 3
+    double* s_xw = reinterpret_cast<double*>(s_x + 3 * (size_t)X);    // [Kpad]    objective warp scratch
+    float* s_lpx = reinterpret_cast<float*>(s_xw + Kpad);              // [2][Kpad] by column parity
+    float* s_other = s_lpx + 2 * Kpad;                                 // [2][Kpad]
+    float* s_lq = s_other + 2 * Kpad;                                  // [2][Kpad]
+    int* s_bin = reinterpret_cast<int*>(s_lq + 2 * Kpad);              // [3]       x row is binary
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = (blockDim.x >> 5) - 1;  // row warps; warp NW is the objective warp
+    const bool is_obj = warp == NW;
+    const int X4 = X >> 2;
+    const float LN2 = 0.6931471805599453f;
+    const uint64_t keep = 0, done = 0;  // placeholders for L2 eviction policies (see ldg_hint)
+    auto mark = [&](int col, int point) {
+        if (TRACE && trace != nullptr && threadIdx.x == 0 && col < 8)
+            trace[(int64_t)blockIdx.x * 40 + col * 5 + point] = clock64();
+    };
+
+    // Staging done by the objective warp, ahead of the row warps:
+    //   per-column scalars (other log-weight terms) one column ahead, the observation row x two ahead
+    auto stage_scalars = [&](int64_t b, int par) {
+        for (int k = lane; k < K; k += 32) {
+            s_other[par * Kpad + k] = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
+            s_lq[par * Kpad + k] = logq ? logq[(int64_t)k * B + b] : 0.f;
+        }
+    };
+    auto stage_x = [&](int64_t b, int slot) {
+        const float4* src = reinterpret_cast<const float4*>(x + b * X);
+        float4* dst = reinterpret_cast<float4*>(s_x + (size_t)slot * X);
+        bool binary = true;
+        for (int v = lane; v < X4; v += 32) {
+            const float4 xx = __ldg(src + v);
+            dst[v] = xx;
+            binary = binary && (xx.x == 0.f || xx.x == 1.f) && (xx.y == 0.f || xx.y == 1.f) &&
+                     (xx.z == 0.f || xx.z == 1.f) && (xx.w == 0.f || xx.w == 1.f);
+        }
+        binary = __all_sync(0xffffffffu, binary);
+        if (lane == 0) s_bin[slot] = binary ? 1 : 0;
+    };
+    if (is_obj) {
+        const int64_t b0 = blockIdx.x, b1 = b0 + gridDim.x;
+        if (b0 < B) { stage_scalars(b0, 0); stage_x(b0, 0); }
+        if (b1 < B) stage_x(b1, 1);
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+        const int par = it & 1, slot = it % 3;
+        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)slot * X);
+        const bool binary = s_bin[slot] != 0;
+        mark(it, 0);
+        if (!is_obj) {
+            // ---- phase A: stream the rows from HBM (they stay in L2), reduce their log-pmf ----------
+            for (int k = warp; k < K; k += NW) {
+                const float4* p4 = reinterpret_cast<const float4*>(probs + ((int64_t)k * B + b) * X);
+                float acc = binary ? row_logpmf<true>(p4, x4, X4, lane, keep) : row_logpmf<false>(p4, x4, X4, lane, keep);
+                acc = warp_sum(acc);
+                if (lane == 0) s_lpx[par * Kpad + k] = acc * LN2;
+            }
+        }
+        mark(it, 1);
+        __syncthreads();  // lpx of this column complete; everything staged so far is visible
+        mark(it, 2);
+        if (is_obj) {
+            colf_objective<EST>(lane, K, B, b, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, s_xw, gscale,
+                                cost, dlogp, dlogq, logpx_out);
+            const int64_t b1 = b + gridDim.x, b2 = b1 + gridDim.x;
+            if (b1 < B) stage_scalars(b1, par ^ 1);
+            if (b2 < B) stage_x(b2, (it + 2) % 3);
+        } else if (dprobs) {
+            // ---- phase B: weights of the owned rows, then the rows again (L2 hits) -> dprobs ---------
+            double m1;
+            float invS;
+            colf_max_sumexp(lane, K, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, m1, invS);
+            for (int k = warp; k < K; k += NW) {
+                const double xv = ((double)s_lpx[par * Kpad + k] - (double)s_lq[par * Kpad + k]) +
+                                  (double)s_other[par * Kpad + k];
+                const float g = -(expf((float)(xv - m1)) * invS) * gscale;
+                const float4* p4 = reinterpret_cast<const float4*>(probs + ((int64_t)k * B + b) * X);
+                float* drow = dprobs + ((int64_t)k * B + b) * X;
+                if (binary) row_dprobs<true>(drow, p4, x4, X4, lane, g, done);
+                else row_dprobs<false>(drow, p4, x4, X4, lane, g, done);
+            }
+        }
+        mark(it, 3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ring variant (default): one persistent CTA per SM, warp-specialised.
+//   row warps      : warp w owns rows k = w, w+NW, ... of every column and a private mini-ring of D
+//                    shared-memory row slots.  Its task stream is
+//                       A(c,k)  first read of the row   (HBM)  -> log-pmf
+//                       B(c,k)  second read of the row  (L2 hit: only ~2 columns per SM are in flight,
+//                                                        ~46 MB chip-wide)  -> dprobs
+//                    Rows arrive by 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) that the
+//                    warp issues itself, D tasks ahead, each time it has consumed a slot: the bytes in
+//                    flight live in shared memory (NW*D*X*4, ~150 KB), not in registers, and A(c+1) loads
+//                    overlap B(c) stores.  Each row warp derives max / sum-exp of the column redundantly,
+//                    so the only CTA-wide rendezvous per column is one named barrier after phase A.
+//   stager warp    : stages the observation row x and the per-column scalars of the columns ahead.
+//   objective warps: two, alternating columns: cost, dlogp, dlogq of a column, with two column periods
+//                    to finish — off the row warps' critical path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct RingLayout {
+    int K, X, R, Kpad;
+    __host__ __device__ RingLayout(int K_, int X_, int R_) : K(K_), X(X_), R(R_), Kpad((K_ + 3) & ~3) {}
+    __host__ __device__ size_t slots_off() const { return 0; }
+    __host__ __device__ size_t x_off() const { return (size_t)R * X * 4; }
+    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)3 * X * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t lpx_off() const { return xw_off() + (size_t)2 * Kpad * 8; }    // xw: [2][Kpad] double
+    __host__ __device__ size_t other_off() const { return lpx_off() + (size_t)4 * Kpad * 4; }  // [4][Kpad]
+    __host__ __device__ size_t lq_off() const { return other_off() + (size_t)4 * Kpad * 4; }
+    __host__ __device__ size_t bin_off() const { return lq_off() + (size_t)4 * Kpad * 4; }
+    __host__ __device__ size_t bar_off() const { return (bin_off() + 16 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t total() const { return bar_off() + (size_t)R * 8; }
+};
+
+template <bool BINARY>
+__device__ __forceinline__ float smem_row_logpmf(const float4* __restrict__ p4, const float4* __restrict__ x4, int X4,
+                                                 int lane) {
+    float acc = 0.f, mn = 1.0f;
+#pragma unroll 4
+    for (int v = lane; v < X4; v += 32) acc += lpmf4<BINARY>(lds128(p4 + v), lds128(x4 + v), mn);
+    if (BINARY && mn < 0.f) acc = __int_as_float(0x7fc00000);
+    return acc;
+}
+template <bool BINARY>
+__device__ __forceinline__ void smem_row_dprobs(float* __restrict__ drow, const float4* __restrict__ p4,
+                                                const float4* __restrict__ x4, int X4, int lane, float g) {
+#pragma unroll 4
+    for (int v = lane; v < X4; v += 32) stg_hint(drow + 4 * v, dprobs4<BINARY>(lds128(p4 + v), lds128(x4 + v), g), 0);
+}
+
+template <int EST, bool TRACE>
+__global__ void __launch_bounds__(1024, 1)
+    k_iw_bernoulli_ring(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
+                        float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
+                        const float* __restrict__ x, const float* __restrict__ logp_other,
+                        const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
+                        long long* __restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const RingLayout L(K, X, R);
+    const int Kpad = L.Kpad;
+    float* slots = reinterpret_cast<float*>(smem + L.slots_off());
+    float* s_x = reinterpret_cast<float*>(smem + L.x_off());
+    double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
+    float* s_lpx = reinterpret_cast<float*>(smem + L.lpx_off());
+    float* s_other = reinterpret_cast<float*>(smem + L.other_off());
+    float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
+    int* s_bin = reinterpret_cast<int*>(smem + L.bin_off());
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off());
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles: [0, NW) row warps | NW stager | NW+1, NW+2 objective warps for even / odd columns
+    const int NW = (blockDim.x >> 5) - 3;
+    const bool is_stager = warp == NW, is_obj = warp > NW;
+    const int X4 = X >> 2;
+    const uint32_t row_bytes = (uint32_t)X * 4u;
+    const float LN2 = 0.6931471805599453f;
+    const int phases = dprobs ? 2 : 1;
+    const int64_t ncols = ((int64_t)blockIdx.x < B) ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto mark = [&](int col, int point) {
+        if (TRACE && trace != nullptr && threadIdx.x == 0 && col < 8)
+            trace[(int64_t)blockIdx.x * 40 + col * 5 + point] = clock64();
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Per-column scalars and log-pmf live in 4 buffers (column & 3), the x row in 3 (column % 3):
+    // an objective warp may work on column c until the barrier of column c+2.
+    auto stage_scalars = [&](int64_t b, int buf) {
+        for (int k = lane; k < K; k += 32) {
+            s_other[buf * Kpad + k] = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
+            s_lq[buf * Kpad + k] = logq ? logq[(int64_t)k * B + b] : 0.f;
+        }
+    };
+    auto stage_x = [&](int64_t b, int slot) {
+        const float4* src = reinterpret_cast<const float4*>(x + b * X);
+        float4* dst = reinterpret_cast<float4*>(s_x + (size_t)slot * X);
+        bool binary = true;
+        for (int v = lane; v < X4; v += 32) {
+            const float4 xx = __ldg(src + v);
+            dst[v] = xx;
+            binary = binary && (xx.x == 0.f || xx.x == 1.f) && (xx.y == 0.f || xx.y == 1.f) &&
+                     (xx.z == 0.f || xx.z == 1.f) && (xx.w == 0.f || xx.w == 1.f);
+        }
+        binary = __all_sync(0xffffffffu, binary);
+        if (lane == 0) s_bin[slot] = binary ? 1 : 0;
+    };
+    if (is_stager && ncols > 0) {
+        stage_scalars(blockIdx.x, 0);
+        stage_x(blockIdx.x, 0);
+        if (ncols > 1) stage_x((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+
+    // column c rendezvous on named barrier 1 + (c & 1): row warps, the stager and the objective warp
+    // of that parity
+    const int sync_threads = (NW + 2) * 32;
+    if (is_stager) {
+        int64_t b = blockIdx.x;
+        for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+            named_bar_sync(1 + (int)(c & 1), sync_threads);
+            if (c + 1 < ncols) stage_scalars(b + gridDim.x, (int)((c + 1) & 3));
+            if (c + 2 < ncols) stage_x(b + 2 * (int64_t)gridDim.x, (int)((c + 2) % 3));
+        }
+        return;
+    }
+    if (is_obj) {
+        // ---- objective warps: cost / dlogp / dlogq of every other column ----------------------------
+        const int p = warp - NW - 1;
+        int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
+            const int buf = (int)(c & 3);
+            named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
+            colf_objective<EST>(lane, K, B, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+        }
+        return;
+    }
+
+    // ---- row warps.  Warp w owns the D slots [w*D, w*D+D) and its row tasks, in order
+    //   A(c, w), A(c, w+NW), ..., B(c, w), B(c, w+NW), ..., A(c+1, w), ...
+    // (A = first read, HBM; B = second read of the same row, an L2 hit).  After consuming a slot the
+    // warp itself re-arms the slot's mbarrier and issues the bulk copy of the task D ahead, so up to D
+    // rows per warp are in flight in shared memory and A(c+1) loads overlap B(c) stores.  A slot is
+    // filled and waited on by one warp only, so its mbarrier phases are always observed in sequence.
+    const int D = R / NW;
+    const int my_rows = (K - warp + NW - 1) / NW;
+    // prefetch cursor (lane 0 only uses it)
+    int64_t pf_c = 0, pf_b = blockIdx.x;
+    int pf_ph = 0, pf_j = 0, pf_pos = 0;
+    auto issue_next = [&]() {
+        if (pf_c >= ncols || my_rows == 0) return;
+        const int k = warp + pf_j * NW;
+        const int s = warp * D + pf_pos;
+        mbar_expect_tx(&full[s], row_bytes);
+        bulk_load(slots + (size_t)s * X, probs + ((int64_t)k * B + pf_b) * X, row_bytes, &full[s]);
+        if (++pf_pos == D) pf_pos = 0;
+        if (++pf_j == my_rows) {
+            pf_j = 0;
+            if (++pf_ph == phases) { pf_ph = 0; ++pf_c; pf_b += gridDim.x; }
+        }
+    };
+    if (lane == 0)
+        for (int i = 0; i < D; ++i) issue_next();
+
+    int ring_pos = 0;         // consumer cursor in the warp's mini-ring
+    uint32_t ring_phase = 0;  // parity of the fill being waited for
+    int64_t b = blockIdx.x;
+    for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+        const int par = (int)(c & 3), xs = (int)(c % 3);
+        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * X);
+        const bool binary = s_bin[xs] != 0;
+        mark((int)c, 0);
+        // ---- phase A: log-pmf of the owned rows as they land ---------------------------------------
+        for (int k = warp; k < K; k += NW) {
+            const int s = warp * D + ring_pos;
+            mbar_wait(&full[s], ring_phase);
+            if (++ring_pos == D) { ring_pos = 0; ring_phase ^= 1u; }
+            const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)s * X);
+            float acc = binary ? smem_row_logpmf<true>(p4, x4, X4, lane) : smem_row_logpmf<false>(p4, x4, X4, lane);
+            acc = warp_sum(acc);  // every lane has finished reading the slot
+            if (lane == 0) {
+                s_lpx[par * Kpad + k] = acc * LN2;
+                issue_next();
+            }
+        }
+        mark((int)c, 1);
+        named_bar_sync(1 + (int)(c & 1), sync_threads);
+        mark((int)c, 2);
+        if (dprobs) {
+            // ---- phase B: weights of the owned rows, rows again (L2) -> dprobs ----------------------
+            double m1;
+            float invS;
+            colf_max_sumexp(lane, K, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, m1, invS);
+            for (int k = warp; k < K; k += NW) {
+                const double xv = ((double)s_lpx[par * Kpad + k] - (double)s_lq[par * Kpad + k]) +
+                                  (double)s_other[par * Kpad + k];
+                const float g = -(expf((float)(xv - m1)) * invS) * gscale;
+                const int s = warp * D + ring_pos;
+                mbar_wait(&full[s], ring_phase);
+                if (++ring_pos == D) { ring_pos = 0; ring_phase ^= 1u; }
+                const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)s * X);
+                float* drow = dprobs + ((int64_t)k * B + b) * X;
+                if (binary) smem_row_dprobs<true>(drow, p4, x4, X4, lane, g);
+                else smem_row_dprobs<false>(drow, p4, x4, X4, lane, g);
+                __syncwarp();
+                if (lane == 0) issue_next();
+            }
+        }
+        mark((int)c, 3);
+    }
+}
+
+static int pick_warps_ring(int K) {
+    // row warps (<= 29: three more warps stage inputs and compute the objective); equal rows per warp
+    for (int d = 29; d >= 4; --d)
+        if (K % d == 0) return d;
+    return K < 24 ? (K < 1 ? 1 : K) : 24;
+}
+
+static int pick_warps_colf(int K) {
+    // row warps: equal rows per warp when a divisor of K exists in [4, COLF_ROW_WARPS_MAX]
+    for (int d = COLF_ROW_WARPS_MAX; d >= 4; --d)
+        if (K % d == 0) return d;
+    return K < COLF_ROW_WARPS_MAX ? (K < 1 ? 1 : K) : COLF_ROW_WARPS_MAX;
+}
+
 static int pick_warps(int K) {
     // each warp owns K/NW rows: prefer an exact divisor so phase A/B are balanced
     int best = 0;
@@ -316,20 +866,24 @@ int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X) {
     return (int64_t)FusedSmemLayout((int)K, (int)X).total();
 }
 
-int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                          const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                          int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
-    ZS_REQUIRE(probs && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
-    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
-    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
-    if (B == 0) return ZS_OK;
-    if (X % 4 != 0 || K < 8 || K > 4096 || X > (1 << 20)) {
-        set_last_error_msg("fused kernel needs X % 4 == 0 and 8 <= K <= 4096");
-        return ZS_ERR_UNSUPPORTED;
+static long long* g_trace = nullptr;
+
+static int fused_impl_choice() {
+    // ZS_FUSED_IMPL=smem selects the shared-memory resident-column kernel, =l2 the L2-resident one
+    static int choice = -1;
+    if (choice < 0) {
+        const char* e = getenv("ZS_FUSED_IMPL");
+        choice = (e && e[0] == 's') ? 0 : ((e && e[0] == 'l') ? 1 : 2);  // smem | l2 | ring (default)
     }
-    if (!aligned16(probs) || !aligned16(x) || !aligned16(dprobs)) {
-        set_last_error_msg("fused kernel needs 16-byte aligned probs / x / dprobs");
-        return ZS_ERR_ALIGN;
+    return choice;
+}
+
+static int launch_fused_smem(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                             const float* probs, const float* x, const float* logp_other, const float* logq,
+                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+    if (K < 8) {
+        set_last_error_msg("shared-memory fused kernel needs K >= 8");
+        return ZS_ERR_UNSUPPORTED;
     }
     const size_t smem = FusedSmemLayout((int)K, (int)X).total();
     int dev = 0, max_optin = 0;
@@ -352,6 +906,122 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                                                                logp_other, logq, (int)K, B, (int)X,
                                                                (float)grad_scale);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_fused");
+    return ZS_OK;
+}
+
+static int launch_fused_l2(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                           const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
+                           int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+    const int nw = pick_warps_colf((int)K);
+    const int threads = (nw + 1) * 32;
+    const int Kpad = ((int)K + 3) & ~3;
+    const size_t smem = (size_t)3 * X * 4 + (size_t)Kpad * (8 + 6 * 4) + 16;
+    if (smem > 200 * 1024) {
+        set_last_error_msg("fused kernel: K too large");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_colfused<ZS_EST_SGVB, false>
+                                         : k_iw_bernoulli_colfused<ZS_EST_VIMCO, false>;
+    if (g_trace != nullptr)
+        kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_colfused<ZS_EST_SGVB, true>
+                                        : k_iw_bernoulli_colfused<ZS_EST_VIMCO, true>;
+    if (smem > 48 * 1024) ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, l2 = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    int occ = 1;
+    ZS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    static int max_ctas = -1, l2_pct = -1;  // tuning knobs (tools/microbench.py sweeps them)
+    if (max_ctas < 0) {
+        const char* e = getenv("ZS_FUSED_CTAS_PER_SM");
+        max_ctas = e ? atoi(e) : 3;
+        const char* f = getenv("ZS_FUSED_L2_PCT");
+        l2_pct = f ? atoi(f) : 60;
+    }
+    if (occ > max_ctas) occ = max_ctas;
+    int64_t grid = (int64_t)sm_count() * occ;
+    // columns in flight must stay L2 resident between their two reads
+    const int64_t col_bytes = K * X * 4;
+    const int64_t cap = (l2 > 0 ? (int64_t)l2 : (int64_t)96 << 20) * l2_pct / 100 / (col_bytes > 0 ? col_bytes : 1);
+    if (cap >= 1 && grid > cap) grid = cap;
+    if (grid > B) grid = B;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
+                                                               logp_other, logq, (int)K, B, (int)X,
+                                                               (float)grad_scale, g_trace);
+    ZS_LAUNCH_CHECK("k_iw_bernoulli_colfused");
+    return ZS_OK;
+}
+
+static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                             const float* probs, const float* x, const float* logp_other, const float* logq,
+                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+    int dev = 0, max_optin = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // per-warp mini-rings: NW row warps x D slots each; deepest D (<= 4) that fits, fewer warps if needed
+    static int depth_cap = -1;
+    if (depth_cap < 0) {
+        const char* e = getenv("ZS_FUSED_RING_DEPTH");
+        depth_cap = e ? atoi(e) : 4;
+        if (depth_cap < 1) depth_cap = 1;
+    }
+    int nw = pick_warps_ring((int)K);
+    int D = depth_cap;
+    while (D > 1 && RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) --D;
+    while (nw > 1 && RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) --nw;
+    if (RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) {
+        set_last_error_msg("ring kernel: a row slot does not fit in shared memory");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    const int R = nw * D;
+    const size_t smem = RingLayout((int)K, (int)X, R).total();
+    const int threads = (nw + 3) * 32;
+    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_ring<ZS_EST_SGVB, false> : k_iw_bernoulli_ring<ZS_EST_VIMCO, false>;
+    if (g_trace != nullptr)
+        kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_ring<ZS_EST_SGVB, true> : k_iw_bernoulli_ring<ZS_EST_VIMCO, true>;
+    ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = sm_count();
+    if (grid > B) grid = B;
+    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
+                                                               logp_other, logq, (int)K, B, (int)X, R,
+                                                               (float)grad_scale, g_trace);
+    ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
+    return ZS_OK;
+}
+
+int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                          const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
+                          int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+    ZS_REQUIRE(probs && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
+    if (B == 0) return ZS_OK;
+    if (X % 4 != 0 || K > 4096 || X > (1 << 20)) {
+        set_last_error_msg("fused kernel needs X % 4 == 0 and K <= 4096");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    if (!aligned16(probs) || !aligned16(x) || !aligned16(dprobs)) {
+        set_last_error_msg("fused kernel needs 16-byte aligned probs / x / dprobs");
+        return ZS_ERR_ALIGN;
+    }
+    if (fused_impl_choice() == 0)
+        return launch_fused_smem(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
+                                 grad_scale, stream);
+    if (fused_impl_choice() == 2) {
+        int rc = launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B,
+                                   X, grad_scale, stream);
+        if (rc != ZS_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_fused_l2(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
+                           grad_scale, stream);
+}
+
+/* Debug hook (not part of the stable ABI surface used by the Python package): device buffer of
+ * grid*40 int64 that the L2-resident fused kernel fills with clock64() phase timestamps; NULL disables. */
+int zs_debug_set_trace(void* device_buffer) {
+    g_trace = (long long*)device_buffer;
     return ZS_OK;
 }
 

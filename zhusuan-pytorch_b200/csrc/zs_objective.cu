@@ -62,6 +62,22 @@ __global__ void __launch_bounds__(OBJ_THREADS)
         return ((A)logp[k * B + b] - (A)logq[k * B + b]) + (extra ? (A)extra[k * B + b] : A(0));
     };
 
+    if (EST == ZS_EST_ELBO) {
+        // ELBO.sgvb (elbo.py:155-156): -mean over particles of (logp - logq); d/dlogp = -1/K, d/dlogq = +1/K
+        A acc = A(0);
+        const T gk = gscale / (T)K;
+        if (valid) {
+            for (int64_t k = threadIdx.y; k < K; k += slices) {
+                acc -= logw(k);
+                if (dlogp) dlogp[k * B + b] = -gk;
+                if (dlogq) dlogq[k * B + b] = gk;
+            }
+        }
+        acc = slice_reduce(acc, sm, cols, slices, [](A a, A c) { return a + c; });
+        if (valid && threadIdx.y == 0 && cost) cost[b] = (T)(acc / (A)K);
+        return;
+    }
+
     // pass 1: max (and, for VIMCO, second max excluding the first argmax)
     A m1 = NEG_INF, m2 = NEG_INF, sumd = A(0);
     long long i1 = -1;
@@ -218,7 +234,7 @@ int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlo
                     const void* logq, const void* logp_extra, int64_t K, int64_t B, double grad_scale,
                     zs_stream_t stream) {
     ZS_REQUIRE(logp && logq && K >= 1 && B >= 0, ZS_ERR_ARG);
-    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO || estimator == ZS_EST_ELBO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && K < 2), ZS_ERR_ARG);
     if (B == 0) return ZS_OK;
     int cols, slices;
@@ -233,6 +249,10 @@ int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlo
             k_iw_objective<float, ZS_EST_SGVB><<<(unsigned)grid, block, smem, st>>>(
                 (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
                 (float)grad_scale, cols, slices);
+        else if (estimator == ZS_EST_ELBO)
+            k_iw_objective<float, ZS_EST_ELBO><<<(unsigned)grid, block, smem, st>>>(
+                (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
+                (float)grad_scale, cols, slices);
         else
             k_iw_objective<float, ZS_EST_VIMCO><<<(unsigned)grid, block, smem, st>>>(
                 (float*)cost, (float*)dlogp, (float*)dlogq, (const float*)logp, (const float*)logq, (const float*)logp_extra, K, B,
@@ -241,6 +261,10 @@ int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlo
         const size_t smem = OBJ_THREADS * (sizeof(double) + sizeof(long long));
         if (estimator == ZS_EST_SGVB)
             k_iw_objective<double, ZS_EST_SGVB><<<(unsigned)grid, block, smem, st>>>(
+                (double*)cost, (double*)dlogp, (double*)dlogq, (const double*)logp, (const double*)logq, (const double*)logp_extra, K, B,
+                grad_scale, cols, slices);
+        else if (estimator == ZS_EST_ELBO)
+            k_iw_objective<double, ZS_EST_ELBO><<<(unsigned)grid, block, smem, st>>>(
                 (double*)cost, (double*)dlogp, (double*)dlogq, (const double*)logp, (const double*)logq, (const double*)logp_extra, K, B,
                 grad_scale, cols, slices);
         else

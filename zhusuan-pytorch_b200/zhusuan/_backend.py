@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libzs_b200.so")
 
 F32, F64 = 0, 1
 FULL, KBCAST, SCALAR = 0, 1, 2
-SGVB, VIMCO = 0, 1
+SGVB, VIMCO, ELBO = 0, 1, 2
 ERR_UNSUPPORTED, ERR_ALIGN = -6, -7
 
 _lib = None
@@ -53,6 +53,7 @@ def _declare(lib):
         "zs_iw_bernoulli_fused_smem_bytes": (i64, [i64, i64]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
         "zs_scale_inplace": (i32, [i32, vp, i64, vp, vp]),
+        "zs_debug_set_trace": (i32, [vp]),
         "zs_sgld_step": (i32, [i32, vp, vp, vp, vp, i64, dbl, u64, u64, vp]),
         "zs_psgld_step": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, u64, u64, vp]),
         "zs_sghmc_pre": (i32, [i32, vp, vp, vp, vp, i64, dbl, i32, i32, u64, u64, vp]),
@@ -94,6 +95,11 @@ def check(rc, what):
 def require_cuda():
     if not torch.cuda.is_available():
         raise BackendError("zhusuan (B200): no CUDA device available; the hot path has no CPU fallback")
+
+
+def on_compute_device(t):
+    """True when `t` already lives where the kernels run (no host<->device shuttle needed)."""
+    return t.is_cuda
 
 
 def dtype_code(dt):

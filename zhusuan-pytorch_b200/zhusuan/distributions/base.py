@@ -4,6 +4,23 @@ import torch
 
 __all__ = ['Distribution']
 
+# The reference's constructors default to device=torch.device('cpu') and move every parameter there
+# (normal.py:50-58).  This object is that default; when a constructor receives exactly this object
+# (i.e. the caller did not pass `device=`) parameters that already live on a CUDA device stay there,
+# instead of being copied to the host and shuttled back for every kernel.
+DEFAULT_DEVICE = torch.device('cpu')
+
+
+def resolve_device(device, *params):
+    """The device the parameters are kept on: an explicit `device=` wins, otherwise the device of the
+    first tensor parameter, otherwise the CPU."""
+    if device is not DEFAULT_DEVICE:
+        return device
+    for p in params:
+        if torch.is_tensor(p):
+            return p.device
+    return device
+
 
 class Distribution(object):
     """Base of the stochastic-node distributions.
@@ -19,7 +36,7 @@ class Distribution(object):
     """
 
     def __init__(self, dtype, is_continuous, is_reparameterized, use_path_derivative=False, group_ndims=0,
-                 device=torch.device('cpu'), **kwargs):
+                 device=DEFAULT_DEVICE, **kwargs):
         # unknown kwargs are accepted and ignored, as in the reference (base.py:77): user models pass
         # reduce_mean_dims / multiplier / check_numerics / n_samples through the distribution ctor
         self._dtype = dtype

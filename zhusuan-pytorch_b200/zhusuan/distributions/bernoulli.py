@@ -6,7 +6,7 @@ floats in {0,1} drawn in-kernel from Philox uniforms (:72-82).
 """
 import torch
 
-from zhusuan.distributions.base import Distribution
+from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
 from zhusuan.distributions.utils import assert_same_log_float_dtype
 from zhusuan import _ops
 
@@ -17,7 +17,8 @@ class Bernoulli(Distribution):
     """Bernoulli(logits | probs).  Exactly one must be given; never reparameterised."""
 
     def __init__(self, logits=None, probs=None, dtype=None, is_continuous=False, group_ndims=0,
-                 device=torch.device('cpu'), **kwargs):
+                 device=DEFAULT_DEVICE, **kwargs):
+        device = resolve_device(device, probs, logits)
         if (logits is None) == (probs is None):
             raise ValueError("Either `probs` or `logits` should be passed. It is not allowed "
                              "that both are specified or both are not.")

@@ -5,7 +5,7 @@ the class index stored in the distribution's float dtype, batch_shape = logits.s
 """
 import torch
 
-from zhusuan.distributions.base import Distribution
+from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
 from zhusuan.distributions.utils import assert_same_log_float_dtype
 from zhusuan import _ops
 
@@ -14,7 +14,8 @@ __all__ = ['Categorical']
 
 class Categorical(Distribution):
     def __init__(self, logits=None, probs=None, dtype=None, is_continuous=False, group_ndims=0,
-                 device=torch.device('cpu'), **kwargs):
+                 device=DEFAULT_DEVICE, **kwargs):
+        device = resolve_device(device, logits, probs)
         if (logits is None) == (probs is None):
             raise ValueError("Either `probs` or `logits` should be passed. It is not allowed "
                              "that both are specified or both are not.")

@@ -6,7 +6,7 @@ log_prob: one kernel for the log-density and its event-axis sum (reference :109-
 """
 import torch
 
-from zhusuan.distributions.base import Distribution
+from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
 from zhusuan.distributions.utils import assert_same_log_float_dtype, check_broadcast
 from zhusuan import _ops
 
@@ -17,7 +17,8 @@ class Normal(Distribution):
     """Normal(mean, std | logstd).  Exactly one of `std` / `logstd` must be given."""
 
     def __init__(self, mean=0., std=None, logstd=None, dtype=None, is_continuous=True, is_reparameterized=True,
-                 group_ndims=0, device=torch.device('cpu'), **kwargs):
+                 group_ndims=0, device=DEFAULT_DEVICE, **kwargs):
+        device = resolve_device(device, mean, std, logstd)
         self._mean = torch.as_tensor(mean, dtype=dtype).to(device)
         if (logstd is None) == (std is None):
             raise ValueError("Either `std` or `logstd` should be passed. It is not allowed "

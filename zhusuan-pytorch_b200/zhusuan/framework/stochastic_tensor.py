@@ -1,0 +1,106 @@
+"""StochasticTensor — a named stochastic node of a BayesianNet.
+
+Drop-in for zhusuan/framework/stochastic_tensor.py of the reference: same constructor, same
+properties, and the same (stateful) semantics:
+  * `.tensor` returns the observation when the node's name is observed in its net (and records it as
+    the distribution's `sample_cache`), otherwise it draws a NEW sample on every access (:114-127);
+  * `.log_prob()` evaluates at `sample_cache` when called without an argument and then applies
+    reduce_mean_dims -> reduce_sum_dims -> squeeze -> multiplier (:160-181).
+B200 build: trailing `reduce_sum_dims` are folded into the distribution's log-density kernel (one
+pass over the [K,B,X] tensor produces the [K,B] result) instead of materialising the elementwise
+log-probabilities and reducing them afterwards.
+"""
+import torch
+
+from zhusuan.distributions.base import Distribution
+
+__all__ = ['StochasticTensor']
+
+
+class StochasticTensor(object):
+    def __init__(self, bn, name, dist, observation=None, n_samples=None, **kwargs):
+        self._bn = bn
+        self._name = name
+        self._dist = dist
+        self._dtype = dist.dtype
+        self._n_samples = n_samples
+        self._observation = observation
+        self._reduce_mean_dims = kwargs.get("reduce_mean_dims", None)
+        self._reduce_sum_dims = kwargs.get("reduce_sum_dims", None)
+        self._multiplier = kwargs.get("multiplier", None)
+
+    @property
+    def bn(self):
+        return self._bn
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def dist(self):
+        return self._dist
+
+    def is_observed(self):
+        return self._observation is not None
+
+    def _observed_value(self):
+        obs = self._bn.observed
+        return obs[self._name] if self._name in obs.keys() else None
+
+    @property
+    def tensor(self):
+        value = self._observed_value()
+        if value is not None:
+            self._dist.sample_cache = value
+            return value
+        return self._dist.sample(n_samples=self._n_samples)
+
+    def sample(self, force=False):
+        value = None if force else self._observed_value()
+        if value is not None:
+            self._dist.sample_cache = value
+            return value
+        return self._dist.sample(n_samples=self._n_samples)
+
+    @property
+    def shape(self):
+        return self.tensor.shape
+
+    def get_shape(self):
+        return self.shape
+
+    # -- reduction plan -------------------------------------------------------------------------
+    def reduction_plan(self, value_shape):
+        """Split the node's reductions into (n_event, mean_dims, sum_dims): `n_event` trailing axes
+        are summed inside the log-density kernel, the rest is applied to its (small) output.
+        Axes index the tensor left after the distribution's own group_ndims sum, as in the reference."""
+        g = self._dist.group_ndims
+        full = torch.broadcast_shapes(tuple(value_shape), tuple(self._dist.batch_shape))
+        nd = len(full) - g
+        mean_dims = sorted(set(d % nd for d in (self._reduce_mean_dims or []))) if nd > 0 else []
+        sum_dims = sorted(set(d % nd for d in (self._reduce_sum_dims or []))) if nd > 0 else []
+        fold = 0
+        if sum_dims and sum_dims == list(range(nd - len(sum_dims), nd)) and not (set(sum_dims) & set(mean_dims)):
+            fold = len(sum_dims)
+            sum_dims = []
+        return g + fold, mean_dims, sum_dims
+
+    def log_prob(self, sample=None):
+        dist = self._dist
+        given = dist._given(sample)
+        n_event, mean_dims, sum_dims = self.reduction_plan(given.shape)
+        lp = dist._log_prob_event(given, n_event)
+        if mean_dims:
+            lp = torch.mean(lp, mean_dims, keepdim=True)
+        if sum_dims:
+            lp = torch.sum(lp, sum_dims, keepdim=True)
+        for d in sorted(set(mean_dims + sum_dims), reverse=True):
+            lp = torch.squeeze(lp, d)
+        if self._multiplier:
+            lp = lp * self._multiplier
+        return lp
