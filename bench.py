@@ -236,39 +236,30 @@ class PathStep(object):
         kbx, kbz, kb, bz, bx = 4 * K * B * X, 4 * K * B * Z, 4 * K * B, 4 * B * Z, 4 * B * X
         fused = 2 * kbx + bx + 4 * kb + 4 * B          # probs R, dprobs W, x R, other/logq R, dlogp/dlogq W, cost W
         if self.vimco:
-            small = (bz + kbz) + 2 * (kbz + bz + kb) + (kb + kbz + bz + bz)   # sample, 2 logpmf fwd, logq bwd
+            small = (bz + kbz + 2 * kb) + (kb + kbz + 2 * bz)            # latent fwd (W z, logq, logp), latent bwd
         else:
-            small = (2 * bz + kbz) + 2 * (kbz + 2 * bz + kb)                  # sample W z, two log-density fwd
-            small += (kb + kbz + kbz) + (kb + kbz + 2 * bz + kbz + 2 * bz)    # prior bwd (dz), q bwd (dz, dmean, dstd)
-            small += 3 * kbz + kbz + (kbz + 2 * bz)                           # dz sum (R 3, W 1), sample bwd
+            small = (2 * bz + kbz + 2 * kb) + (2 * kb + 2 * kbz + 4 * bz)  # fwd: R mean,std W z,logq,logp; bwd: R g's,z,dz_up
         return fused, fused + small
 
     def step(self):
-        be, torch = self.be, self.torch
+        """latent forward (sample + log q + log p(z)) -> fused likelihood+objective fwd+bwd -> latent
+        backward: three launches of our kernels per step."""
+        be = self.be
         K, B, Z, X = K_PART, B_COLS, Z_DIM, X_DIM
         n0 = be.launch_count
         self.offset += 4
         if self.vimco:
-            z = be.bernoulli_sample(self.pq, be.KBCAST, K, B * Z, seed=self.seed, offset=self.offset)
-            logq = be.bernoulli_logpmf_fwd(z, be.FULL, self.pq, be.KBCAST, K, B, Z)
-            logpz = be.bernoulli_logpmf_fwd(z, be.FULL, self.prior, be.KBCAST, K, B, Z)
+            z, logq, logpz = be.bernoulli_latent_fwd(self.pq, be.KBCAST, K, B, Z, seed=self.seed, offset=self.offset)
             r = be.iw_bernoulli_fused(be.VIMCO, self.probs, self.x, logpz, logq, 1.0 / B)
-            _, dpq = be.bernoulli_logpmf_bwd(r["dlogq"], z, be.FULL, self.pq, be.KBCAST, K, B, Z, False, True)
+            dpq = be.bernoulli_latent_bwd(r["dlogq"], z, self.pq, be.KBCAST, K, B, Z)
             self.out = (r["cost"], r["dprobs"], dpq)
         else:
-            z = be.normal_sample(self.mean, be.KBCAST, self.std, be.KBCAST, K, B * Z, seed=self.seed,
-                                 offset=self.offset)
-            logq = be.normal_logprob_fwd(z, be.FULL, self.mean, be.KBCAST, self.std, be.KBCAST, K, B, Z)
-            logpz = be.normal_logprob_fwd(z, be.FULL, self.zeros, be.KBCAST, self.ones, be.KBCAST, K, B, Z)
+            z, logq, logpz = be.normal_latent_fwd(self.mean, self.std, be.KBCAST, K, B, Z, seed=self.seed,
+                                                  offset=self.offset)
             r = be.iw_bernoulli_fused(be.SGVB, self.probs, self.x, logpz, logq, 1.0 / B)
-            dz_p, _, _ = be.normal_logprob_bwd(r["dlogp"], z, be.FULL, self.zeros, be.KBCAST, self.ones, be.KBCAST, K,
-                                               B, Z, True, False, False)
-            dz_q, dm_q, ds_q = be.normal_logprob_bwd(r["dlogq"], z, be.FULL, self.mean, be.KBCAST, self.std,
-                                                     be.KBCAST, K, B, Z, True, True, True)
-            dz = (self.dz_up + dz_p.reshape(K, B, Z) + dz_q.reshape(K, B, Z)).reshape(K, B * Z)
-            dm_s, ds_s = be.normal_sample_bwd(dz, self.mean, be.KBCAST, self.std, be.KBCAST, K, B * Z,
-                                              seed=self.seed, offset=self.offset)
-            self.out = (r["cost"], r["dprobs"], dm_q + dm_s, ds_q + ds_s)
+            dm, ds = be.normal_latent_bwd(r["dlogq"], r["dlogp"], self.dz_up, z, self.mean, self.std, be.KBCAST, K, B,
+                                          Z, reparameterized=True)
+            self.out = (r["cost"], r["dprobs"], dm, ds)
         self.launches_per_step = be.launch_count - n0
         return self.out
 

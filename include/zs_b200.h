@@ -123,6 +123,30 @@ int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, co
                             const void* probs, int probs_mode, int64_t K, int64_t M, int64_t E,
                             zs_stream_t stream);
 
+/* ---- fused latent-node kernels (zs_latent.cu) -------------------------------
+ * Forward: z ~ q (Philox or injected noise), log q(z) and log p(z) under the prior, both summed over
+ * E, in ONE launch: Normal._sample + Normal._log_prob twice (normal.py:89-126; the variational net's
+ * own log-prob and the generator's prior, iwae.py:60-72,102-120), resp. bernoulli.py:72-95.
+ *   mean/std (probs): both ZS_FULL or both ZS_KBCAST; prior_* are [M,E] (KBCAST) or NULL
+ *   (standard Normal / Bernoulli(0.5)); logq / logp may be NULL.  Needs E % 4 == 0 and 16-byte
+ *   aligned tensors, otherwise ZS_ERR_UNSUPPORTED / ZS_ERR_ALIGN (compose the general kernels).      */
+int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* mean, int mean_mode, const void* std,
+                         int std_mode, const void* prior_mean, const void* prior_std, const void* eps_in, int64_t K,
+                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
+                            const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
+                            uint64_t offset, zs_stream_t stream);
+/* Backward in ONE launch: gradient of  <dlogq, log q> + <dlogp, log p> + <dz_up, z>  wrt the variational
+ * parameters: autograd of both log-densities, the decoder's upstream gradient dz_up [K,M,E] (may be
+ * NULL) and, if reparameterized, the pathwise backward of the sample (eps recovered as (z-mean)/std),
+ * summed over K for KBCAST parameters.  dlogq / dlogp [K,M] may be NULL.                            */
+int zs_normal_latent_bwd(int dtype, void* dmean, void* dstd, const void* dlogq, const void* dlogp, const void* dz_up,
+                         const void* z, const void* mean, int mean_mode, const void* std, int std_mode,
+                         const void* prior_mean, const void* prior_std, int reparameterized, int64_t K, int64_t M,
+                         int64_t E, zs_stream_t stream);
+int zs_bernoulli_latent_bwd(int dtype, void* dprobs, const void* dlogq, const void* z, const void* probs,
+                            int probs_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+
 /* ---- Categorical stochastic node (absent from the reference: parity unpinned;
  * API modelled on bernoulli.py) --------------------------------
  * logits [K|1, M, C]; value = class index stored as float/double in x[K,M].     */

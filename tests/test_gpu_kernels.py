@@ -458,6 +458,84 @@ def test_iw_step_host(oracle):
     close(dprobs.numpy(), o["dprobs"], 1e-4)
 
 
+# ----------------------------------------------------------------------------- fused latent-node kernels
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,M,E,mode,prior", [(50, 64, 40, KBCAST, "std"), (50, 64, 40, KBCAST, "given"),
+                                               (7, 5, 8, FULL, "std"), (3, 130, 132, KBCAST, "given"),
+                                               (1, 9, 4, KBCAST, "std")])
+def test_normal_latent_fused(oracle, dt, K, M, E, mode, prior):
+    """sample + log q + log p(z) in one launch and their joint backward == the composition of the
+    per-stage oracle functions (normal.py:89-126 and its autograd)."""
+    rng = np.random.RandomState(21)
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    pshape = (K, M, E) if mode == FULL else (M, E)
+    mean = (0.5 * rng.standard_normal(pshape)).astype(dt)
+    std = np.exp(0.3 * rng.standard_normal(pshape)).astype(dt)
+    pm = (0.2 * rng.standard_normal((M, E))).astype(dt) if prior == "given" else None
+    ps = np.exp(0.2 * rng.standard_normal((M, E))).astype(dt) if prior == "given" else None
+    eps = rng.standard_normal((K, M, E)).astype(dt)
+    r = be.normal_latent_fwd(dev(mean), dev(std), mode, K, M, E, prior_mean=None if pm is None else dev(pm),
+                             prior_std=None if ps is None else dev(ps), eps_in=dev(eps))
+    assert r is not None
+    z, logq, logp = r
+    rt = rtol_of(dt)
+    f64 = lambda a: a.astype(np.float64)
+    pm_o = np.zeros((M, E)) if pm is None else f64(pm)
+    ps_o = np.ones((M, E)) if ps is None else f64(ps)
+    zo = oracle.normal_sample(f64(mean), f64(std), f64(eps).reshape(K, M * E), K, M * E).reshape(K, M, E)
+    close(host(z), zo, rt)
+    zk = host(z).astype(np.float64)  # stage-wise: log-densities at the kernel's own sample
+    close(host(logq), oracle.normal_logprob_fwd(zk, f64(mean), f64(std), K, M, E), rt)
+    close(host(logp), oracle.normal_logprob_fwd(zk, pm_o, ps_o, K, M, E), rt)
+    # backward
+    gq, gp = rng.standard_normal((K, M)).astype(dt), rng.standard_normal((K, M)).astype(dt)
+    dzu = (0.1 * rng.standard_normal((K, M, E))).astype(dt)
+    for reparam in (True, False):
+        dm, ds = be.normal_latent_bwd(dev(gq), dev(gp), dev(dzu), z, dev(mean), dev(std), mode, K, M, E,
+                                      prior_mean=None if pm is None else dev(pm),
+                                      prior_std=None if ps is None else dev(ps), reparameterized=reparam)
+        dzq, dmq, dsq = oracle.normal_logprob_bwd(f64(gq), zk, f64(mean), f64(std), K, M, E)
+        if reparam:
+            dzp, _, _ = oracle.normal_logprob_bwd(f64(gp), zk, pm_o, ps_o, K, M, E)
+            dzt = (f64(dzu) + dzp + dzq).reshape(K, M * E)
+            dms, dss = oracle.normal_sample_bwd(dzt, f64(eps).reshape(K, M * E), f64(mean), f64(std), K, M * E)
+            dmq, dsq = dmq + dms.reshape(dmq.shape), dsq + dss.reshape(dsq.shape)
+        close(host(dm), dmq, rt * 3)
+        close(host(ds), dsq, rt * 3)
+    # Philox mode: the same stream as the stand-alone sampler, and a standard prior == explicit (0, 1)
+    r1 = be.normal_latent_fwd(dev(mean), dev(std), mode, K, M, E, seed=5, offset=8)
+    z_ref = be.normal_sample(dev(mean).reshape(-1) if mode == KBCAST else dev(mean).reshape(K, -1), mode,
+                             dev(std).reshape(-1) if mode == KBCAST else dev(std).reshape(K, -1), mode, K, M * E,
+                             seed=5, offset=8)
+    assert torch.equal(r1[0].reshape(K, -1), z_ref)
+    r2 = be.normal_latent_fwd(dev(mean), dev(std), mode, K, M, E, prior_mean=torch.zeros(M, E, dtype=tdt, device=DEV),
+                              prior_std=torch.ones(M, E, dtype=tdt, device=DEV), seed=5, offset=8)
+    assert torch.equal(r1[2], r2[2])
+    assert be.normal_latent_fwd(dev(mean[..., :3].copy()), dev(std[..., :3].copy()), mode, K, M, 3) is None  # E % 4
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,M,E,prior", [(50, 64, 40, None), (6, 7, 8, "given")])
+def test_bernoulli_latent_fused(oracle, dt, K, M, E, prior):
+    rng = np.random.RandomState(22)
+    pq = rng.uniform(0.05, 0.95, size=(M, E)).astype(dt)
+    pp = rng.uniform(0.2, 0.8, size=(M, E)).astype(dt) if prior else None
+    u = rng.uniform(size=(K, M, E)).astype(dt)
+    z, logq, logp = be.bernoulli_latent_fwd(dev(pq), KBCAST, K, M, E, prior_probs=None if pp is None else dev(pp),
+                                            u_in=dev(u))
+    zo = oracle.bernoulli_sample(pq, u.reshape(K, M * E), K, M * E).reshape(K, M, E)
+    assert np.array_equal(host(z), zo)
+    rt = rtol_of(dt)
+    f64 = lambda a: a.astype(np.float64)
+    close(host(logq), oracle.bernoulli_logpmf_fwd(f64(zo), f64(pq), K, M, E), rt)
+    close(host(logp), oracle.bernoulli_logpmf_fwd(f64(zo), np.full((M, E), 0.5) if pp is None else f64(pp), K, M, E), rt)
+    g = rng.standard_normal((K, M)).astype(dt)
+    dpq = be.bernoulli_latent_bwd(dev(g), z, dev(pq), KBCAST, K, M, E)
+    close(host(dpq), oracle.bernoulli_logpmf_bwd(f64(g), f64(zo), f64(pq), K, M, E), rt)
+    z2, _, _ = be.bernoulli_latent_fwd(dev(pq), KBCAST, K, M, E, seed=3, offset=4)
+    assert torch.equal(z2.reshape(K, -1), be.bernoulli_sample(dev(pq).reshape(-1), KBCAST, K, M * E, seed=3, offset=4))
+
+
 # ----------------------------------------------------------------------------- SG-MCMC
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [4710000 // 10, 1027, 3])

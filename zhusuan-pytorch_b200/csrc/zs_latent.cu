@@ -1,0 +1,423 @@
+// Fused latent-node kernels: everything a latent stochastic node contributes to one objective step,
+// in one launch forward and one launch backward.
+//
+// forward  : z ~ q (Philox in-kernel or injected noise), log q(z) and log p(z) under the prior,
+//            both summed over the event axis E.
+//            Replaces Normal._sample (normal.py:89-107) + Normal._log_prob twice (normal.py:109-126,
+//            once in the variational net, once for the generator's prior, iwae.py:60-72,102-120) + the
+//            event sums (base.py:175-176, stochastic_tensor.py:164-165); for Bernoulli latents
+//            Bernoulli._sample / _log_prob (bernoulli.py:72-95).
+// backward : gradient of (dlogq . log q + dlogp . log p + <dz_up, z>) wrt the variational parameters:
+//            the autograd backward of both log-densities, the upstream gradient of the sample coming
+//            back from the decoder, and the pathwise backward of the sample through `.repeat`
+//            (a sum over the K particles), fused.
+// Both are specialised for what the hot path uses: float4-aligned event rows (E % 4 == 0), variational
+// parameters FULL or KBCAST, prior parameters KBCAST (or NULL = the standard prior) without gradient.
+// Anything else returns ZS_ERR_UNSUPPORTED and the caller composes the general kernels of zs_nodes.cu.
+#include <initializer_list>
+
+#include "zs_common.cuh"
+#include "zs_philox.cuh"
+
+namespace zs {
+
+template <typename T>
+struct V4 {
+    T v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ V4<T> ldv4(const T* p);
+template <>
+__device__ __forceinline__ V4<float> ldv4<float>(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    return V4<float>{{a.x, a.y, a.z, a.w}};
+}
+template <>
+__device__ __forceinline__ V4<double> ldv4<double>(const double* p) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    return V4<double>{{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void stv4(float* p, const V4<float>& q) {
+    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+}
+__device__ __forceinline__ void stv4(double* p, const V4<double>& q) {
+    *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+}
+
+constexpr int FAM_NORMAL = 0, FAM_BERNOULLI = 1;
+
+template <typename T>
+__device__ __forceinline__ T normal_c() {
+    return (T)(-0.9189385332046727);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: G lanes per batch row m; lane j owns float4 units j, j+G, ... of the row.  For KBCAST
+// parameters the group keeps mean / std / log std / precision of its units in registers and walks
+// the particles k = ks, ks+KS, ... — the transcendental work on the parameters is done once per
+// (m, e), not once per particle.  UPL = units per lane held in registers (E/4 <= G*UPL).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct UnitParams {
+    V4<T> a, b, logb, prec;        // variational: mean, std, log std, exp(-2 log std)  (Bernoulli: a = probs)
+    V4<T> pa, plogb, pprec;        // prior: mean, log std, precision                 (Bernoulli: pa = probs)
+};
+
+template <typename T, int FAM>
+__device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, const T* b, const T* pa, const T* pb,
+                                                 int64_t idx, int64_t kidx) {
+    u.a = ldv4(a + idx);
+    if (FAM == FAM_NORMAL) {
+        u.b = ldv4(b + idx);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            u.logb.v[q] = Real<T>::log(u.b.v[q]);
+            u.prec.v[q] = Real<T>::exp(T(-2) * u.logb.v[q]);
+        }
+        if (pa) u.pa = ldv4(pa + kidx);
+        else u.pa = V4<T>{{T(0), T(0), T(0), T(0)}};
+        if (pb) {
+            const V4<T> ps = ldv4(pb + kidx);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                u.plogb.v[q] = Real<T>::log(ps.v[q]);
+                u.pprec.v[q] = Real<T>::exp(T(-2) * u.plogb.v[q]);
+            }
+        } else {
+            // standard prior: log(1) = 0 and exp(-2*0) = 1 exactly, as the reference computes them
+            u.plogb = V4<T>{{T(0), T(0), T(0), T(0)}};
+            u.pprec = V4<T>{{T(1), T(1), T(1), T(1)}};
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // log(p + 1e-8), log((1-p) + 1e-8) of bernoulli.py:94
+            u.logb.v[q] = Real<T>::log(u.a.v[q] + T(1e-8));
+            u.prec.v[q] = Real<T>::log((T(1) - u.a.v[q]) + T(1e-8));
+        }
+        if (pa) u.pa = ldv4(pa + kidx);
+        else u.pa = V4<T>{{T(0.5), T(0.5), T(0.5), T(0.5)}};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            u.plogb.v[q] = Real<T>::log(u.pa.v[q] + T(1e-8));
+            u.pprec.v[q] = Real<T>::log((T(1) - u.pa.v[q]) + T(1e-8));
+        }
+    }
+}
+
+template <typename T, int FAM, int G>
+__global__ void __launch_bounds__(256)
+    k_latent_fwd(T* __restrict__ z, T* __restrict__ logq, T* __restrict__ logp, const T* __restrict__ a,
+                 int a_mode, const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
+                 const T* __restrict__ noise_in, int64_t K, int64_t M, int64_t E, int KS, uint64_t seed,
+                 uint64_t offset) {
+    const int lane = threadIdx.x % G;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;  // group -> (m, k-slice)
+    const int64_t E4 = E >> 2;
+    const int64_t m = grp / KS;
+    const int ks = (int)(grp % KS);
+    const bool valid = m < M;
+    const bool kb = a_mode == ZS_KBCAST;
+    // all lanes of a group run the same trip counts (the group shuffles below need every lane)
+    for (int64_t j0 = 0; j0 < E4; j0 += G) {
+        const int64_t j = j0 + lane;
+        const bool active = valid && j < E4;
+        UnitParams<T> up;
+        if (active && kb) load_unit_params<T, FAM>(up, a, b, pa, pb, m * E + 4 * j, m * E + 4 * j);
+        const int64_t trips = (K + KS - 1) / KS;  // uniform across the warp: the shuffles need every lane
+        for (int64_t t = 0; t < trips; ++t) {
+            const int64_t k = ks + t * KS;
+            T accq = T(0), accp = T(0);
+            if (active && k < K) {
+                const int64_t r = k * M + m, fe = r * E + 4 * j;
+                if (!kb) load_unit_params<T, FAM>(up, a, b, pa, pb, fe, m * E + 4 * j);
+                V4<T> nz;
+                if (noise_in) {
+                    nz = ldv4(noise_in + fe);
+                } else {
+                    float n4[4];  // one Philox counter per float4 unit (element i: counter i/4, word i%4)
+                    if (FAM == FAM_NORMAL) philox_normal4((uint64_t)(fe >> 2), offset, seed, n4);
+                    else philox_uniform4((uint64_t)(fe >> 2), offset, seed, n4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) nz.v[q] = (T)n4[q];
+                }
+                V4<T> zv;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (FAM == FAM_NORMAL) {
+                        const T zz = up.a.v[q] + up.b.v[q] * nz.v[q];  // normal.py:105
+                        zv.v[q] = zz;
+                        const T d = zz - up.a.v[q];                     // normal.py:121-124 at the sample
+                        accq += (normal_c<T>() - up.logb.v[q]) - (T(0.5) * up.prec.v[q]) * (d * d);
+                        const T dp = zz - up.pa.v[q];
+                        accp += (normal_c<T>() - up.plogb.v[q]) - (T(0.5) * up.pprec.v[q]) * (dp * dp);
+                    } else {
+                        const T zz = nz.v[q] < up.a.v[q] ? T(1) : T(0);  // bernoulli.py:79
+                        zv.v[q] = zz;
+                        accq += zz * up.logb.v[q] + (T(1) - zz) * up.prec.v[q];    // bernoulli.py:94
+                        accp += zz * up.plogb.v[q] + (T(1) - zz) * up.pprec.v[q];
+                    }
+                }
+                stv4(z + fe, zv);
+            }
+            // E4 <= G is the common case (one pass): the row sum is complete after the group reduction;
+            // longer rows accumulate across passes through the output (zeroed by the first pass)
+            accq = group_sum<G>(accq);
+            accp = group_sum<G>(accp);
+            if (valid && lane == 0 && k < K) {
+                const int64_t r = k * M + m;
+                if (logq) logq[r] = (j0 == 0 ? T(0) : logq[r]) + accq;
+                if (logp) logp[r] = (j0 == 0 ? T(0) : logp[r]) + accp;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: block = LB_X float4 units of [M,E] x LB_Y particle slices, fixed-order sum over slices.
+// Parameter-only terms (log std, precision, 1/std) are hoisted out of the particle loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int LB_X = 16, LB_Y = 16;
+
+template <typename T, int FAM>
+__global__ void __launch_bounds__(LB_X* LB_Y)
+    k_latent_bwd(T* __restrict__ da, T* __restrict__ db, const T* __restrict__ gq, const T* __restrict__ gp,
+                 const T* __restrict__ dz_up, const T* __restrict__ z, const T* __restrict__ a, int a_mode,
+                 const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
+                 int reparam, int64_t K, int64_t M, int64_t E) {
+    const int64_t ME4 = (M * E) >> 2;
+    const int64_t u = (int64_t)blockIdx.x * LB_X + threadIdx.x;
+    const bool valid = u < ME4;
+    const bool full = a_mode == ZS_FULL;  // FULL parameters: per-particle gradients, no reduction
+    V4<T> sa{{T(0), T(0), T(0), T(0)}}, sb{{T(0), T(0), T(0), T(0)}};
+    if (valid) {
+        const int64_t ke = 4 * u, m = ke / E;
+        UnitParams<T> up;
+        V4<T> rstd;
+        if (!full) {
+            load_unit_params<T, FAM>(up, a, b, pa, pb, ke, ke);
+            if (FAM == FAM_NORMAL)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rstd.v[q] = T(1) / up.b.v[q];
+        }
+        for (int64_t k = threadIdx.y; k < K; k += LB_Y) {
+            const int64_t r = k * M + m, fe = k * (M * E) + ke;
+            const T g_q = gq ? gq[r] : T(0), g_p = gp ? gp[r] : T(0);
+            const V4<T> zv = ldv4(z + fe);
+            V4<T> du{{T(0), T(0), T(0), T(0)}};
+            if (dz_up && reparam) du = ldv4(dz_up + fe);
+            if (full) {
+                load_unit_params<T, FAM>(up, a, b, pa, pb, fe, ke);
+                if (FAM == FAM_NORMAL)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rstd.v[q] = T(1) / up.b.v[q];
+            }
+            V4<T> oa, ob;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (FAM == FAM_NORMAL) {
+                    // autograd of normal.py:121-124 (same association as NormalOp::grad in zs_nodes.cu)
+                    const T prec = up.prec.v[q], zz = zv.v[q];
+                    const T d = zz - up.a.v[q];
+                    const T dzq = -(g_q * (T(0.5) * prec)) * (T(2) * d);
+                    const T dprec = -(g_q * (d * d)) * T(0.5);
+                    const T dlogstd = -g_q + (dprec * prec) * T(-2);
+                    T dmean = -dzq, dstd = dlogstd * rstd.v[q];
+                    if (reparam) {
+                        const T dzp = gp ? -(g_p * (T(0.5) * up.pprec.v[q])) * (T(2) * (zz - up.pa.v[q])) : T(0);
+                        const T dzt = (du.v[q] + dzp) + dzq;  // total gradient reaching the sample
+                        dmean += dzt;                          // z = mean + std*eps
+                        dstd += dzt * (d * rstd.v[q]);         // eps recovered from the sample
+                    }
+                    oa.v[q] = dmean;
+                    ob.v[q] = dstd;
+                } else {
+                    // autograd of bernoulli.py:94 wrt probs (samples carry no gradient)
+                    const T p = up.a.v[q], zz = zv.v[q];
+                    oa.v[q] = (g_q * zz) / (p + T(1e-8)) - (g_q * (T(1) - zz)) / ((T(1) - p) + T(1e-8));
+                    ob.v[q] = T(0);
+                }
+            }
+            if (full) {
+                if (da) stv4(da + fe, oa);
+                if (db && FAM == FAM_NORMAL) stv4(db + fe, ob);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    sa.v[q] += oa.v[q];
+                    sb.v[q] += ob.v[q];
+                }
+            }
+        }
+    }
+    if (full) return;
+    __shared__ T red[2][LB_Y][LB_X][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        red[0][threadIdx.y][threadIdx.x][q] = sa.v[q];
+        red[1][threadIdx.y][threadIdx.x][q] = sb.v[q];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && valid) {
+        V4<T> ta{{T(0), T(0), T(0), T(0)}}, tb{{T(0), T(0), T(0), T(0)}};
+#pragma unroll
+        for (int s = 0; s < LB_Y; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ta.v[q] += red[0][s][threadIdx.x][q];
+                tb.v[q] += red[1][s][threadIdx.x][q];
+            }
+        if (da) stv4(da + 4 * u, ta);
+        if (db && FAM == FAM_NORMAL) stv4(db + 4 * u, tb);
+    }
+}
+
+template <typename T, int FAM>
+static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, const T* b, int b_mode, const T* pa,
+                             const T* pb, const T* noise_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
+                             uint64_t offset, cudaStream_t st) {
+    const int64_t E4 = E >> 2;
+    // k-slices per batch row: enough groups to fill the machine, each slice reusing its parameters
+#define ZS_LATENT_FWD(G)                                                                                          \
+    {                                                                                                             \
+        int64_t KS = (int64_t)sm_count() * 2048 / (M * G > 0 ? M * G : 1);                                        \
+        if (KS < 1) KS = 1;                                                                                       \
+        if (KS > K) KS = K;                                                                                       \
+        if (KS > 16) KS = 16;                                                                                     \
+        const int64_t groups = M * KS;                                                                            \
+        const int64_t grid = (groups * G + 255) / 256;                                                            \
+        ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);                                               \
+        k_latent_fwd<T, FAM, G><<<(unsigned)grid, 256, 0, st>>>(z, logq, logp, a, a_mode, b, b_mode, pa, pb,      \
+                                                                noise_in, K, M, E, (int)KS, seed, offset);        \
+    }
+    if (E4 <= 4) ZS_LATENT_FWD(4)
+    else if (E4 <= 8) ZS_LATENT_FWD(8)
+    else if (E4 <= 16) ZS_LATENT_FWD(16)
+    else ZS_LATENT_FWD(32)
+#undef ZS_LATENT_FWD
+    ZS_LAUNCH_CHECK("k_latent_fwd");
+    return ZS_OK;
+}
+
+static int latent_args_ok(const void* a, int a_mode, const void* b, int b_mode, int fam, int64_t E,
+                          std::initializer_list<const void*> ptrs) {
+    if (E % 4 != 0) {
+        set_last_error_msg("latent kernels need E % 4 == 0");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    if (!(a_mode == ZS_FULL || a_mode == ZS_KBCAST) || (fam == FAM_NORMAL && b_mode != a_mode)) {
+        set_last_error_msg("latent kernels need both variational parameters FULL or both KBCAST");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    for (const void* p : ptrs)
+        if (!aligned16(p)) {
+            set_last_error_msg("latent kernels need 16-byte aligned tensors");
+            return ZS_ERR_ALIGN;
+        }
+    (void)a;
+    (void)b;
+    return ZS_OK;
+}
+
+template <typename T, int FAM>
+static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp, const void* dz_up, const void* z,
+                             const void* a, int a_mode, const void* b, int b_mode, const void* pa, const void* pb,
+                             int reparam, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    const int64_t ME4 = (M * E) >> 2;
+    const int64_t grid = (ME4 + LB_X - 1) / LB_X;
+    ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+    dim3 block(LB_X, LB_Y);
+    k_latent_bwd<T, FAM><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+        (T*)da, (T*)db, (const T*)gq, (const T*)gp, (const T*)dz_up, (const T*)z, (const T*)a, a_mode, (const T*)b,
+        b_mode, (const T*)pa, (const T*)pb, reparam, K, M, E);
+    ZS_LAUNCH_CHECK("k_latent_bwd");
+    return ZS_OK;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" {
+
+int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* mean, int mean_mode, const void* std,
+                         int std_mode, const void* prior_mean, const void* prior_std, const void* eps_in, int64_t K,
+                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(z && mean && std && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    int rc = latent_args_ok(mean, mean_mode, std, std_mode, FAM_NORMAL, E, {z, mean, std, prior_mean, prior_std, eps_in});
+    if (rc != ZS_OK) return rc;
+    if (K * M == 0) return ZS_OK;
+    if (dtype == ZS_F32)
+        return launch_latent_fwd<float, FAM_NORMAL>((float*)z, (float*)logq, (float*)logp, (const float*)mean,
+                                                    mean_mode, (const float*)std, std_mode, (const float*)prior_mean,
+                                                    (const float*)prior_std, (const float*)eps_in, K, M, E, seed,
+                                                    offset, as_stream(stream));
+    if (dtype == ZS_F64)
+        return launch_latent_fwd<double, FAM_NORMAL>((double*)z, (double*)logq, (double*)logp, (const double*)mean,
+                                                     mean_mode, (const double*)std, std_mode,
+                                                     (const double*)prior_mean, (const double*)prior_std,
+                                                     (const double*)eps_in, K, M, E, seed, offset, as_stream(stream));
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
+                            const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
+                            uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(z && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    int rc = latent_args_ok(probs, probs_mode, nullptr, probs_mode, FAM_BERNOULLI, E, {z, probs, prior_probs, u_in});
+    if (rc != ZS_OK) return rc;
+    if (K * M == 0) return ZS_OK;
+    if (dtype == ZS_F32)
+        return launch_latent_fwd<float, FAM_BERNOULLI>((float*)z, (float*)logq, (float*)logp, (const float*)probs,
+                                                       probs_mode, nullptr, probs_mode, (const float*)prior_probs,
+                                                       nullptr, (const float*)u_in, K, M, E, seed, offset,
+                                                       as_stream(stream));
+    if (dtype == ZS_F64)
+        return launch_latent_fwd<double, FAM_BERNOULLI>((double*)z, (double*)logq, (double*)logp,
+                                                        (const double*)probs, probs_mode, nullptr, probs_mode,
+                                                        (const double*)prior_probs, nullptr, (const double*)u_in, K,
+                                                        M, E, seed, offset, as_stream(stream));
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_normal_latent_bwd(int dtype, void* dmean, void* dstd, const void* dlogq, const void* dlogp, const void* dz_up,
+                         const void* z, const void* mean, int mean_mode, const void* std, int std_mode,
+                         const void* prior_mean, const void* prior_std, int reparameterized, int64_t K, int64_t M,
+                         int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(z && mean && std && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    int rc = latent_args_ok(mean, mean_mode, std, std_mode, FAM_NORMAL, E,
+                            {dmean, dstd, dz_up, z, mean, std, prior_mean, prior_std});
+    if (rc != ZS_OK) return rc;
+    if (K * M == 0 || (!dmean && !dstd)) return ZS_OK;
+    if (dtype == ZS_F32)
+        return launch_latent_bwd<float, FAM_NORMAL>(dmean, dstd, dlogq, dlogp, dz_up, z, mean, mean_mode, std,
+                                                    std_mode, prior_mean, prior_std, reparameterized, K, M, E, stream);
+    if (dtype == ZS_F64)
+        return launch_latent_bwd<double, FAM_NORMAL>(dmean, dstd, dlogq, dlogp, dz_up, z, mean, mean_mode, std,
+                                                     std_mode, prior_mean, prior_std, reparameterized, K, M, E,
+                                                     stream);
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+int zs_bernoulli_latent_bwd(int dtype, void* dprobs, const void* dlogq, const void* z, const void* probs,
+                            int probs_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(dprobs && dlogq && z && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    int rc = latent_args_ok(probs, probs_mode, nullptr, probs_mode, FAM_BERNOULLI, E, {dprobs, z, probs});
+    if (rc != ZS_OK) return rc;
+    if (K * M == 0) return ZS_OK;
+    if (dtype == ZS_F32)
+        return launch_latent_bwd<float, FAM_BERNOULLI>(dprobs, nullptr, dlogq, nullptr, nullptr, z, probs, probs_mode,
+                                                       nullptr, probs_mode, nullptr, nullptr, 0, K, M, E, stream);
+    if (dtype == ZS_F64)
+        return launch_latent_bwd<double, FAM_BERNOULLI>(dprobs, nullptr, dlogq, nullptr, nullptr, z, probs,
+                                                        probs_mode, nullptr, probs_mode, nullptr, nullptr, 0, K, M, E,
+                                                        stream);
+    set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+    return ZS_ERR_DTYPE;
+}
+
+}  // extern "C"

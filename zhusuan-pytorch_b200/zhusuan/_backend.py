@@ -41,6 +41,10 @@ def _declare(lib):
         "zs_normal_sample_bwd": (i32, [i32, vp, i32, vp, i32, vp, vp, i64, i64, u64, u64, vp]),
         "zs_normal_logprob_fwd": (i32, [i32, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_normal_logprob_bwd": (i32, [i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
+        "zs_normal_latent_fwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, i64, i64, i64, u64, u64, vp]),
+        "zs_bernoulli_latent_fwd": (i32, [i32, vp, vp, vp, vp, i32, vp, vp, i64, i64, i64, u64, u64, vp]),
+        "zs_normal_latent_bwd": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i64, i64, i64, vp]),
+        "zs_bernoulli_latent_bwd": (i32, [i32, vp, vp, vp, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, u64, u64, vp]),
         "zs_bernoulli_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
@@ -203,6 +207,66 @@ def normal_logprob_bwd(g, x, xm, mean, mm, std, sm, K, M, E, need_x, need_mean, 
                                        _ptr(mean), mm, _ptr(std), sm, K, M, E, _stream()), "zs_normal_logprob_bwd")
     _count()
     return dx, dmean, dstd
+
+
+# ----------------------------------------------------------------------------- fused latent nodes
+def normal_latent_fwd(mean, std, mode, K, M, E, prior_mean=None, prior_std=None, eps_in=None, want_logq=True,
+                      want_logp=True, seed=0, offset=0):
+    """-> (z [K,M,E], logq [K,M] | None, logp [K,M] | None), or None when the shape is not supported."""
+    dt = mean.dtype
+    for t, n in ((mean, "mean"), (std, "std"), (prior_mean, "prior_mean"), (prior_std, "prior_std"), (eps_in, "eps")):
+        _chk_tensor(t, n, dt)
+    z = torch.empty((K, M, E), dtype=dt, device=mean.device)
+    logq = torch.empty((K, M), dtype=dt, device=mean.device) if want_logq else None
+    logp = torch.empty((K, M), dtype=dt, device=mean.device) if want_logp else None
+    rc = load().zs_normal_latent_fwd(dtype_code(dt), _ptr(z), _ptr(logq), _ptr(logp), _ptr(mean), mode, _ptr(std), mode,
+                                     _ptr(prior_mean), _ptr(prior_std), _ptr(eps_in), K, M, E, seed, offset, _stream())
+    if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
+        return None
+    check(rc, "zs_normal_latent_fwd")
+    _count()
+    return z, logq, logp
+
+
+def normal_latent_bwd(dlogq, dlogp, dz_up, z, mean, std, mode, K, M, E, prior_mean=None, prior_std=None,
+                      reparameterized=True):
+    dt = z.dtype
+    for t, n in ((dlogq, "dlogq"), (dlogp, "dlogp"), (dz_up, "dz_up"), (z, "z"), (mean, "mean"), (std, "std")):
+        _chk_tensor(t, n, dt)
+    dmean, dstd = torch.empty_like(mean), torch.empty_like(std)
+    check(load().zs_normal_latent_bwd(dtype_code(dt), _ptr(dmean), _ptr(dstd), _ptr(dlogq), _ptr(dlogp), _ptr(dz_up),
+                                      _ptr(z), _ptr(mean), mode, _ptr(std), mode, _ptr(prior_mean), _ptr(prior_std),
+                                      int(bool(reparameterized)), K, M, E, _stream()), "zs_normal_latent_bwd")
+    _count()
+    return dmean, dstd
+
+
+def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want_logq=True, want_logp=True, seed=0,
+                         offset=0):
+    dt = probs.dtype
+    for t, n in ((probs, "probs"), (prior_probs, "prior_probs"), (u_in, "u_in")):
+        _chk_tensor(t, n, dt)
+    z = torch.empty((K, M, E), dtype=dt, device=probs.device)
+    logq = torch.empty((K, M), dtype=dt, device=probs.device) if want_logq else None
+    logp = torch.empty((K, M), dtype=dt, device=probs.device) if want_logp else None
+    rc = load().zs_bernoulli_latent_fwd(dtype_code(dt), _ptr(z), _ptr(logq), _ptr(logp), _ptr(probs), mode,
+                                        _ptr(prior_probs), _ptr(u_in), K, M, E, seed, offset, _stream())
+    if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
+        return None
+    check(rc, "zs_bernoulli_latent_fwd")
+    _count()
+    return z, logq, logp
+
+
+def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E):
+    dt = z.dtype
+    for t, n in ((dlogq, "dlogq"), (z, "z"), (probs, "probs")):
+        _chk_tensor(t, n, dt)
+    dprobs = torch.empty_like(probs)
+    check(load().zs_bernoulli_latent_bwd(dtype_code(dt), _ptr(dprobs), _ptr(dlogq), _ptr(z), _ptr(probs), mode, K, M, E,
+                                         _stream()), "zs_bernoulli_latent_bwd")
+    _count()
+    return dprobs
 
 
 # ----------------------------------------------------------------------------- Bernoulli
