@@ -231,10 +231,14 @@ int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g,
                   zs_stream_t stream);
 
 /* ---- host-buffer convenience call (end-to-end measurement) ----
- * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers:
- * copies probs/x/logp_other/logq to the device, runs zs_iw_bernoulli_fused (or the
- * two-pass kernels), copies cost/dprobs/dlogp/dlogq back and synchronises.
- * `ws` is a caller-owned device workspace of zs_iw_step_host_workspace() bytes.     */
+ * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers
+ * (pinned memory recommended).  Batch columns are independent, so the step is pipelined over
+ * chunks of 128 columns on three internal streams: the H2D copy of chunk c+1, the fused kernel
+ * (or the two-pass kernels) on chunk c and the D2H copy of chunk c-1 overlap, so the call costs
+ * about max(H2D, D2H) instead of their sum.  Ordered after prior work on `stream`; returns after
+ * everything has landed in the host buffers.  `ws` is a caller-owned device workspace of
+ * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).  The only process-wide state
+ * of the library is the lazily created streams / events of this call.                  */
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X);
 int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
                     const float* probs_host, const float* x_host, const float* logp_other_host,

@@ -1025,12 +1025,50 @@ int zs_debug_set_trace(void* device_buffer) {
     return ZS_OK;
 }
 
+// ---- host-buffer step, pipelined over column chunks -----------------------------------------------
+// Batch columns are independent, so the step is cut into chunks of HS_CHUNK columns that flow through
+// three internal streams: H2D copy of chunk c+1, fused kernel on chunk c and D2H copy of chunk c-1
+// overlap (PCIe is full duplex), with HS_NBUF rotating device buffers.  The [K,B,X] host layout is
+// gathered / scattered with 2-D copies (K rows of chunk*X floats, host pitch B*X).
+namespace {
+constexpr int HS_NBUF = 3;
+constexpr int64_t HS_CHUNK = 128;
+
+struct HostStepCtx {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[HS_NBUF], ev_run[HS_NBUF], ev_out[HS_NBUF], ev_start = nullptr;
+};
+HostStepCtx g_hs;
+
+int host_step_ctx(HostStepCtx** out) {
+    int dev = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    if (!g_hs.ready || g_hs.device != dev) {
+        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_in, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_run, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < HS_NBUF; ++i) {
+            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_in[i], cudaEventDisableTiming));
+            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_run[i], cudaEventDisableTiming));
+            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_out[i], cudaEventDisableTiming));
+        }
+        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_start, cudaEventDisableTiming));
+        g_hs.ready = true;
+        g_hs.device = dev;
+    }
+    *out = &g_hs;
+    return ZS_OK;
+}
+inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+}  // namespace
+
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X) {
     if (K < 1 || B < 0 || X < 1) return -1;
-    // probs, dprobs [K,B,X]; x [B,X]; logp_other, logq, dlogp, dlogq, logpx [K,B]; cost [B]; 256 B slack each
-    const int64_t kbx = K * B * X * 4, bx = B * X * 4, kb = K * B * 4, bb = B * 4;
-    auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
-    return 2 * up(kbx) + up(bx) + 5 * up(kb) + up(bb);
+    const int64_t c = B < HS_CHUNK ? (B > 0 ? B : 1) : HS_CHUNK;
+    const int64_t per = 2 * up256(K * c * X * 4) + up256(c * X * 4) + 5 * up256(K * c * 4) + up256(c * 4);
+    return HS_NBUF * per;
 }
 
 int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
@@ -1038,48 +1076,90 @@ int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* 
                     const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
                     int64_t ws_bytes, zs_stream_t stream) {
     ZS_REQUIRE(probs_host && x_host && ws && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && logq_host == nullptr), ZS_ERR_ARG);
     if (ws_bytes < zs_iw_step_host_workspace(K, B, X)) return ZS_ERR_WORKSPACE;
     ZS_REQUIRE(aligned16(ws), ZS_ERR_ALIGN);
-    cudaStream_t st = as_stream(stream);
-    const int64_t kbx = K * B * X * 4, bx = B * X * 4, kb = K * B * 4, bb = B * 4;
-    auto up = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
-    char* p = (char*)ws;
-    float* d_probs = (float*)p; p += up(kbx);
-    float* d_dprobs = (float*)p; p += up(kbx);
-    float* d_x = (float*)p; p += up(bx);
-    float* d_other = (float*)p; p += up(kb);
-    float* d_logq = (float*)p; p += up(kb);
-    float* d_dlogp = (float*)p; p += up(kb);
-    float* d_dlogq = (float*)p; p += up(kb);
-    float* d_lpx = (float*)p; p += up(kb);
-    float* d_cost = (float*)p;
-
-    ZS_CUDA_TRY(cudaMemcpyAsync(d_probs, probs_host, kbx, cudaMemcpyHostToDevice, st));
-    ZS_CUDA_TRY(cudaMemcpyAsync(d_x, x_host, bx, cudaMemcpyHostToDevice, st));
-    if (logp_other_host) ZS_CUDA_TRY(cudaMemcpyAsync(d_other, logp_other_host, kb, cudaMemcpyHostToDevice, st));
-    if (logq_host) ZS_CUDA_TRY(cudaMemcpyAsync(d_logq, logq_host, kb, cudaMemcpyHostToDevice, st));
-
-    int rc = zs_iw_bernoulli_fused(estimator, d_cost, dprobs_host ? d_dprobs : nullptr, d_dlogp, d_dlogq, nullptr,
-                                   d_probs, d_x, logp_other_host ? d_other : nullptr, logq_host ? d_logq : nullptr, K,
-                                   B, X, grad_scale, stream);
-    if (rc == ZS_ERR_UNSUPPORTED) {
-        // two-pass form: likelihood log-pmf, objective over [K,B], likelihood backward
-        rc = zs_bernoulli_logpmf_fwd(ZS_F32, d_lpx, d_x, ZS_KBCAST, d_probs, ZS_FULL, K, B, X, stream);
-        if (rc != ZS_OK) return rc;
-        if (!logq_host) ZS_CUDA_TRY(cudaMemsetAsync(d_logq, 0, kb, st));
-        rc = zs_iw_objective(ZS_F32, estimator, d_cost, d_dlogp, d_dlogq, d_lpx, d_logq,
-                             logp_other_host ? d_other : nullptr, K, B, grad_scale, stream);
-        if (rc != ZS_OK) return rc;
-        if (dprobs_host)
-            rc = zs_bernoulli_logpmf_bwd(ZS_F32, nullptr, d_dprobs, d_dlogp, d_x, ZS_KBCAST, d_probs, ZS_FULL, K, B, X,
-                                         stream);
-    }
+    HostStepCtx* ctx = nullptr;
+    int rc = host_step_ctx(&ctx);
     if (rc != ZS_OK) return rc;
-    if (cost_host) ZS_CUDA_TRY(cudaMemcpyAsync(cost_host, d_cost, bb, cudaMemcpyDeviceToHost, st));
-    if (dprobs_host) ZS_CUDA_TRY(cudaMemcpyAsync(dprobs_host, d_dprobs, kbx, cudaMemcpyDeviceToHost, st));
-    if (dlogp_host) ZS_CUDA_TRY(cudaMemcpyAsync(dlogp_host, d_dlogp, kb, cudaMemcpyDeviceToHost, st));
-    if (dlogq_host) ZS_CUDA_TRY(cudaMemcpyAsync(dlogq_host, d_dlogq, kb, cudaMemcpyDeviceToHost, st));
-    ZS_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t C = B < HS_CHUNK ? B : HS_CHUNK;
+    const int64_t kcx = up256(K * C * X * 4), cx = up256(C * X * 4), kc = up256(K * C * 4), cb = up256(C * 4);
+    const int64_t per = 2 * kcx + cx + 5 * kc + cb;
+    struct Buf {
+        float *probs, *dprobs, *x, *other, *logq, *dlogp, *dlogq, *lpx, *cost;
+    } buf[HS_NBUF];
+    for (int i = 0; i < HS_NBUF; ++i) {
+        char* p = (char*)ws + i * per;
+        buf[i].probs = (float*)p; p += kcx;
+        buf[i].dprobs = (float*)p; p += kcx;
+        buf[i].x = (float*)p; p += cx;
+        buf[i].other = (float*)p; p += kc;
+        buf[i].logq = (float*)p; p += kc;
+        buf[i].dlogp = (float*)p; p += kc;
+        buf[i].dlogq = (float*)p; p += kc;
+        buf[i].lpx = (float*)p; p += kc;
+        buf[i].cost = (float*)p;
+    }
+    // order the internal streams after whatever the caller already enqueued
+    ZS_CUDA_TRY(cudaEventRecord(ctx->ev_start, as_stream(stream)));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_start, 0));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+
+    const int64_t nchunks = (B + C - 1) / C;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int i = (int)(c % HS_NBUF);
+        const int64_t b0 = c * C, bc = (B - b0 < C) ? (B - b0) : C;
+        Buf& d = buf[i];
+        // the buffer is free once the D2H copies of chunk c - HS_NBUF are done
+        if (c >= HS_NBUF) ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[i], 0));
+        ZS_CUDA_TRY(cudaMemcpy2DAsync(d.probs, bc * X * 4, probs_host + b0 * X, B * X * 4, bc * X * 4, K,
+                                      cudaMemcpyHostToDevice, ctx->s_in));
+        ZS_CUDA_TRY(cudaMemcpyAsync(d.x, x_host + b0 * X, bc * X * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (logp_other_host)
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(d.other, bc * 4, logp_other_host + b0, B * 4, bc * 4, K,
+                                          cudaMemcpyHostToDevice, ctx->s_in));
+        if (logq_host)
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(d.logq, bc * 4, logq_host + b0, B * 4, bc * 4, K, cudaMemcpyHostToDevice,
+                                          ctx->s_in));
+        ZS_CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+
+        ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[i], 0));
+        zs_stream_t run = (zs_stream_t)ctx->s_run;
+        rc = zs_iw_bernoulli_fused(estimator, d.cost, dprobs_host ? d.dprobs : nullptr, d.dlogp, d.dlogq, nullptr,
+                                   d.probs, d.x, logp_other_host ? d.other : nullptr, logq_host ? d.logq : nullptr,
+                                   K, bc, X, grad_scale, run);
+        if (rc == ZS_ERR_UNSUPPORTED || rc == ZS_ERR_ALIGN) {
+            // two-pass form: likelihood log-pmf, objective over [K,bc], likelihood backward
+            rc = zs_bernoulli_logpmf_fwd(ZS_F32, d.lpx, d.x, ZS_KBCAST, d.probs, ZS_FULL, K, bc, X, run);
+            if (rc != ZS_OK) return rc;
+            if (!logq_host) ZS_CUDA_TRY(cudaMemsetAsync(d.logq, 0, K * bc * 4, ctx->s_run));
+            rc = zs_iw_objective(ZS_F32, estimator, d.cost, d.dlogp, d.dlogq, d.lpx, d.logq,
+                                 logp_other_host ? d.other : nullptr, K, bc, grad_scale, run);
+            if (rc != ZS_OK) return rc;
+            if (dprobs_host)
+                rc = zs_bernoulli_logpmf_bwd(ZS_F32, nullptr, d.dprobs, d.dlogp, d.x, ZS_KBCAST, d.probs, ZS_FULL, K,
+                                             bc, X, run);
+        }
+        if (rc != ZS_OK) return rc;
+        ZS_CUDA_TRY(cudaEventRecord(ctx->ev_run[i], ctx->s_run));
+
+        ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_run[i], 0));
+        if (dprobs_host)
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(dprobs_host + b0 * X, B * X * 4, d.dprobs, bc * X * 4, bc * X * 4, K,
+                                          cudaMemcpyDeviceToHost, ctx->s_out));
+        if (cost_host) ZS_CUDA_TRY(cudaMemcpyAsync(cost_host + b0, d.cost, bc * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (dlogp_host)
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogp_host + b0, B * 4, d.dlogp, bc * 4, bc * 4, K, cudaMemcpyDeviceToHost,
+                                          ctx->s_out));
+        if (dlogq_host)
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogq_host + b0, B * 4, d.dlogq, bc * 4, bc * 4, K, cudaMemcpyDeviceToHost,
+                                          ctx->s_out));
+        ZS_CUDA_TRY(cudaEventRecord(ctx->ev_out[i], ctx->s_out));
+    }
+    ZS_CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    ZS_CUDA_TRY(cudaStreamSynchronize(ctx->s_run));
     return ZS_OK;
 }
 

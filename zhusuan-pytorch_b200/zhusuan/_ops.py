@@ -29,14 +29,69 @@ def compute_device():
 
 
 def to_compute(t):
-    """Differentiable move to the CUDA device the kernels run on."""
+    """Differentiable move to the CUDA device the kernels run on.  A CPU tensor that this package
+    itself produced (see back_home) still has its device original attached: reuse it instead of
+    uploading the bytes again."""
     if t.is_cuda:
         return t
+    twin = getattr(t, "_zs_twin", None)
+    if twin is not None and twin[1] == t._version:
+        return twin[0]
     return t.to(compute_device())
 
 
+# Pinned host buffers are slow to allocate (torch.empty(pin_memory=True) ~0.3 ms, cudaHostAlloc of the
+# 160 MB gradient tens of ms), so they are pooled: a buffer is reused once the tensor handed out for it
+# last time is dead (weak reference); while it is alive another buffer is used.
+_pin_pool = {}
+
+
+def pinned_like_pool(shape, dtype, key=None):
+    import weakref
+    shape = tuple(int(v) for v in shape)
+    k = (key, shape, dtype)
+    entries = _pin_pool.setdefault(k, [])
+    for e in entries:
+        if e[1] is None or e[1]() is None:
+            out = e[0].view(shape)
+            e[1] = weakref.ref(out)
+            return out
+    buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+    out = buf.view(shape)
+    entries.append([buf, weakref.ref(out)])
+    return out
+
+
+class _ToHostPinned(torch.autograd.Function):
+    """Device -> host copy through pinned memory (torch's caching host allocator), ~10x the rate of a
+    copy into pageable memory; the gradient goes back with a plain upload."""
+
+    @staticmethod
+    def forward(ctx, t):
+        ctx.dev = t.device
+        out = pinned_like_pool(t.shape, t.dtype)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dev)
+
+
 def back_home(t, home):
-    return t if t.device == home else t.to(home)
+    """Return `t` on the caller's device; remember the device original for later ops."""
+    if t.device == home:
+        return t
+    if home.type == "cpu" and t.is_cuda and t.numel() * t.element_size() >= (1 << 16):
+        out = _ToHostPinned.apply(t)
+    else:
+        out = t.to(home)
+    try:
+        out._zs_twin = (t, out._version)
+    except Exception:
+        pass
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -382,3 +437,61 @@ def iw_bernoulli_fused(probs, x, logp_other, logq, estimator):
     lo = None if logp_other is None else logp_other.contiguous()
     lq = None if logq is None else logq.contiguous()
     return _IWBernoulliFused.apply(probs, x, lo, lq, estimator)
+
+
+# --------------------------------------------------------------------------------------------
+# host-buffer route: probs / x live in (pinned) host memory
+# --------------------------------------------------------------------------------------------
+_host_pool = {}
+
+
+def _pinned(shape, key):
+    return pinned_like_pool(shape, torch.float32, key)
+
+
+def _workspace(nbytes):
+    ws = _host_pool.get("ws")
+    if ws is None or ws.numel() < nbytes or ws.device != compute_device():
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=compute_device())
+        _host_pool["ws"] = ws
+    return ws
+
+
+class _IWBernoulliFusedHost(torch.autograd.Function):
+    """The fused likelihood + objective step for HOST-resident probs / x: zs_iw_step_host pipelines
+    H2D copies, the fused kernel and D2H copies over column chunks; dprobs lands in pinned host memory
+    and is handed to autograd as the gradient of the CPU leaf."""
+
+    @staticmethod
+    def forward(ctx, probs, x, logp_other, logq, estimator):
+        K, B, X = probs.shape
+        cost = _pinned((B,), "cost")
+        dprobs = _pinned((K, B, X), "dprobs") if ctx.needs_input_grad[0] else None
+        dlp = _pinned((K, B), "dlogp")
+        dlq = _pinned((K, B), "dlogq")
+        ws = _workspace(be.iw_step_host_workspace(K, B, X))
+        be.iw_step_host(estimator, cost, dprobs, dlp, dlq, probs, x, logp_other, logq, K, B, X, 1.0 / B, ws)
+        ctx.grads = (dprobs, dlp, dlq)
+        return cost.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            raise RuntimeError("the fused IW objective hands its gradient buffers to autograd and can be "
+                               "back-propagated once; set zhusuan.variational.FUSED = False for retain_graph")
+        dprobs, dlp, dlq = ctx.grads
+        ctx.grads = None
+        gv = float(g)
+        if dprobs is not None and gv != 1.0:
+            dprobs = dprobs * gv
+        return (dprobs, None, dlp * gv if ctx.needs_input_grad[2] else None,
+                dlq * gv if ctx.needs_input_grad[3] else None, None)
+
+
+def iw_bernoulli_fused_host(probs, x, logp_other, logq, estimator):
+    """probs [K,B,X] / x [B,X] float32 CPU tensors (pinned for full PCIe speed), logp_other / logq
+    [K,B] CPU tensors or None -> scalar CPU loss."""
+    be.require_cuda()
+    f = lambda t: None if t is None else t.detach().to(torch.float32).contiguous() if not t.requires_grad else t.to(torch.float32).contiguous()
+    return _IWBernoulliFusedHost.apply(probs.contiguous(), x.to(torch.float32).contiguous(), f(logp_other), f(logq),
+                                       estimator)

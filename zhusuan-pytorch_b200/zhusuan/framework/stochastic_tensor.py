@@ -10,6 +10,8 @@ B200 build: trailing `reduce_sum_dims` are folded into the distribution's log-de
 pass over the [K,B,X] tensor produces the [K,B] result) instead of materialising the elementwise
 log-probabilities and reducing them afterwards.
 """
+import weakref
+
 import torch
 
 from zhusuan.distributions.base import Distribution
@@ -19,7 +21,9 @@ __all__ = ['StochasticTensor']
 
 class StochasticTensor(object):
     def __init__(self, bn, name, dist, observation=None, n_samples=None, **kwargs):
-        self._bn = bn
+        # weak back-reference: bn._nodes[name] -> node -> bn would otherwise be a reference cycle that
+        # keeps every step's samples (device memory) alive until the cyclic GC happens to run
+        self._bn_ref = weakref.ref(bn) if bn is not None else None
         self._name = name
         self._dist = dist
         self._dtype = dist.dtype
@@ -31,7 +35,11 @@ class StochasticTensor(object):
 
     @property
     def bn(self):
-        return self._bn
+        return self._bn_ref() if self._bn_ref is not None else None
+
+    @property
+    def _bn(self):
+        return self.bn
 
     @property
     def name(self):

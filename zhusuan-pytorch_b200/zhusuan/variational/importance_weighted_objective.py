@@ -67,7 +67,9 @@ class ImportanceWeightedObjective(nn.Module):
                 continue
             probs = node.dist.probs
             x = node._observed_value()
-            if x is None or not torch.is_tensor(x) or probs.dim() != 3 or not _be.on_compute_device(probs):
+            if x is None or not torch.is_tensor(x) or probs.dim() != 3:
+                continue
+            if not _be.on_compute_device(probs) and not (probs.device.type == 'cpu' and torch.cuda.is_available()):
                 continue
             if tuple(x.shape) != tuple(probs.shape[1:]) or x.requires_grad or node._multiplier:
                 continue
@@ -108,6 +110,9 @@ class ImportanceWeightedObjective(nn.Module):
         dev = probs.device
         lo = None if logp_other is None else logp_other.to(dev, probs.dtype)
         lq = None if logq is None else logq.to(dev, probs.dtype)
+        if not _be.on_compute_device(probs):
+            # host-resident likelihood tensor: chunk-pipelined H2D / kernel / D2H (zs_iw_step_host)
+            return _ops.iw_bernoulli_fused_host(probs, x.to(dev), lo, lq, est)
         return _ops.iw_bernoulli_fused(probs, x.to(dev), lo, lq, est)
 
     # -- reference protocol ---------------------------------------------------------------------
