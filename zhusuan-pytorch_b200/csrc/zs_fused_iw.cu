@@ -634,8 +634,12 @@ __global__ void __launch_bounds__(COLF_MAX_THREADS, COLF_MIN_CTAS)
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Named barrier over a subset of the CTA's warps (nthreads = 32 * participating warps).  The warp is
+// re-converged first and the non-.aligned form is used, so a lane-0-only branch just before the
+// rendezvous (issue_next) cannot make the arrival divergent.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    __syncwarp();
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 struct RingLayout {
