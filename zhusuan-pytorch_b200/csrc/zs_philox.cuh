@@ -39,14 +39,17 @@ __host__ __device__ __forceinline__ float u01_open(uint32_t r) {
 }
 
 #ifdef __CUDACC__
-// Box-Muller on two words -> two standard normals.
+// Box-Muller on two words -> two standard normals.  The radius uses logf (the SFU lg2 has an absolute
+// error that matters when u1 is within ~1e-6 of 1); the angle uses the SFU sin/cos on (-pi, pi)
+// (abs error 2^-21): the sampling kernels are instruction-bound on the noise and sincospif alone was
+// ~40 instructions.  One definition keeps every kernel's stream identical; the oracle restates it with libm.
 __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
-    float u1 = u01_open(r0), u2 = u01_open(r1);
-    float rad = sqrtf(-2.0f * logf(u1));
+    const float u1 = u01_open(r0), u2 = u01_open(r1);
+    const float rad = sqrtf(-2.0f * logf(u1));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    n0 = rad * c;
-    n1 = rad * s;
+    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &s, &c);
+    n0 = -rad * c;  // cos(t - pi) = -cos t
+    n1 = -rad * s;
 }
 // the four standard normals of element group q (elements 4q .. 4q+3)
 __device__ __forceinline__ void philox_normal4(uint64_t q, uint64_t offset, uint64_t seed, float out[4]) {
