@@ -371,6 +371,117 @@ def gen_sgmcmc():
     save("sgmcmc", **out)
 
 
+# --------------------------------------------------------------------------- BNN (configs 4 and 5, small)
+class _BnnNet(BayesianNet):
+    """The reference's BNN model body (examples/bayesian_neural_nets/bnn_vi.py:16-60 / bnn_sgmcmc.py:16-70),
+    written against the public API: per-layer weight nodes with group_ndims=2 over [n_out, n_in+1],
+    K particles, then a Normal likelihood on y with a scalar logstd, mean over particles and batch."""
+
+    def __init__(self, layer_sizes, K, y_logstd, w_logstds=None):
+        super().__init__()
+        self.layer_sizes, self.K, self.y_logstd, self.w_logstds = layer_sizes, K, y_logstd, w_logstds
+
+    def forward(self, observed):
+        self.observe(observed)
+        x = self.observed["x"]
+        h = x.repeat([self.K, 1, 1])
+        B = x.shape[0]
+        for i, (n_in, n_out) in enumerate(zip(self.layer_sizes[:-1], self.layer_sizes[1:])):
+            kw = dict(std=torch.ones([n_out, n_in + 1], dtype=x.dtype)) if self.w_logstds is None else \
+                dict(logstd=self.w_logstds[i])
+            w = self.normal("w" + str(i), mean=torch.zeros([n_out, n_in + 1], dtype=x.dtype), group_ndims=2,
+                            n_samples=self.K, reduce_mean_dims=[0], **kw)
+            h = torch.cat([h, torch.ones([*h.shape[:-1], 1], dtype=x.dtype)], -1)
+            h = torch.einsum("kof,kbf->kbo", w, h) / math.sqrt(n_in + 1)
+            if i < len(self.layer_sizes) - 2:
+                h = torch.relu(h)
+        y_mean = h.squeeze(2)
+        self.normal("y", mean=y_mean, logstd=self.y_logstd, reduce_mean_dims=[0, 1], multiplier=456)
+        return self
+
+
+class _BnnVar(BayesianNet):
+    def __init__(self, layer_sizes, K, means, logstds):
+        super().__init__()
+        self.layer_sizes, self.K, self.means, self.logstds = layer_sizes, K, means, logstds
+
+    def forward(self, observed):
+        self.observe(observed)
+        for i in range(len(self.layer_sizes) - 1):
+            self.normal("w" + str(i), mean=self.means[i], logstd=self.logstds[i], group_ndims=2, n_samples=self.K,
+                        reduce_mean_dims=[0])
+        return self
+
+
+def gen_bnn():
+    rng = np.random.RandomState(18)
+    K, B, D, H = 5, 7, 6, 4
+    sizes = [D, H, 1]
+    shapes = [(H, D + 1), (1, H + 1)]
+    x64 = rng.standard_normal((B, D))
+    y64 = rng.standard_normal(B)
+    means64 = [0.3 * rng.standard_normal(s) for s in shapes]
+    logstds64 = [0.2 * rng.standard_normal(s) - 1.0 for s in shapes]
+    eps64 = [rng.standard_normal((K,) + s) for s in shapes]
+    out = dict(K=np.int64(K), x=x64, y=y64, w0_mean=means64[0], w1_mean=means64[1], w0_logstd=logstds64[0],
+               w1_logstd=logstds64[1], eps0=eps64[0], eps1=eps64[1])
+    for dn, dt in DT.items():
+        # --- config 4: ELBO / SGVB with weight particles
+        means = [t(m, dt, True) for m in means64]
+        logstds = [t(s, dt, True) for s in logstds64]
+        y_logstd = t(np.array([-0.3]), dt, True)
+        queue = [t(e, dt) for e in eps64] * 2  # .tensor is read twice per node (stochastic_node + ELBO.forward)
+        order = [0, 1, 0, 1]
+        it = iter(order)
+
+        def fake_normal(*args, **kw):
+            return t(eps64[next(it)], dt)
+
+        elbo = ELBO(_BnnNet(sizes, K, y_logstd), _BnnVar(sizes, K, means, logstds))
+        with mock.patch("torch.normal", fake_normal):
+            loss = elbo({"x": t(x64, dt), "y": t(y64, dt)})
+        grads = torch.autograd.grad(loss, means + logstds + [y_logstd])
+        p = "vi_%s_" % dn
+        out[p + "loss"] = npy(loss)
+        for name, g in zip(["dm0", "dm1", "ds0", "ds1", "dylogstd"], grads):
+            out[p + name] = npy(g)
+        # --- config 5: SGLD over the weight chains (prior logstd fixed), 3 updates
+        if dn == "f32":
+            net = _BnnNet(sizes, K, t(np.array([-0.3]), dt), w_logstds=[t(np.zeros(s), dt) for s in shapes])
+            sampler = mcmc.SGLD(learning_rate=1e-3)
+            noise = rng.standard_normal((4, 2) + (K,)).astype(np.float64)  # placeholder keeps the rng stream fixed
+            draws = {"n": 0}
+            sg_eps = [rng.standard_normal((K,) + s) for s in shapes] + [rng.standard_normal((K,) + s) for s in shapes]
+            unit = [[rng.standard_normal((K,) + s) for s in shapes] for _ in range(3)]
+            state = {"calls": []}
+
+            def fake_normal2(*args, **kw):
+                if "size" in kw and len(args) >= 2 and args[1] == 1.0:  # initial reparameterised draws
+                    e = sg_eps[draws["n"]]
+                    draws["n"] += 1
+                    return t(e, dt)
+                std = args[1]
+                size = tuple(kw["size"])
+                i = 0 if size == (K,) + shapes[0] else 1
+                return t(unit[state["step"]][i], dt) * std
+
+            obs = {"x": t(x64, dt), "y": t(y64, dt)}
+            with mock.patch("torch.normal", fake_normal2):
+                w = sampler.sample(net, obs, True)
+                out["sgld_w0_init"], out["sgld_w1_init"] = npy(w["w0"]), npy(w["w1"])
+                traj0, traj1 = [], []
+                for s in range(3):
+                    state["step"] = s
+                    w = sampler.sample(net, obs, False)
+                    traj0.append(npy(w["w0"]).copy())
+                    traj1.append(npy(w["w1"]).copy())
+            out["sgld_w0_traj"], out["sgld_w1_traj"] = np.stack(traj0), np.stack(traj1)
+            out["sgld_unit0"] = np.stack([u[0] for u in unit])
+            out["sgld_unit1"] = np.stack([u[1] for u in unit])
+            out["sgld_init_eps0"], out["sgld_init_eps1"] = sg_eps[2], sg_eps[3]
+    save("bnn", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_normal()
@@ -380,3 +491,4 @@ if __name__ == "__main__":
     gen_iw_path()
     gen_elbo_path()
     gen_sgmcmc()
+    gen_bnn()

@@ -716,3 +716,93 @@ def test_sghmc_multiple_latents(dev):
             w = s.sample(net, {}, False)
         assert tuple(w["a"].shape) == (5, 3, 4) and tuple(w["b"].shape) == (5, 2)
         assert torch.isfinite(w["a"]).all() and w["a"].requires_grad
+
+
+# ============================================================================ BNN (configs 4 and 5)
+class _BnnNet(BayesianNet):
+    """The reference's BNN model body (examples/bayesian_neural_nets/bnn_vi.py:16-60, bnn_sgmcmc.py:16-70)
+    against the public API: weight nodes with group_ndims=2, K particles, scalar-logstd likelihood on y,
+    mean over particles and batch, multiplier."""
+
+    def __init__(self, layer_sizes, K, y_logstd, dev, w_logstds=None):
+        super().__init__(device=dev)
+        self.layer_sizes, self.K, self.y_logstd, self.w_logstds, self.dev = layer_sizes, K, y_logstd, w_logstds, dev
+
+    def forward(self, observed):
+        self.observe(observed)
+        x = self.observed["x"]
+        d, dt = self.dev, x.dtype
+        h = x.repeat([self.K, 1, 1])
+        for i, (n_in, n_out) in enumerate(zip(self.layer_sizes[:-1], self.layer_sizes[1:])):
+            kw = dict(std=torch.ones([n_out, n_in + 1], dtype=dt, device=d)) if self.w_logstds is None else \
+                dict(logstd=self.w_logstds[i])
+            w = self.normal("w" + str(i), mean=torch.zeros([n_out, n_in + 1], dtype=dt, device=d), group_ndims=2,
+                            n_samples=self.K, reduce_mean_dims=[0], **kw)
+            h = torch.cat([h, torch.ones([*h.shape[:-1], 1], dtype=dt, device=d)], -1)
+            h = torch.einsum("kof,kbf->kbo", w, h) / math.sqrt(n_in + 1)
+            if i < len(self.layer_sizes) - 2:
+                h = torch.relu(h)
+        self.normal("y", mean=h.squeeze(2), logstd=self.y_logstd, reduce_mean_dims=[0, 1], multiplier=456)
+        return self
+
+
+class _BnnVar(BayesianNet):
+    def __init__(self, layer_sizes, K, means, logstds, dev):
+        super().__init__(device=dev)
+        self.layer_sizes, self.K, self.means, self.logstds = layer_sizes, K, means, logstds
+
+    def forward(self, observed):
+        self.observe(observed)
+        for i in range(len(self.layer_sizes) - 1):
+            self.normal("w" + str(i), mean=self.means[i], logstd=self.logstds[i], group_ndims=2, n_samples=self.K,
+                        reduce_mean_dims=[0])
+        return self
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+def test_bnn_vi_against_reference_golden(dev, golden, dn):
+    """Config 4 (bnn_vi.py) at a small size: ELBO with 5 weight particles, loss and every gradient."""
+    g = golden("bnn")
+    dt = torch.float32 if dn == "f32" else torch.float64
+    K = int(g["K"])
+    sizes = [g["x"].shape[1], g["w0_mean"].shape[0], 1]
+    means = [T(g["w0_mean"], dev, dt, True), T(g["w1_mean"], dev, dt, True)]
+    logstds = [T(g["w0_logstd"], dev, dt, True), T(g["w1_logstd"], dev, dt, True)]
+    y_logstd = T(np.array([-0.3]), dev, dt, True)
+    eps = [T(g["eps0"], dev, dt), T(g["eps1"], dev, dt)]
+    elbo = ELBO(_BnnNet(sizes, K, y_logstd, dev), _BnnVar(sizes, K, means, logstds, dev))
+    with _rng.inject(normal=[eps[0], eps[1], eps[0], eps[1]]):
+        loss = elbo({"x": T(g["x"], dev, dt), "y": T(g["y"], dev, dt)})
+    rt = 2e-5 if dn == "f32" else 1e-10
+    p = "vi_%s_" % dn
+    assert loss.dim() == 0
+    close(loss, g[p + "loss"], rt)
+    grads = torch.autograd.grad(loss, means + logstds + [y_logstd])
+    for name, gr in zip(["dm0", "dm1", "ds0", "ds1", "dylogstd"], grads):
+        close(gr, g[p + name], rt * 5)
+
+
+def test_bnn_sgld_against_reference_golden(dev, golden):
+    """Config 5 (bnn_sgmcmc.py) at a small size: SGLD over two differently shaped weight latents,
+    5 chains, three updates with the reference's noise."""
+    g = golden("bnn")
+    K = int(g["K"])
+    sizes = [g["x"].shape[1], g["w0_mean"].shape[0], 1]
+    shapes = [tuple(g["w0_mean"].shape), tuple(g["w1_mean"].shape)]
+    net = _BnnNet(sizes, K, T(np.array([-0.3]), dev), dev, w_logstds=[torch.zeros(s, device=dev) for s in shapes])
+    sampler = zhusuan.mcmc.SGLD(learning_rate=1e-3)
+    obs = {"x": T(g["x"], dev), "y": T(g["y"], dev)}
+    init = [T(g["sgld_init_eps0"], dev), T(g["sgld_init_eps1"], dev)]
+    # resample=True: forward draws once per node, then the sampler reads .tensor again (those draws are kept)
+    with _rng.inject(normal=[init[0], init[1], init[0], init[1]]):
+        w = sampler.sample(net, obs, True)
+    close(w["w0"], g["sgld_w0_init"], 1e-6)
+    close(w["w1"], g["sgld_w1_init"], 1e-6)
+    std = np.float32(math.sqrt(float(torch.as_tensor(1e-3))))
+    for s in range(3):
+        inj = [T(g["sgld_unit0"][s].astype(np.float32) * std, dev), T(g["sgld_unit1"][s].astype(np.float32) * std, dev)]
+        with _rng.inject(normal=inj):
+            w = sampler.sample(net, obs, False)
+        close(w["w0"], g["sgld_w0_traj"][s], 2e-5)
+        close(w["w1"], g["sgld_w1_traj"][s], 2e-5)
+        assert w["w0"].requires_grad and w["w0"].is_leaf
