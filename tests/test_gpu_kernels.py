@@ -340,7 +340,11 @@ def _fused_inputs(K, B, X, binary=True, seed=8):
                                     (16, 149, 128)])
 @pytest.mark.parametrize("est", ["sgvb", "vimco"])
 @pytest.mark.parametrize("binary", [True, False])
-def test_fused_vs_oracle(oracle, K, B, X, est, binary):
+@pytest.mark.parametrize("impl", ["ring", "box"])
+def test_fused_vs_oracle(oracle, monkeypatch, K, B, X, est, binary, impl):
+    # ring: rows streamed twice through per-warp slot rings; box: column resident, tensor bulk copies
+    # (shapes the box kernel cannot take fall through to the ring inside the library)
+    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
     probs, x, other, logq = _fused_inputs(K, B, X, binary)
     code = be.SGVB if est == "sgvb" else be.VIMCO
     r = be.iw_bernoulli_fused(code, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B, want_logpx=True)
@@ -381,8 +385,10 @@ def test_fused_golden_path(golden):
     close(2 * host(r["dprobs"])[:K], g[p + "dprobs"], 1e-4)
 
 
-def test_fused_full_size_properties(oracle):
+@pytest.mark.parametrize("impl", ["ring", "box"])
+def test_fused_full_size_properties(oracle, monkeypatch, impl):
     """BASELINE config 2 size (K=50, B=1024, X=784): fused == two-pass kernels == oracle."""
+    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
     K, B, X = 50, 1024, 784
     probs, x, other, logq = _fused_inputs(K, B, X, True, seed=9)
     dp, dx, do, dq = dev(probs), dev(x), dev(other), dev(logq)
@@ -405,13 +411,20 @@ def test_fused_full_size_properties(oracle):
         close(host(r["logpx"]), o["logpx"], 1e-5)
 
 
-def test_fused_invalid_probs_give_nan():
-    K, B, X = 8, 2, 16
+@pytest.mark.parametrize("impl", ["ring", "box"])
+@pytest.mark.parametrize("bad,where", [(1.5, (3, 1, 5)), (-0.25, (0, 0, 0)), (np.float32(1.0) + np.float32(2.0 ** -23), (7, 1, 15)),
+                                       (-3e-8, (2, 0, 9))])
+def test_fused_invalid_probs_give_nan(monkeypatch, impl, bad, where):
+    """bernoulli.py:84-95: log(p + eps) or log(1 - p + eps) of a negative argument is NaN whatever x is;
+    the kernels keep that rule exactly (valid iff -1e-8 <= p <= 1) although they evaluate one log per element."""
+    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+    K, B, X = 8, 2, 32
     probs, x, other, logq = _fused_inputs(K, B, X)
-    probs[3, 1, 5] = 1.5
+    probs[where] = bad
     r = be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), dev(other), dev(logq), 1.0, want_logpx=True)
     lp = host(r["logpx"])
-    assert np.isnan(lp[3, 1]) and np.isfinite(np.delete(lp.ravel(), 3 * B + 1)).all()
+    k, b, _ = where
+    assert np.isnan(lp[k, b]) and np.isfinite(np.delete(lp.ravel(), k * B + b)).all()
 
 
 def test_fused_shape_coverage(oracle):

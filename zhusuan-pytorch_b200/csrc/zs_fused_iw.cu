@@ -19,6 +19,8 @@
 // two-pass form; the unfused entry points remain as the general fallback.
 #include <stdlib.h>
 
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched at run time, libcuda is not linked
+
 #include "zs_common.cuh"
 
 namespace zs {
@@ -642,13 +644,61 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- stager helpers: batched global loads ---------------------------------------------------------------
+__device__ __forceinline__ void stage_scalars_batched(float* s_other, float* s_lq, const float* __restrict__ logp_other,
+                                                      const float* __restrict__ logq, int K, int64_t B, int64_t b, int lane) {
+    for (int k0 = lane; k0 < K; k0 += 32 * 4) {
+        float o[4], q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u;
+            const int kc = k < K ? k : k0;  // always in bounds
+            o[u] = logp_other ? __ldg(logp_other + (int64_t)kc * B + b) : 0.f;
+            q[u] = logq ? __ldg(logq + (int64_t)kc * B + b) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u;
+            if (k < K) {
+                s_other[k] = o[u];
+                s_lq[k] = q[u];
+            }
+        }
+    }
+}
+__device__ __forceinline__ void stage_x_batched(float* s_xrow, int* s_flag, const float* __restrict__ xrow, int X4, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(xrow);
+    float4* dst = reinterpret_cast<float4*>(s_xrow);
+    bool binary = true;
+    for (int v0 = lane; v0 < X4; v0 += 32 * 8) {
+        float4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int v = v0 + 32 * u;
+            t[u] = __ldg(src + (v < X4 ? v : v0));  // always in bounds
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int v = v0 + 32 * u;
+            if (v < X4) {
+                dst[v] = t[u];
+                binary = binary && (t[u].x == 0.f || t[u].x == 1.f) && (t[u].y == 0.f || t[u].y == 1.f) &&
+                         (t[u].z == 0.f || t[u].z == 1.f) && (t[u].w == 0.f || t[u].w == 1.f);
+            }
+        }
+    }
+    binary = __all_sync(0xffffffffu, binary);
+    if (lane == 0) *s_flag = binary ? 1 : 0;
+}
+
 struct RingLayout {
     int K, X, R, Kpad;
     __host__ __device__ RingLayout(int K_, int X_, int R_) : K(K_), X(X_), R(R_), Kpad((K_ + 3) & ~3) {}
     __host__ __device__ size_t slots_off() const { return 0; }
     __host__ __device__ size_t x_off() const { return (size_t)R * X * 4; }
     __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)3 * X * 4 + 15) & ~(size_t)15; }
-    __host__ __device__ size_t lpx_off() const { return xw_off() + (size_t)2 * Kpad * 8; }    // xw: [2][Kpad] double
+    __host__ __device__ size_t xv_off() const { return xw_off() + (size_t)2 * Kpad * 8; }     // xw: [2][Kpad] double
+    __host__ __device__ size_t lpx_off() const { return xv_off() + (size_t)4 * Kpad * 8; }    // xv: [4][Kpad] double
     __host__ __device__ size_t other_off() const { return lpx_off() + (size_t)4 * Kpad * 4; }  // [4][Kpad]
     __host__ __device__ size_t lq_off() const { return other_off() + (size_t)4 * Kpad * 4; }
     __host__ __device__ size_t bin_off() const { return lq_off() + (size_t)4 * Kpad * 4; }
@@ -656,24 +706,94 @@ struct RingLayout {
     __host__ __device__ size_t total() const { return bar_off() + (size_t)R * 8; }
 };
 
+// ---- row loops of the ring kernel ---------------------------------------------------------------------
+// The kernel is issue/latency-bound on an SM well before HBM saturates (37 CTAs alone run at the same
+// 8.5 us per column as 148 do: profiles/r1_notes.md), so these loops are written for instruction count:
+//  * binary x: log2 of the PRODUCT of four selected arguments (one SFU op per 4 elements; arguments are
+//    >= 1e-8 for valid probabilities, so the product cannot underflow); the reference's "a log argument is
+//    negative -> NaN" rule is kept exactly by tracking min / max of p (valid iff -1e-8 <= p <= 1) with two
+//    3-input min/max per 4 elements instead of forming both arguments;
+//  * backward: d/dp = g / s with the signed argument s = x ? p + eps : (p - 1) - eps == -((1 - p) + eps);
+//  * ITER > 0 is the exact compile-time trip count ceil(X/128) per lane: fully unrolled, constant offsets,
+//    no remainder loop (the remainder loops were a quarter of all instructions executed).
 template <bool BINARY>
-__device__ __forceinline__ float smem_row_logpmf(const float4* __restrict__ p4, const float4* __restrict__ x4, int X4,
-                                                 int lane) {
-    float acc = 0.f, mn = 1.0f;
-#pragma unroll 4
-    for (int v = lane; v < X4; v += 32) acc += lpmf4<BINARY>(lds128(p4 + v), lds128(x4 + v), mn);
-    if (BINARY && mn < 0.f) acc = __int_as_float(0x7fc00000);
-    return acc;
+__device__ __forceinline__ void ring_lpmf4(const float4& xx, const float4& p, float& acc, float& pmin, float& pmax) {
+    if (BINARY) {
+        const float a0 = (xx.x == 1.f ? p.x : 1.0f - p.x) + 1e-8f, a1 = (xx.y == 1.f ? p.y : 1.0f - p.y) + 1e-8f;
+        const float a2 = (xx.z == 1.f ? p.z : 1.0f - p.z) + 1e-8f, a3 = (xx.w == 1.f ? p.w : 1.0f - p.w) + 1e-8f;
+        acc += fast_log2((a0 * a1) * (a2 * a3));
+        pmin = fminf(pmin, fminf(p.x, p.y));
+        pmin = fminf(pmin, fminf(p.z, p.w));
+        pmax = fmaxf(pmax, fmaxf(p.x, p.y));
+        pmax = fmaxf(pmax, fmaxf(p.z, p.w));
+    } else {
+        float mn = 1.0f;
+        acc += lpmf4<false>(p, xx, mn);
+    }
 }
 template <bool BINARY>
-__device__ __forceinline__ void smem_row_dprobs(float* __restrict__ drow, const float4* __restrict__ p4,
-                                                const float4* __restrict__ x4, int X4, int lane, float g) {
-#pragma unroll 4
-    for (int v = lane; v < X4; v += 32) stg_hint(drow + 4 * v, dprobs4<BINARY>(lds128(p4 + v), lds128(x4 + v), g), 0);
+__device__ __forceinline__ float4 ring_dprobs4(const float4& xx, const float4& p, float g) {
+    if (BINARY) {
+        float4 o;
+        o.x = g * fast_rcp(xx.x == 1.f ? p.x + 1e-8f : (p.x - 1.0f) - 1e-8f);
+        o.y = g * fast_rcp(xx.y == 1.f ? p.y + 1e-8f : (p.y - 1.0f) - 1e-8f);
+        o.z = g * fast_rcp(xx.z == 1.f ? p.z + 1e-8f : (p.z - 1.0f) - 1e-8f);
+        o.w = g * fast_rcp(xx.w == 1.f ? p.w + 1e-8f : (p.w - 1.0f) - 1e-8f);
+        return o;
+    }
+    return dprobs4<false>(p, xx, g);
 }
 
-template <int EST, bool TRACE>
-__global__ void __launch_bounds__(1024, 1)
+template <bool BINARY, int ITER>
+__device__ __forceinline__ float smem_row_logpmf(const float4* __restrict__ p4, const float4* __restrict__ x4, int X4,
+                                                 int lane) {
+    float acc = 0.f, pmin = 0.f, pmax = 0.f;  // 0 is inside the valid range of p
+    if (ITER > 0) {
+#pragma unroll
+        for (int u = 0; u < ITER; ++u) {
+            const int v = lane + 32 * u;
+            if (u + 1 < ITER || v < X4) ring_lpmf4<BINARY>(lds128(x4 + v), lds128(p4 + v), acc, pmin, pmax);
+        }
+    } else {
+#pragma unroll 4
+        for (int v = lane; v < X4; v += 32) ring_lpmf4<BINARY>(lds128(x4 + v), lds128(p4 + v), acc, pmin, pmax);
+    }
+    // a negative log argument is NaN in the reference: p + eps < 0 or (1 - p) + eps < 0
+    if (BINARY && (pmin < -1e-8f || pmax > 1.0f)) acc = __int_as_float(0x7fc00000);
+    return acc;
+}
+template <bool BINARY, int ITER>
+__device__ __forceinline__ void smem_row_dprobs(float* __restrict__ drow, const float4* __restrict__ p4,
+                                                const float4* __restrict__ x4, int X4, int lane, float g) {
+    if (ITER > 0) {
+#pragma unroll
+        for (int u = 0; u < ITER; ++u) {
+            const int v = lane + 32 * u;
+            if (u + 1 < ITER || v < X4) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(lds128(x4 + v), lds128(p4 + v), g), 0);
+        }
+    } else {
+#pragma unroll 4
+        for (int v = lane; v < X4; v += 32) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(lds128(x4 + v), lds128(p4 + v), g), 0);
+    }
+}
+
+// max and 1/sum-exp of a column's posted log-weights (every row warp, redundantly)
+__device__ __forceinline__ void ring_max_sumexp(int lane, int K, const double* s_xv, double& m1, float& invS) {
+    float mf = -INFINITY;
+    for (int k = lane; k < K; k += 32) mf = fmaxf(mf, (float)s_xv[k]);
+    mf = warp_max(mf);
+    m1 = (double)mf;
+    float S = 0.f;
+    for (int k = lane; k < K; k += 32) S += expf((float)(s_xv[k] - m1));
+    S = warp_sum(S);
+    invS = fast_rcp(S) * (2.0f - S * fast_rcp(S));
+}
+
+#ifndef ZS_RING_MAX_ROW_WARPS
+#define ZS_RING_MAX_ROW_WARPS 25  // + 3 service warps = 896 threads: 72 registers per thread
+#endif
+template <int EST, int ITER>
+__global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
     k_iw_bernoulli_ring(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
                         const float* __restrict__ x, const float* __restrict__ logp_other,
@@ -685,6 +805,7 @@ __global__ void __launch_bounds__(1024, 1)
     float* slots = reinterpret_cast<float*>(smem + L.slots_off());
     float* s_x = reinterpret_cast<float*>(smem + L.x_off());
     double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
+    double* s_xv = reinterpret_cast<double*>(smem + L.xv_off());  // log-weights of a column, posted by the row warps
     float* s_lpx = reinterpret_cast<float*>(smem + L.lpx_off());
     float* s_other = reinterpret_cast<float*>(smem + L.other_off());
     float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
@@ -701,7 +822,7 @@ __global__ void __launch_bounds__(1024, 1)
     const int phases = dprobs ? 2 : 1;
     const int64_t ncols = ((int64_t)blockIdx.x < B) ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto mark = [&](int col, int point) {
-        if (TRACE && trace != nullptr && threadIdx.x == 0 && col < 8)
+        if (trace != nullptr && threadIdx.x == 0 && col < 8)
             trace[(int64_t)blockIdx.x * 40 + col * 5 + point] = clock64();
     };
 
@@ -711,29 +832,17 @@ __global__ void __launch_bounds__(1024, 1)
     }
     // Per-column scalars and log-pmf live in 4 buffers (column & 3), the x row in 3 (column % 3):
     // an objective warp may work on column c until the barrier of column c+2.
-    auto stage_scalars = [&](int64_t b, int buf) {
-        for (int k = lane; k < K; k += 32) {
-            s_other[buf * Kpad + k] = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
-            s_lq[buf * Kpad + k] = logq ? logq[(int64_t)k * B + b] : 0.f;
-        }
-    };
-    auto stage_x = [&](int64_t b, int slot) {
-        const float4* src = reinterpret_cast<const float4*>(x + b * X);
-        float4* dst = reinterpret_cast<float4*>(s_x + (size_t)slot * X);
-        bool binary = true;
-        for (int v = lane; v < X4; v += 32) {
-            const float4 xx = __ldg(src + v);
-            dst[v] = xx;
-            binary = binary && (xx.x == 0.f || xx.x == 1.f) && (xx.y == 0.f || xx.y == 1.f) &&
-                     (xx.z == 0.f || xx.z == 1.f) && (xx.w == 0.f || xx.w == 1.f);
-        }
-        binary = __all_sync(0xffffffffu, binary);
-        if (lane == 0) s_bin[slot] = binary ? 1 : 0;
-    };
+    // The stager takes part in every column rendezvous, so one iteration of its loop bounds the column rate:
+    // its global loads are issued in batches (all in flight together), never one latency after the other.
+    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, B, b, lane); };
+    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * X, s_bin + slot, x + b * X, X4, lane); };
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
-        if (ncols > 1) stage_x((int64_t)blockIdx.x + gridDim.x, 1);
+        if (ncols > 1) {
+            stage_scalars((int64_t)blockIdx.x + gridDim.x, 1);
+            stage_x((int64_t)blockIdx.x + gridDim.x, 1);
+        }
     }
     __syncthreads();
 
@@ -744,8 +853,12 @@ __global__ void __launch_bounds__(1024, 1)
         int64_t b = blockIdx.x;
         for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
             named_bar_sync(1 + (int)(c & 1), sync_threads);
-            if (c + 1 < ncols) stage_scalars(b + gridDim.x, (int)((c + 1) & 3));
-            if (c + 2 < ncols) stage_x(b + 2 * (int64_t)gridDim.x, (int)((c + 2) % 3));
+            // a row warp posts the log-weight of a row of column c+1 as soon as it is reduced, so the
+            // scalars are staged two columns ahead (into the buffer of column c-2, dead by now)
+            if (c + 2 < ncols) {
+                stage_scalars(b + 2 * (int64_t)gridDim.x, (int)((c + 2) & 3));
+                stage_x(b + 2 * (int64_t)gridDim.x, (int)((c + 2) % 3));
+            }
         }
         return;
     }
@@ -802,11 +915,14 @@ __global__ void __launch_bounds__(1024, 1)
             mbar_wait(&full[s], ring_phase);
             if (++ring_pos == D) { ring_pos = 0; ring_phase ^= 1u; }
             const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)s * X);
-            float acc = binary ? smem_row_logpmf<true>(p4, x4, X4, lane) : smem_row_logpmf<false>(p4, x4, X4, lane);
+            float acc = binary ? smem_row_logpmf<true, ITER>(p4, x4, X4, lane) : smem_row_logpmf<false, ITER>(p4, x4, X4, lane);
             acc = warp_sum(acc);  // every lane has finished reading the slot
             if (lane == 0) {
-                s_lpx[par * Kpad + k] = acc * LN2;
                 issue_next();
+                const float lp = acc * LN2;
+                s_lpx[par * Kpad + k] = lp;
+                // same association as k_iw_objective: (logp - logq) + extra, in double
+                s_xv[par * Kpad + k] = ((double)lp - (double)s_lq[par * Kpad + k]) + (double)s_other[par * Kpad + k];
             }
         }
         mark((int)c, 1);
@@ -816,18 +932,16 @@ __global__ void __launch_bounds__(1024, 1)
             // ---- phase B: weights of the owned rows, rows again (L2) -> dprobs ----------------------
             double m1;
             float invS;
-            colf_max_sumexp(lane, K, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, m1, invS);
+            ring_max_sumexp(lane, K, s_xv + par * Kpad, m1, invS);
             for (int k = warp; k < K; k += NW) {
-                const double xv = ((double)s_lpx[par * Kpad + k] - (double)s_lq[par * Kpad + k]) +
-                                  (double)s_other[par * Kpad + k];
-                const float g = -(expf((float)(xv - m1)) * invS) * gscale;
+                const float g = -(expf((float)(s_xv[par * Kpad + k] - m1)) * invS) * gscale;
                 const int s = warp * D + ring_pos;
                 mbar_wait(&full[s], ring_phase);
                 if (++ring_pos == D) { ring_pos = 0; ring_phase ^= 1u; }
                 const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)s * X);
                 float* drow = dprobs + ((int64_t)k * B + b) * X;
-                if (binary) smem_row_dprobs<true>(drow, p4, x4, X4, lane, g);
-                else smem_row_dprobs<false>(drow, p4, x4, X4, lane, g);
+                if (binary) smem_row_dprobs<true, ITER>(drow, p4, x4, X4, lane, g);
+                else smem_row_dprobs<false, ITER>(drow, p4, x4, X4, lane, g);
                 __syncwarp();
                 if (lane == 0) issue_next();
             }
@@ -836,9 +950,319 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Box variant (default when the shape allows): the column is RESIDENT in shared memory between its two
+// passes and arrives by TENSOR bulk copies.
+//
+// Why (tools/probes/tma_probe.cu, tma_tensor_probe.cu, profiles/r1_notes.md): every variant of the ring
+// kernel ran at 8.5 us per column per SM, with 37 CTAs as with 148, with or without the arithmetic.  The
+// bound was the SM's copy engine: a 1-D cp.async.bulk costs ~134 cycles of fixed overhead, so 3 KB row copies
+// peak at 38 GB/s per SM, below the 43 GB/s per SM that HBM can feed, and the ring issued 100 of them per
+// column.  A 3-D tensor copy moves a box {inner, 1, K} -- the same `inner` floats of all K rows of one batch
+// column -- with one instruction at ~13 cycles per row segment: 64 GB/s per SM at 448-byte segments, 105 GB/s
+// at 784.  The column is cut into X/inner boxes that flow through a ring of NSLOT > X/inner slots:
+//   phase A(c)  waits for the boxes of column c in order, adds up the log-pmf pieces of the warp's two rows;
+//   rendezvous  (named barrier, as in the ring kernel; objective + stager warps unchanged);
+//   phase B(c)  walks the still-resident boxes again, writes dprobs, releases each box (empty mbarrier);
+//   producer    one thread refills a released slot with the box NSLOT tasks ahead: every box is requested
+//               about (NSLOT+1)/(2 NBOX) of a column period before its first read.
+// probs is read from L2/HBM exactly once; no second pass over L2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// request a box into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_box_l2(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+struct BoxLayout {
+    int K, X, inner, nslot, Kpad;
+    __host__ __device__ BoxLayout(int K_, int X_, int inner_, int nslot_)
+        : K(K_), X(X_), inner(inner_), nslot(nslot_), Kpad((K_ + 3) & ~3) {}
+    __host__ __device__ size_t slot_bytes() const { return ((size_t)K * inner * 4 + 127) & ~(size_t)127; }
+    __host__ __device__ size_t slots_off() const { return 0; }
+    __host__ __device__ size_t x_off() const { return (size_t)nslot * slot_bytes(); }
+    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)3 * X * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xv_off() const { return xw_off() + (size_t)2 * Kpad * 8; }
+    __host__ __device__ size_t lpx_off() const { return xv_off() + (size_t)4 * Kpad * 8; }
+    __host__ __device__ size_t other_off() const { return lpx_off() + (size_t)4 * Kpad * 4; }
+    __host__ __device__ size_t lq_off() const { return other_off() + (size_t)4 * Kpad * 4; }
+    __host__ __device__ size_t bin_off() const { return lq_off() + (size_t)4 * Kpad * 4; }
+    __host__ __device__ size_t bar_off() const { return (bin_off() + 16 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t total() const { return bar_off() + (size_t)2 * nslot * 8; }
+};
+
+// two rows of one box against the same x piece: one x load and one compare per element serve both rows
+template <bool BINARY>
+__device__ __forceinline__ void box_lpmf_pair(const float4& xx, const float4& pa, const float4& pb, float& acc_a,
+                                              float& acc_b, float (&rng)[4]) {
+    if (BINARY) {
+        const bool s0 = xx.x == 1.f, s1 = xx.y == 1.f, s2 = xx.z == 1.f, s3 = xx.w == 1.f;
+        {
+            const float a0 = (s0 ? pa.x : 1.0f - pa.x) + 1e-8f, a1 = (s1 ? pa.y : 1.0f - pa.y) + 1e-8f;
+            const float a2 = (s2 ? pa.z : 1.0f - pa.z) + 1e-8f, a3 = (s3 ? pa.w : 1.0f - pa.w) + 1e-8f;
+            acc_a += fast_log2((a0 * a1) * (a2 * a3));
+            rng[0] = fminf(rng[0], fminf(pa.x, pa.y));
+            rng[0] = fminf(rng[0], fminf(pa.z, pa.w));
+            rng[1] = fmaxf(rng[1], fmaxf(pa.x, pa.y));
+            rng[1] = fmaxf(rng[1], fmaxf(pa.z, pa.w));
+        }
+        {
+            const float a0 = (s0 ? pb.x : 1.0f - pb.x) + 1e-8f, a1 = (s1 ? pb.y : 1.0f - pb.y) + 1e-8f;
+            const float a2 = (s2 ? pb.z : 1.0f - pb.z) + 1e-8f, a3 = (s3 ? pb.w : 1.0f - pb.w) + 1e-8f;
+            acc_b += fast_log2((a0 * a1) * (a2 * a3));
+            rng[2] = fminf(rng[2], fminf(pb.x, pb.y));
+            rng[2] = fminf(rng[2], fminf(pb.z, pb.w));
+            rng[3] = fmaxf(rng[3], fmaxf(pb.x, pb.y));
+            rng[3] = fmaxf(rng[3], fmaxf(pb.z, pb.w));
+        }
+    } else {
+        float mn = 1.0f;
+        acc_a += lpmf4<false>(pa, xx, mn);
+        acc_b += lpmf4<false>(pb, xx, mn);
+    }
+}
+template <bool BINARY>
+__device__ __forceinline__ void box_dprobs_pair(const float4& xx, const float4& pa, const float4& pb, float ga,
+                                                float gb, float4& oa, float4& ob) {
+    if (BINARY) {
+        const bool s0 = xx.x == 1.f, s1 = xx.y == 1.f, s2 = xx.z == 1.f, s3 = xx.w == 1.f;
+        const float e0 = s0 ? 1e-8f : -1e-8f, e1 = s1 ? 1e-8f : -1e-8f, e2 = s2 ? 1e-8f : -1e-8f,
+                    e3 = s3 ? 1e-8f : -1e-8f;
+        oa.x = ga * fast_rcp((s0 ? pa.x : pa.x - 1.0f) + e0);
+        oa.y = ga * fast_rcp((s1 ? pa.y : pa.y - 1.0f) + e1);
+        oa.z = ga * fast_rcp((s2 ? pa.z : pa.z - 1.0f) + e2);
+        oa.w = ga * fast_rcp((s3 ? pa.w : pa.w - 1.0f) + e3);
+        ob.x = gb * fast_rcp((s0 ? pb.x : pb.x - 1.0f) + e0);
+        ob.y = gb * fast_rcp((s1 ? pb.y : pb.y - 1.0f) + e1);
+        ob.z = gb * fast_rcp((s2 ? pb.z : pb.z - 1.0f) + e2);
+        ob.w = gb * fast_rcp((s3 ? pb.w : pb.w - 1.0f) + e3);
+    } else {
+        oa = dprobs4<false>(pa, xx, ga);
+        ob = dprobs4<false>(pb, xx, gb);
+    }
+}
+
+constexpr int BOX_MAX_ROW_WARPS = 25;  // + stager, two objective warps, producer = 29 warps: 70 registers per thread
+
+template <int EST>
+__global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
+    k_iw_bernoulli_box(const __grid_constant__ CUtensorMap probs_map, float* __restrict__ cost,
+                       float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
+                       float* __restrict__ logpx_out, const float* __restrict__ x,
+                       const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B, int X,
+                       int inner, int nslot, int l2_ahead, float gscale, long long* __restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const BoxLayout L(K, X, inner, nslot);
+    const int Kpad = L.Kpad;
+    const uint32_t slot_bytes = (uint32_t)L.slot_bytes();
+    unsigned char* slots = smem + L.slots_off();
+    float* s_x = reinterpret_cast<float*>(smem + L.x_off());
+    double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
+    double* s_xv = reinterpret_cast<double*>(smem + L.xv_off());
+    float* s_lpx = reinterpret_cast<float*>(smem + L.lpx_off());
+    float* s_other = reinterpret_cast<float*>(smem + L.other_off());
+    float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
+    int* s_bin = reinterpret_cast<int*>(smem + L.bin_off());
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off());
+    uint64_t* empty = full + nslot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles: [0, NW) row warps | NW stager | NW+1, NW+2 objective warps (even / odd columns) | NW+3 producer
+    const int NW = (blockDim.x >> 5) - 4;
+    const int X4 = X >> 2, inner4 = inner >> 2, nbox = X / inner;
+    const uint32_t box_bytes = (uint32_t)K * (uint32_t)inner * 4u;
+    const float LN2 = 0.6931471805599453f;
+    const int64_t ncols = ((int64_t)blockIdx.x < B) ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto mark = [&](int col, int point) {
+        if (trace != nullptr && threadIdx.x == 0 && col < 8)
+            trace[(int64_t)blockIdx.x * 40 + col * 5 + point] = clock64();
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nslot; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], (uint32_t)NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // The stager takes part in every column rendezvous, so one iteration of its loop bounds the column rate:
+    // its global loads are issued in batches (all in flight together), never one latency after the other.
+    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, B, b, lane); };
+    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * X, s_bin + slot, x + b * X, X4, lane); };
+    const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
+    if (is_stager && ncols > 0) {
+        stage_scalars(blockIdx.x, 0);
+        stage_x(blockIdx.x, 0);
+        if (ncols > 1) {
+            stage_scalars((int64_t)blockIdx.x + gridDim.x, 1);
+            stage_x((int64_t)blockIdx.x + gridDim.x, 1);
+        }
+    }
+    __syncthreads();
+
+    if (is_producer) {
+        // ---- producer: box t = (column t / nbox, piece t % nbox) goes to slot t % nslot.  Slots free up only
+        // while phase B runs, so before it blocks the producer asks L2 for the boxes of the next `l2_ahead`
+        // tasks: HBM then streams the next column during phase A as well, and the later copies are L2 hits.
+        if (lane == 0) {
+            int slot = 0, q = 0, pq = 0;
+            uint32_t wait_parity = 1;  // first pass over the ring: nothing to wait for
+            bool first_pass = true;
+            int64_t col = blockIdx.x, pcol = blockIdx.x;
+            const int64_t ntask = ncols * nbox;
+            int64_t pt = 0;  // next task to prefetch into L2
+            for (int64_t t = 0; t < ntask; ++t) {
+                if (l2_ahead > 0 && !first_pass) {
+                    if (pt < t) {  // never behind the real copies
+                        const int64_t skip = t - pt;
+                        pt = t;
+                        pq = q;
+                        pcol = col;
+                        (void)skip;
+                    }
+                    for (; pt < ntask && pt < t + l2_ahead; ++pt) {
+                        tma_prefetch_box_l2(&probs_map, pq * inner, (int)pcol, 0);
+                        if (++pq == nbox) { pq = 0; pcol += gridDim.x; }
+                    }
+                }
+                if (!first_pass) mbar_wait(&empty[slot], wait_parity);
+                mbar_expect_tx(&full[slot], box_bytes);
+                tma_load_box(slots + (size_t)slot * slot_bytes, &probs_map, q * inner, (int)col, 0, &full[slot]);
+                if (++q == nbox) { q = 0; col += gridDim.x; }
+                if (++slot == nslot) {
+                    slot = 0;
+                    if (first_pass) { first_pass = false; wait_parity = 0; }
+                    else wait_parity ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+    // column c rendezvous on named barrier 1 + (c & 1): row warps, the stager and the objective warp of that parity
+    const int sync_threads = (NW + 2) * 32;
+    if (is_stager) {
+        int64_t b = blockIdx.x;
+        for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+            named_bar_sync(1 + (int)(c & 1), sync_threads);
+            // log-weights of column c+1 are posted during its phase A: scalars are staged two columns ahead
+            if (c + 2 < ncols) {
+                stage_scalars(b + 2 * (int64_t)gridDim.x, (int)((c + 2) & 3));
+                stage_x(b + 2 * (int64_t)gridDim.x, (int)((c + 2) % 3));
+            }
+        }
+        return;
+    }
+    if (is_obj) {
+        const int p = warp - NW - 1;
+        int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
+            const int buf = (int)(c & 3);
+            named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
+            colf_objective<EST>(lane, K, B, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+        }
+        return;
+    }
+
+    // ---- row warps: rows ka = warp and kb = warp + NW of every column (kb may not exist) ----------------
+    const int ka = warp, kb = warp + NW;
+    const bool has_b = kb < K;
+    const int kb_eff = has_b ? kb : ka;  // a warp without a second row recomputes row a and drops the result
+    int slot = 0;          // slot of the next box to be read for the first time
+    uint32_t fparity = 0;  // parity of that fill
+    int64_t b = blockIdx.x;
+    for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+        const int par = (int)(c & 3), xs = (int)(c % 3);
+        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * X);
+        const bool binary = s_bin[xs] != 0;
+        const int slot0 = slot;  // first box of this column
+        mark((int)c, 0);
+        // ---- phase A ---------------------------------------------------------------------------------
+        float acc_a = 0.f, acc_b = 0.f;
+        float rng[4] = {0.f, 0.f, 0.f, 0.f};  // min / max of p per row (0 is inside the valid range)
+        for (int q = 0; q < nbox; ++q) {
+            mbar_wait(&full[slot], fparity);
+            const float4* base = reinterpret_cast<const float4*>(slots + (size_t)slot * slot_bytes);
+            const float4* pa4 = base + (size_t)ka * inner4;
+            const float4* pb4 = base + (size_t)kb_eff * inner4;
+            const float4* xq = x4 + q * inner4;
+            if (binary) {
+                for (int v = lane; v < inner4; v += 32)
+                    box_lpmf_pair<true>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
+            } else {
+                for (int v = lane; v < inner4; v += 32)
+                    box_lpmf_pair<false>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
+            }
+            if (!dprobs) {  // forward only: the box is dead after its first read
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            if (++slot == nslot) { slot = 0; fparity ^= 1u; }
+        }
+        if (binary) {
+            // a negative log argument is NaN in the reference: p + eps < 0 or (1 - p) + eps < 0
+            if (rng[0] < -1e-8f || rng[1] > 1.0f) acc_a = __int_as_float(0x7fc00000);
+            if (rng[2] < -1e-8f || rng[3] > 1.0f) acc_b = __int_as_float(0x7fc00000);
+        }
+        acc_a = warp_sum(acc_a);
+        acc_b = warp_sum(acc_b);
+        if (lane == 0) {
+            // log-pmf -> s_lpx; log-weight, same association as k_iw_objective, in double -> s_xv
+            const float la = acc_a * LN2;
+            s_lpx[par * Kpad + ka] = la;
+            s_xv[par * Kpad + ka] = ((double)la - (double)s_lq[par * Kpad + ka]) + (double)s_other[par * Kpad + ka];
+            if (has_b) {
+                const float lb = acc_b * LN2;
+                s_lpx[par * Kpad + kb] = lb;
+                s_xv[par * Kpad + kb] = ((double)lb - (double)s_lq[par * Kpad + kb]) + (double)s_other[par * Kpad + kb];
+            }
+        }
+        mark((int)c, 1);
+        named_bar_sync(1 + (int)(c & 1), sync_threads);
+        mark((int)c, 2);
+        if (dprobs) {
+            // ---- phase B: weights of the two rows, dprobs from the resident boxes, release them -------
+            double m1;
+            float invS;
+            ring_max_sumexp(lane, K, s_xv + par * Kpad, m1, invS);
+            const float ga = -(expf((float)(s_xv[par * Kpad + ka] - m1)) * invS) * gscale;
+            const float gb = -(expf((float)(s_xv[par * Kpad + kb_eff] - m1)) * invS) * gscale;
+            float* da = dprobs + ((int64_t)ka * B + b) * X;
+            float* db = dprobs + ((int64_t)kb_eff * B + b) * X;
+            int bs = slot0;
+            for (int q = 0; q < nbox; ++q) {
+                const float4* base = reinterpret_cast<const float4*>(slots + (size_t)bs * slot_bytes);
+                const float4* pa4 = base + (size_t)ka * inner4;
+                const float4* pb4 = base + (size_t)kb_eff * inner4;
+                const float4* xq = x4 + q * inner4;
+                for (int v = lane; v < inner4; v += 32) {
+                    float4 oa, ob;
+                    if (binary) box_dprobs_pair<true>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
+                    else box_dprobs_pair<false>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
+                    stg_hint(da + q * inner + 4 * v, oa, 0);
+                    if (has_b) stg_hint(db + q * inner + 4 * v, ob, 0);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[bs]);
+                if (++bs == nslot) bs = 0;
+            }
+        }
+        mark((int)c, 3);
+    }
+}
+
 static int pick_warps_ring(int K) {
-    // row warps (<= 29: three more warps stage inputs and compute the objective); equal rows per warp
-    for (int d = 29; d >= 4; --d)
+    // row warps (three more warps stage inputs and compute the objective); equal rows per warp if possible
+    for (int d = ZS_RING_MAX_ROW_WARPS; d >= 4; --d)
         if (K % d == 0) return d;
     return K < 24 ? (K < 1 ? 1 : K) : 24;
 }
@@ -873,13 +1297,15 @@ int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X) {
 static long long* g_trace = nullptr;
 
 static int fused_impl_choice() {
-    // ZS_FUSED_IMPL=smem selects the shared-memory resident-column kernel, =l2 the L2-resident one
-    static int choice = -1;
-    if (choice < 0) {
-        const char* e = getenv("ZS_FUSED_IMPL");
-        choice = (e && e[0] == 's') ? 0 : ((e && e[0] == 'l') ? 1 : 2);  // smem | l2 | ring (default)
+    // ZS_FUSED_IMPL = smem | l2 | ring (default) | box.  Read on every call (tests switch it at run time).
+    const char* e = getenv("ZS_FUSED_IMPL");
+    if (e == nullptr || e[0] == 0) return 2;
+    switch (e[0]) {
+        case 's': return 0;
+        case 'l': return 1;
+        case 'b': return 3;
+        default: return 2;
     }
-    return choice;
 }
 
 static int launch_fused_smem(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
@@ -958,6 +1384,95 @@ static int launch_fused_l2(int estimator, float* cost, float* dprobs, float* dlo
     return ZS_OK;
 }
 
+// Tensor map of probs[K][B][X] with box {inner, 1, K}; the driver's encoder is looked up through the runtime.
+typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_probs_map(CUtensorMap* map, const float* probs, int64_t K, int64_t B, int64_t X, int inner) {
+    static zs_encode_tiled_fn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ZS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+            set_last_error_msg("cuTensorMapEncodeTiled is not available in this driver");
+            return ZS_ERR_UNSUPPORTED;
+        }
+        encode = (zs_encode_tiled_fn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)X, (cuuint64_t)B, (cuuint64_t)K};
+    const cuuint64_t strides[2] = {(cuuint64_t)X * 4, (cuuint64_t)B * (cuuint64_t)X * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)inner, 1, (cuuint32_t)K};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(probs), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error_msg("cuTensorMapEncodeTiled rejected the probs layout");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    return ZS_OK;
+}
+
+// Box geometry: `inner` divides X, is a multiple of 4 and at most 256 floats (the copy engine's box limit);
+// the best choice keeps the most lanes busy (inner/4 float4 per row piece against 32-lane steps).
+static int pick_box_inner(int64_t X) {
+    int best = 0;
+    double best_eff = 0.0;
+    for (int inner = 256; inner >= 32; inner -= 4) {
+        if (X % inner != 0) continue;
+        const int f4 = inner / 4;
+        const double eff = (double)f4 / (32.0 * ((f4 + 31) / 32));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = inner; }
+    }
+    return best_eff >= 0.7 ? best : 0;
+}
+
+static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                            const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
+                            int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+    if (K > 2 * BOX_MAX_ROW_WARPS || B >= ((int64_t)1 << 31) || X * 4 % 16 != 0) {
+        set_last_error_msg("box kernel: at most two rows per warp (K <= 50)");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    const int inner = pick_box_inner(X);
+    if (inner == 0) {
+        set_last_error_msg("box kernel: no box width divides X well");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    int dev = 0, max_optin = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int nbox = (int)(X / inner);
+    int nslot = 2 * nbox;  // at most a whole column of prefetch
+    while (nslot > nbox && BoxLayout((int)K, (int)X, inner, nslot).total() > (size_t)max_optin) --nslot;
+    if (nslot < nbox + 1 || BoxLayout((int)K, (int)X, inner, nslot).total() > (size_t)max_optin) {
+        set_last_error_msg("box kernel: a column plus one box does not fit in shared memory");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    CUtensorMap map;
+    const int rc = make_probs_map(&map, probs, K, B, X, inner);
+    if (rc != ZS_OK) return rc;
+    const int nw = K <= BOX_MAX_ROW_WARPS ? (int)K : (int)((K + 1) / 2);
+    const size_t smem = BoxLayout((int)K, (int)X, inner, nslot).total();
+    const int threads = (nw + 4) * 32;
+    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
+    ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = sm_count();
+    if (grid > B) grid = B;
+    // boxes requested into L2 ahead of the shared-memory copies: measured no gain (0..4) to a loss (>= 7), off
+    static int l2_ahead = -1;
+    if (l2_ahead < 0) {
+        const char* e = getenv("ZS_FUSED_L2_AHEAD");
+        l2_ahead = e ? atoi(e) : 0;
+    }
+    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
+                                                               logq, (int)K, B, (int)X, inner, nslot, l2_ahead,
+                                                               (float)grad_scale, g_trace);
+    ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
+    return ZS_OK;
+}
+
 static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                              const float* probs, const float* x, const float* logp_other, const float* logq,
                              int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
@@ -982,9 +1497,16 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     const int R = nw * D;
     const size_t smem = RingLayout((int)K, (int)X, R).total();
     const int threads = (nw + 3) * 32;
-    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_ring<ZS_EST_SGVB, false> : k_iw_bernoulli_ring<ZS_EST_VIMCO, false>;
-    if (g_trace != nullptr)
-        kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_ring<ZS_EST_SGVB, true> : k_iw_bernoulli_ring<ZS_EST_VIMCO, true>;
+    const bool sgvb = estimator == ZS_EST_SGVB;
+    const int trips = ((int)(X / 4) + 31) / 32;  // 128-bit loads per lane and row
+    auto kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 0> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 0>;
+    switch (trips) {  // exact trip counts of common row lengths are fully unrolled (784 -> 7)
+        case 2: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 2> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 2>; break;
+        case 4: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 4> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 4>; break;
+        case 7: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 7> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 7>; break;
+        case 8: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 8> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 8>; break;
+        default: break;
+    }
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = sm_count();
     if (grid > B) grid = B;
@@ -1013,7 +1535,12 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
     if (fused_impl_choice() == 0)
         return launch_fused_smem(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                                  grad_scale, stream);
-    if (fused_impl_choice() == 2) {
+    if (fused_impl_choice() == 3) {
+        int rc = launch_fused_box(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
+                                  grad_scale, stream);
+        if (rc != ZS_ERR_UNSUPPORTED) return rc;
+    }
+    if (fused_impl_choice() >= 2) {
         int rc = launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B,
                                    X, grad_scale, stream);
         if (rc != ZS_ERR_UNSUPPORTED) return rc;
