@@ -37,13 +37,21 @@ for name, lib in libs:
 stream = torch.cuda.current_stream().cuda_stream
 
 
-def first_call(name, lib):
+def set_env(name, on):
+    # the library reads some knobs once (first call) and ZS_FUSED_IMPL on every call: keep the variant's
+    # environment in place whenever that variant runs
     for k, v in envs[name].items():
-        os.environ[k] = v
+        if on:
+            os.environ[k] = v
+        else:
+            os.environ.pop(k, None)
+
+
+def first_call(name, lib):
+    set_env(name, True)
     run(lib, outs[name], 0)
     torch.cuda.synchronize()
-    for k in envs[name]:
-        del os.environ[k]
+    set_env(name, False)
 
 
 def run(lib, o, est):
@@ -59,6 +67,7 @@ for est, ename in ((0, "sgvb"), (1, "vimco")):
     res = {n: [] for n, _ in libs}
     for rnd in range(6):
         for name, lib in libs:
+            set_env(name, True)
             for _ in range(5):
                 run(lib, outs[name], est)
             torch.cuda.synchronize()
@@ -68,6 +77,7 @@ for est, ename in ((0, "sgvb"), (1, "vimco")):
                 run(lib, outs[name], est)
             e1.record()
             torch.cuda.synchronize()
+            set_env(name, False)
             res[name].append(e0.elapsed_time(e1) / 50 * 1e3)
     for name, _ in libs:
         v = sorted(res[name])

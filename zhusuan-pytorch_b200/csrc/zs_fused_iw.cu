@@ -17,6 +17,7 @@
 //            of the CTA's next column, so next-column loads overlap this column's stores.
 // HBM traffic per particle-sample: 4X read + 4X write (+ [K,B] scalars) instead of 8X + 4X for the
 // two-pass form; the unfused entry points remain as the general fallback.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched at run time, libcuda is not linked
@@ -691,6 +692,17 @@ __device__ __forceinline__ void stage_x_batched(float* s_xrow, int* s_flag, cons
     if (lane == 0) *s_flag = binary ? 1 : 0;
 }
 
+// All CTAs of these persistent kernels otherwise run their read-heavy and write-heavy phases in lock-step
+// (measured with %globaltimer: every SM is in the same phase for the first three columns), which leaves HBM
+// reads idle in one phase and over-subscribed in the other.  CTA i starts (i mod groups) * cycles late.
+__device__ __forceinline__ void stagger_start(int groups, int cycles) {
+    if (groups > 1) {
+        const long long wait = (long long)(blockIdx.x % groups) * cycles;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {}
+    }
+}
+
 struct RingLayout {
     int K, X, R, Kpad;
     __host__ __device__ RingLayout(int K_, int X_, int R_) : K(K_), X(X_), R(R_), Kpad((K_ + 3) & ~3) {}
@@ -798,8 +810,9 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
                         const float* __restrict__ x, const float* __restrict__ logp_other,
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
-                        long long* __restrict__ trace) {
+                        int stagger_groups, int stagger_cycles, long long* __restrict__ trace) {
     extern __shared__ __align__(128) unsigned char smem[];
+    stagger_start(stagger_groups, stagger_cycles);
     const RingLayout L(K, X, R);
     const int Kpad = L.Kpad;
     float* slots = reinterpret_cast<float*>(smem + L.slots_off());
@@ -1059,7 +1072,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                        float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
                        float* __restrict__ logpx_out, const float* __restrict__ x,
                        const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B, int X,
-                       int inner, int nslot, int l2_ahead, float gscale, long long* __restrict__ trace) {
+                       int inner, int nslot, int l2_ahead, float gscale, int stagger_groups, int stagger_cycles,
+                       long long* __restrict__ trace) {
     extern __shared__ __align__(128) unsigned char smem[];
     const BoxLayout L(K, X, inner, nslot);
     const int Kpad = L.Kpad;
@@ -1099,6 +1113,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, B, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
+    stagger_start(stagger_groups, stagger_cycles);
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
@@ -1428,6 +1443,23 @@ static int pick_box_inner(int64_t X) {
     return best_eff >= 0.7 ? best : 0;
 }
 
+struct Stagger {
+    int groups, cycles;
+};
+// Start-time stagger of the persistent CTAs (stagger_start): ZS_FUSED_STAGGER="groups,cycles" overrides.
+static Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
+    const char* e = getenv("ZS_FUSED_STAGGER");
+    if (e != nullptr) {
+        int g = 0, c = 0;
+        if (sscanf(e, "%d%*c%d", &g, &c) == 2) return Stagger{g, c};  // "2,4000" or "2x4000"
+    }
+    if (grid <= 1 || B < 4 * grid) return Stagger{1, 0};  // fewer than four columns per CTA: nothing to desynchronise
+    // measured at K=50, X=784 (column period ~16k cycles): 3-6 groups spanning 4000-5000 cycles are all within
+    // 1% of each other (66.7 us against 70.5 us without); 4 groups of K*X/26 cycles
+    const int64_t cyc = K * X / 26;
+    return Stagger{4, (int)(cyc > 10000 ? 10000 : cyc)};
+}
+
 static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                             const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
                             int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
@@ -1459,7 +1491,13 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = sm_count();
+    {
+        const char* e = getenv("ZS_FUSED_GRID");  // dev knob: fewer CTAs than SMs (per-SM vs chip-level bound)
+        const int cap = e ? atoi(e) : 0;
+        if (cap > 0 && grid > cap) grid = cap;
+    }
     if (grid > B) grid = B;
+    const Stagger stg = pick_stagger(K, X, B, grid);
     // boxes requested into L2 ahead of the shared-memory copies: measured no gain (0..4) to a loss (>= 7), off
     static int l2_ahead = -1;
     if (l2_ahead < 0) {
@@ -1468,7 +1506,7 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     }
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
                                                                logq, (int)K, B, (int)X, inner, nslot, l2_ahead,
-                                                               (float)grad_scale, g_trace);
+                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
     return ZS_OK;
 }
@@ -1509,10 +1547,16 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     }
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = sm_count();
+    {
+        const char* e = getenv("ZS_FUSED_GRID");  // dev knob: fewer CTAs than SMs (per-SM vs chip-level bound)
+        const int cap = e ? atoi(e) : 0;
+        if (cap > 0 && grid > cap) grid = cap;
+    }
     if (grid > B) grid = B;
+    const Stagger stg = pick_stagger(K, X, B, grid);
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
                                                                logp_other, logq, (int)K, B, (int)X, R,
-                                                               (float)grad_scale, g_trace);
+                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
     return ZS_OK;
 }
