@@ -230,20 +230,36 @@ int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g,
                   double lr, double alpha, double beta, int second_order, uint64_t seed, uint64_t offset,
                   zs_stream_t stream);
 
-/* ---- host-buffer convenience call (end-to-end measurement) ----
- * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers
- * (pinned memory recommended).  Batch columns are independent, so the step is pipelined over
- * chunks of 128 columns on three internal streams: the H2D copy of chunk c+1, the fused kernel
- * (or the two-pass kernels) on chunk c and the D2H copy of chunk c-1 overlap, so the call costs
- * about max(H2D, D2H) instead of their sum.  Ordered after prior work on `stream`; returns after
- * everything has landed in the host buffers.  `ws` is a caller-owned device workspace of
- * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).  The only process-wide state
- * of the library is the lazily created streams / events of this call.                  */
+/* ---- host-buffer step (end-to-end measurement) ----
+ * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers for the big
+ * tensors (pinned memory recommended): what a caller whose decoder output lives in host memory
+ * would hand to ImportanceWeightedObjective.forward + backward
+ * (zhusuan/variational/importance_weighted_objective.py:79-132 with the likelihood node of
+ * zhusuan/distributions/bernoulli.py:84-95).  Batch columns are independent, so the step is pipelined
+ * over column chunks (32, 64, 128, ..., 128, 64, 32) on internal streams: the H2D copy of chunk c+1, the
+ * fused kernel (or the two-pass kernels) on chunk c and the D2H copy of chunk c-1 overlap, so the call
+ * costs about max(H2D, D2H) instead of their sum.  `ws` is a caller-owned device workspace of
+ * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).  The only process-wide state of the
+ * library is the lazily created streams / events of these calls (one step in flight at a time).
+ *
+ *   zs_iw_step_host        ordered after prior work on `stream`; returns after everything has landed.
+ *   zs_iw_step_host_begin  enqueues the same step and returns.  With scalars_on_device != 0 the [K,B]
+ *                          arrays logp_other / logq / dlogp / dlogq are DEVICE pointers (row pitch B):
+ *                          they are gathered / scattered per chunk on the device and `stream` is made
+ *                          to wait for the last kernel, so the caller can consume dlogp / dlogq from
+ *                          `stream` with no host round trip.  cost / dprobs are always host buffers.
+ *   zs_iw_step_host_wait   what = 0: the small results (cost; host dlogp / dlogq) have landed and every
+ *                          kernel has run;  what = 1: dprobs has landed too (the step is over).       */
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X);
 int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
                     const float* probs_host, const float* x_host, const float* logp_other_host,
                     const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
                     int64_t ws_bytes, zs_stream_t stream);
+int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, float* dlogp, float* dlogq,
+                          const float* probs_host, const float* x_host, const float* logp_other, const float* logq,
+                          int64_t K, int64_t B, int64_t X, double grad_scale, void* ws, int64_t ws_bytes,
+                          int scalars_on_device, zs_stream_t stream);
+int zs_iw_step_host_wait(int what);
 
 #ifdef __cplusplus
 }

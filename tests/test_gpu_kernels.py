@@ -336,15 +336,21 @@ def _fused_inputs(K, B, X, binary=True, seed=8):
     return probs, x, other, logq
 
 
+def _set_impl(monkeypatch, impl):
+    """ring: rows streamed twice through per-warp bulk-copy rings; box: resident column, tensor bulk copies, fixed
+    geometry where instantiated; boxg: the generic box kernel."""
+    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+
+
 @pytest.mark.parametrize("K,B,X", [(50, 64, 784), (8, 3, 16), (25, 300, 100), (64, 150, 784), (10, 1, 4),
-                                    (16, 149, 128)])
+                                    (16, 149, 128), (50, 301, 256), (33, 200, 512), (20, 160, 1024), (49, 150, 784)])
 @pytest.mark.parametrize("est", ["sgvb", "vimco"])
 @pytest.mark.parametrize("binary", [True, False])
-@pytest.mark.parametrize("impl", ["ring", "box"])
+@pytest.mark.parametrize("impl", ["ring", "box", "boxg"])
 def test_fused_vs_oracle(oracle, monkeypatch, K, B, X, est, binary, impl):
     # ring: rows streamed twice through per-warp slot rings; box: column resident, tensor bulk copies
     # (shapes the box kernel cannot take fall through to the ring inside the library)
-    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+    _set_impl(monkeypatch, impl)
     probs, x, other, logq = _fused_inputs(K, B, X, binary)
     code = be.SGVB if est == "sgvb" else be.VIMCO
     r = be.iw_bernoulli_fused(code, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B, want_logpx=True)
@@ -385,10 +391,10 @@ def test_fused_golden_path(golden):
     close(2 * host(r["dprobs"])[:K], g[p + "dprobs"], 1e-4)
 
 
-@pytest.mark.parametrize("impl", ["ring", "box"])
+@pytest.mark.parametrize("impl", ["ring", "box", "boxg"])
 def test_fused_full_size_properties(oracle, monkeypatch, impl):
     """BASELINE config 2 size (K=50, B=1024, X=784): fused == two-pass kernels == oracle."""
-    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+    _set_impl(monkeypatch, impl)
     K, B, X = 50, 1024, 784
     probs, x, other, logq = _fused_inputs(K, B, X, True, seed=9)
     dp, dx, do, dq = dev(probs), dev(x), dev(other), dev(logq)
@@ -411,13 +417,13 @@ def test_fused_full_size_properties(oracle, monkeypatch, impl):
         close(host(r["logpx"]), o["logpx"], 1e-5)
 
 
-@pytest.mark.parametrize("impl", ["ring", "box"])
+@pytest.mark.parametrize("impl", ["ring", "box", "boxg"])
 @pytest.mark.parametrize("bad,where", [(1.5, (3, 1, 5)), (-0.25, (0, 0, 0)), (np.float32(1.0) + np.float32(2.0 ** -23), (7, 1, 15)),
                                        (-3e-8, (2, 0, 9))])
 def test_fused_invalid_probs_give_nan(monkeypatch, impl, bad, where):
     """bernoulli.py:84-95: log(p + eps) or log(1 - p + eps) of a negative argument is NaN whatever x is;
     the kernels keep that rule exactly (valid iff -1e-8 <= p <= 1) although they evaluate one log per element."""
-    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+    _set_impl(monkeypatch, impl)
     K, B, X = 8, 2, 32
     probs, x, other, logq = _fused_inputs(K, B, X)
     probs[where] = bad
@@ -443,8 +449,9 @@ def test_fused_shape_coverage(oracle):
         close(host(r["dprobs"]), o["dprobs"], 3e-4)
 
 
-def test_iw_step_host(oracle):
-    K, B, X = 50, 96, 784
+@pytest.mark.parametrize("B", [96, 520])
+def test_iw_step_host(oracle, B):
+    K, X = 50, 784
     probs, x, other, logq = _fused_inputs(K, B, X)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     hp, hx, ho, hq = pin(probs), pin(x), pin(other), pin(logq)
@@ -469,6 +476,38 @@ def test_iw_step_host(oracle):
                                  other.astype(np.float64), logq.astype(np.float64))
     close(cost.numpy(), o["cost"], 1e-5)
     close(dprobs.numpy(), o["dprobs"], 1e-4)
+
+
+@pytest.mark.parametrize("B", [1000, 1024, 129, 31])
+def test_iw_step_host_begin_wait_device_scalars(B):
+    """begin/wait form with the [K,B] terms resident on the device, over a multi-chunk schedule
+    (32, 64, 128, ..., 64, 32 columns; rotating buffers): bit-identical to one fused launch."""
+    K, X = 8, 64
+    probs, x, other, logq = _fused_inputs(K, B, X, seed=21)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    hp, hx = pin(probs), pin(x)
+    cost = torch.empty(B).pin_memory()
+    dprobs = torch.empty(K, B, X).pin_memory()
+    ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
+    for code in (be.SGVB, be.VIMCO):
+        do, dq = dev(other), dev(logq)
+        dlp, dlq = torch.zeros(K, B, device=DEV), torch.zeros(K, B, device=DEV)
+        cost.fill_(float("nan"))
+        dprobs.fill_(float("nan"))
+        be.iw_step_host_begin(code, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+        be.iw_step_host_wait(0)
+        r = be.iw_bernoulli_fused(code, dev(probs), dev(x), do, dq, 1.0 / B)
+        assert np.array_equal(cost.numpy(), host(r["cost"]))
+        # dlogp / dlogq are consumable from the caller's stream without a host synchronisation
+        assert torch.equal(dlp, r["dlogp"]) and torch.equal(dlq, r["dlogq"])
+        be.iw_step_host_wait(1)
+        assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
+    # a second begin while the first is still in flight waits for it (shared workspace)
+    be.iw_step_host_begin(be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+    be.iw_step_host_begin(be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+    be.iw_step_host_wait(1)
+    r = be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), do, dq, 1.0 / B)
+    assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 
 
 # ----------------------------------------------------------------------------- fused latent-node kernels

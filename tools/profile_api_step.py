@@ -12,4 +12,10 @@ for _ in range(3): bench.api_step_host(torch, zhusuan, vimco, host)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(5): bench.api_step_host(torch, zhusuan, vimco, host)
 torch.cuda.synchronize(); pr.disable()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28); print(s.getvalue()[:6000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45); print(s.getvalue()[:9000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(25); print(s.getvalue()[:6000])
+import time
+for _ in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    bench.api_step_host(torch, zhusuan, vimco, host)
+    torch.cuda.synchronize(); print("step %.2f ms" % ((time.perf_counter() - t0) * 1e3))

@@ -667,28 +667,67 @@ __device__ __forceinline__ void stage_scalars_batched(float* s_other, float* s_l
         }
     }
 }
+// An x slot holds two arrays of X floats.  Binary x (every element 0 or 1): c = 1 - x and e = (x == 1 ? +1e-8 : -1e-8);
+// the signed log argument t = (p - c) + e then equals p + eps (x = 1) or -((1 - p) + eps) (x = 0) bit for bit, so
+// the row loops need two adds per element instead of compare / subtract / select / add.  Other x: the row itself
+// in the first array.  The flag must be known before anything is written: rows of up to 1024 floats are held in
+// registers meanwhile, longer rows are read twice (the second read is an L1/L2 hit).
+__device__ __forceinline__ void stage_x_write(float4* dst, float4* dst_e, int v, const float4& t, bool binary) {
+    if (binary) {
+        dst[v] = make_float4(1.0f - t.x, 1.0f - t.y, 1.0f - t.z, 1.0f - t.w);
+        dst_e[v] = make_float4(t.x == 1.f ? 1e-8f : -1e-8f, t.y == 1.f ? 1e-8f : -1e-8f, t.z == 1.f ? 1e-8f : -1e-8f,
+                               t.w == 1.f ? 1e-8f : -1e-8f);
+    } else {
+        dst[v] = t;
+    }
+}
+__device__ __forceinline__ bool stage_x_is_binary(const float4& t) {
+    return (t.x == 0.f || t.x == 1.f) && (t.y == 0.f || t.y == 1.f) && (t.z == 0.f || t.z == 1.f) && (t.w == 0.f || t.w == 1.f);
+}
 __device__ __forceinline__ void stage_x_batched(float* s_xrow, int* s_flag, const float* __restrict__ xrow, int X4, int lane) {
     const float4* src = reinterpret_cast<const float4*>(xrow);
     float4* dst = reinterpret_cast<float4*>(s_xrow);
+    float4* dst_e = dst + X4;
     bool binary = true;
-    for (int v0 = lane; v0 < X4; v0 += 32 * 8) {
+    if (X4 <= 32 * 8) {
         float4 t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int v = v0 + 32 * u;
-            t[u] = __ldg(src + (v < X4 ? v : v0));  // always in bounds
+            const int v = lane + 32 * u;
+            t[u] = __ldg(src + (v < X4 ? v : 0));  // always in bounds
+            binary = binary && stage_x_is_binary(t[u]);
         }
+        binary = __all_sync(0xffffffffu, binary);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int v = v0 + 32 * u;
-            if (v < X4) {
-                dst[v] = t[u];
-                binary = binary && (t[u].x == 0.f || t[u].x == 1.f) && (t[u].y == 0.f || t[u].y == 1.f) &&
-                         (t[u].z == 0.f || t[u].z == 1.f) && (t[u].w == 0.f || t[u].w == 1.f);
+            const int v = lane + 32 * u;
+            if (v < X4) stage_x_write(dst, dst_e, v, t[u], binary);
+        }
+    } else {
+        for (int v0 = lane; v0 < X4; v0 += 32 * 8) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int v = v0 + 32 * u;
+                t[u] = __ldg(src + (v < X4 ? v : v0));
+                binary = binary && stage_x_is_binary(t[u]);
+            }
+        }
+        binary = __all_sync(0xffffffffu, binary);
+        for (int v0 = lane; v0 < X4; v0 += 32 * 8) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int v = v0 + 32 * u;
+                t[u] = __ldg(src + (v < X4 ? v : v0));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int v = v0 + 32 * u;
+                if (v < X4) stage_x_write(dst, dst_e, v, t[u], binary);
             }
         }
     }
-    binary = __all_sync(0xffffffffu, binary);
     if (lane == 0) *s_flag = binary ? 1 : 0;
 }
 
@@ -708,7 +747,7 @@ struct RingLayout {
     __host__ __device__ RingLayout(int K_, int X_, int R_) : K(K_), X(X_), R(R_), Kpad((K_ + 3) & ~3) {}
     __host__ __device__ size_t slots_off() const { return 0; }
     __host__ __device__ size_t x_off() const { return (size_t)R * X * 4; }
-    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)3 * X * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)6 * X * 4 + 15) & ~(size_t)15; }
     __host__ __device__ size_t xv_off() const { return xw_off() + (size_t)2 * Kpad * 8; }     // xw: [2][Kpad] double
     __host__ __device__ size_t lpx_off() const { return xv_off() + (size_t)4 * Kpad * 8; }    // xv: [4][Kpad] double
     __host__ __device__ size_t other_off() const { return lpx_off() + (size_t)4 * Kpad * 4; }  // [4][Kpad]
@@ -728,11 +767,15 @@ struct RingLayout {
 //  * backward: d/dp = g / s with the signed argument s = x ? p + eps : (p - 1) - eps == -((1 - p) + eps);
 //  * ITER > 0 is the exact compile-time trip count ceil(X/128) per lane: fully unrolled, constant offsets,
 //    no remainder loop (the remainder loops were a quarter of all instructions executed).
+// x4 points at an x slot (see stage_x_batched).  The ring reads shared memory twice per row and is bound by
+// that (measured: the two-array form costs 8 us per launch here), so its binary path reads c only and selects.
 template <bool BINARY>
-__device__ __forceinline__ void ring_lpmf4(const float4& xx, const float4& p, float& acc, float& pmin, float& pmax) {
+__device__ __forceinline__ void ring_lpmf4(const float4* x4, int X4, int v, const float4& p, float& acc, float& pmin,
+                                           float& pmax) {
     if (BINARY) {
-        const float a0 = (xx.x == 1.f ? p.x : 1.0f - p.x) + 1e-8f, a1 = (xx.y == 1.f ? p.y : 1.0f - p.y) + 1e-8f;
-        const float a2 = (xx.z == 1.f ? p.z : 1.0f - p.z) + 1e-8f, a3 = (xx.w == 1.f ? p.w : 1.0f - p.w) + 1e-8f;
+        const float4 c = lds128(x4 + v);  // c = 1 - x
+        const float a0 = (c.x == 0.f ? p.x : 1.0f - p.x) + 1e-8f, a1 = (c.y == 0.f ? p.y : 1.0f - p.y) + 1e-8f;
+        const float a2 = (c.z == 0.f ? p.z : 1.0f - p.z) + 1e-8f, a3 = (c.w == 0.f ? p.w : 1.0f - p.w) + 1e-8f;
         acc += fast_log2((a0 * a1) * (a2 * a3));
         pmin = fminf(pmin, fminf(p.x, p.y));
         pmin = fminf(pmin, fminf(p.z, p.w));
@@ -740,20 +783,21 @@ __device__ __forceinline__ void ring_lpmf4(const float4& xx, const float4& p, fl
         pmax = fmaxf(pmax, fmaxf(p.z, p.w));
     } else {
         float mn = 1.0f;
-        acc += lpmf4<false>(p, xx, mn);
+        acc += lpmf4<false>(p, lds128(x4 + v), mn);
     }
 }
 template <bool BINARY>
-__device__ __forceinline__ float4 ring_dprobs4(const float4& xx, const float4& p, float g) {
+__device__ __forceinline__ float4 ring_dprobs4(const float4* x4, int X4, int v, const float4& p, float g) {
     if (BINARY) {
+        const float4 c = lds128(x4 + v);
         float4 o;
-        o.x = g * fast_rcp(xx.x == 1.f ? p.x + 1e-8f : (p.x - 1.0f) - 1e-8f);
-        o.y = g * fast_rcp(xx.y == 1.f ? p.y + 1e-8f : (p.y - 1.0f) - 1e-8f);
-        o.z = g * fast_rcp(xx.z == 1.f ? p.z + 1e-8f : (p.z - 1.0f) - 1e-8f);
-        o.w = g * fast_rcp(xx.w == 1.f ? p.w + 1e-8f : (p.w - 1.0f) - 1e-8f);
+        o.x = g * fast_rcp(c.x == 0.f ? p.x + 1e-8f : (p.x - 1.0f) - 1e-8f);
+        o.y = g * fast_rcp(c.y == 0.f ? p.y + 1e-8f : (p.y - 1.0f) - 1e-8f);
+        o.z = g * fast_rcp(c.z == 0.f ? p.z + 1e-8f : (p.z - 1.0f) - 1e-8f);
+        o.w = g * fast_rcp(c.w == 0.f ? p.w + 1e-8f : (p.w - 1.0f) - 1e-8f);
         return o;
     }
-    return dprobs4<false>(p, xx, g);
+    return dprobs4<false>(p, lds128(x4 + v), g);
 }
 
 template <bool BINARY, int ITER>
@@ -764,11 +808,11 @@ __device__ __forceinline__ float smem_row_logpmf(const float4* __restrict__ p4, 
 #pragma unroll
         for (int u = 0; u < ITER; ++u) {
             const int v = lane + 32 * u;
-            if (u + 1 < ITER || v < X4) ring_lpmf4<BINARY>(lds128(x4 + v), lds128(p4 + v), acc, pmin, pmax);
+            if (u + 1 < ITER || v < X4) ring_lpmf4<BINARY>(x4, X4, v, lds128(p4 + v), acc, pmin, pmax);
         }
     } else {
 #pragma unroll 4
-        for (int v = lane; v < X4; v += 32) ring_lpmf4<BINARY>(lds128(x4 + v), lds128(p4 + v), acc, pmin, pmax);
+        for (int v = lane; v < X4; v += 32) ring_lpmf4<BINARY>(x4, X4, v, lds128(p4 + v), acc, pmin, pmax);
     }
     // a negative log argument is NaN in the reference: p + eps < 0 or (1 - p) + eps < 0
     if (BINARY && (pmin < -1e-8f || pmax > 1.0f)) acc = __int_as_float(0x7fc00000);
@@ -781,11 +825,11 @@ __device__ __forceinline__ void smem_row_dprobs(float* __restrict__ drow, const 
 #pragma unroll
         for (int u = 0; u < ITER; ++u) {
             const int v = lane + 32 * u;
-            if (u + 1 < ITER || v < X4) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(lds128(x4 + v), lds128(p4 + v), g), 0);
+            if (u + 1 < ITER || v < X4) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(x4, X4, v, lds128(p4 + v), g), 0);
         }
     } else {
 #pragma unroll 4
-        for (int v = lane; v < X4; v += 32) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(lds128(x4 + v), lds128(p4 + v), g), 0);
+        for (int v = lane; v < X4; v += 32) stg_hint(drow + 4 * v, ring_dprobs4<BINARY>(x4, X4, v, lds128(p4 + v), g), 0);
     }
 }
 
@@ -801,18 +845,23 @@ __device__ __forceinline__ void ring_max_sumexp(int lane, int K, const double* s
     invS = fast_rcp(S) * (2.0f - S * fast_rcp(S));
 }
 
+#ifndef ZS_RING_EARLY_DEFAULT
+#define ZS_RING_EARLY_DEFAULT 0
+#endif
 #ifndef ZS_RING_MAX_ROW_WARPS
 #define ZS_RING_MAX_ROW_WARPS 25  // + 3 service warps = 896 threads: 72 registers per thread
 #endif
+// (A variant that read the second pass with plain L2 loads instead of a second bulk copy was measured at
+// 77-88 us against 67-74 us: the exposed L2 latency costs more than the copy engine saves; removed.)
 template <int EST, int ITER>
 __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
     k_iw_bernoulli_ring(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
                         const float* __restrict__ x, const float* __restrict__ logp_other,
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
-                        int stagger_groups, int stagger_cycles, long long* __restrict__ trace) {
+                        int stagger_groups, int stagger_cycles, long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
-    stagger_start(stagger_groups, stagger_cycles);
+    stagger_start(stagger_groups & 0xff, stagger_cycles);
     const RingLayout L(K, X, R);
     const int Kpad = L.Kpad;
     float* slots = reinterpret_cast<float*>(smem + L.slots_off());
@@ -832,7 +881,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
     const int X4 = X >> 2;
     const uint32_t row_bytes = (uint32_t)X * 4u;
     const float LN2 = 0.6931471805599453f;
-    const int phases = dprobs ? 2 : 1;
+    const int phases = dprobs ? 2 : 1;  // row tasks per column that travel through the ring
     const int64_t ncols = ((int64_t)blockIdx.x < B) ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto mark = [&](int col, int point) {
         if (trace != nullptr && threadIdx.x == 0 && col < 8)
@@ -843,12 +892,38 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
         for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    // ---- row-warp prefetch cursor.  Warp w owns the D slots [w*D, w*D+D) and its row tasks, in order
+    //   A(c, w), A(c, w+NW), ..., B(c, w), B(c, w+NW), ..., A(c+1, w), ...
+    // (A = first read, HBM; B = second read of the same row, an L2 hit;).
+    // The first D copies are issued BEFORE the stager's first (dependent, cold) global loads so the
+    // HBM pipe fills while x and the [K] scalars are staged.
+    const int D = R / NW;
+    const int my_rows = warp < NW ? (K - warp + NW - 1) / NW : 0;
+    int64_t pf_c = 0, pf_b = blockIdx.x;
+    int pf_ph = 0, pf_j = 0, pf_pos = 0;
+    auto issue_next = [&]() {
+        if (pf_c >= ncols || my_rows == 0) return;
+        const int k = warp + pf_j * NW;
+        const int s = warp * D + pf_pos;
+        mbar_expect_tx(&full[s], row_bytes);
+        bulk_load(slots + (size_t)s * X, probs + ((int64_t)k * B + pf_b) * X, row_bytes, &full[s]);
+        if (++pf_pos == D) pf_pos = 0;
+        if (++pf_j == my_rows) {
+            pf_j = 0;
+            if (++pf_ph == phases) { pf_ph = 0; ++pf_c; pf_b += gridDim.x; }
+        }
+    };
+    const bool early_issue = (stagger_groups & 0x100) != 0;  // dev knob folded into the launch parameter
+    stagger_groups &= 0xff;
+    if (early_issue && warp < NW && lane == 0)
+        for (int i = 0; i < D; ++i) issue_next();
     // Per-column scalars and log-pmf live in 4 buffers (column & 3), the x row in 3 (column % 3):
     // an objective warp may work on column c until the barrier of column c+2.
     // The stager takes part in every column rendezvous, so one iteration of its loop bounds the column rate:
     // its global loads are issued in batches (all in flight together), never one latency after the other.
-    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, B, b, lane); };
-    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * X, s_bin + slot, x + b * X, X4, lane); };
+    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
+    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
@@ -858,6 +933,8 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
         }
     }
     __syncthreads();
+    if (!early_issue && warp < NW && lane == 0)
+        for (int i = 0; i < D; ++i) issue_next();
 
     // column c rendezvous on named barrier 1 + (c & 1): row warps, the stager and the objective warp
     // of that parity
@@ -882,44 +959,22 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            colf_objective<EST>(lane, K, B, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
         }
         return;
     }
 
-    // ---- row warps.  Warp w owns the D slots [w*D, w*D+D) and its row tasks, in order
-    //   A(c, w), A(c, w+NW), ..., B(c, w), B(c, w+NW), ..., A(c+1, w), ...
-    // (A = first read, HBM; B = second read of the same row, an L2 hit).  After consuming a slot the
-    // warp itself re-arms the slot's mbarrier and issues the bulk copy of the task D ahead, so up to D
-    // rows per warp are in flight in shared memory and A(c+1) loads overlap B(c) stores.  A slot is
-    // filled and waited on by one warp only, so its mbarrier phases are always observed in sequence.
-    const int D = R / NW;
-    const int my_rows = (K - warp + NW - 1) / NW;
-    // prefetch cursor (lane 0 only uses it)
-    int64_t pf_c = 0, pf_b = blockIdx.x;
-    int pf_ph = 0, pf_j = 0, pf_pos = 0;
-    auto issue_next = [&]() {
-        if (pf_c >= ncols || my_rows == 0) return;
-        const int k = warp + pf_j * NW;
-        const int s = warp * D + pf_pos;
-        mbar_expect_tx(&full[s], row_bytes);
-        bulk_load(slots + (size_t)s * X, probs + ((int64_t)k * B + pf_b) * X, row_bytes, &full[s]);
-        if (++pf_pos == D) pf_pos = 0;
-        if (++pf_j == my_rows) {
-            pf_j = 0;
-            if (++pf_ph == phases) { pf_ph = 0; ++pf_c; pf_b += gridDim.x; }
-        }
-    };
-    if (lane == 0)
-        for (int i = 0; i < D; ++i) issue_next();
-
+    // ---- row warps.  After consuming a slot the warp itself re-arms the slot's mbarrier and issues the
+    // bulk copy of the task D ahead, so up to D rows per warp are in flight in shared memory and the loads
+    // of the next column overlap the stores of this one.  A slot is filled and waited on by one warp only,
+    // so its mbarrier phases are always observed in sequence.
     int ring_pos = 0;         // consumer cursor in the warp's mini-ring
     uint32_t ring_phase = 0;  // parity of the fill being waited for
     int64_t b = blockIdx.x;
     for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
         const int par = (int)(c & 3), xs = (int)(c % 3);
-        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * X);
+        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * 2 * X);
         const bool binary = s_bin[xs] != 0;
         mark((int)c, 0);
         // ---- phase A: log-pmf of the owned rows as they land ---------------------------------------
@@ -948,11 +1003,11 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
             ring_max_sumexp(lane, K, s_xv + par * Kpad, m1, invS);
             for (int k = warp; k < K; k += NW) {
                 const float g = -(expf((float)(s_xv[par * Kpad + k] - m1)) * invS) * gscale;
+                float* drow = dprobs + ((int64_t)k * B + b) * X;
                 const int s = warp * D + ring_pos;
                 mbar_wait(&full[s], ring_phase);
                 if (++ring_pos == D) { ring_pos = 0; ring_phase ^= 1u; }
                 const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)s * X);
-                float* drow = dprobs + ((int64_t)k * B + b) * X;
                 if (binary) smem_row_dprobs<true, ITER>(drow, p4, x4, X4, lane, g);
                 else smem_row_dprobs<false, ITER>(drow, p4, x4, X4, lane, g);
                 __syncwarp();
@@ -1003,7 +1058,7 @@ struct BoxLayout {
     __host__ __device__ size_t slot_bytes() const { return ((size_t)K * inner * 4 + 127) & ~(size_t)127; }
     __host__ __device__ size_t slots_off() const { return 0; }
     __host__ __device__ size_t x_off() const { return (size_t)nslot * slot_bytes(); }
-    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)3 * X * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ size_t xw_off() const { return (x_off() + (size_t)6 * X * 4 + 15) & ~(size_t)15; }
     __host__ __device__ size_t xv_off() const { return xw_off() + (size_t)2 * Kpad * 8; }
     __host__ __device__ size_t lpx_off() const { return xv_off() + (size_t)4 * Kpad * 8; }
     __host__ __device__ size_t other_off() const { return lpx_off() + (size_t)4 * Kpad * 4; }
@@ -1013,52 +1068,50 @@ struct BoxLayout {
     __host__ __device__ size_t total() const { return bar_off() + (size_t)2 * nslot * 8; }
 };
 
-// two rows of one box against the same x piece: one x load and one compare per element serve both rows
+// two rows of one box against the same x piece: one load of the c / e pieces serves both rows
 template <bool BINARY>
-__device__ __forceinline__ void box_lpmf_pair(const float4& xx, const float4& pa, const float4& pb, float& acc_a,
-                                              float& acc_b, float (&rng)[4]) {
+__device__ __forceinline__ void box_lpmf_pair(const float4* xq, int X4, int v, const float4& pa, const float4& pb,
+                                              float& acc_a, float& acc_b, float (&rng)[4]) {
     if (BINARY) {
-        const bool s0 = xx.x == 1.f, s1 = xx.y == 1.f, s2 = xx.z == 1.f, s3 = xx.w == 1.f;
+        const float4 c = lds128(xq + v), e = lds128(xq + X4 + v);
         {
-            const float a0 = (s0 ? pa.x : 1.0f - pa.x) + 1e-8f, a1 = (s1 ? pa.y : 1.0f - pa.y) + 1e-8f;
-            const float a2 = (s2 ? pa.z : 1.0f - pa.z) + 1e-8f, a3 = (s3 ? pa.w : 1.0f - pa.w) + 1e-8f;
-            acc_a += fast_log2((a0 * a1) * (a2 * a3));
+            const float t0 = (pa.x - c.x) + e.x, t1 = (pa.y - c.y) + e.y, t2 = (pa.z - c.z) + e.z, t3 = (pa.w - c.w) + e.w;
+            acc_a += fast_log2(fabsf((t0 * t1) * (t2 * t3)));
             rng[0] = fminf(rng[0], fminf(pa.x, pa.y));
             rng[0] = fminf(rng[0], fminf(pa.z, pa.w));
             rng[1] = fmaxf(rng[1], fmaxf(pa.x, pa.y));
             rng[1] = fmaxf(rng[1], fmaxf(pa.z, pa.w));
         }
         {
-            const float a0 = (s0 ? pb.x : 1.0f - pb.x) + 1e-8f, a1 = (s1 ? pb.y : 1.0f - pb.y) + 1e-8f;
-            const float a2 = (s2 ? pb.z : 1.0f - pb.z) + 1e-8f, a3 = (s3 ? pb.w : 1.0f - pb.w) + 1e-8f;
-            acc_b += fast_log2((a0 * a1) * (a2 * a3));
+            const float t0 = (pb.x - c.x) + e.x, t1 = (pb.y - c.y) + e.y, t2 = (pb.z - c.z) + e.z, t3 = (pb.w - c.w) + e.w;
+            acc_b += fast_log2(fabsf((t0 * t1) * (t2 * t3)));
             rng[2] = fminf(rng[2], fminf(pb.x, pb.y));
             rng[2] = fminf(rng[2], fminf(pb.z, pb.w));
             rng[3] = fmaxf(rng[3], fmaxf(pb.x, pb.y));
             rng[3] = fmaxf(rng[3], fmaxf(pb.z, pb.w));
         }
     } else {
+        const float4 xx = lds128(xq + v);
         float mn = 1.0f;
         acc_a += lpmf4<false>(pa, xx, mn);
         acc_b += lpmf4<false>(pb, xx, mn);
     }
 }
 template <bool BINARY>
-__device__ __forceinline__ void box_dprobs_pair(const float4& xx, const float4& pa, const float4& pb, float ga,
-                                                float gb, float4& oa, float4& ob) {
+__device__ __forceinline__ void box_dprobs_pair(const float4* xq, int X4, int v, const float4& pa, const float4& pb,
+                                                float ga, float gb, float4& oa, float4& ob) {
     if (BINARY) {
-        const bool s0 = xx.x == 1.f, s1 = xx.y == 1.f, s2 = xx.z == 1.f, s3 = xx.w == 1.f;
-        const float e0 = s0 ? 1e-8f : -1e-8f, e1 = s1 ? 1e-8f : -1e-8f, e2 = s2 ? 1e-8f : -1e-8f,
-                    e3 = s3 ? 1e-8f : -1e-8f;
-        oa.x = ga * fast_rcp((s0 ? pa.x : pa.x - 1.0f) + e0);
-        oa.y = ga * fast_rcp((s1 ? pa.y : pa.y - 1.0f) + e1);
-        oa.z = ga * fast_rcp((s2 ? pa.z : pa.z - 1.0f) + e2);
-        oa.w = ga * fast_rcp((s3 ? pa.w : pa.w - 1.0f) + e3);
-        ob.x = gb * fast_rcp((s0 ? pb.x : pb.x - 1.0f) + e0);
-        ob.y = gb * fast_rcp((s1 ? pb.y : pb.y - 1.0f) + e1);
-        ob.z = gb * fast_rcp((s2 ? pb.z : pb.z - 1.0f) + e2);
-        ob.w = gb * fast_rcp((s3 ? pb.w : pb.w - 1.0f) + e3);
+        const float4 c = lds128(xq + v), e = lds128(xq + X4 + v);
+        oa.x = ga * fast_rcp((pa.x - c.x) + e.x);
+        oa.y = ga * fast_rcp((pa.y - c.y) + e.y);
+        oa.z = ga * fast_rcp((pa.z - c.z) + e.z);
+        oa.w = ga * fast_rcp((pa.w - c.w) + e.w);
+        ob.x = gb * fast_rcp((pb.x - c.x) + e.x);
+        ob.y = gb * fast_rcp((pb.y - c.y) + e.y);
+        ob.z = gb * fast_rcp((pb.z - c.z) + e.z);
+        ob.w = gb * fast_rcp((pb.w - c.w) + e.w);
     } else {
+        const float4 xx = lds128(xq + v);
         oa = dprobs4<false>(pa, xx, ga);
         ob = dprobs4<false>(pb, xx, gb);
     }
@@ -1073,7 +1126,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                        float* __restrict__ logpx_out, const float* __restrict__ x,
                        const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B, int X,
                        int inner, int nslot, int l2_ahead, float gscale, int stagger_groups, int stagger_cycles,
-                       long long* __restrict__ trace) {
+                       long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
     const BoxLayout L(K, X, inner, nslot);
     const int Kpad = L.Kpad;
@@ -1110,8 +1163,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     }
     // The stager takes part in every column rendezvous, so one iteration of its loop bounds the column rate:
     // its global loads are issued in batches (all in flight together), never one latency after the other.
-    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, B, b, lane); };
-    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * X, s_bin + slot, x + b * X, X4, lane); };
+    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
+    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
     stagger_start(stagger_groups, stagger_cycles);
     if (is_stager && ncols > 0) {
@@ -1182,7 +1235,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            colf_objective<EST>(lane, K, B, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
         }
         return;
@@ -1197,7 +1250,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     int64_t b = blockIdx.x;
     for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
         const int par = (int)(c & 3), xs = (int)(c % 3);
-        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * X);
+        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)xs * 2 * X);
         const bool binary = s_bin[xs] != 0;
         const int slot0 = slot;  // first box of this column
         mark((int)c, 0);
@@ -1212,10 +1265,10 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             const float4* xq = x4 + q * inner4;
             if (binary) {
                 for (int v = lane; v < inner4; v += 32)
-                    box_lpmf_pair<true>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
+                    box_lpmf_pair<true>(xq, X4, v, lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
             } else {
                 for (int v = lane; v < inner4; v += 32)
-                    box_lpmf_pair<false>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
+                    box_lpmf_pair<false>(xq, X4, v, lds128(pa4 + v), lds128(pb4 + v), acc_a, acc_b, rng);
             }
             if (!dprobs) {  // forward only: the box is dead after its first read
                 __syncwarp();
@@ -1261,8 +1314,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                 const float4* xq = x4 + q * inner4;
                 for (int v = lane; v < inner4; v += 32) {
                     float4 oa, ob;
-                    if (binary) box_dprobs_pair<true>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
-                    else box_dprobs_pair<false>(lds128(xq + v), lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
+                    if (binary) box_dprobs_pair<true>(xq, X4, v, lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
+                    else box_dprobs_pair<false>(xq, X4, v, lds128(pa4 + v), lds128(pb4 + v), ga, gb, oa, ob);
                     stg_hint(da + q * inner + 4 * v, oa, 0);
                     if (has_b) stg_hint(db + q * inner + 4 * v, ob, 0);
                 }
@@ -1272,6 +1325,290 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             }
         }
         mark((int)c, 3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-geometry box kernel.  ncu on the generic box kernel (profiles/r2_box_kernel_ncu.md): 45.6 k warp
+// instructions per column and SM at 65 % issue utilisation -- the kernel was ISSUE-bound, and 40 % of the
+// row warps' instructions were address arithmetic and loop control around run-time box geometry.  Here the
+// box width (INNER4 float4 per row piece) and the boxes per column (NBOX) are template parameters: the box
+// loops are fully unrolled, every shared-memory access is a 32-bit base register plus an immediate, every
+// global store a 64-bit row pointer plus an immediate.  Roles, barriers and numerics are those of
+// k_iw_bernoulli_box; the prologue stages only column 0 before the first rendezvous.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128_u32(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "ZS_WAITU:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra ZS_DONEU;\n"
+        "bra ZS_WAITU;\n"
+        "ZS_DONEU:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct BoxCursor {
+    uint32_t slot, addr, parity;  // ring position, shared address of that slot, parity of the fill waited for
+};
+
+template <bool BINARY, int INNER4, int NBOX>
+__device__ __forceinline__ void boxf_phase_a(BoxCursor& cur, uint32_t slots_u, uint32_t slot_bytes, uint32_t nslot,
+                                             uint32_t full_u, uint32_t empty_u, uint32_t row_a, uint32_t row_b,
+                                             uint32_t x_u, int lane, bool release, float& acc_a, float& acc_b,
+                                             float (&rng)[4]) {
+    constexpr int VIT = (INNER4 + 31) / 32, XB = INNER4 * NBOX * 16;  // XB: bytes of one x array
+#pragma unroll
+    for (int q = 0; q < NBOX; ++q) {
+        mbar_wait_u32(full_u + cur.slot * 8, cur.parity);
+#pragma unroll
+        for (int i = 0; i < VIT; ++i) {
+            if ((i + 1) * 32 <= INNER4 || lane + 32 * i < INNER4) {
+                const uint32_t o = (uint32_t)(i * 512);
+                const float4 pa = lds128_u32(cur.addr + row_a + o), pb = lds128_u32(cur.addr + row_b + o);
+                const uint32_t xo = x_u + (uint32_t)(q * INNER4 * 16) + o;
+                if (BINARY) {
+                    const float4 c = lds128_u32(xo), e = lds128_u32(xo + XB);
+                    {
+                        const float t0 = (pa.x - c.x) + e.x, t1 = (pa.y - c.y) + e.y, t2 = (pa.z - c.z) + e.z,
+                                    t3 = (pa.w - c.w) + e.w;
+                        acc_a += fast_log2(fabsf((t0 * t1) * (t2 * t3)));
+                        rng[0] = fminf(rng[0], fminf(pa.x, pa.y));
+                        rng[0] = fminf(rng[0], fminf(pa.z, pa.w));
+                        rng[1] = fmaxf(rng[1], fmaxf(pa.x, pa.y));
+                        rng[1] = fmaxf(rng[1], fmaxf(pa.z, pa.w));
+                    }
+                    {
+                        const float t0 = (pb.x - c.x) + e.x, t1 = (pb.y - c.y) + e.y, t2 = (pb.z - c.z) + e.z,
+                                    t3 = (pb.w - c.w) + e.w;
+                        acc_b += fast_log2(fabsf((t0 * t1) * (t2 * t3)));
+                        rng[2] = fminf(rng[2], fminf(pb.x, pb.y));
+                        rng[2] = fminf(rng[2], fminf(pb.z, pb.w));
+                        rng[3] = fmaxf(rng[3], fmaxf(pb.x, pb.y));
+                        rng[3] = fmaxf(rng[3], fmaxf(pb.z, pb.w));
+                    }
+                } else {
+                    const float4 xx = lds128_u32(xo);
+                    float mn = 1.0f;
+                    acc_a += lpmf4<false>(pa, xx, mn);
+                    acc_b += lpmf4<false>(pb, xx, mn);
+                }
+            }
+        }
+        if (release) {  // forward only: the box is dead after its first read
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(empty_u + cur.slot * 8);
+        }
+        cur.addr += slot_bytes;
+        if (++cur.slot == nslot) { cur.slot = 0; cur.addr = slots_u; cur.parity ^= 1u; }
+    }
+}
+
+template <bool BINARY, int INNER4, int NBOX>
+__device__ __forceinline__ void boxf_phase_b(uint32_t bs, uint32_t bs_addr, uint32_t slots_u, uint32_t slot_bytes,
+                                             uint32_t nslot, uint32_t empty_u, uint32_t row_a, uint32_t row_b,
+                                             uint32_t x_u, int lane, float ga, float gb, float* __restrict__ da,
+                                             float* __restrict__ db, bool has_b) {
+    constexpr int VIT = (INNER4 + 31) / 32, XB = INNER4 * NBOX * 16;
+#pragma unroll
+    for (int q = 0; q < NBOX; ++q) {
+#pragma unroll
+        for (int i = 0; i < VIT; ++i) {
+            if ((i + 1) * 32 <= INNER4 || lane + 32 * i < INNER4) {
+                const uint32_t o = (uint32_t)(i * 512);
+                const float4 pa = lds128_u32(bs_addr + row_a + o), pb = lds128_u32(bs_addr + row_b + o);
+                const uint32_t xo = x_u + (uint32_t)(q * INNER4 * 16) + o;
+                float4 oa, ob;
+                if (BINARY) {
+                    const float4 c = lds128_u32(xo), e = lds128_u32(xo + XB);
+                    oa.x = ga * fast_rcp((pa.x - c.x) + e.x);
+                    oa.y = ga * fast_rcp((pa.y - c.y) + e.y);
+                    oa.z = ga * fast_rcp((pa.z - c.z) + e.z);
+                    oa.w = ga * fast_rcp((pa.w - c.w) + e.w);
+                    ob.x = gb * fast_rcp((pb.x - c.x) + e.x);
+                    ob.y = gb * fast_rcp((pb.y - c.y) + e.y);
+                    ob.z = gb * fast_rcp((pb.z - c.z) + e.z);
+                    ob.w = gb * fast_rcp((pb.w - c.w) + e.w);
+                } else {
+                    const float4 xx = lds128_u32(xo);
+                    oa = dprobs4<false>(pa, xx, ga);
+                    ob = dprobs4<false>(pb, xx, gb);
+                }
+                stg_hint(da + q * INNER4 * 4 + i * 128, oa, 0);
+                if (has_b) stg_hint(db + q * INNER4 * 4 + i * 128, ob, 0);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(empty_u + bs * 8);
+        bs_addr += slot_bytes;
+        if (++bs == nslot) { bs = 0; bs_addr = slots_u; }
+    }
+}
+
+template <int EST, int INNER4, int NBOX>
+__global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
+    k_iw_bernoulli_boxf(const __grid_constant__ CUtensorMap probs_map, float* __restrict__ cost,
+                        float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
+                        float* __restrict__ logpx_out, const float* __restrict__ x,
+                        const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B,
+                        int nslot, float gscale, int stagger_groups, int stagger_cycles, int64_t ldkb) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int INNER = INNER4 * 4, X = INNER * NBOX, X4 = X / 4;
+    const BoxLayout L(K, X, INNER, nslot);
+    const int Kpad = L.Kpad;
+    const uint32_t slot_bytes = (uint32_t)L.slot_bytes();
+    unsigned char* slots = smem + L.slots_off();
+    float* s_x = reinterpret_cast<float*>(smem + L.x_off());
+    double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
+    double* s_xv = reinterpret_cast<double*>(smem + L.xv_off());
+    float* s_lpx = reinterpret_cast<float*>(smem + L.lpx_off());
+    float* s_other = reinterpret_cast<float*>(smem + L.other_off());
+    float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
+    int* s_bin = reinterpret_cast<int*>(smem + L.bin_off());
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off());
+    uint64_t* empty = full + nslot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles: [0, NW) row warps | NW stager | NW+1, NW+2 objective warps (even / odd columns) | NW+3 producer
+    const int NW = (blockDim.x >> 5) - 4;
+    const uint32_t box_bytes = (uint32_t)K * (uint32_t)INNER * 4u;
+    const float LN2 = 0.6931471805599453f;
+    const int64_t ncols = ((int64_t)blockIdx.x < B) ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nslot; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], (uint32_t)NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
+    auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
+    const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
+    stagger_start(stagger_groups, stagger_cycles);
+    if (is_stager && ncols > 0) {  // column 0 only: column 1 is staged while column 0 is being read
+        stage_scalars(blockIdx.x, 0);
+        stage_x(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    if (is_producer) {
+        // box t = (column t / NBOX, piece t % NBOX) goes to slot t % nslot
+        if (lane == 0) {
+            int slot = 0, q = 0;
+            uint32_t wait_parity = 1;
+            bool first_pass = true;
+            int64_t col = blockIdx.x;
+            const int64_t ntask = ncols * NBOX;
+            for (int64_t t = 0; t < ntask; ++t) {
+                if (!first_pass) mbar_wait(&empty[slot], wait_parity);
+                mbar_expect_tx(&full[slot], box_bytes);
+                tma_load_box(slots + (size_t)slot * slot_bytes, &probs_map, q * INNER, (int)col, 0, &full[slot]);
+                if (++q == NBOX) { q = 0; col += gridDim.x; }
+                if (++slot == nslot) {
+                    slot = 0;
+                    if (first_pass) { first_pass = false; wait_parity = 0; }
+                    else wait_parity ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+    const int sync_threads = (NW + 2) * 32;
+    if (is_stager) {
+        int64_t b = blockIdx.x;
+        if (ncols > 1) {
+            stage_scalars(b + gridDim.x, 1);
+            stage_x(b + gridDim.x, 1);
+        }
+        for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+            named_bar_sync(1 + (int)(c & 1), sync_threads);
+            if (c + 2 < ncols) {
+                stage_scalars(b + 2 * (int64_t)gridDim.x, (int)((c + 2) & 3));
+                stage_x(b + 2 * (int64_t)gridDim.x, (int)((c + 2) % 3));
+            }
+        }
+        return;
+    }
+    if (is_obj) {
+        const int p = warp - NW - 1;
+        int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
+            const int buf = (int)(c & 3);
+            named_bar_sync(1 + p, sync_threads);
+            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+        }
+        return;
+    }
+
+    // ---- row warps: rows ka = warp and kb = warp + NW of every column (kb may not exist) ----------------
+    const int ka = warp, kb = warp + NW;
+    const bool has_b = kb < K;
+    const int kb_eff = has_b ? kb : ka;
+    const uint32_t slots_u = smem_u32(slots), full_u = smem_u32(full), empty_u = smem_u32(empty);
+    const uint32_t row_a = (uint32_t)ka * (INNER * 4) + (uint32_t)lane * 16, row_b = (uint32_t)kb_eff * (INNER * 4) + (uint32_t)lane * 16;
+    const uint32_t sx_u = smem_u32(s_x) + (uint32_t)lane * 16;
+    BoxCursor cur{0u, slots_u, 0u};
+    int64_t b = blockIdx.x;
+    for (int64_t c = 0; c < ncols; ++c, b += gridDim.x) {
+        const int par = (int)(c & 3), xs = (int)(c % 3);
+        const uint32_t x_u = sx_u + (uint32_t)xs * (2 * X * 4);
+        // the stager publishes column 1's x only after the first rendezvous of column 0 for c >= 2; column 1's
+        // staging is ordered by the rendezvous of column 0 as well (the stager arrives after staging it)
+        const bool binary = s_bin[xs] != 0;
+        const uint32_t slot0 = cur.slot, addr0 = cur.addr;
+        float acc_a = 0.f, acc_b = 0.f;
+        float rng[4] = {0.f, 0.f, 0.f, 0.f};
+        if (binary)
+            boxf_phase_a<true, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
+                                             lane, dprobs == nullptr, acc_a, acc_b, rng);
+        else
+            boxf_phase_a<false, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
+                                              lane, dprobs == nullptr, acc_a, acc_b, rng);
+        if (binary) {
+            if (rng[0] < -1e-8f || rng[1] > 1.0f) acc_a = __int_as_float(0x7fc00000);
+            if (rng[2] < -1e-8f || rng[3] > 1.0f) acc_b = __int_as_float(0x7fc00000);
+        }
+        acc_a = warp_sum(acc_a);
+        acc_b = warp_sum(acc_b);
+        if (lane == 0) {
+            const float la = acc_a * LN2;
+            s_lpx[par * Kpad + ka] = la;
+            s_xv[par * Kpad + ka] = ((double)la - (double)s_lq[par * Kpad + ka]) + (double)s_other[par * Kpad + ka];
+            if (has_b) {
+                const float lb = acc_b * LN2;
+                s_lpx[par * Kpad + kb] = lb;
+                s_xv[par * Kpad + kb] = ((double)lb - (double)s_lq[par * Kpad + kb]) + (double)s_other[par * Kpad + kb];
+            }
+        }
+        named_bar_sync(1 + (int)(c & 1), sync_threads);
+        if (dprobs) {
+            double m1;
+            float invS;
+            ring_max_sumexp(lane, K, s_xv + par * Kpad, m1, invS);
+            const float ga = -(expf((float)(s_xv[par * Kpad + ka] - m1)) * invS) * gscale;
+            const float gb = -(expf((float)(s_xv[par * Kpad + kb_eff] - m1)) * invS) * gscale;
+            float* da = dprobs + ((int64_t)ka * B + b) * X + lane * 4;
+            float* db = dprobs + ((int64_t)kb_eff * B + b) * X + lane * 4;
+            if (binary)
+                boxf_phase_b<true, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
+                                                 lane, ga, gb, da, db, has_b);
+            else
+                boxf_phase_b<false, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
+                                                  lane, ga, gb, da, db, has_b);
+        }
     }
 }
 
@@ -1311,14 +1648,18 @@ int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X) {
 
 static long long* g_trace = nullptr;
 
+#ifndef ZS_FUSED_DEFAULT_IMPL
+#define ZS_FUSED_DEFAULT_IMPL 3
+#endif
 static int fused_impl_choice() {
-    // ZS_FUSED_IMPL = smem | l2 | ring (default) | box.  Read on every call (tests switch it at run time).
+    // ZS_FUSED_IMPL = smem | l2 | ring | box (default: fixed-geometry box kernels where instantiated, else the
+    // generic box kernel, else the ring) | boxg (generic box kernel only).  Read on every call (tests switch it).
     const char* e = getenv("ZS_FUSED_IMPL");
-    if (e == nullptr || e[0] == 0) return 2;
+    if (e == nullptr || e[0] == 0) return ZS_FUSED_DEFAULT_IMPL;
     switch (e[0]) {
         case 's': return 0;
         case 'l': return 1;
-        case 'b': return 3;
+        case 'b': return (e[1] == 'o' && e[2] == 'x' && e[3] == 'g') ? 4 : 3;
         default: return 2;
     }
 }
@@ -1462,7 +1803,8 @@ static Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
 
 static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                             const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                            int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+                            int64_t B, int64_t X, double grad_scale, zs_stream_t stream, bool generic_only,
+                            int64_t ldkb) {
     if (K > 2 * BOX_MAX_ROW_WARPS || B >= ((int64_t)1 << 31) || X * 4 % 16 != 0) {
         set_last_error_msg("box kernel: at most two rows per warp (K <= 50)");
         return ZS_ERR_UNSUPPORTED;
@@ -1488,8 +1830,6 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     const int nw = K <= BOX_MAX_ROW_WARPS ? (int)K : (int)((K + 1) / 2);
     const size_t smem = BoxLayout((int)K, (int)X, inner, nslot).total();
     const int threads = (nw + 4) * 32;
-    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
-    ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = sm_count();
     {
         const char* e = getenv("ZS_FUSED_GRID");  // dev knob: fewer CTAs than SMs (per-SM vs chip-level bound)
@@ -1498,6 +1838,31 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     }
     if (grid > B) grid = B;
     const Stagger stg = pick_stagger(K, X, B, grid);
+    // fixed-geometry instantiations (fully unrolled box loops) for the common row lengths
+    using boxf_fn = decltype(&k_iw_bernoulli_boxf<ZS_EST_SGVB, 28, 7>);
+    boxf_fn fixed = nullptr;
+    if (!generic_only) {
+        const bool sg = estimator == ZS_EST_SGVB;
+#define ZS_BOXF_PICK(I4, NB)                                                                                  \
+    if (inner == 4 * (I4) && nbox == (NB))                                                                     \
+        fixed = sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB>
+        ZS_BOXF_PICK(28, 7);   // X = 784
+        ZS_BOXF_PICK(32, 1);   // X = 128
+        ZS_BOXF_PICK(64, 1);   // X = 256
+        ZS_BOXF_PICK(64, 2);   // X = 512
+        ZS_BOXF_PICK(64, 4);   // X = 1024
+#undef ZS_BOXF_PICK
+    }
+    if (fixed != nullptr) {
+        ZS_CUDA_TRY(cudaFuncSetAttribute(fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fixed<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
+                                                                     logq, (int)K, B, nslot, (float)grad_scale, stg.groups,
+                                                                     stg.cycles, ldkb);
+        ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
+        return ZS_OK;
+    }
+    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
+    ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // boxes requested into L2 ahead of the shared-memory copies: measured no gain (0..4) to a loss (>= 7), off
     static int l2_ahead = -1;
     if (l2_ahead < 0) {
@@ -1506,14 +1871,14 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     }
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
                                                                logq, (int)K, B, (int)X, inner, nslot, l2_ahead,
-                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace);
+                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace, ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
     return ZS_OK;
 }
 
 static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                              const float* probs, const float* x, const float* logp_other, const float* logq,
-                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream, int64_t ldkb) {
     int dev = 0, max_optin = 0;
     ZS_CUDA_TRY(cudaGetDevice(&dev));
     ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1537,8 +1902,9 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     const int threads = (nw + 3) * 32;
     const bool sgvb = estimator == ZS_EST_SGVB;
     const int trips = ((int)(X / 4) + 31) / 32;  // 128-bit loads per lane and row
+    // exact trip counts of common row lengths are fully unrolled (784 -> 7)
     auto kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 0> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 0>;
-    switch (trips) {  // exact trip counts of common row lengths are fully unrolled (784 -> 7)
+    switch (trips) {
         case 2: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 2> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 2>; break;
         case 4: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 4> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 4>; break;
         case 7: kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 7> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 7>; break;
@@ -1554,11 +1920,42 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     }
     if (grid > B) grid = B;
     const Stagger stg = pick_stagger(K, X, B, grid);
+    int early = ZS_RING_EARLY_DEFAULT;
+    {
+        const char* e = getenv("ZS_FUSED_EARLY");  // dev knob: first bulk copies before / after the first staging
+        if (e != nullptr && e[0] != 0) early = e[0] != '0';
+    }
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
                                                                logp_other, logq, (int)K, B, (int)X, R,
-                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace);
+                                                               (float)grad_scale, (stg.groups & 0xff) | (early ? 0x100 : 0),
+                                                               stg.cycles, g_trace, ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
     return ZS_OK;
+}
+
+// Box / ring kernels with the [K, .] arrays (logp_other, logq, dlogp, dlogq, logpx_out) at row pitch `ldkb` >= B:
+// the host-buffer step runs chunks of columns straight out of / into full-size device arrays.
+static int fused_launch_pitched(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
+                                const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
+                                int64_t B, int64_t X, int64_t ldkb, double grad_scale, zs_stream_t stream) {
+    if (X % 4 != 0 || K > 4096 || X > (1 << 20)) {
+        set_last_error_msg("fused kernel needs X % 4 == 0 and K <= 4096");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    if (!aligned16(probs) || !aligned16(x) || !aligned16(dprobs)) {
+        set_last_error_msg("fused kernel needs 16-byte aligned probs / x / dprobs");
+        return ZS_ERR_ALIGN;
+    }
+    const int impl = fused_impl_choice();
+    if (impl >= 3) {
+        int rc = launch_fused_box(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
+                                  grad_scale, stream, impl == 4, ldkb);
+        if (rc != ZS_ERR_UNSUPPORTED) return rc;
+    }
+    if (impl >= 2)
+        return launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
+                                 grad_scale, stream, ldkb);
+    return ZS_ERR_UNSUPPORTED;
 }
 
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
@@ -1568,27 +1965,12 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
     if (B == 0) return ZS_OK;
-    if (X % 4 != 0 || K > 4096 || X > (1 << 20)) {
-        set_last_error_msg("fused kernel needs X % 4 == 0 and K <= 4096");
-        return ZS_ERR_UNSUPPORTED;
-    }
-    if (!aligned16(probs) || !aligned16(x) || !aligned16(dprobs)) {
-        set_last_error_msg("fused kernel needs 16-byte aligned probs / x / dprobs");
-        return ZS_ERR_ALIGN;
-    }
+    int rc = fused_launch_pitched(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B,
+                                  grad_scale, stream);
+    if (rc != ZS_ERR_UNSUPPORTED || X % 4 != 0 || K > 4096 || X > (1 << 20)) return rc;
     if (fused_impl_choice() == 0)
         return launch_fused_smem(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                                  grad_scale, stream);
-    if (fused_impl_choice() == 3) {
-        int rc = launch_fused_box(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
-                                  grad_scale, stream);
-        if (rc != ZS_ERR_UNSUPPORTED) return rc;
-    }
-    if (fused_impl_choice() >= 2) {
-        int rc = launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B,
-                                   X, grad_scale, stream);
-        if (rc != ZS_ERR_UNSUPPORTED) return rc;
-    }
     return launch_fused_l2(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                            grad_scale, stream);
 }
@@ -1601,19 +1983,26 @@ int zs_debug_set_trace(void* device_buffer) {
 }
 
 // ---- host-buffer step, pipelined over column chunks -----------------------------------------------
-// Batch columns are independent, so the step is cut into chunks of HS_CHUNK columns that flow through
-// three internal streams: H2D copy of chunk c+1, fused kernel on chunk c and D2H copy of chunk c-1
-// overlap (PCIe is full duplex), with HS_NBUF rotating device buffers.  The [K,B,X] host layout is
-// gathered / scattered with 2-D copies (K rows of chunk*X floats, host pitch B*X).
+// Batch columns are independent, so the step is cut into chunks of columns that flow through internal
+// streams: H2D copy of chunk c+1, fused kernel on chunk c and D2H copy of chunk c-1 overlap (PCIe is
+// full duplex), with HS_NBUF rotating device buffers.  The [K,B,X] host layout is gathered / scattered
+// with 2-D copies (K rows of chunk*X floats, host pitch B*X).  The first H2D and the last D2H cannot
+// overlap anything, so the chunk schedule starts and ends with small chunks (32, 64, 128, ..., 64, 32).
+// The small results (cost, dlogp, dlogq) travel on their own stream ahead of the big dprobs copies, so
+// a caller can go on (zs_iw_step_host_wait(0)) while the gradient of the likelihood is still landing.
 namespace {
 constexpr int HS_NBUF = 3;
 constexpr int64_t HS_CHUNK = 128;
+constexpr int64_t HS_CHUNK_MIN = 32;
+constexpr int HS_MAX_CHUNKS = 4096;
 
 struct HostStepCtx {
     bool ready = false;
     int device = -1;
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[HS_NBUF], ev_run[HS_NBUF], ev_out[HS_NBUF], ev_start = nullptr;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr, s_small = nullptr;
+    cudaEvent_t ev_in[HS_NBUF], ev_run[HS_NBUF], ev_out[HS_NBUF], ev_small[HS_NBUF], ev_start = nullptr;
+    cudaEvent_t ev_small_done = nullptr, ev_all_done = nullptr;
+    bool pending = false;
 };
 HostStepCtx g_hs;
 
@@ -1624,40 +2013,96 @@ int host_step_ctx(HostStepCtx** out) {
         ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_in, cudaStreamNonBlocking));
         ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_run, cudaStreamNonBlocking));
         ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_out, cudaStreamNonBlocking));
+        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_small, cudaStreamNonBlocking));
         for (int i = 0; i < HS_NBUF; ++i) {
             ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_in[i], cudaEventDisableTiming));
             ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_run[i], cudaEventDisableTiming));
             ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_out[i], cudaEventDisableTiming));
+            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_small[i], cudaEventDisableTiming));
         }
         ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_start, cudaEventDisableTiming));
+        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_small_done, cudaEventDisableTiming));
+        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_all_done, cudaEventDisableTiming));
         g_hs.ready = true;
         g_hs.device = dev;
+        g_hs.pending = false;
     }
     *out = &g_hs;
     return ZS_OK;
 }
 inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+// chunk sizes: 32, 64 at the head, 64, 32 at the tail, HS_CHUNK in between (fewer, smaller chunks for small B)
+int chunk_schedule(int64_t B, int64_t* sizes) {
+    int n = 0;
+    int64_t head[8], tail[8];
+    int nh = 0, nt = 0;
+    int64_t left = B;
+    for (int64_t c = HS_CHUNK_MIN; c < HS_CHUNK && left >= 4 * c; c *= 2) {
+        head[nh++] = c;
+        tail[nt++] = c;
+        left -= 2 * c;
+    }
+    for (int i = 0; i < nh; ++i) sizes[n++] = head[i];
+    while (left > 0 && n < HS_MAX_CHUNKS - 8) {
+        const int64_t c = left < HS_CHUNK ? left : HS_CHUNK;
+        sizes[n++] = c;
+        left -= c;
+    }
+    if (left > 0) return -1;
+    for (int i = nt - 1; i >= 0; --i) sizes[n++] = tail[i];
+    return n;
+}
 }  // namespace
 
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X) {
     if (K < 1 || B < 0 || X < 1) return -1;
     const int64_t c = B < HS_CHUNK ? (B > 0 ? B : 1) : HS_CHUNK;
     const int64_t per = 2 * up256(K * c * X * 4) + up256(c * X * 4) + 5 * up256(K * c * 4) + up256(c * 4);
-    return HS_NBUF * per;
+    // + full-size [K,B] log-weight terms and gradients, and the per-column costs
+    return HS_NBUF * per + 4 * up256(K * B * 4) + up256(B * 4);
 }
 
-int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
-                    const float* probs_host, const float* x_host, const float* logp_other_host,
-                    const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
-                    int64_t ws_bytes, zs_stream_t stream) {
+int zs_iw_step_host_wait(int what) {
+    if (!g_hs.ready) return ZS_OK;
+    int dev = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != g_hs.device) ZS_CUDA_TRY(cudaSetDevice(g_hs.device));
+    cudaError_t e = cudaSuccess;
+    if (what == 0) {
+        e = cudaEventSynchronize(g_hs.ev_small_done);
+    } else {
+        e = cudaEventSynchronize(g_hs.ev_all_done);
+        if (e == cudaSuccess) g_hs.pending = false;
+    }
+    if (dev != g_hs.device) cudaSetDevice(dev);
+    ZS_CUDA_TRY(e);
+    return ZS_OK;
+}
+
+int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, float* dlogp, float* dlogq,
+                          const float* probs_host, const float* x_host, const float* logp_other, const float* logq,
+                          int64_t K, int64_t B, int64_t X, double grad_scale, void* ws, int64_t ws_bytes,
+                          int scalars_on_device, zs_stream_t stream) {
     ZS_REQUIRE(probs_host && x_host && ws && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
-    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && logq_host == nullptr), ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && logq == nullptr), ZS_ERR_ARG);
     if (ws_bytes < zs_iw_step_host_workspace(K, B, X)) return ZS_ERR_WORKSPACE;
     ZS_REQUIRE(aligned16(ws), ZS_ERR_ALIGN);
     HostStepCtx* ctx = nullptr;
     int rc = host_step_ctx(&ctx);
     if (rc != ZS_OK) return rc;
+    // a previous step whose big copies were left in flight shares the workspace: let it land first
+    if (ctx->pending) {
+        rc = zs_iw_step_host_wait(1);
+        if (rc != ZS_OK) return rc;
+    }
+    static int64_t sizes[HS_MAX_CHUNKS];
+    const int nchunks = chunk_schedule(B, sizes);
+    if (nchunks < 0) {
+        set_last_error_msg("host step: too many column chunks");
+        return ZS_ERR_UNSUPPORTED;
+    }
     const int64_t C = B < HS_CHUNK ? B : HS_CHUNK;
     const int64_t kcx = up256(K * C * X * 4), cx = up256(C * X * 4), kc = up256(K * C * 4), cb = up256(C * 4);
     const int64_t per = 2 * kcx + cx + 5 * kc + cb;
@@ -1669,53 +2114,80 @@ int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* 
         buf[i].probs = (float*)p; p += kcx;
         buf[i].dprobs = (float*)p; p += kcx;
         buf[i].x = (float*)p; p += cx;
-        buf[i].other = (float*)p; p += kc;
+        buf[i].other = (float*)p; p += kc;   // the dense [K,bc] arrays serve the two-pass fallback only
         buf[i].logq = (float*)p; p += kc;
         buf[i].dlogp = (float*)p; p += kc;
         buf[i].dlogq = (float*)p; p += kc;
         buf[i].lpx = (float*)p; p += kc;
         buf[i].cost = (float*)p;
     }
+    const bool dev_sc = scalars_on_device != 0;
+    const int64_t kb = up256(K * B * 4);
+    char* gp = (char*)ws + HS_NBUF * per;
+    // full-size device arrays of the [K,B] terms: the caller's own (device mode) or workspace copies of the
+    // host arrays, moved with ONE contiguous copy each way instead of K short rows per chunk
+    float* other_full = dev_sc ? const_cast<float*>(logp_other) : (logp_other ? (float*)gp : nullptr);
+    float* logq_full = dev_sc ? const_cast<float*>(logq) : (logq ? (float*)(gp + kb) : nullptr);
+    float* dlogp_full = dev_sc ? dlogp : (float*)(gp + 2 * kb);
+    float* dlogq_full = dev_sc ? dlogq : (float*)(gp + 3 * kb);
+    float* cost_full = (float*)(gp + 4 * kb);
+    if (dev_sc && dlogp_full == nullptr) dlogp_full = (float*)(gp + 2 * kb);
+    if (dev_sc && dlogq_full == nullptr) dlogq_full = (float*)(gp + 3 * kb);
     // order the internal streams after whatever the caller already enqueued
     ZS_CUDA_TRY(cudaEventRecord(ctx->ev_start, as_stream(stream)));
     ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_start, 0));
     ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_small, ctx->ev_start, 0));
+    ctx->pending = true;
+    if (!dev_sc) {
+        if (logp_other)
+            ZS_CUDA_TRY(cudaMemcpyAsync(other_full, logp_other, K * B * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (logq) ZS_CUDA_TRY(cudaMemcpyAsync(logq_full, logq, K * B * 4, cudaMemcpyHostToDevice, ctx->s_in));
+    }
 
-    const int64_t nchunks = (B + C - 1) / C;
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int i = (int)(c % HS_NBUF);
-        const int64_t b0 = c * C, bc = (B - b0 < C) ? (B - b0) : C;
+    int64_t b0 = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int i = c % HS_NBUF;
+        const int64_t bc = sizes[c];
         Buf& d = buf[i];
-        // the buffer is free once the D2H copies of chunk c - HS_NBUF are done
+        // the buffer set is free once the D2H copy of chunk c - HS_NBUF is done
         if (c >= HS_NBUF) ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[i], 0));
         ZS_CUDA_TRY(cudaMemcpy2DAsync(d.probs, bc * X * 4, probs_host + b0 * X, B * X * 4, bc * X * 4, K,
                                       cudaMemcpyHostToDevice, ctx->s_in));
         ZS_CUDA_TRY(cudaMemcpyAsync(d.x, x_host + b0 * X, bc * X * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        if (logp_other_host)
-            ZS_CUDA_TRY(cudaMemcpy2DAsync(d.other, bc * 4, logp_other_host + b0, B * 4, bc * 4, K,
-                                          cudaMemcpyHostToDevice, ctx->s_in));
-        if (logq_host)
-            ZS_CUDA_TRY(cudaMemcpy2DAsync(d.logq, bc * 4, logq_host + b0, B * 4, bc * 4, K, cudaMemcpyHostToDevice,
-                                          ctx->s_in));
         ZS_CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
 
         ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[i], 0));
+        if (c >= HS_NBUF) ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[i], 0));  // dprobs buffer reuse
         zs_stream_t run = (zs_stream_t)ctx->s_run;
-        rc = zs_iw_bernoulli_fused(estimator, d.cost, dprobs_host ? d.dprobs : nullptr, d.dlogp, d.dlogq, nullptr,
-                                   d.probs, d.x, logp_other_host ? d.other : nullptr, logq_host ? d.logq : nullptr,
-                                   K, bc, X, grad_scale, run);
+        rc = fused_launch_pitched(estimator, cost_full + b0, dprobs_host ? d.dprobs : nullptr, dlogp_full + b0,
+                                  dlogq_full + b0, nullptr, d.probs, d.x, other_full ? other_full + b0 : nullptr,
+                                  logq_full ? logq_full + b0 : nullptr, K, bc, X, B, grad_scale, run);
         if (rc == ZS_ERR_UNSUPPORTED || rc == ZS_ERR_ALIGN) {
-            // two-pass form: likelihood log-pmf, objective over [K,bc], likelihood backward
+            // two-pass form on dense [K,bc] copies of the chunk's columns: likelihood log-pmf, objective,
+            // likelihood backward
+            if (other_full)
+                ZS_CUDA_TRY(cudaMemcpy2DAsync(d.other, bc * 4, other_full + b0, B * 4, bc * 4, K, cudaMemcpyDeviceToDevice,
+                                              ctx->s_run));
+            if (logq_full)
+                ZS_CUDA_TRY(cudaMemcpy2DAsync(d.logq, bc * 4, logq_full + b0, B * 4, bc * 4, K, cudaMemcpyDeviceToDevice,
+                                              ctx->s_run));
+            else
+                ZS_CUDA_TRY(cudaMemsetAsync(d.logq, 0, K * bc * 4, ctx->s_run));
             rc = zs_bernoulli_logpmf_fwd(ZS_F32, d.lpx, d.x, ZS_KBCAST, d.probs, ZS_FULL, K, bc, X, run);
             if (rc != ZS_OK) return rc;
-            if (!logq_host) ZS_CUDA_TRY(cudaMemsetAsync(d.logq, 0, K * bc * 4, ctx->s_run));
-            rc = zs_iw_objective(ZS_F32, estimator, d.cost, d.dlogp, d.dlogq, d.lpx, d.logq,
-                                 logp_other_host ? d.other : nullptr, K, bc, grad_scale, run);
+            rc = zs_iw_objective(ZS_F32, estimator, cost_full + b0, d.dlogp, d.dlogq, d.lpx, d.logq,
+                                 other_full ? d.other : nullptr, K, bc, grad_scale, run);
             if (rc != ZS_OK) return rc;
             if (dprobs_host)
                 rc = zs_bernoulli_logpmf_bwd(ZS_F32, nullptr, d.dprobs, d.dlogp, d.x, ZS_KBCAST, d.probs, ZS_FULL, K,
                                              bc, X, run);
+            if (rc != ZS_OK) return rc;
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogp_full + b0, B * 4, d.dlogp, bc * 4, bc * 4, K, cudaMemcpyDeviceToDevice,
+                                          ctx->s_run));
+            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogq_full + b0, B * 4, d.dlogq, bc * 4, bc * 4, K, cudaMemcpyDeviceToDevice,
+                                          ctx->s_run));
         }
         if (rc != ZS_OK) return rc;
         ZS_CUDA_TRY(cudaEventRecord(ctx->ev_run[i], ctx->s_run));
@@ -1724,18 +2196,38 @@ int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* 
         if (dprobs_host)
             ZS_CUDA_TRY(cudaMemcpy2DAsync(dprobs_host + b0 * X, B * X * 4, d.dprobs, bc * X * 4, bc * X * 4, K,
                                           cudaMemcpyDeviceToHost, ctx->s_out));
-        if (cost_host) ZS_CUDA_TRY(cudaMemcpyAsync(cost_host + b0, d.cost, bc * 4, cudaMemcpyDeviceToHost, ctx->s_out));
-        if (dlogp_host)
-            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogp_host + b0, B * 4, d.dlogp, bc * 4, bc * 4, K, cudaMemcpyDeviceToHost,
-                                          ctx->s_out));
-        if (dlogq_host)
-            ZS_CUDA_TRY(cudaMemcpy2DAsync(dlogq_host + b0, B * 4, d.dlogq, bc * 4, bc * 4, K, cudaMemcpyDeviceToHost,
-                                          ctx->s_out));
         ZS_CUDA_TRY(cudaEventRecord(ctx->ev_out[i], ctx->s_out));
+        b0 += bc;
     }
-    ZS_CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
-    ZS_CUDA_TRY(cudaStreamSynchronize(ctx->s_run));
+    // small results: one contiguous copy each, on their own stream, right after the last kernel (ahead of the
+    // tail of the dprobs copies).  "small results landed" also means every kernel has run; "all landed" joins
+    // every internal stream.  The caller's stream is ordered after the kernels so device-resident gradients can
+    // be consumed from it without a host round trip.
+    const int last = (nchunks - 1) % HS_NBUF;
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_small, ctx->ev_run[last], 0));
+    if (cost_host) ZS_CUDA_TRY(cudaMemcpyAsync(cost_host, cost_full, B * 4, cudaMemcpyDeviceToHost, ctx->s_small));
+    if (!dev_sc) {
+        if (dlogp) ZS_CUDA_TRY(cudaMemcpyAsync(dlogp, dlogp_full, K * B * 4, cudaMemcpyDeviceToHost, ctx->s_small));
+        if (dlogq) ZS_CUDA_TRY(cudaMemcpyAsync(dlogq, dlogq_full, K * B * 4, cudaMemcpyDeviceToHost, ctx->s_small));
+    }
+    ZS_CUDA_TRY(cudaEventRecord(ctx->ev_small_done, ctx->s_small));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_small_done, 0));
+    ZS_CUDA_TRY(cudaEventRecord(ctx->ev_all_done, ctx->s_out));
+    ZS_CUDA_TRY(cudaStreamWaitEvent(as_stream(stream), ctx->ev_run[last], 0));
     return ZS_OK;
+}
+
+int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
+                    const float* probs_host, const float* x_host, const float* logp_other_host,
+                    const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
+                    int64_t ws_bytes, zs_stream_t stream) {
+    int rc = zs_iw_step_host_begin(estimator, cost_host, dprobs_host, dlogp_host, dlogq_host, probs_host, x_host,
+                                   logp_other_host, logq_host, K, B, X, grad_scale, ws, ws_bytes, 0, stream);
+    if (rc != ZS_OK) {
+        zs_iw_step_host_wait(1);
+        return rc;
+    }
+    return zs_iw_step_host_wait(1);
 }
 
 }  // extern "C"

@@ -64,6 +64,8 @@ def _declare(lib):
         "zs_sghmc_post": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, i32, u64, u64, vp]),
         "zs_iw_step_host_workspace": (i64, [i64, i64, i64]),
         "zs_iw_step_host": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp, i64, vp]),
+        "zs_iw_step_host_begin": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp, i64, i32, vp]),
+        "zs_iw_step_host_wait": (i32, [i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -478,3 +480,20 @@ def iw_step_host(estimator, cost_h, dprobs_h, dlogp_h, dlogq_h, probs_h, x_h, ot
                                  hp(other_h), hp(logq_h), K, B, X, float(grad_scale), _ptr(ws), ws.numel(), _stream()),
           "zs_iw_step_host")
     _count()
+
+
+def iw_step_host_begin(estimator, cost_h, dprobs_h, dlogp, dlogq, probs_h, x_h, other, logq, K, B, X, grad_scale, ws,
+                       scalars_on_device):
+    """Enqueue the host-buffer step and return.  cost_h / dprobs_h / probs_h / x_h are pinned CPU tensors;
+    other / logq / dlogp / dlogq are CUDA tensors [K,B] when `scalars_on_device` else pinned CPU tensors.
+    Follow with iw_step_host_wait(0) (cost and every kernel done) and iw_step_host_wait(1) (dprobs landed)."""
+    hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    check(load().zs_iw_step_host_begin(estimator, hp(cost_h), hp(dprobs_h), hp(dlogp), hp(dlogq), hp(probs_h), hp(x_h),
+                                       hp(other), hp(logq), K, B, X, float(grad_scale), _ptr(ws), ws.numel(),
+                                       1 if scalars_on_device else 0, _stream()),
+          "zs_iw_step_host_begin")
+    _count()
+
+
+def iw_step_host_wait(what):
+    check(load().zs_iw_step_host_wait(int(what)), "zs_iw_step_host_wait")

@@ -79,9 +79,26 @@ class _ToHostPinned(torch.autograd.Function):
         return g.to(ctx.dev)
 
 
+_keep_on_device = [0]
+
+
+class device_results(object):
+    """Inside this context ops return their results on the compute device instead of the caller's
+    device.  The objectives use it for intermediate [K,B] log-probabilities that only they consume, so a
+    host-resident model does not pay a device->host->device round trip (and two synchronisations) per node."""
+
+    def __enter__(self):
+        _keep_on_device[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _keep_on_device[0] -= 1
+        return False
+
+
 def back_home(t, home):
     """Return `t` on the caller's device; remember the device original for later ops."""
-    if t.device == home:
+    if t.device == home or _keep_on_device[0]:
         return t
     if home.type == "cpu" and t.is_cuda and t.numel() * t.element_size() >= (1 << 16):
         out = _ToHostPinned.apply(t)
@@ -458,19 +475,25 @@ def _workspace(nbytes):
 
 
 class _IWBernoulliFusedHost(torch.autograd.Function):
-    """The fused likelihood + objective step for HOST-resident probs / x: zs_iw_step_host pipelines
-    H2D copies, the fused kernel and D2H copies over column chunks; dprobs lands in pinned host memory
-    and is handed to autograd as the gradient of the CPU leaf."""
+    """The fused likelihood + objective step for HOST-resident probs / x: zs_iw_step_host_begin pipelines
+    H2D copies, the fused kernel and D2H copies over column chunks.  The [K,B] log-weight terms and their
+    gradients stay on the device (they come from / go to the latent nodes' kernels); forward returns as soon
+    as the per-column costs have landed, while the tail of dprobs is still on its way to pinned host memory.
+    backward hands that buffer to autograd as the gradient of the CPU leaf and queues an end-of-backward
+    callback that waits for the last copy, so the latent nodes' backward overlaps the transfer."""
 
     @staticmethod
     def forward(ctx, probs, x, logp_other, logq, estimator):
         K, B, X = probs.shape
+        dev = compute_device()
         cost = _pinned((B,), "cost")
         dprobs = _pinned((K, B, X), "dprobs") if ctx.needs_input_grad[0] else None
-        dlp = _pinned((K, B), "dlogp")
-        dlq = _pinned((K, B), "dlogq")
+        dlp = torch.empty((K, B), dtype=torch.float32, device=dev)
+        dlq = torch.empty((K, B), dtype=torch.float32, device=dev)
         ws = _workspace(be.iw_step_host_workspace(K, B, X))
-        be.iw_step_host(estimator, cost, dprobs, dlp, dlq, probs, x, logp_other, logq, K, B, X, 1.0 / B, ws)
+        be.iw_step_host_begin(estimator, cost, dprobs, dlp, dlq, probs, x, logp_other, logq, K, B, X, 1.0 / B, ws,
+                              True)
+        be.iw_step_host_wait(0)
         ctx.grads = (dprobs, dlp, dlq)
         return cost.mean()
 
@@ -482,16 +505,26 @@ class _IWBernoulliFusedHost(torch.autograd.Function):
         dprobs, dlp, dlq = ctx.grads
         ctx.grads = None
         gv = float(g)
-        if dprobs is not None and gv != 1.0:
-            dprobs = dprobs * gv
+        if dprobs is not None:
+            if gv != 1.0:
+                be.iw_step_host_wait(1)
+                dprobs = dprobs * gv
+            else:
+                # dprobs may still be landing: the engine runs this after the whole backward pass, before
+                # loss.backward() / autograd.grad() return to the caller
+                torch.autograd.Variable._execution_engine.queue_callback(_host_step_landed)
         return (dprobs, None, dlp * gv if ctx.needs_input_grad[2] else None,
                 dlq * gv if ctx.needs_input_grad[3] else None, None)
 
 
+def _host_step_landed():
+    be.iw_step_host_wait(1)
+
+
 def iw_bernoulli_fused_host(probs, x, logp_other, logq, estimator):
     """probs [K,B,X] / x [B,X] float32 CPU tensors (pinned for full PCIe speed), logp_other / logq
-    [K,B] CPU tensors or None -> scalar CPU loss."""
+    [K,B] tensors (any device; moved to the compute device) or None -> scalar CPU loss."""
     be.require_cuda()
-    f = lambda t: None if t is None else t.detach().to(torch.float32).contiguous() if not t.requires_grad else t.to(torch.float32).contiguous()
+    f = lambda t: None if t is None else to_compute(t).to(torch.float32).contiguous()
     return _IWBernoulliFusedHost.apply(probs.contiguous(), x.to(torch.float32).contiguous(), f(logp_other), f(logq),
                                        estimator)

@@ -100,19 +100,26 @@ class ImportanceWeightedObjective(nn.Module):
                 total = lp if total is None else total + lp
             return total
 
-        logp_other = kb_sum(nodes_p, skip=lik)
-        logq = kb_sum(nodes_q)
+        host_route = not _be.on_compute_device(probs)
+        if host_route:
+            # the [K,B] terms are consumed by the kernel only: keep them (and their gradients) on the device
+            with _ops.device_results():
+                logp_other = kb_sum(nodes_p, skip=lik)
+                logq = kb_sum(nodes_q)
+        else:
+            logp_other = kb_sum(nodes_p, skip=lik)
+            logq = kb_sum(nodes_q)
         if logp_other is False or logq is False:
             return None
         if self.estimator == 'vimco' and logq is None:
             return None
         est = _be.SGVB if self.estimator == 'sgvb' else _be.VIMCO
         dev = probs.device
+        if host_route:
+            # host-resident likelihood tensor: chunk-pipelined H2D / kernel / D2H (zs_iw_step_host_begin)
+            return _ops.iw_bernoulli_fused_host(probs, x.to(dev), logp_other, logq, est)
         lo = None if logp_other is None else logp_other.to(dev, probs.dtype)
         lq = None if logq is None else logq.to(dev, probs.dtype)
-        if not _be.on_compute_device(probs):
-            # host-resident likelihood tensor: chunk-pipelined H2D / kernel / D2H (zs_iw_step_host)
-            return _ops.iw_bernoulli_fused_host(probs, x.to(dev), lo, lq, est)
         return _ops.iw_bernoulli_fused(probs, x.to(dev), lo, lq, est)
 
     # -- reference protocol ---------------------------------------------------------------------
