@@ -122,6 +122,15 @@ int zs_bernoulli_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, con
 int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, const void* x, int x_mode,
                             const void* probs, int probs_mode, int64_t K, int64_t M, int64_t E,
                             zs_stream_t stream);
+/* The same log-pmf for a Bernoulli given by LOGITS: probs = sigmoid(logits) (Bernoulli.__init__,
+ * bernoulli.py:47-50) is formed in registers, then bernoulli.py:84-95 as above; dlogits = dprobs * p * (1 - p)
+ * (autograd of torch.sigmoid).  Replaces the decoder's Sigmoid + its backward (examples' iwae.py:45-46,75):
+ * the [K,M,E] tensor makes one HBM trip each way instead of three.                  */
+int zs_bernoulli_logits_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* logits, int logits_mode,
+                                   int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+int zs_bernoulli_logits_logpmf_bwd(int dtype, void* dx, void* dlogits, const void* g, const void* x, int x_mode,
+                                   const void* logits, int logits_mode, int64_t K, int64_t M, int64_t E,
+                                   zs_stream_t stream);
 
 /* ---- fused latent-node kernels (zs_latent.cu) -------------------------------
  * Forward: z ~ q (Philox or injected noise), log q(z) and log p(z) under the prior, both summed over
@@ -200,6 +209,15 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
                           zs_stream_t stream);
+/* The same launch for a likelihood given by LOGITS [K,B,X] (Bernoulli(logits=...), bernoulli.py:47-50): the
+ * sigmoid is applied as the rows arrive in shared memory and its derivative is chained into the result, so
+ * `dlogits` is the gradient w.r.t. the decoder's pre-activations.  Available where a fixed-geometry kernel is
+ * instantiated (X in {128, 256, 512, 784, 1024}, K <= 50); otherwise ZS_ERR_UNSUPPORTED and the caller composes
+ * zs_bernoulli_logits_logpmf_fwd -> zs_iw_objective -> zs_bernoulli_logits_logpmf_bwd.              */
+int zs_iw_bernoulli_fused_logits(int estimator, float* cost, float* dlogits, float* dlogp, float* dlogq,
+                                 float* logpx_out, const float* logits, const float* x, const float* logp_other,
+                                 const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                                 zs_stream_t stream);
 
 /* Debug hook: device buffer (grid*40 int64) that the fused kernel fills with clock64() phase
  * timestamps of each CTA's first 8 columns; NULL (default) disables tracing. */

@@ -155,6 +155,35 @@ def bernoulli_logpmf_bwd(g, x, probs, K, M, E, need_dx=False):
     return dprobs.reshape(probs.shape)
 
 
+# Bernoulli given by logits: the reference forms probs = torch.sigmoid(logits) in the operand dtype
+# (zhusuan/distributions/bernoulli.py:47-50) and evaluates the log-pmf above (:84-95); autograd of torch.sigmoid
+# is grad * (1 - p) * p.  Restated in numpy on top of the C functions above.
+def sigmoid(logits):
+    dt = logits.dtype.type
+    return (dt(1) / (dt(1) + np.exp(-logits))).astype(dt)
+
+
+def bernoulli_logits_logpmf_fwd(x, logits, K, M, E):
+    return bernoulli_logpmf_fwd(x, sigmoid(np.asarray(logits)), K, M, E)
+
+
+def bernoulli_logits_logpmf_bwd(g, x, logits, K, M, E, need_dx=False):
+    p = sigmoid(np.asarray(logits))
+    r = bernoulli_logpmf_bwd(g, x, p, K, M, E, need_dx=need_dx)
+    dx, dp = r if need_dx else (None, r)
+    dl = (dp * ((1 - p) * p)).astype(p.dtype)
+    return (dx, dl) if need_dx else dl
+
+
+def iw_bernoulli_logits_step(estimator, logits, x, logp_other, logq, grad_scale=None, need_dprobs=True):
+    """iw_bernoulli_step for a likelihood given by logits; "dprobs" of the result is the gradient w.r.t. the logits."""
+    p = sigmoid(np.asarray(logits))
+    r = iw_bernoulli_step(estimator, p, x, logp_other, logq, grad_scale, need_dprobs)
+    if need_dprobs:
+        r["dprobs"] = (r["dprobs"] * ((1 - p) * p)).astype(p.dtype)
+    return r
+
+
 # --------------------------------------------------------------------------- Categorical (parity unpinned)
 def categorical_logpmf_fwd(x, logits, K, M, C):
     dt = logits.dtype.type

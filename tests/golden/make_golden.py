@@ -179,9 +179,9 @@ def gen_reinforce():
 class _Gen(BayesianNet):
     """Generator with the decoder output given as a leaf (the path boundary of SURVEY.md §8d)."""
 
-    def __init__(self, probs, K, latent):
+    def __init__(self, probs, K, latent, logits=False):
         super().__init__()
-        self.probs, self.K, self.latent = probs, K, latent
+        self.probs, self.K, self.latent, self.logits = probs, K, latent, logits
 
     def forward(self, observed):
         self.observe(observed)
@@ -192,7 +192,10 @@ class _Gen(BayesianNet):
         else:
             self.bernoulli("z", probs=0.5 * torch.ones([B, Z], dtype=self.probs.dtype), n_samples=self.K,
                            reduce_sum_dims=[2])
-        self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
+        if self.logits:  # the decoder's pre-activations: the reference applies the sigmoid itself (bernoulli.py:47-50)
+            self.sn(Bernoulli(logits=self.probs), name="x", reduce_sum_dims=[2])
+        else:
+            self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
         return self
 
 
@@ -260,6 +263,76 @@ def gen_iw_path():
             out[p + "logpz"] = npy(gen.nodes["z"].log_prob())
             out[p + "logpx"] = npy(gen.nodes["x"].log_prob())
     save("iw_path", **out)
+
+
+# --------------------------------------------------------------------------- Bernoulli(logits=...)
+def gen_logits_path():
+    """Bernoulli given by logits: the node's log_prob + gradient, and the whole IW path with a logits likelihood
+    at a row length the fused logits kernel is instantiated for (X = 128)."""
+    rng = np.random.RandomState(23)
+    out = {}
+    # (a) node level, with saturated logits and a non-binary x case
+    K, M, E = 5, 7, 20
+    l64 = 3.0 * rng.standard_normal((K, M, E))
+    l64.reshape(-1)[:6] = [0.0, 20.0, -20.0, 40.0, -40.0, 1e-4]
+    xb64 = (rng.uniform(size=(M, E)) < 0.5).astype(np.float64)
+    xr64 = rng.uniform(size=(M, E))
+    g64 = rng.standard_normal((K, M))
+    out.update(node_logits=l64, node_x_binary=xb64, node_x_real=xr64, node_g=g64)
+    for dn, dt in DT.items():
+        for xn, x64 in (("binary", xb64), ("real", xr64)):
+            l = t(l64, dt, True)
+            d = Bernoulli(logits=l, group_ndims=1)
+            lp = d.log_prob(t(x64, dt))
+            (dl,) = torch.autograd.grad(lp, [l], grad_outputs=t(g64, dt))
+            out["node_%s_%s_lp" % (xn, dn)] = npy(lp)
+            out["node_%s_%s_dlogits" % (xn, dn)] = npy(dl)
+    # (b) IW path
+    K, B, Z, X = 6, 5, 4, 128
+    out.update(K=np.int64(K), B=np.int64(B), Z=np.int64(Z), X=np.int64(X))
+    mean64 = 0.5 * rng.standard_normal((B, Z))
+    logstd64 = 0.3 * rng.standard_normal((B, Z))
+    pq64 = 1.0 / (1.0 + np.exp(-rng.standard_normal((B, Z))))
+    logits64 = 2.0 * rng.standard_normal((K, B, X))
+    x64 = (rng.uniform(size=(B, X)) < 0.5).astype(np.float64)
+    eps64 = rng.standard_normal((K, B, Z))
+    u64 = rng.uniform(size=(K, B, Z))
+    out.update(mean=mean64, logstd=logstd64, probs_q=pq64, logits=logits64, x=x64, eps=eps64, u=u64)
+    for dn, dt in DT.items():
+        for est, latent in (("sgvb", "normal"), ("vimco", "bernoulli")):
+            logits = t(logits64, dt, True)
+            if latent == "normal":
+                a, b = t(mean64, dt, True), t(logstd64, dt, True)
+            else:
+                a, b = t(pq64, dt, True), None
+            eps, u = t(eps64, dt), t(u64, dt)
+
+            def fake_normal(*args, **kw):
+                if "size" in kw:
+                    return eps.clone()
+                m, s_ = args[0], args[1]
+                return (m + s_ * eps).detach()
+
+            def fake_bernoulli(p, *args, **kw):
+                return (u < p).to(p.dtype)
+
+            gen = _Gen(logits, K, latent, logits=True)
+            var = _Var(a, b, K, latent, reparam=(est == "sgvb"))
+            obj = ImportanceWeightedObjective(gen, var, axis=0, estimator=est)
+            with mock.patch("torch.normal", fake_normal), mock.patch("torch.bernoulli", fake_bernoulli):
+                loss = obj({"x": t(x64, dt)})
+            leaves = [logits, a] + ([b] if b is not None else [])
+            grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+            p_ = "%s_%s_%s_" % (est, latent, dn)
+            out[p_ + "loss"] = npy(loss)
+            out[p_ + "dlogits"] = npy(grads[0])
+            out[p_ + "da"] = npy(grads[1])
+            if b is not None:
+                out[p_ + "db"] = npy(grads[2])
+            out[p_ + "logq"] = npy(var.nodes["z"].log_prob())
+            out[p_ + "logpz"] = npy(gen.nodes["z"].log_prob())
+            out[p_ + "logpx"] = npy(gen.nodes["x"].log_prob())
+    save("logits_path", **out)
 
 
 # --------------------------------------------------------------------------- VAE ELBO (cfg 1 shapes, small)
@@ -489,6 +562,7 @@ if __name__ == "__main__":
     gen_objectives()
     gen_reinforce()
     gen_iw_path()
+    gen_logits_path()
     gen_elbo_path()
     gen_sgmcmc()
     gen_bnn()

@@ -53,12 +53,14 @@ def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0):
     return _t(O.bernoulli_sample(_np(probs), u.reshape(K, N), K, N), probs)
 
 
-def bernoulli_logpmf_fwd(x, xm, probs, pm, K, M, E):
-    return _t(O.bernoulli_logpmf_fwd(_np(x), _np(probs), K, M, E), probs)
+def bernoulli_logpmf_fwd(x, xm, probs, pm, K, M, E, logits=False):
+    f = O.bernoulli_logits_logpmf_fwd if logits else O.bernoulli_logpmf_fwd
+    return _t(f(_np(x), _np(probs), K, M, E), probs)
 
 
-def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs):
-    dx, dp = O.bernoulli_logpmf_bwd(_np(g), _np(x), _np(probs), K, M, E, need_dx=True)
+def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs, logits=False):
+    f = O.bernoulli_logits_logpmf_bwd if logits else O.bernoulli_logpmf_bwd
+    dx, dp = f(_np(g), _np(x), _np(probs), K, M, E, need_dx=True)
     return (_t(dx, probs) if need_x else None, _t(dp, probs) if need_probs else None)
 
 
@@ -101,9 +103,10 @@ def fused_supported(K, X, dtype):
     return dtype == torch.float32 and X % 4 == 0 and 1 <= K <= 4096
 
 
-def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False, out=None):
-    r = O.iw_bernoulli_step(estimator, _np(probs), _np(x), _np(logp_other), _np(logq), grad_scale,
-                            need_dprobs=need_dprobs)
+def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False, out=None,
+                       logits=False):
+    f = O.iw_bernoulli_logits_step if logits else O.iw_bernoulli_step
+    r = f(estimator, _np(probs), _np(x), _np(logp_other), _np(logq), grad_scale, need_dprobs=need_dprobs)
     return dict(cost=_t(r["cost"], probs), dprobs=_t(r["dprobs"], probs) if need_dprobs else None,
                 dlogp=_t(r["dlogp"], probs), dlogq=_t(r["dlogq"], probs),
                 logpx=_t(r["logpx"], probs) if want_logpx else None)

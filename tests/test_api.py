@@ -437,9 +437,9 @@ def test_reinforce_against_reference_golden(dev, golden):
 
 
 class _PathGen(BayesianNet):
-    def __init__(self, probs, K, latent):
+    def __init__(self, probs, K, latent, logits=False):
         super().__init__(device=probs.device)
-        self.probs, self.K, self.latent = probs, K, latent
+        self.probs, self.K, self.latent, self.logits = probs, K, latent, logits
 
     def forward(self, observed):
         self.observe(observed)
@@ -451,7 +451,10 @@ class _PathGen(BayesianNet):
         else:
             self.bernoulli("z", probs=0.5 * torch.ones([B, Z], dtype=dt, device=d), n_samples=self.K,
                            reduce_sum_dims=[2])
-        self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
+        if self.logits:
+            self.sn(Bernoulli(logits=self.probs), name="x", reduce_sum_dims=[2])
+        else:
+            self.sn(Bernoulli(probs=self.probs), name="x", reduce_sum_dims=[2])
         return self
 
 
@@ -506,6 +509,43 @@ def test_iw_path_against_reference_golden(dev, golden, est, latent, dn):
     close(grads[1], ref["da"], gt)
     if b is not None:
         close(grads[2], g[(p if est == "sgvb" or dn == "f64" else p.replace("f32", "f64")) + "db"], gt)
+
+
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("est,latent", [("sgvb", "normal"), ("vimco", "bernoulli")])
+def test_iw_logits_path_against_reference_golden(dev, golden, est, latent, dn):
+    """The hot path with the likelihood given by LOGITS (Bernoulli(logits=...)): the sigmoid is applied inside the
+    kernels and the gradient reaches the logits directly; against the reference run (make_golden.py:gen_logits_path)."""
+    g = golden("logits_path")
+    dt = torch.float32 if dn == "f32" else torch.float64
+    K = int(g["K"])
+    p = "%s_%s_%s_" % (est, latent, dn)
+    logits = T(g["logits"], dev, dt, True)
+    if latent == "normal":
+        a, b = T(g["mean"], dev, dt, True), T(g["logstd"], dev, dt, True)
+        inj = dict(normal=[T(g["eps"], dev, dt)] * 2)
+    else:
+        a, b = T(g["probs_q"], dev, dt, True), None
+        inj = dict(uniform=[T(g["u"], dev, dt)] * 2)
+    gen, var = _PathGen(logits, K, latent, logits=True), _PathVar(a, b, K, latent, est == "sgvb")
+    obj = ImportanceWeightedObjective(gen, var, axis=0, estimator=est)
+    with _rng.inject(**inj):
+        loss = obj({"x": T(g["x"], dev, dt)})
+    rt = 1e-5 if dn == "f32" else 1e-10
+    close(loss, g[p + "loss"], rt)
+    close(gen.nodes["x"].log_prob(), g[p + "logpx"], rt)
+    leaves = [logits, a] + ([b] if b is not None else [])
+    grads = torch.autograd.grad(loss, leaves)
+    gt = 4e-5 if dn == "f32" else 1e-10
+    pr = p if est == "sgvb" or dn == "f64" else p.replace("f32", "f64")
+    close(grads[0], g[pr + "dlogits"], gt)
+    close(grads[1], g[pr + "da"], gt)
+    if b is not None:
+        close(grads[2], g[pr + "db"], gt)
+    # the node API: probs is still available (computed on demand), logits is what was passed
+    d = Bernoulli(logits=logits)
+    close(d.probs, 1.0 / (1.0 + np.exp(-g["logits"])), rt)
+    assert d.logits is not None and tuple(d.batch_shape) == tuple(logits.shape)
 
 
 def test_elbo_path_against_reference_golden(dev, golden):

@@ -169,6 +169,48 @@ def test_iw_path_composite(oracle, golden, est, latent, dn):
         close(dpq, g[p + "da"], dn, loose)
 
 
+@pytest.mark.parametrize("dn", [F32, F64])
+@pytest.mark.parametrize("xn", ["binary", "real"])
+def test_bernoulli_logits_node(oracle, golden, xn, dn):
+    """Bernoulli(logits=...).log_prob and its gradient w.r.t. the logits, incl. saturated logits
+    (tests/golden/make_golden.py:gen_logits_path, reference bernoulli.py:47-50,84-95)."""
+    g = golden("logits_path")
+    dt = np.float32 if dn == F32 else np.float64
+    l, x, up = g["node_logits"].astype(dt), g["node_x_" + xn].astype(dt), g["node_g"].astype(dt)
+    K, M, E = l.shape
+    close(oracle.bernoulli_logits_logpmf_fwd(x, l, K, M, E), g["node_%s_%s_lp" % (xn, dn)], dn)
+    close(oracle.bernoulli_logits_logpmf_bwd(up, x, l, K, M, E), g["node_%s_%s_dlogits" % (xn, dn)], dn, 30)
+
+
+@pytest.mark.parametrize("dn", [F32, F64])
+@pytest.mark.parametrize("est,latent", [("sgvb", "normal"), ("vimco", "bernoulli")])
+def test_iw_logits_path_composite(oracle, golden, est, latent, dn):
+    """The IW path with the likelihood given by logits, against the reference run with the same injected noise."""
+    g = golden("logits_path")
+    dt = np.float32 if dn == F32 else np.float64
+    K, B, Z, X = int(g["K"]), int(g["B"]), int(g["Z"]), int(g["X"])
+    p = "%s_%s_%s_" % (est, latent, dn)
+    logits, x = g["logits"].astype(dt), g["x"].astype(dt)
+    if latent == "normal":
+        mean, logstd, eps = g["mean"].astype(dt), g["logstd"].astype(dt), g["eps"].astype(dt)
+        std = np.exp(logstd)
+        z = oracle.normal_sample(mean, std, eps, K, B * Z).reshape(K, B, Z)
+        logq = oracle.normal_logprob_fwd(z, mean, std, K, B, Z)
+        logpz = oracle.normal_logprob_fwd(z, np.zeros((B, Z), dt), np.ones((B, Z), dt), K, B, Z)
+    else:
+        pq, u = g["probs_q"].astype(dt), g["u"].astype(dt)
+        z = oracle.bernoulli_sample(pq, u, K, B * Z).reshape(K, B, Z)
+        logq = oracle.bernoulli_logpmf_fwd(z, pq, K, B, Z)
+        logpz = oracle.bernoulli_logpmf_fwd(z, np.full((B, Z), 0.5, dt), K, B, Z)
+    close(logq, g[p + "logq"], dn)
+    close(logpz, g[p + "logpz"], dn)
+    code = oracle.SGVB if est == "sgvb" else oracle.VIMCO
+    r = oracle.iw_bernoulli_logits_step(code, logits, x, logpz, logq)
+    close(r["logpx"], g[p + "logpx"], dn)
+    close(r["cost"].mean(), g[p + "loss"], dn)
+    close(r["dprobs"], g[p + "dlogits"], dn, 30)
+
+
 def _replay_sgmcmc(oracle, g, name):
     """Re-run the reference trajectory with the oracle's single-step updates and the recorded noise."""
     n, steps = int(g["n"]), int(g["steps"])

@@ -115,6 +115,13 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// sigmoid on the SFU: ex2 + rcp (relative error ~1e-6 over |l| <= 40; saturates to exactly 0 / 1 beyond, like
+// torch.sigmoid in float32)
+__device__ __forceinline__ float fast_sigmoid(float l) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * -1.4426950408889634f));
+    return fast_rcp(1.0f + e);
+}
 
 template <typename T>
 struct Real;

@@ -1359,11 +1359,25 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void sts128_u32(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 sigmoid4(const float4& l) {
+    return make_float4(fast_sigmoid(l.x), fast_sigmoid(l.y), fast_sigmoid(l.z), fast_sigmoid(l.w));
+}
+// p (1 - p), the derivative of the sigmoid at the stored probability
+__device__ __forceinline__ float4 dsigmoid4(const float4& o, const float4& p) {
+    return make_float4(o.x * ((1.0f - p.x) * p.x), o.y * ((1.0f - p.y) * p.y), o.z * ((1.0f - p.z) * p.z),
+                       o.w * ((1.0f - p.w) * p.w));
+}
+
 struct BoxCursor {
     uint32_t slot, addr, parity;  // ring position, shared address of that slot, parity of the fill waited for
 };
 
-template <bool BINARY, int INNER4, int NBOX>
+// LOGITS: the tensor holds the decoder's pre-activations; phase A turns each element into p = sigmoid(l) once and
+// writes it back into its shared-memory slot, phase B reads p and chains the sigmoid's derivative into the result.
+template <bool BINARY, bool LOGITS, int INNER4, int NBOX>
 __device__ __forceinline__ void boxf_phase_a(BoxCursor& cur, uint32_t slots_u, uint32_t slot_bytes, uint32_t nslot,
                                              uint32_t full_u, uint32_t empty_u, uint32_t row_a, uint32_t row_b,
                                              uint32_t x_u, int lane, bool release, float& acc_a, float& acc_b,
@@ -1376,7 +1390,13 @@ __device__ __forceinline__ void boxf_phase_a(BoxCursor& cur, uint32_t slots_u, u
         for (int i = 0; i < VIT; ++i) {
             if ((i + 1) * 32 <= INNER4 || lane + 32 * i < INNER4) {
                 const uint32_t o = (uint32_t)(i * 512);
-                const float4 pa = lds128_u32(cur.addr + row_a + o), pb = lds128_u32(cur.addr + row_b + o);
+                float4 pa = lds128_u32(cur.addr + row_a + o), pb = lds128_u32(cur.addr + row_b + o);
+                if (LOGITS) {
+                    pa = sigmoid4(pa);
+                    pb = sigmoid4(pb);
+                    sts128_u32(cur.addr + row_a + o, pa);
+                    sts128_u32(cur.addr + row_b + o, pb);
+                }
                 const uint32_t xo = x_u + (uint32_t)(q * INNER4 * 16) + o;
                 if (BINARY) {
                     const float4 c = lds128_u32(xo), e = lds128_u32(xo + XB);
@@ -1407,6 +1427,7 @@ __device__ __forceinline__ void boxf_phase_a(BoxCursor& cur, uint32_t slots_u, u
             }
         }
         if (release) {  // forward only: the box is dead after its first read
+            if (LOGITS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(empty_u + cur.slot * 8);
         }
@@ -1415,7 +1436,7 @@ __device__ __forceinline__ void boxf_phase_a(BoxCursor& cur, uint32_t slots_u, u
     }
 }
 
-template <bool BINARY, int INNER4, int NBOX>
+template <bool BINARY, bool LOGITS, int INNER4, int NBOX>
 __device__ __forceinline__ void boxf_phase_b(uint32_t bs, uint32_t bs_addr, uint32_t slots_u, uint32_t slot_bytes,
                                              uint32_t nslot, uint32_t empty_u, uint32_t row_a, uint32_t row_b,
                                              uint32_t x_u, int lane, float ga, float gb, float* __restrict__ da,
@@ -1445,10 +1466,16 @@ __device__ __forceinline__ void boxf_phase_b(uint32_t bs, uint32_t bs_addr, uint
                     oa = dprobs4<false>(pa, xx, ga);
                     ob = dprobs4<false>(pb, xx, gb);
                 }
+                if (LOGITS) {
+                    oa = dsigmoid4(oa, pa);
+                    ob = dsigmoid4(ob, pb);
+                }
                 stg_hint(da + q * INNER4 * 4 + i * 128, oa, 0);
                 if (has_b) stg_hint(db + q * INNER4 * 4 + i * 128, ob, 0);
             }
         }
+        // LOGITS: this warp's generic-proxy writes to the slot (phase A) precede the async-proxy refill
+        if (LOGITS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(empty_u + bs * 8);
         bs_addr += slot_bytes;
@@ -1456,7 +1483,7 @@ __device__ __forceinline__ void boxf_phase_b(uint32_t bs, uint32_t bs_addr, uint
     }
 }
 
-template <int EST, int INNER4, int NBOX>
+template <int EST, int INNER4, int NBOX, bool LOGITS>
 __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     k_iw_bernoulli_boxf(const __grid_constant__ CUtensorMap probs_map, float* __restrict__ cost,
                         float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
@@ -1497,7 +1524,11 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
     stagger_start(stagger_groups, stagger_cycles);
-    if (is_stager && ncols > 0) {  // column 0 only: column 1 is staged while column 0 is being read
+    // Column 0 only: column 1 is staged while column 0 is being read.  The first tensor copies are issued AFTER
+    // this staging on purpose: issuing them first (measured here and in the ring kernel: +4 and +7 us per launch)
+    // starts every CTA's column 0 at the same instant, and the chip then alternates between a read-only phase A
+    // and a write-heavy phase B in lock-step; the variable staging latency spreads the CTAs out.
+    if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
     }
@@ -1572,10 +1603,10 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
         float acc_a = 0.f, acc_b = 0.f;
         float rng[4] = {0.f, 0.f, 0.f, 0.f};
         if (binary)
-            boxf_phase_a<true, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
+            boxf_phase_a<true, LOGITS, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
                                              lane, dprobs == nullptr, acc_a, acc_b, rng);
         else
-            boxf_phase_a<false, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
+            boxf_phase_a<false, LOGITS, INNER4, NBOX>(cur, slots_u, slot_bytes, (uint32_t)nslot, full_u, empty_u, row_a, row_b, x_u,
                                               lane, dprobs == nullptr, acc_a, acc_b, rng);
         if (binary) {
             if (rng[0] < -1e-8f || rng[1] > 1.0f) acc_a = __int_as_float(0x7fc00000);
@@ -1603,10 +1634,10 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             float* da = dprobs + ((int64_t)ka * B + b) * X + lane * 4;
             float* db = dprobs + ((int64_t)kb_eff * B + b) * X + lane * 4;
             if (binary)
-                boxf_phase_b<true, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
+                boxf_phase_b<true, LOGITS, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
                                                  lane, ga, gb, da, db, has_b);
             else
-                boxf_phase_b<false, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
+                boxf_phase_b<false, LOGITS, INNER4, NBOX>(slot0, addr0, slots_u, slot_bytes, (uint32_t)nslot, empty_u, row_a, row_b, x_u,
                                                   lane, ga, gb, da, db, has_b);
         }
     }
@@ -1804,7 +1835,7 @@ static Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
 static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                             const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
                             int64_t B, int64_t X, double grad_scale, zs_stream_t stream, bool generic_only,
-                            int64_t ldkb) {
+                            int64_t ldkb, bool logits = false) {
     if (K > 2 * BOX_MAX_ROW_WARPS || B >= ((int64_t)1 << 31) || X * 4 % 16 != 0) {
         set_last_error_msg("box kernel: at most two rows per warp (K <= 50)");
         return ZS_ERR_UNSUPPORTED;
@@ -1839,13 +1870,14 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     if (grid > B) grid = B;
     const Stagger stg = pick_stagger(K, X, B, grid);
     // fixed-geometry instantiations (fully unrolled box loops) for the common row lengths
-    using boxf_fn = decltype(&k_iw_bernoulli_boxf<ZS_EST_SGVB, 28, 7>);
+    using boxf_fn = decltype(&k_iw_bernoulli_boxf<ZS_EST_SGVB, 28, 7, false>);
     boxf_fn fixed = nullptr;
     if (!generic_only) {
         const bool sg = estimator == ZS_EST_SGVB;
-#define ZS_BOXF_PICK(I4, NB)                                                                                  \
-    if (inner == 4 * (I4) && nbox == (NB))                                                                     \
-        fixed = sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB>
+#define ZS_BOXF_PICK(I4, NB)                                                                                        \
+    if (inner == 4 * (I4) && nbox == (NB))                                                                           \
+        fixed = logits ? (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, true> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, true>) \
+                       : (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, false> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, false>)
         ZS_BOXF_PICK(28, 7);   // X = 784
         ZS_BOXF_PICK(32, 1);   // X = 128
         ZS_BOXF_PICK(64, 1);   // X = 256
@@ -1860,6 +1892,10 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
                                                                      stg.cycles, ldkb);
         ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
         return ZS_OK;
+    }
+    if (logits) {
+        set_last_error_msg("fused logits form: no fixed-geometry kernel instantiated for this row length");
+        return ZS_ERR_UNSUPPORTED;
     }
     auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1956,6 +1992,22 @@ static int fused_launch_pitched(int estimator, float* cost, float* dprobs, float
         return launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                                  grad_scale, stream, ldkb);
     return ZS_ERR_UNSUPPORTED;
+}
+
+int zs_iw_bernoulli_fused_logits(int estimator, float* cost, float* dlogits, float* dlogp, float* dlogq,
+                                 float* logpx_out, const float* logits, const float* x, const float* logp_other,
+                                 const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                                 zs_stream_t stream) {
+    ZS_REQUIRE(logits && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
+    if (B == 0) return ZS_OK;
+    if (X % 4 != 0 || !aligned16(logits) || !aligned16(x) || !aligned16(dlogits)) {
+        set_last_error_msg("fused logits form needs X % 4 == 0 and 16-byte aligned logits / x / dlogits");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    return launch_fused_box(estimator, cost, dlogits, dlogp, dlogq, logpx_out, logits, x, logp_other, logq, K, B, X,
+                            grad_scale, stream, false, B, true);
 }
 
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,

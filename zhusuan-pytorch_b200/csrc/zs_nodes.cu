@@ -95,6 +95,44 @@ struct BernoulliOp<double> {
     }
 };
 
+// Bernoulli parameterised by logits (bernoulli.py:47-50 builds probs = sigmoid(logits) and then evaluates the same
+// log-pmf, :84-95): the sigmoid is computed in registers, so the decoder's final Sigmoid and its backward never make
+// a round trip through HBM.  Same "+1e-8" arguments as the probs form; d/dlogits = d/dp * p (1 - p).
+template <typename T>
+struct BernoulliLogitsOp;
+
+template <>
+struct BernoulliLogitsOp<float> {
+    static __device__ __forceinline__ float sigmoid(float l) { return fast_sigmoid(l); }
+    static __device__ __forceinline__ float term(float x, float l, float) {
+        return BernoulliOp<float>::term(x, sigmoid(l), 0.f);
+    }
+    static __device__ __forceinline__ float finish(float acc) { return acc * 0.6931471805599453f; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(float g, float x, float l, float, float& dx, float& dl, float& unused) {
+        const float p = sigmoid(l);
+        float dp;
+        BernoulliOp<float>::grad<NEED_X>(g, x, p, 0.f, dx, dp, unused);
+        dl = dp * ((1.0f - p) * p);
+    }
+};
+template <>
+struct BernoulliLogitsOp<double> {
+    static __device__ __forceinline__ double sigmoid(double l) { return 1.0 / (1.0 + ::exp(-l)); }
+    static __device__ __forceinline__ double term(double x, double l, double) {
+        return BernoulliOp<double>::term(x, sigmoid(l), 0.0);
+    }
+    static __device__ __forceinline__ double finish(double acc) { return acc; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(double g, double x, double l, double, double& dx, double& dl,
+                                                double& unused) {
+        const double p = sigmoid(l);
+        double dp;
+        BernoulliOp<double>::grad<NEED_X>(g, x, p, 0.0, dx, dp, unused);
+        dl = dp * ((1.0 - p) * p);
+    }
+};
+
 // ---------------------------------------------------------------------------
 // forward: out[r] = finish( sum_e term(x, a, b) ),  LPR lanes cooperate on a row
 // ---------------------------------------------------------------------------
@@ -673,6 +711,31 @@ int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, co
                                                Operand<T>{(const T*)x, x_mode},
                                                Operand<T>{(const T*)probs, probs_mode},
                                                Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_bernoulli_logits_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* logits, int logits_mode,
+                                   int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(out && x && logits && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(logits_mode), ZS_ERR_ARG);
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_rows_fwd<T, BernoulliLogitsOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                          Operand<T>{(const T*)logits, logits_mode},
+                                                          Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_bernoulli_logits_logpmf_bwd(int dtype, void* dx, void* dlogits, const void* g, const void* x, int x_mode,
+                                   const void* logits, int logits_mode, int64_t K, int64_t M, int64_t E,
+                                   zs_stream_t stream) {
+    ZS_REQUIRE(g && x && logits && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(logits_mode), ZS_ERR_ARG);
+    if (!dx && !dlogits) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        return dispatch_bwd<T, BernoulliLogitsOp<T>>((T*)dx, (T*)dlogits, (T*)nullptr, (const T*)g,
+                                                     Operand<T>{(const T*)x, x_mode},
+                                                     Operand<T>{(const T*)logits, logits_mode},
+                                                     Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
     })
 }
 

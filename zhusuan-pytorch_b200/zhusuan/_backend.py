@@ -48,6 +48,8 @@ def _declare(lib):
         "zs_bernoulli_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, u64, u64, vp]),
         "zs_bernoulli_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
+        "zs_bernoulli_logits_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
+        "zs_bernoulli_logits_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_categorical_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, i64, u64, u64, vp]),
         "zs_categorical_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_categorical_logpmf_bwd": (i32, [i32, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
@@ -56,6 +58,7 @@ def _declare(lib):
         "zs_log_mean_exp_bwd": (i32, [i32, vp, vp, vp, i64, i64, vp]),
         "zs_iw_bernoulli_fused_smem_bytes": (i64, [i64, i64]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
+        "zs_iw_bernoulli_fused_logits": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
         "zs_scale_inplace": (i32, [i32, vp, i64, vp, vp]),
         "zs_debug_set_trace": (i32, [vp]),
         "zs_sgld_step": (i32, [i32, vp, vp, vp, vp, i64, dbl, u64, u64, vp]),
@@ -283,24 +286,27 @@ def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0):
     return out
 
 
-def bernoulli_logpmf_fwd(x, xm, probs, pm, K, M, E):
+def bernoulli_logpmf_fwd(x, xm, probs, pm, K, M, E, logits=False):
+    """`logits=True`: `probs` holds logits and the sigmoid is applied in registers (zs_bernoulli_logits_logpmf_fwd)."""
     dt = probs.dtype
     _chk_tensor(x, "x", dt)
     _chk_tensor(probs, "probs", dt)
     out = torch.empty((K, M), dtype=dt, device=probs.device)
-    check(load().zs_bernoulli_logpmf_fwd(dtype_code(dt), _ptr(out), _ptr(x), xm, _ptr(probs), pm, K, M, E, _stream()),
-          "zs_bernoulli_logpmf_fwd")
+    fn = load().zs_bernoulli_logits_logpmf_fwd if logits else load().zs_bernoulli_logpmf_fwd
+    check(fn(dtype_code(dt), _ptr(out), _ptr(x), xm, _ptr(probs), pm, K, M, E, _stream()),
+          "zs_bernoulli_logits_logpmf_fwd" if logits else "zs_bernoulli_logpmf_fwd")
     _count()
     return out
 
 
-def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs):
+def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs, logits=False):
     dt = probs.dtype
     _chk_tensor(g, "g", dt)
     dx = torch.empty_like(x) if need_x else None
     dprobs = torch.empty_like(probs) if need_probs else None
-    check(load().zs_bernoulli_logpmf_bwd(dtype_code(dt), _ptr(dx), _ptr(dprobs), _ptr(g), _ptr(x), xm, _ptr(probs), pm,
-                                         K, M, E, _stream()), "zs_bernoulli_logpmf_bwd")
+    fn = load().zs_bernoulli_logits_logpmf_bwd if logits else load().zs_bernoulli_logpmf_bwd
+    check(fn(dtype_code(dt), _ptr(dx), _ptr(dprobs), _ptr(g), _ptr(x), xm, _ptr(probs), pm, K, M, E, _stream()),
+          "zs_bernoulli_logits_logpmf_bwd" if logits else "zs_bernoulli_logpmf_bwd")
     _count()
     return dx, dprobs
 
@@ -381,9 +387,23 @@ def fused_supported(K, X, dtype):
     return dtype == torch.float32 and X % 4 == 0 and 1 <= K <= 4096 and X <= (1 << 20)
 
 
+def fused_logits_supported(K, X, dtype):
+    """Shapes zs_iw_bernoulli_fused_logits takes: a fixed-geometry box kernel must be instantiated for the row
+    length and a column plus one box must fit in shared memory (mirrors launch_fused_box in zs_fused_iw.cu)."""
+    geo = {784: (112, 7), 128: (128, 1), 256: (256, 1), 512: (256, 2), 1024: (256, 4)}
+    if dtype != torch.float32 or X not in geo or not (1 <= K <= 50):
+        return False
+    inner, nbox = geo[X]
+    kpad = (K + 3) & ~3
+    slot = (K * inner * 4 + 127) // 128 * 128
+    fixed = 6 * X * 4 + 16 + 6 * kpad * 8 + 12 * kpad * 4 + 64
+    return (nbox + 1) * (slot + 16) + fixed <= 227 * 1024
+
+
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False,
-                       out=None):
-    """probs [K,B,X], x [B,X], logp_other/logq [K,B] or None.
+                       out=None, logits=False):
+    """probs [K,B,X], x [B,X], logp_other/logq [K,B] or None.  `logits=True`: `probs` holds logits and "dprobs" is
+    the gradient w.r.t. them (zs_iw_bernoulli_fused_logits).
     Returns dict(cost[B], dprobs, dlogp, dlogq, logpx) or None when the shape is not supported."""
     for t, n in ((probs, "probs"), (x, "x"), (logp_other, "logp_other"), (logq, "logq")):
         _chk_tensor(t, n, torch.float32)
@@ -395,8 +415,9 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
     dlp = o.get("dlogp") if "dlogp" in o else torch.empty((K, B), dtype=torch.float32, device=dev)
     dlq = o.get("dlogq") if "dlogq" in o else torch.empty((K, B), dtype=torch.float32, device=dev)
     lpx = (o.get("logpx") if "logpx" in o else torch.empty((K, B), dtype=torch.float32, device=dev)) if want_logpx else None
-    rc = load().zs_iw_bernoulli_fused(estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx), _ptr(probs),
-                                      _ptr(x), _ptr(logp_other), _ptr(logq), K, B, X, float(grad_scale), _stream())
+    fn = load().zs_iw_bernoulli_fused_logits if logits else load().zs_iw_bernoulli_fused
+    rc = fn(estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx), _ptr(probs), _ptr(x), _ptr(logp_other),
+            _ptr(logq), K, B, X, float(grad_scale), _stream())
     if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
         return None
     check(rc, "zs_iw_bernoulli_fused")

@@ -240,23 +240,26 @@ def normal_sample(mean, std, n_samples, reparameterized):
 # --------------------------------------------------------------------------------------------
 class _BernoulliLogPmf(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, probs, modes, K, M, E):
-        out = be.bernoulli_logpmf_fwd(x, modes[0], probs, modes[1], K, M, E)
+    def forward(ctx, x, probs, modes, K, M, E, logits=False):
+        out = be.bernoulli_logpmf_fwd(x, modes[0], probs, modes[1], K, M, E, logits=logits)
         ctx.save_for_backward(x, probs)
-        ctx.cfg = (modes, K, M, E)
+        ctx.cfg = (modes, K, M, E, logits)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, probs = ctx.saved_tensors
-        modes, K, M, E = ctx.cfg
+        modes, K, M, E, logits = ctx.cfg
         nx, np_ = ctx.needs_input_grad[:2]
-        dx, dprobs = be.bernoulli_logpmf_bwd(g.contiguous(), x, modes[0], probs, modes[1], K, M, E, nx, np_)
-        return dx, dprobs, None, None, None, None
+        dx, dprobs = be.bernoulli_logpmf_bwd(g.contiguous(), x, modes[0], probs, modes[1], K, M, E, nx, np_,
+                                             logits=logits)
+        return dx, dprobs, None, None, None, None, None
 
 
-def bernoulli_log_prob(x, probs, n_event):
-    """sum over the last n_event axes of x*log(p+1e-8) + (1-x)*log(1-p+1e-8) (bernoulli.py:84-95)."""
+def bernoulli_log_prob(x, probs, n_event, logits=False):
+    """sum over the last n_event axes of x*log(p+1e-8) + (1-x)*log(1-p+1e-8) (bernoulli.py:84-95).
+    `logits=True`: `probs` holds logits, p = sigmoid(logits) is formed inside the kernel (bernoulli.py:47-50)
+    and the gradient flows to the logits."""
     home = probs.device
     x, probs = to_compute(x), to_compute(probs)
     L = Layout([x.shape, probs.shape], n_event)
@@ -265,7 +268,7 @@ def bernoulli_log_prob(x, probs, n_event):
     (xc, xm), (pc, pm) = L.canon(x), L.canon(probs)
     if pm == SCALAR:  # the kernels take probs as FULL / KBCAST only when it needs no gradient either way
         pc, pm = probs.expand(L.S).contiguous(), FULL
-    out = _BernoulliLogPmf.apply(xc, pc, (xm, pm), L.K, L.M, L.E)
+    out = _BernoulliLogPmf.apply(xc, pc, (xm, pm), L.K, L.M, L.E, bool(logits))
     return back_home(out.reshape(L.lead), home)
 
 
@@ -422,10 +425,10 @@ class _IWBernoulliFused(torch.autograd.Function):
     scalar with zs_scale_inplace, which is a no-op launch for the usual loss.backward()."""
 
     @staticmethod
-    def forward(ctx, probs, x, logp_other, logq, estimator):
+    def forward(ctx, probs, x, logp_other, logq, estimator, logits=False):
         K, B, X = probs.shape
         r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, 1.0 / B,
-                                  need_dprobs=ctx.needs_input_grad[0])
+                                  need_dprobs=ctx.needs_input_grad[0], logits=logits)
         if r is None:
             raise be.BackendError("fused IW kernel refused a shape fused_supported() accepted")
         ctx.grads = (r["dprobs"], r["dlogp"], r["dlogq"])
@@ -444,16 +447,17 @@ class _IWBernoulliFused(torch.autograd.Function):
         return (dprobs, None,
                 dlp * g if ctx.needs_input_grad[2] else None,
                 dlq * g if ctx.needs_input_grad[3] else None,
-                None)
+                None, None)
 
 
-def iw_bernoulli_fused(probs, x, logp_other, logq, estimator):
-    """probs [K,B,X] (CUDA, float32), x [B,X], logp_other / logq [K,B] or None -> scalar loss."""
+def iw_bernoulli_fused(probs, x, logp_other, logq, estimator, logits=False):
+    """probs [K,B,X] (CUDA, float32; logits when `logits=True`), x [B,X], logp_other / logq [K,B] or None
+    -> scalar loss."""
     probs = probs.contiguous()
     x = x.to(probs.dtype).contiguous()
     lo = None if logp_other is None else logp_other.contiguous()
     lq = None if logq is None else logq.contiguous()
-    return _IWBernoulliFused.apply(probs, x, lo, lq, estimator)
+    return _IWBernoulliFused.apply(probs, x, lo, lq, estimator, bool(logits))
 
 
 # --------------------------------------------------------------------------------------------

@@ -3,6 +3,11 @@
 log_prob is x*log(p+1e-8) + (1-x)*log(1-p+1e-8) with the event-axis sum fused (one kernel instead of
 the reference's ~8 elementwise kernels over the [K,B,X] likelihood tensor, :84-95); samples are
 floats in {0,1} drawn in-kernel from Philox uniforms (:72-82).
+
+Bernoulli(logits=...) (reference :47-50: probs = sigmoid(logits), then the same log-pmf): the kernels take the
+logits and apply the sigmoid in registers, and the gradient flows to the logits directly, so a decoder that
+ends in a Linear layer (no nn.Sigmoid) saves one read + one write of the [K,B,X] tensor in each direction
+(SURVEY 8(f)-1).  `.probs` is still available and is computed on first use.
 """
 import torch
 
@@ -25,18 +30,28 @@ class Bernoulli(Distribution):
         if logits is None:
             self._probs = torch.as_tensor(probs, dtype=dtype).to(device)
             self._logits_cache = None  # log(p/(1-p)) is built lazily: nothing on the hot path reads it
+            self._from_logits = None
         else:
             _logits = torch.as_tensor(logits, dtype=dtype)
             assert_same_log_float_dtype([(_logits, "Bernoulli.logits")])
             self._logits_cache = torch.as_tensor(logits).to(device)
-            self._probs = torch.sigmoid(_logits).to(device)
-        dtype = assert_same_log_float_dtype([(self._probs, "Bernoulli.probs")])
+            self._from_logits = _logits.to(device)  # what the kernels read; sigmoid happens in registers
+            self._probs = None
+        dtype = assert_same_log_float_dtype([(self._from_logits if self._probs is None else self._probs,
+                                              "Bernoulli.probs")])
         super(Bernoulli, self).__init__(dtype, is_continuous, is_reparameterized=False, group_ndims=group_ndims,
                                         device=device, **kwargs)
 
     @property
     def probs(self):
+        if self._probs is None:
+            self._probs = torch.sigmoid(self._from_logits)
         return self._probs
+
+    @property
+    def from_logits(self):
+        """The logits tensor when the distribution was built from logits (the kernels' operand), else None."""
+        return self._from_logits
 
     @property
     def logits(self):
@@ -46,18 +61,20 @@ class Bernoulli(Distribution):
         return self._logits_cache
 
     def _batch_shape(self):
-        return self._probs.shape
+        return (self._from_logits if self._probs is None else self._probs).shape
 
     def _sample(self, n_samples=1, **kwargs):
-        s = _ops.bernoulli_sample(self._probs, n_samples)
+        s = _ops.bernoulli_sample(self.probs, n_samples)
         self.sample_cache = s
         return s
 
     def _log_prob_event(self, given, n_event):
+        if self._from_logits is not None:
+            return _ops.bernoulli_log_prob(self._given(given), self._from_logits, n_event, logits=True)
         return _ops.bernoulli_log_prob(self._given(given), self._probs, n_event)
 
     def _log_prob(self, sample=None):
-        return _ops.bernoulli_log_prob(self._given(sample), self._probs, 0)
+        return self._log_prob_event(sample, 0)
 
     def _prob(self, given):
         return torch.exp(self._log_prob(given))

@@ -61,11 +61,12 @@ class ImportanceWeightedObjective(nn.Module):
         from zhusuan import variational as _v
         if not _v.FUSED or self._axis != 0:
             return None
-        best = None
+        best, best_numel = None, 0
         for name, node in nodes_p.items():
             if not isinstance(node, StochasticTensor) or not isinstance(node.dist, Bernoulli):
                 continue
-            probs = node.dist.probs
+            logits = node.dist.from_logits
+            probs = node.dist.probs if logits is None else logits  # the kernel's [K,B,X] operand
             x = node._observed_value()
             if x is None or not torch.is_tensor(x) or probs.dim() != 3:
                 continue
@@ -76,15 +77,21 @@ class ImportanceWeightedObjective(nn.Module):
             n_event, mean_dims, sum_dims = node.reduction_plan(x.shape)
             if n_event != 1 or mean_dims or sum_dims:
                 continue
-            if not _be.fused_supported(int(probs.shape[0]), int(probs.shape[2]), probs.dtype):
+            if logits is not None:
+                # the logits form exists on the device-resident route, for the instantiated row lengths
+                if not _be.on_compute_device(probs) or not _be.fused_logits_supported(
+                        int(probs.shape[0]), int(probs.shape[2]), probs.dtype):
+                    continue
+            elif not _be.fused_supported(int(probs.shape[0]), int(probs.shape[2]), probs.dtype):
                 continue
-            if best is None or probs.numel() > nodes_p[best].dist.probs.numel():
-                best = name
+            if best is None or probs.numel() > best_numel:
+                best, best_numel = name, probs.numel()
         return best
 
     def _forward_fused(self, nodes_p, nodes_q, lik):
         node = nodes_p[lik]
-        probs = node.dist.probs
+        logits = node.dist.from_logits
+        probs = node.dist.probs if logits is None else logits
         K, B = int(probs.shape[0]), int(probs.shape[1])
         x = node._observed_value()
         node.dist.sample_cache = x
@@ -120,7 +127,7 @@ class ImportanceWeightedObjective(nn.Module):
             return _ops.iw_bernoulli_fused_host(probs, x.to(dev), logp_other, logq, est)
         lo = None if logp_other is None else logp_other.to(dev, probs.dtype)
         lq = None if logq is None else logq.to(dev, probs.dtype)
-        return _ops.iw_bernoulli_fused(probs, x.to(dev), lo, lq, est)
+        return _ops.iw_bernoulli_fused(probs, x.to(dev), lo, lq, est, logits=logits is not None)
 
     # -- reference protocol ---------------------------------------------------------------------
     def forward(self, observed, reduce_mean=True):
