@@ -185,6 +185,17 @@ int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlo
 /* buf[n] *= *scale_dev, a no-op launch when *scale_dev == 1: applies the upstream gradient of the
  * scalar loss to gradients the fused kernels computed for a unit upstream gradient.          */
 int zs_scale_inplace(int dtype, void* buf, int64_t n, const void* scale_dev, zs_stream_t stream);
+/* ELBO.reinforce (zhusuan/variational/elbo.py:163-238), the form the examples use: variance reduction with the
+ * moving-mean baseline, no user baseline, mean over all N = prod(shape) elements.  One launch of one 8-CTA
+ * thread-block cluster: bc = mean(logp - logq); the float32 state is updated IN PLACE on the device exactly as the
+ * reference does (:221-224): mm -= (mm - bc)(1 - decay); ++step; mm /= 1 - decay^step; then
+ * cost[0] = -mean(logp + (logp - logq - mm) logq), dlogp = -grad_scale, dlogq = -(logp - logq - mm) grad_scale
+ * (pass grad_scale = 1/N).  moving_mean [1] float32 and local_step [1] int32 are DEVICE buffers (the module's
+ * registered buffers); dlogp / dlogq may be NULL.                                                          */
+int zs_reinforce_step(int dtype, void* cost, void* dlogp, void* dlogq, float* moving_mean, int* local_step,
+                      const void* logp, const void* logq, int64_t N, double decay, double grad_scale,
+                      zs_stream_t stream);
+
 /* log_mean_exp over the leading axis of [K,B] -> [B]   (zhusuan/utils.py:6-21)    */
 int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, zs_stream_t stream);
 /* backward: dx[K,B] = g[B] * softmax_k(x)                                          */

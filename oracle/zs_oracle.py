@@ -258,6 +258,23 @@ def iw_bernoulli_step(estimator, probs, x, logp_other, logq, grad_scale=None, ne
     return dict(cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx)
 
 
+def reinforce_step(logp, logq, moving_mean, local_step, decay=0.8, grad_scale=None):
+    """ELBO.reinforce with the moving-mean baseline (elbo.py:200-238).  Returns (cost, dlogp, dlogq,
+    new moving_mean (float32), new local_step)."""
+    dt = np.result_type(logp, logq).type
+    shape = np.shape(logp)
+    logp, logq = _c(logp, dt).reshape(-1), _c(logq, dt).reshape(-1)
+    n = logp.size
+    gs = (1.0 / n) if grad_scale is None else grad_scale
+    cost, dlp, dlq = np.empty(1, dt), np.empty(n, dt), np.empty(n, dt)
+    mm = np.array([moving_mean], np.float32).reshape(1)
+    ls = np.array([local_step], np.int32).reshape(1)
+    gs_c = ctypes.c_float(gs) if dt == np.float32 else ctypes.c_double(gs)
+    _call("orc_reinforce_step", dt, _p(cost), _p(dlp), _p(dlq), _p(mm), _p(ls), _p(logp), _p(logq), _i64(n),
+          ctypes.c_double(decay), gs_c)
+    return cost[0], dlp.reshape(shape), dlq.reshape(shape), mm[0], int(ls[0])
+
+
 # --------------------------------------------------------------------------- SG-MCMC (in place on copies)
 def sgld_step(w, g, noise, lr):
     dt = w.dtype.type

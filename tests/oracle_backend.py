@@ -112,6 +112,14 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
                 logpx=_t(r["logpx"], probs) if want_logpx else None)
 
 
+def reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=True):
+    cost, dlp, dlq, mm, ls = O.reinforce_step(_np(logp), _np(logq), float(moving_mean), int(local_step), decay)
+    moving_mean.fill_(float(mm))
+    local_step.fill_(int(ls))
+    return (torch.tensor([cost], dtype=logq.dtype), _t(dlp, logq) if need_grads else None,
+            _t(dlq, logq) if need_grads else None)
+
+
 def scale_inplace(buf, scale_dev):
     if float(scale_dev) != 1.0:
         buf.mul_(scale_dev)
@@ -169,7 +177,7 @@ def install(monkeypatch):
     for name in ("normal_sample", "normal_sample_bwd", "normal_logprob_fwd", "normal_logprob_bwd", "bernoulli_sample",
                  "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "categorical_sample", "categorical_logpmf_fwd",
                  "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
-                 "iw_bernoulli_fused", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
+                 "iw_bernoulli_fused", "reinforce_step", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
                  "sghmc_post"):
         monkeypatch.setattr(_backend, name, globals()[name])
     monkeypatch.setattr(_backend, "require_cuda", lambda: None)

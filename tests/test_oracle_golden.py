@@ -211,6 +211,21 @@ def test_iw_logits_path_composite(oracle, golden, est, latent, dn):
     close(r["dprobs"], g[p + "dlogits"], dn, 30)
 
 
+def test_reinforce_steps(oracle, golden):
+    """ELBO.reinforce over three consecutive calls: cost, gradients and the in-place moving-mean state
+    (tests/golden/make_golden.py:gen_reinforce, reference elbo.py:200-238)."""
+    g = golden("reinforce")
+    mm, ls = 0.0, 0
+    for step in range(3):
+        p = "f32_s%d_" % step
+        cost, dlp, dlq, mm, ls = oracle.reinforce_step(g[p + "logp"], g[p + "logq"], mm, ls, 0.8)
+        close(cost, g[p + "loss"], F32)
+        close(dlp, g[p + "dlogp"], F32)
+        close(dlq, g[p + "dlogq"], F32, 30)
+        close(mm, g[p + "moving_mean"], F32)
+        assert ls == int(np.asarray(g[p + "local_step"]).reshape(-1)[0])
+
+
 def _replay_sgmcmc(oracle, g, name):
     """Re-run the reference trajectory with the oracle's single-step updates and the recorded noise."""
     n, steps = int(g["n"]), int(g["steps"])

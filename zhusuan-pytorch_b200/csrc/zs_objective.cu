@@ -16,6 +16,8 @@
 // reference's fp32 result.
 #include "zs_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace zs {
 
 constexpr int OBJ_THREADS = 256;
@@ -224,6 +226,86 @@ static void column_geometry(int64_t B, int& cols, int& slices) {
     slices = OBJ_THREADS / cols;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ELBO.reinforce (zhusuan/variational/elbo.py:163-238), the common form: variance reduction with the moving-mean
+// baseline, no user baseline, mean over all axes.  The reference runs ~15 aten kernels and keeps the state on the
+// host; here ONE launch of ONE thread-block cluster (8 CTAs, distributed shared memory) does
+//   s_i = logp_i - logq_i ;  bc = mean_i s_i                                      (:206-219)
+//   mm <- mm - (mm - bc)(1 - decay) ; step <- step + 1 ; mm <- mm / (1 - decay^step)   (:221-224, float32 state,
+//                                                                             bias-corrected IN PLACE as the reference)
+//   sig_i = s_i - mm ;  cost = -mean_i( logp_i + sig_i logq_i )                   (:225-238)
+//   dlogp_i = -gscale ;  dlogq_i = -sig_i gscale                                  (autograd of the surrogate)
+// The [N] arrays are small ([K,B], 0.2 MB at config 2): the kernel is latency-bound by design, the cluster only
+// keeps the two passes and both reductions inside one launch.  Reductions are fixed-order (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int RF_CLUSTER = 8;
+constexpr int RF_THREADS = 512;
+
+__device__ __forceinline__ double rf_block_sum(double v, double* s_warp) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();  // s_warp may still be read from the previous reduction
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < RF_THREADS / 32; ++w) t += s_warp[w];  // fixed order, every thread
+    return t;
+}
+
+template <typename T>
+__global__ void __cluster_dims__(RF_CLUSTER, 1, 1) __launch_bounds__(RF_THREADS)
+    k_reinforce(T* __restrict__ cost, T* __restrict__ dlogp, T* __restrict__ dlogq, float* __restrict__ moving_mean,
+                int* __restrict__ local_step, const T* __restrict__ logp, const T* __restrict__ logq, int64_t N,
+                float decay, T gscale) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_warp[RF_THREADS / 32];
+    __shared__ double s_part[2];  // [0]: sum of s over this CTA's slice, [1]: sum of the surrogate terms
+    const unsigned rank = cluster.block_rank();
+    const int64_t per = (N + RF_CLUSTER - 1) / RF_CLUSTER;
+    const int64_t lo = (int64_t)rank * per, hi = (lo + per < N) ? lo + per : N;
+    // the state is read by every CTA before CTA 0 overwrites it (ordered by the first cluster barrier)
+    const float mm_old = *moving_mean;
+    const int step = *local_step + 1;
+
+    double acc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RF_THREADS) acc += (double)logp[i] - (double)logq[i];
+    acc = rf_block_sum(acc, s_warp);
+    if (threadIdx.x == 0) s_part[0] = acc;
+    cluster.sync();
+    double total = 0.0;
+    for (unsigned r = 0; r < RF_CLUSTER; ++r) total += *cluster.map_shared_rank(&s_part[0], r);
+    const T bc = (T)(total / (double)N);
+    // float32 state arithmetic, in the reference's operation order
+    float mm;
+    if (sizeof(T) == 4) mm = mm_old - (mm_old - (float)bc) * (float)(1.0 - (double)decay);
+    else mm = (float)((double)mm_old - ((double)mm_old - (double)bc) * (1.0 - (double)decay));
+    const float bias = 1.0f - powf(decay, (float)step);
+    mm = mm / bias;
+    if (rank == 0 && threadIdx.x == 0) {
+        *moving_mean = mm;
+        *local_step = step;
+    }
+
+    double cacc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RF_THREADS) {
+        const T lp = logp[i], lq = logq[i];
+        const T sig = (lp - lq) - (T)mm;
+        cacc += (double)(lp + sig * lq);
+        if (dlogp) dlogp[i] = -gscale;
+        if (dlogq) dlogq[i] = -sig * gscale;
+    }
+    cacc = rf_block_sum(cacc, s_warp);
+    if (threadIdx.x == 0) s_part[1] = cacc;
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+        double c = 0.0;
+        for (unsigned r = 0; r < RF_CLUSTER; ++r) c += *cluster.map_shared_rank(&s_part[1], r);
+        *cost = (T)(-(c / (double)N));
+    }
+    cluster.sync();  // no CTA may exit while CTA 0 still reads its shared memory
+}
+
 }  // namespace zs
 
 using namespace zs;
@@ -338,6 +420,24 @@ int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64
                         zs_stream_t stream) {
     ZS_REQUIRE(g != nullptr, ZS_ERR_ARG);
     return lme_launch(dtype, true, dx, g, x, K, B, stream);
+}
+
+int zs_reinforce_step(int dtype, void* cost, void* dlogp, void* dlogq, float* moving_mean, int* local_step,
+                      const void* logp, const void* logq, int64_t N, double decay, double grad_scale,
+                      zs_stream_t stream) {
+    ZS_REQUIRE(cost && moving_mean && local_step && logp && logq && N >= 1, ZS_ERR_ARG);
+    if (dtype == ZS_F32)
+        k_reinforce<float><<<RF_CLUSTER, RF_THREADS, 0, as_stream(stream)>>>(
+            (float*)cost, (float*)dlogp, (float*)dlogq, moving_mean, local_step, (const float*)logp, (const float*)logq, N,
+            (float)decay, (float)grad_scale);
+    else if (dtype == ZS_F64)
+        k_reinforce<double><<<RF_CLUSTER, RF_THREADS, 0, as_stream(stream)>>>(
+            (double*)cost, (double*)dlogp, (double*)dlogq, moving_mean, local_step, (const double*)logp,
+            (const double*)logq, N, (float)decay, grad_scale);
+    else
+        return ZS_ERR_DTYPE;
+    ZS_LAUNCH_CHECK("k_reinforce");
+    return ZS_OK;
 }
 
 }  // extern "C"

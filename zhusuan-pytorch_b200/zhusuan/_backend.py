@@ -65,6 +65,7 @@ def _declare(lib):
         "zs_psgld_step": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, u64, u64, vp]),
         "zs_sghmc_pre": (i32, [i32, vp, vp, vp, vp, i64, dbl, i32, i32, u64, u64, vp]),
         "zs_sghmc_post": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, i32, u64, u64, vp]),
+        "zs_reinforce_step": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, vp]),
         "zs_iw_step_host_workspace": (i64, [i64, i64, i64]),
         "zs_iw_step_host": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp, i64, vp]),
         "zs_iw_step_host_begin": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp, i64, i32, vp]),
@@ -423,6 +424,25 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
     check(rc, "zs_iw_bernoulli_fused")
     _count()
     return dict(cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx)
+
+
+def reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=True):
+    """ELBO.reinforce with the moving-mean baseline in one launch (zs_reinforce_step).  logp / logq: same-shaped
+    contiguous CUDA tensors; moving_mean [1] float32 and local_step [1] int32 CUDA buffers, updated in place.
+    Returns (cost [1], dlogp, dlogq) with the gradients of the mean surrogate."""
+    dt = logq.dtype
+    _chk_tensor(logp, "logp", dt)
+    _chk_tensor(logq, "logq", dt)
+    _chk_tensor(moving_mean, "moving_mean", torch.float32)
+    _chk_tensor(local_step, "local_step", torch.int32)
+    n = logq.numel()
+    cost = torch.empty(1, dtype=dt, device=logq.device)
+    dlp = torch.empty_like(logq) if need_grads else None
+    dlq = torch.empty_like(logq) if need_grads else None
+    check(load().zs_reinforce_step(dtype_code(dt), _ptr(cost), _ptr(dlp), _ptr(dlq), _ptr(moving_mean), _ptr(local_step),
+                                   _ptr(logp), _ptr(logq), n, float(decay), 1.0 / n, _stream()), "zs_reinforce_step")
+    _count()
+    return cost, dlp, dlq
 
 
 # ----------------------------------------------------------------------------- SG-MCMC

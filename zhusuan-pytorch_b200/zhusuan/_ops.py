@@ -394,6 +394,40 @@ def iw_objective(logp, logq, axis, estimator, reduce_mean):
     return back_home(out, home)
 
 
+class _Reinforce(torch.autograd.Function):
+    """ELBO.reinforce, moving-mean baseline, mean over all elements: surrogate cost, both gradients and the in-place
+    update of the float32 state in ONE launch (elbo.py:200-238)."""
+
+    @staticmethod
+    def forward(ctx, logp, logq, moving_mean, local_step, decay):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        cost, dlp, dlq = be.reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=need)
+        ctx.save_for_backward(dlp, dlq)
+        return cost.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dlp, dlq = ctx.saved_tensors
+        return (dlp * g if ctx.needs_input_grad[0] else None, dlq * g if ctx.needs_input_grad[1] else None, None, None,
+                None)
+
+
+def reinforce(logp, logq, moving_mean, local_step, decay):
+    """logp / logq broadcastable tensors; moving_mean [1] float32 / local_step [1] int32 module buffers (any device:
+    they are moved to the compute device for the launch and written back)."""
+    home = logq.device
+    lp, lq = torch.broadcast_tensors(to_compute(logp), to_compute(logq))
+    lp, lq = lp.contiguous(), lq.contiguous()
+    mm = moving_mean if be.on_compute_device(moving_mean) else to_compute(moving_mean.detach()).clone()
+    ls = local_step if be.on_compute_device(local_step) else to_compute(local_step.detach()).clone()
+    out = _Reinforce.apply(lp, lq, mm, ls, float(decay))
+    if mm is not moving_mean:
+        with torch.no_grad():
+            moving_mean.copy_(mm)
+            local_step.copy_(ls)
+    return back_home(out, home)
+
+
 class _LogMeanExp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -85,8 +85,14 @@ class ELBO(nn.Module):
     def reinforce(self, logpxz, logqz, reduce_mean=True, baseline=None, variance_reduction=True, decay=0.8):
         """Score-function estimator with a moving-mean baseline (:163-238).  The stored moving mean is
         bias-corrected in place every call, exactly as the reference does (:221-224)."""
-        signal = (logpxz - logqz).detach()
         reduce = torch.is_tensor(logqz) and logqz.dim() > 0 and reduce_mean
+        if (reduce and variance_reduction and baseline is None and torch.is_tensor(logpxz)
+                and logpxz.dtype == logqz.dtype and logqz.dtype in (torch.float32, torch.float64)
+                and logqz.numel() > 0):
+            # the form the examples use: one kernel for the signal, the moving-mean update (in place, on the
+            # device), the surrogate and both gradients
+            return _ops.reinforce(logpxz, logqz, self.moving_mean, self.local_step, decay)
+        signal = (logpxz - logqz).detach()
         baseline_cost = None
         if variance_reduction:
             if baseline is not None:
