@@ -229,6 +229,9 @@ class PathStep(object):
             self.dz_up = (1e-3 * rn(K, B, Z)).contiguous()
         self.launches_per_step = 0
         self.out = None
+        # data-parallel runs: the per-column objectives of successive steps are summed in place by the fused launch
+        # (zs_iw_bernoulli_fused_accumulate) and reduced once per bucket of steps, not once per step
+        self.cost_sum = None
 
     def algorithmic_bytes(self):
         """Compulsory HBM bytes of one step with the fused design."""
@@ -250,18 +253,21 @@ class PathStep(object):
         self.offset += 4
         if self.vimco:
             z, logq, logpz = be.bernoulli_latent_fwd(self.pq, be.KBCAST, K, B, Z, seed=self.seed, offset=self.offset)
-            r = be.iw_bernoulli_fused(be.VIMCO, self.probs, self.x, logpz, logq, 1.0 / B)
+            r = be.iw_bernoulli_fused(be.VIMCO, self.probs, self.x, logpz, logq, 1.0 / B, **self._acc())
             dpq = be.bernoulli_latent_bwd(r["dlogq"], z, self.pq, be.KBCAST, K, B, Z)
             self.out = (r["cost"], r["dprobs"], dpq)
         else:
             z, logq, logpz = be.normal_latent_fwd(self.mean, self.std, be.KBCAST, K, B, Z, seed=self.seed,
                                                   offset=self.offset)
-            r = be.iw_bernoulli_fused(be.SGVB, self.probs, self.x, logpz, logq, 1.0 / B)
+            r = be.iw_bernoulli_fused(be.SGVB, self.probs, self.x, logpz, logq, 1.0 / B, **self._acc())
             dm, ds = be.normal_latent_bwd(r["dlogq"], r["dlogp"], self.dz_up, z, self.mean, self.std, be.KBCAST, K, B,
                                           Z, reparameterized=True)
             self.out = (r["cost"], r["dprobs"], dm, ds)
         self.launches_per_step = be.launch_count - n0
         return self.out
+
+    def _acc(self):
+        return {} if self.cost_sum is None else dict(out={"cost": self.cost_sum}, accumulate_cost=True)
 
     def fused_only(self, other, logq, out=None):
         return self.be.iw_bernoulli_fused(self.be.VIMCO if self.vimco else self.be.SGVB, self.probs, self.x, other,
@@ -331,6 +337,8 @@ def run_b200_arm(args):
     vimco = args.workload == "vimco"
     ps = PathStep(torch, be, vimco, dev, seed=1234 + rank)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    if world > 1:
+        ps.cost_sum = torch.zeros(B_COLS, device=dev)
 
     def barrier():
         if world > 1:
@@ -357,12 +365,13 @@ def run_b200_arm(args):
             graph = None
             sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))
 
-    # The only cross-rank exchange of this path is the scalar objective.  Per-step losses are kept in a
-    # device ring and all-reduced LOSS_BUCKET at a time on a side stream (collectives sized for launch
-    # latency, not per step), overlapping the following steps.
+    # The only cross-rank exchange of this path is the scalar objective.  The fused launch adds each step's
+    # per-column objectives into ps.cost_sum; once per LOSS_BUCKET steps the sum is snapshotted (two tiny launches on
+    # the compute stream), then reduced and all-reduced on a side stream while the following steps run: collectives
+    # sized for launch latency, nothing per step.
     LOSS_BUCKET = 32
-    loss_ring = torch.zeros(LOSS_BUCKET, device=dev)
-    reduced = torch.zeros(LOSS_BUCKET, device=dev)
+    snap = torch.zeros(B_COLS, device=dev)
+    reduced = torch.zeros(1, device=dev)
     state = {"i": 0}
 
     def one_step():
@@ -371,15 +380,17 @@ def run_b200_arm(args):
         else:
             ps.step()
         if world > 1:
-            j = state["i"] % LOSS_BUCKET
-            torch.mean(ps.out[0], dim=0, out=loss_ring[j])
             state["i"] += 1
-            if j == LOSS_BUCKET - 1:
+            if state["i"] % LOSS_BUCKET == 0:
+                torch.cuda.current_stream().wait_stream(comm_stream)  # the previous bucket's reduction read `snap`
+                snap.copy_(ps.cost_sum)
+                ps.cost_sum.zero_()
                 ev = torch.cuda.Event()
                 ev.record()
                 comm_stream.wait_event(ev)
                 with torch.cuda.stream(comm_stream):
-                    reduced.copy_(loss_ring)
+                    torch.sum(snap, dim=0, keepdim=True, out=reduced)
+                    reduced.mul_(1.0 / (LOSS_BUCKET * B_COLS * world))
                     dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
 
     clocks = ClockSampler(local)
@@ -412,10 +423,12 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
             t_clock_end = time.perf_counter()
         clocks.stop()
+    ms_by_rank = [ms]
     if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt)
+        allms = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], device=dev))
+        ms_by_rank = [float(t) for t in allms]
+        ms = max(ms_by_rank)
     ms_per_step = ms / args.steps
     value = world * K_PART * B_COLS / (ms_per_step * 1e-3)
 
@@ -478,7 +491,8 @@ def run_b200_arm(args):
                    "estimator": "vimco" if vimco else "sgvb", "parallelism": "batch columns sharded x%d" % world,
                    "l2": "inputs+outputs of a step (%.0f MB) exceed the 126 MB L2; no explicit flush" % (step_bytes / 1e6),
                    "launch": "cuda-graph replay" if graph is not None else "eager launches",
-                   "timed_wall_s": t_end - t_start},
+                   "timed_wall_s": t_end - t_start,
+                   "ms_per_step_by_rank": [round(v / args.steps, 6) for v in ms_by_rank]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_iw_bernoulli_boxf (zs_iw_bernoulli_fused)", "kernel_ms": fused_ms,
                      "algorithmic_bytes_per_launch": fused_bytes, "peak_kind": peak_kind + " (MEASURED_PEAKS.json)"

@@ -220,6 +220,14 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
                           zs_stream_t stream);
+/* The same launch with cost_sum[b] += cost_b instead of cost[b] = cost_b: a running sum of the per-column
+ * objectives over steps.  A data-parallel training loop reports its scalar objective from this buffer every N steps
+ * (one reduction + one all-reduce per N steps instead of per step; each column has exactly one writer, so the sum
+ * is deterministic).  ZS_ERR_UNSUPPORTED for shapes only the two-pass kernels take.                        */
+int zs_iw_bernoulli_fused_accumulate(int estimator, float* cost_sum, float* dprobs, float* dlogp, float* dlogq,
+                                     float* logpx_out, const float* probs, const float* x, const float* logp_other,
+                                     const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                                     zs_stream_t stream);
 /* The same launch for a likelihood given by LOGITS [K,B,X] (Bernoulli(logits=...), bernoulli.py:47-50): the
  * sigmoid is applied as the rows arrive in shared memory and its derivative is chained into the result, so
  * `dlogits` is the gradient w.r.t. the decoder's pre-activations.  Available where a fixed-geometry kernel is

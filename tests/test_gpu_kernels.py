@@ -462,6 +462,21 @@ def test_fused_invalid_probs_give_nan(monkeypatch, impl, bad, where):
     assert np.isnan(lp[k, b]) and np.isfinite(np.delete(lp.ravel(), k * B + b)).all()
 
 
+@pytest.mark.parametrize("impl", ["ring", "box", "boxg"])
+def test_fused_accumulate_cost(monkeypatch, impl):
+    """zs_iw_bernoulli_fused_accumulate: cost_sum[b] += cost_b over launches (the data-parallel loss buffer)."""
+    _set_impl(monkeypatch, impl)
+    K, B, X = 50, 333, 784
+    probs, x, other, logq = _fused_inputs(K, B, X, seed=12)
+    dp, dx, do, dq = dev(probs), dev(x), dev(other), dev(logq)
+    r = be.iw_bernoulli_fused(be.SGVB, dp, dx, do, dq, 1.0 / B)
+    acc = torch.zeros(B, device=DEV)
+    for _ in range(3):
+        r2 = be.iw_bernoulli_fused(be.SGVB, dp, dx, do, dq, 1.0 / B, out={"cost": acc}, accumulate_cost=True)
+    assert torch.equal(r2["dprobs"], r["dprobs"]) and torch.equal(r2["dlogq"], r["dlogq"])
+    torch.testing.assert_close(acc, 3 * r["cost"], rtol=1e-6, atol=0)
+
+
 def test_fused_shape_coverage(oracle):
     """X % 4 != 0 is refused (callers use the two-pass kernels); small K and columns far larger than
     shared memory are handled (the ring streams rows, it does not keep a column resident)."""

@@ -429,7 +429,8 @@ template <int EST>
 __device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
                                                const float* s_other, const float* s_lq, double* s_xw, float gscale,
                                                float* __restrict__ cost, float* __restrict__ dlogp,
-                                               float* __restrict__ dlogq, float* __restrict__ logpx_out) {
+                                               float* __restrict__ dlogq, float* __restrict__ logpx_out,
+                                               bool accumulate = false) {
     const unsigned FULL = 0xffffffffu;
     // log-weights in double; max in float (any value within an ulp of the max stabilises exp)
     float mf = -INFINITY;
@@ -502,7 +503,8 @@ __device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64
         if (logpx_out) logpx_out[(int64_t)k * B + b] = s_lpx[k];
     }
     c_acc = warp_sum(c_acc);
-    if (lane == 0 && cost) cost[b] = (float)c_acc;
+    // accumulate: running sum of the column's objective over launches (one writer per column: deterministic)
+    if (lane == 0 && cost) cost[b] = accumulate ? cost[b] + (float)c_acc : (float)c_acc;
 }
 
 // Every row warp needs only max and sum-exp of the column to weight its own rows.
@@ -861,6 +863,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
                         int stagger_groups, int stagger_cycles, long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
     stagger_start(stagger_groups & 0xff, stagger_cycles);
     const RingLayout L(K, X, R);
     const int Kpad = L.Kpad;
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
             colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
     }
@@ -1166,7 +1169,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    stagger_start(stagger_groups, stagger_cycles);
+    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
+    stagger_start(stagger_groups & 0xff, stagger_cycles);
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
@@ -1236,7 +1240,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
             colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
     }
@@ -1523,7 +1527,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    stagger_start(stagger_groups, stagger_cycles);
+    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
+    stagger_start(stagger_groups & 0xff, stagger_cycles);
     // Column 0 only: column 1 is staged while column 0 is being read.  The first tensor copies are issued AFTER
     // this staging on purpose: issuing them first (measured here and in the ring kernel: +4 and +7 us per launch)
     // starts every CTA's column 0 at the same instant, and the chip then alternates between a read-only phase A
@@ -1579,7 +1584,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);
             colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
     }
@@ -1678,6 +1683,7 @@ int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X) {
 }
 
 static long long* g_trace = nullptr;
+static thread_local bool g_accumulate_cost = false;  // set by zs_iw_bernoulli_fused_accumulate around its launch
 
 #ifndef ZS_FUSED_DEFAULT_IMPL
 #define ZS_FUSED_DEFAULT_IMPL 3
@@ -1888,7 +1894,8 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     if (fixed != nullptr) {
         ZS_CUDA_TRY(cudaFuncSetAttribute(fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fixed<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
-                                                                     logq, (int)K, B, nslot, (float)grad_scale, stg.groups,
+                                                                     logq, (int)K, B, nslot, (float)grad_scale,
+                                                                     (stg.groups & 0xff) | (g_accumulate_cost ? 0x200 : 0),
                                                                      stg.cycles, ldkb);
         ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
         return ZS_OK;
@@ -1907,7 +1914,8 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     }
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
                                                                logq, (int)K, B, (int)X, inner, nslot, l2_ahead,
-                                                               (float)grad_scale, stg.groups, stg.cycles, g_trace, ldkb);
+                                                               (float)grad_scale, (stg.groups & 0xff) | (g_accumulate_cost ? 0x200 : 0),
+                                                               stg.cycles, g_trace, ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
     return ZS_OK;
 }
@@ -1963,7 +1971,8 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     }
     kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
                                                                logp_other, logq, (int)K, B, (int)X, R,
-                                                               (float)grad_scale, (stg.groups & 0xff) | (early ? 0x100 : 0),
+                                                               (float)grad_scale,
+                                                               (stg.groups & 0xff) | (early ? 0x100 : 0) | (g_accumulate_cost ? 0x200 : 0),
                                                                stg.cycles, g_trace, ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
     return ZS_OK;
@@ -2020,11 +2029,23 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
     int rc = fused_launch_pitched(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B,
                                   grad_scale, stream);
     if (rc != ZS_ERR_UNSUPPORTED || X % 4 != 0 || K > 4096 || X > (1 << 20)) return rc;
+    if (g_accumulate_cost) return ZS_ERR_UNSUPPORTED;  // only the box / ring kernels accumulate
     if (fused_impl_choice() == 0)
         return launch_fused_smem(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                                  grad_scale, stream);
     return launch_fused_l2(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
                            grad_scale, stream);
+}
+
+int zs_iw_bernoulli_fused_accumulate(int estimator, float* cost_sum, float* dprobs, float* dlogp, float* dlogq,
+                                     float* logpx_out, const float* probs, const float* x, const float* logp_other,
+                                     const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                                     zs_stream_t stream) {
+    g_accumulate_cost = true;
+    const int rc = zs_iw_bernoulli_fused(estimator, cost_sum, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq,
+                                         K, B, X, grad_scale, stream);
+    g_accumulate_cost = false;
+    return rc;
 }
 
 /* Debug hook (not part of the stable ABI surface used by the Python package): device buffer of

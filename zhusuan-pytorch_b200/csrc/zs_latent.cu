@@ -74,7 +74,8 @@ __device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, c
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             u.logb.v[q] = Real<T>::log(u.b.v[q]);
-            u.prec.v[q] = Real<T>::exp(T(-2) * u.logb.v[q]);
+            // exp(-2 log std) of normal.py:122 is 1 / std^2 to within an ulp; the division costs a third of expf
+            u.prec.v[q] = T(1) / (u.b.v[q] * u.b.v[q]);
         }
         if (pa) u.pa = ldv4(pa + kidx);
         else u.pa = V4<T>{{T(0), T(0), T(0), T(0)}};
@@ -83,7 +84,7 @@ __device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, c
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 u.plogb.v[q] = Real<T>::log(ps.v[q]);
-                u.pprec.v[q] = Real<T>::exp(T(-2) * u.plogb.v[q]);
+                u.pprec.v[q] = T(1) / (ps.v[q] * ps.v[q]);
             }
         } else {
             // standard prior: log(1) = 0 and exp(-2*0) = 1 exactly, as the reference computes them
@@ -175,13 +176,116 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, packed rows (E/4 <= 32, the hot-path case: Z = 40 -> 10 units).  ncu on the kernel above at config 2:
+// 11.0 M warp instructions with 22 of 32 lanes active (10 of the 16 lanes of a group own a unit) and the
+// parameter transcendentals redone by 16 k-slices per row -- issue-bound at 17.5 us for 8 MB of output.  Here a warp
+// packs RW = 32 / (E/4) rows (30 of 32 lanes busy at Z = 40), row sums are segmented shuffle reductions
+// (no shared memory, fixed order), a thread keeps its unit's parameters for all its particles
+// k = ks, ks + KS, ... (gridDim.y = KS slices with equal trip counts) and works on two particles at a time so two
+// Philox / Box-Muller chains are in flight.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int FAM>
+__device__ __forceinline__ void latent_unit(const UnitParams<T>& up, const T* __restrict__ noise_in, T* __restrict__ z,
+                                            int64_t fe, uint64_t seed, uint64_t offset, T& accq, T& accp) {
+    V4<T> nz;
+    if (noise_in) {
+        nz = ldv4(noise_in + fe);
+    } else {
+        float n4[4];  // one Philox counter per float4 unit (element i: counter i/4, word i%4)
+        if (FAM == FAM_NORMAL) philox_normal4((uint64_t)(fe >> 2), offset, seed, n4);
+        else philox_uniform4((uint64_t)(fe >> 2), offset, seed, n4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nz.v[q] = (T)n4[q];
+    }
+    V4<T> zv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (FAM == FAM_NORMAL) {
+            const T zz = up.a.v[q] + up.b.v[q] * nz.v[q];  // normal.py:105
+            zv.v[q] = zz;
+            const T d = zz - up.a.v[q];                     // normal.py:121-124 at the sample
+            accq += (normal_c<T>() - up.logb.v[q]) - (T(0.5) * up.prec.v[q]) * (d * d);
+            const T dp = zz - up.pa.v[q];
+            accp += (normal_c<T>() - up.plogb.v[q]) - (T(0.5) * up.pprec.v[q]) * (dp * dp);
+        } else {
+            const T zz = nz.v[q] < up.a.v[q] ? T(1) : T(0);  // bernoulli.py:79
+            zv.v[q] = zz;
+            accq += zz * up.logb.v[q] + (T(1) - zz) * up.prec.v[q];    // bernoulli.py:94
+            accp += zz * up.plogb.v[q] + (T(1) - zz) * up.pprec.v[q];
+        }
+    }
+    stv4(z + fe, zv);
+}
+
+// sum over the E4 consecutive lanes of a row; valid in the row's first lane (j == 0)
+template <typename T>
+__device__ __forceinline__ T segment_sum(T v, int j, int E4) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T other = __shfl_down_sync(0xffffffffu, v, o);
+        if (j + o < E4) v += other;
+    }
+    return v;
+}
+
+constexpr int LF_WARPS = 4;
+
+template <typename T, int FAM>
+__global__ void __launch_bounds__(LF_WARPS * 32)
+    k_latent_fwd_packed(T* __restrict__ z, T* __restrict__ logq, T* __restrict__ logp, const T* __restrict__ a,
+                        int a_mode, const T* __restrict__ b, const T* __restrict__ pa, const T* __restrict__ pb,
+                        const T* __restrict__ noise_in, int K, int64_t M, int E4, int RW, int KS, uint64_t seed,
+                        uint64_t offset) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = lane / E4, j = lane - rl * E4;
+    const int64_t m = ((int64_t)blockIdx.x * LF_WARPS + warp) * RW + rl;
+    const bool active = rl < RW && m < M;
+    const int64_t E = 4 * (int64_t)E4, ME = M * E;
+    const bool kb = a_mode == ZS_KBCAST;
+    const int64_t pidx = m * E + 4 * j;  // the unit inside [M,E]
+    UnitParams<T> up;
+    if (active && kb) load_unit_params<T, FAM>(up, a, b, pa, pb, pidx, pidx);
+    // every slice runs the same trip count (the shuffles need the whole warp); particles past K are skipped
+    const int trips = (K + KS - 1) / KS;
+    for (int t = 0; t < trips; t += 2) {
+        const int k0 = (int)blockIdx.y + t * KS, k1 = k0 + KS;
+        const bool on0 = active && k0 < K, on1 = active && t + 1 < trips && k1 < K;
+        T q0 = T(0), p0 = T(0), q1 = T(0), p1 = T(0);
+        if (on0) {
+            const int64_t fe = (int64_t)k0 * ME + pidx;
+            if (!kb) load_unit_params<T, FAM>(up, a, b, pa, pb, fe, pidx);
+            latent_unit<T, FAM>(up, noise_in, z, fe, seed, offset, q0, p0);
+        }
+        if (on1) {
+            const int64_t fe = (int64_t)k1 * ME + pidx;
+            if (!kb) load_unit_params<T, FAM>(up, a, b, pa, pb, fe, pidx);
+            latent_unit<T, FAM>(up, noise_in, z, fe, seed, offset, q1, p1);
+        }
+        q0 = segment_sum(q0, j, E4);
+        p0 = segment_sum(p0, j, E4);
+        q1 = segment_sum(q1, j, E4);
+        p1 = segment_sum(p1, j, E4);
+        if (j == 0) {
+            if (on0) {
+                if (logq) logq[(int64_t)k0 * M + m] = q0;
+                if (logp) logp[(int64_t)k0 * M + m] = p0;
+            }
+            if (on1) {
+                if (logq) logq[(int64_t)k1 * M + m] = q1;
+                if (logp) logp[(int64_t)k1 * M + m] = p1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward: block = LB_X float4 units of [M,E] x LB_Y particle slices, fixed-order sum over slices.
 // Parameter-only terms (log std, precision, 1/std) are hoisted out of the particle loop.
 // ---------------------------------------------------------------------------------------------
 constexpr int LB_X = 16, LB_Y = 16;
 
 template <typename T, int FAM>
-__global__ void __launch_bounds__(LB_X* LB_Y)
+__global__ void __launch_bounds__(LB_X* LB_Y, 3)
     k_latent_bwd(T* __restrict__ da, T* __restrict__ db, const T* __restrict__ gq, const T* __restrict__ gp,
                  const T* __restrict__ dz_up, const T* __restrict__ z, const T* __restrict__ a, int a_mode,
                  const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
@@ -193,60 +297,95 @@ __global__ void __launch_bounds__(LB_X* LB_Y)
     V4<T> sa{{T(0), T(0), T(0), T(0)}}, sb{{T(0), T(0), T(0), T(0)}};
     if (valid) {
         const int64_t ke = 4 * u, m = ke / E;
-        UnitParams<T> up;
+        UnitParams<T> up;  // only a, b, prec, pa, pprec are used here: no logarithms on the backward path
         V4<T> rstd;
-        if (!full) {
-            load_unit_params<T, FAM>(up, a, b, pa, pb, ke, ke);
-            if (FAM == FAM_NORMAL)
+        auto load_params = [&](int64_t idx) {
+            up.a = ldv4(a + idx);
+            if (FAM == FAM_BERNOULLI) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rstd.v[q] = T(1) / up.b.v[q];
-        }
-        for (int64_t k = threadIdx.y; k < K; k += LB_Y) {
-            const int64_t r = k * M + m, fe = k * (M * E) + ke;
-            const T g_q = gq ? gq[r] : T(0), g_p = gp ? gp[r] : T(0);
-            const V4<T> zv = ldv4(z + fe);
-            V4<T> du{{T(0), T(0), T(0), T(0)}};
-            if (dz_up && reparam) du = ldv4(dz_up + fe);
-            if (full) {
-                load_unit_params<T, FAM>(up, a, b, pa, pb, fe, ke);
-                if (FAM == FAM_NORMAL)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) rstd.v[q] = T(1) / up.b.v[q];
-            }
-            V4<T> oa, ob;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (FAM == FAM_NORMAL) {
-                    // autograd of normal.py:121-124 (same association as NormalOp::grad in zs_nodes.cu)
-                    const T prec = up.prec.v[q], zz = zv.v[q];
-                    const T d = zz - up.a.v[q];
-                    const T dzq = -(g_q * (T(0.5) * prec)) * (T(2) * d);
-                    const T dprec = -(g_q * (d * d)) * T(0.5);
-                    const T dlogstd = -g_q + (dprec * prec) * T(-2);
-                    T dmean = -dzq, dstd = dlogstd * rstd.v[q];
-                    if (reparam) {
-                        const T dzp = gp ? -(g_p * (T(0.5) * up.pprec.v[q])) * (T(2) * (zz - up.pa.v[q])) : T(0);
-                        const T dzt = (du.v[q] + dzp) + dzq;  // total gradient reaching the sample
-                        dmean += dzt;                          // z = mean + std*eps
-                        dstd += dzt * (d * rstd.v[q]);         // eps recovered from the sample
-                    }
-                    oa.v[q] = dmean;
-                    ob.v[q] = dstd;
-                } else {
-                    // autograd of bernoulli.py:94 wrt probs (samples carry no gradient)
-                    const T p = up.a.v[q], zz = zv.v[q];
-                    oa.v[q] = (g_q * zz) / (p + T(1e-8)) - (g_q * (T(1) - zz)) / ((T(1) - p) + T(1e-8));
-                    ob.v[q] = T(0);
+                for (int q = 0; q < 4; ++q) {  // the two reciprocals of bernoulli.py:94's autograd, once per unit
+                    up.logb.v[q] = T(1) / (up.a.v[q] + T(1e-8));
+                    up.prec.v[q] = T(1) / ((T(1) - up.a.v[q]) + T(1e-8));
                 }
             }
-            if (full) {
-                if (da) stv4(da + fe, oa);
-                if (db && FAM == FAM_NORMAL) stv4(db + fe, ob);
-            } else {
+            if (FAM == FAM_NORMAL) {
+                up.b = ldv4(b + idx);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    sa.v[q] += oa.v[q];
-                    sb.v[q] += ob.v[q];
+                    rstd.v[q] = T(1) / up.b.v[q];
+                    up.prec.v[q] = rstd.v[q] * rstd.v[q];  // exp(-2 log std) of normal.py:122
+                }
+                if (pa) up.pa = ldv4(pa + ke);
+                else up.pa = V4<T>{{T(0), T(0), T(0), T(0)}};
+                if (pb) {
+                    const V4<T> ps = ldv4(pb + ke);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) up.pprec.v[q] = T(1) / (ps.v[q] * ps.v[q]);
+                } else {
+                    up.pprec = V4<T>{{T(1), T(1), T(1), T(1)}};
+                }
+            }
+        };
+        if (!full) load_params(ke);
+        // particles k = y, y + LB_Y, ...: the loads of up to LBU of them are issued together (the kernel was
+        // latency-bound with one particle's loads in flight per thread)
+        constexpr int LBU = 2;
+        for (int64_t k0 = threadIdx.y; k0 < K; k0 += LBU * LB_Y) {
+            T g_q[LBU], g_p[LBU];
+            V4<T> zv[LBU], du[LBU];
+#pragma unroll
+            for (int i = 0; i < LBU; ++i) {
+                const int64_t k = k0 + (int64_t)i * LB_Y;
+                const bool on = k < K;
+                const int64_t kc = on ? k : k0;
+                const int64_t r = kc * M + m, fe = kc * (M * E) + ke;
+                g_q[i] = gq ? gq[r] : T(0);
+                g_p[i] = gp ? gp[r] : T(0);
+                zv[i] = ldv4(z + fe);
+                if (dz_up && reparam) du[i] = ldv4(dz_up + fe);
+                else du[i] = V4<T>{{T(0), T(0), T(0), T(0)}};
+            }
+#pragma unroll
+            for (int i = 0; i < LBU; ++i) {
+                const int64_t k = k0 + (int64_t)i * LB_Y;
+                if (k >= K) break;
+                const int64_t fe = k * (M * E) + ke;
+                if (full) load_params(fe);
+                V4<T> oa, ob;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (FAM == FAM_NORMAL) {
+                        // autograd of normal.py:121-124 (same association as NormalOp::grad in zs_nodes.cu)
+                        const T prec = up.prec.v[q], zz = zv[i].v[q];
+                        const T d = zz - up.a.v[q];
+                        const T dzq = -(g_q[i] * (T(0.5) * prec)) * (T(2) * d);
+                        const T dprec = -(g_q[i] * (d * d)) * T(0.5);
+                        const T dlogstd = -g_q[i] + (dprec * prec) * T(-2);
+                        T dmean = -dzq, dstd = dlogstd * rstd.v[q];
+                        if (reparam) {
+                            const T dzp = gp ? -(g_p[i] * (T(0.5) * up.pprec.v[q])) * (T(2) * (zz - up.pa.v[q])) : T(0);
+                            const T dzt = (du[i].v[q] + dzp) + dzq;  // total gradient reaching the sample
+                            dmean += dzt;                            // z = mean + std*eps
+                            dstd += dzt * (d * rstd.v[q]);           // eps recovered from the sample
+                        }
+                        oa.v[q] = dmean;
+                        ob.v[q] = dstd;
+                    } else {
+                        // autograd of bernoulli.py:94 wrt probs (samples carry no gradient)
+                        const T zz = zv[i].v[q];
+                        oa.v[q] = (g_q[i] * zz) * up.logb.v[q] - (g_q[i] * (T(1) - zz)) * up.prec.v[q];
+                        ob.v[q] = T(0);
+                    }
+                }
+                if (full) {
+                    if (da) stv4(da + fe, oa);
+                    if (db && FAM == FAM_NORMAL) stv4(db + fe, ob);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sa.v[q] += oa.v[q];
+                        sb.v[q] += ob.v[q];
+                    }
                 }
             }
         }
@@ -278,6 +417,24 @@ static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, con
                              const T* pb, const T* noise_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
                              uint64_t offset, cudaStream_t st) {
     const int64_t E4 = E >> 2;
+    if (E4 <= 32 && K < ((int64_t)1 << 30)) {
+        const int RW = (int)(32 / E4);
+        const int64_t row_warps = (M + RW - 1) / RW;
+        const int64_t gx = (row_warps + LF_WARPS - 1) / LF_WARPS;
+        // k-slices: ~24 warps per SM, then equal trip counts per slice
+        int64_t KS = ((int64_t)sm_count() * 24 + row_warps - 1) / row_warps;
+        if (KS > K) KS = K;
+        if (KS > 64) KS = 64;
+        if (KS < 1) KS = 1;
+        const int64_t trips = (K + KS - 1) / KS;
+        KS = (K + trips - 1) / trips;
+        ZS_REQUIRE(gx < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+        dim3 grid((unsigned)gx, (unsigned)KS);
+        k_latent_fwd_packed<T, FAM><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, (int)K, M,
+                                                                    (int)E4, RW, (int)KS, seed, offset);
+        ZS_LAUNCH_CHECK("k_latent_fwd_packed");
+        return ZS_OK;
+    }
     // k-slices per batch row: enough groups to fill the machine, each slice reusing its parameters
 #define ZS_LATENT_FWD(G)                                                                                          \
     {                                                                                                             \

@@ -59,6 +59,7 @@ def _declare(lib):
         "zs_iw_bernoulli_fused_smem_bytes": (i64, [i64, i64]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
         "zs_iw_bernoulli_fused_logits": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
+        "zs_iw_bernoulli_fused_accumulate": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, vp]),
         "zs_scale_inplace": (i32, [i32, vp, i64, vp, vp]),
         "zs_debug_set_trace": (i32, [vp]),
         "zs_sgld_step": (i32, [i32, vp, vp, vp, vp, i64, dbl, u64, u64, vp]),
@@ -402,9 +403,10 @@ def fused_logits_supported(K, X, dtype):
 
 
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False,
-                       out=None, logits=False):
+                       out=None, logits=False, accumulate_cost=False):
     """probs [K,B,X], x [B,X], logp_other/logq [K,B] or None.  `logits=True`: `probs` holds logits and "dprobs" is
-    the gradient w.r.t. them (zs_iw_bernoulli_fused_logits).
+    the gradient w.r.t. them (zs_iw_bernoulli_fused_logits).  `accumulate_cost=True` (needs out["cost"]): the
+    per-column objectives are ADDED to out["cost"] (zs_iw_bernoulli_fused_accumulate).
     Returns dict(cost[B], dprobs, dlogp, dlogq, logpx) or None when the shape is not supported."""
     for t, n in ((probs, "probs"), (x, "x"), (logp_other, "logp_other"), (logq, "logq")):
         _chk_tensor(t, n, torch.float32)
@@ -416,7 +418,8 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
     dlp = o.get("dlogp") if "dlogp" in o else torch.empty((K, B), dtype=torch.float32, device=dev)
     dlq = o.get("dlogq") if "dlogq" in o else torch.empty((K, B), dtype=torch.float32, device=dev)
     lpx = (o.get("logpx") if "logpx" in o else torch.empty((K, B), dtype=torch.float32, device=dev)) if want_logpx else None
-    fn = load().zs_iw_bernoulli_fused_logits if logits else load().zs_iw_bernoulli_fused
+    fn = load().zs_iw_bernoulli_fused_logits if logits else (
+        load().zs_iw_bernoulli_fused_accumulate if accumulate_cost else load().zs_iw_bernoulli_fused)
     rc = fn(estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx), _ptr(probs), _ptr(x), _ptr(logp_other),
             _ptr(logq), K, B, X, float(grad_scale), _stream())
     if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
