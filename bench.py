@@ -336,7 +336,6 @@ def run_b200_arm(args):
     be.load()
     vimco = args.workload == "vimco"
     ps = PathStep(torch, be, vimco, dev, seed=1234 + rank)
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     if world > 1:
         ps.cost_sum = torch.zeros(B_COLS, device=dev)
 
@@ -366,11 +365,12 @@ def run_b200_arm(args):
             sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))
 
     # The only cross-rank exchange of this path is the scalar objective.  The fused launch adds each step's
-    # per-column objectives into ps.cost_sum; once per LOSS_BUCKET steps the sum is snapshotted (two tiny launches on
-    # the compute stream), then reduced and all-reduced on a side stream while the following steps run: collectives
-    # sized for launch latency, nothing per step.
-    LOSS_BUCKET = 32
-    snap = torch.zeros(B_COLS, device=dev)
+    # per-column objectives into ps.cost_sum; once per LOSS_BUCKET steps (the loss-reporting interval) the sum is
+    # reduced and all-reduced.  The collective is ordered IN the compute stream on purpose: measured at N=2, an
+    # NCCL kernel that overlaps the step (side stream) holds SMs while it waits for its peer, the persistent
+    # 148-CTA likelihood kernel then runs one CTA short and takes a second pass -- 11 % slower steps.  In-stream,
+    # the cost is ~30 us per bucket.
+    LOSS_BUCKET = 128
     reduced = torch.zeros(1, device=dev)
     state = {"i": 0}
 
@@ -382,16 +382,10 @@ def run_b200_arm(args):
         if world > 1:
             state["i"] += 1
             if state["i"] % LOSS_BUCKET == 0:
-                torch.cuda.current_stream().wait_stream(comm_stream)  # the previous bucket's reduction read `snap`
-                snap.copy_(ps.cost_sum)
+                torch.sum(ps.cost_sum, dim=0, keepdim=True, out=reduced)
                 ps.cost_sum.zero_()
-                ev = torch.cuda.Event()
-                ev.record()
-                comm_stream.wait_event(ev)
-                with torch.cuda.stream(comm_stream):
-                    torch.sum(snap, dim=0, keepdim=True, out=reduced)
-                    reduced.mul_(1.0 / (LOSS_BUCKET * B_COLS * world))
-                    dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
+                reduced.mul_(1.0 / (LOSS_BUCKET * B_COLS * world))
+                dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -404,8 +398,6 @@ def run_b200_arm(args):
     e0.record()
     for _ in range(args.steps):
         one_step()
-    if world > 1:
-        torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
     barrier()
     t_end = time.perf_counter()

@@ -273,7 +273,7 @@ int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g,
  * would hand to ImportanceWeightedObjective.forward + backward
  * (zhusuan/variational/importance_weighted_objective.py:79-132 with the likelihood node of
  * zhusuan/distributions/bernoulli.py:84-95).  Batch columns are independent, so the step is pipelined
- * over column chunks (32, 64, 128, ..., 128, 64, 32) on internal streams: the H2D copy of chunk c+1, the
+ * over chunks of 128 columns on internal streams: the H2D copy of chunk c+1, the
  * fused kernel (or the two-pass kernels) on chunk c and the D2H copy of chunk c-1 overlap, so the call
  * costs about max(H2D, D2H) instead of their sum.  `ws` is a caller-owned device workspace of
  * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).  The only process-wide state of the

@@ -2060,14 +2060,22 @@ int zs_debug_set_trace(void* device_buffer) {
 // streams: H2D copy of chunk c+1, fused kernel on chunk c and D2H copy of chunk c-1 overlap (PCIe is
 // full duplex), with HS_NBUF rotating device buffers.  The [K,B,X] host layout is gathered / scattered
 // with 2-D copies (K rows of chunk*X floats, host pitch B*X).  The first H2D and the last D2H cannot
-// overlap anything, so the chunk schedule starts and ends with small chunks (32, 64, 128, ..., 64, 32).
+// overlap anything; a schedule that starts and ends with small chunks (ZS_HS_CHUNK_MIN=32: 32, 64, 128, ..., 64, 32)
+// was measured SLOWER than uniform 128-column chunks (4.06 vs 3.93 ms; 256: 4.14, 512: 4.74; floor 3.45-3.5 ms):
+// the K = 50 strided rows of a small chunk are short DMA segments.  Uniform chunks are the default.
 // The small results (cost, dlogp, dlogq) travel on their own stream ahead of the big dprobs copies, so
 // a caller can go on (zs_iw_step_host_wait(0)) while the gradient of the likelihood is still landing.
 namespace {
 constexpr int HS_NBUF = 3;
-constexpr int64_t HS_CHUNK = 128;
-constexpr int64_t HS_CHUNK_MIN = 32;
 constexpr int HS_MAX_CHUNKS = 4096;
+// columns per chunk (ZS_HS_CHUNK) and the size of the first / last chunk (ZS_HS_CHUNK_MIN): dev knobs, read once
+static int64_t hs_env(const char* name, int64_t dflt) {
+    const char* e = getenv(name);
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? (int64_t)v : dflt;
+}
+static const int64_t HS_CHUNK = hs_env("ZS_HS_CHUNK", 128);
+static const int64_t HS_CHUNK_MIN = hs_env("ZS_HS_CHUNK_MIN", 128);
 
 struct HostStepCtx {
     bool ready = false;

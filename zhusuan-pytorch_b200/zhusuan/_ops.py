@@ -9,6 +9,7 @@ Responsibilities (all host logic, no math):
     reference's tests feed CPU tensors); there is no CPU implementation to fall back to.
 """
 import torch
+from ._shapes import broadcast_shapes as _bshapes
 
 from . import _backend as be
 from . import _rng
@@ -28,6 +29,25 @@ def compute_device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_upload_memo = [None]
+
+
+class upload_memo(object):
+    """Within this context a host tensor is uploaded once, however many nodes read it (an objective step reads the
+    variational parameters three times: two draws, one log-density), and its gradient comes back with one copy."""
+
+    def __enter__(self):
+        self.owner = _upload_memo[0] is None
+        if self.owner:
+            _upload_memo[0] = {}
+        return self
+
+    def __exit__(self, *exc):
+        if self.owner:
+            _upload_memo[0] = None
+        return False
+
+
 def to_compute(t):
     """Differentiable move to the CUDA device the kernels run on.  A CPU tensor that this package
     itself produced (see back_home) still has its device original attached: reuse it instead of
@@ -37,7 +57,16 @@ def to_compute(t):
     twin = getattr(t, "_zs_twin", None)
     if twin is not None and twin[1] == t._version:
         return twin[0]
-    return t.to(compute_device())
+    memo = _upload_memo[0]
+    if memo is None:
+        return t.to(compute_device())
+    key = (id(t), t._version)
+    hit = memo.get(key)
+    if hit is not None and hit[0] is t:
+        return hit[1]
+    d = t.to(compute_device())
+    memo[key] = (t, d)  # holding `t` keeps its id unique for the life of the memo
+    return d
 
 
 # Pinned host buffers are slow to allocate (torch.empty(pin_memory=True) ~0.3 ms, cudaHostAlloc of the
@@ -118,7 +147,7 @@ class Layout(object):
     """[K, M, E] view of the broadcast of `shapes` with the last `n_event` axes summed."""
 
     def __init__(self, shapes, n_event):
-        S = tuple(torch.broadcast_shapes(*shapes))
+        S = tuple(_bshapes(*shapes))
         if n_event > len(S):
             raise ValueError("cannot reduce %d event axes of a %d-d value" % (n_event, len(S)))
         self.S = S
@@ -211,7 +240,7 @@ def normal_sample(mean, std, n_samples, reparameterized):
     eps_in = _rng.take_injected("normal")
     if eps_in is not None:
         eps_in = to_compute(eps_in).to(mean.dtype).reshape(K, N).contiguous()
-    fits = tuple(torch.broadcast_shapes(base, std.shape)) == base
+    fits = tuple(_bshapes(base, std.shape)) == base
     if not fits or N == 0:
         # std broadcasts the mean (e.g. mean [1,3], std [2,1]): rare, composed from a noise draw
         if eps_in is None:

@@ -5,6 +5,7 @@ sample  : one kernel (Philox + Box-Muller + mean + std*eps), parameters broadcas
 log_prob: one kernel for the log-density and its event-axis sum (reference :109-126 + base.py:175-176).
 """
 import torch
+from zhusuan._shapes import broadcast_shapes as _bshapes
 
 from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
 from zhusuan.distributions.utils import assert_same_log_float_dtype, check_broadcast
@@ -47,7 +48,7 @@ class Normal(Distribution):
         return torch.log(self._std)
 
     def _batch_shape(self):
-        return torch.broadcast_shapes(self._mean.shape, self._std.shape)
+        return _bshapes(self._mean.shape, self._std.shape)
 
     def _sample(self, n_samples=1):
         z = _ops.normal_sample(self._mean, self._std, n_samples, self.is_reparameterized)

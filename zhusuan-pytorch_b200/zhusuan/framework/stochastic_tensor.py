@@ -13,6 +13,7 @@ log-probabilities and reducing them afterwards.
 import weakref
 
 import torch
+from zhusuan._shapes import broadcast_shapes as _bshapes
 
 from zhusuan.distributions.base import Distribution
 
@@ -88,7 +89,7 @@ class StochasticTensor(object):
         are summed inside the log-density kernel, the rest is applied to its (small) output.
         Axes index the tensor left after the distribution's own group_ndims sum, as in the reference."""
         g = self._dist.group_ndims
-        full = torch.broadcast_shapes(tuple(value_shape), tuple(self._dist.batch_shape))
+        full = _bshapes(tuple(value_shape), tuple(self._dist.batch_shape))
         nd = len(full) - g
         mean_dims = sorted(set(d % nd for d in (self._reduce_mean_dims or []))) if nd > 0 else []
         sum_dims = sorted(set(d % nd for d in (self._reduce_sum_dims or []))) if nd > 0 else []

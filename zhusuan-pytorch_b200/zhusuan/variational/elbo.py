@@ -42,6 +42,10 @@ class ELBO(nn.Module):
         return total
 
     def forward(self, observed, reduce_mean=True, **kwargs):
+        with _ops.upload_memo():  # host-resident parameters cross PCIe once per step
+            return self._forward(observed, reduce_mean, **kwargs)
+
+    def _forward(self, observed, reduce_mean=True, **kwargs):
         self.variational(observed)
         nodes_q = self.variational.nodes
         log_det = None

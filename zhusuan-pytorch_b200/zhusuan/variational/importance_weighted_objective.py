@@ -8,6 +8,7 @@ likelihood log-pmf, the objective and the likelihood's backward are fused furthe
 resident-column kernel (zs_iw_bernoulli_fused): probs is read from HBM once, dprobs written once.
 """
 import torch
+from zhusuan._shapes import broadcast_shapes as _bshapes
 import torch.nn as nn
 
 from zhusuan.framework.stochastic_tensor import StochasticTensor
@@ -131,6 +132,10 @@ class ImportanceWeightedObjective(nn.Module):
 
     # -- reference protocol ---------------------------------------------------------------------
     def forward(self, observed, reduce_mean=True):
+        with _ops.upload_memo():  # host-resident parameters cross PCIe once per step
+            return self._forward(observed, reduce_mean)
+
+    def _forward(self, observed, reduce_mean=True):
         self.variational(observed)
         nodes_q = self.variational.nodes
         latents = {}
@@ -166,7 +171,7 @@ class ImportanceWeightedObjective(nn.Module):
         logpxz, logqz = _as_pair(logpxz, logqz)
         err_msg = "VIMCO is a multi-sample gradient estimator, size along " \
                   "`axis` in the objective should be larger than 1."
-        shape = tuple(torch.broadcast_shapes(logpxz.shape, logqz.shape))
+        shape = tuple(_bshapes(logpxz.shape, logqz.shape))
         try:
             if shape[self._axis] < 2:
                 raise ValueError(err_msg)
