@@ -548,6 +548,38 @@ def test_iw_logits_path_against_reference_golden(dev, golden, est, latent, dn):
     assert d.logits is not None and tuple(d.batch_shape) == tuple(logits.shape)
 
 
+def test_particle_linear_matches_reference_layer():
+    """zhusuan.particle_linear == the repeat + matmul layer of the reference's BNN examples (bnn_vi.py:39-45), values
+    and gradients, without materialising [K, B, n_out, n_in + 1]."""
+    import zhusuan
+    torch.manual_seed(3)
+    K, B, n_in, n_out = 5, 7, 6, 4
+    w = torch.randn(K, n_out, n_in + 1, dtype=torch.float64, requires_grad=True)
+    h = torch.randn(K, B, n_in, dtype=torch.float64, requires_grad=True)
+
+    def reference_layer(w, h):
+        ww = torch.unsqueeze(w, 1).repeat([1, B, 1, 1])
+        hh = torch.cat((h, torch.ones([*h.shape[:-1], 1], dtype=h.dtype)), -1)
+        hh = torch.unsqueeze(hh, -1)
+        p = torch.sqrt(torch.as_tensor(hh.shape[2], dtype=torch.float32))
+        return torch.squeeze(torch.matmul(ww, hh) / p, -1)
+
+    ref = reference_layer(w, h)
+    out = zhusuan.particle_linear(w, h)
+    torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-9)
+    g = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, [w, h], g)
+    go = torch.autograd.grad(out, [w, h], g)
+    torch.testing.assert_close(go[0], gr[0], rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(go[1], gr[1], rtol=1e-6, atol=1e-9)
+    # 2-D activations are shared by all particles (the first layer of the examples)
+    x = torch.randn(B, n_in, dtype=torch.float64)
+    torch.testing.assert_close(zhusuan.particle_linear(w, x), reference_layer(w, x.unsqueeze(0).repeat(K, 1, 1)),
+                               rtol=1e-6, atol=1e-9)
+    with pytest.raises(RuntimeError):
+        zhusuan.particle_linear(w, torch.randn(K, B, n_in + 2, dtype=torch.float64))
+
+
 def test_elbo_path_against_reference_golden(dev, golden):
     """VAE ELBO (config 1 shapes, reduce_mean_dims=[0], reduce_sum_dims=[1]) vs the reference."""
     g = golden("elbo_path")

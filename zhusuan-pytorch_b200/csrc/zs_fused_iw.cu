@@ -431,6 +431,8 @@ __device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64
                                                float* __restrict__ cost, float* __restrict__ dlogp,
                                                float* __restrict__ dlogq, float* __restrict__ logpx_out,
                                                bool accumulate = false) {
+    // running-sum mode: the old value is requested first so its latency hides behind the objective's arithmetic
+    const float prev_cost = (accumulate && lane == 0 && cost) ? cost[b] : 0.f;
     const unsigned FULL = 0xffffffffu;
     // log-weights in double; max in float (any value within an ulp of the max stabilises exp)
     float mf = -INFINITY;
@@ -504,7 +506,7 @@ __device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64
     }
     c_acc = warp_sum(c_acc);
     // accumulate: running sum of the column's objective over launches (one writer per column: deterministic)
-    if (lane == 0 && cost) cost[b] = accumulate ? cost[b] + (float)c_acc : (float)c_acc;
+    if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc;
 }
 
 // Every row warp needs only max and sum-exp of the column to weight its own rows.
