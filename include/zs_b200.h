@@ -47,6 +47,8 @@ typedef void* zs_stream_t; /* cudaStream_t */
 enum { ZS_F32 = 0, ZS_F64 = 1 };
 enum { ZS_FULL = 0, ZS_KBCAST = 1, ZS_SCALAR = 2 };
 enum { ZS_EST_SGVB = 0, ZS_EST_VIMCO = 1, ZS_EST_ELBO = 2 };
+/* location-scale families of the zs_locscale_* entry points */
+enum { ZS_FAM_LOGISTIC = 1, ZS_FAM_LAPLACE = 2 };
 
 enum {
     ZS_OK = 0,
@@ -108,6 +110,24 @@ int zs_normal_logprob_fwd(int dtype, void* out, const void* x, int x_mode, const
 int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const void* g, const void* x, int x_mode,
                           const void* mean, int mean_mode, const void* std, int std_mode, int64_t K, int64_t M,
                           int64_t E, zs_stream_t stream);
+
+/* ---- Logistic / Laplace stochastic nodes, on the Normal node's kernel templates --------------
+ * z[K,N] = loc + scale * eps:  Logistic eps = log u - log(1 - u), u ~ U(0,1)  (Logistic._sample,
+ * zhusuan/distributions/logistic.py:56-70, reparameterised);  Laplace eps = -sign(u) log1p(-|u|), u ~ U(-1,1)
+ * (torch.distributions.Laplace.sample as called by laplace.py:60-76).  u_in != NULL injects the uniforms.
+ * _sample_bwd: dloc = sum_k dz, dscale = sum_k dz * eps (KBCAST) or elementwise (FULL), eps regenerated from
+ * (seed, offset) or from `u`.
+ * _logprob_fwd: out[K,M] = sum_e log p(x; loc, scale):  Logistic -z - 2 softplus(-z) - log(scale), z = (x-loc)/scale
+ * (logistic.py:72-83);  Laplace -log(2 scale) - |x - loc| / scale (laplace.py:78-92).  _logprob_bwd: autograd of those. */
+int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_mode, const void* scale, int scale_mode,
+                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void* dscale, int scale_mode, const void* dz,
+                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_locscale_logprob_fwd(int dtype, int family, void* out, const void* x, int x_mode, const void* loc, int loc_mode,
+                            const void* scale, int scale_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+int zs_locscale_logprob_bwd(int dtype, int family, void* dx, void* dloc, void* dscale, const void* g, const void* x,
+                            int x_mode, const void* loc, int loc_mode, const void* scale, int scale_mode, int64_t K,
+                            int64_t M, int64_t E, zs_stream_t stream);
 
 /* ---- Bernoulli stochastic node -------------------------------------------
  * out[K,N] = (u < probs) as float, u ~ Philox uniform   (Bernoulli._sample,

@@ -50,6 +50,17 @@ void orc_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset) {
 static float u01_closed_open(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-8f; }
 static float u01_open(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f; }
 
+/* uniforms on the OPEN interval (0,1): the noise source of the Logistic / Laplace samplers */
+void orc_philox_uniform_open_f32(float* out, int64_t n, uint64_t seed, uint64_t offset) {
+    for (int64_t q = 0; q < (n + 3) / 4; ++q) {
+        uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+        uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        philox4x32_10(c, k);
+        for (int j = 0; j < 4; ++j)
+            if (4 * q + j < n) out[4 * q + j] = u01_open(c[j]);
+    }
+}
+
 void orc_philox_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t offset) {
     for (int64_t q = 0; q < (n + 3) / 4; ++q) {
         uint32_t c[4] = {(uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};

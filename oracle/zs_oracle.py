@@ -184,6 +184,74 @@ def iw_bernoulli_logits_step(estimator, logits, x, logp_other, logq, grad_scale=
     return r
 
 
+# --------------------------------------------------------------------------- Logistic / Laplace (numpy restatement)
+LOGISTIC, LAPLACE = 1, 2
+
+
+def locscale_noise(family, u):
+    """eps of z = loc + scale * eps.  Logistic: log u - log(1 - u), u ~ U(0,1) (zhusuan/distributions/logistic.py:66-67);
+    Laplace: -sign(u) log1p(-|u|), u ~ U(-1,1) (torch.distributions.Laplace.sample, called by laplace.py:74)."""
+    u = np.asarray(u)
+    if family == LOGISTIC:
+        return (np.log(u) - np.log(1 - u)).astype(u.dtype)
+    return (-np.sign(u) * np.log1p(-np.abs(u))).astype(u.dtype)
+
+
+def locscale_sample(family, loc, scale, u, K, N):
+    eps = locscale_noise(family, np.asarray(u).reshape(K, N))
+    loc, scale = np.asarray(loc).reshape(-1, N), np.asarray(scale).reshape(-1, N)
+    return (loc + scale * eps).astype(eps.dtype)                      # logistic.py:68 / Laplace.rsample
+
+
+def locscale_sample_bwd(family, dz, u, K, N, full=False):
+    """Pathwise gradient of the sample: (dloc, dscale), summed over K unless `full`."""
+    eps = locscale_noise(family, np.asarray(u).reshape(K, N))
+    dz = np.asarray(dz).reshape(K, N)
+    if full:
+        return dz.copy(), (dz * eps).astype(dz.dtype)
+    return dz.sum(0).astype(dz.dtype), (dz * eps).sum(0).astype(dz.dtype)
+
+
+def _softplus(v):
+    return np.where(v > 20, v, np.log1p(np.exp(np.minimum(v, 20))))   # torch.nn.Softplus (threshold 20)
+
+
+def locscale_logprob_fwd(family, x, loc, scale, K, M, E):
+    dt = np.result_type(x, loc, scale).type
+    x, loc, scale = (np.broadcast_to(np.asarray(a, dt).reshape((-1, M, E)), (K, M, E)) for a in (x, loc, scale))
+    if family == LOGISTIC:
+        z = (x - loc) / scale                                          # logistic.py:81
+        lp = -z - 2 * _softplus(-z) - np.log(scale)                    # logistic.py:82
+    else:
+        lp = -np.log(2 * scale) - np.abs(x - loc) / scale              # torch Laplace.log_prob (laplace.py:92)
+    return lp.astype(dt).sum(-1).astype(dt)
+
+
+def locscale_logprob_bwd(family, g, x, loc, scale, K, M, E):
+    """Autograd of the expressions above for upstream g[K,M]: (dx, dloc, dscale), each reduced to its operand's
+    shape ([K,M,E] or [M,E])."""
+    dt = np.result_type(x, loc, scale).type
+    shapes = [np.asarray(a).reshape((-1, M, E)).shape for a in (x, loc, scale)]
+    x, loc, scale = (np.broadcast_to(np.asarray(a, dt).reshape((-1, M, E)), (K, M, E)) for a in (x, loc, scale))
+    g = np.asarray(g, dt).reshape(K, M, 1)
+    if family == LOGISTIC:
+        z = (x - loc) / scale
+        with np.errstate(over="ignore"):
+            sgm = np.where(-z > 20, 1.0, 1.0 / (1.0 + np.exp(z)))
+        dz = g * (-1 + 2 * sgm)
+        dx = dz / scale
+        dscale = -(dz * z) / scale - g / scale
+    else:
+        d = x - loc
+        dx = -(g * np.sign(d)) / scale
+        dscale = -g / scale + (g * np.abs(d)) / (scale * scale)
+    outs = []
+    for grad, shp in zip((dx, -dx, dscale), shapes):
+        grad = grad.astype(dt)
+        outs.append(grad if shp[0] == K and K > 1 or shp == (K, M, E) else grad.sum(0, keepdims=True).astype(dt))
+    return tuple(o.reshape(s) for o, s in zip(outs, shapes))
+
+
 # --------------------------------------------------------------------------- Categorical (parity unpinned)
 def categorical_logpmf_fwd(x, logits, K, M, C):
     dt = logits.dtype.type
@@ -326,6 +394,12 @@ def philox_raw(n, seed, offset):
 def philox_uniform(n, seed, offset):
     out = np.empty(n, np.float32)
     lib().orc_philox_uniform_f32(_p(out), _i64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset))
+    return out
+
+
+def philox_uniform_open(n, seed, offset):
+    out = np.empty(n, np.float32)
+    lib().orc_philox_uniform_open_f32(_p(out), _i64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset))
     return out
 
 

@@ -22,7 +22,7 @@ if REF not in sys.path:
     sys.path.insert(0, REF)
 
 import zhusuan  # noqa: E402  (the reference)
-from zhusuan.distributions import Bernoulli, Normal  # noqa: E402
+from zhusuan.distributions import Bernoulli, Normal, Laplace, Logistic  # noqa: E402
 from zhusuan.framework import BayesianNet  # noqa: E402
 from zhusuan.variational import ELBO, ImportanceWeightedObjective  # noqa: E402
 from zhusuan import mcmc  # noqa: E402
@@ -335,6 +335,38 @@ def gen_logits_path():
     save("logits_path", **out)
 
 
+# --------------------------------------------------------------------------- Logistic / Laplace
+def gen_locscale():
+    """Logistic and Laplace nodes: log_prob + gradients with parameters broadcast over particles, and the Logistic
+    reparameterised sample with injected uniforms (torch.nn.init.uniform_ patched)."""
+    rng = np.random.RandomState(29)
+    K, M, E = 5, 6, 8
+    x64 = 2.0 * rng.standard_normal((K, M, E))
+    x64.reshape(-1)[:3] = [0.0, 60.0, -60.0]
+    loc64 = rng.standard_normal((M, E))
+    loc64.reshape(-1)[0] = 0.0  # x == loc: the sign(0) corner of the Laplace gradient
+    scale64 = np.exp(0.4 * rng.standard_normal((M, E)))
+    g64 = rng.standard_normal((K, M))
+    u64 = rng.uniform(0.02, 0.98, size=(K, M, E))
+    dz64 = rng.standard_normal((K, M, E))
+    out = dict(x=x64, loc=loc64, scale=scale64, g=g64, u=u64, dz=dz64)
+    for dn, dt in DT.items():
+        for name, cls in (("logistic", Logistic), ("laplace", Laplace)):
+            x, loc, scale = t(x64, dt, True), t(loc64, dt, True), t(scale64, dt, True)
+            d = cls(loc=loc, scale=scale, group_ndims=1)
+            lp = d.log_prob(x)
+            gr = torch.autograd.grad(lp, [x, loc, scale], grad_outputs=t(g64, dt))
+            p = "%s_%s_" % (name, dn)
+            out.update({p + "lp": npy(lp), p + "dx": npy(gr[0]), p + "dloc": npy(gr[1]), p + "dscale": npy(gr[2])})
+        loc, scale = t(loc64, dt, True), t(scale64, dt, True)
+        u = t(u64, dt)
+        with mock.patch("torch.nn.init.uniform_", lambda tensor, a=0., b=1.: u.clone()):
+            z = Logistic(loc=loc, scale=scale).sample(K)
+        gr = torch.autograd.grad(z, [loc, scale], grad_outputs=t(dz64, dt))
+        out.update({"logistic_%s_z" % dn: npy(z), "logistic_%s_sdloc" % dn: npy(gr[0]), "logistic_%s_sdscale" % dn: npy(gr[1])})
+    save("locscale", **out)
+
+
 # --------------------------------------------------------------------------- VAE ELBO (cfg 1 shapes, small)
 def gen_elbo_path():
     rng = np.random.RandomState(16)
@@ -563,6 +595,7 @@ if __name__ == "__main__":
     gen_reinforce()
     gen_iw_path()
     gen_logits_path()
+    gen_locscale()
     gen_elbo_path()
     gen_sgmcmc()
     gen_bnn()

@@ -64,6 +64,39 @@ def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs, logit
     return (_t(dx, probs) if need_x else None, _t(dp, probs) if need_probs else None)
 
 
+FAM_LOGISTIC, FAM_LAPLACE = 1, 2
+
+
+def _locscale_u(family, K, N, dtype, u_in, seed, offset):
+    if u_in is not None:
+        return _np(u_in).reshape(K, N)
+    u = O.philox_uniform_open(K * N, seed, offset).astype(dtype).reshape(K, N)
+    return (2 * u - 1).astype(dtype) if family == FAM_LAPLACE else u
+
+
+def locscale_sample(family, loc, loc_mode, scale, scale_mode, K, N, u_in=None, seed=0, offset=0):
+    u = _locscale_u(family, K, N, _np(loc).dtype, u_in, seed, offset)
+    return _t(O.locscale_sample(family, _np(loc), _np(scale), u, K, N), loc)
+
+
+def locscale_sample_bwd(family, dz, loc_like, loc_mode, scale_like, scale_mode, K, N, u=None, seed=0, offset=0,
+                        need_loc=True, need_scale=True):
+    uu = _locscale_u(family, K, N, _np(dz).dtype, u, seed, offset)
+    dl, ds = O.locscale_sample_bwd(family, _np(dz), uu, K, N, full=(loc_mode == FULL and K > 1))
+    return (_t(dl.reshape(loc_like.shape), dz) if need_loc else None,
+            _t(ds.reshape(scale_like.shape), dz) if need_scale else None)
+
+
+def locscale_logprob_fwd(family, x, xm, loc, lm, scale, sm, K, M, E):
+    return _t(O.locscale_logprob_fwd(family, _np(x), _np(loc), _np(scale), K, M, E), x)
+
+
+def locscale_logprob_bwd(family, g, x, xm, loc, lm, scale, sm, K, M, E, need_x, need_loc, need_scale):
+    dx, dl, ds = O.locscale_logprob_bwd(family, _np(g), _np(x), _np(loc), _np(scale), K, M, E)
+    return (_t(dx.reshape(x.shape), x) if need_x else None, _t(dl.reshape(loc.shape), x) if need_loc else None,
+            _t(ds.reshape(scale.shape), x) if need_scale else None)
+
+
 def categorical_sample(logits, lm, K, M, C, u_in=None, seed=0, offset=0):
     u = O.philox_uniform(K * M, seed, offset).astype(_np(logits).dtype) if u_in is None else _np(u_in)
     return _t(O.categorical_sample(_np(logits), u.reshape(K, M), K, M, C), logits)
@@ -175,7 +208,8 @@ def install(monkeypatch):
     """Patch the product's backend / device helpers with the CPU stand-ins above."""
     from zhusuan import _backend, _ops, _rng
     for name in ("normal_sample", "normal_sample_bwd", "normal_logprob_fwd", "normal_logprob_bwd", "bernoulli_sample",
-                 "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "categorical_sample", "categorical_logpmf_fwd",
+                 "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "locscale_sample", "locscale_sample_bwd",
+                 "locscale_logprob_fwd", "locscale_logprob_bwd", "categorical_sample", "categorical_logpmf_fwd",
                  "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
                  "iw_bernoulli_fused", "reinforce_step", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
                  "sghmc_post"):

@@ -548,6 +548,59 @@ def test_iw_logits_path_against_reference_golden(dev, golden, est, latent, dn):
     assert d.logits is not None and tuple(d.batch_shape) == tuple(logits.shape)
 
 
+@pytest.mark.parametrize("name", ["logistic", "laplace"])
+def test_locscale_distributions_against_reference_golden(dev, golden, name):
+    """zhusuan.distributions.{Logistic, Laplace}: log_prob with parameters broadcast over particles, gradients,
+    the Logistic reparameterised sample with injected uniforms, properties and errors (reference logistic.py / laplace.py)."""
+    from zhusuan.distributions import Laplace, Logistic
+    g = golden("locscale")
+    cls = Logistic if name == "logistic" else Laplace
+    for dn, dt, rt in (("f32", torch.float32, 1e-5), ("f64", torch.float64, 1e-10)):
+        x, loc, scale = T(g["x"], dev, dt, True), T(g["loc"], dev, dt, True), T(g["scale"], dev, dt, True)
+        d = cls(loc=loc, scale=scale, group_ndims=1)
+        assert d.is_reparameterized == (name == "logistic") and tuple(d.batch_shape) == tuple(loc.shape)
+        lp = d.log_prob(x)
+        p = "%s_%s_" % (name, dn)
+        close(lp, g[p + "lp"], rt)
+        gr = torch.autograd.grad(lp, [x, loc, scale], grad_outputs=T(g["g"], dev, dt))
+        close(gr[0], g[p + "dx"], rt)
+        close(gr[1], g[p + "dloc"], rt)
+        close(gr[2], g[p + "dscale"], rt)
+        K = g["x"].shape[0]
+        if name == "logistic":
+            with _rng.inject(uniform=[T(g["u"], dev, dt)]):
+                z = cls(loc=loc, scale=scale).sample(K)
+            close(z, g[p + "z"], rt)
+            sg = torch.autograd.grad(z, [loc, scale], grad_outputs=T(g["dz"], dev, dt))
+            close(sg[0], g[p + "sdloc"], rt)
+            close(sg[1], g[p + "sdscale"], rt)
+        else:
+            z = cls(loc=loc, scale=scale).sample(K)
+            assert tuple(z.shape) == (K,) + tuple(loc.shape) and not z.requires_grad
+    with pytest.raises(RuntimeError):
+        cls(loc=torch.zeros(2, 3), scale=torch.ones(4))
+    if name == "logistic":
+        with pytest.raises(ValueError, match="scale less than zero"):
+            Logistic(loc=torch.zeros(3), scale=torch.tensor([1.0, 0.0, 2.0]))
+
+
+def test_bn_logistic_builds_laplace_like_the_reference(dev):
+    """framework/bn.py:336-352 of the reference: `bn.logistic` constructs a Laplace."""
+    from zhusuan.distributions import Laplace
+
+    class Net(BayesianNet):
+        def forward(self, observed):
+            self.observe(observed)
+            self.logistic("a", loc=torch.zeros(3), scale=torch.ones(3))
+            self.laplace("b", loc=torch.zeros(3), scale=torch.ones(3))
+            self.stochastic_node("Logistic", "c", loc=torch.zeros(3), scale=torch.ones(3))
+            return self
+
+    net = Net()({})
+    assert isinstance(net.nodes["a"].dist, Laplace) and isinstance(net.nodes["b"].dist, Laplace)
+    assert type(net.nodes["c"].dist).__name__ == "Logistic"
+
+
 def test_particle_linear_matches_reference_layer():
     """zhusuan.particle_linear == the repeat + matmul layer of the reference's BNN examples (bnn_vi.py:39-45), values
     and gradients, without materialising [K, B, n_out, n_in + 1]."""

@@ -598,6 +598,55 @@ def test_iw_step_host_begin_wait_device_scalars(B):
     assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 
 
+# ----------------------------------------------------------------------------- Logistic / Laplace nodes
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["logistic", "laplace"])
+def test_locscale_golden(golden, oracle, name, dn):
+    g = golden("locscale")
+    dt = np.float32 if dn == "f32" else np.float64
+    fam = be.FAM_LOGISTIC if name == "logistic" else be.FAM_LAPLACE
+    x, loc, scale, up = (g[k].astype(dt) for k in ("x", "loc", "scale", "g"))
+    K, M, E = x.shape
+    p = "%s_%s_" % (name, dn)
+    rt = 1e-5 if dn == "f32" else 1e-11
+    out = be.locscale_logprob_fwd(fam, dev(x), FULL, dev(loc), KBCAST, dev(scale), KBCAST, K, M, E)
+    close(host(out), g[p + "lp"], rt)
+    dx, dloc, dscale = be.locscale_logprob_bwd(fam, dev(up), dev(x), FULL, dev(loc), KBCAST, dev(scale), KBCAST, K, M, E,
+                                               True, True, True)
+    close(host(dx), g[p + "dx"], rt)
+    close(host(dloc), g[p + "dloc"], rt)
+    close(host(dscale), g[p + "dscale"], rt)
+    if name == "logistic":
+        u, dz = g["u"].astype(dt), g["dz"].astype(dt)
+        N = M * E
+        z = be.locscale_sample(fam, dev(loc.reshape(N)), KBCAST, dev(scale.reshape(N)), KBCAST, K, N,
+                               u_in=dev(u.reshape(K, N)))
+        close(host(z).reshape(K, M, E), g[p + "z"], rt)
+        sl, ss = be.locscale_sample_bwd(fam, dev(dz.reshape(K, N)), dev(loc.reshape(N)), KBCAST, dev(scale.reshape(N)),
+                                        KBCAST, K, N, u=dev(u.reshape(K, N)))
+        close(host(sl).reshape(M, E), g[p + "sdloc"], rt)
+        close(host(ss).reshape(M, E), g[p + "sdscale"], rt)
+
+
+@pytest.mark.parametrize("name", ["logistic", "laplace"])
+def test_locscale_sampler_statistics(oracle, name):
+    """In-kernel Philox draws: bit-level agreement with the oracle's Philox + transform restatement, moments, KS."""
+    import scipy.stats as st
+    fam = be.FAM_LOGISTIC if name == "logistic" else be.FAM_LAPLACE
+    K, N = 64, 4099
+    loc = np.full(N, 1.5, np.float32)
+    scale = np.full(N, 0.7, np.float32)
+    z = host(be.locscale_sample(fam, dev(loc), KBCAST, dev(scale), KBCAST, K, N, seed=123, offset=8))
+    u = oracle.philox_uniform_open(K * N, 123, 8).reshape(K, N)
+    if name == "laplace":
+        u = (2 * u - 1).astype(np.float32)
+    ref = oracle.locscale_sample(oracle.LOGISTIC if name == "logistic" else oracle.LAPLACE, loc, scale, u, K, N)
+    close(z, ref, 2e-6)
+    dist = st.logistic(1.5, 0.7) if name == "logistic" else st.laplace(1.5, 0.7)
+    assert abs(z.mean() - dist.mean()) < 0.02 and abs(z.std() - dist.std()) < 0.02
+    assert st.kstest(z.ravel()[:20000], dist.cdf).pvalue > 1e-3
+
+
 # ----------------------------------------------------------------------------- REINFORCE (one cluster launch)
 def test_reinforce_golden(golden):
     g = golden("reinforce")

@@ -211,6 +211,30 @@ def test_iw_logits_path_composite(oracle, golden, est, latent, dn):
     close(r["dprobs"], g[p + "dlogits"], dn, 30)
 
 
+@pytest.mark.parametrize("dn", [F32, F64])
+@pytest.mark.parametrize("name", ["logistic", "laplace"])
+def test_locscale_nodes(oracle, golden, name, dn):
+    """Logistic / Laplace log_prob + gradients (parameters broadcast over particles, saturated z, x == loc) and the
+    Logistic reparameterised sample with injected uniforms (tests/golden/make_golden.py:gen_locscale)."""
+    g = golden("locscale")
+    dt = np.float32 if dn == F32 else np.float64
+    fam = oracle.LOGISTIC if name == "logistic" else oracle.LAPLACE
+    x, loc, scale, up = (g[k].astype(dt) for k in ("x", "loc", "scale", "g"))
+    K, M, E = x.shape
+    p = "%s_%s_" % (name, dn)
+    close(oracle.locscale_logprob_fwd(fam, x, loc, scale, K, M, E), g[p + "lp"], dn)
+    dx, dloc, dscale = oracle.locscale_logprob_bwd(fam, up, x, loc, scale, K, M, E)
+    close(dx.reshape(K, M, E), g[p + "dx"], dn, 30)
+    close(dloc.reshape(M, E), g[p + "dloc"], dn, 30)
+    close(dscale.reshape(M, E), g[p + "dscale"], dn, 30)
+    if name == "logistic":
+        u, dz = g["u"].astype(dt), g["dz"].astype(dt)
+        close(oracle.locscale_sample(fam, loc, scale, u, K, M * E).reshape(K, M, E), g[p + "z"], dn)
+        sl, ss = oracle.locscale_sample_bwd(fam, dz, u, K, M * E)
+        close(sl.reshape(M, E), g[p + "sdloc"], dn, 30)
+        close(ss.reshape(M, E), g[p + "sdscale"], dn, 30)
+
+
 def test_reinforce_steps(oracle, golden):
     """ELBO.reinforce over three consecutive calls: cost, gradients and the in-place moving-mean state
     (tests/golden/make_golden.py:gen_reinforce, reference elbo.py:200-238)."""

@@ -58,6 +58,48 @@ struct NormalOp {
     }
 };
 
+// Laplace(loc, scale): torch.distributions.Laplace.log_prob as the reference calls it
+// (zhusuan/distributions/laplace.py:92): -log(2 scale) - |x - loc| / scale
+template <typename T>
+struct LaplaceOp {
+    static __device__ __forceinline__ T term(T x, T loc, T scale) {
+        T d = x - loc;
+        return -Real<T>::log(T(2) * scale) - (d < T(0) ? -d : d) / scale;
+    }
+    static __device__ __forceinline__ T finish(T acc) { return acc; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(T g, T x, T loc, T scale, T& dx, T& dloc, T& dscale) {
+        T d = x - loc;
+        T sg = d > T(0) ? T(1) : (d < T(0) ? T(-1) : T(0));  // torch: d|u|/du = sign(u), 0 at u = 0
+        T ad = d < T(0) ? -d : d;
+        dx = -(g * sg) / scale;
+        dloc = -dx;
+        dscale = -g / scale + (g * ad) / (scale * scale);
+    }
+};
+
+// Logistic(loc, scale): zhusuan/distributions/logistic.py:81-82
+//   z = (x - loc) / scale ;  log p = -z - 2 softplus(-z) - log(scale)      (softplus: torch's, threshold 20)
+template <typename T>
+struct LogisticOp {
+    static __device__ __forceinline__ T softplus(T v) { return v > T(20) ? v : log1p(Real<T>::exp(v)); }
+    static __device__ __forceinline__ T term(T x, T loc, T scale) {
+        T z = (x - loc) / scale;
+        return (-z - T(2) * softplus(-z)) - Real<T>::log(scale);
+    }
+    static __device__ __forceinline__ T finish(T acc) { return acc; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(T g, T x, T loc, T scale, T& dx, T& dloc, T& dscale) {
+        T z = (x - loc) / scale;
+        // d/dz(-z - 2 softplus(-z)) = -1 + 2 sigmoid(-z)   (softplus' = sigmoid below the threshold, 1 above)
+        T sgm = -z > T(20) ? T(1) : T(1) / (T(1) + Real<T>::exp(z));
+        T dz = g * (T(-1) + T(2) * sgm);
+        dx = dz / scale;
+        dloc = -dx;
+        dscale = -(dz * z) / scale - g / scale;
+    }
+};
+
 template <typename T>
 struct BernoulliOp;
 
@@ -354,7 +396,39 @@ __global__ void __launch_bounds__(KR_X* KR_Y) k_kreduce_bwd(T* __restrict__ dx, 
 // sampling
 // ---------------------------------------------------------------------------
 // Normal: z = mean + std*eps over [K,N]; 4 consecutive elements per thread (one Philox call).
-template <typename T, bool ALIGNED4>
+// Location-scale noise families: eps of  z = loc + scale * eps.
+//   NOISE_NORMAL   standard normal (Box-Muller)                                        normal.py:104
+//   NOISE_LOGISTIC log(u) - log(1 - u), u ~ U(0,1)                                     logistic.py:66-67
+//   NOISE_LAPLACE  -sign(u) log1p(-|u|), u ~ U(-1,1)      torch.distributions.Laplace.sample (laplace.py:74)
+// Injected noise (`eps_in`) is the family's UNIFORM for the last two, so the transform itself is under test.
+constexpr int NOISE_NORMAL = 0, NOISE_LOGISTIC = 1, NOISE_LAPLACE = 2;
+
+template <typename T, int NOISE>
+__device__ __forceinline__ T noise_from_uniform(T u) {
+    if (NOISE == NOISE_LOGISTIC) return Real<T>::log(u) - Real<T>::log(T(1) - u);
+    if (NOISE == NOISE_LAPLACE) {
+        const T a = u < T(0) ? -u : u;
+        const T l = log1p(-a);
+        return u > T(0) ? -l : (u < T(0) ? l : T(0));
+    }
+    return u;
+}
+template <int NOISE>
+__device__ __forceinline__ void philox_noise4(uint64_t q, uint64_t offset, uint64_t seed, float out[4]) {
+    if (NOISE == NOISE_NORMAL) {
+        philox_normal4(q, offset, seed, out);
+    } else {
+        Philox4 r = philox4x32_10(q, offset, seed);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float u = u01_open(w[j]);  // (0,1)
+            out[j] = noise_from_uniform<float, NOISE>(NOISE == NOISE_LAPLACE ? 2.0f * u - 1.0f : u);
+        }
+    }
+}
+
+template <typename T, bool ALIGNED4, int NOISE = NOISE_NORMAL>
 __global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const T* __restrict__ mean, int mm,
                                                        const T* __restrict__ std, int sm, const T* __restrict__ eps_in,
                                                        T* __restrict__ eps_out, int64_t K, int64_t N, uint64_t seed,
@@ -365,7 +439,7 @@ __global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const 
     const T ss = sm == ZS_SCALAR ? std[0] : T(0);
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         float e4[4];
-        if (!eps_in) philox_normal4((uint64_t)q, offset, seed, e4);
+        if (!eps_in) philox_noise4<NOISE>((uint64_t)q, offset, seed, e4);
         const int64_t i0 = q * 4;
         // ALIGNED4: N % 4 == 0, so the 4 elements share a particle and are contiguous in [N]
         int64_t n0 = ALIGNED4 ? (i0 % N) : 0;
@@ -374,7 +448,7 @@ __global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const 
             const int64_t i = i0 + j;
             if (i < total) {
                 const int64_t n = ALIGNED4 ? n0 + j : i % N;
-                T e = eps_in ? eps_in[i] : (T)e4[j];
+                T e = eps_in ? noise_from_uniform<T, NOISE>(eps_in[i]) : (T)e4[j];
                 T mv = mm == ZS_FULL ? mean[i] : (mm == ZS_KBCAST ? mean[n] : ms);
                 T sv = sm == ZS_FULL ? std[i] : (sm == ZS_KBCAST ? std[n] : ss);
                 z[i] = mv + sv * e;
@@ -385,7 +459,7 @@ __global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const 
 }
 
 // pathwise backward of the sample: dmean = sum_k dz ; dstd = sum_k dz*eps (KBCAST), elementwise (FULL)
-template <typename T>
+template <typename T, int NOISE = NOISE_NORMAL>
 __global__ void __launch_bounds__(KR_X* KR_Y) k_normal_sample_bwd(T* __restrict__ dmean, int mm, T* __restrict__ dstd,
                                                                    int sm, const T* __restrict__ dz,
                                                                    const T* __restrict__ eps, int64_t K, int64_t N,
@@ -400,10 +474,10 @@ __global__ void __launch_bounds__(KR_X* KR_Y) k_normal_sample_bwd(T* __restrict_
             T d = dz[i];
             T e;
             if (eps) {
-                e = eps[i];
+                e = noise_from_uniform<T, NOISE>(eps[i]);
             } else {
                 float e4[4];
-                philox_normal4((uint64_t)(i >> 2), offset, seed, e4);
+                philox_noise4<NOISE>((uint64_t)(i >> 2), offset, seed, e4);
                 e = (T)e4[i & 3];
             }
             if (dmean) {
@@ -711,6 +785,85 @@ int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, co
                                                Operand<T>{(const T*)x, x_mode},
                                                Operand<T>{(const T*)probs, probs_mode},
                                                Operand<T>{nullptr, ZS_SCALAR}, K, M, E, as_stream(stream));
+    })
+}
+
+/* ---- location-scale families beyond Normal ------------------------------------------------ */
+int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_mode, const void* scale, int scale_mode,
+                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(z && loc && scale && K >= 0 && N >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    if (K * N == 0) return ZS_OK;
+    const int grid = grid_for((K * N + 3) / 4, 256);
+    ZS_DTYPE_SWITCH(dtype, {
+        if (family == ZS_FAM_LOGISTIC)
+            k_normal_sample<T, false, NOISE_LOGISTIC><<<grid, 256, 0, as_stream(stream)>>>(
+                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset);
+        else
+            k_normal_sample<T, false, NOISE_LAPLACE><<<grid, 256, 0, as_stream(stream)>>>(
+                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset);
+    })
+    ZS_LAUNCH_CHECK("k_normal_sample<locscale>");
+    return ZS_OK;
+}
+
+int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void* dscale, int scale_mode, const void* dz,
+                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(dz && K >= 0 && N >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    if ((dloc && loc_mode == ZS_SCALAR) || (dscale && scale_mode == ZS_SCALAR)) {
+        set_last_error_msg("SCALAR-mode gradients are not produced by the kernels; expand the operand");
+        return ZS_ERR_UNSUPPORTED;
+    }
+    if (K * N == 0 || (!dloc && !dscale)) return ZS_OK;
+    dim3 block(KR_X, KR_Y);
+    const int64_t grid = (N + KR_X - 1) / KR_X;
+    ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
+    ZS_DTYPE_SWITCH(dtype, {
+        if (family == ZS_FAM_LOGISTIC)
+            k_normal_sample_bwd<T, NOISE_LOGISTIC><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset);
+        else
+            k_normal_sample_bwd<T, NOISE_LAPLACE><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset);
+    })
+    ZS_LAUNCH_CHECK("k_normal_sample_bwd<locscale>");
+    return ZS_OK;
+}
+
+int zs_locscale_logprob_fwd(int dtype, int family, void* out, const void* x, int x_mode, const void* loc, int loc_mode,
+                            const void* scale, int scale_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(out && x && loc && scale && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    ZS_DTYPE_SWITCH(dtype, {
+        if (family == ZS_FAM_LOGISTIC)
+            return dispatch_rows_fwd<T, LogisticOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                       Operand<T>{(const T*)loc, loc_mode},
+                                                       Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
+        return dispatch_rows_fwd<T, LaplaceOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                  Operand<T>{(const T*)loc, loc_mode},
+                                                  Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
+    })
+}
+
+int zs_locscale_logprob_bwd(int dtype, int family, void* dx, void* dloc, void* dscale, const void* g, const void* x,
+                            int x_mode, const void* loc, int loc_mode, const void* scale, int scale_mode, int64_t K,
+                            int64_t M, int64_t E, zs_stream_t stream) {
+    ZS_REQUIRE(g && x && loc && scale && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(valid_mode(x_mode) && valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    if (!dx && !dloc && !dscale) return ZS_OK;
+    ZS_DTYPE_SWITCH(dtype, {
+        if (family == ZS_FAM_LOGISTIC)
+            return dispatch_bwd<T, LogisticOp<T>>((T*)dx, (T*)dloc, (T*)dscale, (const T*)g, Operand<T>{(const T*)x, x_mode},
+                                                  Operand<T>{(const T*)loc, loc_mode},
+                                                  Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
+        return dispatch_bwd<T, LaplaceOp<T>>((T*)dx, (T*)dloc, (T*)dscale, (const T*)g, Operand<T>{(const T*)x, x_mode},
+                                             Operand<T>{(const T*)loc, loc_mode},
+                                             Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
     })
 }
 

@@ -48,6 +48,10 @@ def _declare(lib):
         "zs_bernoulli_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, u64, u64, vp]),
         "zs_bernoulli_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
+        "zs_locscale_sample": (i32, [i32, i32, vp, vp, i32, vp, i32, vp, i64, i64, u64, u64, vp]),
+        "zs_locscale_sample_bwd": (i32, [i32, i32, vp, i32, vp, i32, vp, vp, i64, i64, u64, u64, vp]),
+        "zs_locscale_logprob_fwd": (i32, [i32, i32, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
+        "zs_locscale_logprob_bwd": (i32, [i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logits_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logits_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_categorical_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, i64, u64, u64, vp]),
@@ -311,6 +315,57 @@ def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs, logit
           "zs_bernoulli_logits_logpmf_bwd" if logits else "zs_bernoulli_logpmf_bwd")
     _count()
     return dx, dprobs
+
+
+# ----------------------------------------------------------------------------- Logistic / Laplace
+FAM_LOGISTIC, FAM_LAPLACE = 1, 2
+
+
+def locscale_sample(family, loc, loc_mode, scale, scale_mode, K, N, u_in=None, seed=0, offset=0):
+    dt = loc.dtype
+    for t, n in ((loc, "loc"), (scale, "scale"), (u_in, "u_in")):
+        _chk_tensor(t, n, dt)
+    z = torch.empty((K, N), dtype=dt, device=loc.device)
+    check(load().zs_locscale_sample(dtype_code(dt), family, _ptr(z), _ptr(loc), loc_mode, _ptr(scale), scale_mode,
+                                    _ptr(u_in), K, N, seed, offset, _stream()), "zs_locscale_sample")
+    _count()
+    return z
+
+
+def locscale_sample_bwd(family, dz, loc_like, loc_mode, scale_like, scale_mode, K, N, u=None, seed=0, offset=0,
+                        need_loc=True, need_scale=True):
+    dt = dz.dtype
+    _chk_tensor(dz, "dz", dt)
+    _chk_tensor(u, "u", dt)
+    dloc = torch.empty_like(loc_like) if need_loc else None
+    dscale = torch.empty_like(scale_like) if need_scale else None
+    check(load().zs_locscale_sample_bwd(dtype_code(dt), family, _ptr(dloc), loc_mode, _ptr(dscale), scale_mode, _ptr(dz),
+                                        _ptr(u), K, N, seed, offset, _stream()), "zs_locscale_sample_bwd")
+    _count()
+    return dloc, dscale
+
+
+def locscale_logprob_fwd(family, x, xm, loc, lm, scale, sm, K, M, E):
+    dt = x.dtype
+    for t, n in ((x, "x"), (loc, "loc"), (scale, "scale")):
+        _chk_tensor(t, n, dt)
+    out = torch.empty((K, M), dtype=dt, device=x.device)
+    check(load().zs_locscale_logprob_fwd(dtype_code(dt), family, _ptr(out), _ptr(x), xm, _ptr(loc), lm, _ptr(scale), sm,
+                                         K, M, E, _stream()), "zs_locscale_logprob_fwd")
+    _count()
+    return out
+
+
+def locscale_logprob_bwd(family, g, x, xm, loc, lm, scale, sm, K, M, E, need_x, need_loc, need_scale):
+    dt = x.dtype
+    _chk_tensor(g, "g", dt)
+    dx = torch.empty_like(x) if need_x else None
+    dloc = torch.empty_like(loc) if need_loc else None
+    dscale = torch.empty_like(scale) if need_scale else None
+    check(load().zs_locscale_logprob_bwd(dtype_code(dt), family, _ptr(dx), _ptr(dloc), _ptr(dscale), _ptr(g), _ptr(x), xm,
+                                         _ptr(loc), lm, _ptr(scale), sm, K, M, E, _stream()), "zs_locscale_logprob_bwd")
+    _count()
+    return dx, dloc, dscale
 
 
 # ----------------------------------------------------------------------------- Categorical

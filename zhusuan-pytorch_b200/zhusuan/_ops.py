@@ -265,6 +265,82 @@ def normal_sample(mean, std, n_samples, reparameterized):
 
 
 # --------------------------------------------------------------------------------------------
+# Logistic / Laplace: the Normal node's kernel templates with another noise transform / log-density
+# --------------------------------------------------------------------------------------------
+class _LocScaleLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, loc, scale, family, modes, K, M, E):
+        out = be.locscale_logprob_fwd(family, x, modes[0], loc, modes[1], scale, modes[2], K, M, E)
+        ctx.save_for_backward(x, loc, scale)
+        ctx.cfg = (family, modes, K, M, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, loc, scale = ctx.saved_tensors
+        family, modes, K, M, E = ctx.cfg
+        nx, nl, ns = ctx.needs_input_grad[:3]
+        dx, dloc, dscale = be.locscale_logprob_bwd(family, g.contiguous(), x, modes[0], loc, modes[1], scale, modes[2],
+                                                   K, M, E, nx, nl, ns)
+        return dx, dloc, dscale, None, None, None, None, None
+
+
+def locscale_log_prob(family, x, loc, scale, n_event):
+    """Sum over the last n_event axes of the Logistic (logistic.py:72-83) / Laplace (laplace.py:78-92) log-density."""
+    home = x.device
+    x, loc, scale = to_compute(x), to_compute(loc), to_compute(scale)
+    L = Layout([x.shape, loc.shape, scale.shape], n_event)
+    if _prod(L.S) == 0:
+        return back_home(torch.zeros(L.lead, dtype=x.dtype, device=x.device), home)
+    (xc, xm), (lc, lm), (sc, sm) = L.canon(x), L.canon(loc), L.canon(scale)
+    out = _LocScaleLogProb.apply(xc, lc, sc, family, (xm, lm, sm), L.K, L.M, L.E)
+    return back_home(out.reshape(L.lead), home)
+
+
+class _LocScaleSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, scale, family, modes, K, N, u_in):
+        seed, offset = (0, 0) if u_in is not None else _rng.next_philox(loc.device)
+        z = be.locscale_sample(family, loc, modes[0], scale, modes[1], K, N, u_in=u_in, seed=seed, offset=offset)
+        ctx.save_for_backward(loc, scale, u_in)
+        ctx.cfg = (family, modes, K, N, seed, offset)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        loc, scale, u = ctx.saved_tensors
+        family, modes, K, N, seed, offset = ctx.cfg
+        nl, ns = ctx.needs_input_grad[:2]
+        dloc, dscale = be.locscale_sample_bwd(family, dz.contiguous(), loc, modes[0], scale, modes[1], K, N, u=u,
+                                              seed=seed, offset=offset, need_loc=nl, need_scale=ns)
+        return dloc, dscale, None, None, None, None, None
+
+
+def locscale_sample(family, loc, scale, n_samples, reparameterized):
+    """Logistic._sample (logistic.py:56-70) / Laplace._sample (laplace.py:60-76): [n_samples] + batch shape, noise
+    from in-kernel Philox uniforms (or injected uniforms, _rng.inject(uniform=...))."""
+    home = loc.device
+    loc, scale = to_compute(loc), to_compute(scale)
+    base = tuple(_bshapes(loc.shape, scale.shape))
+    loc, scale = loc.expand(base).contiguous(), scale.expand(base).contiguous()
+    K = int(n_samples)
+    out_shape = ((K,) if K > 1 else ()) + base
+    N = _prod(base)
+    if N == 0:
+        return back_home(torch.zeros(out_shape, dtype=loc.dtype, device=loc.device), home)
+    u_in = _rng.take_injected("uniform")
+    if u_in is not None:
+        u_in = to_compute(u_in).to(loc.dtype).reshape(K, N).contiguous()
+    mode = KBCAST if K > 1 else FULL
+    if reparameterized:
+        z = _LocScaleSample.apply(loc, scale, family, (mode, mode), K, N, u_in)
+    else:
+        with torch.no_grad():
+            z = _LocScaleSample.apply(loc.detach(), scale.detach(), family, (mode, mode), K, N, u_in)
+    return back_home(z.reshape(out_shape), home)
+
+
+# --------------------------------------------------------------------------------------------
 # Bernoulli
 # --------------------------------------------------------------------------------------------
 class _BernoulliLogPmf(torch.autograd.Function):

@@ -1,7 +1,10 @@
-"""Hot-path distributions.  The reference's other wrappers over torch.distributions (beta, gamma,
-laplace, ...; zhusuan/distributions/__init__.py:3-13) are outside the accelerated path and are not
-rebuilt here."""
+"""Hot-path distributions, plus the two location-scale families of SURVEY 8(f)-4 (Logistic, Laplace) on the same
+kernel templates.  The reference's remaining wrappers over torch.distributions (beta, gamma, poisson, studentT,
+uniform, exponential; zhusuan/distributions/__init__.py:3-13) are outside the accelerated path and are not rebuilt
+here."""
 from .base import *
 from .normal import *
 from .bernoulli import *
 from .categorical import *
+from .logistic import *
+from .laplace import *

@@ -1,0 +1,52 @@
+"""Univariate Logistic — drop-in for zhusuan/distributions/logistic.py of the reference.
+
+sample  : loc + scale * (log u - log(1 - u)), u from in-kernel Philox, reparameterised (reference :56-70 draws u on
+          the CPU); log_prob: -z - 2 softplus(-z) - log(scale), z = (x - loc) / scale, with the event-axis sum fused
+          (reference :72-83).  Same kernel templates as the Normal node.
+"""
+import torch
+
+from zhusuan._shapes import broadcast_shapes as _bshapes
+from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
+from zhusuan.distributions.utils import assert_same_log_float_dtype, check_broadcast
+from zhusuan import _ops, _backend as _be
+
+__all__ = ['Logistic']
+
+
+class Logistic(Distribution):
+    def __init__(self, loc, scale, dtype=None, is_continuous=True, group_ndims=0, device=DEFAULT_DEVICE, **kwargs):
+        device = resolve_device(device, loc, scale)
+        self._loc = torch.as_tensor(loc, dtype=dtype).to(device)
+        self._scale = torch.as_tensor(scale, dtype=dtype).to(device)
+        if torch.less_equal(self._scale, 0.).any():
+            raise ValueError("scale less than zero")
+        check_broadcast(self._loc, self._scale)
+        dtype = assert_same_log_float_dtype([(self._loc, "Logistic.loc"), (self._scale, "Logistic.scale")])
+        super(Logistic, self).__init__(dtype, is_continuous, is_reparameterized=True, group_ndims=group_ndims,
+                                       device=device, **kwargs)
+
+    @property
+    def loc(self):
+        return self._loc
+
+    @property
+    def scale(self):
+        return self._scale
+
+    def _batch_shape(self):
+        return _bshapes(self._loc.shape, self._scale.shape)
+
+    def _sample(self, n_samples=1, **kwargs):
+        z = _ops.locscale_sample(_be.FAM_LOGISTIC, self._loc, self._scale, n_samples, True)
+        self.sample_cache = z
+        return z
+
+    def _log_prob_event(self, given, n_event):
+        return _ops.locscale_log_prob(_be.FAM_LOGISTIC, self._given(given), self._loc, self._scale, n_event)
+
+    def _log_prob(self, sample=None, **kwargs):
+        return self._log_prob_event(sample, 0)
+
+    def _prob(self, given):
+        return torch.exp(self._log_prob(given))

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from zhusuan.framework.stochastic_tensor import StochasticTensor
-from zhusuan.distributions import Distribution, Normal, Bernoulli, Categorical
+from zhusuan.distributions import Distribution, Normal, Bernoulli, Categorical, Logistic, Laplace
 
 __all__ = ['BayesianNet']
 
@@ -18,9 +18,11 @@ name_mapping = {
     "Normal": Normal,
     "Bernoulli": Bernoulli,
     "Categorical": Categorical,
+    "Logistic": Logistic,
+    "Laplace": Laplace,
 }
 
-_OUT_OF_SCOPE = ("Beta", "Exponential", "Gamma", "Laplace", "Logistic", "Poisson", "StudentT", "Uniform")
+_OUT_OF_SCOPE = ("Beta", "Exponential", "Gamma", "Poisson", "StudentT", "Uniform")
 
 
 class BayesianNet(nn.Module):
@@ -113,6 +115,22 @@ class BayesianNet(nn.Module):
             raise ValueError("name of stochastic_node must be str")
         dist = Categorical(logits=logits, probs=probs, dtype=dtype, is_continuous=is_continuous,
                            group_ndims=group_ndims, device=self.device, **kwargs)
+        return self._register(name, dist, n_samples, kwargs)
+
+    def laplace(self, name, loc, scale, dtype=None, is_continuous=True, group_ndims=0, n_samples=None, **kwargs):
+        if not isinstance(name, str):
+            raise ValueError("name of stochastic_node must be str")
+        dist = Laplace(loc=loc, scale=scale, dtype=dtype, is_continuous=is_continuous, group_ndims=group_ndims,
+                       device=self.device, **kwargs)
+        return self._register(name, dist, n_samples, kwargs)
+
+    def logistic(self, name, loc, scale, dtype=None, is_continuous=True, group_ndims=0, n_samples=None, **kwargs):
+        """As in the reference, `bn.logistic` builds a LAPLACE node (framework/bn.py:336-352 constructs
+        `Laplace(...)`).  Use `bn.sn(Logistic(...), name)` for a Logistic node."""
+        if not isinstance(name, str):
+            raise ValueError("name of stochastic_node must be str")
+        dist = Laplace(loc=loc, scale=scale, dtype=dtype, is_continuous=is_continuous, group_ndims=group_ndims,
+                       device=self.device, **kwargs)
         return self._register(name, dist, n_samples, kwargs)
 
     # -- log joint ------------------------------------------------------------------------------
