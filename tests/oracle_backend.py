@@ -48,6 +48,60 @@ def normal_logprob_bwd(g, x, xm, mean, mm, std, sm, K, M, E, need_x, need_mean, 
     return (_t(dx, x) if need_x else None, _t(dm, x) if need_mean else None, _t(ds, x) if need_std else None)
 
 
+def normal_latent_fwd(mean, std, mode, K, M, E, prior_mean=None, prior_std=None, eps_in=None, want_logq=True,
+                      want_logp=True, seed=0, offset=0):
+    dt = _np(mean).dtype
+    eps = (O.philox_normal(K * M * E, seed, offset).astype(dt) if eps_in is None else _np(eps_in)).reshape(K, M * E)
+    z = O.normal_sample(_np(mean), _np(std), eps, K, M * E).reshape(K, M, E)
+    logq = O.normal_logprob_fwd(z, _np(mean), _np(std), K, M, E) if want_logq else None
+    logp = None
+    if want_logp:
+        pm_ = np.zeros((M, E), dt) if prior_mean is None else _np(prior_mean)
+        ps_ = np.ones((M, E), dt) if prior_std is None else _np(prior_std)
+        logp = O.normal_logprob_fwd(z, pm_, ps_, K, M, E)
+    return _t(z, mean), None if logq is None else _t(logq, mean), None if logp is None else _t(logp, mean)
+
+
+def normal_latent_bwd(dlogq, dlogp, dz_up, z, mean, std, mode, K, M, E, prior_mean=None, prior_std=None,
+                      reparameterized=True):
+    dt = _np(z).dtype
+    zz, m, sd = _np(z).reshape(K, M, E), _np(mean), _np(std)
+    gq = np.zeros((K, M), dt) if dlogq is None else _np(dlogq).reshape(K, M)
+    dz_q, dm, ds = O.normal_logprob_bwd(gq, zz, m, sd, K, M, E)
+    dzt = dz_q.reshape(K, M, E).copy()
+    if dlogp is not None:
+        pm_ = np.zeros((M, E), dt) if prior_mean is None else _np(prior_mean)
+        ps_ = np.ones((M, E), dt) if prior_std is None else _np(prior_std)
+        dz_p, _, _ = O.normal_logprob_bwd(_np(dlogp).reshape(K, M), zz, pm_, ps_, K, M, E)
+        dzt = dzt + dz_p.reshape(K, M, E)
+    if dz_up is not None:
+        dzt = dzt + _np(dz_up).reshape(K, M, E)
+    dm, ds = dm.reshape(m.shape).astype(dt), ds.reshape(sd.shape).astype(dt)
+    if reparameterized:
+        eps = ((zz - m.reshape((-1, M, E))) / sd.reshape((-1, M, E))).astype(dt)
+        sm, ss = O.normal_sample_bwd(dzt.reshape(K, M * E), eps.reshape(K, M * E), m, sd, K, M * E)
+        dm, ds = dm + sm.reshape(m.shape), ds + ss.reshape(sd.shape)
+    return _t(dm, z), _t(ds, z)
+
+
+def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want_logq=True, want_logp=True, seed=0,
+                         offset=0):
+    dt = _np(probs).dtype
+    u = (O.philox_uniform(K * M * E, seed, offset).astype(dt) if u_in is None else _np(u_in)).reshape(K, M * E)
+    z = O.bernoulli_sample(_np(probs), u, K, M * E).reshape(K, M, E)
+    logq = O.bernoulli_logpmf_fwd(z, _np(probs), K, M, E) if want_logq else None
+    logp = None
+    if want_logp:
+        pp = np.full((M, E), 0.5, dt) if prior_probs is None else _np(prior_probs)
+        logp = O.bernoulli_logpmf_fwd(z, pp, K, M, E)
+    return _t(z, probs), None if logq is None else _t(logq, probs), None if logp is None else _t(logp, probs)
+
+
+def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E):
+    dp = O.bernoulli_logpmf_bwd(_np(dlogq).reshape(K, M), _np(z).reshape(K, M, E), _np(probs), K, M, E)
+    return _t(dp.reshape(probs.shape), probs)
+
+
 def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0):
     u = O.philox_uniform(K * N, seed, offset).astype(_np(probs).dtype).reshape(K, N) if u_in is None else _np(u_in)
     return _t(O.bernoulli_sample(_np(probs), u.reshape(K, N), K, N), probs)
@@ -207,7 +261,8 @@ def _next_philox(device):
 def install(monkeypatch):
     """Patch the product's backend / device helpers with the CPU stand-ins above."""
     from zhusuan import _backend, _ops, _rng
-    for name in ("normal_sample", "normal_sample_bwd", "normal_logprob_fwd", "normal_logprob_bwd", "bernoulli_sample",
+    for name in ("normal_sample", "normal_sample_bwd", "normal_logprob_fwd", "normal_logprob_bwd", "normal_latent_fwd", "normal_latent_bwd",
+                 "bernoulli_latent_fwd", "bernoulli_latent_bwd", "bernoulli_sample",
                  "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "locscale_sample", "locscale_sample_bwd",
                  "locscale_logprob_fwd", "locscale_logprob_bwd", "categorical_sample", "categorical_logpmf_fwd",
                  "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",

@@ -601,6 +601,45 @@ def test_bn_logistic_builds_laplace_like_the_reference(dev):
     assert type(net.nodes["c"].dist).__name__ == "Logistic"
 
 
+@pytest.mark.parametrize("est,latent", [("sgvb", "normal"), ("vimco", "bernoulli")])
+def test_fused_latent_route_equals_separate_kernels(dev, golden, est, latent):
+    """A latent node whose reductions end in an event sum draws its sample and log q in ONE launch
+    (distribution.sample_for_node); loss and gradients equal the separate sample / log-prob kernels' on the same
+    injected noise, and the node protocol (sample_cache, log_prob at another value) is unchanged."""
+    import zhusuan.distributions as D
+    g = golden("iw_path")
+    K = int(g["K"])
+    res = {}
+    for fused in (True, False):
+        D.FUSED_LATENT = fused
+        try:
+            probs = T(g["probs"], dev, torch.float32, True)
+            if latent == "normal":
+                a, b = T(g["mean"], dev, torch.float32, True), T(g["logstd"], dev, torch.float32, True)
+                inj = dict(normal=[T(g["eps"], dev)] * 2)
+            else:
+                a, b = T(g["probs_q"], dev, torch.float32, True), None
+                inj = dict(uniform=[T(g["u"], dev)] * 2)
+            gen, var = _PathGen(probs, K, latent), _PathVar(a, b, K, latent, est == "sgvb")
+            obj = ImportanceWeightedObjective(gen, var, axis=0, estimator=est)
+            with _rng.inject(**inj):
+                loss = obj({"x": T(g["x"], dev)})
+            node = var.nodes["z"]
+            used = node.dist._logq_cache is not None
+            leaves = [probs, a] + ([b] if b is not None else [])
+            grads = torch.autograd.grad(loss, leaves)
+            other = node.log_prob(torch.zeros_like(node.dist.sample_cache))  # not the cached sample: separate kernel
+            res[fused] = (loss, grads, node.log_prob(), other, used)
+        finally:
+            D.FUSED_LATENT = True
+    assert res[True][4] and not res[False][4]
+    close(res[True][0], res[False][0].detach().cpu().numpy(), 2e-6)
+    for ga, gb in zip(res[True][1], res[False][1]):
+        close(ga, gb.detach().cpu().numpy(), 2e-5)
+    close(res[True][2], res[False][2].detach().cpu().numpy(), 2e-6)
+    close(res[True][3], res[False][3].detach().cpu().numpy(), 2e-6)
+
+
 def test_particle_linear_matches_reference_layer():
     """zhusuan.particle_linear == the repeat + matmul layer of the reference's BNN examples (bnn_vi.py:39-45), values
     and gradients, without materialising [K, B, n_out, n_in + 1]."""

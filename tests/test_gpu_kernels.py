@@ -598,6 +598,28 @@ def test_iw_step_host_begin_wait_device_scalars(B):
     assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 
 
+# ----------------------------------------------------------------------------- few, long rows (config 4 shapes)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("K,E", [(100, 8192), (100, 4601), (3, 2048), (7, 100003)])
+def test_normal_logprob_few_long_rows(oracle, dt, K, E):
+    """The BNN likelihood [K, 1, batch] (bnn_vi.py: y under mean[K, b], scalar std, summed over the batch) and the
+    weight nodes [K, 1, 4601]: one CTA per row instead of one warp per row."""
+    rng = np.random.RandomState(E % 97)
+    mean = rng.standard_normal((K, 1, E)).astype(dt)
+    y = rng.standard_normal((1, E)).astype(dt)
+    std = np.array([0.3], dt)
+    g = rng.standard_normal((K, 1)).astype(dt)
+    rt = 1e-5 if dt == np.float32 else 1e-11
+    out = be.normal_logprob_fwd(dev(y), KBCAST, dev(mean), FULL, dev(std), SCALAR, K, 1, E)
+    ref = oracle.normal_logprob_fwd(y.astype(np.float64), mean.astype(np.float64), np.full((1, E), 0.3), K, 1, E)
+    close(host(out), ref, rt)
+    _, dmean, _ = be.normal_logprob_bwd(dev(g), dev(y), KBCAST, dev(mean), FULL, dev(std), SCALAR, K, 1, E, False, True,
+                                        False)
+    _, rdm, _ = oracle.normal_logprob_bwd(g.astype(np.float64), y.astype(np.float64), mean.astype(np.float64),
+                                          np.full((1, E), 0.3), K, 1, E)
+    close(host(dmean), rdm.reshape(K, 1, E), rt)
+
+
 # ----------------------------------------------------------------------------- Logistic / Laplace nodes
 @pytest.mark.parametrize("dn", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["logistic", "laplace"])

@@ -12,6 +12,8 @@
 // CPU-side RNG + H2D copy by in-kernel Philox, and the ~8 (fwd) / ~12 (bwd) elementwise aten
 // kernels plus the event-axis reduction by one pass each.
 #include "zs_common.cuh"
+
+#include <cooperative_groups.h>
 #include "zs_philox.cuh"
 
 namespace zs {
@@ -241,8 +243,105 @@ __global__ void __launch_bounds__(256) k_rows_fwd(T* __restrict__ out, Operand<T
                 }
             }
         }
-        acc = group_sum<LPR>(acc);
+        if (LPR > 32) {
+            // one CTA per row (few, long rows: the BNN likelihood [K, 1, batch]): warp sums, then a fixed-order
+            // sum of the warps' partials
+            __shared__ T s_part[8];
+            acc = warp_sum(acc);
+            __syncthreads();  // s_part may still be read from the previous row
+            if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            acc = T(0);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += s_part[w];
+        } else {
+            acc = group_sum<(LPR > 32 ? 32 : LPR)>(acc);
+        }
         if (valid && lane == 0) out[r] = Op::finish(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// forward for FEW, LONG rows (the BNN likelihood [K, 1, batch] of bnn_vi.py: K = 100 rows of 131 072 datapoints):
+// one warp -- or one CTA -- per row leaves most of the machine idle (measured 118 GB/s, then 870 GB/s).  Here a
+// thread-block CLUSTER of 8 CTAs owns a row: each CTA reduces a contiguous eighth, the partial sums meet in
+// distributed shared memory (cluster.map_shared_rank) and rank 0 adds them in fixed order.  One launch, no
+// workspace, deterministic.
+// ---------------------------------------------------------------------------
+constexpr int ROWC = 8;  // CTAs per row
+
+template <typename T, typename Op, bool VEC>
+__global__ void __cluster_dims__(ROWC, 1, 1) __launch_bounds__(256)
+    k_rows_fwd_cluster(T* __restrict__ out, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K, int64_t M, int64_t E) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int VN = Pack<T>::N;
+    __shared__ T s_warp[8];
+    __shared__ T s_part;
+    const unsigned rank = cluster.block_rank();
+    const int64_t R = K * M;
+    const T xs = x.mode == ZS_SCALAR ? x.p[0] : T(0);
+    const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
+    const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
+    const bool hasb = b.p != nullptr;
+    // contiguous segment of this CTA, a multiple of the pack width
+    const int64_t per = ((E + (int64_t)ROWC * VN - 1) / ((int64_t)ROWC * VN)) * VN;
+    const int64_t lo = (int64_t)rank * per, hi = lo + per < E ? lo + per : E;
+    for (int64_t r = blockIdx.x / ROWC; r < R; r += gridDim.x / ROWC) {
+        const int64_t m = r % M;
+        const T* xr = x.row(r, m, E);
+        const T* ar = a.row(r, m, E);
+        const T* br = hasb ? b.row(r, m, E) : nullptr;
+        T acc = T(0);
+        if (VEC) {
+#pragma unroll 4
+            for (int64_t e = lo + (int64_t)threadIdx.x * VN; e < hi; e += 256 * VN) {
+                Pack<T> px, pa, pb;
+                if (x.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) px.v[j] = xs;
+                } else {
+                    px = x.mode == ZS_FULL ? ld_pack_stream(xr + e) : ld_pack(xr + e);
+                }
+                if (a.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) pa.v[j] = as;
+                } else {
+                    pa = a.mode == ZS_FULL ? ld_pack_stream(ar + e) : ld_pack(ar + e);
+                }
+                if (!hasb || b.mode == ZS_SCALAR) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) pb.v[j] = bs;
+                } else {
+                    pb = b.mode == ZS_FULL ? ld_pack_stream(br + e) : ld_pack(br + e);
+                }
+#pragma unroll
+                for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+            }
+        } else {
+            for (int64_t e = lo + threadIdx.x; e < hi; e += 256) {
+                const T xv = x.mode == ZS_SCALAR ? xs : xr[e];
+                const T av = a.mode == ZS_SCALAR ? as : ar[e];
+                const T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
+                acc += Op::term(xv, av, bv);
+            }
+        }
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T t = T(0);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_warp[w];
+            s_part = t;
+        }
+        cluster.sync();
+        if (rank == 0 && threadIdx.x == 0) {
+            T t = T(0);
+            for (unsigned q = 0; q < ROWC; ++q) t += *cluster.map_shared_rank(&s_part, q);
+            out[r] = Op::finish(t);
+        }
+        cluster.sync();  // partials are read before the next row overwrites them / before any CTA exits
     }
 }
 
@@ -252,7 +351,7 @@ __global__ void __launch_bounds__(256) k_rows_fwd(T* __restrict__ out, Operand<T
 template <typename T, typename Op, int LPR, bool VEC>
 __global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restrict__ da, T* __restrict__ db,
                                                   const T* __restrict__ g, Operand<T> x, Operand<T> a, Operand<T> b,
-                                                  int64_t K, int64_t M, int64_t E) {
+                                                  int64_t K, int64_t M, int64_t E, int64_t gdiv) {
     constexpr int VN = Pack<T>::N;
     const int lane = threadIdx.x % LPR;
     const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -265,7 +364,7 @@ __global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restr
 
     for (int64_t r = grp; r < R; r += ngrp) {
         const int64_t m = r % M;
-        const T gv = g[r];
+        const T gv = g[r / gdiv];  // gdiv > 1: a long row was cut into gdiv virtual rows that share its upstream gradient
         const T* xr = x.row(r, m, E);
         const T* ar = a.row(r, m, E);
         const T* br = hasb ? b.row(r, m, E) : nullptr;
@@ -573,7 +672,7 @@ static int launch_rows_fwd(T* out, Operand<T> x, Operand<T> a, Operand<T> b, int
     const int64_t R = K * M;
     const int rows_per_block = 256 / LPR;
     const int grid = grid_for(R, rows_per_block, 256);
-    const bool vec = LPR == 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N;
+    const bool vec = LPR >= 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N;
     if (vec)
         k_rows_fwd<T, Op, LPR, true><<<grid, 256, 0, st>>>(out, x, a, b, K, M, E);
     else
@@ -588,21 +687,33 @@ static int dispatch_rows_fwd(T* out, Operand<T> x, Operand<T> a, Operand<T> b, i
     if (K * M == 0) return ZS_OK;
     if (E <= 2) return launch_rows_fwd<T, Op, 1>(out, x, a, b, K, M, E, st);
     if (E <= 48) return launch_rows_fwd<T, Op, 8>(out, x, a, b, K, M, E, st);
+    // few, long rows (one warp per row would leave most of the machine idle): one CTA per row
+    if (E >= 2048 && K * M * 32 < (int64_t)sm_count() * 1024) {
+        const int64_t R = K * M;
+        const int64_t rows_in_flight = R < 2048 ? R : 2048;
+        const bool vec = vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E);
+        if (vec)
+            k_rows_fwd_cluster<T, Op, true><<<(unsigned)(rows_in_flight * ROWC), 256, 0, st>>>(out, x, a, b, K, M, E);
+        else
+            k_rows_fwd_cluster<T, Op, false><<<(unsigned)(rows_in_flight * ROWC), 256, 0, st>>>(out, x, a, b, K, M, E);
+        ZS_LAUNCH_CHECK("k_rows_fwd_cluster");
+        return ZS_OK;
+    }
     return launch_rows_fwd<T, Op, 32>(out, x, a, b, K, M, E, st);
 }
 
 template <typename T, typename Op, int LPR>
 static int launch_rows_bwd(T* dx, T* da, T* db, const T* g, Operand<T> x, Operand<T> a, Operand<T> b, int64_t K,
-                           int64_t M, int64_t E, cudaStream_t st) {
+                           int64_t M, int64_t E, cudaStream_t st, int64_t gdiv = 1) {
     const int64_t R = K * M;
     const int rows_per_block = 256 / LPR;
     const int grid = grid_for(R, rows_per_block, 256);
-    const bool vec = LPR == 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N &&
+    const bool vec = LPR >= 32 && vec_ok(x, E) && vec_ok(a, E) && vec_ok(b, E) && E >= Pack<T>::N &&
                      aligned16(dx) && aligned16(da) && aligned16(db);
     if (vec)
-        k_rows_bwd<T, Op, LPR, true><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E);
+        k_rows_bwd<T, Op, LPR, true><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E, gdiv);
     else
-        k_rows_bwd<T, Op, LPR, false><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E);
+        k_rows_bwd<T, Op, LPR, false><<<grid, 256, 0, st>>>(dx, da, db, g, x, a, b, K, M, E, gdiv);
     ZS_LAUNCH_CHECK("k_rows_bwd");
     return ZS_OK;
 }
@@ -630,6 +741,16 @@ static int dispatch_bwd(T* dx, T* da, T* db, const T* g, Operand<T> x, Operand<T
     }
     if (E <= 2) return launch_rows_bwd<T, Op, 1>(dx, da, db, g, x, a, b, K, M, E, st);
     if (E <= 48) return launch_rows_bwd<T, Op, 8>(dx, da, db, g, x, a, b, K, M, E, st);
+    if (E >= 2048 && K * M * 32 < (int64_t)sm_count() * 1024) {
+        // few, long rows: the backward has no reduction along the row, so a row is simply cut into S virtual rows
+        // [K, M*S, E/S] (pure re-indexing for FULL and KBCAST operands alike) until the machine is full
+        int64_t S = 1;
+        while (S < 256 && E % (2 * S * Pack<T>::N) == 0 && E / (2 * S) >= 1024 &&
+               K * M * S * 32 < (int64_t)sm_count() * 2048)
+            S *= 2;
+        if (S > 1) return launch_rows_bwd<T, Op, 32>(dx, da, db, g, x, a, b, K, M * S, E / S, st, S);
+        return launch_rows_bwd<T, Op, 256>(dx, da, db, g, x, a, b, K, M, E, st);
+    }
     return launch_rows_bwd<T, Op, 32>(dx, da, db, g, x, a, b, K, M, E, st);
 }
 

@@ -265,6 +265,115 @@ def normal_sample(mean, std, n_samples, reparameterized):
 
 
 # --------------------------------------------------------------------------------------------
+# Latent nodes: sample AND log q(sample) from one launch (zs_*_latent_fwd), joint backward (zs_*_latent_bwd)
+# --------------------------------------------------------------------------------------------
+class _NormalLatent(torch.autograd.Function):
+    """(mean, std) -> (z [K,M,E], log q(z) [K,M]).  backward receives the gradients reaching z (decoder, prior node)
+    and log q and returns d/dmean, d/dstd from ONE launch: the density terms, the pathwise term through
+    z = mean + std*eps when reparameterised (eps recovered from the sample), summed over particles."""
+
+    @staticmethod
+    def forward(ctx, mean, std, mode, K, M, E, eps_in, reparameterized):
+        seed, offset = (0, 0) if eps_in is not None else _rng.next_philox(mean.device)
+        r = be.normal_latent_fwd(mean, std, mode, K, M, E, eps_in=eps_in, want_logp=False, seed=seed, offset=offset)
+        if r is None:
+            raise be.BackendError("latent kernel refused a shape latent_supported() accepted")
+        z, logq, _ = r
+        ctx.save_for_backward(z, mean, std)
+        ctx.cfg = (mode, K, M, E, reparameterized)
+        if not reparameterized:
+            ctx.mark_non_differentiable(z)
+        return z, logq
+
+    @staticmethod
+    def backward(ctx, dz, dlogq):
+        z, mean, std = ctx.saved_tensors
+        mode, K, M, E, reparam = ctx.cfg
+        dz = dz.contiguous() if (dz is not None and reparam) else None
+        dlogq = None if dlogq is None else dlogq.contiguous()
+        dmean, dstd = be.normal_latent_bwd(dlogq, None, dz, z, mean, std, mode, K, M, E, reparameterized=reparam)
+        return dmean, dstd, None, None, None, None, None, None
+
+
+class _BernoulliLatent(torch.autograd.Function):
+    """probs -> (z, log q(z)); samples carry no gradient, log q's gradient reaches probs in one launch."""
+
+    @staticmethod
+    def forward(ctx, probs, mode, K, M, E, u_in):
+        seed, offset = (0, 0) if u_in is not None else _rng.next_philox(probs.device)
+        r = be.bernoulli_latent_fwd(probs, mode, K, M, E, u_in=u_in, want_logp=False, seed=seed, offset=offset)
+        if r is None:
+            raise be.BackendError("latent kernel refused a shape latent_supported() accepted")
+        z, logq, _ = r
+        ctx.save_for_backward(z, probs)
+        ctx.cfg = (mode, K, M, E)
+        ctx.mark_non_differentiable(z)
+        return z, logq
+
+    @staticmethod
+    def backward(ctx, dz, dlogq):
+        z, probs = ctx.saved_tensors
+        mode, K, M, E = ctx.cfg
+        if dlogq is None:
+            return torch.zeros_like(probs), None, None, None, None, None
+        return be.bernoulli_latent_bwd(dlogq.contiguous(), z, probs, mode, K, M, E), None, None, None, None, None
+
+
+def _aligned(t):
+    """Contiguous and 16-byte aligned (a view into the middle of a buffer may not be); differentiable."""
+    t = t.contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
+def latent_supported(base_shape, n_event, dtype, *params):
+    """Shapes the fused latent kernels take: the last n_event axes form an event row of E % 4 == 0 elements, every
+    parameter has exactly the batch shape (no inner broadcasting), float32 / float64."""
+    if n_event < 1 or n_event > len(base_shape) or dtype not in (torch.float32, torch.float64):
+        return False
+    E = _prod(base_shape[len(base_shape) - n_event:])
+    if E == 0 or E % 4 != 0 or _prod(base_shape) == 0:
+        return False
+    return all(tuple(p.shape) == tuple(base_shape) for p in params)
+
+
+def normal_sample_logq(mean, std, n_samples, reparameterized, n_event):
+    """Normal._sample (normal.py:89-107) and the node's log q at that sample (normal.py:109-126 + the event sums) from
+    one launch.  Returns (z, logq): z like normal_sample(), logq of shape ([K] +) batch_shape[:-n_event]."""
+    home = mean.device
+    mean, std = to_compute(mean), to_compute(std)
+    K = int(n_samples)
+    base = tuple(mean.shape)
+    E = _prod(base[len(base) - n_event:])
+    M = _prod(base[:len(base) - n_event])
+    out_shape = ((K,) if K > 1 else ()) + base
+    lead = ((K,) if K > 1 else ()) + base[:len(base) - n_event]
+    eps_in = _rng.take_injected("normal")
+    if eps_in is not None:
+        eps_in = to_compute(eps_in).to(mean.dtype).reshape(K, M, E).contiguous()
+    mode = KBCAST if K > 1 else FULL
+    mc, sc = _aligned(mean.reshape(M, E)), _aligned(std.reshape(M, E))
+    z, logq = _NormalLatent.apply(mc, sc, mode, K, M, E, eps_in, bool(reparameterized))
+    return back_home(z.reshape(out_shape), home), logq.reshape(lead)
+
+
+def bernoulli_sample_logq(probs, n_samples, n_event):
+    home = probs.device
+    probs = to_compute(probs)
+    K = int(n_samples)
+    base = tuple(probs.shape)
+    E = _prod(base[len(base) - n_event:])
+    M = _prod(base[:len(base) - n_event])
+    out_shape = ((K,) if K > 1 else ()) + base
+    lead = ((K,) if K > 1 else ()) + base[:len(base) - n_event]
+    u_in = _rng.take_injected("uniform")
+    if u_in is not None:
+        u_in = to_compute(u_in).to(probs.dtype).reshape(K, M, E).contiguous()
+    mode = KBCAST if K > 1 else FULL
+    z, logq = _BernoulliLatent.apply(_aligned(probs.reshape(M, E)), mode, K, M, E, u_in)
+    return back_home(z.reshape(out_shape), home), logq.reshape(lead)
+
+
+# --------------------------------------------------------------------------------------------
 # Logistic / Laplace: the Normal node's kernel templates with another noise transform / log-density
 # --------------------------------------------------------------------------------------------
 class _LocScaleLogProb(torch.autograd.Function):

@@ -8,3 +8,7 @@ from .bernoulli import *
 from .categorical import *
 from .logistic import *
 from .laplace import *
+
+# Latent nodes draw their sample and its log q in one launch when the node's event reduction allows it
+# (zs_normal_latent_fwd / zs_bernoulli_latent_fwd); set to False to always use the separate kernels.
+FUSED_LATENT = True

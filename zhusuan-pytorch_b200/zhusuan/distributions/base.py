@@ -45,6 +45,7 @@ class Distribution(object):
         self._use_path_derivative = use_path_derivative
         self._device = device
         self.sample_cache = None
+        self._logq_cache = None  # (sample, n_event, log q) of the last fused draw, see sample_for_node
         if isinstance(group_ndims, int):
             if group_ndims < 0:
                 raise ValueError("group_ndims must be non-negative.")
@@ -90,6 +91,32 @@ class Distribution(object):
 
     def _sample(self, n_samples, **kwargs):
         raise NotImplementedError()
+
+    # -- B200 build: a node that knows its event reduction can ask for the sample and its log q together
+    def _sample_fused(self, n_samples, n_event):
+        """Return (sample, log q(sample) summed over the last n_event axes) from one launch, or None when the
+        distribution / shape has no fused form."""
+        return None
+
+    def sample_for_node(self, n_samples, n_event):
+        """`sample()` for a StochasticTensor that will evaluate `log_prob()` at this sample with `n_event`
+        trailing axes summed: the log-density is produced by the sampling launch and kept for that call."""
+        K = 1 if n_samples is None else int(n_samples)
+        from zhusuan import distributions as _d
+        fused = self._sample_fused(K, n_event) if _d.FUSED_LATENT else None
+        if fused is None:
+            self._logq_cache = None
+            return self.sample(n_samples)
+        z, logq = fused
+        self.sample_cache = z
+        self._logq_cache = (z, n_event, logq)
+        return z
+
+    def cached_log_prob(self, given, n_event):
+        c = self._logq_cache
+        if c is not None and c[0] is given and c[1] == n_event:
+            return c[2]
+        return None
 
     def log_prob(self, given):
         """Log density / mass at `given`, summed over the last ``group_ndims`` axes."""

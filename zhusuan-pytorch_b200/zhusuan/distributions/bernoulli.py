@@ -68,6 +68,13 @@ class Bernoulli(Distribution):
         self.sample_cache = s
         return s
 
+    def _sample_fused(self, n_samples, n_event):
+        if self._from_logits is not None:
+            return None
+        if not _ops.latent_supported(tuple(self._probs.shape), n_event, self._dtype, self._probs):
+            return None
+        return _ops.bernoulli_sample_logq(self._probs, n_samples, n_event)
+
     def _log_prob_event(self, given, n_event):
         if self._from_logits is not None:
             return _ops.bernoulli_log_prob(self._given(given), self._from_logits, n_event, logits=True)

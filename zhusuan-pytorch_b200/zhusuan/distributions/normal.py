@@ -55,6 +55,11 @@ class Normal(Distribution):
         self.sample_cache = z
         return z
 
+    def _sample_fused(self, n_samples, n_event):
+        if not _ops.latent_supported(tuple(self._mean.shape), n_event, self._dtype, self._mean, self._std):
+            return None
+        return _ops.normal_sample_logq(self._mean, self._std, n_samples, self.is_reparameterized, n_event)
+
     def _log_prob_event(self, given, n_event):
         return _ops.normal_log_prob(self._given(given), self._mean, self._std, n_event)
 

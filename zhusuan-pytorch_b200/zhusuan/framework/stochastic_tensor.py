@@ -67,14 +67,26 @@ class StochasticTensor(object):
         if value is not None:
             self._dist.sample_cache = value
             return value
-        return self._dist.sample(n_samples=self._n_samples)
+        return self._draw()
+
+    def _draw(self):
+        """A new sample; when the node's reductions end in an event sum the kernels can take, log q at that sample
+        comes out of the same launch and is kept for `log_prob()` (distribution.sample_for_node)."""
+        dist = self._dist
+        K = self._n_samples
+        try:
+            shape = (((int(K),) if K is not None and int(K) > 1 else ()) + tuple(dist.batch_shape))
+            n_event, _, _ = self.reduction_plan(shape)
+        except Exception:
+            return dist.sample(n_samples=K)
+        return dist.sample_for_node(K, n_event)
 
     def sample(self, force=False):
         value = None if force else self._observed_value()
         if value is not None:
             self._dist.sample_cache = value
             return value
-        return self._dist.sample(n_samples=self._n_samples)
+        return self._draw()
 
     @property
     def shape(self):
@@ -103,7 +115,12 @@ class StochasticTensor(object):
         dist = self._dist
         given = dist._given(sample)
         n_event, mean_dims, sum_dims = self.reduction_plan(given.shape)
-        lp = dist._log_prob_event(given, n_event)
+        lp = dist.cached_log_prob(given, n_event) if sample is None else None
+        if lp is None:
+            lp = dist._log_prob_event(given, n_event)
+        else:
+            from zhusuan import _ops
+            lp = _ops.back_home(lp, given.device)
         if mean_dims:
             lp = torch.mean(lp, mean_dims, keepdim=True)
         if sum_dims:
