@@ -222,19 +222,24 @@ int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, z
 int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64_t K, int64_t B,
                         zs_stream_t stream);
 
-/* ---- fused resident-column kernel: Bernoulli likelihood + objective, fwd+bwd --
- * For every batch column b the K particle rows probs[:, b, :] are staged ONCE in
- * shared memory (bulk async copies), their log-pmf at x[b,:] is reduced, combined
- * with the rest of the log-weight, the estimator weights are formed, and dprobs is
- * produced from the resident rows — probs is read from HBM once, dprobs written once.
+/* ---- fused likelihood + objective kernel: Bernoulli likelihood + IW objective, fwd+bwd in one launch --
+ * Replaces, for a Bernoulli likelihood node over [K,B,X] probabilities, Bernoulli._log_prob + the event sum
+ * (bernoulli.py:84-95, stochastic_tensor.py:160-181), the log-joint sum (importance_weighted_objective.py:66-77),
+ * the estimator (:102-191) and the autograd backward of all three.
+ * For every batch column b the K particle rows probs[:, b, :] are brought into shared memory ONCE (TMA tensor
+ * copies of {inner, 1, K} boxes; persistent warp-specialised CTAs, one per SM), their log-pmf at x[b,:] is
+ * reduced, combined with the rest of the log-weight, the estimator weights are formed, and dprobs is produced
+ * from the resident rows -- probs is read from HBM once, dprobs written once.
  *   logp_other[K,B] = sum of the other generator log-probs (may be NULL = 0)
  *   logq[K,B]       = variational log-prob (may be NULL = 0 for SGVB; required for VIMCO)
  *   log w = logpx + logp_other - logq
- *   cost[B], dprobs[K,B,X], dlogp[K,B] (= gradient wrt every generator log-prob term),
- *   dlogq[K,B]; logpx_out[K,B] optional copy of the likelihood term.
- * Requires f32, X % 4 == 0, 16-byte aligned probs/dprobs/x and
- * zs_iw_bernoulli_fused_smem_bytes(K,X) <= device opt-in shared memory; otherwise
- * returns ZS_ERR_UNSUPPORTED and the caller uses the two-pass entry points.         */
+ *   cost[B], dprobs[K,B,X] (may be NULL: forward only), dlogp[K,B] (= gradient wrt every generator log-prob
+ *   term), dlogq[K,B]; logpx_out[K,B] optional copy of the likelihood term.
+ * Kernel selection: fixed-geometry box kernel for X in {128, 256, 512, 784, 1024} and K <= 50,
+ * generic box kernel for other K <= 50, row-streaming ring kernel for any K <= 4096, re-read-from-L2 kernel last.
+ * Requires f32, X % 4 == 0 and 16-byte aligned probs / dprobs / x; otherwise ZS_ERR_UNSUPPORTED / ZS_ERR_ALIGN and
+ * the caller uses the two-pass entry points.  zs_iw_bernoulli_fused_smem_bytes(K,X) reports the shared memory of
+ * the legacy whole-column variant (ZS_FUSED_IMPL=smem) and is kept for ABI stability.                    */
 int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X);
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq,
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
