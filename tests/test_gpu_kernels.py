@@ -598,6 +598,45 @@ def test_iw_step_host_begin_wait_device_scalars(B):
     assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 
 
+def test_latent_kernels_full_size_properties():
+    """BASELINE config 2 / 3 size (K=50, B=1024, Z=40): the fused latent kernels == the stand-alone kernels on the
+    same Philox stream (sample, log q, log p, joint backward), and sample moments."""
+    K, M, E = 50, 1024, 40
+    g = torch.Generator(device=DEV).manual_seed(3)
+    mean = 0.5 * torch.randn(M, E, device=DEV, generator=g)
+    std = torch.exp(0.3 * torch.randn(M, E, device=DEV, generator=g))
+    z, lq, lp = be.normal_latent_fwd(mean, std, KBCAST, K, M, E, seed=11, offset=16)
+    z2 = be.normal_sample(mean.reshape(-1), KBCAST, std.reshape(-1), KBCAST, K, M * E, seed=11, offset=16)
+    torch.testing.assert_close(z.reshape(K, -1), z2, rtol=0, atol=2e-6)
+    lq2 = be.normal_logprob_fwd(z, FULL, mean, KBCAST, std, KBCAST, K, M, E)
+    zero, one = torch.zeros(M, E, device=DEV), torch.ones(M, E, device=DEV)
+    lp2 = be.normal_logprob_fwd(z, FULL, zero, KBCAST, one, KBCAST, K, M, E)
+    torch.testing.assert_close(lq, lq2, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(lp, lp2, rtol=1e-5, atol=1e-4)
+    eps = (z - mean) / std
+    assert abs(float(eps.mean())) < 2e-3 and abs(float(eps.std()) - 1) < 2e-3
+    gq, gp = torch.randn(K, M, device=DEV, generator=g), torch.randn(K, M, device=DEV, generator=g)
+    dzu = 0.1 * torch.randn(K, M, E, device=DEV, generator=g)
+    dm, ds = be.normal_latent_bwd(gq, gp, dzu, z, mean, std, KBCAST, K, M, E, reparameterized=True)
+    dzq, dmq, dsq = be.normal_logprob_bwd(gq, z, FULL, mean, KBCAST, std, KBCAST, K, M, E, True, True, True)
+    dzp, _, _ = be.normal_logprob_bwd(gp, z, FULL, zero, KBCAST, one, KBCAST, K, M, E, True, False, False)
+    dzt = (dzu + dzp) + dzq
+    dms, dss = be.normal_sample_bwd(dzt.reshape(K, -1), mean.reshape(-1), KBCAST, std.reshape(-1), KBCAST, K, M * E,
+                                    seed=11, offset=16)
+    torch.testing.assert_close(dm, dmq + dms.reshape(M, E), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ds, dsq + dss.reshape(M, E), rtol=1e-4, atol=2e-4)
+    # Bernoulli latents (config 3)
+    p = torch.sigmoid(torch.randn(M, E, device=DEV, generator=g))
+    zb, lqb, lpb = be.bernoulli_latent_fwd(p, KBCAST, K, M, E, seed=11, offset=20)
+    zb2 = be.bernoulli_sample(p.reshape(-1), KBCAST, K, M * E, seed=11, offset=20)
+    assert torch.equal(zb.reshape(K, -1), zb2)
+    torch.testing.assert_close(lqb, be.bernoulli_logpmf_fwd(zb, FULL, p, KBCAST, K, M, E), rtol=1e-5, atol=1e-4)
+    assert abs(float(zb.mean()) - float(p.mean())) < 2e-3
+    dp = be.bernoulli_latent_bwd(gq, zb, p, KBCAST, K, M, E)
+    _, dp2 = be.bernoulli_logpmf_bwd(gq, zb, FULL, p, KBCAST, K, M, E, False, True)
+    torch.testing.assert_close(dp, dp2, rtol=1e-4, atol=1e-3)
+
+
 # ----------------------------------------------------------------------------- few, long rows (config 4 shapes)
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("K,E", [(100, 8192), (100, 4601), (3, 2048), (7, 100003)])
