@@ -640,6 +640,43 @@ def test_fused_latent_route_equals_separate_kernels(dev, golden, est, latent):
     close(res[True][3], res[False][3].detach().cpu().numpy(), 2e-6)
 
 
+def test_plain_python_broadcast_shapes_matches_torch():
+    """zhusuan._shapes.broadcast_shapes (used on the host path instead of torch.broadcast_shapes, which costs ~30 us
+    per call) gives torch's result and torch's error type."""
+    import itertools
+    from zhusuan._shapes import broadcast_shapes
+    dims = [(), (1,), (3,), (0,), (2, 1), (1, 3), (2, 3), (4, 1, 3), (1, 2, 1), (5, 2, 3)]
+    for a, b in itertools.product(dims, dims):
+        try:
+            ref = torch.broadcast_shapes(a, b)
+        except RuntimeError:
+            ref = None
+        if ref is None:
+            with pytest.raises(RuntimeError):
+                broadcast_shapes(a, b)
+        else:
+            out = broadcast_shapes(a, b)
+            assert isinstance(out, torch.Size) and out == ref
+    assert broadcast_shapes((2, 1), (1, 3), (4, 1, 1)) == torch.Size([4, 2, 3])
+
+
+def test_upload_memo_shares_one_device_copy(dev):
+    """Inside ops.upload_memo() a host tensor is moved to the compute device once and its gradient comes back through
+    one edge; outside it every call uploads again.  (With the oracle backend `to_compute` is the identity.)"""
+    from zhusuan import _ops
+    t = torch.randn(4, 3, requires_grad=True)
+    with _ops.upload_memo():
+        a, b = _ops.to_compute(t), _ops.to_compute(t)
+        assert a is b
+        with _ops.upload_memo():  # nested contexts share the outer memo
+            assert _ops.to_compute(t) is a
+        t2 = t.detach().clone()
+        t2.add_(1.0)  # a different tensor / version is a different entry
+        assert _ops.to_compute(t2) is not a
+    (a.sum() * 2 + b.sum()).backward()
+    torch.testing.assert_close(t.grad, torch.full_like(t, 3.0))
+
+
 def test_particle_linear_matches_reference_layer():
     """zhusuan.particle_linear == the repeat + matmul layer of the reference's BNN examples (bnn_vi.py:39-45), values
     and gradients, without materialising [K, B, n_out, n_in + 1]."""
