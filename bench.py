@@ -371,7 +371,7 @@ def run_b200_arm(args):
     # NCCL kernel that overlaps the step (side stream) holds SMs while it waits for its peer, the persistent
     # 148-CTA likelihood kernel then runs one CTA short and takes a second pass -- 11 % slower steps.  In-stream,
     # the cost is ~30 us per bucket.
-    LOSS_BUCKET = 128
+    LOSS_BUCKET = int(os.environ.get("ZS_BENCH_BUCKET", "128"))
     reduced = torch.zeros(1, device=dev)
     state = {"i": 0}
 
