@@ -331,9 +331,14 @@ def run_b200_arm(args):
     be.require_cuda()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 or os.environ.get("ZS_BENCH_FORCE_PG") == "1":  # the env knob: a 1-rank NCCL group, for diagnosis
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("MASTER_PORT", "29577")
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev, rank=0, world_size=1)
+            dist.all_reduce(torch.zeros(1, device=dev))
     be.load()
     vimco = args.workload == "vimco"
     ps = PathStep(torch, be, vimco, dev, seed=1234 + rank)
@@ -546,7 +551,7 @@ def run_b200_arm(args):
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
+    if world > 1 or os.environ.get("ZS_BENCH_FORCE_PG") == "1":
         dist.destroy_process_group()
 
 
