@@ -7,16 +7,21 @@
 //   ImportanceWeightedObjective.log_joint / sgvb / vimco
 //                                  zhusuan/variational/importance_weighted_objective.py:66-77,102-191
 //
-// Design: one persistent CTA per SM walks batch columns b.  For a column, the K
-// particle rows probs[k, b, :] (K*X*4 bytes, 157 KB at K=50, X=784) are staged in shared memory by
-// 1-D bulk async copies (cp.async.bulk, one mbarrier per row).  Each warp owns a fixed set of rows:
-//   phase A  wait for the row, reduce its log-pmf against x[b,:]            (warp shuffle)
-//   sync     warp 0 forms log-weights, softmax weights / VIMCO signal, cost, d/dlogp, d/dlogq
-//   phase B  dprobs = g_k * (x/(p+eps) - (1-x)/((1-p)+eps)) from the RESIDENT row -> HBM,
-//            then immediately re-arm the row's mbarrier and issue the bulk copy of the same row
-//            of the CTA's next column, so next-column loads overlap this column's stores.
+// Five kernels live in this file, newest last; zs_iw_bernoulli_fused picks box -> generic box -> ring -> l2
+// (ZS_FUSED_IMPL overrides; DESIGN.md 3.1 has the measurements behind each step):
+//   k_iw_bernoulli_fused   (smem) whole column resident, no prefetch, objective on the critical path   123 us
+//   k_iw_bernoulli_colfused (l2)  no residency, second pass re-reads "from L2", several CTAs per SM      95 us
+//   k_iw_bernoulli_ring    (ring) persistent warp-specialised CTA, per-warp rings of 1-D bulk row copies  66.5 us
+//   k_iw_bernoulli_box     (boxg) column resident between its two passes, 3-D TENSOR bulk copies         69.8 us
+//   k_iw_bernoulli_boxf    (box)  the same with compile-time box geometry, signed-argument x staging,
+//                                 optional in-place sigmoid for logits                              62-64 us
+// All of them: one persistent CTA per SM walks batch columns b; for a column
+//   phase A  log-pmf of the K rows probs[k, b, :] against x[b, :]                         (warp shuffle sums)
+//   sync     one named barrier; an objective warp forms log-weights, weights / VIMCO signal, cost, d/dlogp, d/dlogq
+//   phase B  dprobs = g_k * (x/(p+eps) - (1-x)/((1-p)+eps)) -> HBM
 // HBM traffic per particle-sample: 4X read + 4X write (+ [K,B] scalars) instead of 8X + 4X for the
-// two-pass form; the unfused entry points remain as the general fallback.
+// two-pass form; the unfused entry points remain as the general fallback.  The host-buffer step
+// (zs_iw_step_host*) at the end of the file pipelines the same kernels over column chunks.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -623,7 +628,7 @@ __global__ void __launch_bounds__(COLF_MAX_THREADS, COLF_MIN_CTAS)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ring variant (default): one persistent CTA per SM, warp-specialised.
+// Ring variant (fallback for shapes the box kernels do not take): one persistent CTA per SM, warp-specialised.
 //   row warps      : warp w owns rows k = w, w+NW, ... of every column and a private mini-ring of D
 //                    shared-memory row slots.  Its task stream is
 //                       A(c,k)  first read of the row   (HBM)  -> log-pmf
@@ -1024,8 +1029,8 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Box variant (default when the shape allows): the column is RESIDENT in shared memory between its two
-// passes and arrives by TENSOR bulk copies.
+// Generic box variant (run-time geometry; the fixed-geometry kernel further down is the default): the column is
+// RESIDENT in shared memory between its two passes and arrives by TENSOR bulk copies.
 //
 // Why (tools/probes/tma_probe.cu, tma_tensor_probe.cu, profiles/r1_notes.md): every variant of the ring
 // kernel ran at 8.5 us per column per SM, with 37 CTAs as with 148, with or without the arithmetic.  The
