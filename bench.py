@@ -349,6 +349,8 @@ def run_b200_arm(args):
     pg_first = os.environ.get("ZS_BENCH_PG_FIRST") == "1"
     if pg and pg_first:
         init_pg()
+    pad_mb = float(os.environ.get("ZS_BENCH_PAD_MB", "0"))  # dev knob: shift the placement of the step's tensors
+    pad = torch.empty(int(pad_mb * (1 << 20)), dtype=torch.uint8, device=dev) if pad_mb > 0 else None
     ps = PathStep(torch, be, vimco, dev, seed=1234 + rank)
     if world > 1 or os.environ.get("ZS_BENCH_ACCUM") == "1":  # the env knob isolates the cost of the running sum
         ps.cost_sum = torch.zeros(B_COLS, device=dev)
