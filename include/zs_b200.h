@@ -16,7 +16,8 @@
  *     zhusuan/distributions/utils.py:5); all tensor arguments of one call share it;
  *   - return value: ZS_OK (0) or a negative ZS_ERR_* code; zs_strerror() names
  *     it, zs_last_error() returns the CUDA error string of the calling thread;
- *   - no global mutable state besides that thread-local error string.
+ *   - no global mutable state besides that thread-local error string (and the zs_debug_* developer hooks);
+ *     calls that need state across launches take a caller-owned handle or device buffer.
  *
  * Tensor layout ("particle rows")
  *   A stochastic node's value is viewed as [K, M, E], contiguous, where
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ZS_ABI_VERSION 1
+#define ZS_ABI_VERSION 2
 
 typedef void* zs_stream_t; /* cudaStream_t */
 
@@ -72,12 +73,31 @@ int zs_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Element i of a call uses counter (i/4 lo, i/4 hi, offset lo, offset hi), key
  * (seed lo, seed hi), word i%4.  Results do not depend on the launch geometry.
  * Replaces the CPU-side torch.normal / torch.bernoulli + H2D copies at
- * normal.py:104, bernoulli.py:79, SGLD.py:51, SGHMC.py:27,33,34.               */
-int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream);
+ * normal.py:104, bernoulli.py:79, SGLD.py:51, SGHMC.py:27,33,34.
+ *
+ * Graph-safe stream position.  Every sampling entry point takes (seed, offset, rng_state):
+ *   rng_state == NULL : the launch draws from Philox(seed, offset) -- a pure function of its arguments (parity
+ *                       tests; also what a captured CUDA graph would replay unchanged, i.e. the SAME noise).
+ *   rng_state != NULL : a DEVICE zs_rng_state.  The launch draws from Philox(seed, offset + rng_state->offset) and
+ *                       advances rng_state->offset by ZS_RNG_TICK once all of its CTAs have read it, so the next
+ *                       sampling launch on the stream -- or the next replay of a captured graph -- draws fresh
+ *                       noise.  One state per stream of sampling launches (launches that share a state must be
+ *                       stream-ordered).  Initialise with zs_rng_state_init (or write {offset, 0, 0} yourself).
+ * Entry points whose backward regenerates the forward's noise also take `rng_snapshot` (DEVICE zs_rng_state, may be
+ * NULL): it receives the position the forward used; hand it to the backward as its rng_state (read, not advanced). */
+#define ZS_RNG_TICK 4
+typedef struct zs_rng_state {
+    uint64_t offset;    /* added to the by-value offset                                      */
+    uint32_t arrivals;  /* CTAs of the current launch that have read `offset` (0 between launches) */
+    uint32_t reserved;
+} zs_rng_state;
+int zs_rng_state_init(void* rng_state, uint64_t offset, zs_stream_t stream);
+int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, void* rng_state,
+                      zs_stream_t stream);
 int zs_philox_normal(int dtype, void* out, int64_t n, double mean, double std, uint64_t seed, uint64_t offset,
-                     zs_stream_t stream);
+                     void* rng_state, zs_stream_t stream);
 /* raw 32-bit words (n must be a multiple of 4); used by the bit-exact RNG tests */
-int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream);
+int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 
 /* ---- Normal stochastic node ----------------------------------------------
  * zs_normal_sample: z[K,N] = mean + std * eps      (Normal._sample, normal.py:89-107)
@@ -89,13 +109,13 @@ int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, zs_s
  * normal.py:101-102): the value is identical, only autograd differs.            */
 int zs_normal_sample(int dtype, void* z, const void* mean, int mean_mode, const void* std, int std_mode,
                      const void* eps_in, void* eps_out, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
-                     zs_stream_t stream);
+                     void* rng_state, void* rng_snapshot, zs_stream_t stream);
 /* Pathwise gradient of the sample: dmean = sum_k dz, dstd = sum_k dz*eps (sums only
  * over broadcast axes).  eps == NULL regenerates the noise from (seed, offset).
  * dmean / dstd may be NULL.  SCALAR-mode grads are not produced here (host sums).  */
 int zs_normal_sample_bwd(int dtype, void* dmean, int mean_mode, void* dstd, int std_mode, const void* dz,
                          const void* eps, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
-                         zs_stream_t stream);
+                         const void* rng_state, zs_stream_t stream);
 
 /* out[K,M] = sum_e ( c - log(std) - 0.5*exp(-2 log std)*(x-mean)^2 )
  * Normal._log_prob (normal.py:109-126) + Distribution.log_prob's group_ndims sum
@@ -120,9 +140,11 @@ int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const vo
  * _logprob_fwd: out[K,M] = sum_e log p(x; loc, scale):  Logistic -z - 2 softplus(-z) - log(scale), z = (x-loc)/scale
  * (logistic.py:72-83);  Laplace -log(2 scale) - |x - loc| / scale (laplace.py:78-92).  _logprob_bwd: autograd of those. */
 int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_mode, const void* scale, int scale_mode,
-                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, void* rng_state,
+                       void* rng_snapshot, zs_stream_t stream);
 int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void* dscale, int scale_mode, const void* dz,
-                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
+                           const void* rng_state, zs_stream_t stream);
 int zs_locscale_logprob_fwd(int dtype, int family, void* out, const void* x, int x_mode, const void* loc, int loc_mode,
                             const void* scale, int scale_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream);
 int zs_locscale_logprob_bwd(int dtype, int family, void* dx, void* dloc, void* dscale, const void* g, const void* x,
@@ -133,7 +155,7 @@ int zs_locscale_logprob_bwd(int dtype, int family, void* dx, void* dloc, void* d
  * out[K,N] = (u < probs) as float, u ~ Philox uniform   (Bernoulli._sample,
  * bernoulli.py:72-82); u_in != NULL injects the uniforms (parity mode).         */
 int zs_bernoulli_sample(int dtype, void* out, const void* probs, int probs_mode, const void* u_in, int64_t K,
-                        int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                        int64_t N, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 /* out[K,M] = sum_e ( x*log(p+1e-8) + (1-x)*log((1-p)+1e-8) )
  * Bernoulli._log_prob (bernoulli.py:84-95) + the same event sums as above.      */
 int zs_bernoulli_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* probs, int probs_mode,
@@ -161,10 +183,10 @@ int zs_bernoulli_logits_logpmf_bwd(int dtype, void* dx, void* dlogits, const voi
  *   aligned tensors, otherwise ZS_ERR_UNSUPPORTED / ZS_ERR_ALIGN (compose the general kernels).      */
 int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* mean, int mean_mode, const void* std,
                          int std_mode, const void* prior_mean, const void* prior_std, const void* eps_in, int64_t K,
-                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
                             const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                            uint64_t offset, zs_stream_t stream);
+                            uint64_t offset, void* rng_state, zs_stream_t stream);
 /* Backward in ONE launch: gradient of  <dlogq, log q> + <dlogp, log p> + <dz_up, z>  wrt the variational
  * parameters: autograd of both log-densities, the decoder's upstream gradient dz_up [K,M,E] (may be
  * NULL) and, if reparameterized, the pathwise backward of the sample (eps recovered as (z-mean)/std),
@@ -180,7 +202,7 @@ int zs_bernoulli_latent_bwd(int dtype, void* dprobs, const void* dlogq, const vo
  * API modelled on bernoulli.py) --------------------------------
  * logits [K|1, M, C]; value = class index stored as float/double in x[K,M].     */
 int zs_categorical_sample(int dtype, void* out, const void* logits, int logits_mode, const void* u_in, int64_t K,
-                          int64_t M, int64_t C, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                          int64_t M, int64_t C, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 int zs_categorical_logpmf_fwd(int dtype, void* out, const void* x, int x_mode, const void* logits, int logits_mode,
                               int64_t K, int64_t M, int64_t C, zs_stream_t stream);
 int zs_categorical_logpmf_bwd(int dtype, void* dlogits, const void* g, const void* x, int x_mode,
@@ -236,36 +258,31 @@ int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64
  *   cost[B], dprobs[K,B,X] (may be NULL: forward only), dlogp[K,B] (= gradient wrt every generator log-prob
  *   term), dlogq[K,B]; logpx_out[K,B] optional copy of the likelihood term.
  * Kernel selection: fixed-geometry box kernel for X in {128, 256, 512, 784, 1024} and K <= 50,
- * generic box kernel for other K <= 50, row-streaming ring kernel for any K <= 4096, re-read-from-L2 kernel last.
+ * generic box kernel for other K <= 50, row-streaming ring kernel for any K <= 4096.
  * Requires f32, X % 4 == 0 and 16-byte aligned probs / dprobs / x; otherwise ZS_ERR_UNSUPPORTED / ZS_ERR_ALIGN and
- * the caller uses the two-pass entry points.  zs_iw_bernoulli_fused_smem_bytes(K,X) reports the shared memory of
- * the legacy whole-column variant (ZS_FUSED_IMPL=smem) and is kept for ABI stability.                    */
-int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X);
+ * the caller uses the two-pass entry points.
+ * flags:
+ *   ZS_FUSED_ACCUMULATE_COST  cost[b] += cost_b instead of cost[b] = cost_b: a running sum of the per-column
+ *       objectives over steps.  A data-parallel training loop reports its scalar objective from this buffer every N
+ *       steps (one reduction + one all-reduce per N steps instead of per step; each column has exactly one writer,
+ *       so the sum is deterministic).
+ *   ZS_FUSED_LOGITS  `probs` holds LOGITS [K,B,X] (Bernoulli(logits=...), bernoulli.py:47-50): the sigmoid is applied
+ *       as the rows arrive in shared memory and its derivative is chained into the result, so `dprobs` is the
+ *       gradient w.r.t. the decoder's pre-activations.  Available where a fixed-geometry kernel is instantiated
+ *       (X in {128, 256, 512, 784, 1024}, K <= 50); otherwise ZS_ERR_UNSUPPORTED and the caller composes
+ *       zs_bernoulli_logits_logpmf_fwd -> zs_iw_objective -> zs_bernoulli_logits_logpmf_bwd.              */
+enum { ZS_FUSED_ACCUMULATE_COST = 1, ZS_FUSED_LOGITS = 2 };
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq,
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
-                          const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
+                          const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, int flags,
                           zs_stream_t stream);
-/* The same launch with cost_sum[b] += cost_b instead of cost[b] = cost_b: a running sum of the per-column
- * objectives over steps.  A data-parallel training loop reports its scalar objective from this buffer every N steps
- * (one reduction + one all-reduce per N steps instead of per step; each column has exactly one writer, so the sum
- * is deterministic).  ZS_ERR_UNSUPPORTED for shapes only the two-pass kernels take.                        */
-int zs_iw_bernoulli_fused_accumulate(int estimator, float* cost_sum, float* dprobs, float* dlogp, float* dlogq,
-                                     float* logpx_out, const float* probs, const float* x, const float* logp_other,
-                                     const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
-                                     zs_stream_t stream);
-/* The same launch for a likelihood given by LOGITS [K,B,X] (Bernoulli(logits=...), bernoulli.py:47-50): the
- * sigmoid is applied as the rows arrive in shared memory and its derivative is chained into the result, so
- * `dlogits` is the gradient w.r.t. the decoder's pre-activations.  Available where a fixed-geometry kernel is
- * instantiated (X in {128, 256, 512, 784, 1024}, K <= 50); otherwise ZS_ERR_UNSUPPORTED and the caller composes
- * zs_bernoulli_logits_logpmf_fwd -> zs_iw_objective -> zs_bernoulli_logits_logpmf_bwd.              */
-int zs_iw_bernoulli_fused_logits(int estimator, float* cost, float* dlogits, float* dlogp, float* dlogq,
-                                 float* logpx_out, const float* logits, const float* x, const float* logp_other,
-                                 const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
-                                 zs_stream_t stream);
 
-/* Debug hook: device buffer (grid*40 int64) that the fused kernel fills with clock64() phase
- * timestamps of each CTA's first 8 columns; NULL (default) disables tracing. */
+/* Debug hooks.  zs_debug_set_trace: device buffer (grid*40 int64) that the generic box / ring kernels fill with
+ * clock64() phase timestamps of each CTA's first 8 columns; NULL (default) disables tracing.
+ * zs_debug_set_fused_impl: 2 = ring, 3 = box (default order), 4 = generic box only, -1 = back to the default
+ * (the ZS_FUSED_IMPL environment variable, read once per process).  Process-wide; tests and tools only. */
 int zs_debug_set_trace(void* device_buffer);
+int zs_debug_set_fused_impl(int impl);
 
 /* ---- SG-MCMC updates across parallel chains (one pass) -----------------------
  * w_out receives the updated chain state and may alias w (in place); the reference
@@ -275,11 +292,12 @@ int zs_debug_set_trace(void* device_buffer);
  * it is drawn from Philox(seed, offset) inside the kernel.
  * SGLD._update (SGLD.py:42-54):  w += 0.5*lr*g + N(0, lr)                          */
 int zs_sgld_step(int dtype, void* w_out, const void* w, const void* g, const void* noise, int64_t n, double lr,
-                 uint64_t seed, uint64_t offset, zs_stream_t stream);
+                 uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 /* PSGLD._update (SGLD.py:67-82): aux = decay*aux + (1-decay) g^2; G = 1/(eps+sqrt(aux));
  * w += 0.5*lr*G*g + N(0, lr*G).  noise_unit != NULL injects UNIT normals.          */
 int zs_psgld_step(int dtype, void* w_out, const void* w, void* aux, const void* g, const void* noise_unit, int64_t n,
-                  double lr, double decay, double epsilon, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                  double lr, double decay, double epsilon, uint64_t seed, uint64_t offset, void* rng_state,
+                  zs_stream_t stream);
 /* SGHMC._update (SGHMC.py:25-56).
  *   zs_sghmc_pre : optional velocity resample v ~ N(0, lr) (resample != 0; v_noise
  *                  injects it) and, for second_order, the half step w += 0.5 v.
@@ -287,10 +305,35 @@ int zs_psgld_step(int dtype, void* w_out, const void* w, void* aux, const void* 
  *                  second order v = d (d v + lr g + n), d = exp(-alpha/2) ; w += 0.5 v
  *                  n ~ N(0, 2(alpha-beta) lr) (noise injects it).                   */
 int zs_sghmc_pre(int dtype, void* w_out, const void* w, void* v, const void* v_noise, int64_t n, double lr,
-                 int resample, int second_order, uint64_t seed, uint64_t offset, zs_stream_t stream);
+                 int resample, int second_order, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
 int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g, const void* noise, int64_t n,
                   double lr, double alpha, double beta, int second_order, uint64_t seed, uint64_t offset,
-                  zs_stream_t stream);
+                  void* rng_state, zs_stream_t stream);
+
+/* Multi-tensor apply: the update of EVERY chain-state tensor of a sampler in ONE launch (the reference loops over
+ * the latents in Python, SGLD.py:49-54, SGHMC.py:29-56: one CPU noise draw + H2D + 3-6 kernels each).  The table is
+ * read on the host and travels in the kernel parameters, so the call is CUDA-graph capturable and needs no device
+ * allocation.  Tensor t owns the quads [q_t, q_t + ceil(n_t / 4)) of ONE Philox stream position (q_0 = 0): element i
+ * of tensor t draws word i % 4 of counter q_t + i / 4, so a one-tensor call equals the single-tensor entry point
+ * bit for bit, and the whole update consumes one tick.
+ *   algorithm ZS_ALG_SGLD       : zs_sgld_step;        state unused
+ *             ZS_ALG_PSGLD      : zs_psgld_step;       state = aux, a = decay, b = epsilon, noise = unit normals
+ *             ZS_ALG_SGHMC_PRE  : zs_sghmc_pre;        state = v, g unused, noise = injected resampled velocity
+ *             ZS_ALG_SGHMC_POST : zs_sghmc_post;       state = v, a = alpha, b = beta
+ * At most ZS_CHAIN_MAX_TENSORS tensors per call (ZS_ERR_UNSUPPORTED beyond; split the call). */
+#define ZS_CHAIN_MAX_TENSORS 32
+enum { ZS_ALG_SGLD = 0, ZS_ALG_PSGLD = 1, ZS_ALG_SGHMC_PRE = 2, ZS_ALG_SGHMC_POST = 3 };
+typedef struct zs_chain_tensor {
+    void* w_out;       /* updated chain state (may alias w)                          */
+    const void* w;     /* current chain state                                         */
+    const void* g;     /* gradient of the log joint                                   */
+    void* state;       /* v (SGHMC) / aux (PSGLD), updated in place; NULL for SGLD    */
+    const void* noise; /* injected noise (parity mode) or NULL = Philox in registers */
+    int64_t n;         /* elements                                                    */
+} zs_chain_tensor;
+int zs_sgmcmc_multi_step(int dtype, int algorithm, const zs_chain_tensor* tensors_host, int n_tensors, double lr,
+                         double a, double b, int resample, int second_order, uint64_t seed, uint64_t offset,
+                         void* rng_state, zs_stream_t stream);
 
 /* ---- host-buffer step (end-to-end measurement) ----
  * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers for the big
@@ -298,11 +341,15 @@ int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g,
  * would hand to ImportanceWeightedObjective.forward + backward
  * (zhusuan/variational/importance_weighted_objective.py:79-132 with the likelihood node of
  * zhusuan/distributions/bernoulli.py:84-95).  Batch columns are independent, so the step is pipelined
- * over chunks of 128 columns on internal streams: the H2D copy of chunk c+1, the
+ * over chunks of 128 columns on the handle's streams: the H2D copy of chunk c+1, the
  * fused kernel (or the two-pass kernels) on chunk c and the D2H copy of chunk c-1 overlap, so the call
  * costs about max(H2D, D2H) instead of their sum.  `ws` is a caller-owned device workspace of
- * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).  The only process-wide state of the
- * library is the lazily created streams / events of these calls (one step in flight at a time).
+ * zs_iw_step_host_workspace() bytes (three chunk-sized buffer sets).
+ *
+ * All state (four streams, the events, the chunk schedule, "a step is in flight") lives in an opaque handle created
+ * on the current device: the library keeps no global state for these calls.  Handles are independent (one per
+ * thread / per caller stream is fine); one step per handle is in flight at a time, a second _begin on the same handle
+ * first waits for the previous step to land.
  *
  *   zs_iw_step_host        ordered after prior work on `stream`; returns after everything has landed.
  *   zs_iw_step_host_begin  enqueues the same step and returns.  With scalars_on_device != 0 the [K,B]
@@ -312,16 +359,19 @@ int zs_sghmc_post(int dtype, void* w_out, const void* w, void* v, const void* g,
  *                          `stream` with no host round trip.  cost / dprobs are always host buffers.
  *   zs_iw_step_host_wait   what = 0: the small results (cost; host dlogp / dlogq) have landed and every
  *                          kernel has run;  what = 1: dprobs has landed too (the step is over).       */
+typedef struct zs_host_step zs_host_step;
+int zs_host_step_create(zs_host_step** handle);
+int zs_host_step_destroy(zs_host_step* handle);
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X);
-int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
-                    const float* probs_host, const float* x_host, const float* logp_other_host,
+int zs_iw_step_host(zs_host_step* handle, int estimator, float* cost_host, float* dprobs_host, float* dlogp_host,
+                    float* dlogq_host, const float* probs_host, const float* x_host, const float* logp_other_host,
                     const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
                     int64_t ws_bytes, zs_stream_t stream);
-int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, float* dlogp, float* dlogq,
-                          const float* probs_host, const float* x_host, const float* logp_other, const float* logq,
-                          int64_t K, int64_t B, int64_t X, double grad_scale, void* ws, int64_t ws_bytes,
-                          int scalars_on_device, zs_stream_t stream);
-int zs_iw_step_host_wait(int what);
+int zs_iw_step_host_begin(zs_host_step* handle, int estimator, float* cost_host, float* dprobs_host, float* dlogp,
+                          float* dlogq, const float* probs_host, const float* x_host, const float* logp_other,
+                          const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
+                          int64_t ws_bytes, int scalars_on_device, zs_stream_t stream);
+int zs_iw_step_host_wait(zs_host_step* handle, int what);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,8 @@ def _t(a, like):
     return torch.from_numpy(np.ascontiguousarray(a)).to(like.dtype)
 
 
-def normal_sample(mean, mean_mode, std, std_mode, K, N, eps_in=None, eps_out=None, seed=0, offset=0):
+def normal_sample(mean, mean_mode, std, std_mode, K, N, eps_in=None, eps_out=None, seed=0, offset=0, rng_state=None,
+                  rng_snapshot=None):
     if eps_in is None:
         eps = O.philox_normal(K * N, seed, offset).astype(_np(mean).dtype).reshape(K, N)
     else:
@@ -33,7 +34,7 @@ def normal_sample(mean, mean_mode, std, std_mode, K, N, eps_in=None, eps_out=Non
 
 
 def normal_sample_bwd(dz, mean_like, mean_mode, std_like, std_mode, K, N, eps=None, seed=0, offset=0,
-                      need_mean=True, need_std=True):
+                      need_mean=True, need_std=True, rng_state=None):
     e = O.philox_normal(K * N, seed, offset).astype(_np(dz).dtype).reshape(K, N) if eps is None else _np(eps).reshape(K, N)
     dm, ds = O.normal_sample_bwd(_np(dz).reshape(K, N), e, _np(mean_like), _np(std_like), K, N)
     return (_t(dm, dz) if need_mean else None), (_t(ds, dz) if need_std else None)
@@ -49,7 +50,7 @@ def normal_logprob_bwd(g, x, xm, mean, mm, std, sm, K, M, E, need_x, need_mean, 
 
 
 def normal_latent_fwd(mean, std, mode, K, M, E, prior_mean=None, prior_std=None, eps_in=None, want_logq=True,
-                      want_logp=True, seed=0, offset=0):
+                      want_logp=True, seed=0, offset=0, rng_state=None):
     dt = _np(mean).dtype
     eps = (O.philox_normal(K * M * E, seed, offset).astype(dt) if eps_in is None else _np(eps_in)).reshape(K, M * E)
     z = O.normal_sample(_np(mean), _np(std), eps, K, M * E).reshape(K, M, E)
@@ -85,7 +86,7 @@ def normal_latent_bwd(dlogq, dlogp, dz_up, z, mean, std, mode, K, M, E, prior_me
 
 
 def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want_logq=True, want_logp=True, seed=0,
-                         offset=0):
+                         offset=0, rng_state=None):
     dt = _np(probs).dtype
     u = (O.philox_uniform(K * M * E, seed, offset).astype(dt) if u_in is None else _np(u_in)).reshape(K, M * E)
     z = O.bernoulli_sample(_np(probs), u, K, M * E).reshape(K, M, E)
@@ -102,7 +103,7 @@ def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E):
     return _t(dp.reshape(probs.shape), probs)
 
 
-def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0):
+def bernoulli_sample(probs, pm, K, N, u_in=None, seed=0, offset=0, rng_state=None):
     u = O.philox_uniform(K * N, seed, offset).astype(_np(probs).dtype).reshape(K, N) if u_in is None else _np(u_in)
     return _t(O.bernoulli_sample(_np(probs), u.reshape(K, N), K, N), probs)
 
@@ -128,13 +129,14 @@ def _locscale_u(family, K, N, dtype, u_in, seed, offset):
     return (2 * u - 1).astype(dtype) if family == FAM_LAPLACE else u
 
 
-def locscale_sample(family, loc, loc_mode, scale, scale_mode, K, N, u_in=None, seed=0, offset=0):
+def locscale_sample(family, loc, loc_mode, scale, scale_mode, K, N, u_in=None, seed=0, offset=0, rng_state=None,
+                    rng_snapshot=None):
     u = _locscale_u(family, K, N, _np(loc).dtype, u_in, seed, offset)
     return _t(O.locscale_sample(family, _np(loc), _np(scale), u, K, N), loc)
 
 
 def locscale_sample_bwd(family, dz, loc_like, loc_mode, scale_like, scale_mode, K, N, u=None, seed=0, offset=0,
-                        need_loc=True, need_scale=True):
+                        need_loc=True, need_scale=True, rng_state=None):
     uu = _locscale_u(family, K, N, _np(dz).dtype, u, seed, offset)
     dl, ds = O.locscale_sample_bwd(family, _np(dz), uu, K, N, full=(loc_mode == FULL and K > 1))
     return (_t(dl.reshape(loc_like.shape), dz) if need_loc else None,
@@ -151,7 +153,7 @@ def locscale_logprob_bwd(family, g, x, xm, loc, lm, scale, sm, K, M, E, need_x, 
             _t(ds.reshape(scale.shape), x) if need_scale else None)
 
 
-def categorical_sample(logits, lm, K, M, C, u_in=None, seed=0, offset=0):
+def categorical_sample(logits, lm, K, M, C, u_in=None, seed=0, offset=0, rng_state=None):
     u = O.philox_uniform(K * M, seed, offset).astype(_np(logits).dtype) if u_in is None else _np(u_in)
     return _t(O.categorical_sample(_np(logits), u.reshape(K, M), K, M, C), logits)
 
@@ -212,18 +214,18 @@ def scale_inplace(buf, scale_dev):
         buf.mul_(scale_dev)
 
 
-def philox_normal(n, dtype, mean, std, seed, offset, device):
+def philox_normal(n, dtype, mean, std, seed, offset, device, rng_state=None):
     return torch.from_numpy(O.philox_normal(n, seed, offset, mean, std)).to(dtype)
 
 
-def sgld_step(w, g, lr, noise=None, seed=0, offset=0, out=None):
+def sgld_step(w, g, lr, noise=None, seed=0, offset=0, out=None, rng_state=None):
     if noise is None:
         noise = philox_normal(w.numel(), w.dtype, 0.0, float(np.float32(np.sqrt(np.float64(np.float32(lr))))), seed,
                               offset, None).reshape(w.shape)
     return _t(O.sgld_step(_np(w), _np(g), _np(noise), lr), w)
 
 
-def psgld_step(w, aux, g, lr, decay, epsilon, noise_unit=None, seed=0, offset=0, out=None):
+def psgld_step(w, aux, g, lr, decay, epsilon, noise_unit=None, seed=0, offset=0, out=None, rng_state=None):
     if noise_unit is None:
         noise_unit = philox_normal(w.numel(), w.dtype, 0.0, 1.0, seed, offset, None).reshape(w.shape)
     nw, na = O.psgld_step(_np(w), _np(aux), _np(g), _np(noise_unit), lr, decay, epsilon)
@@ -231,7 +233,7 @@ def psgld_step(w, aux, g, lr, decay, epsilon, noise_unit=None, seed=0, offset=0,
     return _t(nw, w)
 
 
-def sghmc_pre(w, v, lr, resample, second_order, v_noise=None, seed=0, offset=0, out=None):
+def sghmc_pre(w, v, lr, resample, second_order, v_noise=None, seed=0, offset=0, out=None, rng_state=None):
     if not resample and not second_order:
         return w
     if resample and v_noise is None:
@@ -241,7 +243,7 @@ def sghmc_pre(w, v, lr, resample, second_order, v_noise=None, seed=0, offset=0, 
     return _t(nw, w) if second_order else w
 
 
-def sghmc_post(w, v, g, lr, alpha, beta, second_order, noise=None, seed=0, offset=0, out=None):
+def sghmc_post(w, v, g, lr, alpha, beta, second_order, noise=None, seed=0, offset=0, out=None, rng_state=None):
     if noise is None:
         std = float(np.float32(np.sqrt(2.0 * (alpha - beta) * lr)))
         noise = philox_normal(w.numel(), w.dtype, 0.0, std, seed, offset, None).reshape(w.shape)
@@ -250,12 +252,63 @@ def sghmc_post(w, v, g, lr, alpha, beta, second_order, noise=None, seed=0, offse
     return _t(nw, w)
 
 
+ALG_SGLD, ALG_PSGLD, ALG_SGHMC_PRE, ALG_SGHMC_POST = 0, 1, 2, 3
+
+
+def sgmcmc_multi_step(algorithm, ws, gs=None, states=None, noises=None, outs=None, lr=0.0, a=0.0, b=0.0, resample=False,
+                      second_order=False, seed=0, offset=0, rng_state=None):
+    """Stand-in of zs_sgmcmc_multi_step: tensor t draws its noise from the quads [q_t, q_t + ceil(n_t/4)) of ONE
+    Philox stream position, exactly as the kernel does."""
+    n = len(ws)
+    gs = gs if gs is not None else [None] * n
+    states = states if states is not None else [None] * n
+    noises = noises if noises is not None else [None] * n
+    total_q = sum((w.numel() + 3) // 4 for w in ws)
+    unit = None
+
+    def unit_noise(q0, cnt):
+        nonlocal unit
+        if unit is None:
+            unit = O.philox_normal(4 * total_q, seed, offset, 0.0, 1.0)
+        return unit[4 * q0:4 * q0 + cnt]
+
+    res, q0 = [], 0
+    for i, w in enumerate(ws):
+        cnt = w.numel()
+        dt = _np(w).dtype
+
+        def scaled(std):
+            return _t((np.float32(std) * unit_noise(q0, cnt)).astype(dt).reshape(w.shape), w)
+
+        if algorithm == ALG_SGLD:
+            nz = noises[i] if noises[i] is not None else scaled(np.float32(np.sqrt(np.float64(np.float32(lr)))))
+            res.append(sgld_step(w, gs[i], lr, noise=nz))
+        elif algorithm == ALG_PSGLD:
+            nz = noises[i] if noises[i] is not None else scaled(1.0)
+            res.append(psgld_step(w, states[i], gs[i], lr, a, b, noise_unit=nz))
+        elif algorithm == ALG_SGHMC_PRE:
+            nz = noises[i]
+            if resample and nz is None:
+                nz = scaled(np.float32(np.sqrt(lr)))
+            res.append(sghmc_pre(w, states[i], lr, resample, second_order, v_noise=nz))
+        else:
+            nz = noises[i] if noises[i] is not None else scaled(np.float32(np.sqrt(2.0 * (a - b) * lr)))
+            res.append(sghmc_post(w, states[i], gs[i], lr, a, b, second_order, noise=nz))
+        q0 += (cnt + 3) // 4
+    return res
+
+
 _counter = {"off": 0}
 
 
 def _next_philox(device):
     _counter["off"] += 4
     return 1234, _counter["off"]
+
+
+def _draw_args(device):
+    seed, offset = _next_philox(device)
+    return dict(seed=seed, offset=offset, rng_state=None)
 
 
 def install(monkeypatch):
@@ -267,11 +320,12 @@ def install(monkeypatch):
                  "locscale_logprob_fwd", "locscale_logprob_bwd", "categorical_sample", "categorical_logpmf_fwd",
                  "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
                  "iw_bernoulli_fused", "reinforce_step", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
-                 "sghmc_post"):
+                 "sghmc_post", "sgmcmc_multi_step"):
         monkeypatch.setattr(_backend, name, globals()[name])
     monkeypatch.setattr(_backend, "require_cuda", lambda: None)
     monkeypatch.setattr(_backend, "on_compute_device", lambda t: True)
     monkeypatch.setattr(_ops, "to_compute", lambda t: t)
     monkeypatch.setattr(_ops, "compute_device", lambda: torch.device("cpu"))
     monkeypatch.setattr(_rng, "next_philox", _next_philox)
+    monkeypatch.setattr(_rng, "draw_args", _draw_args)
     _counter["off"] = 0

@@ -368,7 +368,15 @@ def _fused_inputs(K, B, X, binary=True, seed=8):
 def _set_impl(monkeypatch, impl):
     """ring: rows streamed twice through per-warp bulk-copy rings; box: resident column, tensor bulk copies, fixed
     geometry where instantiated; boxg: the generic box kernel."""
-    monkeypatch.setenv("ZS_FUSED_IMPL", impl)
+    be.set_fused_impl({"ring": be.IMPL_RING, "box": be.IMPL_BOX, "boxg": be.IMPL_BOXG}[impl])
+
+
+@pytest.fixture(autouse=True)
+def _default_fused_impl():
+    """zs_debug_set_fused_impl is process-wide: every test starts and ends on the default kernel selection."""
+    yield
+    if torch.cuda.is_available():
+        be.set_fused_impl(be.IMPL_DEFAULT)
 
 
 @pytest.mark.parametrize("K,B,X", [(50, 64, 784), (8, 3, 16), (25, 300, 100), (64, 150, 784), (10, 1, 4),
@@ -547,8 +555,9 @@ def test_iw_step_host(oracle, B):
     dprobs = torch.empty(K, B, X).pin_memory()
     dlp, dlq = torch.empty(K, B).pin_memory(), torch.empty(K, B).pin_memory()
     ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
+    hs = be.HostStep(DEV)
     for code, ocode in ((be.SGVB, oracle.SGVB), (be.VIMCO, oracle.VIMCO)):
-        be.iw_step_host(code, cost, dprobs, dlp, dlq, hp, hx, ho, hq, K, B, X, 1.0 / B, ws)
+        be.iw_step_host(hs, code, cost, dprobs, dlp, dlq, hp, hx, ho, hq, K, B, X, 1.0 / B, ws)
         r = be.iw_bernoulli_fused(code, dev(probs), dev(x), dev(other), dev(logq), 1.0 / B)
         assert np.array_equal(cost.numpy(), host(r["cost"]))
         assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
@@ -559,7 +568,7 @@ def test_iw_step_host(oracle, B):
     cost = torch.empty(B).pin_memory()
     dprobs = torch.empty(K, B, X).pin_memory()
     ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
-    be.iw_step_host(be.VIMCO, cost, dprobs, None, None, pin(probs), pin(x), pin(other), pin(logq), K, B, X, 1.0 / B, ws)
+    be.iw_step_host(hs, be.VIMCO, cost, dprobs, None, None, pin(probs), pin(x), pin(other), pin(logq), K, B, X, 1.0 / B, ws)
     o = oracle.iw_bernoulli_step(oracle.VIMCO, probs.astype(np.float64), x.astype(np.float64),
                                  other.astype(np.float64), logq.astype(np.float64))
     close(cost.numpy(), o["cost"], 1e-5)
@@ -577,23 +586,24 @@ def test_iw_step_host_begin_wait_device_scalars(B):
     cost = torch.empty(B).pin_memory()
     dprobs = torch.empty(K, B, X).pin_memory()
     ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=DEV)
+    hs = be.HostStep(DEV)
     for code in (be.SGVB, be.VIMCO):
         do, dq = dev(other), dev(logq)
         dlp, dlq = torch.zeros(K, B, device=DEV), torch.zeros(K, B, device=DEV)
         cost.fill_(float("nan"))
         dprobs.fill_(float("nan"))
-        be.iw_step_host_begin(code, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
-        be.iw_step_host_wait(0)
+        be.iw_step_host_begin(hs, code, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+        be.iw_step_host_wait(hs, 0)
         r = be.iw_bernoulli_fused(code, dev(probs), dev(x), do, dq, 1.0 / B)
         assert np.array_equal(cost.numpy(), host(r["cost"]))
         # dlogp / dlogq are consumable from the caller's stream without a host synchronisation
         assert torch.equal(dlp, r["dlogp"]) and torch.equal(dlq, r["dlogq"])
-        be.iw_step_host_wait(1)
+        be.iw_step_host_wait(hs, 1)
         assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
     # a second begin while the first is still in flight waits for it (shared workspace)
-    be.iw_step_host_begin(be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
-    be.iw_step_host_begin(be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
-    be.iw_step_host_wait(1)
+    be.iw_step_host_begin(hs, be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+    be.iw_step_host_begin(hs, be.SGVB, cost, dprobs, dlp, dlq, hp, hx, do, dq, K, B, X, 1.0 / B, ws, True)
+    be.iw_step_host_wait(hs, 1)
     r = be.iw_bernoulli_fused(be.SGVB, dev(probs), dev(x), do, dq, 1.0 / B)
     assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 

@@ -22,7 +22,7 @@ for arg in sys.argv[1:]:
     lib = c.CDLL(copy)
     envs[name] = env
     lib.zs_iw_bernoulli_fused.restype = i32
-    lib.zs_iw_bernoulli_fused.argtypes = [i32] + [vp] * 9 + [i64, i64, i64, dbl, vp]
+    lib.zs_iw_bernoulli_fused.argtypes = [i32] + [vp] * 9 + [i64, i64, i64, dbl, i32, vp]
     libs.append((name, lib))
 dev = "cuda"
 torch.manual_seed(0)
@@ -38,8 +38,8 @@ stream = torch.cuda.current_stream().cuda_stream
 
 
 def set_env(name, on):
-    # the library reads some knobs once (first call) and ZS_FUSED_IMPL on every call: keep the variant's
-    # environment in place whenever that variant runs
+    # every variant library reads its knobs once, at its first call: the variant's environment must be in place
+    # then (set_env around first_call)
     for k, v in envs[name].items():
         if on:
             os.environ[k] = v
@@ -57,7 +57,7 @@ def first_call(name, lib):
 def run(lib, o, est):
     rc = lib.zs_iw_bernoulli_fused(est, o["cost"].data_ptr(), o["dprobs"].data_ptr(), o["dlogp"].data_ptr(),
                                    o["dlogq"].data_ptr(), None, probs.data_ptr(), x.data_ptr(), other.data_ptr(),
-                                   logq.data_ptr(), K, B, X, 1.0 / B, stream)
+                                   logq.data_ptr(), K, B, X, 1.0 / B, 0, stream)
     assert rc == 0, rc
 
 

@@ -31,8 +31,9 @@ def both():
     with torch.cuda.stream(s2): dprobs_h.copy_(d, non_blocking=True)
 dt = t("H2D + D2H concurrently", both); print("   %.1f GB/s aggregate" % (2 * nb / dt / 1e9))
 ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=dev)
-t("zs_iw_step_host (C ABI, pipelined)", lambda: be.iw_step_host(be.SGVB, cost_h, dprobs_h, dlp_h, dlq_h, probs_h, x_h, other_h, logq_h, K, B, X, 1.0 / B, ws))
-t("zs_iw_step_host, no dprobs", lambda: be.iw_step_host(be.SGVB, cost_h, None, dlp_h, dlq_h, probs_h, x_h, other_h, logq_h, K, B, X, 1.0 / B, ws))
+hs = be.HostStep(dev)
+t("zs_iw_step_host (C ABI, pipelined)", lambda: be.iw_step_host(hs, be.SGVB, cost_h, dprobs_h, dlp_h, dlq_h, probs_h, x_h, other_h, logq_h, K, B, X, 1.0 / B, ws))
+t("zs_iw_step_host, no dprobs", lambda: be.iw_step_host(hs, be.SGVB, cost_h, None, dlp_h, dlq_h, probs_h, x_h, other_h, logq_h, K, B, X, 1.0 / B, ws))
 from zhusuan import _ops
 def api():
     p = probs_h.detach().requires_grad_()

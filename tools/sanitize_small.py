@@ -16,10 +16,10 @@ for K, B, X in ((50, 9, 784), (7, 5, 128), (25, 160, 256), (33, 20, 512), (20, 6
     other, logq = torch.randn(K, B, device=dev) - 55, torch.randn(K, B, device=dev) + 30
     for est in (be.SGVB, be.VIMCO):
         for impl in ("box", "boxg", "ring"):
-            os.environ["ZS_FUSED_IMPL"] = impl
+            be.set_fused_impl({"box": be.IMPL_BOX, "boxg": be.IMPL_BOXG, "ring": be.IMPL_RING}[impl])
             be.iw_bernoulli_fused(est, probs, x, other, logq, 1.0 / B, want_logpx=True)
             be.iw_bernoulli_fused(est, probs, x, other, logq, 1.0 / B, need_dprobs=False)
-        os.environ.pop("ZS_FUSED_IMPL")
+        be.set_fused_impl(be.IMPL_DEFAULT)
         acc = torch.zeros(B, device=dev)
         be.iw_bernoulli_fused(est, probs, x, other, logq, 1.0 / B, out={"cost": acc}, accumulate_cost=True)
         if be.fused_logits_supported(K, X, torch.float32):
@@ -56,9 +56,10 @@ pin = lambda t: t.pin_memory()
 probs = pin(torch.rand(K, B, X).clamp(0.01, 0.99)); x = pin((torch.rand(B, X) < 0.5).float())
 cost, dprobs = pin(torch.empty(B)), pin(torch.empty(K, B, X))
 ws = torch.empty(be.iw_step_host_workspace(K, B, X), dtype=torch.uint8, device=dev)
+hs = be.HostStep(dev)
 do, dq = torch.randn(K, B, device=dev) - 55, torch.randn(K, B, device=dev) + 30
 dlp, dlq = torch.empty(K, B, device=dev), torch.empty(K, B, device=dev)
-be.iw_step_host_begin(be.SGVB, cost, dprobs, dlp, dlq, probs, x, do, dq, K, B, X, 1.0 / B, ws, True)
-be.iw_step_host_wait(1)
+be.iw_step_host_begin(hs, be.SGVB, cost, dprobs, dlp, dlq, probs, x, do, dq, K, B, X, 1.0 / B, ws, True)
+be.iw_step_host_wait(hs, 1)
 torch.cuda.synchronize()
 print("sanitize_small: all launches completed,", be.launch_count, "launches")

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) k_cat_logpmf_bwd_kb(T* __restrict__ dlogi
 template <typename T>
 __global__ void __launch_bounds__(256) k_cat_sample(T* __restrict__ out, const T* __restrict__ logits, int lm,
                                                     const T* __restrict__ u_in, int64_t K, int64_t M, int64_t C,
-                                                    uint64_t seed, uint64_t offset) {
+                                                    uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     const int64_t R = K * M;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = r % M;
@@ -170,17 +171,18 @@ using namespace zs;
 extern "C" {
 
 int zs_categorical_sample(int dtype, void* out, const void* logits, int logits_mode, const void* u_in, int64_t K,
-                          int64_t M, int64_t C, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                          int64_t M, int64_t C, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(out && logits && K >= 0 && M >= 0 && C >= 1, ZS_ERR_ARG);
+    unsigned long long* rs = u_in ? nullptr : (unsigned long long*)rng_state;  // injected uniforms: no draw
     ZS_REQUIRE(logits_mode == ZS_FULL || logits_mode == ZS_KBCAST, ZS_ERR_ARG);
     if (K * M == 0) return ZS_OK;
     const int grid = grid_for(K * M, 256);
     if (dtype == ZS_F32)
         k_cat_sample<float><<<grid, 256, 0, as_stream(stream)>>>((float*)out, (const float*)logits, logits_mode,
-                                                                  (const float*)u_in, K, M, C, seed, offset);
+                                                                  (const float*)u_in, K, M, C, seed, offset, rs);
     else if (dtype == ZS_F64)
         k_cat_sample<double><<<grid, 256, 0, as_stream(stream)>>>((double*)out, (const double*)logits, logits_mode,
-                                                                   (const double*)u_in, K, M, C, seed, offset);
+                                                                   (const double*)u_in, K, M, C, seed, offset, rs);
     else {
         set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
         return ZS_ERR_DTYPE;

@@ -42,7 +42,7 @@ inline bool valid_mode(int m) { return m == ZS_FULL || m == ZS_KBCAST || m == ZS
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(zs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();  // cached per process (current device at first call)
+int sm_count();  // of the current device (cached per device)
 
 // ---- 16-byte packs ---------------------------------------------------------
 template <typename T>

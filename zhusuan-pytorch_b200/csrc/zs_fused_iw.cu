@@ -7,10 +7,9 @@
 //   ImportanceWeightedObjective.log_joint / sgvb / vimco
 //                                  zhusuan/variational/importance_weighted_objective.py:66-77,102-191
 //
-// Five kernels live in this file, newest last; zs_iw_bernoulli_fused picks box -> generic box -> ring -> l2
-// (ZS_FUSED_IMPL overrides; DESIGN.md 3.1 has the measurements behind each step):
-//   k_iw_bernoulli_fused   (smem) whole column resident, no prefetch, objective on the critical path   123 us
-//   k_iw_bernoulli_colfused (l2)  no residency, second pass re-reads "from L2", several CTAs per SM      95 us
+// Three kernels live in this file; zs_iw_bernoulli_fused picks box -> generic box -> ring
+// (DESIGN.md 3.1 has the measurements behind each step; the two round-1 predecessors -- whole column resident
+// without prefetch, 123 us, and re-read-from-L2, 95 us -- were removed):
 //   k_iw_bernoulli_ring    (ring) persistent warp-specialised CTA, per-warp rings of 1-D bulk row copies  66.5 us
 //   k_iw_bernoulli_box     (boxg) column resident between its two passes, 3-D TENSOR bulk copies         69.8 us
 //   k_iw_bernoulli_boxf    (box)  the same with compile-time box geometry, signed-argument x staging,
@@ -27,9 +26,16 @@
 
 #include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched at run time, libcuda is not linked
 
+#include <initializer_list>
+#include <new>
+
 #include "zs_common.cuh"
 
 namespace zs {
+
+// launch flags of the fused kernels (kernel parameter `flags`)
+constexpr int FUSED_ACCUMULATE = 1;   // cost[b] += cost_b (running sum over launches) instead of cost[b] = cost_b
+constexpr int FUSED_EARLY_ISSUE = 2;  // ring kernel dev knob: first bulk copies before the first staging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,287 +78,10 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                  : "memory");
 }
 
-struct FusedSmemLayout {
-    int K, X, Kpad;
-    __host__ __device__ FusedSmemLayout(int K_, int X_) : K(K_), X(X_), Kpad((K_ + 3) & ~3) {}
-    __host__ __device__ size_t rows_off() const { return 0; }
-    __host__ __device__ size_t xrow_off() const { return (size_t)K * X * 4; }
-    __host__ __device__ size_t lpx_off() const { return xrow_off() + (size_t)2 * X * 4; }   // [2][Kpad]
-    __host__ __device__ size_t rest_off() const { return lpx_off() + (size_t)2 * Kpad * 4; }
-    __host__ __device__ size_t lq_off() const { return rest_off() + (size_t)Kpad * 4; }
-    __host__ __device__ size_t g_off() const { return lq_off() + (size_t)Kpad * 4; }
-    __host__ __device__ size_t xw_off() const { return (g_off() + (size_t)Kpad * 4 + 15) & ~(size_t)15; }  // double[Kpad]
-    __host__ __device__ size_t bar_off() const { return (xw_off() + (size_t)Kpad * 8 + 15) & ~(size_t)15; }
-    __host__ __device__ size_t total() const { return bar_off() + (size_t)(K + 2) * 8; }
-};
-
-// One warp turns the K log-weights of a column into cost, weights and gradients (all in smem/regs).
-// As in k_iw_objective, log w and its centring are carried in double (K values: negligible work).
-template <int EST>
-__device__ __forceinline__ void warp_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
-                                               const float* s_other, const float* s_lq, double* s_xw, float* s_g,
-                                               float gscale, float* __restrict__ cost, float* __restrict__ dlogp,
-                                               float* __restrict__ dlogq, float* __restrict__ logpx_out) {
-    const unsigned FULL = 0xffffffffu;
-    double m1 = -INFINITY, m2 = -INFINITY, sumd = 0.0;
-    int i1 = -1;
-    for (int k = lane; k < K; k += 32) {
-        // same association as k_iw_objective: (logp - logq) + extra
-        double xv = ((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k];
-        s_xw[k] = xv;
-        if (xv > m1 || i1 < 0) {
-            m2 = m1; m1 = xv; i1 = k;
-        } else if (xv > m2) {
-            m2 = xv;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double om1 = __shfl_xor_sync(FULL, m1, o), om2 = __shfl_xor_sync(FULL, m2, o);
-        int oi1 = __shfl_xor_sync(FULL, i1, o);
-        bool other = (oi1 >= 0) && (i1 < 0 || om1 > m1 || (om1 == m1 && oi1 < i1));
-        double loser = other ? m1 : om1;
-        m2 = fmax(loser, fmax(m2, om2));
-        m1 = other ? om1 : m1;
-        i1 = other ? oi1 : i1;
-    }
-    const float gap = (float)(m1 - m2);
-
-    float S = 0.f, S2 = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        double xv = s_xw[k];
-        S += expf((float)(xv - m1));
-        if (EST == ZS_EST_VIMCO) {
-            sumd += xv - m1;
-            if (k != i1) S2 += expf((float)(xv - m2));
-        }
-    }
-    S = warp_sum(S);
-    if (EST == ZS_EST_VIMCO) {
-        S2 = warp_sum(S2);
-        sumd = warp_sum(sumd);
-    }
-
-    double c_acc = 0.0;
-    const float invS = 1.0f / S;
-    const double km1 = (double)(K - 1);
-    for (int k = lane; k < K; k += 32) {
-        const double xv = s_xw[k];
-        const float e = expf((float)(xv - m1));
-        const float wt = e / S;
-        c_acc -= (double)wt * xv;
-        float gq = wt;
-        if (EST == ZS_EST_VIMCO) {
-            const float lq = s_lq[k];
-            const float mu_m = (float)((sumd - (xv - m1)) / km1);
-            float sig;
-            if (k == i1 && gap > 1.0f) {
-                float Sloo = S2 + expf(mu_m + gap);
-                sig = gap + (logf(S) - logf(Sloo));
-            } else {
-                sig = -log1pf((expf(mu_m) - e) * invS);
-            }
-            c_acc -= (double)lq * (double)sig;
-            gq = wt - sig;
-        }
-        const float gp = -wt * gscale;
-        s_g[k] = gp;
-        if (dlogp) dlogp[(int64_t)k * B + b] = gp;
-        if (dlogq) dlogq[(int64_t)k * B + b] = gq * gscale;
-        if (logpx_out) logpx_out[(int64_t)k * B + b] = s_lpx[k];
-    }
-    c_acc = warp_sum(c_acc);
-    if (lane == 0 && cost) cost[b] = (float)c_acc;
-}
-
-template <int EST>
-__global__ void __launch_bounds__(1024, 1)
-    k_iw_bernoulli_fused(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
-                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
-                         const float* __restrict__ x, const float* __restrict__ logp_other,
-                         const float* __restrict__ logq, int K, int64_t B, int X, float gscale) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const FusedSmemLayout L(K, X);
-    float* rows = reinterpret_cast<float*>(smem + L.rows_off());
-    float* xrow = reinterpret_cast<float*>(smem + L.xrow_off());
-    float* s_lpx = reinterpret_cast<float*>(smem + L.lpx_off());
-    float* s_rest = reinterpret_cast<float*>(smem + L.rest_off());
-    float* s_lq = reinterpret_cast<float*>(smem + L.lq_off());
-    float* s_g = reinterpret_cast<float*>(smem + L.g_off());
-    double* s_xw = reinterpret_cast<double*>(smem + L.xw_off());
-    uint64_t* bar_row = reinterpret_cast<uint64_t*>(smem + L.bar_off());
-    uint64_t* bar_x = bar_row + K;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
-    const int X4 = X >> 2;
-    const uint32_t row_bytes = (uint32_t)X * 4u;
-    const float LN2 = 0.6931471805599453f;
-
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < K + 2; ++k) mbar_init(&bar_row[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int64_t b0 = blockIdx.x;
-    if (b0 >= B) return;  // uniform per CTA
-
-    // prologue: first column's rows (each warp loads the rows it owns) and x row
-    if (lane == 0) {
-        for (int k = warp; k < K; k += NW) {
-            mbar_expect_tx(&bar_row[k], row_bytes);
-            bulk_load(rows + (size_t)k * X, probs + ((int64_t)k * B + b0) * X, row_bytes, &bar_row[k]);
-        }
-    }
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar_x[0], row_bytes);
-        bulk_load(xrow, x + b0 * X, row_bytes, &bar_x[0]);
-    }
-
-    int it = 0;
-    for (int64_t b = b0; b < B; b += gridDim.x, ++it) {
-        const int64_t b_next = b + gridDim.x;
-        const bool has_next = b_next < B;
-        const float* xb = xrow + (size_t)(it & 1) * X;
-        float* lpx = s_lpx + (size_t)(it & 1) * L.Kpad;
-
-        // per-column scalars of the other log-weight terms
-        for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            float o = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
-            float q = logq ? logq[(int64_t)k * B + b] : 0.f;
-            s_rest[k] = o;
-            s_lq[k] = q;
-        }
-
-        mbar_wait(&bar_x[it & 1], (uint32_t)((it >> 1) & 1));
-        const float4* x4 = reinterpret_cast<const float4*>(xb);
-        // binary observations (the MNIST-shaped configs) need one log / one reciprocal per element
-        bool binary = true;
-        for (int v = lane; v < X4; v += 32) {
-            float4 xx = x4[v];
-            binary = binary && (xx.x == 0.f || xx.x == 1.f) && (xx.y == 0.f || xx.y == 1.f) &&
-                     (xx.z == 0.f || xx.z == 1.f) && (xx.w == 0.f || xx.w == 1.f);
-        }
-        binary = __all_sync(0xffffffffu, binary);
-
-        // ---- phase A: log-pmf of each owned row -------------------------------------------
-        for (int k = warp; k < K; k += NW) {
-            mbar_wait(&bar_row[k], (uint32_t)(it & 1));
-            const float4* p4 = reinterpret_cast<const float4*>(rows + (size_t)k * X);
-            float acc = 0.f;
-            if (binary) {
-                float mn = 1.0f;
-#pragma unroll 4
-                for (int v = lane; v < X4; v += 32) {
-                    const float4 p = p4[v], xx = x4[v];
-                    float a, bb;
-                    a = p.x + 1e-8f; bb = (1.0f - p.x) + 1e-8f; mn = fminf(mn, fminf(a, bb)); acc += fast_log2(xx.x == 1.f ? a : bb);
-                    a = p.y + 1e-8f; bb = (1.0f - p.y) + 1e-8f; mn = fminf(mn, fminf(a, bb)); acc += fast_log2(xx.y == 1.f ? a : bb);
-                    a = p.z + 1e-8f; bb = (1.0f - p.z) + 1e-8f; mn = fminf(mn, fminf(a, bb)); acc += fast_log2(xx.z == 1.f ? a : bb);
-                    a = p.w + 1e-8f; bb = (1.0f - p.w) + 1e-8f; mn = fminf(mn, fminf(a, bb)); acc += fast_log2(xx.w == 1.f ? a : bb);
-                }
-                // the reference's x*log(a) + (1-x)*log(b) is NaN whenever either log argument is negative
-                if (mn < 0.f) acc = __int_as_float(0x7fc00000);
-            } else {
-#pragma unroll 4
-                for (int v = lane; v < X4; v += 32) {
-                    const float4 p = p4[v], xx = x4[v];
-                    acc += xx.x * fast_log2(p.x + 1e-8f) + (1.0f - xx.x) * fast_log2((1.0f - p.x) + 1e-8f);
-                    acc += xx.y * fast_log2(p.y + 1e-8f) + (1.0f - xx.y) * fast_log2((1.0f - p.y) + 1e-8f);
-                    acc += xx.z * fast_log2(p.z + 1e-8f) + (1.0f - xx.z) * fast_log2((1.0f - p.z) + 1e-8f);
-                    acc += xx.w * fast_log2(p.w + 1e-8f) + (1.0f - xx.w) * fast_log2((1.0f - p.w) + 1e-8f);
-                }
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) lpx[k] = acc * LN2;
-        }
-        __syncthreads();
-
-        // x row of the next column: its buffer was last read in phase B of the previous column
-        if (threadIdx.x == 0 && has_next) {
-            mbar_expect_tx(&bar_x[(it + 1) & 1], row_bytes);
-            bulk_load(xrow + (size_t)((it + 1) & 1) * X, x + b_next * X, row_bytes, &bar_x[(it + 1) & 1]);
-        }
-        if (warp == 0)
-            warp_objective<EST>(lane, K, B, b, lpx, s_rest, s_lq, s_xw, s_g, gscale, cost, dlogp, dlogq, logpx_out);
-        __syncthreads();
-
-        // ---- phase B: dprobs from the resident rows, then refill the row for the next column ----
-        for (int k = warp; k < K; k += NW) {
-            if (dprobs) {
-                const float4* p4 = reinterpret_cast<const float4*>(rows + (size_t)k * X);
-                float* drow = dprobs + ((int64_t)k * B + b) * X;
-                const float g = s_g[k];
-                if (binary) {
-                    const float ng = -g;
-#pragma unroll 4
-                    for (int v = lane; v < X4; v += 32) {
-                        const float4 p = p4[v], xx = x4[v];
-                        Pack<float> o;
-                        o.v[0] = (xx.x == 1.f ? g : ng) * fast_rcp(xx.x == 1.f ? p.x + 1e-8f : (1.0f - p.x) + 1e-8f);
-                        o.v[1] = (xx.y == 1.f ? g : ng) * fast_rcp(xx.y == 1.f ? p.y + 1e-8f : (1.0f - p.y) + 1e-8f);
-                        o.v[2] = (xx.z == 1.f ? g : ng) * fast_rcp(xx.z == 1.f ? p.z + 1e-8f : (1.0f - p.z) + 1e-8f);
-                        o.v[3] = (xx.w == 1.f ? g : ng) * fast_rcp(xx.w == 1.f ? p.w + 1e-8f : (1.0f - p.w) + 1e-8f);
-                        st_pack_stream(drow + 4 * v, o);
-                    }
-                } else {
-#pragma unroll 4
-                    for (int v = lane; v < X4; v += 32) {
-                        const float4 p = p4[v], xx = x4[v];
-                        Pack<float> o;
-                        o.v[0] = (g * xx.x) * fast_rcp(p.x + 1e-8f) - (g * (1.0f - xx.x)) * fast_rcp((1.0f - p.x) + 1e-8f);
-                        o.v[1] = (g * xx.y) * fast_rcp(p.y + 1e-8f) - (g * (1.0f - xx.y)) * fast_rcp((1.0f - p.y) + 1e-8f);
-                        o.v[2] = (g * xx.z) * fast_rcp(p.z + 1e-8f) - (g * (1.0f - xx.z)) * fast_rcp((1.0f - p.z) + 1e-8f);
-                        o.v[3] = (g * xx.w) * fast_rcp(p.w + 1e-8f) - (g * (1.0f - xx.w)) * fast_rcp((1.0f - p.w) + 1e-8f);
-                        st_pack_stream(drow + 4 * v, o);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && has_next) {
-                mbar_expect_tx(&bar_row[k], row_bytes);
-                bulk_load(rows + (size_t)k * X, probs + ((int64_t)k * B + b_next) * X, row_bytes, &bar_row[k]);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Column-fused variant that keeps the in-flight columns in L2 instead of shared memory.
-// A CTA walks batch columns; phase A streams the K rows of its column from HBM and reduces their
-// log-pmf, warp 0 forms the weights, phase B RE-READS the same rows — now L2 hits, the 126 MB L2
-// holds every in-flight column (CTAs * K*X*4 bytes, 46 MB at 2 CTAs/SM) — and writes dprobs.
-// HBM traffic equals the shared-memory variant (probs once, dprobs once) but several CTAs per SM sit
-// in different phases, so loads, math and stores overlap by thread-level parallelism and there is no
-// K*X shared-memory limit.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// not volatile: loads of read-only data may be hoisted and batched by the compiler
-__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t) {
-    float4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-        : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void stg_hint(float* p, const float4& v, uint64_t) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
-
-constexpr int COLF_ROW_WARPS_MAX = 12;                         // row-owning warps per CTA
-constexpr int COLF_MAX_THREADS = (COLF_ROW_WARPS_MAX + 1) * 32;  // + one objective warp
-constexpr int COLF_BATCH = 4;                                  // float4 loads in flight per lane
-constexpr int COLF_MIN_CTAS = 3;
 
 // log-pmf contribution of 4 elements (log2 units) / their dprobs; binary x needs one SFU op per element
 template <bool BINARY>
@@ -389,49 +118,10 @@ __device__ __forceinline__ float4 dprobs4(const float4& p, const float4& xx, flo
     return o;
 }
 
-template <bool BINARY>
-__device__ __forceinline__ float row_logpmf(const float4* __restrict__ p4, const float4* __restrict__ x4, int X4,
-                                            int lane, uint64_t pol) {
-    float acc = 0.f, mn = 1.0f;
-    for (int v0 = lane; v0 < X4; v0 += 32 * COLF_BATCH) {
-        float4 p[COLF_BATCH];
-#pragma unroll
-        for (int u = 0; u < COLF_BATCH; ++u) {
-            const int v = v0 + 32 * u;
-            p[u] = ldg_hint(p4 + (v < X4 ? v : v0), pol);  // always in bounds: p[] stays in registers
-        }
-#pragma unroll
-        for (int u = 0; u < COLF_BATCH; ++u) {
-            const int v = v0 + 32 * u;
-            if (v < X4) acc += lpmf4<BINARY>(p[u], lds128(x4 + v), mn);
-        }
-    }
-    if (BINARY && mn < 0.f) acc = __int_as_float(0x7fc00000);  // a negative log argument is NaN in the reference
-    return acc;
-}
-
-template <bool BINARY>
-__device__ __forceinline__ void row_dprobs(float* __restrict__ drow, const float4* __restrict__ p4,
-                                           const float4* __restrict__ x4, int X4, int lane, float g, uint64_t pol) {
-    for (int v0 = lane; v0 < X4; v0 += 32 * COLF_BATCH) {
-        float4 p[COLF_BATCH];
-#pragma unroll
-        for (int u = 0; u < COLF_BATCH; ++u) {
-            const int v = v0 + 32 * u;
-            p[u] = ldg_hint(p4 + (v < X4 ? v : v0), pol);
-        }
-#pragma unroll
-        for (int u = 0; u < COLF_BATCH; ++u) {
-            const int v = v0 + 32 * u;
-            if (v < X4) stg_hint(drow + 4 * v, dprobs4<BINARY>(p[u], lds128(x4 + v), g), pol);
-        }
-    }
-}
-
 // Objective warp: turns the K log-weights of a column into cost, dlogp, dlogq (global) — off the
 // critical path of the row warps.  Same math as k_iw_objective; reciprocal instead of IEEE division.
 template <int EST>
-__device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
+__device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
                                                const float* s_other, const float* s_lq, double* s_xw, float gscale,
                                                float* __restrict__ cost, float* __restrict__ dlogp,
                                                float* __restrict__ dlogq, float* __restrict__ logpx_out,
@@ -512,119 +202,6 @@ __device__ __forceinline__ void colf_objective(int lane, int K, int64_t B, int64
     c_acc = warp_sum(c_acc);
     // accumulate: running sum of the column's objective over launches (one writer per column: deterministic)
     if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc;
-}
-
-// Every row warp needs only max and sum-exp of the column to weight its own rows.
-__device__ __forceinline__ void colf_max_sumexp(int lane, int K, const float* s_lpx, const float* s_other,
-                                                const float* s_lq, double& m1, float& invS) {
-    float mf = -INFINITY;
-    for (int k = lane; k < K; k += 32)
-        mf = fmaxf(mf, (float)(((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k]));
-    mf = warp_max(mf);
-    m1 = (double)mf;
-    float S = 0.f;
-    for (int k = lane; k < K; k += 32)
-        S += expf((float)((((double)s_lpx[k] - (double)s_lq[k]) + (double)s_other[k]) - m1));
-    S = warp_sum(S);
-    invS = fast_rcp(S) * (2.0f - S * fast_rcp(S));
-}
-
-template <int EST, bool TRACE>
-__global__ void __launch_bounds__(COLF_MAX_THREADS, COLF_MIN_CTAS)
-    k_iw_bernoulli_colfused(float* __restrict__ cost, float* __restrict__ dprobs, float* __restrict__ dlogp,
-                            float* __restrict__ dlogq, float* __restrict__ logpx_out,
-                            const float* __restrict__ probs, const float* __restrict__ x,
-                            const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B,
-                            int X, float gscale, long long* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int Kpad = (K + 3) & ~3;
-    float* s_x = reinterpret_cast<float*>(smem);                      // [3][X]    x rows, by column % 3
-    double* s_xw = reinterpret_cast<double*>(s_x + 3 * (size_t)X);    // [Kpad]    objective warp scratch
-    float* s_lpx = reinterpret_cast<float*>(s_xw + Kpad);              // [2][Kpad] by column parity
-    float* s_other = s_lpx + 2 * Kpad;                                 // [2][Kpad]
-    float* s_lq = s_other + 2 * Kpad;                                  // [2][Kpad]
-    int* s_bin = reinterpret_cast<int*>(s_lq + 2 * Kpad);              // [3]       x row is binary
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NW = (blockDim.x >> 5) - 1;  // row warps; warp NW is the objective warp
-    const bool is_obj = warp == NW;
-    const int X4 = X >> 2;
-    const float LN2 = 0.6931471805599453f;
-    const uint64_t keep = 0, done = 0;  // placeholders for L2 eviction policies (see ldg_hint)
-    auto mark = [&](int col, int point) {
-        if (TRACE && trace != nullptr && threadIdx.x == 0 && col < 8)
-            trace[(int64_t)blockIdx.x * 40 + col * 5 + point] = clock64();
-    };
-
-    // Staging done by the objective warp, ahead of the row warps:
-    //   per-column scalars (other log-weight terms) one column ahead, the observation row x two ahead
-    auto stage_scalars = [&](int64_t b, int par) {
-        for (int k = lane; k < K; k += 32) {
-            s_other[par * Kpad + k] = logp_other ? logp_other[(int64_t)k * B + b] : 0.f;
-            s_lq[par * Kpad + k] = logq ? logq[(int64_t)k * B + b] : 0.f;
-        }
-    };
-    auto stage_x = [&](int64_t b, int slot) {
-        const float4* src = reinterpret_cast<const float4*>(x + b * X);
-        float4* dst = reinterpret_cast<float4*>(s_x + (size_t)slot * X);
-        bool binary = true;
-        for (int v = lane; v < X4; v += 32) {
-            const float4 xx = __ldg(src + v);
-            dst[v] = xx;
-            binary = binary && (xx.x == 0.f || xx.x == 1.f) && (xx.y == 0.f || xx.y == 1.f) &&
-                     (xx.z == 0.f || xx.z == 1.f) && (xx.w == 0.f || xx.w == 1.f);
-        }
-        binary = __all_sync(0xffffffffu, binary);
-        if (lane == 0) s_bin[slot] = binary ? 1 : 0;
-    };
-    if (is_obj) {
-        const int64_t b0 = blockIdx.x, b1 = b0 + gridDim.x;
-        if (b0 < B) { stage_scalars(b0, 0); stage_x(b0, 0); }
-        if (b1 < B) stage_x(b1, 1);
-    }
-    __syncthreads();
-
-    int it = 0;
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x, ++it) {
-        const int par = it & 1, slot = it % 3;
-        const float4* x4 = reinterpret_cast<const float4*>(s_x + (size_t)slot * X);
-        const bool binary = s_bin[slot] != 0;
-        mark(it, 0);
-        if (!is_obj) {
-            // ---- phase A: stream the rows from HBM (they stay in L2), reduce their log-pmf ----------
-            for (int k = warp; k < K; k += NW) {
-                const float4* p4 = reinterpret_cast<const float4*>(probs + ((int64_t)k * B + b) * X);
-                float acc = binary ? row_logpmf<true>(p4, x4, X4, lane, keep) : row_logpmf<false>(p4, x4, X4, lane, keep);
-                acc = warp_sum(acc);
-                if (lane == 0) s_lpx[par * Kpad + k] = acc * LN2;
-            }
-        }
-        mark(it, 1);
-        __syncthreads();  // lpx of this column complete; everything staged so far is visible
-        mark(it, 2);
-        if (is_obj) {
-            colf_objective<EST>(lane, K, B, b, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, s_xw, gscale,
-                                cost, dlogp, dlogq, logpx_out);
-            const int64_t b1 = b + gridDim.x, b2 = b1 + gridDim.x;
-            if (b1 < B) stage_scalars(b1, par ^ 1);
-            if (b2 < B) stage_x(b2, (it + 2) % 3);
-        } else if (dprobs) {
-            // ---- phase B: weights of the owned rows, then the rows again (L2 hits) -> dprobs ---------
-            double m1;
-            float invS;
-            colf_max_sumexp(lane, K, s_lpx + par * Kpad, s_other + par * Kpad, s_lq + par * Kpad, m1, invS);
-            for (int k = warp; k < K; k += NW) {
-                const double xv = ((double)s_lpx[par * Kpad + k] - (double)s_lq[par * Kpad + k]) +
-                                  (double)s_other[par * Kpad + k];
-                const float g = -(expf((float)(xv - m1)) * invS) * gscale;
-                const float4* p4 = reinterpret_cast<const float4*>(probs + ((int64_t)k * B + b) * X);
-                float* drow = dprobs + ((int64_t)k * B + b) * X;
-                if (binary) row_dprobs<true>(drow, p4, x4, X4, lane, g, done);
-                else row_dprobs<false>(drow, p4, x4, X4, lane, g, done);
-            }
-        }
-        mark(it, 3);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -868,10 +445,10 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
                         const float* __restrict__ x, const float* __restrict__ logp_other,
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
-                        int stagger_groups, int stagger_cycles, long long* __restrict__ trace, int64_t ldkb) {
+                        int stagger_groups, int stagger_cycles, int flags, long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
-    stagger_start(stagger_groups & 0xff, stagger_cycles);
+    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
+    stagger_start(stagger_groups, stagger_cycles);
     const RingLayout L(K, X, R);
     const int Kpad = L.Kpad;
     float* slots = reinterpret_cast<float*>(smem + L.slots_off());
@@ -924,8 +501,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
             if (++pf_ph == phases) { pf_ph = 0; ++pf_c; pf_b += gridDim.x; }
         }
     };
-    const bool early_issue = (stagger_groups & 0x100) != 0;  // dev knob folded into the launch parameter
-    stagger_groups &= 0xff;
+    const bool early_issue = (flags & FUSED_EARLY_ISSUE) != 0;  // dev knob
     if (early_issue && warp < NW && lane == 0)
         for (int i = 0; i < D; ++i) issue_next();
     // Per-column scalars and log-pmf live in 4 buffers (column & 3), the x row in 3 (column % 3):
@@ -969,7 +545,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
@@ -1136,7 +712,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                        float* __restrict__ logpx_out, const float* __restrict__ x,
                        const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B, int X,
                        int inner, int nslot, int l2_ahead, float gscale, int stagger_groups, int stagger_cycles,
-                       long long* __restrict__ trace, int64_t ldkb) {
+                       int flags, long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
     const BoxLayout L(K, X, inner, nslot);
     const int Kpad = L.Kpad;
@@ -1176,8 +752,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
-    stagger_start(stagger_groups & 0xff, stagger_cycles);
+    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
+    stagger_start(stagger_groups, stagger_cycles);
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
         stage_x(blockIdx.x, 0);
@@ -1246,7 +822,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
@@ -1500,7 +1076,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                         float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
                         float* __restrict__ logpx_out, const float* __restrict__ x,
                         const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B,
-                        int nslot, float gscale, int stagger_groups, int stagger_cycles, int64_t ldkb) {
+                        int nslot, float gscale, int stagger_groups, int stagger_cycles, int flags, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int INNER = INNER4 * 4, X = INNER * NBOX, X4 = X / 4;
     const BoxLayout L(K, X, INNER, nslot);
@@ -1534,8 +1110,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    const bool accumulate_cost = (stagger_groups & 0x200) != 0;  // launch flags ride in the upper bits
-    stagger_start(stagger_groups & 0xff, stagger_cycles);
+    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
+    stagger_start(stagger_groups, stagger_cycles);
     // Column 0 only: column 1 is staged while column 0 is being read.  The first tensor copies are issued AFTER
     // this staging on purpose: issuing them first (measured here and in the ring kernel: +4 and +7 us per launch)
     // starts every CTA's column 0 at the same instant, and the chip then alternates between a read-only phase A
@@ -1590,7 +1166,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);
-            colf_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
+            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
         }
         return;
@@ -1662,133 +1238,67 @@ static int pick_warps_ring(int K) {
     return K < 24 ? (K < 1 ? 1 : K) : 24;
 }
 
-static int pick_warps_colf(int K) {
-    // row warps: equal rows per warp when a divisor of K exists in [4, COLF_ROW_WARPS_MAX]
-    for (int d = COLF_ROW_WARPS_MAX; d >= 4; --d)
-        if (K % d == 0) return d;
-    return K < COLF_ROW_WARPS_MAX ? (K < 1 ? 1 : K) : COLF_ROW_WARPS_MAX;
-}
-
-static int pick_warps(int K) {
-    // each warp owns K/NW rows: prefer an exact divisor so phase A/B are balanced
-    int best = 0;
-    for (int d = 32; d >= 8; --d)
-        if (K % d == 0) { best = d; break; }
-    if (best) return best;
-    return K < 32 ? K : 32;
-}
-
 }  // namespace zs
 
 using namespace zs;
 
-extern "C" {
+namespace {
 
-int64_t zs_iw_bernoulli_fused_smem_bytes(int64_t K, int64_t X) {
-    if (K < 1 || X < 1 || K > 1 << 20 || X > 1 << 24) return -1;
-    return (int64_t)FusedSmemLayout((int)K, (int)X).total();
+long long* g_trace = nullptr;  // zs_debug_set_trace
+int g_impl_override = -1;      // zs_debug_set_fused_impl
+
+enum { IMPL_RING = 2, IMPL_BOX = 3, IMPL_BOXG = 4 };
+
+// Developer knobs, read from the environment ONCE per process (the hot path never calls getenv):
+//   ZS_FUSED_IMPL       ring | box (default: fixed-geometry box kernels where instantiated, else the generic box kernel,
+//                       else the ring) | boxg (generic box kernel only); zs_debug_set_fused_impl overrides at run time
+//   ZS_FUSED_GRID       fewer CTAs than SMs (per-SM vs chip-level bound)
+//   ZS_FUSED_STAGGER    "groups,cycles" of the CTA start stagger
+//   ZS_FUSED_L2_AHEAD   boxes requested into L2 ahead of the shared-memory copies (generic box kernel)
+//   ZS_FUSED_RING_DEPTH slots per row warp of the ring kernel;  ZS_FUSED_EARLY  first bulk copies before the staging
+struct FusedKnobs {
+    int impl = IMPL_BOX, grid_cap = 0, l2_ahead = 0, ring_depth = 4, early = ZS_RING_EARLY_DEFAULT;
+    bool stagger_set = false;
+    int stagger_groups = 0, stagger_cycles = 0;
+    FusedKnobs() {
+        if (const char* e = getenv("ZS_FUSED_IMPL")) {
+            if (e[0] == 'r') impl = IMPL_RING;
+            else if (e[0] == 'b') impl = (e[1] == 'o' && e[2] == 'x' && e[3] == 'g') ? IMPL_BOXG : IMPL_BOX;
+        }
+        if (const char* e = getenv("ZS_FUSED_GRID")) grid_cap = atoi(e);
+        if (const char* e = getenv("ZS_FUSED_L2_AHEAD")) l2_ahead = atoi(e);
+        if (const char* e = getenv("ZS_FUSED_RING_DEPTH")) ring_depth = atoi(e) < 1 ? 1 : atoi(e);
+        if (const char* e = getenv("ZS_FUSED_EARLY"))
+            if (e[0] != 0) early = e[0] != '0';
+        if (const char* e = getenv("ZS_FUSED_STAGGER"))
+            stagger_set = sscanf(e, "%d%*c%d", &stagger_groups, &stagger_cycles) == 2;  // "2,4000" or "2x4000"
+    }
+};
+const FusedKnobs& knobs() {
+    static const FusedKnobs k;
+    return k;
 }
+int fused_impl_choice() { return g_impl_override >= 0 ? g_impl_override : knobs().impl; }
 
-static long long* g_trace = nullptr;
-static thread_local bool g_accumulate_cost = false;  // set by zs_iw_bernoulli_fused_accumulate around its launch
-
-#ifndef ZS_FUSED_DEFAULT_IMPL
-#define ZS_FUSED_DEFAULT_IMPL 3
-#endif
-static int fused_impl_choice() {
-    // ZS_FUSED_IMPL = smem | l2 | ring | box (default: fixed-geometry box kernels where instantiated, else the
-    // generic box kernel, else the ring) | boxg (generic box kernel only).  Read on every call (tests switch it).
-    const char* e = getenv("ZS_FUSED_IMPL");
-    if (e == nullptr || e[0] == 0) return ZS_FUSED_DEFAULT_IMPL;
-    switch (e[0]) {
-        case 's': return 0;
-        case 'l': return 1;
-        case 'b': return (e[1] == 'o' && e[2] == 'x' && e[3] == 'g') ? 4 : 3;
-        default: return 2;
-    }
-}
-
-static int launch_fused_smem(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                             const float* probs, const float* x, const float* logp_other, const float* logq,
-                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
-    if (K < 8) {
-        set_last_error_msg("shared-memory fused kernel needs K >= 8");
-        return ZS_ERR_UNSUPPORTED;
-    }
-    const size_t smem = FusedSmemLayout((int)K, (int)X).total();
-    int dev = 0, max_optin = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (smem > (size_t)max_optin) {
-        set_last_error_msg("fused kernel: K*X rows do not fit in shared memory");
-        return ZS_ERR_UNSUPPORTED;
-    }
-    const int nw = pick_warps((int)K);
-    const int threads = nw * 32;
-    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_fused<ZS_EST_SGVB> : k_iw_bernoulli_fused<ZS_EST_VIMCO>;
-    ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    ZS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)sm_count() * occ;
-    if (grid > B) grid = B;
-    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
-                                                               logp_other, logq, (int)K, B, (int)X,
-                                                               (float)grad_scale);
-    ZS_LAUNCH_CHECK("k_iw_bernoulli_fused");
-    return ZS_OK;
-}
-
-static int launch_fused_l2(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                           const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                           int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
-    const int nw = pick_warps_colf((int)K);
-    const int threads = (nw + 1) * 32;
-    const int Kpad = ((int)K + 3) & ~3;
-    const size_t smem = (size_t)3 * X * 4 + (size_t)Kpad * (8 + 6 * 4) + 16;
-    if (smem > 200 * 1024) {
-        set_last_error_msg("fused kernel: K too large");
-        return ZS_ERR_UNSUPPORTED;
-    }
-    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_colfused<ZS_EST_SGVB, false>
-                                         : k_iw_bernoulli_colfused<ZS_EST_VIMCO, false>;
-    if (g_trace != nullptr)
-        kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_colfused<ZS_EST_SGVB, true>
-                                        : k_iw_bernoulli_colfused<ZS_EST_VIMCO, true>;
-    if (smem > 48 * 1024) ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, l2 = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    ZS_CUDA_TRY(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
-    int occ = 1;
-    ZS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) occ = 1;
-    static int max_ctas = -1, l2_pct = -1;  // tuning knobs (tools/microbench.py sweeps them)
-    if (max_ctas < 0) {
-        const char* e = getenv("ZS_FUSED_CTAS_PER_SM");
-        max_ctas = e ? atoi(e) : 3;
-        const char* f = getenv("ZS_FUSED_L2_PCT");
-        l2_pct = f ? atoi(f) : 60;
-    }
-    if (occ > max_ctas) occ = max_ctas;
-    int64_t grid = (int64_t)sm_count() * occ;
-    // columns in flight must stay L2 resident between their two reads
-    const int64_t col_bytes = K * X * 4;
-    const int64_t cap = (l2 > 0 ? (int64_t)l2 : (int64_t)96 << 20) * l2_pct / 100 / (col_bytes > 0 ? col_bytes : 1);
-    if (cap >= 1 && grid > cap) grid = cap;
-    if (grid > B) grid = B;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
-                                                               logp_other, logq, (int)K, B, (int)X,
-                                                               (float)grad_scale, g_trace);
-    ZS_LAUNCH_CHECK("k_iw_bernoulli_colfused");
-    return ZS_OK;
-}
+// One fused launch, as the internal launchers see it.  The [K, .] arrays (logp_other, logq, dlogp, dlogq,
+// logpx_out) have row pitch `ldkb` >= B: the host-buffer step runs chunks of columns straight out of / into
+// full-size device arrays.
+struct FusedCall {
+    int estimator;
+    float *cost, *dprobs, *dlogp, *dlogq, *logpx_out;
+    const float *probs, *x, *logp_other, *logq;
+    int64_t K, B, X, ldkb;
+    double grad_scale;
+    int kflags;  // FUSED_ACCUMULATE | FUSED_EARLY_ISSUE, as the kernels read them
+    bool logits;
+    cudaStream_t st;
+};
 
 // Tensor map of probs[K][B][X] with box {inner, 1, K}; the driver's encoder is looked up through the runtime.
 typedef CUresult (*zs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_probs_map(CUtensorMap* map, const float* probs, int64_t K, int64_t B, int64_t X, int inner) {
+int make_probs_map(CUtensorMap* map, const float* probs, int64_t K, int64_t B, int64_t X, int inner) {
     static zs_encode_tiled_fn encode = nullptr;
     if (encode == nullptr) {
         void* fn = nullptr;
@@ -1816,7 +1326,7 @@ static int make_probs_map(CUtensorMap* map, const float* probs, int64_t K, int64
 
 // Box geometry: `inner` divides X, is a multiple of 4 and at most 256 floats (the copy engine's box limit);
 // the best choice keeps the most lanes busy (inner/4 float4 per row piece against 32-lane steps).
-static int pick_box_inner(int64_t X) {
+int pick_box_inner(int64_t X) {
     int best = 0;
     double best_eff = 0.0;
     for (int inner = 256; inner >= 32; inner -= 4) {
@@ -1831,13 +1341,9 @@ static int pick_box_inner(int64_t X) {
 struct Stagger {
     int groups, cycles;
 };
-// Start-time stagger of the persistent CTAs (stagger_start): ZS_FUSED_STAGGER="groups,cycles" overrides.
-static Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
-    const char* e = getenv("ZS_FUSED_STAGGER");
-    if (e != nullptr) {
-        int g = 0, c = 0;
-        if (sscanf(e, "%d%*c%d", &g, &c) == 2) return Stagger{g, c};  // "2,4000" or "2x4000"
-    }
+// Start-time stagger of the persistent CTAs (stagger_start).
+Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
+    if (knobs().stagger_set) return Stagger{knobs().stagger_groups, knobs().stagger_cycles};
     if (grid <= 1 || B < 4 * grid) return Stagger{1, 0};  // fewer than four columns per CTA: nothing to desynchronise
     // measured at K=50, X=784 (column period ~16k cycles): 3-6 groups spanning 4000-5000 cycles are all within
     // 1% of each other (66.7 us against 70.5 us without); 4 groups of K*X/26 cycles
@@ -1845,10 +1351,26 @@ static Stagger pick_stagger(int64_t K, int64_t X, int64_t B, int64_t grid) {
     return Stagger{4, (int)(cyc > 10000 ? 10000 : cyc)};
 }
 
-static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                            const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                            int64_t B, int64_t X, double grad_scale, zs_stream_t stream, bool generic_only,
-                            int64_t ldkb, bool logits = false) {
+int max_optin_smem(int* out) {
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        ZS_CUDA_TRY(cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cached_dev = dev;
+    }
+    *out = cached;
+    return ZS_OK;
+}
+
+int64_t persistent_grid(int64_t B) {
+    int64_t grid = sm_count();
+    if (knobs().grid_cap > 0 && grid > knobs().grid_cap) grid = knobs().grid_cap;
+    return grid > B ? B : grid;
+}
+
+int launch_fused_box(const FusedCall& c, bool generic_only) {
+    const int64_t K = c.K, B = c.B, X = c.X;
     if (K > 2 * BOX_MAX_ROW_WARPS || B >= ((int64_t)1 << 31) || X * 4 % 16 != 0) {
         set_last_error_msg("box kernel: at most two rows per warp (K <= 50)");
         return ZS_ERR_UNSUPPORTED;
@@ -1858,9 +1380,9 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
         set_last_error_msg("box kernel: no box width divides X well");
         return ZS_ERR_UNSUPPORTED;
     }
-    int dev = 0, max_optin = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int max_optin = 0;
+    int rc = max_optin_smem(&max_optin);
+    if (rc != ZS_OK) return rc;
     const int nbox = (int)(X / inner);
     int nslot = 2 * nbox;  // at most a whole column of prefetch
     while (nslot > nbox && BoxLayout((int)K, (int)X, inner, nslot).total() > (size_t)max_optin) --nslot;
@@ -1869,28 +1391,22 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
         return ZS_ERR_UNSUPPORTED;
     }
     CUtensorMap map;
-    const int rc = make_probs_map(&map, probs, K, B, X, inner);
+    rc = make_probs_map(&map, c.probs, K, B, X, inner);
     if (rc != ZS_OK) return rc;
     const int nw = K <= BOX_MAX_ROW_WARPS ? (int)K : (int)((K + 1) / 2);
     const size_t smem = BoxLayout((int)K, (int)X, inner, nslot).total();
     const int threads = (nw + 4) * 32;
-    int64_t grid = sm_count();
-    {
-        const char* e = getenv("ZS_FUSED_GRID");  // dev knob: fewer CTAs than SMs (per-SM vs chip-level bound)
-        const int cap = e ? atoi(e) : 0;
-        if (cap > 0 && grid > cap) grid = cap;
-    }
-    if (grid > B) grid = B;
+    const int64_t grid = persistent_grid(B);
     const Stagger stg = pick_stagger(K, X, B, grid);
     // fixed-geometry instantiations (fully unrolled box loops) for the common row lengths
     using boxf_fn = decltype(&k_iw_bernoulli_boxf<ZS_EST_SGVB, 28, 7, false>);
     boxf_fn fixed = nullptr;
     if (!generic_only) {
-        const bool sg = estimator == ZS_EST_SGVB;
+        const bool sg = c.estimator == ZS_EST_SGVB;
 #define ZS_BOXF_PICK(I4, NB)                                                                                        \
     if (inner == 4 * (I4) && nbox == (NB))                                                                           \
-        fixed = logits ? (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, true> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, true>) \
-                       : (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, false> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, false>)
+        fixed = c.logits ? (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, true> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, true>) \
+                         : (sg ? k_iw_bernoulli_boxf<ZS_EST_SGVB, I4, NB, false> : k_iw_bernoulli_boxf<ZS_EST_VIMCO, I4, NB, false>)
         ZS_BOXF_PICK(28, 7);   // X = 784
         ZS_BOXF_PICK(32, 1);   // X = 128
         ZS_BOXF_PICK(64, 1);   // X = 256
@@ -1900,48 +1416,38 @@ static int launch_fused_box(int estimator, float* cost, float* dprobs, float* dl
     }
     if (fixed != nullptr) {
         ZS_CUDA_TRY(cudaFuncSetAttribute(fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fixed<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
-                                                                     logq, (int)K, B, nslot, (float)grad_scale,
-                                                                     (stg.groups & 0xff) | (g_accumulate_cost ? 0x200 : 0),
-                                                                     stg.cycles, ldkb);
+        fixed<<<(unsigned)grid, threads, smem, c.st>>>(map, c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.x,
+                                                        c.logp_other, c.logq, (int)K, B, nslot, (float)c.grad_scale,
+                                                        stg.groups, stg.cycles, c.kflags, c.ldkb);
         ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
         return ZS_OK;
     }
-    if (logits) {
+    if (c.logits) {
         set_last_error_msg("fused logits form: no fixed-geometry kernel instantiated for this row length");
         return ZS_ERR_UNSUPPORTED;
     }
-    auto kern = estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
+    auto kern = c.estimator == ZS_EST_SGVB ? k_iw_bernoulli_box<ZS_EST_SGVB> : k_iw_bernoulli_box<ZS_EST_VIMCO>;
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // boxes requested into L2 ahead of the shared-memory copies: measured no gain (0..4) to a loss (>= 7), off
-    static int l2_ahead = -1;
-    if (l2_ahead < 0) {
-        const char* e = getenv("ZS_FUSED_L2_AHEAD");
-        l2_ahead = e ? atoi(e) : 0;
-    }
-    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(map, cost, dprobs, dlogp, dlogq, logpx_out, x, logp_other,
-                                                               logq, (int)K, B, (int)X, inner, nslot, l2_ahead,
-                                                               (float)grad_scale, (stg.groups & 0xff) | (g_accumulate_cost ? 0x200 : 0),
-                                                               stg.cycles, g_trace, ldkb);
+    kern<<<(unsigned)grid, threads, smem, c.st>>>(map, c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.x, c.logp_other,
+                                                  c.logq, (int)K, B, (int)X, inner, nslot, knobs().l2_ahead,
+                                                  (float)c.grad_scale, stg.groups, stg.cycles, c.kflags, g_trace, c.ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
     return ZS_OK;
 }
 
-static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                             const float* probs, const float* x, const float* logp_other, const float* logq,
-                             int64_t K, int64_t B, int64_t X, double grad_scale, zs_stream_t stream, int64_t ldkb) {
-    int dev = 0, max_optin = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    ZS_CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // per-warp mini-rings: NW row warps x D slots each; deepest D (<= 4) that fits, fewer warps if needed
-    static int depth_cap = -1;
-    if (depth_cap < 0) {
-        const char* e = getenv("ZS_FUSED_RING_DEPTH");
-        depth_cap = e ? atoi(e) : 4;
-        if (depth_cap < 1) depth_cap = 1;
+int launch_fused_ring(const FusedCall& c) {
+    const int64_t K = c.K, B = c.B, X = c.X;
+    if (c.logits) {
+        set_last_error_msg("fused logits form: only the fixed-geometry box kernels take logits");
+        return ZS_ERR_UNSUPPORTED;
     }
+    int max_optin = 0;
+    int rc = max_optin_smem(&max_optin);
+    if (rc != ZS_OK) return rc;
+    // per-warp mini-rings: NW row warps x D slots each; deepest D (<= 4) that fits, fewer warps if needed
     int nw = pick_warps_ring((int)K);
-    int D = depth_cap;
+    int D = knobs().ring_depth;
     while (D > 1 && RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) --D;
     while (nw > 1 && RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) --nw;
     if (RingLayout((int)K, (int)X, nw * D).total() > (size_t)max_optin) {
@@ -1951,7 +1457,7 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
     const int R = nw * D;
     const size_t smem = RingLayout((int)K, (int)X, R).total();
     const int threads = (nw + 3) * 32;
-    const bool sgvb = estimator == ZS_EST_SGVB;
+    const bool sgvb = c.estimator == ZS_EST_SGVB;
     const int trips = ((int)(X / 4) + 31) / 32;  // 128-bit loads per lane and row
     // exact trip counts of common row lengths are fully unrolled (784 -> 7)
     auto kern = sgvb ? k_iw_bernoulli_ring<ZS_EST_SGVB, 0> : k_iw_bernoulli_ring<ZS_EST_VIMCO, 0>;
@@ -1963,107 +1469,68 @@ static int launch_fused_ring(int estimator, float* cost, float* dprobs, float* d
         default: break;
     }
     ZS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = sm_count();
-    {
-        const char* e = getenv("ZS_FUSED_GRID");  // dev knob: fewer CTAs than SMs (per-SM vs chip-level bound)
-        const int cap = e ? atoi(e) : 0;
-        if (cap > 0 && grid > cap) grid = cap;
-    }
-    if (grid > B) grid = B;
+    const int64_t grid = persistent_grid(B);
     const Stagger stg = pick_stagger(K, X, B, grid);
-    int early = ZS_RING_EARLY_DEFAULT;
-    {
-        const char* e = getenv("ZS_FUSED_EARLY");  // dev knob: first bulk copies before / after the first staging
-        if (e != nullptr && e[0] != 0) early = e[0] != '0';
-    }
-    kern<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(cost, dprobs, dlogp, dlogq, logpx_out, probs, x,
-                                                               logp_other, logq, (int)K, B, (int)X, R,
-                                                               (float)grad_scale,
-                                                               (stg.groups & 0xff) | (early ? 0x100 : 0) | (g_accumulate_cost ? 0x200 : 0),
-                                                               stg.cycles, g_trace, ldkb);
+    kern<<<(unsigned)grid, threads, smem, c.st>>>(c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.probs, c.x,
+                                                  c.logp_other, c.logq, (int)K, B, (int)X, R, (float)c.grad_scale,
+                                                  stg.groups, stg.cycles,
+                                                  c.kflags | (knobs().early ? FUSED_EARLY_ISSUE : 0), g_trace, c.ldkb);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
     return ZS_OK;
 }
 
-// Box / ring kernels with the [K, .] arrays (logp_other, logq, dlogp, dlogq, logpx_out) at row pitch `ldkb` >= B:
-// the host-buffer step runs chunks of columns straight out of / into full-size device arrays.
-static int fused_launch_pitched(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
-                                const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                                int64_t B, int64_t X, int64_t ldkb, double grad_scale, zs_stream_t stream) {
-    if (X % 4 != 0 || K > 4096 || X > (1 << 20)) {
+// fixed-geometry box kernel -> generic box kernel -> row-streaming ring; ZS_ERR_UNSUPPORTED / ZS_ERR_ALIGN when no
+// fused kernel takes the shape (the caller composes the two-pass entry points)
+int fused_launch(const FusedCall& c) {
+    if (c.X % 4 != 0 || c.K > 4096 || c.X > (1 << 20)) {
         set_last_error_msg("fused kernel needs X % 4 == 0 and K <= 4096");
         return ZS_ERR_UNSUPPORTED;
     }
-    if (!aligned16(probs) || !aligned16(x) || !aligned16(dprobs)) {
+    if (!aligned16(c.probs) || !aligned16(c.x) || !aligned16(c.dprobs)) {
         set_last_error_msg("fused kernel needs 16-byte aligned probs / x / dprobs");
         return ZS_ERR_ALIGN;
     }
     const int impl = fused_impl_choice();
-    if (impl >= 3) {
-        int rc = launch_fused_box(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
-                                  grad_scale, stream, impl == 4, ldkb);
+    if (impl >= IMPL_BOX) {
+        const int rc = launch_fused_box(c, impl == IMPL_BOXG);
         if (rc != ZS_ERR_UNSUPPORTED) return rc;
     }
-    if (impl >= 2)
-        return launch_fused_ring(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
-                                 grad_scale, stream, ldkb);
-    return ZS_ERR_UNSUPPORTED;
+    return launch_fused_ring(c);
 }
 
-int zs_iw_bernoulli_fused_logits(int estimator, float* cost, float* dlogits, float* dlogp, float* dlogq,
-                                 float* logpx_out, const float* logits, const float* x, const float* logp_other,
-                                 const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
-                                 zs_stream_t stream) {
-    ZS_REQUIRE(logits && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
-    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
-    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
-    if (B == 0) return ZS_OK;
-    if (X % 4 != 0 || !aligned16(logits) || !aligned16(x) || !aligned16(dlogits)) {
-        set_last_error_msg("fused logits form needs X % 4 == 0 and 16-byte aligned logits / x / dlogits");
-        return ZS_ERR_UNSUPPORTED;
-    }
-    return launch_fused_box(estimator, cost, dlogits, dlogp, dlogq, logpx_out, logits, x, logp_other, logq, K, B, X,
-                            grad_scale, stream, false, B, true);
-}
+}  // namespace
+
+extern "C" {
 
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq, float* logpx_out,
                           const float* probs, const float* x, const float* logp_other, const float* logq, int64_t K,
-                          int64_t B, int64_t X, double grad_scale, zs_stream_t stream) {
+                          int64_t B, int64_t X, double grad_scale, int flags, zs_stream_t stream) {
     ZS_REQUIRE(probs && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
+    ZS_REQUIRE((flags & ~(ZS_FUSED_ACCUMULATE_COST | ZS_FUSED_LOGITS)) == 0, ZS_ERR_ARG);
     if (B == 0) return ZS_OK;
-    int rc = fused_launch_pitched(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B,
-                                  grad_scale, stream);
-    if (rc != ZS_ERR_UNSUPPORTED || X % 4 != 0 || K > 4096 || X > (1 << 20)) return rc;
-    if (g_accumulate_cost) return ZS_ERR_UNSUPPORTED;  // only the box / ring kernels accumulate
-    if (fused_impl_choice() == 0)
-        return launch_fused_smem(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
-                                 grad_scale, stream);
-    return launch_fused_l2(estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X,
-                           grad_scale, stream);
+    FusedCall c{estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B, grad_scale,
+                (flags & ZS_FUSED_ACCUMULATE_COST) ? FUSED_ACCUMULATE : 0, (flags & ZS_FUSED_LOGITS) != 0,
+                as_stream(stream)};
+    return fused_launch(c);
 }
 
-int zs_iw_bernoulli_fused_accumulate(int estimator, float* cost_sum, float* dprobs, float* dlogp, float* dlogq,
-                                     float* logpx_out, const float* probs, const float* x, const float* logp_other,
-                                     const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale,
-                                     zs_stream_t stream) {
-    g_accumulate_cost = true;
-    const int rc = zs_iw_bernoulli_fused(estimator, cost_sum, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq,
-                                         K, B, X, grad_scale, stream);
-    g_accumulate_cost = false;
-    return rc;
-}
-
-/* Debug hook (not part of the stable ABI surface used by the Python package): device buffer of
- * grid*40 int64 that the L2-resident fused kernel fills with clock64() phase timestamps; NULL disables. */
+/* Debug hooks (not used by the Python package's hot path). */
 int zs_debug_set_trace(void* device_buffer) {
     g_trace = (long long*)device_buffer;
     return ZS_OK;
 }
+int zs_debug_set_fused_impl(int impl) {
+    ZS_REQUIRE(impl == -1 || impl == IMPL_RING || impl == IMPL_BOX || impl == IMPL_BOXG, ZS_ERR_ARG);
+    g_impl_override = impl;
+    return ZS_OK;
+}
+
+}  // extern "C"
 
 // ---- host-buffer step, pipelined over column chunks -----------------------------------------------
-// Batch columns are independent, so the step is cut into chunks of columns that flow through internal
+// Batch columns are independent, so the step is cut into chunks of columns that flow through the handle's
 // streams: H2D copy of chunk c+1, fused kernel on chunk c and D2H copy of chunk c-1 overlap (PCIe is
 // full duplex), with HS_NBUF rotating device buffers.  The [K,B,X] host layout is gathered / scattered
 // with 2-D copies (K rows of chunk*X floats, host pitch B*X).  The first H2D and the last D2H cannot
@@ -2071,56 +1538,34 @@ int zs_debug_set_trace(void* device_buffer) {
 // was measured SLOWER than uniform 128-column chunks (4.06 vs 3.93 ms; 256: 4.14, 512: 4.74; floor 3.45-3.5 ms):
 // the K = 50 strided rows of a small chunk are short DMA segments.  Uniform chunks are the default.
 // The small results (cost, dlogp, dlogq) travel on their own stream ahead of the big dprobs copies, so
-// a caller can go on (zs_iw_step_host_wait(0)) while the gradient of the likelihood is still landing.
+// a caller can go on (zs_iw_step_host_wait(h, 0)) while the gradient of the likelihood is still landing.
+// All state lives in the caller's handle (zs_host_step_create): any number of handles may be in flight, one step
+// per handle at a time.
 namespace {
 constexpr int HS_NBUF = 3;
 constexpr int HS_MAX_CHUNKS = 4096;
 // columns per chunk (ZS_HS_CHUNK) and the size of the first / last chunk (ZS_HS_CHUNK_MIN): dev knobs, read once
-static int64_t hs_env(const char* name, int64_t dflt) {
+int64_t hs_env(const char* name, int64_t dflt) {
     const char* e = getenv(name);
     const long v = e ? atol(e) : 0;
     return v > 0 ? (int64_t)v : dflt;
 }
-static const int64_t HS_CHUNK = hs_env("ZS_HS_CHUNK", 128);
-static const int64_t HS_CHUNK_MIN = hs_env("ZS_HS_CHUNK_MIN", 128);
+const int64_t HS_CHUNK = hs_env("ZS_HS_CHUNK", 128);
+const int64_t HS_CHUNK_MIN = hs_env("ZS_HS_CHUNK_MIN", 128);
+inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+}  // namespace
 
-struct HostStepCtx {
-    bool ready = false;
+struct zs_host_step {
     int device = -1;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr, s_small = nullptr;
-    cudaEvent_t ev_in[HS_NBUF], ev_run[HS_NBUF], ev_out[HS_NBUF], ev_small[HS_NBUF], ev_start = nullptr;
+    cudaEvent_t ev_in[HS_NBUF] = {}, ev_run[HS_NBUF] = {}, ev_out[HS_NBUF] = {}, ev_start = nullptr;
     cudaEvent_t ev_small_done = nullptr, ev_all_done = nullptr;
     bool pending = false;
+    int64_t sizes[HS_MAX_CHUNKS];
 };
-HostStepCtx g_hs;
 
-int host_step_ctx(HostStepCtx** out) {
-    int dev = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    if (!g_hs.ready || g_hs.device != dev) {
-        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_in, cudaStreamNonBlocking));
-        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_run, cudaStreamNonBlocking));
-        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_out, cudaStreamNonBlocking));
-        ZS_CUDA_TRY(cudaStreamCreateWithFlags(&g_hs.s_small, cudaStreamNonBlocking));
-        for (int i = 0; i < HS_NBUF; ++i) {
-            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_in[i], cudaEventDisableTiming));
-            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_run[i], cudaEventDisableTiming));
-            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_out[i], cudaEventDisableTiming));
-            ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_small[i], cudaEventDisableTiming));
-        }
-        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_start, cudaEventDisableTiming));
-        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_small_done, cudaEventDisableTiming));
-        ZS_CUDA_TRY(cudaEventCreateWithFlags(&g_hs.ev_all_done, cudaEventDisableTiming));
-        g_hs.ready = true;
-        g_hs.device = dev;
-        g_hs.pending = false;
-    }
-    *out = &g_hs;
-    return ZS_OK;
-}
-inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
-
-// chunk sizes: 32, 64 at the head, 64, 32 at the tail, HS_CHUNK in between (fewer, smaller chunks for small B)
+namespace {
+// chunk sizes: HS_CHUNK_MIN, 2 HS_CHUNK_MIN, ... at the head and mirrored at the tail, HS_CHUNK in between
 int chunk_schedule(int64_t B, int64_t* sizes) {
     int n = 0;
     int64_t head[8], tail[8];
@@ -2141,7 +1586,60 @@ int chunk_schedule(int64_t B, int64_t* sizes) {
     for (int i = nt - 1; i >= 0; --i) sizes[n++] = tail[i];
     return n;
 }
+
+// run `body` with the handle's device current
+struct DeviceScope {
+    int prev = -1, want = -1;
+    explicit DeviceScope(int dev) : want(dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceScope() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+};
 }  // namespace
+
+extern "C" {
+
+int zs_host_step_create(zs_host_step** out) {
+    ZS_REQUIRE(out != nullptr, ZS_ERR_ARG);
+    *out = nullptr;
+    zs_host_step* h = new (std::nothrow) zs_host_step();
+    ZS_REQUIRE(h != nullptr, ZS_ERR_ARG);
+    auto fail = [&](cudaError_t e, const char* what) {
+        set_last_error(what, e);
+        zs_host_step_destroy(h);
+        return ZS_ERR_CUDA;
+    };
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) return fail(e, "cudaGetDevice");
+    for (cudaStream_t* s : {&h->s_in, &h->s_run, &h->s_out, &h->s_small})
+        if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    for (int i = 0; i < HS_NBUF; ++i)
+        for (cudaEvent_t* ev : {&h->ev_in[i], &h->ev_run[i], &h->ev_out[i]})
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    for (cudaEvent_t* ev : {&h->ev_start, &h->ev_small_done, &h->ev_all_done})
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    *out = h;
+    return ZS_OK;
+}
+
+int zs_host_step_destroy(zs_host_step* h) {
+    if (h == nullptr) return ZS_OK;
+    DeviceScope scope(h->device);
+    if (h->pending && h->ev_all_done) cudaEventSynchronize(h->ev_all_done);
+    for (cudaStream_t s : {h->s_in, h->s_run, h->s_out, h->s_small})
+        if (s) cudaStreamDestroy(s);
+    for (int i = 0; i < HS_NBUF; ++i)
+        for (cudaEvent_t ev : {h->ev_in[i], h->ev_run[i], h->ev_out[i]})
+            if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {h->ev_start, h->ev_small_done, h->ev_all_done})
+        if (ev) cudaEventDestroy(ev);
+    (void)cudaGetLastError();
+    delete h;
+    return ZS_OK;
+}
 
 int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X) {
     if (K < 1 || B < 0 || X < 1) return -1;
@@ -2151,41 +1649,41 @@ int64_t zs_iw_step_host_workspace(int64_t K, int64_t B, int64_t X) {
     return HS_NBUF * per + 4 * up256(K * B * 4) + up256(B * 4);
 }
 
-int zs_iw_step_host_wait(int what) {
-    if (!g_hs.ready) return ZS_OK;
-    int dev = 0;
-    ZS_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev != g_hs.device) ZS_CUDA_TRY(cudaSetDevice(g_hs.device));
-    cudaError_t e = cudaSuccess;
+int zs_iw_step_host_wait(zs_host_step* h, int what) {
+    ZS_REQUIRE(h != nullptr && (what == 0 || what == 1), ZS_ERR_ARG);
+    if (!h->pending) return ZS_OK;
+    DeviceScope scope(h->device);
     if (what == 0) {
-        e = cudaEventSynchronize(g_hs.ev_small_done);
+        ZS_CUDA_TRY(cudaEventSynchronize(h->ev_small_done));
     } else {
-        e = cudaEventSynchronize(g_hs.ev_all_done);
-        if (e == cudaSuccess) g_hs.pending = false;
+        ZS_CUDA_TRY(cudaEventSynchronize(h->ev_all_done));
+        h->pending = false;
     }
-    if (dev != g_hs.device) cudaSetDevice(dev);
-    ZS_CUDA_TRY(e);
     return ZS_OK;
 }
 
-int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, float* dlogp, float* dlogq,
-                          const float* probs_host, const float* x_host, const float* logp_other, const float* logq,
-                          int64_t K, int64_t B, int64_t X, double grad_scale, void* ws, int64_t ws_bytes,
-                          int scalars_on_device, zs_stream_t stream) {
-    ZS_REQUIRE(probs_host && x_host && ws && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
+int zs_iw_step_host_begin(zs_host_step* ctx, int estimator, float* cost_host, float* dprobs_host, float* dlogp,
+                          float* dlogq, const float* probs_host, const float* x_host, const float* logp_other,
+                          const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
+                          int64_t ws_bytes, int scalars_on_device, zs_stream_t stream) {
+    ZS_REQUIRE(ctx && probs_host && x_host && ws && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && logq == nullptr), ZS_ERR_ARG);
     if (ws_bytes < zs_iw_step_host_workspace(K, B, X)) return ZS_ERR_WORKSPACE;
     ZS_REQUIRE(aligned16(ws), ZS_ERR_ALIGN);
-    HostStepCtx* ctx = nullptr;
-    int rc = host_step_ctx(&ctx);
-    if (rc != ZS_OK) return rc;
-    // a previous step whose big copies were left in flight shares the workspace: let it land first
+    int dev = -1;
+    ZS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != ctx->device) {
+        set_last_error_msg("host step: the handle was created on another device");
+        return ZS_ERR_ARG;
+    }
+    int rc = ZS_OK;
+    // a previous step of this handle whose big copies were left in flight shares the workspace: let it land first
     if (ctx->pending) {
-        rc = zs_iw_step_host_wait(1);
+        rc = zs_iw_step_host_wait(ctx, 1);
         if (rc != ZS_OK) return rc;
     }
-    static int64_t sizes[HS_MAX_CHUNKS];
+    int64_t* sizes = ctx->sizes;
     const int nchunks = chunk_schedule(B, sizes);
     if (nchunks < 0) {
         set_last_error_msg("host step: too many column chunks");
@@ -2249,9 +1747,10 @@ int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, f
         ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[i], 0));
         if (c >= HS_NBUF) ZS_CUDA_TRY(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[i], 0));  // dprobs buffer reuse
         zs_stream_t run = (zs_stream_t)ctx->s_run;
-        rc = fused_launch_pitched(estimator, cost_full + b0, dprobs_host ? d.dprobs : nullptr, dlogp_full + b0,
-                                  dlogq_full + b0, nullptr, d.probs, d.x, other_full ? other_full + b0 : nullptr,
-                                  logq_full ? logq_full + b0 : nullptr, K, bc, X, B, grad_scale, run);
+        FusedCall call{estimator, cost_full + b0, dprobs_host ? d.dprobs : nullptr, dlogp_full + b0, dlogq_full + b0,
+                       nullptr, d.probs, d.x, other_full ? other_full + b0 : nullptr, logq_full ? logq_full + b0 : nullptr,
+                       K, bc, X, B, grad_scale, 0, false, ctx->s_run};
+        rc = fused_launch(call);
         if (rc == ZS_ERR_UNSUPPORTED || rc == ZS_ERR_ALIGN) {
             // two-pass form on dense [K,bc] copies of the chunk's columns: likelihood log-pmf, objective,
             // likelihood backward
@@ -2305,17 +1804,17 @@ int zs_iw_step_host_begin(int estimator, float* cost_host, float* dprobs_host, f
     return ZS_OK;
 }
 
-int zs_iw_step_host(int estimator, float* cost_host, float* dprobs_host, float* dlogp_host, float* dlogq_host,
-                    const float* probs_host, const float* x_host, const float* logp_other_host,
+int zs_iw_step_host(zs_host_step* h, int estimator, float* cost_host, float* dprobs_host, float* dlogp_host,
+                    float* dlogq_host, const float* probs_host, const float* x_host, const float* logp_other_host,
                     const float* logq_host, int64_t K, int64_t B, int64_t X, double grad_scale, void* ws,
                     int64_t ws_bytes, zs_stream_t stream) {
-    int rc = zs_iw_step_host_begin(estimator, cost_host, dprobs_host, dlogp_host, dlogq_host, probs_host, x_host,
+    int rc = zs_iw_step_host_begin(h, estimator, cost_host, dprobs_host, dlogp_host, dlogq_host, probs_host, x_host,
                                    logp_other_host, logq_host, K, B, X, grad_scale, ws, ws_bytes, 0, stream);
     if (rc != ZS_OK) {
-        zs_iw_step_host_wait(1);
+        if (h != nullptr) zs_iw_step_host_wait(h, 1);
         return rc;
     }
-    return zs_iw_step_host_wait(1);
+    return zs_iw_step_host_wait(h, 1);
 }
 
 }  // extern "C"

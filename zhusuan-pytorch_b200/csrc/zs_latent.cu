@@ -53,6 +53,14 @@ __device__ __forceinline__ T normal_c() {
     return (T)(-0.9189385332046727);
 }
 
+// Parameter-only transcendentals.  They are redone by every k-slice of a row, so for float they go to the SFU:
+// lg2.approx has an absolute error of 2^-22 in log2 units on [0.5, 2] and <= 2 ulp elsewhere, rcp.approx <= 1 ulp --
+// both far inside the 1e-5 parity budget of a 40-term row sum.  double keeps libm / IEEE division.
+__device__ __forceinline__ float lat_log(float x) { return fast_log2(x) * 0.6931471805599453f; }
+__device__ __forceinline__ double lat_log(double x) { return ::log(x); }
+__device__ __forceinline__ float lat_rcp(float x) { return fast_rcp(x); }
+__device__ __forceinline__ double lat_rcp(double x) { return 1.0 / x; }
+
 // ---------------------------------------------------------------------------------------------
 // forward: G lanes per batch row m; lane j owns float4 units j, j+G, ... of the row.  For KBCAST
 // parameters the group keeps mean / std / log std / precision of its units in registers and walks
@@ -73,9 +81,9 @@ __device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, c
         u.b = ldv4(b + idx);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            u.logb.v[q] = Real<T>::log(u.b.v[q]);
-            // exp(-2 log std) of normal.py:122 is 1 / std^2 to within an ulp; the division costs a third of expf
-            u.prec.v[q] = T(1) / (u.b.v[q] * u.b.v[q]);
+            u.logb.v[q] = lat_log(u.b.v[q]);
+            // exp(-2 log std) of normal.py:122 is 1 / std^2 to within an ulp
+            u.prec.v[q] = lat_rcp(u.b.v[q] * u.b.v[q]);
         }
         if (pa) u.pa = ldv4(pa + kidx);
         else u.pa = V4<T>{{T(0), T(0), T(0), T(0)}};
@@ -83,8 +91,8 @@ __device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, c
             const V4<T> ps = ldv4(pb + kidx);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                u.plogb.v[q] = Real<T>::log(ps.v[q]);
-                u.pprec.v[q] = T(1) / (ps.v[q] * ps.v[q]);
+                u.plogb.v[q] = lat_log(ps.v[q]);
+                u.pprec.v[q] = lat_rcp(ps.v[q] * ps.v[q]);
             }
         } else {
             // standard prior: log(1) = 0 and exp(-2*0) = 1 exactly, as the reference computes them
@@ -94,15 +102,15 @@ __device__ __forceinline__ void load_unit_params(UnitParams<T>& u, const T* a, c
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {  // log(p + 1e-8), log((1-p) + 1e-8) of bernoulli.py:94
-            u.logb.v[q] = Real<T>::log(u.a.v[q] + T(1e-8));
-            u.prec.v[q] = Real<T>::log((T(1) - u.a.v[q]) + T(1e-8));
+            u.logb.v[q] = lat_log(u.a.v[q] + T(1e-8));
+            u.prec.v[q] = lat_log((T(1) - u.a.v[q]) + T(1e-8));
         }
         if (pa) u.pa = ldv4(pa + kidx);
         else u.pa = V4<T>{{T(0.5), T(0.5), T(0.5), T(0.5)}};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            u.plogb.v[q] = Real<T>::log(u.pa.v[q] + T(1e-8));
-            u.pprec.v[q] = Real<T>::log((T(1) - u.pa.v[q]) + T(1e-8));
+            u.plogb.v[q] = lat_log(u.pa.v[q] + T(1e-8));
+            u.pprec.v[q] = lat_log((T(1) - u.pa.v[q]) + T(1e-8));
         }
     }
 }
@@ -112,7 +120,8 @@ __global__ void __launch_bounds__(256)
     k_latent_fwd(T* __restrict__ z, T* __restrict__ logq, T* __restrict__ logp, const T* __restrict__ a,
                  int a_mode, const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
                  const T* __restrict__ noise_in, int64_t K, int64_t M, int64_t E, int KS, uint64_t seed,
-                 uint64_t offset) {
+                 uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     const int lane = threadIdx.x % G;
     const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;  // group -> (m, k-slice)
     const int64_t E4 = E >> 2;
@@ -235,7 +244,8 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
     k_latent_fwd_packed(T* __restrict__ z, T* __restrict__ logq, T* __restrict__ logp, const T* __restrict__ a,
                         int a_mode, const T* __restrict__ b, const T* __restrict__ pa, const T* __restrict__ pb,
                         const T* __restrict__ noise_in, int K, int64_t M, int E4, int RW, int KS, uint64_t seed,
-                        uint64_t offset) {
+                        uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rl = lane / E4, j = lane - rl * E4;
     const int64_t m = ((int64_t)blockIdx.x * LF_WARPS + warp) * RW + rl;
@@ -279,19 +289,24 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: block = LB_X float4 units of [M,E] x LB_Y particle slices, fixed-order sum over slices.
-// Parameter-only terms (log std, precision, 1/std) are hoisted out of the particle loop.
+// backward: block = LB_X float4 units of [M,E] x blockDim.y particle slices, fixed-order sum over slices.
+// Parameter-only terms (precision, 1/std) are hoisted out of the particle loop and take the SFU reciprocal.
+// The kernel moves 17 MB at config 2 and was latency-bound (ncu round 1: long_scoreboard 4.35, 1.44 waves of
+// 16 x 16 blocks whose threads walked 3-4 particles two at a time): now blockDim.y = ceil(K/2) slices (25 at K = 50),
+// every thread owns two particles whose six loads are all issued before the first use, LB_X = 8 units (one 128-byte
+// line per particle row) so that 1280 CTAs spread evenly over the SMs.
 // ---------------------------------------------------------------------------------------------
-constexpr int LB_X = 16, LB_Y = 16;
+constexpr int LB_X = 8, LB_Y_MAX = 32;
 
 template <typename T, int FAM>
-__global__ void __launch_bounds__(LB_X* LB_Y, 3)
+__global__ void __launch_bounds__(LB_X* LB_Y_MAX, sizeof(T) == 4 ? 3 : 1)
     k_latent_bwd(T* __restrict__ da, T* __restrict__ db, const T* __restrict__ gq, const T* __restrict__ gp,
                  const T* __restrict__ dz_up, const T* __restrict__ z, const T* __restrict__ a, int a_mode,
                  const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
                  int reparam, int64_t K, int64_t M, int64_t E) {
     const int64_t ME4 = (M * E) >> 2;
     const int64_t u = (int64_t)blockIdx.x * LB_X + threadIdx.x;
+    const int LBY = blockDim.y;
     const bool valid = u < ME4;
     const bool full = a_mode == ZS_FULL;  // FULL parameters: per-particle gradients, no reduction
     V4<T> sa{{T(0), T(0), T(0), T(0)}}, sb{{T(0), T(0), T(0), T(0)}};
@@ -304,15 +319,15 @@ __global__ void __launch_bounds__(LB_X* LB_Y, 3)
             if (FAM == FAM_BERNOULLI) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {  // the two reciprocals of bernoulli.py:94's autograd, once per unit
-                    up.logb.v[q] = T(1) / (up.a.v[q] + T(1e-8));
-                    up.prec.v[q] = T(1) / ((T(1) - up.a.v[q]) + T(1e-8));
+                    up.logb.v[q] = lat_rcp(up.a.v[q] + T(1e-8));
+                    up.prec.v[q] = lat_rcp((T(1) - up.a.v[q]) + T(1e-8));
                 }
             }
             if (FAM == FAM_NORMAL) {
                 up.b = ldv4(b + idx);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    rstd.v[q] = T(1) / up.b.v[q];
+                    rstd.v[q] = lat_rcp(up.b.v[q]);
                     up.prec.v[q] = rstd.v[q] * rstd.v[q];  // exp(-2 log std) of normal.py:122
                 }
                 if (pa) up.pa = ldv4(pa + ke);
@@ -320,24 +335,20 @@ __global__ void __launch_bounds__(LB_X* LB_Y, 3)
                 if (pb) {
                     const V4<T> ps = ldv4(pb + ke);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) up.pprec.v[q] = T(1) / (ps.v[q] * ps.v[q]);
+                    for (int q = 0; q < 4; ++q) up.pprec.v[q] = lat_rcp(ps.v[q] * ps.v[q]);
                 } else {
                     up.pprec = V4<T>{{T(1), T(1), T(1), T(1)}};
                 }
             }
         };
-        if (!full) load_params(ke);
-        // particles k = y, y + LB_Y, ...: the loads of up to LBU of them are issued together (the kernel was
-        // latency-bound with one particle's loads in flight per thread)
-        constexpr int LBU = 2;
-        for (int64_t k0 = threadIdx.y; k0 < K; k0 += LBU * LB_Y) {
+        constexpr int LBU = 2;  // particles in flight per thread
+        for (int64_t k0 = threadIdx.y; k0 < K; k0 += (int64_t)LBU * LBY) {
             T g_q[LBU], g_p[LBU];
             V4<T> zv[LBU], du[LBU];
 #pragma unroll
             for (int i = 0; i < LBU; ++i) {
-                const int64_t k = k0 + (int64_t)i * LB_Y;
-                const bool on = k < K;
-                const int64_t kc = on ? k : k0;
+                const int64_t k = k0 + (int64_t)i * LBY;
+                const int64_t kc = k < K ? k : k0;  // always in bounds
                 const int64_t r = kc * M + m, fe = kc * (M * E) + ke;
                 g_q[i] = gq ? gq[r] : T(0);
                 g_p[i] = gp ? gp[r] : T(0);
@@ -345,9 +356,10 @@ __global__ void __launch_bounds__(LB_X* LB_Y, 3)
                 if (dz_up && reparam) du[i] = ldv4(dz_up + fe);
                 else du[i] = V4<T>{{T(0), T(0), T(0), T(0)}};
             }
+            if (!full) load_params(ke);  // loop-invariant: hoisted by the compiler, placed after the particle loads
 #pragma unroll
             for (int i = 0; i < LBU; ++i) {
-                const int64_t k = k0 + (int64_t)i * LB_Y;
+                const int64_t k = k0 + (int64_t)i * LBY;
                 if (k >= K) break;
                 const int64_t fe = k * (M * E) + ke;
                 if (full) load_params(fe);
@@ -391,47 +403,48 @@ __global__ void __launch_bounds__(LB_X* LB_Y, 3)
         }
     }
     if (full) return;
-    __shared__ T red[2][LB_Y][LB_X][4];
+    __shared__ T red[2][LB_Y_MAX][LB_X][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         red[0][threadIdx.y][threadIdx.x][q] = sa.v[q];
         red[1][threadIdx.y][threadIdx.x][q] = sb.v[q];
     }
     __syncthreads();
-    if (threadIdx.y == 0 && valid) {
-        V4<T> ta{{T(0), T(0), T(0), T(0)}}, tb{{T(0), T(0), T(0), T(0)}};
-#pragma unroll
-        for (int s = 0; s < LB_Y; ++s)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ta.v[q] += red[0][s][threadIdx.x][q];
-                tb.v[q] += red[1][s][threadIdx.x][q];
-            }
-        if (da) stv4(da + 4 * u, ta);
-        if (db && FAM == FAM_NORMAL) stv4(db + 4 * u, tb);
+    // fixed-order sum over the slices: thread (x, y < 8) adds up component (y & 3) of array (y >> 2)
+    if (threadIdx.y < 8 && valid) {
+        const int arr = threadIdx.y >> 2, q = threadIdx.y & 3;
+        T t = T(0);
+        for (int sl = 0; sl < LBY; ++sl) t += red[arr][sl][threadIdx.x][q];
+        T* dst = arr == 0 ? da : (FAM == FAM_NORMAL ? db : nullptr);
+        if (dst) dst[4 * u + q] = t;
     }
 }
 
 template <typename T, int FAM>
 static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, const T* b, int b_mode, const T* pa,
                              const T* pb, const T* noise_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                             uint64_t offset, cudaStream_t st) {
+                             uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+    if (noise_in) rs = nullptr;  // injected noise: no draw, the stream position stays
     const int64_t E4 = E >> 2;
     if (E4 <= 32 && K < ((int64_t)1 << 30)) {
         const int RW = (int)(32 / E4);
         const int64_t row_warps = (M + RW - 1) / RW;
         const int64_t gx = (row_warps + LF_WARPS - 1) / LF_WARPS;
-        // k-slices: ~24 warps per SM, then equal trip counts per slice
-        int64_t KS = ((int64_t)sm_count() * 24 + row_warps - 1) / row_warps;
-        if (KS > K) KS = K;
-        if (KS > 64) KS = 64;
+        // k-slices: two particles per thread (both Philox / Box-Muller chains in flight) until that is more than
+        // ~48 warps per SM, then equal trip counts per slice.  The parameter terms a slice recomputes are SFU ops
+        // (lat_log / lat_rcp), so small slices cost little and fill the machine: at config 2 (K = 50, M = 1024,
+        // Z = 40) 25 slices x 86 CTAs of 4 warps, against 10 slices (0.73 waves, 29 % active warps) before.
+        int64_t KS = (K + 1) / 2;
+        const int64_t cap = ((int64_t)sm_count() * 48 + row_warps - 1) / row_warps;
+        if (KS > cap) KS = cap;
+        if (KS > 65535) KS = 65535;
         if (KS < 1) KS = 1;
         const int64_t trips = (K + KS - 1) / KS;
         KS = (K + trips - 1) / trips;
         ZS_REQUIRE(gx < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
         dim3 grid((unsigned)gx, (unsigned)KS);
         k_latent_fwd_packed<T, FAM><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, (int)K, M,
-                                                                    (int)E4, RW, (int)KS, seed, offset);
+                                                                    (int)E4, RW, (int)KS, seed, offset, rs);
         ZS_LAUNCH_CHECK("k_latent_fwd_packed");
         return ZS_OK;
     }
@@ -446,7 +459,7 @@ static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, con
         const int64_t grid = (groups * G + 255) / 256;                                                            \
         ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);                                               \
         k_latent_fwd<T, FAM, G><<<(unsigned)grid, 256, 0, st>>>(z, logq, logp, a, a_mode, b, b_mode, pa, pb,      \
-                                                                noise_in, K, M, E, (int)KS, seed, offset);        \
+                                                                noise_in, K, M, E, (int)KS, seed, offset, rs);    \
     }
     if (E4 <= 4) ZS_LATENT_FWD(4)
     else if (E4 <= 8) ZS_LATENT_FWD(8)
@@ -484,7 +497,10 @@ static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp,
     const int64_t ME4 = (M * E) >> 2;
     const int64_t grid = (ME4 + LB_X - 1) / LB_X;
     ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
-    dim3 block(LB_X, LB_Y);
+    int lby = (int)((K + 1) / 2);  // two particles per thread
+    if (lby > LB_Y_MAX) lby = LB_Y_MAX;
+    if (lby < 8) lby = 8;          // the epilogue's eight (array, component) sums are taken by slices 0..7
+    dim3 block(LB_X, lby);
     k_latent_bwd<T, FAM><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
         (T*)da, (T*)db, (const T*)gq, (const T*)gp, (const T*)dz_up, (const T*)z, (const T*)a, a_mode, (const T*)b,
         b_mode, (const T*)pa, (const T*)pb, reparam, K, M, E);
@@ -500,7 +516,7 @@ extern "C" {
 
 int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* mean, int mean_mode, const void* std,
                          int std_mode, const void* prior_mean, const void* prior_std, const void* eps_in, int64_t K,
-                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                         int64_t M, int64_t E, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(z && mean && std && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
     int rc = latent_args_ok(mean, mean_mode, std, std_mode, FAM_NORMAL, E, {z, mean, std, prior_mean, prior_std, eps_in});
     if (rc != ZS_OK) return rc;
@@ -509,19 +525,20 @@ int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void*
         return launch_latent_fwd<float, FAM_NORMAL>((float*)z, (float*)logq, (float*)logp, (const float*)mean,
                                                     mean_mode, (const float*)std, std_mode, (const float*)prior_mean,
                                                     (const float*)prior_std, (const float*)eps_in, K, M, E, seed,
-                                                    offset, as_stream(stream));
+                                                    offset, (unsigned long long*)rng_state, as_stream(stream));
     if (dtype == ZS_F64)
         return launch_latent_fwd<double, FAM_NORMAL>((double*)z, (double*)logq, (double*)logp, (const double*)mean,
                                                      mean_mode, (const double*)std, std_mode,
                                                      (const double*)prior_mean, (const double*)prior_std,
-                                                     (const double*)eps_in, K, M, E, seed, offset, as_stream(stream));
+                                                     (const double*)eps_in, K, M, E, seed, offset,
+                                                     (unsigned long long*)rng_state, as_stream(stream));
     set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
     return ZS_ERR_DTYPE;
 }
 
 int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
                             const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                            uint64_t offset, zs_stream_t stream) {
+                            uint64_t offset, void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(z && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
     int rc = latent_args_ok(probs, probs_mode, nullptr, probs_mode, FAM_BERNOULLI, E, {z, probs, prior_probs, u_in});
     if (rc != ZS_OK) return rc;
@@ -530,12 +547,13 @@ int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const vo
         return launch_latent_fwd<float, FAM_BERNOULLI>((float*)z, (float*)logq, (float*)logp, (const float*)probs,
                                                        probs_mode, nullptr, probs_mode, (const float*)prior_probs,
                                                        nullptr, (const float*)u_in, K, M, E, seed, offset,
-                                                       as_stream(stream));
+                                                       (unsigned long long*)rng_state, as_stream(stream));
     if (dtype == ZS_F64)
         return launch_latent_fwd<double, FAM_BERNOULLI>((double*)z, (double*)logq, (double*)logp,
                                                         (const double*)probs, probs_mode, nullptr, probs_mode,
                                                         (const double*)prior_probs, nullptr, (const double*)u_in, K,
-                                                        M, E, seed, offset, as_stream(stream));
+                                                        M, E, seed, offset, (unsigned long long*)rng_state,
+                                                        as_stream(stream));
     set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
     return ZS_ERR_DTYPE;
 }

@@ -14,15 +14,19 @@ void set_last_error(const char* where, cudaError_t e) {
 void set_last_error_msg(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
+    // per device: a process may drive several GPUs (the value only sizes grids, so a benign race on the cache is fine)
+    static int cached[64] = {0};
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
         (void)cudaGetLastError();
-        return 148;  // B200; only used to size grids
+        return 148;  // B200
     }
-    cached = n;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
 }
 

@@ -531,7 +531,9 @@ template <typename T, bool ALIGNED4, int NOISE = NOISE_NORMAL>
 __global__ void __launch_bounds__(256) k_normal_sample(T* __restrict__ z, const T* __restrict__ mean, int mm,
                                                        const T* __restrict__ std, int sm, const T* __restrict__ eps_in,
                                                        T* __restrict__ eps_out, int64_t K, int64_t N, uint64_t seed,
-                                                       uint64_t offset) {
+                                                       uint64_t offset, unsigned long long* rs,
+                                                       unsigned long long* snap) {
+    offset = rng_acquire(offset, rs, snap, true);
     const int64_t total = K * N;
     const int64_t nq = (total + 3) / 4;
     const T ms = mm == ZS_SCALAR ? mean[0] : T(0);
@@ -562,7 +564,9 @@ template <typename T, int NOISE = NOISE_NORMAL>
 __global__ void __launch_bounds__(KR_X* KR_Y) k_normal_sample_bwd(T* __restrict__ dmean, int mm, T* __restrict__ dstd,
                                                                    int sm, const T* __restrict__ dz,
                                                                    const T* __restrict__ eps, int64_t K, int64_t N,
-                                                                   uint64_t seed, uint64_t offset) {
+                                                                   uint64_t seed, uint64_t offset,
+                                                                   unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, false);  // the forward's snapshot: read, never advanced
     const int64_t n = (int64_t)blockIdx.x * KR_X + threadIdx.x;
     const bool valid = n < N;
     T sm_acc = T(0), ss_acc = T(0);
@@ -606,7 +610,8 @@ __global__ void __launch_bounds__(KR_X* KR_Y) k_normal_sample_bwd(T* __restrict_
 template <typename T, bool ALIGNED4>
 __global__ void __launch_bounds__(256) k_bernoulli_sample(T* __restrict__ out, const T* __restrict__ probs, int pm,
                                                           const T* __restrict__ u_in, int64_t K, int64_t N,
-                                                          uint64_t seed, uint64_t offset) {
+                                                          uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     const int64_t total = K * N;
     const int64_t nq = (total + 3) / 4;
     const T ps = pm == ZS_SCALAR ? probs[0] : T(0);
@@ -630,7 +635,8 @@ __global__ void __launch_bounds__(256) k_bernoulli_sample(T* __restrict__ out, c
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_philox_fill(T* __restrict__ out, int64_t n, T mean, T std, int normal,
-                                                     uint64_t seed, uint64_t offset) {
+                                                     uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     const int64_t nq = (n + 3) / 4;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         float v4[4];
@@ -647,7 +653,8 @@ __global__ void __launch_bounds__(256) k_philox_fill(T* __restrict__ out, int64_
 }
 
 __global__ void __launch_bounds__(256) k_philox_raw(uint32_t* __restrict__ out, int64_t nq, uint64_t seed,
-                                                    uint64_t offset) {
+                                                    uint64_t offset, unsigned long long* rs) {
+    offset = rng_acquire(offset, rs, nullptr, true);
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         Philox4 r = philox4x32_10((uint64_t)q, offset, seed);
         out[4 * q + 0] = r.x;
@@ -758,6 +765,14 @@ static int dispatch_bwd(T* dx, T* da, T* db, const T* g, Operand<T> x, Operand<T
 
 using namespace zs;
 
+__global__ void k_rng_state_init(unsigned long long* st, unsigned long long offset) {
+    st[0] = offset;
+    st[1] = 0ull;
+}
+static inline unsigned long long* rs_ptr(const void* p) {
+    return reinterpret_cast<unsigned long long*>(const_cast<void*>(p));
+}
+
 #define ZS_DTYPE_SWITCH(dtype, ...)              \
     if ((dtype) == ZS_F32) {                     \
         using T = float;                         \
@@ -772,32 +787,40 @@ using namespace zs;
 
 extern "C" {
 
-int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+int zs_rng_state_init(void* rng_state, uint64_t offset, zs_stream_t stream) {
+    ZS_REQUIRE(rng_state != nullptr && (reinterpret_cast<uintptr_t>(rng_state) & 7u) == 0, ZS_ERR_ARG);
+    k_rng_state_init<<<1, 1, 0, as_stream(stream)>>>((unsigned long long*)rng_state, offset);
+    ZS_LAUNCH_CHECK("k_rng_state_init");
+    return ZS_OK;
+}
+
+int zs_philox_raw(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(out != nullptr && n >= 0 && n % 4 == 0, ZS_ERR_ARG);
     if (n == 0) return ZS_OK;
-    k_philox_raw<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(out, n / 4, seed, offset);
+    k_philox_raw<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(out, n / 4, seed, offset, rs_ptr(rng_state));
     ZS_LAUNCH_CHECK("k_philox_raw");
     return ZS_OK;
 }
 
-int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+int zs_philox_uniform(int dtype, void* out, int64_t n, uint64_t seed, uint64_t offset, void* rng_state,
+                      zs_stream_t stream) {
     ZS_REQUIRE(out != nullptr && n >= 0, ZS_ERR_ARG);
     if (n == 0) return ZS_OK;
     ZS_DTYPE_SWITCH(dtype, {
         k_philox_fill<T><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>((T*)out, n, T(0), T(1), 0, seed,
-                                                                                     offset);
+                                                                                     offset, rs_ptr(rng_state));
     })
     ZS_LAUNCH_CHECK("k_philox_fill");
     return ZS_OK;
 }
 
 int zs_philox_normal(int dtype, void* out, int64_t n, double mean, double std, uint64_t seed, uint64_t offset,
-                     zs_stream_t stream) {
+                     void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(out != nullptr && n >= 0, ZS_ERR_ARG);
     if (n == 0) return ZS_OK;
     ZS_DTYPE_SWITCH(dtype, {
         k_philox_fill<T><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>((T*)out, n, (T)mean, (T)std, 1,
-                                                                                     seed, offset);
+                                                                                     seed, offset, rs_ptr(rng_state));
     })
     ZS_LAUNCH_CHECK("k_philox_fill");
     return ZS_OK;
@@ -805,8 +828,9 @@ int zs_philox_normal(int dtype, void* out, int64_t n, double mean, double std, u
 
 int zs_normal_sample(int dtype, void* z, const void* mean, int mean_mode, const void* std, int std_mode,
                      const void* eps_in, void* eps_out, int64_t K, int64_t N, uint64_t seed, uint64_t offset,
-                     zs_stream_t stream) {
+                     void* rng_state, void* rng_snapshot, zs_stream_t stream) {
     ZS_REQUIRE(z && mean && std && K >= 0 && N >= 0, ZS_ERR_ARG);
+    if (eps_in) rng_state = rng_snapshot = nullptr;  // injected noise: no draw, the stream position stays
     ZS_REQUIRE(valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
     if (K * N == 0) return ZS_OK;
     const int grid = grid_for((K * N + 3) / 4, 256);
@@ -814,18 +838,19 @@ int zs_normal_sample(int dtype, void* z, const void* mean, int mean_mode, const 
         if (N % 4 == 0)
             k_normal_sample<T, true><<<grid, 256, 0, as_stream(stream)>>>(
                 (T*)z, (const T*)mean, mean_mode, (const T*)std, std_mode, (const T*)eps_in, (T*)eps_out, K, N, seed,
-                offset);
+                offset, rs_ptr(rng_state), rs_ptr(rng_snapshot));
         else
             k_normal_sample<T, false><<<grid, 256, 0, as_stream(stream)>>>(
                 (T*)z, (const T*)mean, mean_mode, (const T*)std, std_mode, (const T*)eps_in, (T*)eps_out, K, N, seed,
-                offset);
+                offset, rs_ptr(rng_state), rs_ptr(rng_snapshot));
     })
     ZS_LAUNCH_CHECK("k_normal_sample");
     return ZS_OK;
 }
 
 int zs_normal_sample_bwd(int dtype, void* dmean, int mean_mode, void* dstd, int std_mode, const void* dz,
-                         const void* eps, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                         const void* eps, int64_t K, int64_t N, uint64_t seed, uint64_t offset, const void* rng_state,
+                         zs_stream_t stream) {
     ZS_REQUIRE(dz && K >= 0 && N >= 0, ZS_ERR_ARG);
     ZS_REQUIRE(valid_mode(mean_mode) && valid_mode(std_mode), ZS_ERR_ARG);
     if ((dmean && mean_mode == ZS_SCALAR) || (dstd && std_mode == ZS_SCALAR)) {
@@ -838,7 +863,8 @@ int zs_normal_sample_bwd(int dtype, void* dmean, int mean_mode, void* dstd, int 
     ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
     ZS_DTYPE_SWITCH(dtype, {
         k_normal_sample_bwd<T><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
-            (T*)dmean, mean_mode, (T*)dstd, std_mode, (const T*)dz, (const T*)eps, K, N, seed, offset);
+            (T*)dmean, mean_mode, (T*)dstd, std_mode, (const T*)dz, (const T*)eps, K, N, seed, offset,
+            eps ? nullptr : rs_ptr(rng_state));
     })
     ZS_LAUNCH_CHECK("k_normal_sample_bwd");
     return ZS_OK;
@@ -869,17 +895,20 @@ int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const vo
 }
 
 int zs_bernoulli_sample(int dtype, void* out, const void* probs, int probs_mode, const void* u_in, int64_t K,
-                        int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                        int64_t N, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream) {
     ZS_REQUIRE(out && probs && K >= 0 && N >= 0 && valid_mode(probs_mode), ZS_ERR_ARG);
+    if (u_in) rng_state = nullptr;
     if (K * N == 0) return ZS_OK;
     const int grid = grid_for((K * N + 3) / 4, 256);
     ZS_DTYPE_SWITCH(dtype, {
         if (N % 4 == 0)
             k_bernoulli_sample<T, true><<<grid, 256, 0, as_stream(stream)>>>((T*)out, (const T*)probs, probs_mode,
-                                                                              (const T*)u_in, K, N, seed, offset);
+                                                                              (const T*)u_in, K, N, seed, offset,
+                                                                              rs_ptr(rng_state));
         else
             k_bernoulli_sample<T, false><<<grid, 256, 0, as_stream(stream)>>>((T*)out, (const T*)probs, probs_mode,
-                                                                               (const T*)u_in, K, N, seed, offset);
+                                                                               (const T*)u_in, K, N, seed, offset,
+                                                                               rs_ptr(rng_state));
     })
     ZS_LAUNCH_CHECK("k_bernoulli_sample");
     return ZS_OK;
@@ -911,8 +940,10 @@ int zs_bernoulli_logpmf_bwd(int dtype, void* dx, void* dprobs, const void* g, co
 
 /* ---- location-scale families beyond Normal ------------------------------------------------ */
 int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_mode, const void* scale, int scale_mode,
-                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                       const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, void* rng_state,
+                       void* rng_snapshot, zs_stream_t stream) {
     ZS_REQUIRE(z && loc && scale && K >= 0 && N >= 0, ZS_ERR_ARG);
+    if (u_in) rng_state = rng_snapshot = nullptr;
     ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
     ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
     if (K * N == 0) return ZS_OK;
@@ -920,17 +951,20 @@ int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             k_normal_sample<T, false, NOISE_LOGISTIC><<<grid, 256, 0, as_stream(stream)>>>(
-                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset);
+                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset,
+                rs_ptr(rng_state), rs_ptr(rng_snapshot));
         else
             k_normal_sample<T, false, NOISE_LAPLACE><<<grid, 256, 0, as_stream(stream)>>>(
-                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset);
+                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset,
+                rs_ptr(rng_state), rs_ptr(rng_snapshot));
     })
     ZS_LAUNCH_CHECK("k_normal_sample<locscale>");
     return ZS_OK;
 }
 
 int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void* dscale, int scale_mode, const void* dz,
-                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset, zs_stream_t stream) {
+                           const void* u, int64_t K, int64_t N, uint64_t seed, uint64_t offset, const void* rng_state,
+                           zs_stream_t stream) {
     ZS_REQUIRE(dz && K >= 0 && N >= 0, ZS_ERR_ARG);
     ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
     ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
@@ -945,10 +979,12 @@ int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             k_normal_sample_bwd<T, NOISE_LOGISTIC><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
-                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset);
+                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset,
+                u ? nullptr : rs_ptr(rng_state));
         else
             k_normal_sample_bwd<T, NOISE_LAPLACE><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
-                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset);
+                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset,
+                u ? nullptr : rs_ptr(rng_state));
     })
     ZS_LAUNCH_CHECK("k_normal_sample_bwd<locscale>");
     return ZS_OK;

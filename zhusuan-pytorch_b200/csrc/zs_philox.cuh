@@ -39,6 +39,44 @@ __host__ __device__ __forceinline__ float u01_open(uint32_t r) {
 }
 
 #ifdef __CUDACC__
+// ---- graph-safe stream position ------------------------------------------------------------------------------
+// A sampling launch whose (seed, offset) are passed by value draws the same noise every time a captured CUDA graph
+// replays it.  With a device-side state (zs_rng_state in include/zs_b200.h: {uint64 offset; uint32 arrivals; uint32
+// reserved}) the launch reads its stream position from device memory and advances it for the next launch:
+//   - every CTA's leader reads state->offset, THEN (after a fence) counts itself in state->arrivals;
+//   - the CTA that arrives last therefore knows every other CTA has already read the offset: it resets the
+//     arrival count and stores offset + ZS_RNG_TICK.  Nothing waits on anything, so grids larger than the machine
+//     (or persistent kernels) are fine; the next launch on the stream sees the advanced offset.
+// `advance == false` only reads (the backward of a sample regenerates the forward's noise from a snapshot).
+// `snapshot` (may be null) receives the position this launch used.  Must be called by ALL threads of the CTA (it
+// contains a __syncthreads) before the first draw; returns by-value offset + device offset.
+constexpr unsigned long long ZS_RNG_TICK_DEV = 4ull;  // == ZS_RNG_TICK
+
+__device__ __forceinline__ uint64_t rng_acquire(uint64_t offset, unsigned long long* state, unsigned long long* snapshot,
+                                                bool advance) {
+    if (state == nullptr) return offset;  // uniform over the grid
+    __shared__ unsigned long long s_rng_base;
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        const unsigned long long base = *reinterpret_cast<volatile unsigned long long*>(state);
+        s_rng_base = base;
+        if (snapshot != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            snapshot[0] = base + offset;
+            snapshot[1] = 0ull;
+        }
+        if (advance) {
+            __threadfence();
+            unsigned int* arrivals = reinterpret_cast<unsigned int*>(state + 1);
+            const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(arrivals, 1u) == total - 1u) {
+                *reinterpret_cast<volatile unsigned int*>(arrivals) = 0u;
+                *reinterpret_cast<volatile unsigned long long*>(state) = base + ZS_RNG_TICK_DEV;
+            }
+        }
+    }
+    __syncthreads();
+    return offset + s_rng_base;
+}
+
 // Box-Muller on two words -> two standard normals.  The radius uses logf (the SFU lg2 has an absolute
 // error that matters when u1 is within ~1e-6 of 1); the angle uses the SFU sin/cos on (-pi, pi)
 // (abs error 2^-21): the sampling kernels are instruction-bound on the noise and sincospif alone was

@@ -8,11 +8,14 @@ Responsibilities (all host logic, no math):
   * move CPU tensors to the current CUDA device and results back to the caller's device (the
     reference's tests feed CPU tensors); there is no CPU implementation to fall back to.
 """
+import weakref
+
 import torch
 from ._shapes import broadcast_shapes as _bshapes
 
 from . import _backend as be
 from . import _rng
+from ._lazy import LazyDraw, lazy_first_draws, lazy_active  # noqa: F401  (re-exported)
 
 FULL, KBCAST, SCALAR = be.FULL, be.KBCAST, be.SCALAR
 
@@ -51,11 +54,14 @@ class upload_memo(object):
 def to_compute(t):
     """Differentiable move to the CUDA device the kernels run on.  A CPU tensor that this package
     itself produced (see back_home) still has its device original attached: reuse it instead of
-    uploading the bytes again."""
+    uploading the bytes again -- unless the CPU tensor takes part in autograd itself (a user may ask for the gradient
+    w.r.t. it, or hook it): then the op must stay connected to the CPU tensor."""
+    if isinstance(t, LazyDraw):
+        t = t._zs_materialize()
     if t.is_cuda:
         return t
     twin = getattr(t, "_zs_twin", None)
-    if twin is not None and twin[1] == t._version:
+    if twin is not None and twin[1] == t._version and not t.requires_grad:
         return twin[0]
     memo = _upload_memo[0]
     if memo is None:
@@ -69,31 +75,33 @@ def to_compute(t):
     return d
 
 
-# Pinned host buffers are slow to allocate (torch.empty(pin_memory=True) ~0.3 ms, cudaHostAlloc of the
-# 160 MB gradient tens of ms), so they are pooled: a buffer is reused once the tensor handed out for it
-# last time is dead (weak reference); while it is alive another buffer is used.
+# Pinned host buffers are slow to allocate (cudaHostAlloc of the 160 MB gradient takes tens of ms), so they are
+# pooled.  A buffer is handed out again only when NOTHING else uses its storage: the pool's own tensor is then the
+# storage's single owner (use count 2 = that tensor + the temporary storage handle of the query).  Views, detach()ed
+# aliases, autograd's saved tensors and `.grad` attributes all hold the storage, so results a caller still looks at
+# are never overwritten (a weak reference to the tensor object handed out does not see those aliases).
 _pin_pool = {}
 
 
+def _storage_in_use(buf):
+    return torch._C._storage_Use_Count(buf.untyped_storage()._cdata) > 2
+
+
 def pinned_like_pool(shape, dtype, key=None):
-    import weakref
     shape = tuple(int(v) for v in shape)
     k = (key, shape, dtype)
     entries = _pin_pool.setdefault(k, [])
-    for e in entries:
-        if e[1] is None or e[1]() is None:
-            out = e[0].view(shape)
-            e[1] = weakref.ref(out)
-            return out
+    for buf in entries:
+        if not _storage_in_use(buf):
+            return buf.view(shape)
     buf = torch.empty(shape, dtype=dtype, pin_memory=True)
-    out = buf.view(shape)
-    entries.append([buf, weakref.ref(out)])
-    return out
+    entries.append(buf)
+    return buf.view(shape)
 
 
 class _ToHostPinned(torch.autograd.Function):
-    """Device -> host copy through pinned memory (torch's caching host allocator), ~10x the rate of a
-    copy into pageable memory; the gradient goes back with a plain upload."""
+    """Device -> host copy through pinned memory, ~10x the rate of a copy into pageable memory; the gradient goes
+    back with a plain upload."""
 
     @staticmethod
     def forward(ctx, t):
@@ -109,6 +117,21 @@ class _ToHostPinned(torch.autograd.Function):
 
 
 _keep_on_device = [0]
+
+# data-parallel runs: the number of batch columns of the GLOBAL batch (zhusuan.distributed.global_batch), or None
+_global_batch = [None]
+
+
+def _mean_scale(B):
+    """1 / (columns the mean objective averages over): the local batch, or the global batch of a data-parallel step
+    (each rank then returns its additive share of the global mean and of its gradient)."""
+    n = _global_batch[0]
+    return 1.0 / float(n if n else B)
+
+
+def _mean_cost(cost, B):
+    n = _global_batch[0]
+    return cost.mean() if not n else cost.sum() * (1.0 / float(n))
 
 
 class device_results(object):
@@ -204,25 +227,37 @@ def normal_log_prob(x, mean, std, n_event):
     return back_home(out.reshape(L.lead), home)
 
 
+def _draw_kwargs(dev, injected, want_snapshot=False):
+    """(kwargs of the sampling launch, kwargs of a backward that regenerates its noise)."""
+    if injected is not None:
+        return dict(seed=0, offset=0), dict(seed=0, offset=0)
+    kw = _rng.draw_args(dev)
+    if kw.get("rng_state") is None:
+        return kw, dict(seed=kw["seed"], offset=kw["offset"])
+    if not want_snapshot:
+        return kw, None
+    snap = _rng.snapshot_buffer(dev)
+    kw = dict(kw, rng_snapshot=snap)
+    # the snapshot holds the absolute position the forward used: the backward adds nothing to it
+    return kw, dict(seed=kw["seed"], offset=0, rng_state=snap)
+
+
 class _NormalSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mean, std, modes, K, N, eps_in):
-        if eps_in is not None:
-            seed, offset = 0, 0
-        else:
-            seed, offset = _rng.next_philox(mean.device)
-        z = be.normal_sample(mean, modes[0], std, modes[1], K, N, eps_in=eps_in, seed=seed, offset=offset)
+        fwd_kw, bwd_kw = _draw_kwargs(mean.device, eps_in, want_snapshot=True)
+        z = be.normal_sample(mean, modes[0], std, modes[1], K, N, eps_in=eps_in, **fwd_kw)
         ctx.save_for_backward(mean, std, eps_in)
-        ctx.cfg = (modes, K, N, seed, offset)
+        ctx.cfg = (modes, K, N, bwd_kw)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         mean, std, eps = ctx.saved_tensors
-        modes, K, N, seed, offset = ctx.cfg
+        modes, K, N, bwd_kw = ctx.cfg
         nm, ns = ctx.needs_input_grad[:2]
-        dmean, dstd = be.normal_sample_bwd(dz.contiguous(), mean, modes[0], std, modes[1], K, N, eps=eps, seed=seed,
-                                           offset=offset, need_mean=nm, need_std=ns)
+        dmean, dstd = be.normal_sample_bwd(dz.contiguous(), mean, modes[0], std, modes[1], K, N, eps=eps,
+                                           need_mean=nm, need_std=ns, **bwd_kw)
         return dmean, dstd, None, None, None, None
 
 
@@ -244,8 +279,7 @@ def normal_sample(mean, std, n_samples, reparameterized):
     if not fits or N == 0:
         # std broadcasts the mean (e.g. mean [1,3], std [2,1]): rare, composed from a noise draw
         if eps_in is None:
-            seed, offset = _rng.next_philox(mean.device)
-            eps_in = be.philox_normal(K * N, mean.dtype, 0.0, 1.0, seed, offset, mean.device)
+            eps_in = be.philox_normal(K * N, mean.dtype, 0.0, 1.0, device=mean.device, **_rng.draw_args(mean.device))
         eps = eps_in.reshape(out_shape)
         z = (mean.unsqueeze(0) + std.unsqueeze(0) * eps) if K > 1 else (mean + std * eps)
         z = z if reparameterized else z.detach()
@@ -268,55 +302,115 @@ def normal_sample(mean, std, n_samples, reparameterized):
 # Latent nodes: sample AND log q(sample) from one launch (zs_*_latent_fwd), joint backward (zs_*_latent_bwd)
 # --------------------------------------------------------------------------------------------
 class _NormalLatent(torch.autograd.Function):
-    """(mean, std) -> (z [K,M,E], log q(z) [K,M]).  backward receives the gradients reaching z (decoder, prior node)
-    and log q and returns d/dmean, d/dstd from ONE launch: the density terms, the pathwise term through
-    z = mean + std*eps when reparameterised (eps recovered from the sample), summed over particles."""
+    """(mean, std) -> (z [K,M,E], log q(z) [K,M], log N(z; 0, 1) [K,M]).  The third output is the log-density of the
+    sample under the STANDARD Normal prior, produced by the same launch because it costs two FMAs per element there
+    and a launch plus a pass over z anywhere else; a generator whose prior node is a standard Normal picks it up
+    (std_prior_logp), any other prior ignores it.  backward receives the gradients reaching z (decoder, a non-standard
+    prior node), log q and the standard-prior term and returns d/dmean, d/dstd from ONE launch: the density terms,
+    the pathwise term through z = mean + std*eps when reparameterised (eps recovered from the sample), summed over
+    particles."""
 
     @staticmethod
     def forward(ctx, mean, std, mode, K, M, E, eps_in, reparameterized):
-        seed, offset = (0, 0) if eps_in is not None else _rng.next_philox(mean.device)
-        r = be.normal_latent_fwd(mean, std, mode, K, M, E, eps_in=eps_in, want_logp=False, seed=seed, offset=offset)
+        fwd_kw, _ = _draw_kwargs(mean.device, eps_in)
+        r = be.normal_latent_fwd(mean, std, mode, K, M, E, eps_in=eps_in, want_logp=True, **fwd_kw)
         if r is None:
             raise be.BackendError("latent kernel refused a shape latent_supported() accepted")
-        z, logq, _ = r
+        z, logq, logp = r
         ctx.save_for_backward(z, mean, std)
         ctx.cfg = (mode, K, M, E, reparameterized)
         if not reparameterized:
             ctx.mark_non_differentiable(z)
-        return z, logq
+        return z, logq, logp
 
     @staticmethod
-    def backward(ctx, dz, dlogq):
+    def backward(ctx, dz, dlogq, dlogp):
         z, mean, std = ctx.saved_tensors
         mode, K, M, E, reparam = ctx.cfg
         dz = dz.contiguous() if (dz is not None and reparam) else None
         dlogq = None if dlogq is None else dlogq.contiguous()
-        dmean, dstd = be.normal_latent_bwd(dlogq, None, dz, z, mean, std, mode, K, M, E, reparameterized=reparam)
+        # the prior term depends on the parameters only through the sample
+        dlogp = dlogp.contiguous() if (dlogp is not None and reparam) else None
+        dmean, dstd = be.normal_latent_bwd(dlogq, dlogp, dz, z, mean, std, mode, K, M, E, reparameterized=reparam)
         return dmean, dstd, None, None, None, None, None, None
 
 
 class _BernoulliLatent(torch.autograd.Function):
-    """probs -> (z, log q(z)); samples carry no gradient, log q's gradient reaches probs in one launch."""
+    """probs -> (z, log q(z), log Bernoulli(z; 0.5)); samples carry no gradient, log q's gradient reaches probs in
+    one launch (the prior term is constant in probs)."""
 
     @staticmethod
     def forward(ctx, probs, mode, K, M, E, u_in):
-        seed, offset = (0, 0) if u_in is not None else _rng.next_philox(probs.device)
-        r = be.bernoulli_latent_fwd(probs, mode, K, M, E, u_in=u_in, want_logp=False, seed=seed, offset=offset)
+        fwd_kw, _ = _draw_kwargs(probs.device, u_in)
+        r = be.bernoulli_latent_fwd(probs, mode, K, M, E, u_in=u_in, want_logp=True, **fwd_kw)
         if r is None:
             raise be.BackendError("latent kernel refused a shape latent_supported() accepted")
-        z, logq, _ = r
+        z, logq, logp = r
         ctx.save_for_backward(z, probs)
         ctx.cfg = (mode, K, M, E)
-        ctx.mark_non_differentiable(z)
-        return z, logq
+        ctx.mark_non_differentiable(z, logp)
+        return z, logq, logp
 
     @staticmethod
-    def backward(ctx, dz, dlogq):
+    def backward(ctx, dz, dlogq, dlogp):
         z, probs = ctx.saved_tensors
         mode, K, M, E = ctx.cfg
         if dlogq is None:
             return torch.zeros_like(probs), None, None, None, None, None
         return be.bernoulli_latent_bwd(dlogq.contiguous(), z, probs, mode, K, M, E), None, None, None, None, None
+
+
+# log-density of a fused draw under the standard prior of its family, keyed by the identity of the sample tensor the
+# caller holds: {id(z): (weakref(z), family, n_event, logp)}.  Entries die with the sample.
+_std_logp = {}
+
+
+def _remember_std_logp(z, family, n_event, logp):
+    key = id(z)
+
+    def _gone(_ref, key=key):
+        _std_logp.pop(key, None)
+
+    _std_logp[key] = (weakref.ref(z, _gone), family, n_event, logp)
+
+
+def std_prior_logp(given, family, n_event):
+    """log p(given) under the family's standard prior (Normal(0, 1) / Bernoulli(0.5)) summed over the last n_event
+    axes, if `given` is a sample whose fused draw already produced it; else None."""
+    e = _std_logp.get(id(given))
+    if e is None or e[0]() is not given or e[1] != family or e[2] != n_event:
+        return None
+    return e[3]
+
+
+# "is this prior parameter tensor all equal to c?" without synchronising the hot path: Python numbers are known,
+# host tensors are checked on the host, CUDA tensors are checked ONCE per tensor object and version (one
+# synchronisation at first sight, never during stream capture).
+_const_memo = {}
+
+
+def is_constant(t, c):
+    if not torch.is_tensor(t):
+        return float(t) == c
+    if t.numel() == 0 or t.requires_grad:
+        return False
+    if not t.is_cuda:
+        return bool((t == c).all())
+    key = (id(t), float(c))
+    hit = _const_memo.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    val = bool((t == c).all())
+    if len(_const_memo) > 256:
+        _const_memo.clear()
+
+    def _gone(_ref, key=key):
+        _const_memo.pop(key, None)
+
+    _const_memo[key] = (weakref.ref(t, _gone), t._version, val)
+    return val
 
 
 def _aligned(t):
@@ -352,8 +446,10 @@ def normal_sample_logq(mean, std, n_samples, reparameterized, n_event):
         eps_in = to_compute(eps_in).to(mean.dtype).reshape(K, M, E).contiguous()
     mode = KBCAST if K > 1 else FULL
     mc, sc = _aligned(mean.reshape(M, E)), _aligned(std.reshape(M, E))
-    z, logq = _NormalLatent.apply(mc, sc, mode, K, M, E, eps_in, bool(reparameterized))
-    return back_home(z.reshape(out_shape), home), logq.reshape(lead)
+    z, logq, logp = _NormalLatent.apply(mc, sc, mode, K, M, E, eps_in, bool(reparameterized))
+    z = back_home(z.reshape(out_shape), home)
+    _remember_std_logp(z, "normal", n_event, logp.reshape(lead))
+    return z, logq.reshape(lead)
 
 
 def bernoulli_sample_logq(probs, n_samples, n_event):
@@ -369,8 +465,10 @@ def bernoulli_sample_logq(probs, n_samples, n_event):
     if u_in is not None:
         u_in = to_compute(u_in).to(probs.dtype).reshape(K, M, E).contiguous()
     mode = KBCAST if K > 1 else FULL
-    z, logq = _BernoulliLatent.apply(_aligned(probs.reshape(M, E)), mode, K, M, E, u_in)
-    return back_home(z.reshape(out_shape), home), logq.reshape(lead)
+    z, logq, logp = _BernoulliLatent.apply(_aligned(probs.reshape(M, E)), mode, K, M, E, u_in)
+    z = back_home(z.reshape(out_shape), home)
+    _remember_std_logp(z, "bernoulli", n_event, logp.reshape(lead))
+    return z, logq.reshape(lead)
 
 
 # --------------------------------------------------------------------------------------------
@@ -409,19 +507,19 @@ def locscale_log_prob(family, x, loc, scale, n_event):
 class _LocScaleSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, loc, scale, family, modes, K, N, u_in):
-        seed, offset = (0, 0) if u_in is not None else _rng.next_philox(loc.device)
-        z = be.locscale_sample(family, loc, modes[0], scale, modes[1], K, N, u_in=u_in, seed=seed, offset=offset)
+        fwd_kw, bwd_kw = _draw_kwargs(loc.device, u_in, want_snapshot=True)
+        z = be.locscale_sample(family, loc, modes[0], scale, modes[1], K, N, u_in=u_in, **fwd_kw)
         ctx.save_for_backward(loc, scale, u_in)
-        ctx.cfg = (family, modes, K, N, seed, offset)
+        ctx.cfg = (family, modes, K, N, bwd_kw)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         loc, scale, u = ctx.saved_tensors
-        family, modes, K, N, seed, offset = ctx.cfg
+        family, modes, K, N, bwd_kw = ctx.cfg
         nl, ns = ctx.needs_input_grad[:2]
         dloc, dscale = be.locscale_sample_bwd(family, dz.contiguous(), loc, modes[0], scale, modes[1], K, N, u=u,
-                                              seed=seed, offset=offset, need_loc=nl, need_scale=ns)
+                                              need_loc=nl, need_scale=ns, **bwd_kw)
         return dloc, dscale, None, None, None, None, None
 
 
@@ -497,13 +595,10 @@ def bernoulli_sample(probs, n_samples):
     if N == 0:
         return back_home(torch.zeros(out_shape, dtype=probs.dtype, device=probs.device), home)
     u_in = _rng.take_injected("uniform")
-    seed = offset = 0
     if u_in is not None:
         u_in = to_compute(u_in).to(probs.dtype).reshape(K, N).contiguous()
-    else:
-        seed, offset = _rng.next_philox(probs.device)
-    out = be.bernoulli_sample(probs.contiguous(), KBCAST if K > 1 else FULL, K, N, u_in=u_in, seed=seed,
-                              offset=offset)
+    kw, _ = _draw_kwargs(probs.device, u_in)
+    out = be.bernoulli_sample(probs.contiguous(), KBCAST if K > 1 else FULL, K, N, u_in=u_in, **kw)
     return back_home(out.reshape(out_shape), home)
 
 
@@ -557,12 +652,10 @@ def categorical_sample(logits, n_samples):
     if M == 0:
         return back_home(torch.zeros(out_shape, dtype=logits.dtype, device=logits.device), home)
     u_in = _rng.take_injected("uniform")
-    seed = offset = 0
     if u_in is not None:
         u_in = to_compute(u_in).to(logits.dtype).reshape(K, M).contiguous()
-    else:
-        seed, offset = _rng.next_philox(logits.device)
-    out = be.categorical_sample(logits, KBCAST if K > 1 else FULL, K, M, C, u_in=u_in, seed=seed, offset=offset)
+    kw, _ = _draw_kwargs(logits.device, u_in)
+    out = be.categorical_sample(logits, KBCAST if K > 1 else FULL, K, M, C, u_in=u_in, **kw)
     return back_home(out.reshape(out_shape), home)
 
 
@@ -577,10 +670,10 @@ class _IWObjective(torch.autograd.Function):
     def forward(ctx, logp, logq, estimator, reduce_mean):
         K, B = logp.shape
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        cost, dlp, dlq = be.iw_objective(estimator, logp, logq, (1.0 / B) if reduce_mean else 1.0, need_grads=need)
+        cost, dlp, dlq = be.iw_objective(estimator, logp, logq, _mean_scale(B) if reduce_mean else 1.0, need_grads=need)
         ctx.save_for_backward(dlp, dlq)
         ctx.reduce_mean = reduce_mean
-        return cost.mean() if reduce_mean else cost
+        return _mean_cost(cost, B) if reduce_mean else cost
 
     @staticmethod
     def backward(ctx, g):
@@ -675,12 +768,12 @@ class _IWBernoulliFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probs, x, logp_other, logq, estimator, logits=False):
         K, B, X = probs.shape
-        r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, 1.0 / B,
+        r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, _mean_scale(B),
                                   need_dprobs=ctx.needs_input_grad[0], logits=logits)
         if r is None:
             raise be.BackendError("fused IW kernel refused a shape fused_supported() accepted")
         ctx.grads = (r["dprobs"], r["dlogp"], r["dlogq"])
-        return r["cost"].mean()
+        return _mean_cost(r["cost"], B)
 
     @staticmethod
     def backward(ctx, g):
@@ -701,8 +794,8 @@ class _IWBernoulliFused(torch.autograd.Function):
 def iw_bernoulli_fused(probs, x, logp_other, logq, estimator, logits=False):
     """probs [K,B,X] (CUDA, float32; logits when `logits=True`), x [B,X], logp_other / logq [K,B] or None
     -> scalar loss."""
-    probs = probs.contiguous()
-    x = x.to(probs.dtype).contiguous()
+    probs = _aligned(probs)
+    x = _aligned(x.to(probs.dtype))
     lo = None if logp_other is None else logp_other.contiguous()
     lq = None if logq is None else logq.contiguous()
     return _IWBernoulliFused.apply(probs, x, lo, lq, estimator, bool(logits))
@@ -726,28 +819,45 @@ def _workspace(nbytes):
     return ws
 
 
+def _host_step_handle(dev):
+    """One zs_host_step handle per (thread's) compute device: the library keeps no global state for these calls."""
+    key = ("hs", dev.index)
+    hs = _host_pool.get(key)
+    if hs is None:
+        hs = be.HostStep(dev)
+        _host_pool[key] = hs
+    return hs
+
+
 class _IWBernoulliFusedHost(torch.autograd.Function):
     """The fused likelihood + objective step for HOST-resident probs / x: zs_iw_step_host_begin pipelines
     H2D copies, the fused kernel and D2H copies over column chunks.  The [K,B] log-weight terms and their
     gradients stay on the device (they come from / go to the latent nodes' kernels); forward returns as soon
     as the per-column costs have landed, while the tail of dprobs is still on its way to pinned host memory.
-    backward hands that buffer to autograd as the gradient of the CPU leaf and queues an end-of-backward
-    callback that waits for the last copy, so the latent nodes' backward overlaps the transfer."""
+
+    backward must hand autograd a gradient that HAS landed whenever anything may read it during the backward pass:
+    a CPU decoder upstream of `probs` (its backward nodes run on the CPU thread right away), or an existing
+    `probs.grad` (AccumulateGrad adds into it).  Only when `probs` is a leaf without a gradient -- AccumulateGrad
+    then just stores the tensor -- the wait is deferred to an end-of-backward callback so the latent nodes'
+    backward overlaps the transfer (`defer_ok`, decided by the caller who sees the real tensor)."""
 
     @staticmethod
-    def forward(ctx, probs, x, logp_other, logq, estimator):
+    def forward(ctx, probs, x, logp_other, logq, estimator, defer_ok):
         K, B, X = probs.shape
         dev = compute_device()
+        hs = _host_step_handle(dev)
         cost = _pinned((B,), "cost")
         dprobs = _pinned((K, B, X), "dprobs") if ctx.needs_input_grad[0] else None
         dlp = torch.empty((K, B), dtype=torch.float32, device=dev)
         dlq = torch.empty((K, B), dtype=torch.float32, device=dev)
         ws = _workspace(be.iw_step_host_workspace(K, B, X))
-        be.iw_step_host_begin(estimator, cost, dprobs, dlp, dlq, probs, x, logp_other, logq, K, B, X, 1.0 / B, ws,
-                              True)
-        be.iw_step_host_wait(0)
+        be.iw_step_host_begin(hs, estimator, cost, dprobs, dlp, dlq, probs, x, logp_other, logq, K, B, X,
+                              _mean_scale(B), ws, True)
+        be.iw_step_host_wait(hs, 0)
         ctx.grads = (dprobs, dlp, dlq)
-        return cost.mean()
+        ctx.hs = hs
+        ctx.defer_ok = bool(defer_ok)
+        return _mean_cost(cost, B)
 
     @staticmethod
     def backward(ctx, g):
@@ -756,21 +866,19 @@ class _IWBernoulliFusedHost(torch.autograd.Function):
                                "back-propagated once; set zhusuan.variational.FUSED = False for retain_graph")
         dprobs, dlp, dlq = ctx.grads
         ctx.grads = None
+        hs = ctx.hs
         gv = float(g)
         if dprobs is not None:
-            if gv != 1.0:
-                be.iw_step_host_wait(1)
-                dprobs = dprobs * gv
+            if gv != 1.0 or not ctx.defer_ok:
+                be.iw_step_host_wait(hs, 1)
+                if gv != 1.0:
+                    dprobs = dprobs * gv
             else:
                 # dprobs may still be landing: the engine runs this after the whole backward pass, before
                 # loss.backward() / autograd.grad() return to the caller
-                torch.autograd.Variable._execution_engine.queue_callback(_host_step_landed)
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: be.iw_step_host_wait(hs, 1))
         return (dprobs, None, dlp * gv if ctx.needs_input_grad[2] else None,
-                dlq * gv if ctx.needs_input_grad[3] else None, None)
-
-
-def _host_step_landed():
-    be.iw_step_host_wait(1)
+                dlq * gv if ctx.needs_input_grad[3] else None, None, None)
 
 
 def iw_bernoulli_fused_host(probs, x, logp_other, logq, estimator):
@@ -778,5 +886,7 @@ def iw_bernoulli_fused_host(probs, x, logp_other, logq, estimator):
     [K,B] tensors (any device; moved to the compute device) or None -> scalar CPU loss."""
     be.require_cuda()
     f = lambda t: None if t is None else to_compute(t).to(torch.float32).contiguous()
+    # the deferred wait is only safe when autograd will merely STORE the gradient (see the class docstring)
+    defer_ok = probs.is_leaf and probs.grad is None and probs.is_contiguous()
     return _IWBernoulliFusedHost.apply(probs.contiguous(), x.to(torch.float32).contiguous(), f(logp_other), f(logq),
-                                       estimator)
+                                       estimator, defer_ok)

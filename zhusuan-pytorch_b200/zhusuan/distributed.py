@@ -1,14 +1,28 @@
-"""Data-parallel helpers for the hot path (one process per GPU, torch.distributed).
+"""Data-parallel helpers for the hot path (one process per GPU, torch.distributed over NCCL / NVLink).
 
 The path shards naturally: batch columns (VAE / IWAE / VIMCO / BNN-VI) or chains
 (SG-MCMC) are split over ranks, every particle-axis reduction stays inside a rank, and the only
-exchange is a sum of the scalar objective (plus the usual parameter-gradient all-reduce of the user's
-networks).  The reference has no distributed code at all; nothing here changes its API.
+exchange is a SUM of the scalar objective and of the replicated networks' parameter gradients.
+The reference has no distributed code at all; nothing here changes its API.
+
+How a data-parallel step is put together:
+
+    bucket = zd.GradientBucket([decoder.parameters(), encoder.parameters()])   # once
+    with zd.global_batch(B_global):            # kernels scale by 1/B_global: every rank's loss and gradients are
+        loss = objective({"x": x_local})       #   its additive share of the GLOBAL mean -- no rescaling pass
+        loss.backward()                        # gradients accumulate straight into the bucket's flat buffer;
+    bucket.finish(loss)                        #   each segment's all-reduce is launched (async, NCCL stream) as soon
+                                               #   as its last gradient is written, i.e. it overlaps the rest of backward
+    loss_global = bucket.loss()                # one SUM all-reduce per segment, no torch.cat, no copy-back
+
+`all_reduce_gradients` keeps the round-1 call signature on top of the same machinery.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
-from . import _rng
+from . import _ops, _rng
 
 # Philox offsets of different ranks are separated by this many ticks so their noise never overlaps
 RANK_OFFSET_STRIDE = 1 << 40
@@ -41,6 +55,20 @@ def decorrelate_rng(rank=None):
     _rng.rank_stride = (r if rank is None else rank) * RANK_OFFSET_STRIDE
 
 
+@contextlib.contextmanager
+def global_batch(n_global):
+    """Inside the block the objectives average over `n_global` batch columns instead of the local batch: the
+    kernels' grad_scale becomes 1/n_global (zs_iw_objective / zs_iw_bernoulli_fused take it as an argument), the
+    returned loss is this rank's share sum_b cost_b / n_global.  SUM-all-reducing losses and gradients over ranks
+    then gives the global-batch mean and its gradient with no rescaling pass over any gradient."""
+    prev = _ops._global_batch[0]
+    _ops._global_batch[0] = int(n_global)
+    try:
+        yield
+    finally:
+        _ops._global_batch[0] = prev
+
+
 def global_mean_objective(local_mean_loss, n_local, n_global, group=None, async_op=False):
     """Mean objective over the GLOBAL batch from each rank's mean over its local columns:
     sum_r (loss_r * n_r) / n_global.  One all-reduce of a single scalar."""
@@ -51,21 +79,127 @@ def global_mean_objective(local_mean_loss, n_local, n_global, group=None, async_
     return (t.reshape(()), work) if async_op else t.reshape(())
 
 
-def all_reduce_gradients(params, n_local, n_global, group=None):
-    """Turn gradients of the LOCAL mean loss into gradients of the GLOBAL mean loss:
-    g <- sum_r g_r * n_r / n_global, flattened into one all-reduce."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+class GradientBucket(object):
+    """Persistent flat gradient buffer of the replicated networks, all-reduced in place.
+
+    `param_groups`: an iterable of parameter iterables, in the order their gradients become ready during backward
+    (for a VAE: decoder first, encoder second).  Each group is one contiguous SEGMENT of the flat buffer; the last
+    segment carries one extra slot for the scalar objective.  Every parameter's `.grad` is a view into the buffer, so
+    autograd accumulates into it directly: there is no flatten (`torch.cat`) before the collective and no copy back
+    after it.  A post-accumulate hook on each parameter counts the segment down and launches its all-reduce
+    (async: NCCL's own stream, ordered after the compute stream at that point) when the segment is complete, so
+    the collective of the decoder's gradients overlaps the latent nodes' and the encoder's backward.
+    Without torch.distributed (or with world size 1) everything degenerates to local no-ops.
+    """
+
+    def __init__(self, param_groups, device=None, dtype=None, group=None):
+        groups = [[p for p in g if p.requires_grad] for g in param_groups]
+        groups = [g for g in groups if g]
+        self.params = [p for g in groups for p in g]
+        first = self.params[0] if self.params else None
+        self.device = device if device is not None else (first.device if first is not None else torch.device("cpu"))
+        self.dtype = dtype if dtype is not None else (first.dtype if first is not None else torch.float32)
+        self.group = group
+        sizes = [sum(p.numel() for p in g) for g in groups] or [0]
+        sizes[-1] += 1  # the objective's slot
+        self.flat = torch.zeros(sum(sizes), dtype=self.dtype, device=self.device)
+        self.segments = []
+        off = 0
+        for n in sizes:
+            self.segments.append(self.flat[off:off + n])
+            off += n
+        self._views, self._seg_of, self._pending, self._works = {}, {}, [], []
+        off = 0
+        for si, g in enumerate(groups):
+            for p in g:
+                v = self.flat[off:off + p.numel()].view_as(p)
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+                self._views[id(p)] = v
+                self._seg_of[id(p)] = si
+                off += p.numel()
+                if hasattr(p, "register_post_accumulate_grad_hook"):
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+        self._sizes = [len(g) for g in groups] or [0]
+        self.zero_grad()
+
+    # -- per step ---------------------------------------------------------------------------------
+    def zero_grad(self):
+        """Zero every gradient (one memset of the flat buffer) and re-arm the segment counters.  Use this instead
+        of optimizer.zero_grad(set_to_none=True), which would detach the parameters from the buffer."""
+        self.flat.zero_()
+        self._pending = list(self._sizes)
+        self._works = []
+
+    @property
+    def loss_slot(self):
+        return self.flat[-1:]
+
+    def _on_grad(self, p):
+        v = self._views.get(id(p))
+        if v is None:
+            return
+        if p.grad is not v:  # someone replaced .grad (set_to_none): fold it back into the buffer
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.add_(p.grad)
+            p.grad = v
+        si = self._seg_of[id(p)]
+        self._pending[si] -= 1
+        if self._pending[si] == 0 and si < len(self.segments) - 1:
+            self._launch(si)
+
+    def _launch(self, si):
+        if is_initialized() and dist.get_world_size(self.group) > 1:
+            self._works.append(dist.all_reduce(self.segments[si], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce_segment(self, si):
+        """Launch segment `si`'s all-reduce now (for loops that write gradients without autograd hooks)."""
+        self._launch(si)
+
+    def finish(self, loss=None):
+        """Store this rank's share of the objective in its slot, launch the last segment's all-reduce and make the
+        current stream wait for every collective of the step."""
+        if loss is not None:
+            self.loss_slot.copy_(loss.detach().reshape(1))
+        self._launch(len(self.segments) - 1)
+        for w in self._works:
+            w.wait()  # stream-level wait: the host does not block
+        self._works = []
+
+    def loss(self):
+        """The all-reduced objective (valid after finish())."""
+        return self.flat[-1]
+
+
+_legacy_buckets = {}
+
+
+def all_reduce_gradients(params, n_local=None, n_global=None, group=None):
+    """Turn gradients of the LOCAL mean loss into gradients of the GLOBAL mean loss: g <- sum_r g_r * n_r / n_global.
+    Kept for callers that do not use `global_batch` + `GradientBucket` directly: the gradients are moved into a
+    persistent flat buffer on first use (one copy, once), scaled in place by n_local / n_global (skip the scale by
+    computing the loss under `global_batch`: pass n_local=None) and SUM-all-reduced with ONE collective; `.grad`
+    stays a view of the buffer, so nothing is copied back."""
+    params = [p for p in params if p.grad is not None]
+    if not params:
         return
-    scale = float(n_local) / float(n_global)
-    if not is_initialized():
-        for g in grads:
-            g.mul_(scale)
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads]) * scale
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].reshape(g.shape))
-        off += n
+    key = tuple(id(p) for p in params)
+    b = _legacy_buckets.get(key)
+    if b is None:
+        grads = [p.grad for p in params]
+        b = GradientBucket([params], group=group)
+        for p, g in zip(params, grads):  # the constructor zeroed the buffer after adopting the gradients
+            p.grad.copy_(g)
+        _legacy_buckets.clear()
+        _legacy_buckets[key] = b
+    else:
+        for p in params:
+            v = b._views[id(p)]
+            if p.grad is not v:
+                v.copy_(p.grad)
+                p.grad = v
+    if n_local is not None and n_global is not None and float(n_local) != float(n_global):
+        b.flat.mul_(float(n_local) / float(n_global))
+    if is_initialized():
+        dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=group)

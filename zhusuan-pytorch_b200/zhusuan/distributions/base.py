@@ -112,6 +112,11 @@ class Distribution(object):
         self._logq_cache = (z, n_event, logq)
         return z
 
+    def sample_device(self):
+        """Device a sample of this distribution is returned on.  Distributions that support a deferred first draw
+        (StochasticTensor.first_draw) override this; the default opts out."""
+        raise NotImplementedError()
+
     def cached_log_prob(self, given, n_event):
         c = self._logq_cache
         if c is not None and c[0] is given and c[1] == n_event:

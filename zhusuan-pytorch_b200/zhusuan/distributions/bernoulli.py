@@ -11,6 +11,7 @@ ends in a Linear layer (no nn.Sigmoid) saves one read + one write of the [K,B,X]
 """
 import torch
 
+from zhusuan._shapes import broadcast_shapes as _bshapes
 from zhusuan.distributions.base import Distribution, DEFAULT_DEVICE, resolve_device
 from zhusuan.distributions.utils import assert_same_log_float_dtype
 from zhusuan import _ops
@@ -27,6 +28,7 @@ class Bernoulli(Distribution):
         if (logits is None) == (probs is None):
             raise ValueError("Either `probs` or `logits` should be passed. It is not allowed "
                              "that both are specified or both are not.")
+        self._ctor_probs = probs  # as given: lets _is_half() decide on the host
         if logits is None:
             self._probs = torch.as_tensor(probs, dtype=dtype).to(device)
             self._logits_cache = None  # log(p/(1-p)) is built lazily: nothing on the hot path reads it
@@ -63,6 +65,9 @@ class Bernoulli(Distribution):
     def _batch_shape(self):
         return (self._from_logits if self._probs is None else self._probs).shape
 
+    def sample_device(self):
+        return (self._from_logits if self._probs is None else self._probs).device
+
     def _sample(self, n_samples=1, **kwargs):
         s = _ops.bernoulli_sample(self.probs, n_samples)
         self.sample_cache = s
@@ -75,7 +80,16 @@ class Bernoulli(Distribution):
             return None
         return _ops.bernoulli_sample_logq(self._probs, n_samples, n_event)
 
+    def _is_half(self):
+        """True when this is Bernoulli(0.5) in every element, known without a device synchronisation."""
+        return self._ctor_probs is not None and _ops.is_constant(self._ctor_probs, 0.5)
+
     def _log_prob_event(self, given, n_event):
+        given = self._given(given)
+        lp = _ops.std_prior_logp(given, "bernoulli", n_event)  # see Normal._log_prob_event
+        if (lp is not None and lp.dtype == self._dtype and self._is_half()
+                and tuple(_bshapes(tuple(given.shape), tuple(self._batch_shape()))) == tuple(given.shape)):
+            return lp
         if self._from_logits is not None:
             return _ops.bernoulli_log_prob(self._given(given), self._from_logits, n_event, logits=True)
         return _ops.bernoulli_log_prob(self._given(given), self._probs, n_event)

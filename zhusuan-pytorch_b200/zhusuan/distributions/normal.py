@@ -20,6 +20,7 @@ class Normal(Distribution):
     def __init__(self, mean=0., std=None, logstd=None, dtype=None, is_continuous=True, is_reparameterized=True,
                  group_ndims=0, device=DEFAULT_DEVICE, **kwargs):
         device = resolve_device(device, mean, std, logstd)
+        self._ctor_args = (mean, std, logstd)  # as given: lets _is_standard() decide on the host
         self._mean = torch.as_tensor(mean, dtype=dtype).to(device)
         if (logstd is None) == (std is None):
             raise ValueError("Either `std` or `logstd` should be passed. It is not allowed "
@@ -50,6 +51,9 @@ class Normal(Distribution):
     def _batch_shape(self):
         return _bshapes(self._mean.shape, self._std.shape)
 
+    def sample_device(self):
+        return self._mean.device
+
     def _sample(self, n_samples=1):
         z = _ops.normal_sample(self._mean, self._std, n_samples, self.is_reparameterized)
         self.sample_cache = z
@@ -60,8 +64,23 @@ class Normal(Distribution):
             return None
         return _ops.normal_sample_logq(self._mean, self._std, n_samples, self.is_reparameterized, n_event)
 
+    def _is_standard(self):
+        """True when this is Normal(0, 1) in every element and that is known WITHOUT synchronising with the device
+        (Python numbers, host tensors, or CUDA tensors already checked once): _ops.is_constant."""
+        mean, std, logstd = self._ctor_args
+        if not _ops.is_constant(mean, 0.0):
+            return False
+        return _ops.is_constant(logstd, 0.0) if std is None else _ops.is_constant(std, 1.0)
+
     def _log_prob_event(self, given, n_event):
-        return _ops.normal_log_prob(self._given(given), self._mean, self._std, n_event)
+        given = self._given(given)
+        # a sample drawn by a fused latent launch carries its standard-Normal log-density: a standard prior node
+        # (the generator's p(z) in the VAE / IWAE examples, iwae.py:60-72) needs no launch of its own
+        lp = _ops.std_prior_logp(given, "normal", n_event)
+        if (lp is not None and lp.dtype == self._dtype and self._is_standard()
+                and tuple(_bshapes(tuple(given.shape), tuple(self._batch_shape()))) == tuple(given.shape)):
+            return lp
+        return _ops.normal_log_prob(given, self._mean, self._std, n_event)
 
     def _log_prob(self, sample=None):
         return _ops.normal_log_prob(self._given(sample), self._mean, self._std, 0)

@@ -68,7 +68,7 @@ class BayesianNet(nn.Module):
         if not isinstance(name, str):
             raise ValueError("name of stochastic_node must be str")
         self._nodes[name] = StochasticTensor(self, name, distribution, n_samples=n_samples, **kwargs)
-        return self._nodes[name].tensor
+        return self._nodes[name].first_draw()
 
     def stochastic_node(self, distribution, name, n_samples=None, **kwargs):
         """Add node `name` following `distribution` (a registered name or a Distribution instance)

@@ -81,6 +81,37 @@ class StochasticTensor(object):
             return dist.sample(n_samples=K)
         return dist.sample_for_node(K, n_event)
 
+    def first_draw(self):
+        """The value `stochastic_node` hands to the user's `forward` (reference framework/bn.py:158): the observation,
+        or draw #1.  Inside `_ops.lazy_first_draws()` (the objectives and samplers, which read `.tensor` again and
+        use THAT draw) an unobserved node returns a LazyDraw -- the sampling launch runs only if `forward` actually
+        uses the value (zhusuan/_lazy.py).  Injected noise keeps draws eager so it is consumed in reference order."""
+        from zhusuan import _ops, _rng
+        value = self._observed_value()
+        if value is not None or not _ops.lazy_active() or _rng.has_injected():
+            return self.tensor
+        dist = self._dist
+        K = self._n_samples
+        try:
+            shape = (((int(K),) if K is not None and int(K) > 1 else ()) + tuple(dist.batch_shape))
+            device = dist.sample_device()
+        except Exception:
+            return self.tensor
+        lazy = _ops.LazyDraw(self._materialize_lazy, shape, dist.dtype, device)
+        dist.sample_cache = lazy
+        dist._logq_cache = None
+        return lazy
+
+    def _materialize_lazy(self, lazy):
+        """Run the deferred draw #1.  A newer draw / observation that has become the distribution's current value in
+        the meantime stays current (`log_prob(None)` must keep evaluating at it)."""
+        dist = self._dist
+        current = (dist.sample_cache, dist._logq_cache)
+        z = self._draw()
+        if current[0] is not lazy:
+            dist.sample_cache, dist._logq_cache = current
+        return z
+
     def sample(self, force=False):
         value = None if force else self._observed_value()
         if value is not None:

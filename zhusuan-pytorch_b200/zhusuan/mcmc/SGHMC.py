@@ -1,7 +1,8 @@
 """SGHMC (Chen et al. 2014), first order and second order (symmetric splitting) — drop-in for
 zhusuan/mcmc/SGHMC.py.
 
-Per chain-state tensor an update is at most two kernels around the gradient evaluation:
+An update is at most two launches around the gradient evaluation, each covering EVERY chain-state tensor
+(zs_sgmcmc_multi_step):
   pre : optional velocity resample v ~ N(0, lr) and, for second order, the half step w += v/2
   post: v = (1-alpha) v + lr g + n ; w += v                      (first order,  reference :46-50)
         v = d (d v + lr g + n), d = exp(-alpha/2) ; w += v/2      (second order, reference :51-56)
@@ -37,34 +38,29 @@ class SGHMC(SGMCMC):
     def _draw_velocity(self, like):
         v = self._noise(like)
         if v is None:
-            seed, offset = _rng.next_philox(like.device)
-            v = _be.philox_normal(like.numel(), like.dtype, 0.0, math.sqrt(self.lr), seed, offset,
-                                  like.device).reshape(like.shape)
+            v = _be.philox_normal(like.numel(), like.dtype, 0.0, math.sqrt(self.lr), device=like.device,
+                                  **_rng.draw_args(like.device)).reshape(like.shape)
         return v
 
     def _update(self, bn, observed):
-        states = [_ops.to_compute(q.detach()).contiguous() for q in self._var_list]
         homes = [q.device for q in self._var_list]
+        states = [self._on_device(q) for q in self._var_list]
         if not self.vs:
-            self.vs = [self._draw_velocity(w) for w in states]
+            self.vs = [self._draw_velocity(w) for w in states]  # velocities live on the compute device
         resample = self.n_iter_resample_v != 0 and self.t % self.n_iter_resample_v == 0
-        gaussian = []
-        for i, w in enumerate(states):
-            # draw order per variable follows the reference: velocity resample first, then the term
-            v_noise = self._noise(w) if resample else None
-            seed, offset = (0, 0) if (v_noise is not None or not resample) else _rng.next_philox(w.device)
-            half = _be.sghmc_pre(w, self.vs[i], self.lr, resample, self.second_order, v_noise=v_noise, seed=seed,
-                                 offset=offset)
+        # injected noise, per variable in the reference's draw order: resampled velocity first, then the Gaussian term
+        v_noise, gaussian = [], []
+        for w in states:
+            v_noise.append(self._noise(w) if resample else None)
             gaussian.append(self._noise(w))
+        if resample or self.second_order:
+            states = self._multi_step(_be.ALG_SGHMC_PRE, states, None, self.vs, v_noise, lr=self.lr,
+                                      resample=resample, second_order=self.second_order)
             if self.second_order:
-                states[i] = half
-                self._var_list[i] = self._leaf(half, homes[i])
+                self._var_list = [self._leaf(w, h) for w, h in zip(states, homes)]
+                states = [self._on_device(q) for q in self._var_list]
         grad = self._gradients(bn, observed)
-        for i, g in enumerate(grad):
-            w = states[i]
-            gd = _ops.to_compute(g.detach()).to(w.dtype).contiguous()
-            n = gaussian[i]
-            seed, offset = (0, 0) if n is not None else _rng.next_philox(w.device)
-            new = _be.sghmc_post(w, self.vs[i], gd, self.lr, self.alpha, self.beta, self.second_order, noise=n,
-                                 seed=seed, offset=offset)
-            self._var_list[i] = self._leaf(new, homes[i])
+        gs = [self._on_device(g, w.dtype) for g, w in zip(grad, states)]
+        new = self._multi_step(_be.ALG_SGHMC_POST, states, gs, self.vs, gaussian, lr=self.lr, a=self.alpha,
+                               b=self.beta, second_order=self.second_order)
+        self._var_list = [self._leaf(w, h) for w, h in zip(new, homes)]

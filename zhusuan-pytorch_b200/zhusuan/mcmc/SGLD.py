@@ -1,8 +1,9 @@
 """SGLD and preconditioned SGLD (drop-in for zhusuan/mcmc/SGLD.py).
 
-Each chain-state tensor is updated by ONE kernel that reads w and the gradient, draws the Gaussian
-term from Philox in registers and writes the new state (12 B per element for SGLD).  The reference
-draws the noise on the CPU, copies it to the device and runs 3 elementwise kernels (:50-52).
+ALL chain-state tensors of the net are updated by ONE launch (zs_sgmcmc_multi_step) that reads w and the
+gradient, draws the Gaussian term from Philox in registers and writes the new state (12 B per element for SGLD).
+The reference loops over the latents in Python and, per tensor, draws the noise on the CPU, copies it to the device
+and runs 3 elementwise kernels (:49-54).
 """
 import math
 
@@ -35,16 +36,12 @@ class SGLD(SGMCMC):
 
     def _update(self, bn, observed):
         grad = self._gradients(bn, observed)
-        lr = float(self.lr)
-        for i, g in enumerate(grad):
-            w = self._var_list[i]
-            home = w.device
-            wd = _ops.to_compute(w.detach()).contiguous()
-            gd = _ops.to_compute(g.detach()).to(wd.dtype).contiguous()
-            noise = self._noise(wd)
-            seed, offset = (0, 0) if noise is not None else _rng.next_philox(wd.device)
-            new = _be.sgld_step(wd, gd, lr, noise=noise, seed=seed, offset=offset)
-            self._var_list[i] = self._leaf(new, home)
+        homes = [w.device for w in self._var_list]
+        ws = [self._on_device(w) for w in self._var_list]
+        gs = [self._on_device(g, w.dtype) for g, w in zip(grad, ws)]
+        noises = [self._noise(w) for w in ws]  # injected Gaussian terms (parity tests), in variable order
+        new = self._multi_step(_be.ALG_SGLD, ws, gs, None, noises, lr=float(self.lr))
+        self._var_list = [self._leaf(w, h) for w, h in zip(new, homes)]
 
 
 class PSGLD(SGLD):
@@ -59,17 +56,12 @@ class PSGLD(SGLD):
         self.epsilon = epsilon
 
     def _update(self, bn, observed):
+        homes = [w.device for w in self._var_list]
+        ws = [self._on_device(w) for w in self._var_list]
         if not self.aux:
-            self.aux = [torch.zeros_like(_ops.to_compute(q.detach())) for q in self._var_list]
+            self.aux = [torch.zeros_like(w) for w in ws]  # running second moments, kept on the compute device
         grad = self._gradients(bn, observed)
-        lr = float(self.lr)
-        for i, g in enumerate(grad):
-            w = self._var_list[i]
-            home = w.device
-            wd = _ops.to_compute(w.detach()).contiguous()
-            gd = _ops.to_compute(g.detach()).to(wd.dtype).contiguous()
-            unit = self._noise(wd)
-            seed, offset = (0, 0) if unit is not None else _rng.next_philox(wd.device)
-            new = _be.psgld_step(wd, self.aux[i], gd, lr, self.decay, self.epsilon, noise_unit=unit, seed=seed,
-                                 offset=offset)
-            self._var_list[i] = self._leaf(new, home)
+        gs = [self._on_device(g, w.dtype) for g, w in zip(grad, ws)]
+        units = [self._noise(w) for w in ws]
+        new = self._multi_step(_be.ALG_PSGLD, ws, gs, self.aux, units, lr=float(self.lr), a=self.decay, b=self.epsilon)
+        self._var_list = [self._leaf(w, h) for w, h in zip(new, homes)]

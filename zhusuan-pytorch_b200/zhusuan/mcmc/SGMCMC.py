@@ -43,10 +43,41 @@ class SGMCMC(nn.Module):
         t.requires_grad = True
         return t
 
+    @staticmethod
+    def _on_device(t, dtype=None):
+        """The chain-state / gradient tensor as the kernels read it: as is when it already is a contiguous CUDA
+        tensor (the usual case: no per-tensor detach / copy), otherwise moved / made contiguous."""
+        if isinstance(t, _ops.LazyDraw):
+            t = t._zs_materialize()
+        if t.is_cuda and t.is_contiguous() and (dtype is None or t.dtype == dtype):
+            return t.detach() if t.requires_grad else t
+        t = _ops.to_compute(t.detach())
+        return (t if dtype is None else t.to(dtype)).contiguous()
+
+    def _multi_step(self, algorithm, ws, gs=None, states=None, noises=None, **coef):
+        """One launch over every chain-state tensor (zs_sgmcmc_multi_step); tensors of different dtypes (rare) go in
+        one launch per dtype.  Returns the updated states in the order of `ws`."""
+        from zhusuan import _backend as _be
+        n = len(ws)
+        out = [None] * n
+        groups = {}
+        for i, w in enumerate(ws):
+            groups.setdefault((w.dtype, w.device), []).append(i)
+        for (_, dev), idx in groups.items():
+            pick = lambda lst: None if lst is None else [lst[i] for i in idx]
+            nz = pick(noises)
+            injected = nz is not None and all(v is not None for v in nz)
+            kw = dict(seed=0, offset=0) if injected else _rng.draw_args(dev)
+            res = _be.sgmcmc_multi_step(algorithm, pick(ws), pick(gs), pick(states), nz, None, **coef, **kw)
+            for i, r in zip(idx, res):
+                out[i] = r
+        return out
+
     def forward(self, bn, observed, resample=False, step=1):
         if resample:
             self.t = 0
-            bn.forward(observed)
+            with _ops.lazy_first_draws():  # the states are the `.tensor` reads below, not stochastic_node's returns
+                bn.forward(observed)
             self.t += 1
             self._latent = {k: v.tensor for k, v in bn.nodes.items() if k not in observed.keys()}
             self._latent_k = self._latent.keys()

@@ -46,7 +46,8 @@ class ELBO(nn.Module):
             return self._forward(observed, reduce_mean, **kwargs)
 
     def _forward(self, observed, reduce_mean=True, **kwargs):
-        self.variational(observed)
+        with _ops.lazy_first_draws():  # draw #1 is materialised only if the variational net's forward uses it
+            self.variational(observed)
         nodes_q = self.variational.nodes
         log_det = None
         latents = {}

@@ -136,7 +136,10 @@ class ImportanceWeightedObjective(nn.Module):
             return self._forward(observed, reduce_mean)
 
     def _forward(self, observed, reduce_mean=True):
-        self.variational(observed)
+        # draw #1 of every latent (what stochastic_node returns to the variational net's forward) is deferred until
+        # that forward uses it; the draw both nets see is the `.tensor` read below, as in the reference (:85)
+        with _ops.lazy_first_draws():
+            self.variational(observed)
         nodes_q = self.variational.nodes
         latents = {}
         for k, v in nodes_q.items():
