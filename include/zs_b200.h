@@ -224,9 +224,11 @@ int zs_categorical_logpmf_bwd(int dtype, void* dlogits, const void* g, const voi
 int zs_iw_objective(int dtype, int estimator, void* cost, void* dlogp, void* dlogq, const void* logp,
                     const void* logq, const void* logp_extra, int64_t K, int64_t B, double grad_scale,
                     zs_stream_t stream);
-/* buf[n] *= *scale_dev, a no-op launch when *scale_dev == 1: applies the upstream gradient of the
- * scalar loss to gradients the fused kernels computed for a unit upstream gradient.          */
-int zs_scale_inplace(int dtype, void* buf, int64_t n, const void* scale_dev, zs_stream_t stream);
+/* buf_i[n_i] *= *scale_dev for up to three buffers (buf1 / buf2 may be NULL), a no-op launch when *scale_dev == 1:
+ * applies the upstream gradient of the scalar loss to the gradients the fused kernels computed for a unit upstream
+ * gradient (dprobs, dlogp, dlogq) without a host synchronisation and, in the usual case, without touching them. */
+int zs_scale_inplace(int dtype, void* buf0, int64_t n0, void* buf1, int64_t n1, void* buf2, int64_t n2,
+                     const void* scale_dev, zs_stream_t stream);
 /* ELBO.reinforce (zhusuan/variational/elbo.py:163-238), the form the examples use: variance reduction with the
  * moving-mean baseline, no user baseline, mean over all N = prod(shape) elements.  One launch of one 8-CTA
  * thread-block cluster: bc = mean(logp - logq); the float32 state is updated IN PLACE on the device exactly as the

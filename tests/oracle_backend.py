@@ -209,9 +209,11 @@ def reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=True):
             _t(dlq, logq) if need_grads else None)
 
 
-def scale_inplace(buf, scale_dev):
+def scale_inplace(buf, scale_dev, buf1=None, buf2=None):
     if float(scale_dev) != 1.0:
-        buf.mul_(scale_dev)
+        for b in (buf, buf1, buf2):
+            if b is not None:
+                b.mul_(scale_dev)
 
 
 def philox_normal(n, dtype, mean, std, seed, offset, device, rng_state=None):

@@ -178,6 +178,46 @@ struct BernoulliLogitsOp<double> {
 };
 
 // ---------------------------------------------------------------------------
+// A SCALAR (or absent) second parameter is the same for every element of the launch: whatever the op derives from it
+// alone is computed once per thread, not once per element.  For the Normal op that is log(std), exp(-2 log std) and
+// 1/std -- the BNN likelihood of bnn_vi.py:55-60 (mean [K, batch], ONE logstd) otherwise spends three transcendentals
+// per element on a constant and is issue-bound at 0.3-0.4 of the HBM roofline (profiles/r1_bnn_kernels.json).
+// Same expressions in the same order as Op::term / Op::grad, so results are bit-identical.
+// ---------------------------------------------------------------------------
+template <typename T, typename Op>
+struct ScalarB {
+    T b;
+    __device__ __forceinline__ explicit ScalarB(T b_) : b(b_) {}
+    __device__ __forceinline__ T term(T x, T a) const { return Op::term(x, a, b); }
+    template <bool NEED_X>
+    __device__ __forceinline__ void grad(T g, T x, T a, T& dx, T& da, T& db) const {
+        Op::template grad<NEED_X>(g, x, a, b, dx, da, db);
+    }
+};
+template <typename T>
+struct ScalarB<T, NormalOp<T>> {
+    T std, logstd, prec;
+    __device__ __forceinline__ explicit ScalarB(T b_) : std(b_) {
+        logstd = Real<T>::log(b_);
+        prec = Real<T>::exp(T(-2) * logstd);
+    }
+    __device__ __forceinline__ T term(T x, T mean) const {
+        T d = x - mean;
+        return (NormalOp<T>::c() - logstd) - (T(0.5) * prec) * (d * d);
+    }
+    template <bool NEED_X>
+    __device__ __forceinline__ void grad(T g, T x, T mean, T& dx, T& dmean, T& dstd) const {
+        T d = x - mean;
+        T dd = -(g * (T(0.5) * prec)) * (T(2) * d);
+        dx = dd;
+        dmean = -dd;
+        T dprec = -(g * (d * d)) * T(0.5);
+        T dlogstd = -g + (dprec * prec) * T(-2);
+        dstd = dlogstd / std;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // forward: out[r] = finish( sum_e term(x, a, b) ),  LPR lanes cooperate on a row
 // ---------------------------------------------------------------------------
 template <typename T, typename Op, int LPR, bool VEC>
@@ -192,6 +232,8 @@ __global__ void __launch_bounds__(256) k_rows_fwd(T* __restrict__ out, Operand<T
     const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
     const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
     const bool hasb = b.p != nullptr;
+    const bool bsc = !hasb || b.mode == ZS_SCALAR;
+    const ScalarB<T, Op> sb(bs);
 
     for (int64_t base = 0; base < R; base += ngrp) {
         const int64_t r = base + grp;
@@ -223,23 +265,21 @@ __global__ void __launch_bounds__(256) k_rows_fwd(T* __restrict__ out, Operand<T
                     } else {
                         pa = ld_pack(ar + v * VN);
                     }
-                    if (!hasb || b.mode == ZS_SCALAR) {
+                    if (bsc) {
 #pragma unroll
-                        for (int j = 0; j < VN; ++j) pb.v[j] = bs;
-                    } else if (b.mode == ZS_FULL) {
-                        pb = ld_pack_stream(br + v * VN);
+                        for (int j = 0; j < VN; ++j) acc += sb.term(px.v[j], pa.v[j]);
                     } else {
-                        pb = ld_pack(br + v * VN);
-                    }
+                        pb = b.mode == ZS_FULL ? ld_pack_stream(br + v * VN) : ld_pack(br + v * VN);
 #pragma unroll
-                    for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+                        for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+                    }
                 }
             } else {
                 for (int64_t e = lane; e < E; e += LPR) {
                     T xv = x.mode == ZS_SCALAR ? xs : xr[e];
                     T av = a.mode == ZS_SCALAR ? as : ar[e];
-                    T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
-                    acc += Op::term(xv, av, bv);
+                    if (bsc) acc += sb.term(xv, av);
+                    else acc += Op::term(xv, av, br[e]);
                 }
             }
         }
@@ -284,6 +324,8 @@ __global__ void __cluster_dims__(ROWC, 1, 1) __launch_bounds__(256)
     const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
     const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
     const bool hasb = b.p != nullptr;
+    const bool bsc = !hasb || b.mode == ZS_SCALAR;
+    const ScalarB<T, Op> sb(bs);
     // contiguous segment of this CTA, a multiple of the pack width
     const int64_t per = ((E + (int64_t)ROWC * VN - 1) / ((int64_t)ROWC * VN)) * VN;
     const int64_t lo = (int64_t)rank * per, hi = lo + per < E ? lo + per : E;
@@ -309,21 +351,21 @@ __global__ void __cluster_dims__(ROWC, 1, 1) __launch_bounds__(256)
                 } else {
                     pa = a.mode == ZS_FULL ? ld_pack_stream(ar + e) : ld_pack(ar + e);
                 }
-                if (!hasb || b.mode == ZS_SCALAR) {
+                if (bsc) {
 #pragma unroll
-                    for (int j = 0; j < VN; ++j) pb.v[j] = bs;
+                    for (int j = 0; j < VN; ++j) acc += sb.term(px.v[j], pa.v[j]);
                 } else {
                     pb = b.mode == ZS_FULL ? ld_pack_stream(br + e) : ld_pack(br + e);
-                }
 #pragma unroll
-                for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+                    for (int j = 0; j < VN; ++j) acc += Op::term(px.v[j], pa.v[j], pb.v[j]);
+                }
             }
         } else {
             for (int64_t e = lo + threadIdx.x; e < hi; e += 256) {
                 const T xv = x.mode == ZS_SCALAR ? xs : xr[e];
                 const T av = a.mode == ZS_SCALAR ? as : ar[e];
-                const T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
-                acc += Op::term(xv, av, bv);
+                if (bsc) acc += sb.term(xv, av);
+                else acc += Op::term(xv, av, br[e]);
             }
         }
         acc = warp_sum(acc);
@@ -361,6 +403,8 @@ __global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restr
     const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
     const T bs = (b.p != nullptr && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
     const bool hasb = b.p != nullptr;
+    const bool bsc = !hasb || b.mode == ZS_SCALAR;
+    const ScalarB<T, Op> sb(bs);
 
     for (int64_t r = grp; r < R; r += ngrp) {
         const int64_t m = r % M;
@@ -392,20 +436,21 @@ __global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restr
                 } else {
                     pa = ld_pack(ar + v * VN);
                 }
-                if (!hasb || b.mode == ZS_SCALAR) {
+                if (bsc) {
 #pragma unroll
-                    for (int j = 0; j < VN; ++j) pb.v[j] = bs;
-                } else if (b.mode == ZS_FULL) {
-                    pb = ld_pack_stream(br + v * VN);
+                    for (int j = 0; j < VN; ++j) {
+                        if (dx) sb.template grad<true>(gv, px.v[j], pa.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                        else sb.template grad<false>(gv, px.v[j], pa.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                    }
                 } else {
-                    pb = ld_pack(br + v * VN);
-                }
+                    pb = b.mode == ZS_FULL ? ld_pack_stream(br + v * VN) : ld_pack(br + v * VN);
 #pragma unroll
-                for (int j = 0; j < VN; ++j) {
-                    if (dx)
-                        Op::template grad<true>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
-                    else
-                        Op::template grad<false>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                    for (int j = 0; j < VN; ++j) {
+                        if (dx)
+                            Op::template grad<true>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                        else
+                            Op::template grad<false>(gv, px.v[j], pa.v[j], pb.v[j], ox.v[j], oa.v[j], ob.v[j]);
+                    }
                 }
                 if (dxr) st_pack_stream(dxr + v * VN, ox);
                 if (dar) st_pack_stream(dar + v * VN, oa);
@@ -415,12 +460,17 @@ __global__ void __launch_bounds__(256) k_rows_bwd(T* __restrict__ dx, T* __restr
             for (int64_t e = lane; e < E; e += LPR) {
                 T xv = x.mode == ZS_SCALAR ? xs : xr[e];
                 T av = a.mode == ZS_SCALAR ? as : ar[e];
-                T bv = (!hasb || b.mode == ZS_SCALAR) ? bs : br[e];
                 T ox, oa, ob;
-                if (dx)
-                    Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
-                else
-                    Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+                if (bsc) {
+                    if (dx) sb.template grad<true>(gv, xv, av, ox, oa, ob);
+                    else sb.template grad<false>(gv, xv, av, ox, oa, ob);
+                } else {
+                    const T bv = br[e];
+                    if (dx)
+                        Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
+                    else
+                        Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+                }
                 if (dxr) dxr[e] = ox;
                 if (dar) dar[e] = oa;
                 if (dbr) dbr[e] = ob;
@@ -449,18 +499,25 @@ __global__ void __launch_bounds__(KR_X* KR_Y) k_kreduce_bwd(T* __restrict__ dx, 
         const T xs = x.mode == ZS_SCALAR ? x.p[0] : T(0);
         const T as = a.mode == ZS_SCALAR ? a.p[0] : T(0);
         const T bs = (hasb && b.mode == ZS_SCALAR) ? b.p[0] : T(0);
+        const bool bsc = !hasb || b.mode == ZS_SCALAR;
+        const ScalarB<T, Op> sbp(bs);
 #pragma unroll 4
         for (int64_t k = threadIdx.y; k < K; k += KR_Y) {
             const int64_t f = k * ME + n;
             T gv = g[k * M + m];
             T xv = x.mode == ZS_FULL ? x.p[f] : (x.mode == ZS_KBCAST ? x.p[n] : xs);
             T av = a.mode == ZS_FULL ? a.p[f] : (a.mode == ZS_KBCAST ? a.p[n] : as);
-            T bv = !hasb ? T(0) : (b.mode == ZS_FULL ? b.p[f] : (b.mode == ZS_KBCAST ? b.p[n] : bs));
             T ox, oa, ob;
-            if (dx)
-                Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
-            else
-                Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+            if (bsc) {
+                if (dx) sbp.template grad<true>(gv, xv, av, ox, oa, ob);
+                else sbp.template grad<false>(gv, xv, av, ox, oa, ob);
+            } else {
+                const T bv = b.mode == ZS_FULL ? b.p[f] : b.p[n];
+                if (dx)
+                    Op::template grad<true>(gv, xv, av, bv, ox, oa, ob);
+                else
+                    Op::template grad<false>(gv, xv, av, bv, ox, oa, ob);
+            }
             if (dx) {
                 if (x.mode == ZS_FULL) dx[f] = ox; else sx += ox;
             }

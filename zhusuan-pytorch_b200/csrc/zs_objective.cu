@@ -205,9 +205,8 @@ __global__ void __launch_bounds__(OBJ_THREADS)
 // forward+backward kernel hand out gradients computed for a unit upstream gradient without a host
 // sync and without a second pass over them.
 template <typename T>
-__global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ buf, int64_t n, const T* __restrict__ scale) {
-    const T s = *scale;
-    if (s == T(1)) return;
+__device__ __forceinline__ void scale_buffer(T* __restrict__ buf, int64_t n, T s) {
+    if (buf == nullptr) return;
     constexpr int VN = Pack<T>::N;
     const int64_t nv = n / VN;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -218,6 +217,16 @@ __global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ buf, int6
         st_pack(buf + v * VN, p);
     }
     for (int64_t i = nv * VN + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= s;
+}
+// up to three buffers (the fused objective's dprobs, dlogp, dlogq) in one launch
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ b0, int64_t n0, T* __restrict__ b1, int64_t n1,
+                                                       T* __restrict__ b2, int64_t n2, const T* __restrict__ scale) {
+    const T s = *scale;
+    if (s == T(1)) return;
+    scale_buffer(b0, n0, s);
+    scale_buffer(b1, n1, s);
+    scale_buffer(b2, n2, s);
 }
 
 static void column_geometry(int64_t B, int& cols, int& slices) {
@@ -395,15 +404,21 @@ static int lme_launch(int dtype, bool bwd, void* out, const void* g, const void*
     return ZS_OK;
 }
 
-int zs_scale_inplace(int dtype, void* buf, int64_t n, const void* scale_dev, zs_stream_t stream) {
-    ZS_REQUIRE(buf && scale_dev && n >= 0, ZS_ERR_ARG);
-    ZS_REQUIRE(aligned16(buf), ZS_ERR_ALIGN);
+int zs_scale_inplace(int dtype, void* buf0, int64_t n0, void* buf1, int64_t n1, void* buf2, int64_t n2,
+                     const void* scale_dev, zs_stream_t stream) {
+    ZS_REQUIRE(buf0 && scale_dev && n0 >= 0 && n1 >= 0 && n2 >= 0, ZS_ERR_ARG);
+    ZS_REQUIRE(aligned16(buf0) && aligned16(buf1) && aligned16(buf2), ZS_ERR_ALIGN);
+    int64_t n = n0;
+    if (buf1 && n1 > n) n = n1;
+    if (buf2 && n2 > n) n = n2;
     if (n == 0) return ZS_OK;
     const int grid = grid_for(n / 4 + 1, 256, 8);
     if (dtype == ZS_F32)
-        k_scale_inplace<float><<<grid, 256, 0, as_stream(stream)>>>((float*)buf, n, (const float*)scale_dev);
+        k_scale_inplace<float><<<grid, 256, 0, as_stream(stream)>>>((float*)buf0, n0, (float*)buf1, n1, (float*)buf2, n2,
+                                                                      (const float*)scale_dev);
     else if (dtype == ZS_F64)
-        k_scale_inplace<double><<<grid, 256, 0, as_stream(stream)>>>((double*)buf, n, (const double*)scale_dev);
+        k_scale_inplace<double><<<grid, 256, 0, as_stream(stream)>>>((double*)buf0, n0, (double*)buf1, n1, (double*)buf2,
+                                                                       n2, (const double*)scale_dev);
     else {
         set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
         return ZS_ERR_DTYPE;

@@ -74,7 +74,7 @@ def _declare(lib):
         "zs_log_mean_exp": (i32, [i32, vp, vp, i64, i64, vp]),
         "zs_log_mean_exp_bwd": (i32, [i32, vp, vp, vp, i64, i64, vp]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, i32, vp]),
-        "zs_scale_inplace": (i32, [i32, vp, i64, vp, vp]),
+        "zs_scale_inplace": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp]),
         "zs_debug_set_trace": (i32, [vp]),
         "zs_debug_set_fused_impl": (i32, [i32]),
         "zs_sgld_step": (i32, [i32, vp, vp, vp, vp, i64, dbl, u64, u64, vp, vp]),
@@ -516,11 +516,14 @@ def reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=True):
     return cost, dlp, dlq
 
 
-def scale_inplace(buf, scale_dev):
-    """buf *= scale_dev[0] on the device; the launch exits immediately when the scalar is 1."""
+def scale_inplace(buf, scale_dev, buf1=None, buf2=None):
+    """buf *= scale_dev[0] (and buf1, buf2 when given) on the device, one launch; it exits immediately when the
+    scalar is 1."""
     dt, dev = buf.dtype, buf.device
-    _chk(dev, dt, buf=buf, scale=scale_dev)
-    _go("zs_scale_inplace", dev, dtype_code(dt), _ptr(buf), buf.numel(), _ptr(scale_dev))
+    _chk(dev, dt, buf=buf, buf1=buf1, buf2=buf2, scale=scale_dev)
+    n = lambda t: 0 if t is None else t.numel()
+    _go("zs_scale_inplace", dev, dtype_code(dt), _ptr(buf), n(buf), _ptr(buf1), n(buf1), _ptr(buf2), n(buf2),
+        _ptr(scale_dev))
 
 
 # ----------------------------------------------------------------------------- SG-MCMC

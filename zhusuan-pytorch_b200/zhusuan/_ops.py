@@ -374,9 +374,14 @@ def _remember_std_logp(z, family, n_event, logp):
     _std_logp[key] = (weakref.ref(z, _gone), family, n_event, logp)
 
 
+STD_PRIOR_FOLD = True  # set False to always evaluate a prior node with its own launch
+
+
 def std_prior_logp(given, family, n_event):
     """log p(given) under the family's standard prior (Normal(0, 1) / Bernoulli(0.5)) summed over the last n_event
     axes, if `given` is a sample whose fused draw already produced it; else None."""
+    if not STD_PRIOR_FOLD:
+        return None
     e = _std_logp.get(id(given))
     if e is None or e[0]() is not given or e[1] != family or e[2] != n_event:
         return None
@@ -783,11 +788,12 @@ class _IWBernoulliFused(torch.autograd.Function):
         dprobs, dlp, dlq = ctx.grads
         ctx.grads = None
         g1 = g.reshape(1).contiguous()
+        # one launch applies the upstream scalar to all three gradient buffers (a no-op for loss.backward())
         if dprobs is not None:
-            be.scale_inplace(dprobs, g1)
-        return (dprobs, None,
-                dlp * g if ctx.needs_input_grad[2] else None,
-                dlq * g if ctx.needs_input_grad[3] else None,
+            be.scale_inplace(dprobs, g1, dlp, dlq)
+        else:
+            be.scale_inplace(dlp, g1, dlq)
+        return (dprobs, None, dlp if ctx.needs_input_grad[2] else None, dlq if ctx.needs_input_grad[3] else None,
                 None, None)
 
 
