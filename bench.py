@@ -489,28 +489,60 @@ def make_leaves(torch, vimco, device, B, seed):
     return leaves
 
 
-def capture(torch, fn, dev, use_graph=True, warm=3):
-    """Warm `fn` up and capture it into a CUDA graph; returns (callable, "cuda-graph replay" | "eager launches")."""
-    for _ in range(warm):
-        fn()
+_side_streams = {}
+
+
+def capture(torch, fn, dev, use_graph=True, warm=3, count=None):
+    """Warm `fn` up and capture it into a CUDA graph; returns (callable, "cuda-graph replay" | "eager launches",
+    launches of this package's kernels in one call of fn).
+    Everything, warm-up included, runs on ONE side stream: autograd remembers the stream on which a leaf's
+    AccumulateGrad node was created, the nets' node caches keep the previous step's graph (and with it those nodes)
+    alive, and a backward captured on another stream would have to synchronise with that stream -- which
+    invalidates the capture (torch's CUDA-graph recipe warms up on the capture stream for the same reason)."""
+    if not use_graph:  # eager by request (profiler runs): plain launches on the current stream
+        for _ in range(warm):
+            fn()
+        launches = None
+        if count is not None:
+            n0 = count()
+            fn()
+            launches = count() - n0
+        torch.cuda.synchronize()
+        return fn, "eager launches", launches
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    launches = None
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+        if count is not None:
+            n0 = count()
+            fn()
+            launches = count() - n0
+        graph, how = None, "eager launches"
+        if use_graph:
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    fn()
+                how = "cuda-graph replay"
+            except Exception as e:  # capture unsupported: fall back to eager launches, and say so
+                sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))
+                graph, how = None, "eager launches (capture failed: %s)" % (repr(e)[:120],)
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    if not use_graph:
-        return fn, "eager launches"
-    try:
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
+    if graph is not None:
+        return graph.replay, how, launches
+
+    def eager():  # capture failed: stay on the stream the warm-up ran on; it is joined before the closing event
         with torch.cuda.stream(side):
             fn()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                fn()
         torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        return graph.replay, "cuda-graph replay"
-    except Exception as e:  # capture unsupported: fall back to eager launches, and say so
-        sys.stderr.write("CUDA graph capture failed, timing eager launches: %r\n" % (e,))
-        torch.cuda.synchronize()
-        return fn, "eager launches (capture failed: %s)" % (repr(e)[:120],)
+
+    return eager, how, launches
 
 
 def time_steps(torch, dist, run, steps, warm, world):
@@ -557,10 +589,7 @@ def measure_api(torch, dist, zd, be, vimco, dev, B, world, rank, steps, warm, us
                         "objective after it; zhusuan.distributed.GradientBucket"
                         % (VAE_DECODER_PARAMS, VAE_ENCODER_PARAMS + 1)}
     step = make_api_step(torch, vimco, leaves, dev, B, world, bucket)
-    n0 = be.launch_count
-    step()
-    launches = be.launch_count - n0
-    run, how = capture(torch, step, dev, use_graph)
+    run, how, launches = capture(torch, step, dev, use_graph, count=lambda: be.launch_count)
     ms, by_rank, wall = time_steps(torch, dist, run, steps, warm, world)
     out = dict(ms=ms, by_rank=by_rank, launch=how, launches_per_step=launches, comm=comm, wall=wall, run=run)
     return out
@@ -624,8 +653,7 @@ def run_b200_arm(args):
 
     # ---- the same step as three raw C-ABI launches (round 1's headline), no collectives
     ks = KernelSequence(torch, be, vimco, dev, seed=1234 + rank, B=B)
-    ks.step()
-    ks_run, ks_how = capture(torch, ks.step, dev, use_graph)
+    ks_run, ks_how, _ = capture(torch, ks.step, dev, use_graph)
     ks_ms, _, _ = time_steps(torch, dist, ks_run, min(args.steps, 500), min(args.warmup, 50), world)
 
     # ---- dominant kernel alone (roofline): CUDA events on the launching stream, 20 launches per graph replay so that
@@ -635,8 +663,8 @@ def run_b200_arm(args):
     logq = torch.randn(K_PART, B, device=dev) + 30.0
     outbuf = ks.fused_only(other, logq)
     per_graph = 20
-    k_run, k_how = capture(torch, lambda: [ks.fused_only(other, logq, out=outbuf) for _ in range(per_graph)], dev,
-                           use_graph)
+    k_run, k_how, _ = capture(torch, lambda: [ks.fused_only(other, logq, out=outbuf) for _ in range(per_graph)], dev,
+                              use_graph)
     reps = 10
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_run()
@@ -787,36 +815,42 @@ def e2e_block(torch, dist, be, zs, dev, world, rank, vimco, B, n_e2e):
         host.update(a=pin(0.5 * torch.randn(B, Z, generator=g)), b=pin(torch.exp(0.3 * torch.randn(B, Z, generator=g))),
                     zeros=pin(torch.zeros(B, Z)), ones=pin(torch.ones(B, Z)))
 
+    # persistent leaves and nets, as in a training loop; gradients are dropped at the start of a step (what
+    # optimizer.zero_grad() does), which also returns the previous step's pinned gradient buffer to the pool
+    probs = host["probs"].detach().requires_grad_()
+    a = host["a"].detach().requires_grad_()
+    b = None if vimco else host["b"].detach().requires_grad_()
+
+    class Gen(BayesianNet):
+        def forward(self, observed):
+            self.observe(observed)
+            if vimco:
+                self.bernoulli("z", probs=host["prior"], n_samples=K, reduce_sum_dims=[2])
+            else:
+                self.normal("z", mean=host["zeros"], std=host["ones"], is_reparameterized=False, n_samples=K,
+                            reduce_sum_dims=[2])
+            self.sn(Bernoulli(probs=probs), name="x", reduce_sum_dims=[2])
+            return self
+
+    class Var(BayesianNet):
+        def forward(self, observed):
+            self.observe(observed)
+            if vimco:
+                self.sn(Bernoulli(probs=a), name="z", n_samples=K, reduce_sum_dims=[2])
+            else:
+                self.sn(Normal(mean=a, std=b), name="z", n_samples=K, reduce_sum_dims=[2])
+            return self
+
+    obj = ImportanceWeightedObjective(Gen(device=cpu), Var(device=cpu), axis=0, estimator="vimco" if vimco else "sgvb")
+    leaves = [t for t in (probs, a, b) if t is not None]
+
     def step():
-        probs = host["probs"].detach().requires_grad_()
-        a = host["a"].detach().requires_grad_()
-        b = None if vimco else host["b"].detach().requires_grad_()
-
-        class Gen(BayesianNet):
-            def forward(self, observed):
-                self.observe(observed)
-                if vimco:
-                    self.bernoulli("z", probs=host["prior"], n_samples=K, reduce_sum_dims=[2])
-                else:
-                    self.normal("z", mean=host["zeros"], std=host["ones"], is_reparameterized=False, n_samples=K,
-                                reduce_sum_dims=[2])
-                self.sn(Bernoulli(probs=probs), name="x", reduce_sum_dims=[2])
-                return self
-
-        class Var(BayesianNet):
-            def forward(self, observed):
-                self.observe(observed)
-                if vimco:
-                    self.sn(Bernoulli(probs=a), name="z", n_samples=K, reduce_sum_dims=[2])
-                else:
-                    self.sn(Normal(mean=a, std=b), name="z", n_samples=K, reduce_sum_dims=[2])
-                return self
-
-        obj = ImportanceWeightedObjective(Gen(device=cpu), Var(device=cpu), axis=0, estimator="vimco" if vimco else "sgvb")
+        for t in leaves:
+            t.grad = None
         loss = obj({"x": host["x"]})
         loss.backward()
         assert probs.grad is not None and probs.grad.device.type == "cpu" and a.grad is not None
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(3):
         step()

@@ -272,8 +272,10 @@ int zs_log_mean_exp_bwd(int dtype, void* dx, const void* g, const void* x, int64
  *       as the rows arrive in shared memory and its derivative is chained into the result, so `dprobs` is the
  *       gradient w.r.t. the decoder's pre-activations.  Available where a fixed-geometry kernel is instantiated
  *       (X in {128, 256, 512, 784, 1024}, K <= 50); otherwise ZS_ERR_UNSUPPORTED and the caller composes
- *       zs_bernoulli_logits_logpmf_fwd -> zs_iw_objective -> zs_bernoulli_logits_logpmf_bwd.              */
-enum { ZS_FUSED_ACCUMULATE_COST = 1, ZS_FUSED_LOGITS = 2 };
+ *       zs_bernoulli_logits_logpmf_fwd -> zs_iw_objective -> zs_bernoulli_logits_logpmf_bwd.
+ *   ZS_FUSED_COST_SCALED  cost[b] = cost_b * grad_scale, so that sum_b cost[b] is the (global-batch) mean objective:
+ *       one reduction, no separate scaling pass over the per-column costs.                                  */
+enum { ZS_FUSED_ACCUMULATE_COST = 1, ZS_FUSED_LOGITS = 2, ZS_FUSED_COST_SCALED = 4 };
 int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlogp, float* dlogq,
                           float* logpx_out, const float* probs, const float* x, const float* logp_other,
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, int flags,

@@ -193,10 +193,11 @@ def fused_supported(K, X, dtype):
 
 
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False, out=None,
-                       logits=False):
+                       logits=False, accumulate_cost=False, cost_scaled=False):
     f = O.iw_bernoulli_logits_step if logits else O.iw_bernoulli_step
     r = f(estimator, _np(probs), _np(x), _np(logp_other), _np(logq), grad_scale, need_dprobs=need_dprobs)
-    return dict(cost=_t(r["cost"], probs), dprobs=_t(r["dprobs"], probs) if need_dprobs else None,
+    cost = r["cost"] * (np.float32(grad_scale) if cost_scaled else np.float32(1.0))
+    return dict(cost=_t(cost, probs), dprobs=_t(r["dprobs"], probs) if need_dprobs else None,
                 dlogp=_t(r["dlogp"], probs), dlogq=_t(r["dlogq"], probs),
                 logpx=_t(r["logpx"], probs) if want_logpx else None)
 

@@ -392,15 +392,19 @@ def test_public_api_step_captured_in_a_cuda_graph(vimco):
         loss.backward()
         return loss
 
-    eager = []
-    for _ in range(3):  # tick 0, 1, 2 of a freshly seeded stream
-        loss = step()
-        eager.append((loss.detach().clone(), mean.grad.clone(), var.nodes["z"].dist.sample_cache.detach().clone()))
-    torch.manual_seed(5)
-    step()  # warm-up outside capture: tick 0 (also re-initialises the device state from the generator)
+    # Everything runs on ONE side stream, as torch's CUDA-graph recipe does with its warm-up: autograd binds a leaf's
+    # AccumulateGrad node to the stream it was first used on, the nets' node caches keep the previous step's graph
+    # alive, and a backward captured on a different stream would have to synchronise with it (invalid during capture).
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
+        eager = []
+        for _ in range(3):  # tick 0, 1, 2 of a freshly seeded stream
+            loss = step()
+            eager.append((loss.detach().clone(), mean.grad.clone(), var.nodes["z"].dist.sample_cache.detach().clone()))
+        torch.manual_seed(5)
+        step()  # warm-up outside capture: tick 0 (also re-initialises the device state from the generator)
+        torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = be.launch_count
         with torch.cuda.graph(g, stream=s):

@@ -36,6 +36,7 @@ namespace zs {
 // launch flags of the fused kernels (kernel parameter `flags`)
 constexpr int FUSED_ACCUMULATE = 1;   // cost[b] += cost_b (running sum over launches) instead of cost[b] = cost_b
 constexpr int FUSED_EARLY_ISSUE = 2;  // ring kernel dev knob: first bulk copies before the first staging
+constexpr int FUSED_COST_SCALED = 4;  // cost[b] = cost_b * grad_scale: sum_b cost[b] is the mean objective
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -125,7 +126,9 @@ __device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int
                                                const float* s_other, const float* s_lq, double* s_xw, float gscale,
                                                float* __restrict__ cost, float* __restrict__ dlogp,
                                                float* __restrict__ dlogq, float* __restrict__ logpx_out,
-                                               bool accumulate = false) {
+                                               int flags = 0) {
+    const bool accumulate = (flags & FUSED_ACCUMULATE) != 0;
+    const float cscale = (flags & FUSED_COST_SCALED) ? gscale : 1.0f;
     // running-sum mode: the old value is requested first so its latency hides behind the objective's arithmetic
     const float prev_cost = (accumulate && lane == 0 && cost) ? cost[b] : 0.f;
     const unsigned FULL = 0xffffffffu;
@@ -201,7 +204,7 @@ __device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int
     }
     c_acc = warp_sum(c_acc);
     // accumulate: running sum of the column's objective over launches (one writer per column: deterministic)
-    if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc;
+    if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc * cscale;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,7 +450,6 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
                         int stagger_groups, int stagger_cycles, int flags, long long* __restrict__ trace, int64_t ldkb) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
     stagger_start(stagger_groups, stagger_cycles);
     const RingLayout L(K, X, R);
     const int Kpad = L.Kpad;
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
         return;
     }
@@ -752,7 +754,6 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
     stagger_start(stagger_groups, stagger_cycles);
     if (is_stager && ncols > 0) {
         stage_scalars(blockIdx.x, 0);
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
         return;
     }
@@ -1110,7 +1111,6 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
-    const bool accumulate_cost = (flags & FUSED_ACCUMULATE) != 0;
     stagger_start(stagger_groups, stagger_cycles);
     // Column 0 only: column 1 is staged while column 0 is being read.  The first tensor copies are issued AFTER
     // this staging on purpose: issuing them first (measured here and in the ring kernel: +4 and +7 us per launch)
@@ -1167,7 +1167,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, accumulate_cost);
+                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
         return;
     }
@@ -1508,10 +1508,12 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
     ZS_REQUIRE(probs && x && K >= 1 && B >= 0 && X >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
-    ZS_REQUIRE((flags & ~(ZS_FUSED_ACCUMULATE_COST | ZS_FUSED_LOGITS)) == 0, ZS_ERR_ARG);
+    ZS_REQUIRE((flags & ~(ZS_FUSED_ACCUMULATE_COST | ZS_FUSED_LOGITS | ZS_FUSED_COST_SCALED)) == 0, ZS_ERR_ARG);
     if (B == 0) return ZS_OK;
     FusedCall c{estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B, grad_scale,
-                (flags & ZS_FUSED_ACCUMULATE_COST) ? FUSED_ACCUMULATE : 0, (flags & ZS_FUSED_LOGITS) != 0,
+                ((flags & ZS_FUSED_ACCUMULATE_COST) ? FUSED_ACCUMULATE : 0) |
+                    ((flags & ZS_FUSED_COST_SCALED) ? FUSED_COST_SCALED : 0),
+                (flags & ZS_FUSED_LOGITS) != 0,
                 as_stream(stream)};
     return fused_launch(c);
 }

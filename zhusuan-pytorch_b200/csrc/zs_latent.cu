@@ -15,6 +15,7 @@
 // parameters FULL or KBCAST, prior parameters KBCAST (or NULL = the standard prior) without gradient.
 // Anything else returns ZS_ERR_UNSUPPORTED and the caller composes the general kernels of zs_nodes.cu.
 #include <initializer_list>
+#include <stdlib.h>
 
 #include "zs_common.cuh"
 #include "zs_philox.cuh"
@@ -245,7 +246,6 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
                         int a_mode, const T* __restrict__ b, const T* __restrict__ pa, const T* __restrict__ pb,
                         const T* __restrict__ noise_in, int K, int64_t M, int E4, int RW, int KS, uint64_t seed,
                         uint64_t offset, unsigned long long* rs) {
-    offset = rng_acquire(offset, rs, nullptr, true);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rl = lane / E4, j = lane - rl * E4;
     const int64_t m = ((int64_t)blockIdx.x * LF_WARPS + warp) * RW + rl;
@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
     const int64_t pidx = m * E + 4 * j;  // the unit inside [M,E]
     UnitParams<T> up;
     if (active && kb) load_unit_params<T, FAM>(up, a, b, pa, pb, pidx, pidx);
+    // the stream position is read by the CTA's leader while the other warps load and prepare their parameters
+    offset = rng_acquire(offset, rs, nullptr, true);
     // every slice runs the same trip count (the shuffles need the whole warp); particles past K are skipped
     const int trips = (K + KS - 1) / KS;
     for (int t = 0; t < trips; t += 2) {
@@ -296,48 +298,48 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
 // every thread owns two particles whose six loads are all issued before the first use, LB_X = 8 units (one 128-byte
 // line per particle row) so that 1280 CTAs spread evenly over the SMs.
 // ---------------------------------------------------------------------------------------------
-constexpr int LB_X = 8, LB_Y_MAX = 32;
+constexpr int LB_X_MAX = 8, LB_Y_MAX = 32;
 
-template <typename T, int FAM>
-__global__ void __launch_bounds__(LB_X* LB_Y_MAX, sizeof(T) == 4 ? 3 : 1)
+// STDP: the prior is the family's standard one (prior_mean / prior_std NULL): its terms are constants, not registers.
+template <typename T, int FAM, bool STDP>
+__global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, sizeof(T) == 4 ? 4 : 1)
     k_latent_bwd(T* __restrict__ da, T* __restrict__ db, const T* __restrict__ gq, const T* __restrict__ gp,
                  const T* __restrict__ dz_up, const T* __restrict__ z, const T* __restrict__ a, int a_mode,
                  const T* __restrict__ b, int b_mode, const T* __restrict__ pa, const T* __restrict__ pb,
                  int reparam, int64_t K, int64_t M, int64_t E) {
     const int64_t ME4 = (M * E) >> 2;
-    const int64_t u = (int64_t)blockIdx.x * LB_X + threadIdx.x;
-    const int LBY = blockDim.y;
+    const int LBX = blockDim.x, LBY = blockDim.y;
+    const int64_t u = (int64_t)blockIdx.x * LBX + threadIdx.x;
     const bool valid = u < ME4;
     const bool full = a_mode == ZS_FULL;  // FULL parameters: per-particle gradients, no reduction
     V4<T> sa{{T(0), T(0), T(0), T(0)}}, sb{{T(0), T(0), T(0), T(0)}};
     if (valid) {
         const int64_t ke = 4 * u, m = ke / E;
-        UnitParams<T> up;  // only a, b, prec, pa, pprec are used here: no logarithms on the backward path
-        V4<T> rstd;
+        // per unit: a (mean | probs), 1/std (Normal) or the two reciprocals of bernoulli.py:94's autograd; the
+        // prior's mean and precision unless STDP.  No logarithms on the backward path.
+        V4<T> pa_, r0, r1, pm, pprec;
         auto load_params = [&](int64_t idx) {
-            up.a = ldv4(a + idx);
+            pa_ = ldv4(a + idx);
             if (FAM == FAM_BERNOULLI) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {  // the two reciprocals of bernoulli.py:94's autograd, once per unit
-                    up.logb.v[q] = lat_rcp(up.a.v[q] + T(1e-8));
-                    up.prec.v[q] = lat_rcp((T(1) - up.a.v[q]) + T(1e-8));
-                }
-            }
-            if (FAM == FAM_NORMAL) {
-                up.b = ldv4(b + idx);
-#pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    rstd.v[q] = lat_rcp(up.b.v[q]);
-                    up.prec.v[q] = rstd.v[q] * rstd.v[q];  // exp(-2 log std) of normal.py:122
+                    r0.v[q] = lat_rcp(pa_.v[q] + T(1e-8));
+                    r1.v[q] = lat_rcp((T(1) - pa_.v[q]) + T(1e-8));
                 }
-                if (pa) up.pa = ldv4(pa + ke);
-                else up.pa = V4<T>{{T(0), T(0), T(0), T(0)}};
-                if (pb) {
-                    const V4<T> ps = ldv4(pb + ke);
+            } else {
+                const V4<T> sd = ldv4(b + idx);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) up.pprec.v[q] = lat_rcp(ps.v[q] * ps.v[q]);
-                } else {
-                    up.pprec = V4<T>{{T(1), T(1), T(1), T(1)}};
+                for (int q = 0; q < 4; ++q) r0.v[q] = lat_rcp(sd.v[q]);  // 1/std; exp(-2 log std) = (1/std)^2
+                if (!STDP) {
+                    if (pa) pm = ldv4(pa + ke);
+                    else pm = V4<T>{{T(0), T(0), T(0), T(0)}};
+                    if (pb) {
+                        const V4<T> ps = ldv4(pb + ke);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) pprec.v[q] = lat_rcp(ps.v[q] * ps.v[q]);
+                    } else {
+                        pprec = V4<T>{{T(1), T(1), T(1), T(1)}};
+                    }
                 }
             }
         };
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(LB_X* LB_Y_MAX, sizeof(T) == 4 ? 3 : 1)
                 if (dz_up && reparam) du[i] = ldv4(dz_up + fe);
                 else du[i] = V4<T>{{T(0), T(0), T(0), T(0)}};
             }
-            if (!full) load_params(ke);  // loop-invariant: hoisted by the compiler, placed after the particle loads
+            if (!full) load_params(ke);  // loop-invariant: issued after the particle loads, hoisted by the compiler
 #pragma unroll
             for (int i = 0; i < LBU; ++i) {
                 const int64_t k = k0 + (int64_t)i * LBY;
@@ -368,24 +370,28 @@ __global__ void __launch_bounds__(LB_X* LB_Y_MAX, sizeof(T) == 4 ? 3 : 1)
                 for (int q = 0; q < 4; ++q) {
                     if (FAM == FAM_NORMAL) {
                         // autograd of normal.py:121-124 (same association as NormalOp::grad in zs_nodes.cu)
-                        const T prec = up.prec.v[q], zz = zv[i].v[q];
-                        const T d = zz - up.a.v[q];
+                        const T rstd = r0.v[q], prec = rstd * rstd, zz = zv[i].v[q];
+                        const T d = zz - pa_.v[q];
                         const T dzq = -(g_q[i] * (T(0.5) * prec)) * (T(2) * d);
                         const T dprec = -(g_q[i] * (d * d)) * T(0.5);
                         const T dlogstd = -g_q[i] + (dprec * prec) * T(-2);
-                        T dmean = -dzq, dstd = dlogstd * rstd.v[q];
+                        T dmean = -dzq, dstd = dlogstd * rstd;
                         if (reparam) {
-                            const T dzp = gp ? -(g_p[i] * (T(0.5) * up.pprec.v[q])) * (T(2) * (zz - up.pa.v[q])) : T(0);
+                            T dzp = T(0);
+                            if (gp) {
+                                if (STDP) dzp = -(g_p[i] * T(0.5)) * (T(2) * zz);
+                                else dzp = -(g_p[i] * (T(0.5) * pprec.v[q])) * (T(2) * (zz - pm.v[q]));
+                            }
                             const T dzt = (du[i].v[q] + dzp) + dzq;  // total gradient reaching the sample
                             dmean += dzt;                            // z = mean + std*eps
-                            dstd += dzt * (d * rstd.v[q]);           // eps recovered from the sample
+                            dstd += dzt * (d * rstd);                // eps recovered from the sample
                         }
                         oa.v[q] = dmean;
                         ob.v[q] = dstd;
                     } else {
                         // autograd of bernoulli.py:94 wrt probs (samples carry no gradient)
                         const T zz = zv[i].v[q];
-                        oa.v[q] = (g_q[i] * zz) * up.logb.v[q] - (g_q[i] * (T(1) - zz)) * up.prec.v[q];
+                        oa.v[q] = (g_q[i] * zz) * r0.v[q] - (g_q[i] * (T(1) - zz)) * r1.v[q];
                         ob.v[q] = T(0);
                     }
                 }
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(LB_X* LB_Y_MAX, sizeof(T) == 4 ? 3 : 1)
         }
     }
     if (full) return;
-    __shared__ T red[2][LB_Y_MAX][LB_X][4];
+    __shared__ T red[2][LB_Y_MAX][LB_X_MAX][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         red[0][threadIdx.y][threadIdx.x][q] = sa.v[q];
@@ -430,17 +436,17 @@ static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, con
         const int RW = (int)(32 / E4);
         const int64_t row_warps = (M + RW - 1) / RW;
         const int64_t gx = (row_warps + LF_WARPS - 1) / LF_WARPS;
-        // k-slices: two particles per thread (both Philox / Box-Muller chains in flight) until that is more than
-        // ~48 warps per SM, then equal trip counts per slice.  The parameter terms a slice recomputes are SFU ops
-        // (lat_log / lat_rcp), so small slices cost little and fill the machine: at config 2 (K = 50, M = 1024,
-        // Z = 40) 25 slices x 86 CTAs of 4 warps, against 10 slices (0.73 waves, 29 % active warps) before.
-        int64_t KS = (K + 1) / 2;
-        const int64_t cap = ((int64_t)sm_count() * 48 + row_warps - 1) / row_warps;
-        if (KS > cap) KS = cap;
+        // k-slices: two particles in flight per thread (two Philox / Box-Muller chains), and as many pairs per
+        // thread as it takes for the whole grid to be resident at once (8 CTAs of 4 warps per SM at 60 registers):
+        // a 1.2-wave grid leaves the machine a quarter full for the length of its second wave.  The parameter
+        // terms a slice recomputes are SFU ops (lat_log / lat_rcp), so slices are cheap.  Config 2 (K = 50,
+        // M = 1024, Z = 40): 86 CTAs x 13 slices of 4 particles = 1118 CTAs on 148 x 8 slots.
+        const int64_t resident = (int64_t)sm_count() * 8;
+        int64_t trips = K < 2 ? 1 : 2;
+        while (gx * ((K + trips - 1) / trips) > resident && trips < K) trips += 2;
+        int64_t KS = (K + trips - 1) / trips;
         if (KS > 65535) KS = 65535;
         if (KS < 1) KS = 1;
-        const int64_t trips = (K + KS - 1) / KS;
-        KS = (K + trips - 1) / trips;
         ZS_REQUIRE(gx < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
         dim3 grid((unsigned)gx, (unsigned)KS);
         k_latent_fwd_packed<T, FAM><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, (int)K, M,
@@ -495,13 +501,23 @@ static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp,
                              const void* a, int a_mode, const void* b, int b_mode, const void* pa, const void* pb,
                              int reparam, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
     const int64_t ME4 = (M * E) >> 2;
-    const int64_t grid = (ME4 + LB_X - 1) / LB_X;
+    // blockDim.x float4 units of [M,E] (8 = one 128-byte line per particle row; 4 when that leaves fewer than ~16
+    // CTAs per SM: the grid is a few waves deep, so small CTAs keep the last wave's imbalance small)
+    static const int forced_x = [] {
+        const char* e = getenv("ZS_LATENT_BWD_X");
+        return e ? atoi(e) : 0;
+    }();
+    int lbx = (ME4 / LB_X_MAX >= (int64_t)sm_count() * 16) ? LB_X_MAX : 4;
+    if (forced_x == 4 || forced_x == 8) lbx = forced_x;
+    const int64_t grid = (ME4 + lbx - 1) / lbx;
     ZS_REQUIRE(grid < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
     int lby = (int)((K + 1) / 2);  // two particles per thread
     if (lby > LB_Y_MAX) lby = LB_Y_MAX;
     if (lby < 8) lby = 8;          // the epilogue's eight (array, component) sums are taken by slices 0..7
-    dim3 block(LB_X, lby);
-    k_latent_bwd<T, FAM><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+    dim3 block(lbx, lby);
+    const bool stdp = pa == nullptr && pb == nullptr;
+    auto kern = stdp ? k_latent_bwd<T, FAM, true> : k_latent_bwd<T, FAM, false>;
+    kern<<<(unsigned)grid, block, 0, as_stream(stream)>>>(
         (T*)da, (T*)db, (const T*)gq, (const T*)gp, (const T*)dz_up, (const T*)z, (const T*)a, a_mode, (const T*)b,
         b_mode, (const T*)pa, (const T*)pb, reparam, K, M, E);
     ZS_LAUNCH_CHECK("k_latent_bwd");

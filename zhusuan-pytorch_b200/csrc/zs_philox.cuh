@@ -56,11 +56,19 @@ __device__ __forceinline__ uint64_t rng_acquire(uint64_t offset, unsigned long l
                                                 bool advance) {
     if (state == nullptr) return offset;  // uniform over the grid
     __shared__ unsigned long long s_rng_base;
-    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
-        const unsigned long long base = *reinterpret_cast<volatile unsigned long long*>(state);
+    const bool leader = threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0;
+    unsigned long long base = 0ull;
+    if (leader) {
+        base = *reinterpret_cast<volatile unsigned long long*>(state);
         s_rng_base = base;
+    }
+    __syncthreads();
+    const uint64_t eff = offset + s_rng_base;
+    // the CTA's only read of the device state is the leader's, above: its arrival may follow the barrier, so the
+    // other warps do not wait for the fence and the atomic round trip
+    if (leader) {
         if (snapshot != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-            snapshot[0] = base + offset;
+            snapshot[0] = eff;
             snapshot[1] = 0ull;
         }
         if (advance) {
@@ -73,8 +81,7 @@ __device__ __forceinline__ uint64_t rng_acquire(uint64_t offset, unsigned long l
             }
         }
     }
-    __syncthreads();
-    return offset + s_rng_base;
+    return eff;
 }
 
 // Box-Muller on two words -> two standard normals.  The radius uses logf (the SFU lg2 has an absolute

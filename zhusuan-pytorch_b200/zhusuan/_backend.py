@@ -18,7 +18,7 @@ F32, F64 = 0, 1
 FULL, KBCAST, SCALAR = 0, 1, 2
 SGVB, VIMCO, ELBO = 0, 1, 2
 ERR_UNSUPPORTED, ERR_ALIGN = -6, -7
-FUSED_ACCUMULATE_COST, FUSED_LOGITS = 1, 2
+FUSED_ACCUMULATE_COST, FUSED_LOGITS, FUSED_COST_SCALED = 1, 2, 4
 ALG_SGLD, ALG_PSGLD, ALG_SGHMC_PRE, ALG_SGHMC_POST = 0, 1, 2, 3
 CHAIN_MAX_TENSORS = 32
 IMPL_DEFAULT, IMPL_RING, IMPL_BOX, IMPL_BOXG = -1, 2, 3, 4
@@ -475,10 +475,11 @@ def set_fused_impl(impl):
 
 
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False,
-                       out=None, logits=False, accumulate_cost=False):
+                       out=None, logits=False, accumulate_cost=False, cost_scaled=False):
     """probs [K,B,X], x [B,X], logp_other/logq [K,B] or None.  `logits=True`: `probs` holds logits and "dprobs" is
     the gradient w.r.t. them (ZS_FUSED_LOGITS).  `accumulate_cost=True` (needs out["cost"]): the per-column
-    objectives are ADDED to out["cost"] (ZS_FUSED_ACCUMULATE_COST).
+    objectives are ADDED to out["cost"] (ZS_FUSED_ACCUMULATE_COST).  `cost_scaled=True`: cost[b] already carries
+    grad_scale, so cost.sum() is the mean objective (ZS_FUSED_COST_SCALED).
     Returns dict(cost[B], dprobs, dlogp, dlogq, logpx) or None when the shape is not supported."""
     dev = probs.device
     _chk(dev, torch.float32, probs=probs, x=x, logp_other=logp_other, logq=logq)
@@ -490,7 +491,8 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
     dlq = o.get("dlogq") if "dlogq" in o else torch.empty((K, B), dtype=torch.float32, device=dev)
     lpx = (o.get("logpx") if "logpx" in o else torch.empty((K, B), dtype=torch.float32, device=dev)) if want_logpx else None
     _chk(dev, torch.float32, cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx)
-    flags = (FUSED_LOGITS if logits else 0) | (FUSED_ACCUMULATE_COST if accumulate_cost else 0)
+    flags = ((FUSED_LOGITS if logits else 0) | (FUSED_ACCUMULATE_COST if accumulate_cost else 0) |
+             (FUSED_COST_SCALED if cost_scaled else 0))
     rc = _run("zs_iw_bernoulli_fused", dev, estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx),
               _ptr(probs), _ptr(x), _ptr(logp_other), _ptr(logq), K, B, X, float(grad_scale), flags)
     if rc in (ERR_UNSUPPORTED, ERR_ALIGN):

@@ -773,12 +773,14 @@ class _IWBernoulliFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probs, x, logp_other, logq, estimator, logits=False):
         K, B, X = probs.shape
+        # per-column costs come out already scaled by 1 / (columns of the local or global batch): the mean objective
+        # is ONE reduction over them
         r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, _mean_scale(B),
-                                  need_dprobs=ctx.needs_input_grad[0], logits=logits)
+                                  need_dprobs=ctx.needs_input_grad[0], logits=logits, cost_scaled=True)
         if r is None:
             raise be.BackendError("fused IW kernel refused a shape fused_supported() accepted")
         ctx.grads = (r["dprobs"], r["dlogp"], r["dlogq"])
-        return _mean_cost(r["cost"], B)
+        return r["cost"].sum()
 
     @staticmethod
     def backward(ctx, g):

@@ -89,7 +89,7 @@ class Bernoulli(Distribution):
         lp = _ops.std_prior_logp(given, "bernoulli", n_event)  # see Normal._log_prob_event
         if (lp is not None and lp.dtype == self._dtype and self._is_half()
                 and tuple(_bshapes(tuple(given.shape), tuple(self._batch_shape()))) == tuple(given.shape)):
-            return lp
+            return _ops.back_home(lp, given.device)
         if self._from_logits is not None:
             return _ops.bernoulli_log_prob(self._given(given), self._from_logits, n_event, logits=True)
         return _ops.bernoulli_log_prob(self._given(given), self._probs, n_event)

@@ -79,7 +79,7 @@ class Normal(Distribution):
         lp = _ops.std_prior_logp(given, "normal", n_event)
         if (lp is not None and lp.dtype == self._dtype and self._is_standard()
                 and tuple(_bshapes(tuple(given.shape), tuple(self._batch_shape()))) == tuple(given.shape)):
-            return lp
+            return _ops.back_home(lp, given.device)
         return _ops.normal_log_prob(given, self._mean, self._std, n_event)
 
     def _log_prob(self, sample=None):
