@@ -41,6 +41,14 @@ __device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
     st_pack(p + 2, b);
 }
 
+// The reference evaluates every update as a chain of separate torch ops (SGLD.py:50-52, SGHMC.py:46-56): each product
+// and sum is rounded on its own.  The bodies below spell the roundings out (no fused multiply-add contraction), so the
+// single-tensor and the multi-tensor kernels -- different code around the same body -- agree bit for bit.
+__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float radd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double radd(double a, double b) { return __dadd_rn(a, b); }
+
 // Generic driver: Body::apply(i-th element state...) over n elements, 4 per thread.
 // VEC requires 16-byte aligned pointers; the last n%4 elements always take the scalar path.
 template <typename T, typename Body, bool VEC>
@@ -75,16 +83,16 @@ struct SgldBody {
         wo = (T*)c.w_out; w = (const T*)c.w; g = (const T*)c.g; noise = (const T*)c.noise;
     }
     bool valid(const zs_chain_tensor& c) const { return c.w_out && c.w && c.g; }
-    __device__ __forceinline__ T upd(T wv, T gv, T e) const { return (wv + half_lr * gv) + e; }
+    __device__ __forceinline__ T upd(T wv, T gv, T e) const { return radd(radd(wv, rmul(half_lr, gv)), e); }
     __device__ void one(int64_t i, float xi) const {
-        T e = noise ? noise[i] : (T)(std * xi);
+        T e = noise ? noise[i] : (T)rmul(std, xi);
         wo[i] = upd(w[i], g[i], e);
     }
     __device__ void vec(int64_t i, const float* xi) const {
         Quad<T> wv = ld4(w + i), gv = ld4(g + i), ev;
         if (noise) ev = ld4(noise + i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wv.v[j] = upd(wv.v[j], gv.v[j], noise ? ev.v[j] : (T)(std * xi[j]));
+        for (int j = 0; j < 4; ++j) wv.v[j] = upd(wv.v[j], gv.v[j], noise ? ev.v[j] : (T)rmul(std, xi[j]));
         st4(wo + i, wv);
     }
 };
@@ -103,10 +111,10 @@ struct PsgldBody {
     }
     bool valid(const zs_chain_tensor& c) const { return c.w_out && c.w && c.g && c.state; }
     __device__ __forceinline__ void upd(T& wv, T& av, T gv, T xi) const {
-        av = decay * av + one_m_decay * (gv * gv);
-        T G = T(1) / (eps + Real<T>::sqrt(av));
-        T e = Real<T>::sqrt(lr * G) * xi;
-        wv = (wv + (half_lr * G) * gv) + e;
+        av = radd(rmul(decay, av), rmul(one_m_decay, rmul(gv, gv)));
+        T G = T(1) / radd(eps, Real<T>::sqrt(av));
+        T e = rmul(Real<T>::sqrt(rmul(lr, G)), xi);
+        wv = radd(radd(wv, rmul(rmul(half_lr, G), gv)), e);
     }
     __device__ void one(int64_t i, float xi) const {
         T wv = w[i], av = aux[i];
@@ -139,11 +147,11 @@ struct SghmcPreBody {
     bool valid(const zs_chain_tensor& c) const { return c.w_out && c.w && c.state; }
     __device__ __forceinline__ void upd(T& wv, T& vv, T fresh) const {
         if (resample) vv = fresh;
-        if (second_order) wv = wv + T(0.5) * vv;
+        if (second_order) wv = radd(wv, rmul(T(0.5), vv));
     }
     __device__ void one(int64_t i, float xi) const {
         T wv = w[i], vv = v[i];
-        upd(wv, vv, v_noise ? v_noise[i] : (T)(std * xi));
+        upd(wv, vv, v_noise ? v_noise[i] : (T)rmul(std, xi));
         if (resample) v[i] = vv;
         if (second_order) wo[i] = wv;
     }
@@ -151,7 +159,7 @@ struct SghmcPreBody {
         Quad<T> wv = ld4(w + i), vv = ld4(v + i), nv;
         if (v_noise) nv = ld4(v_noise + i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], v_noise ? nv.v[j] : (T)(std * xi[j]));
+        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], v_noise ? nv.v[j] : (T)rmul(std, xi[j]));
         if (resample) st4(v + i, vv);
         if (second_order) st4(wo + i, wv);
     }
@@ -174,16 +182,16 @@ struct SghmcPostBody {
     bool valid(const zs_chain_tensor& c) const { return c.w_out && c.w && c.g && c.state; }
     __device__ __forceinline__ void upd(T& wv, T& vv, T gv, T n) const {
         if (!second_order) {
-            vv = (one_m_alpha * vv + lr * gv) + n;
-            wv = wv + vv;
+            vv = radd(radd(rmul(one_m_alpha, vv), rmul(lr, gv)), n);
+            wv = radd(wv, vv);
         } else {
-            vv = decay_half * ((decay_half * vv + lr * gv) + n);
-            wv = wv + T(0.5) * vv;
+            vv = rmul(decay_half, radd(radd(rmul(decay_half, vv), rmul(lr, gv)), n));
+            wv = radd(wv, rmul(T(0.5), vv));
         }
     }
     __device__ void one(int64_t i, float xi) const {
         T wv = w[i], vv = v[i];
-        upd(wv, vv, g[i], noise ? noise[i] : (T)(std * xi));
+        upd(wv, vv, g[i], noise ? noise[i] : (T)rmul(std, xi));
         wo[i] = wv;
         v[i] = vv;
     }
@@ -191,7 +199,7 @@ struct SghmcPostBody {
         Quad<T> wv = ld4(w + i), vv = ld4(v + i), gv = ld4(g + i), nv;
         if (noise) nv = ld4(noise + i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], gv.v[j], noise ? nv.v[j] : (T)(std * xi[j]));
+        for (int j = 0; j < 4; ++j) upd(wv.v[j], vv.v[j], gv.v[j], noise ? nv.v[j] : (T)rmul(std, xi[j]));
         st4(wo + i, wv);
         st4(v + i, vv);
     }
