@@ -291,6 +291,150 @@ __global__ void __launch_bounds__(LF_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward, the hot configuration (float, KBCAST parameters, E/4 <= 32, everything indexable in 32 bits): the packed
+// kernel above executed ~350 instructions per float4 of latents (ncu round 2: 6.3 M warp instructions for 512 k
+// float4, issue-bound at 11 us).  This one is written for instruction count:
+//   * every parameter-only term is reduced to what the particle loop needs: the per-row constant
+//     sum_q (c - log std_q) is added once, the loop keeps 0.5/std_q^2 (Normal) or the two logs (Bernoulli);
+//   * a standard prior (STDP) contributes E*c - 0.5 sum z^2 (Normal) or E*log(0.5 + 1e-8) (Bernoulli(0.5):
+//     both branches of bernoulli.py:94 are the same number) -- no prior registers, one FMA per element;
+//   * 32-bit index arithmetic, lane -> (row, unit) by a multiply-shift instead of an integer division,
+//     the segmented row sums skip the shuffle levels wider than a row;
+//   * Box-Muller on the SFU (zs_philox.cuh).
+// Sums are re-associated against the reference's elementwise order (a float32 rounding-level difference, 1e-7
+// relative; the parity budget is 1e-5).
+// ---------------------------------------------------------------------------------------------
+template <int FAM, bool STDP>
+__global__ void __launch_bounds__(LF_WARPS * 32, 8)
+    k_latent_fwd_fast(float* __restrict__ z, float* __restrict__ logq, float* __restrict__ logp,
+                      const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
+                      const float* __restrict__ pb, const float* __restrict__ noise_in, int K, int M, int E4, int RW,
+                      int KS, unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = (int)(((unsigned)lane * inv_e4) >> 16), j = lane - rl * E4;  // lane / E4, lane % E4
+    const int m = ((int)blockIdx.x * LF_WARPS + warp) * RW + rl;
+    const bool active = rl < RW && m < M;
+    const int E = 4 * E4;
+    const unsigned ME4 = (unsigned)M * (unsigned)E4;   // float4 units per particle
+    const unsigned punit = (unsigned)m * (unsigned)E4 + (unsigned)j;  // this thread's unit inside [M, E/4]
+    // ---- per-unit constants
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av, h = av, l0 = av, l1 = av;
+    float cq = 0.f, cp = 0.f;  // particle-independent parts of this unit's log q / log p
+    float4 pm = av, hp = av;
+    if (active) {
+        av = *reinterpret_cast<const float4*>(a + 4 * (size_t)punit);
+        if (FAM == FAM_NORMAL) {
+            bv = *reinterpret_cast<const float4*>(b + 4 * (size_t)punit);
+            const float c = normal_c<float>();
+            cq = (c - lat_log(bv.x)) + (c - lat_log(bv.y)) + (c - lat_log(bv.z)) + (c - lat_log(bv.w));
+            h = make_float4(0.5f * lat_rcp(bv.x * bv.x), 0.5f * lat_rcp(bv.y * bv.y), 0.5f * lat_rcp(bv.z * bv.z),
+                            0.5f * lat_rcp(bv.w * bv.w));
+            if (STDP) {
+                cp = 4.0f * c;
+            } else {
+                if (pa) pm = *reinterpret_cast<const float4*>(pa + 4 * (size_t)punit);
+                float4 ps = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (pb) ps = *reinterpret_cast<const float4*>(pb + 4 * (size_t)punit);
+                cp = (c - lat_log(ps.x)) + (c - lat_log(ps.y)) + (c - lat_log(ps.z)) + (c - lat_log(ps.w));
+                hp = make_float4(0.5f * lat_rcp(ps.x * ps.x), 0.5f * lat_rcp(ps.y * ps.y), 0.5f * lat_rcp(ps.z * ps.z),
+                                 0.5f * lat_rcp(ps.w * ps.w));
+            }
+        } else {
+            // log(p + 1e-8), log((1-p) + 1e-8) of bernoulli.py:94: l1 + z (l0 - l1) per element
+            l0 = make_float4(lat_log(av.x + 1e-8f), lat_log(av.y + 1e-8f), lat_log(av.z + 1e-8f), lat_log(av.w + 1e-8f));
+            l1 = make_float4(lat_log((1.f - av.x) + 1e-8f), lat_log((1.f - av.y) + 1e-8f), lat_log((1.f - av.z) + 1e-8f),
+                             lat_log((1.f - av.w) + 1e-8f));
+            cq = (l1.x + l1.y) + (l1.z + l1.w);
+            l0 = make_float4(l0.x - l1.x, l0.y - l1.y, l0.z - l1.z, l0.w - l1.w);
+            if (STDP) {
+                cp = 4.0f * lat_log(0.5f + 1e-8f);
+            } else {
+                const float4 pp = *reinterpret_cast<const float4*>(pa + 4 * (size_t)punit);
+                pm = make_float4(lat_log(pp.x + 1e-8f), lat_log(pp.y + 1e-8f), lat_log(pp.z + 1e-8f), lat_log(pp.w + 1e-8f));
+                hp = make_float4(lat_log((1.f - pp.x) + 1e-8f), lat_log((1.f - pp.y) + 1e-8f), lat_log((1.f - pp.z) + 1e-8f),
+                                 lat_log((1.f - pp.w) + 1e-8f));
+                cp = (hp.x + hp.y) + (hp.z + hp.w);
+                pm = make_float4(pm.x - hp.x, pm.y - hp.y, pm.z - hp.z, pm.w - hp.w);
+            }
+        }
+    }
+    // the stream position is read by the CTA's leader while the other warps prepare their constants
+    offset = rng_acquire(offset, rs, nullptr, true);
+
+    auto one = [&](int k, float& accq, float& accp) {
+        const unsigned unit = (unsigned)k * ME4 + punit;  // global float4 index == Philox counter of these 4 elements
+        float n4[4];
+        if (noise_in) {
+            const float4 t = *reinterpret_cast<const float4*>(noise_in + 4 * (size_t)unit);
+            n4[0] = t.x; n4[1] = t.y; n4[2] = t.z; n4[3] = t.w;
+        } else if (FAM == FAM_NORMAL) {
+            philox_normal4((uint64_t)unit, offset, seed, n4);
+        } else {
+            philox_uniform4((uint64_t)unit, offset, seed, n4);
+        }
+        float4 zv;
+        if (FAM == FAM_NORMAL) {
+            zv = make_float4(fmaf(bv.x, n4[0], av.x), fmaf(bv.y, n4[1], av.y), fmaf(bv.z, n4[2], av.z),
+                             fmaf(bv.w, n4[3], av.w));  // normal.py:105
+            const float d0 = zv.x - av.x, d1 = zv.y - av.y, d2 = zv.z - av.z, d3 = zv.w - av.w;  // normal.py:121-124
+            accq = cq - ((h.x * (d0 * d0) + h.y * (d1 * d1)) + (h.z * (d2 * d2) + h.w * (d3 * d3)));
+            if (STDP) {
+                accp = cp - 0.5f * ((zv.x * zv.x + zv.y * zv.y) + (zv.z * zv.z + zv.w * zv.w));
+            } else {
+                const float e0 = zv.x - pm.x, e1 = zv.y - pm.y, e2 = zv.z - pm.z, e3 = zv.w - pm.w;
+                accp = cp - ((hp.x * (e0 * e0) + hp.y * (e1 * e1)) + (hp.z * (e2 * e2) + hp.w * (e3 * e3)));
+            }
+        } else {
+            zv = make_float4(n4[0] < av.x ? 1.f : 0.f, n4[1] < av.y ? 1.f : 0.f, n4[2] < av.z ? 1.f : 0.f,
+                             n4[3] < av.w ? 1.f : 0.f);  // bernoulli.py:79
+            accq = cq + ((zv.x * l0.x + zv.y * l0.y) + (zv.z * l0.z + zv.w * l0.w));
+            if (STDP) accp = cp;
+            else accp = cp + ((zv.x * pm.x + zv.y * pm.y) + (zv.z * pm.z + zv.w * pm.w));
+        }
+        *reinterpret_cast<float4*>(z + 4 * (size_t)unit) = zv;
+    };
+    // sum over the E4 consecutive lanes of a row (valid in the row's first lane); levels wider than a row are skipped
+    auto row_sum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            if (o < E4) {  // uniform
+                const float other = __shfl_down_sync(0xffffffffu, v, o);
+                if (j + o < E4) v += other;
+            }
+        }
+        return v;
+    };
+    const int trips = (K + KS - 1) / KS;  // equal for every slice (the shuffles need the whole warp)
+    for (int t = 0; t < trips; t += 2) {
+        const int k0 = (int)blockIdx.y + t * KS, k1 = k0 + KS;
+        const bool on0 = active && k0 < K, on1 = active && t + 1 < trips && k1 < K;
+        float q0 = 0.f, p0 = 0.f, q1 = 0.f, p1 = 0.f;
+        if (on0) one(k0, q0, p0);
+        if (on1) one(k1, q1, p1);
+        q0 = row_sum(q0);
+        q1 = row_sum(q1);
+        if (logp != nullptr && !(STDP && FAM == FAM_BERNOULLI)) {
+            p0 = row_sum(p0);
+            p1 = row_sum(p1);
+        } else {
+            p0 *= (float)E4;  // a constant per unit: E4 units of it
+            p1 *= (float)E4;
+        }
+        if (j == 0) {
+            if (on0) {
+                if (logq) logq[(unsigned)k0 * (unsigned)M + (unsigned)m] = q0;
+                if (logp) logp[(unsigned)k0 * (unsigned)M + (unsigned)m] = p0;
+            }
+            if (on1) {
+                if (logq) logq[(unsigned)k1 * (unsigned)M + (unsigned)m] = q1;
+                if (logp) logp[(unsigned)k1 * (unsigned)M + (unsigned)m] = p1;
+            }
+        }
+    }
+    (void)E;
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward: block = LB_X float4 units of [M,E] x blockDim.y particle slices, fixed-order sum over slices.
 // Parameter-only terms (precision, 1/std) are hoisted out of the particle loop and take the SFU reciprocal.
 // The kernel moves 17 MB at config 2 and was latency-bound (ncu round 1: long_scoreboard 4.35, 1.44 waves of
@@ -426,6 +570,49 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, sizeof(T) == 4 ? 4 : 1)
     }
 }
 
+// float / KBCAST / 32-bit indexable shapes go to k_latent_fwd_fast; returns false when the shape does not qualify
+template <typename T, int FAM>
+static bool launch_latent_fwd_fast(dim3, T*, T*, T*, const T*, int, const T*, const T*, const T*, const T*, int64_t,
+                                   int64_t, int64_t, int, int64_t, uint64_t, uint64_t, unsigned long long*,
+                                   cudaStream_t) {
+    return false;
+}
+template <>
+bool launch_latent_fwd_fast<float, FAM_NORMAL>(dim3 grid, float* z, float* logq, float* logp, const float* a, int a_mode,
+                                               const float* b, const float* pa, const float* pb, const float* noise_in,
+                                               int64_t K, int64_t M, int64_t E4, int RW, int64_t KS, uint64_t seed,
+                                               uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+    if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
+    const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
+    if (pa == nullptr && pb == nullptr)
+        k_latent_fwd_fast<FAM_NORMAL, true><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in, (int)K,
+                                                                            (int)M, (int)E4, RW, (int)KS, inv, seed,
+                                                                            offset, rs);
+    else
+        k_latent_fwd_fast<FAM_NORMAL, false><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in, (int)K,
+                                                                             (int)M, (int)E4, RW, (int)KS, inv, seed,
+                                                                             offset, rs);
+    return true;
+}
+template <>
+bool launch_latent_fwd_fast<float, FAM_BERNOULLI>(dim3 grid, float* z, float* logq, float* logp, const float* a,
+                                                  int a_mode, const float* b, const float* pa, const float* pb,
+                                                  const float* noise_in, int64_t K, int64_t M, int64_t E4, int RW,
+                                                  int64_t KS, uint64_t seed, uint64_t offset, unsigned long long* rs,
+                                                  cudaStream_t st) {
+    if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
+    const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
+    if (pa == nullptr)
+        k_latent_fwd_fast<FAM_BERNOULLI, true><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in,
+                                                                               (int)K, (int)M, (int)E4, RW, (int)KS, inv,
+                                                                               seed, offset, rs);
+    else
+        k_latent_fwd_fast<FAM_BERNOULLI, false><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in,
+                                                                                (int)K, (int)M, (int)E4, RW, (int)KS, inv,
+                                                                                seed, offset, rs);
+    return true;
+}
+
 template <typename T, int FAM>
 static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, const T* b, int b_mode, const T* pa,
                              const T* pb, const T* noise_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
@@ -449,6 +636,11 @@ static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, con
         if (KS < 1) KS = 1;
         ZS_REQUIRE(gx < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
         dim3 grid((unsigned)gx, (unsigned)KS);
+        if (launch_latent_fwd_fast<T, FAM>(grid, z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, RW, KS, seed,
+                                           offset, rs, st)) {
+            ZS_LAUNCH_CHECK("k_latent_fwd_fast");
+            return ZS_OK;
+        }
         k_latent_fwd_packed<T, FAM><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, (int)K, M,
                                                                     (int)E4, RW, (int)KS, seed, offset, rs);
         ZS_LAUNCH_CHECK("k_latent_fwd_packed");
@@ -496,10 +688,169 @@ static int latent_args_ok(const void* a, int a_mode, const void* b, int b_mode, 
     return ZS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, the hot configuration (float, KBCAST parameters, 32-bit indexable).  The generic kernel above mirrors
+// autograd term by term (~50 floating-point instructions per element, 4.5 M warp instructions at config 2) and was
+// latency- AND issue-bound at 11 us for 17 MB.  Algebra first: with z = mean + std*eps and d = z - mean,
+//     d log q / d mean  through the density (+g prec d) and through the sample (-g prec d) cancel exactly,
+//     d log q / d std   = -g/std  after the same cancellation of the (g d^2 prec / std) pair,
+// so for a reparameterised node, with t = dz_up + d(log p)/dz the gradient reaching the sample from outside,
+//     dmean = sum_k t          dstd = sum_k (t * d - g_q) / std
+// and for a non-reparameterised one  dmean = sum_k g_q prec d,  dstd = sum_k g_q (d^2 prec - 1) / std.
+// The reference computes the cancelling pairs and adds them up in float32; this form has no cancellation (it is the
+// closer of the two to the float64 reference run) and ~8 instructions per element.  Four particles per thread, all
+// eight 128-bit loads issued before the first use.
+// ---------------------------------------------------------------------------------------------
+constexpr int LBF_U = 4;  // particles in flight per thread
+
+template <int FAM, bool STDP>
+__global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, 4)
+    k_latent_bwd_fast(float* __restrict__ da, float* __restrict__ db, const float* __restrict__ gq,
+                      const float* __restrict__ gp, const float* __restrict__ dz_up, const float* __restrict__ z,
+                      const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
+                      const float* __restrict__ pb, int reparam, int K, int M, int E) {
+    const int LBX = blockDim.x, LBY = blockDim.y;
+    const unsigned ME4 = ((unsigned)M * (unsigned)E) >> 2;
+    const unsigned u = blockIdx.x * LBX + threadIdx.x;
+    const bool valid = u < ME4;
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    if (valid) {
+        const unsigned m = (4u * u) / (unsigned)E;
+        const float4 av = *reinterpret_cast<const float4*>(a + 4 * (size_t)u);
+        float4 r0, r1 = make_float4(0.f, 0.f, 0.f, 0.f), pm = r1, pprec = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (FAM == FAM_NORMAL) {
+            const float4 sd = *reinterpret_cast<const float4*>(b + 4 * (size_t)u);
+            r0 = make_float4(lat_rcp(sd.x), lat_rcp(sd.y), lat_rcp(sd.z), lat_rcp(sd.w));  // 1/std
+            if (!STDP) {
+                if (pa) pm = *reinterpret_cast<const float4*>(pa + 4 * (size_t)u);
+                if (pb) {
+                    const float4 ps = *reinterpret_cast<const float4*>(pb + 4 * (size_t)u);
+                    pprec = make_float4(lat_rcp(ps.x * ps.x), lat_rcp(ps.y * ps.y), lat_rcp(ps.z * ps.z),
+                                        lat_rcp(ps.w * ps.w));
+                }
+            }
+        } else {
+            // bernoulli.py:94's autograd wrt probs: g (z / (p + eps) - (1 - z) / ((1 - p) + eps))
+            r0 = make_float4(lat_rcp(av.x + 1e-8f), lat_rcp(av.y + 1e-8f), lat_rcp(av.z + 1e-8f), lat_rcp(av.w + 1e-8f));
+            r1 = make_float4(lat_rcp((1.f - av.x) + 1e-8f), lat_rcp((1.f - av.y) + 1e-8f), lat_rcp((1.f - av.z) + 1e-8f),
+                             lat_rcp((1.f - av.w) + 1e-8f));
+        }
+        const bool path = reparam != 0 && FAM == FAM_NORMAL;
+        const bool has_du = path && dz_up != nullptr, has_gp = path && gp != nullptr;
+        for (int k0 = threadIdx.y; k0 < K; k0 += LBF_U * LBY) {
+            float g_q[LBF_U], g_p[LBF_U];
+            float4 zv[LBF_U], du[LBF_U];
+#pragma unroll
+            for (int i = 0; i < LBF_U; ++i) {
+                const int k = k0 + i * LBY;
+                const unsigned kc = (unsigned)(k < K ? k : k0);  // always in bounds
+                const unsigned r = kc * (unsigned)M + m;
+                const size_t fe = 4 * ((size_t)kc * ME4 + u);
+                g_q[i] = gq ? __ldg(gq + r) : 0.f;
+                g_p[i] = has_gp ? __ldg(gp + r) : 0.f;
+                zv[i] = *reinterpret_cast<const float4*>(z + fe);
+                du[i] = has_du ? *reinterpret_cast<const float4*>(dz_up + fe) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < LBF_U; ++i) {
+                if (k0 + i * LBY >= K) break;
+                const float g = g_q[i], h = g_p[i];
+                if (FAM == FAM_NORMAL) {
+                    const float d0 = zv[i].x - av.x, d1 = zv[i].y - av.y, d2 = zv[i].z - av.z, d3 = zv[i].w - av.w;
+                    if (path) {
+                        float t0 = du[i].x, t1 = du[i].y, t2 = du[i].z, t3 = du[i].w;
+                        if (STDP) {  // d/dz of c - z^2/2
+                            t0 = fmaf(-h, zv[i].x, t0); t1 = fmaf(-h, zv[i].y, t1);
+                            t2 = fmaf(-h, zv[i].z, t2); t3 = fmaf(-h, zv[i].w, t3);
+                        } else {
+                            t0 = fmaf(-h * pprec.x, zv[i].x - pm.x, t0); t1 = fmaf(-h * pprec.y, zv[i].y - pm.y, t1);
+                            t2 = fmaf(-h * pprec.z, zv[i].z - pm.z, t2); t3 = fmaf(-h * pprec.w, zv[i].w - pm.w, t3);
+                        }
+                        sa.x += t0; sa.y += t1; sa.z += t2; sa.w += t3;
+                        sb.x += fmaf(t0, d0, -g); sb.y += fmaf(t1, d1, -g);
+                        sb.z += fmaf(t2, d2, -g); sb.w += fmaf(t3, d3, -g);
+                    } else {  // score-function estimators: the sample carries no gradient
+                        const float e0 = d0 * r0.x, e1 = d1 * r0.y, e2 = d2 * r0.z, e3 = d3 * r0.w;  // eps
+                        sa.x += g * e0; sa.y += g * e1; sa.z += g * e2; sa.w += g * e3;   // x 1/std below
+                        sb.x += g * fmaf(e0, e0, -1.f); sb.y += g * fmaf(e1, e1, -1.f);
+                        sb.z += g * fmaf(e2, e2, -1.f); sb.w += g * fmaf(e3, e3, -1.f);
+                    }
+                } else {
+                    sa.x += g * (zv[i].x != 0.f ? r0.x : -r1.x); sa.y += g * (zv[i].y != 0.f ? r0.y : -r1.y);
+                    sa.z += g * (zv[i].z != 0.f ? r0.z : -r1.z); sa.w += g * (zv[i].w != 0.f ? r0.w : -r1.w);
+                }
+            }
+        }
+        if (FAM == FAM_NORMAL) {  // the common 1/std factor, once
+            sb.x *= r0.x; sb.y *= r0.y; sb.z *= r0.z; sb.w *= r0.w;
+            if (!path) { sa.x *= r0.x; sa.y *= r0.y; sa.z *= r0.z; sa.w *= r0.w; }
+        }
+    }
+    __shared__ float red[2][LB_Y_MAX][LB_X_MAX][4];
+    red[0][threadIdx.y][threadIdx.x][0] = sa.x; red[0][threadIdx.y][threadIdx.x][1] = sa.y;
+    red[0][threadIdx.y][threadIdx.x][2] = sa.z; red[0][threadIdx.y][threadIdx.x][3] = sa.w;
+    red[1][threadIdx.y][threadIdx.x][0] = sb.x; red[1][threadIdx.y][threadIdx.x][1] = sb.y;
+    red[1][threadIdx.y][threadIdx.x][2] = sb.z; red[1][threadIdx.y][threadIdx.x][3] = sb.w;
+    __syncthreads();
+    // fixed-order sum over the slices: thread (x, y < 8) adds up component (y & 3) of array (y >> 2)
+    if (threadIdx.y < 8 && valid) {
+        const int arr = threadIdx.y >> 2, q = threadIdx.y & 3;
+        float t = 0.f;
+        for (int sl = 0; sl < LBY; ++sl) t += red[arr][sl][threadIdx.x][q];
+        float* dst = arr == 0 ? da : (FAM == FAM_NORMAL ? db : nullptr);
+        if (dst) dst[4 * (size_t)u + q] = t;
+    }
+}
+
+template <typename T, int FAM>
+static bool launch_latent_bwd_fast(void*, void*, const void*, const void*, const void*, const void*, const void*, int,
+                                   const void*, const void*, const void*, int, int64_t, int64_t, int64_t, cudaStream_t) {
+    return false;
+}
+template <int FAM>
+static bool latent_bwd_fast_f32(void* da, void* db, const void* gq, const void* gp, const void* dz_up, const void* z,
+                                const void* a, int a_mode, const void* b, const void* pa, const void* pb, int reparam,
+                                int64_t K, int64_t M, int64_t E, cudaStream_t st) {
+    if (a_mode != ZS_KBCAST || K * M * E >= ((int64_t)1 << 31) || da == nullptr || (FAM == FAM_NORMAL && db == nullptr))
+        return false;
+    const int64_t ME4 = (M * E) >> 2;
+    const int lbx = LB_X_MAX;
+    int lby = (int)((K + LBF_U - 1) / LBF_U);
+    if (lby > LB_Y_MAX) lby = LB_Y_MAX;
+    if (lby < 8) lby = 8;  // the epilogue's eight (array, component) sums are taken by slices 0..7
+    const unsigned grid = (unsigned)((ME4 + lbx - 1) / lbx);
+    dim3 block(lbx, lby);
+    const bool stdp = pa == nullptr && pb == nullptr;
+    auto kern = stdp ? k_latent_bwd_fast<FAM, true> : k_latent_bwd_fast<FAM, false>;
+    kern<<<grid, block, 0, st>>>((float*)da, (float*)db, (const float*)gq, (const float*)gp, (const float*)dz_up,
+                                 (const float*)z, (const float*)a, (const float*)b, (const float*)pa, (const float*)pb,
+                                 reparam, (int)K, (int)M, (int)E);
+    return true;
+}
+template <>
+bool launch_latent_bwd_fast<float, FAM_NORMAL>(void* da, void* db, const void* gq, const void* gp, const void* dz_up,
+                                               const void* z, const void* a, int a_mode, const void* b, const void* pa,
+                                               const void* pb, int reparam, int64_t K, int64_t M, int64_t E,
+                                               cudaStream_t st) {
+    return latent_bwd_fast_f32<FAM_NORMAL>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st);
+}
+template <>
+bool launch_latent_bwd_fast<float, FAM_BERNOULLI>(void* da, void* db, const void* gq, const void* gp, const void* dz_up,
+                                                  const void* z, const void* a, int a_mode, const void* b,
+                                                  const void* pa, const void* pb, int reparam, int64_t K, int64_t M,
+                                                  int64_t E, cudaStream_t st) {
+    return latent_bwd_fast_f32<FAM_BERNOULLI>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st);
+}
+
 template <typename T, int FAM>
 static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp, const void* dz_up, const void* z,
                              const void* a, int a_mode, const void* b, int b_mode, const void* pa, const void* pb,
                              int reparam, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+    if (launch_latent_bwd_fast<T, FAM>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E,
+                                       as_stream(stream))) {
+        ZS_LAUNCH_CHECK("k_latent_bwd_fast");
+        return ZS_OK;
+    }
     const int64_t ME4 = (M * E) >> 2;
     // blockDim.x float4 units of [M,E] (8 = one 128-byte line per particle row; 4 when that leaves fewer than ~16
     // CTAs per SM: the grid is a few waves deep, so small CTAs keep the last wave's imbalance small)

@@ -84,13 +84,24 @@ __device__ __forceinline__ uint64_t rng_acquire(uint64_t offset, unsigned long l
     return eff;
 }
 
-// Box-Muller on two words -> two standard normals.  The radius uses logf (the SFU lg2 has an absolute
-// error that matters when u1 is within ~1e-6 of 1); the angle uses the SFU sin/cos on (-pi, pi)
-// (abs error 2^-21): the sampling kernels are instruction-bound on the noise and sincospif alone was
-// ~40 instructions.  One definition keeps every kernel's stream identical; the oracle restates it with libm.
+// Box-Muller on two words -> two standard normals, written for instruction count: the sampling kernels are
+// issue-bound on the noise (ncu round 2: 350 instructions per float4 of latents, two thirds of them RNG), and libm's
+// logf / IEEE sqrtf with their range and denormal handling were ~45 of the ~110 Box-Muller instructions per pair.
+//   w = -ln(u1):  lg2.approx has an ABSOLUTE error of 2^-22 (in log2 units) on [0.5, 2): harmless unless w itself is
+//       tiny, i.e. u1 within 2^-8 of 1, where the radius sqrt(2w) would inherit a large relative error.  There
+//       v = 1 - u1 is exact in float and -ln(1 - v) = v + v^2/2 + v^3/3 (next term < 6e-11) is used instead.
+//   radius sqrt.approx (relative error 2^-23); angle on (-pi, pi) with the SFU sin / cos (absolute error 2^-21).
+// The resulting normals are within ~2e-6 (absolute) of the libm evaluation of the same uniforms, which is how the
+// oracle restates it; one definition keeps every kernel's stream identical.
 __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float& n0, float& n1) {
     const float u1 = u01_open(r0), u2 = u01_open(r1);
-    const float rad = sqrtf(-2.0f * logf(u1));
+    const float v = 1.0f - u1;
+    float lg, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    const float w_far = lg * -0.6931471805599453f;
+    const float w_near = v * fmaf(v, fmaf(v, 0.33333334f, 0.5f), 1.0f);
+    const float w = v < 0.00390625f ? w_near : w_far;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(w + w));
     float s, c;
     __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &s, &c);
     n0 = -rad * c;  // cos(t - pi) = -cos t
