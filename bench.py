@@ -581,10 +581,13 @@ def measure_api(torch, dist, zd, be, vimco, dev, B, world, rank, steps, warm, us
     if collectives and world > 1:
         dec = torch.zeros(VAE_DECODER_PARAMS, device=dev, requires_grad=True)
         enc = torch.zeros(VAE_ENCODER_PARAMS, device=dev, requires_grad=True)
-        bucket = zd.GradientBucket([[dec], [enc]])
+        bucket = zd.GradientBucket([[dec], [enc]], backend=os.environ.get("ZS_BENCH_COMM", "auto"))
         comm = {"collectives_per_step": 2, "all_reduce_floats_per_step": int(bucket.flat.numel()),
-                "all_reduce_bytes_per_step": int(bucket.flat.numel()) * 4,
-                "what": "SUM all-reduce (NCCL) of a %d-float decoder-gradient segment, launched when dprobs is done so "
+                "all_reduce_bytes_per_step": int(bucket.flat.numel()) * 4, "backend": bucket.backend,
+                "backend_is": "peer = zs_allreduce_sum_peer, this library's kernel over NVLink peer memory; "
+                              "nccl = torch.distributed.all_reduce",
+                "peer_unavailable": getattr(bucket, "_peer_error", None),
+                "what": "SUM all-reduce of a %d-float decoder-gradient segment, launched when dprobs is done so "
                         "it overlaps the latent backward, and of a %d-float encoder-gradient segment + the scalar "
                         "objective after it; zhusuan.distributed.GradientBucket"
                         % (VAE_DECODER_PARAMS, VAE_ENCODER_PARAMS + 1)}
@@ -616,6 +619,7 @@ def run_b200_arm(args):
     vimco = args.workload == "vimco"
     B = int(args.batch)
     use_graph = bool(args.graph)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # no version banner on stdout: rank 0 prints ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29577")

@@ -339,6 +339,28 @@ int zs_sgmcmc_multi_step(int dtype, int algorithm, const zs_chain_tensor* tensor
                          double a, double b, int resample, int second_order, uint64_t seed, uint64_t offset,
                          void* rng_state, zs_stream_t stream);
 
+/* ---- peer-memory all-reduce over NVLink / NVSwitch (zs_collective.cu) ------------------------------------
+ * The exchange of the data-parallel path: SUM of a float32 buffer -- the replicated networks'
+ * parameter gradients and the scalar objective -- over the ranks of one node.  The reference has no counterpart
+ * (a user would call torch.distributed.all_reduce); for a buffer of a few MB that call is bound by NCCL's launch and
+ * protocol latency, so the exchange is a kernel of this library instead:
+ *   bufs_host[p]  : base pointer of rank p's buffer as mapped into THIS process (peer / symmetric memory; the same
+ *                   layout on every rank), p < world <= ZS_MAX_PEERS
+ *   flags_host[p] : rank p's flag area, zs_allreduce_peer_flag_bytes() bytes, zero-initialised before the first call
+ *   [first, first + count) : the floats to reduce (multiples of 4); every rank passes the same values
+ *   flag_set      : 0 .. ZS_PEER_FLAG_SETS-1; calls that may be in flight at the same time use different sets
+ *   ctas          : CTAs of the launch, the same on every rank (0 = default)
+ * Rank r reduces slice r in rank order and stores the sums into every rank's buffer: results are bit-identical on all
+ * ranks.  Enqueued on `stream`; every rank must enqueue the matching call (a CTA waits for its counterpart on every
+ * peer).  The per-CTA epochs live in the flag area, so the launch can be captured in a CUDA graph and replayed. */
+#define ZS_MAX_PEERS 8
+#define ZS_PEER_MAX_CTAS 64
+#define ZS_PEER_FLAG_SETS 4
+#define ZS_PEER_THREADS 512
+int64_t zs_allreduce_peer_flag_bytes(void);
+int zs_allreduce_sum_peer(float* const* bufs_host, void* const* flags_host, int rank, int world, int64_t first,
+                          int64_t count, int flag_set, int ctas, zs_stream_t stream);
+
 /* ---- host-buffer step (end-to-end measurement) ----
  * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers for the big
  * tensors (pinned memory recommended): what a caller whose decoder output lives in host memory

@@ -25,7 +25,7 @@ def _inputs():
                 u=rng.uniform(size=(K, B, Z)).astype(np.float32))
 
 
-def _step(dev, cols, n_global, vimco, use_bucket):
+def _step(dev, cols, n_global, vimco, use_bucket, backend="auto"):
     """One objective step on the batch columns `cols` of the shared inputs; returns (loss, decoder, leaves, bucket)."""
     import zhusuan.distributed as zd
     from zhusuan import _rng
@@ -62,7 +62,7 @@ def _step(dev, cols, n_global, vimco, use_bucket):
             return self
 
     obj = ImportanceWeightedObjective(Gen(device=dev), Var(device=dev), axis=0, estimator="vimco" if vimco else "sgvb")
-    bucket = zd.GradientBucket([dec.parameters()]) if use_bucket else None
+    bucket = zd.GradientBucket([dec.parameters()], backend=backend) if use_bucket else None
     inj = dict(uniform=[u, u]) if vimco else dict(normal=[eps, eps])
     with zd.global_batch(n_global), _rng.inject(**inj):
         loss = obj({"x": x})
@@ -72,7 +72,7 @@ def _step(dev, cols, n_global, vimco, use_bucket):
     return loss.detach(), dec, (a, b), bucket
 
 
-def _worker(rank, world, port, vimco, out):
+def _worker(rank, world, port, vimco, backend, out):
     import torch.distributed as dist
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "zhusuan-pytorch_b200")):
@@ -85,9 +85,16 @@ def _worker(rank, world, port, vimco, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         lo, hi = zd.shard_range(B)
-        loss, dec, (a, b), bucket = _step(dev, slice(lo, hi), B, vimco, True)
+        try:
+            loss, dec, (a, b), bucket = _step(dev, slice(lo, hi), B, vimco, True, backend)
+        except Exception as e:
+            if backend != "peer":
+                raise
+            out.put((rank, {"unavailable": repr(e)[:300]}))
+            dist.barrier()
+            return
         torch.cuda.synchronize()
-        res = {"loss": float(bucket.loss()), "local_loss": float(loss), "lo": lo, "hi": hi,
+        res = {"loss": float(bucket.loss()), "backend": bucket.backend, "local_loss": float(loss), "lo": lo, "hi": hi,
                "dec": [p.grad.detach().cpu().numpy() for p in dec.parameters()],
                "a": a.grad.detach().cpu().numpy(), "b": None if b is None else b.grad.detach().cpu().numpy(),
                "views": all(p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr()
@@ -99,19 +106,25 @@ def _worker(rank, world, port, vimco, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("backend", ["peer", "nccl"])
 @pytest.mark.parametrize("vimco", [False, True])
-def test_two_ranks_equal_one_gpu(vimco):
+def test_two_ranks_equal_one_gpu(vimco, backend):
+    """backend "peer": the exchange is this library's NVLink peer-memory kernel (zs_allreduce_sum_peer);
+    "nccl": torch.distributed.all_reduce on the same bucket."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29650 + (1 if vimco else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, vimco, out)) for r in range(2)]
+    port = 29650 + (1 if vimco else 0) + (2 if backend == "peer" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, vimco, backend, out)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(out.get(timeout=600) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    if "unavailable" in got[0]:
+        pytest.skip("peer-mapped memory not available on this box: " + got[0]["unavailable"])
+    assert got[0]["backend"] == backend and got[1]["backend"] == backend
     # the whole batch on one GPU, no process group: global_batch(B) is then the plain batch mean
     dev = torch.device("cuda", 0)
     loss, dec, (a, b), _ = _step(dev, slice(0, B), B, vimco, False)

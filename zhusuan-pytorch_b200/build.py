@@ -13,7 +13,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzs_b200.so")
 STAMP = os.path.join(LIBDIR, "libzs_b200.stamp")
 
-SOURCES = ["zs_lib.cu", "zs_nodes.cu", "zs_objective.cu", "zs_fused_iw.cu", "zs_latent.cu", "zs_sgmcmc.cu", "zs_categorical.cu"]
+SOURCES = ["zs_lib.cu", "zs_nodes.cu", "zs_objective.cu", "zs_fused_iw.cu", "zs_latent.cu", "zs_sgmcmc.cu", "zs_categorical.cu", "zs_collective.cu"]
 HEADERS = ["zs_common.cuh", "zs_philox.cuh", os.path.join("..", "..", "include", "zs_b200.h")]
 
 NVCC_FLAGS = [

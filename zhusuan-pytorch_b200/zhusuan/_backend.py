@@ -83,6 +83,8 @@ def _declare(lib):
         "zs_sghmc_post": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, i32, u64, u64, vp, vp]),
         "zs_sgmcmc_multi_step": (i32, [i32, i32, c.POINTER(ChainTensor), i32, dbl, dbl, dbl, i32, i32, u64, u64, vp, vp]),
         "zs_reinforce_step": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, vp]),
+        "zs_allreduce_peer_flag_bytes": (i64, []),
+        "zs_allreduce_sum_peer": (i32, [c.POINTER(vp), c.POINTER(vp), i32, i32, i64, i64, i32, i32, vp]),
         "zs_host_step_create": (i32, [c.POINTER(vp)]),
         "zs_host_step_destroy": (i32, [vp]),
         "zs_iw_step_host_workspace": (i64, [i64, i64, i64]),
@@ -615,6 +617,23 @@ def sgmcmc_multi_step(algorithm, ws, gs=None, states=None, noises=None, outs=Non
     _go("zs_sgmcmc_multi_step", dev, dtype_code(dt), int(algorithm), table, n, float(lr), float(a), float(b),
         int(bool(resample)), int(bool(second_order)), seed, offset, _ptr(rng_state))
     return outs
+
+
+# ----------------------------------------------------------------------------- peer-memory all-reduce
+MAX_PEERS, PEER_FLAG_SETS = 8, 4
+
+
+def allreduce_peer_flag_bytes():
+    return int(load().zs_allreduce_peer_flag_bytes())
+
+
+def allreduce_sum_peer(buf_ptrs, flag_ptrs, rank, first, count, flag_set, device, ctas=0):
+    """SUM-all-reduce floats [first, first + count) of the ranks' peer-mapped buffers (zs_allreduce_sum_peer) on
+    torch's current stream of `device`.  buf_ptrs / flag_ptrs: per-rank base addresses (ints) as mapped here."""
+    world = len(buf_ptrs)
+    bufs = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in buf_ptrs])
+    flags = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+    _go("zs_allreduce_sum_peer", device, bufs, flags, int(rank), world, int(first), int(count), int(flag_set), int(ctas))
 
 
 # ----------------------------------------------------------------------------- host-buffer step (e2e)

@@ -22,6 +22,7 @@ import contextlib
 import torch
 import torch.distributed as dist
 
+from . import _backend as _be
 from . import _ops, _rng
 
 # Philox offsets of different ranks are separated by this many ticks so their noise never overlaps
@@ -92,7 +93,10 @@ class GradientBucket(object):
     Without torch.distributed (or with world size 1) everything degenerates to local no-ops.
     """
 
-    def __init__(self, param_groups, device=None, dtype=None, group=None):
+    def __init__(self, param_groups, device=None, dtype=None, group=None, backend="auto"):
+        """backend: "peer" = this library's NVLink peer-memory all-reduce kernel (zs_allreduce_sum_peer; float32 CUDA
+        buffers on one node, up to 8 ranks), "nccl" / "gloo" = torch.distributed.all_reduce, "auto" = peer where it
+        is available, else torch.distributed.  `self.backend` says which one is in use."""
         groups = [[p for p in g if p.requires_grad] for g in param_groups]
         groups = [g for g in groups if g]
         self.params = [p for g in groups for p in g]
@@ -102,15 +106,33 @@ class GradientBucket(object):
         self.group = group
         sizes = [sum(p.numel() for p in g) for g in groups] or [0]
         sizes[-1] += 1  # the objective's slot
-        self.flat = torch.zeros(sum(sizes), dtype=self.dtype, device=self.device)
-        self.segments = []
-        off = 0
+        # segments start on 16-byte boundaries (the peer kernel moves float4s; it also keeps every view aligned)
+        starts, total = [], 0
         for n in sizes:
-            self.segments.append(self.flat[off:off + n])
-            off += n
+            starts.append(total)
+            total += (n + 3) // 4 * 4
+        self._peer = None
+        self.backend = "local"
+        if is_initialized() and dist.get_world_size(group) > 1:
+            self.backend = dist.get_backend(group)
+            if backend in ("auto", "peer"):
+                try:
+                    self._peer = _PeerBuffer(total, self.device, self.dtype, group)
+                    self.backend = "peer"
+                except Exception as e:  # no peer access / symmetric memory: torch.distributed does the exchange
+                    if backend == "peer":
+                        raise
+                    self._peer_error = repr(e)
+        self.flat = self._peer.flat if self._peer is not None else torch.zeros(total, dtype=self.dtype,
+                                                                                  device=self.device)
+        self.segments, self._ranges = [], []
+        for st, n in zip(starts, sizes):
+            self.segments.append(self.flat[st:st + n])
+            self._ranges.append((st, (n + 3) // 4 * 4))
+        self._comm_stream = None
         self._views, self._seg_of, self._pending, self._works = {}, {}, [], []
-        off = 0
         for si, g in enumerate(groups):
+            off = starts[si]
             for p in g:
                 v = self.flat[off:off + p.numel()].view_as(p)
                 if p.grad is not None:
@@ -134,7 +156,7 @@ class GradientBucket(object):
 
     @property
     def loss_slot(self):
-        return self.flat[-1:]
+        return self.segments[-1][-1:]
 
     def _on_grad(self, p):
         v = self._views.get(id(p))
@@ -150,8 +172,21 @@ class GradientBucket(object):
             self._launch(si)
 
     def _launch(self, si):
-        if is_initialized() and dist.get_world_size(self.group) > 1:
+        if not (is_initialized() and dist.get_world_size(self.group) > 1):
+            return
+        if self._peer is None:
             self._works.append(dist.all_reduce(self.segments[si], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        # this library's kernel, on a side stream ordered after what the compute stream has enqueued so far: the
+        # exchange overlaps whatever backward launches next; finish() joins the streams
+        cur = torch.cuda.current_stream(self.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        self._comm_stream.wait_stream(cur)
+        first, count = self._ranges[si]
+        with torch.cuda.stream(self._comm_stream):
+            self._peer.all_reduce(first, count, flag_set=si % _be.PEER_FLAG_SETS)
+        self._works.append(_StreamJoin(self._comm_stream, self.device))
 
     def reduce_segment(self, si):
         """Launch segment `si`'s all-reduce now (for loops that write gradients without autograd hooks)."""
@@ -169,7 +204,47 @@ class GradientBucket(object):
 
     def loss(self):
         """The all-reduced objective (valid after finish())."""
-        return self.flat[-1]
+        return self.segments[-1][-1]
+
+
+class _StreamJoin(object):
+    """`.wait()` of a launch on a side stream: the current stream waits for it (no host blocking)."""
+
+    def __init__(self, stream, device):
+        self.stream, self.device = stream, device
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
+class _PeerBuffer(object):
+    """A float32 buffer in peer-mapped (symmetric) device memory plus the flag area of zs_allreduce_sum_peer.
+    torch.distributed._symmetric_memory does the plumbing -- allocation and the exchange of the mappings between the
+    ranks of the group; the data movement is this library's kernel."""
+
+    def __init__(self, n, device, dtype, group):
+        import torch.distributed._symmetric_memory as symm
+        if dtype != torch.float32 or torch.device(device).type != "cuda":
+            raise RuntimeError("the peer all-reduce takes float32 CUDA buffers")
+        pg = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(pg)
+        if self.world > _be.MAX_PEERS:
+            raise RuntimeError("the peer all-reduce takes at most %d ranks" % _be.MAX_PEERS)
+        flag_floats = (_be.allreduce_peer_flag_bytes() + 3) // 4
+        n_pad = (n + 3) // 4 * 4
+        self.storage = symm.empty(n_pad + flag_floats, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.storage, pg.group_name)
+        self.storage.zero_()
+        self.rank = self.handle.rank
+        self.buf_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.flag_ptrs = [p + 4 * n_pad for p in self.buf_ptrs]
+        self.flat = self.storage[:n]
+        self.device = self.storage.device
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=pg)  # every rank's flags are zero before anyone's first kernel signals
+
+    def all_reduce(self, first, count, flag_set=0):
+        _be.allreduce_sum_peer(self.buf_ptrs, self.flag_ptrs, self.rank, first, count, flag_set, self.device)
 
 
 _legacy_buckets = {}
@@ -202,4 +277,7 @@ def all_reduce_gradients(params, n_local=None, n_global=None, group=None):
     if n_local is not None and n_global is not None and float(n_local) != float(n_global):
         b.flat.mul_(float(n_local) / float(n_global))
     if is_initialized():
-        dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=group)
+        if b._peer is not None:
+            b._peer.all_reduce(0, (b.flat.numel() + 3) // 4 * 4)
+        else:
+            dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=group)
