@@ -1,0 +1,62 @@
+"""SUM all-reduce of the data-parallel step's gradient buffer: this library's peer-memory kernel (zs_allreduce_sum_peer)
+against torch.distributed.all_reduce (NCCL), per call, on N ranks of one box.  Run under torchrun:
+    python -m torch.distributed.run --nproc-per-node N tools/allreduce_bench.py
+Rank 0 prints one JSON line per size."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "zhusuan-pytorch_b200"))
+import torch
+import torch.distributed as dist
+import zhusuan.distributed as zd
+
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+
+def timed(fn, reps=200, warm=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+for n in (4, 663784, 1346868):
+    peer = zd._PeerBuffer(n, dev, torch.float32, None)
+    peer.flat.fill_(float(rank + 1))
+    torch.cuda.synchronize(); dist.barrier()
+    peer.all_reduce(0, (n + 3) // 4 * 4)
+    torch.cuda.synchronize()
+    ok = bool((peer.flat == world * (world + 1) / 2).all())
+    res = {"floats": n, "world": world, "peer_correct": ok}
+    for ctas in (16, 32, 64):
+        import zhusuan._backend as be
+        res["peer_us_ctas%d" % ctas] = round(timed(lambda: be.allreduce_sum_peer(peer.buf_ptrs, peer.flag_ptrs, peer.rank, 0,
+                                                                                   (n + 3) // 4 * 4, 0, dev, ctas)), 2)
+    t = torch.ones(n, device=dev)
+    res["nccl_us"] = round(timed(lambda: dist.all_reduce(t)), 2)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(10):
+                dist.all_reduce(t)
+    torch.cuda.current_stream().wait_stream(s)
+    res["nccl_us_in_graph"] = round(timed(g.replay, reps=30, warm=3) / 10, 2)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    del peer
+dist.destroy_process_group()

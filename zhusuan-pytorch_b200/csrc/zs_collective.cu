@@ -48,6 +48,12 @@ __host__ __device__ inline size_t epoch_index(int set, int cta) {
     return (size_t)ZS_PEER_FLAG_SETS * 2 * ZS_PEER_MAX_CTAS * ZS_MAX_PEERS + (size_t)set * ZS_PEER_MAX_CTAS + cta;
 }
 
+// WORLD ranks (compile time: 2, 4 or 8; a smaller world leaves table entries unused), U float4 per thread and rank in
+// flight.  The first version (one float4 per thread and rank per iteration, 32 CTAs) took ~30 us for 2.7 MB at
+// N = 2: every iteration is an NVLink round trip (~2 us) and a thread went through ~20 of them one after the other.
+// Here WORLD x U = 16 loads are issued before the first use and 64 CTAs x 512 threads cover a 2.7 MB slice in ONE
+// iteration: the launch costs two flag barriers plus about one round trip.
+template <int WORLD, int U>
 __global__ void __launch_bounds__(ZS_PEER_THREADS)
     k_allreduce_peer(const __grid_constant__ PeerTable tab, int rank, int world, long long first, long long count,
                      int set) {
@@ -67,19 +73,29 @@ __global__ void __launch_bounds__(ZS_PEER_THREADS)
     const long long units = count >> 2;                   // count % 4 == 0 (checked by the launcher)
     const long long per = (units + world - 1) / world;
     const long long lo = (long long)rank * per, hi = lo + per < units ? lo + per : units;
-    for (long long i = lo + (long long)cta * blockDim.x + tid; i < hi; i += (long long)gridDim.x * blockDim.x) {
-        const long long off = first + 4 * i;
-        float4 v[ZS_MAX_PEERS];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = lo + (long long)cta * blockDim.x + tid; i0 < hi; i0 += stride * U) {
+        float4 v[WORLD][U];
 #pragma unroll
-        for (int p = 0; p < ZS_MAX_PEERS; ++p)
-            if (p < world) v[p] = ld_peer(tab.buf[p] + off);
-        float4 s = v[0];
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
 #pragma unroll
-        for (int p = 1; p < ZS_MAX_PEERS; ++p)
-            if (p < world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+            for (int p = 0; p < WORLD; ++p)
+                if (p < world && i < hi) v[p][u] = ld_peer(tab.buf[p] + first + 4 * i);
+        }
 #pragma unroll
-        for (int p = 0; p < ZS_MAX_PEERS; ++p)
-            if (p < world) st_peer(tab.buf[p] + off, s);
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
+                float4 s = v[0][u];
+#pragma unroll
+                for (int p = 1; p < WORLD; ++p)
+                    if (p < world) { s.x += v[p][u].x; s.y += v[p][u].y; s.z += v[p][u].z; s.w += v[p][u].w; }
+#pragma unroll
+                for (int p = 0; p < WORLD; ++p)
+                    if (p < world) st_peer(tab.buf[p] + first + 4 * i, s);
+            }
+        }
     }
     // ---- barrier 1: my pushes are visible everywhere; every peer's pushes into my buffer are too
     __threadfence_system();
@@ -120,10 +136,10 @@ int zs_allreduce_sum_peer(float* const* bufs_host, void* const* flags_host, int 
             return ZS_ERR_ARG;
         }
     }
-    if (ctas <= 0) ctas = 32;
+    if (ctas <= 0) ctas = 64;
     if (ctas > ZS_PEER_MAX_CTAS) ctas = ZS_PEER_MAX_CTAS;
-    k_allreduce_peer<<<ctas, ZS_PEER_THREADS, 0, as_stream(stream)>>>(tab, rank, world, (long long)first,
-                                                                     (long long)count, flag_set);
+    auto kern = world <= 2 ? k_allreduce_peer<2, 8> : (world <= 4 ? k_allreduce_peer<4, 4> : k_allreduce_peer<8, 2>);
+    kern<<<ctas, ZS_PEER_THREADS, 0, as_stream(stream)>>>(tab, rank, world, (long long)first, (long long)count, flag_set);
     ZS_LAUNCH_CHECK("k_allreduce_peer");
     return ZS_OK;
 }
