@@ -819,6 +819,14 @@ static bool latent_bwd_fast_f32(void* da, void* db, const void* gq, const void* 
     if (lby > LB_Y_MAX) lby = LB_Y_MAX;
     if (lby < 8) lby = 8;  // the epilogue's eight (array, component) sums are taken by slices 0..7
     const unsigned grid = (unsigned)((ME4 + lbx - 1) / lbx);
+    // Wave quantisation: at 64 registers an SM holds 32 warps.  A grid slightly larger than what is resident at once
+    // (config 2: 1280 CTAs of 4 warps on 148 x 8 slots, "1.08 waves") runs its last few CTAs alone and doubles the
+    // kernel's duration (ncu round 2: SMs active 52 % of 9.9 us).  Halve the slices (each thread then walks twice
+    // as many particles, still four at a time) until the grid is resident in one go.
+    {
+        const int64_t warp_slots = (int64_t)sm_count() * 32;
+        while (lby > 8 && (int64_t)grid * ((lbx * lby + 31) / 32) > warp_slots) lby = (lby + 1) / 2 < 8 ? 8 : (lby + 1) / 2;
+    }
     dim3 block(lbx, lby);
     const bool stdp = pa == nullptr && pb == nullptr;
     auto kern = stdp ? k_latent_bwd_fast<FAM, true> : k_latent_bwd_fast<FAM, false>;
