@@ -451,7 +451,7 @@ def make_api_step(torch, vimco, leaves, device, B, world=1, bucket=None):
     gen, var = Gen(device=device), Var(device=device)
     obj = ImportanceWeightedObjective(gen, var, axis=0, estimator="vimco" if vimco else "sgvb")
     grads = [t for t in (probs, a, b) if t is not None]
-    if bucket is not None:
+    if bucket is not None and len(bucket.segments) > 1:
         # the decoder's parameter gradients are complete once dprobs has gone through the decoder's backward: launch
         # their all-reduce at that point, so it overlaps the latent nodes' backward (and, in a real model, the encoder's)
         probs.register_post_accumulate_grad_hook(lambda p: bucket.reduce_segment(0))
@@ -581,16 +581,18 @@ def measure_api(torch, dist, zd, be, vimco, dev, B, world, rank, steps, warm, us
     if collectives and world > 1:
         dec = torch.zeros(VAE_DECODER_PARAMS, device=dev, requires_grad=True)
         enc = torch.zeros(VAE_ENCODER_PARAMS, device=dev, requires_grad=True)
-        bucket = zd.GradientBucket([[dec], [enc]], backend=os.environ.get("ZS_BENCH_COMM", "auto"))
-        comm = {"collectives_per_step": 2, "all_reduce_floats_per_step": int(bucket.flat.numel()),
+        two = os.environ.get("ZS_BENCH_SEGMENTS", "1") == "2"
+        bucket = zd.GradientBucket([[dec], [enc]] if two else [[dec, enc]], backend=os.environ.get("ZS_BENCH_COMM", "auto"))
+        comm = {"collectives_per_step": 2 if two else 1, "all_reduce_floats_per_step": int(bucket.flat.numel()),
                 "all_reduce_bytes_per_step": int(bucket.flat.numel()) * 4, "backend": bucket.backend,
                 "backend_is": "peer = zs_allreduce_sum_peer, this library's kernel over NVLink peer memory; "
                               "nccl = torch.distributed.all_reduce",
                 "peer_unavailable": getattr(bucket, "_peer_error", None),
-                "what": "SUM all-reduce of a %d-float decoder-gradient segment, launched when dprobs is done so "
-                        "it overlaps the latent backward, and of a %d-float encoder-gradient segment + the scalar "
-                        "objective after it; zhusuan.distributed.GradientBucket"
-                        % (VAE_DECODER_PARAMS, VAE_ENCODER_PARAMS + 1)}
+                "what": "every step: SUM all-reduce of the example VAE's %d decoder + %d encoder parameter gradients and "
+                        "the scalar objective, one bucket (what a 25 MB DDP bucket would hold), launched when backward "
+                        "is done; zhusuan.distributed.GradientBucket.  ZS_BENCH_SEGMENTS=2: decoder segment launched "
+                        "when dprobs is done (overlaps the latent backward), encoder segment after it"
+                        % (VAE_DECODER_PARAMS, VAE_ENCODER_PARAMS)}
     step = make_api_step(torch, vimco, leaves, dev, B, world, bucket)
     run, how, launches = capture(torch, step, dev, use_graph, count=lambda: be.launch_count)
     ms, by_rank, wall = time_steps(torch, dist, run, steps, warm, world)

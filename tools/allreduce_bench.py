@@ -43,6 +43,16 @@ for n in (4, 663784, 1346868):
         import zhusuan._backend as be
         res["peer_us_ctas%d" % ctas] = round(timed(lambda: be.allreduce_sum_peer(peer.buf_ptrs, peer.flag_ptrs, peer.rank, 0,
                                                                                    (n + 3) // 4 * 4, 0, dev, ctas)), 2)
+    # the kernel itself, without the host's launch cost: 10 launches per graph replay
+    gp = torch.cuda.CUDAGraph()
+    sp = torch.cuda.Stream()
+    sp.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(sp):
+        with torch.cuda.graph(gp, stream=sp):
+            for _ in range(10):
+                be.allreduce_sum_peer(peer.buf_ptrs, peer.flag_ptrs, peer.rank, 0, (n + 3) // 4 * 4, 1, dev, 64)
+    torch.cuda.current_stream().wait_stream(sp)
+    res["peer_us_in_graph"] = round(timed(gp.replay, reps=30, warm=3) / 10, 2)
     t = torch.ones(n, device=dev)
     res["nccl_us"] = round(timed(lambda: dist.all_reduce(t)), 2)
     g = torch.cuda.CUDAGraph()
@@ -58,5 +68,9 @@ for n in (4, 663784, 1346868):
     res["nccl_us_in_graph"] = round(timed(g.replay, reps=30, warm=3) / 10, 2)
     if rank == 0:
         print(json.dumps(res), flush=True)
-    del peer
-dist.destroy_process_group()
+    keep = globals().setdefault("_keep", [])
+    keep.append((peer, gp, g))  # peer-mapped buffers stay alive until every rank is done
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+os._exit(0)  # skip the teardown of symmetric memory / NCCL (the previous version of this tool hung there)

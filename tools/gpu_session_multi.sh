@@ -5,15 +5,16 @@
 TAG=${1:-r2n}; N=${2:-2}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multirank.py tests/test_gpu_round2.py -m gpu -q -k "two_ranks or non_current_device" > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
+timeout 400 python -m pytest tests/test_gpu_multirank.py tests/test_gpu_round2.py -m gpu -q -k "two_ranks or non_current_device" > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -4 $OUT/${TAG}_pytest.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 \
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 \
     tools/allreduce_bench.py > $OUT/${TAG}_allreduce_n$N.jsonl 2> $OUT/${TAG}_allreduce_n$N.err; echo "allreduce bench rc=$?"; cat $OUT/${TAG}_allreduce_n$N.jsonl
 QUICK="--no-e2e --no-secondary --no-cpu-baseline"
 for n in $(seq 2 $N | awk -v N=$N '$1==2||$1==4||$1==8'); do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29611 \
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29611 \
       bench.py --gpus $n --steps 1000 --warmup 100 $QUICK > $OUT/${TAG}_bench_n$n.json 2> $OUT/${TAG}_bench_n$n.err; echo "bench n=$n rc=$?"
 done
+if [ "${3:-}" != "diag" ]; then ls -la $OUT | grep ${TAG}; exit 0; fi
 # N = 1 with and without a 1-rank NCCL communicator: step time and per-kernel durations
 timeout 300 python bench.py --steps 1000 --warmup 100 $QUICK --no-strong > $OUT/${TAG}_n1_nopg.json 2> $OUT/${TAG}_n1_nopg.err
 ZS_BENCH_FORCE_PG=1 timeout 300 python bench.py --steps 1000 --warmup 100 $QUICK --no-strong > $OUT/${TAG}_n1_pg.json 2> $OUT/${TAG}_n1_pg.err

@@ -10,7 +10,7 @@
 //     element in flight together), adds them up in rank order (the result is bit-identical on all ranks, whatever
 //     the world size) and stores the sum into slice r of every rank's buffer -- a reduce-scatter and an all-gather
 //     in one pass, each byte crossing NVLink once in each direction;
-//   * two flag barriers per CTA (peers' data ready / peers' pushes landed) with release / acquire at system scope;
+//   * two flag barriers per CTA (peers' data ready / peers' pushes landed), system-scope flags;
 //     a CTA of rank r only ever talks to the same-numbered CTA of the other ranks, so nothing is grid-wide.  Flags
 //     carry a per-CTA epoch kept in device memory, so a captured CUDA graph can replay the launch.
 // No NCCL kernel, no staging copy, no host involvement.
@@ -23,12 +23,18 @@ struct PeerTable {
     unsigned* flags[ZS_MAX_PEERS];
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Flags are written and polled with relaxed system-scope accesses; the ordering they need is provided around them:
+//   barrier 0 publishes nothing (what the peers read was written by EARLIER kernels of this stream, complete and
+//             visible at the home L2 before this kernel started) and the data loads that follow are volatile, i.e. they
+//             are served by the owner's L2, never by a stale local cache line;
+//   barrier 1 every thread fences at system scope after its pushes (they must have landed before the flag does); what
+//             was pushed into this rank's buffer is read by LATER kernels of this stream.
+__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float4 ld_peer(const float* p) {
@@ -65,8 +71,8 @@ __global__ void __launch_bounds__(ZS_PEER_THREADS)
     const unsigned e = s_epoch;
     // ---- barrier 0: my earlier work on this stream is done (this kernel is running); so is every peer's
     if (tid < world && tid != rank) {
-        st_release_sys(tab.flags[tid] + flag_index(set, 0, cta, rank), e);
-        while ((int)(ld_acquire_sys(mine + flag_index(set, 0, cta, tid)) - e) < 0) {}
+        st_flag(tab.flags[tid] + flag_index(set, 0, cta, rank), e);
+        while ((int)(ld_flag(mine + flag_index(set, 0, cta, tid)) - e) < 0) {}
     }
     __syncthreads();
     // ---- slice `rank` of [first, first + count): float4 units, the last slice takes the remainder
@@ -101,8 +107,8 @@ __global__ void __launch_bounds__(ZS_PEER_THREADS)
     __threadfence_system();
     __syncthreads();
     if (tid < world && tid != rank) {
-        st_release_sys(tab.flags[tid] + flag_index(set, 1, cta, rank), e);
-        while ((int)(ld_acquire_sys(mine + flag_index(set, 1, cta, tid)) - e) < 0) {}
+        st_flag(tab.flags[tid] + flag_index(set, 1, cta, rank), e);
+        while ((int)(ld_flag(mine + flag_index(set, 1, cta, tid)) - e) < 0) {}
     }
     __syncthreads();
     if (tid == 0) mine[epoch_index(set, cta)] = e;
