@@ -49,7 +49,7 @@ enum { ZS_F32 = 0, ZS_F64 = 1 };
 enum { ZS_FULL = 0, ZS_KBCAST = 1, ZS_SCALAR = 2 };
 enum { ZS_EST_SGVB = 0, ZS_EST_VIMCO = 1, ZS_EST_ELBO = 2 };
 /* location-scale families of the zs_locscale_* entry points */
-enum { ZS_FAM_LOGISTIC = 1, ZS_FAM_LAPLACE = 2 };
+enum { ZS_FAM_LOGISTIC = 1, ZS_FAM_LAPLACE = 2, ZS_FAM_UNIFORM = 3 };
 
 enum {
     ZS_OK = 0,
@@ -138,7 +138,11 @@ int zs_normal_logprob_bwd(int dtype, void* dx, void* dmean, void* dstd, const vo
  * _sample_bwd: dloc = sum_k dz, dscale = sum_k dz * eps (KBCAST) or elementwise (FULL), eps regenerated from
  * (seed, offset) or from `u`.
  * _logprob_fwd: out[K,M] = sum_e log p(x; loc, scale):  Logistic -z - 2 softplus(-z) - log(scale), z = (x-loc)/scale
- * (logistic.py:72-83);  Laplace -log(2 scale) - |x - loc| / scale (laplace.py:78-92).  _logprob_bwd: autograd of those. */
+ * (logistic.py:72-83);  Laplace -log(2 scale) - |x - loc| / scale (laplace.py:78-92).  _logprob_bwd: autograd of those.
+ * ZS_FAM_UNIFORM (Uniform, zhusuan/distributions/uniform.py:51-83): _sample draws u ~ U[0,1) (torch.rand, :63-66) and
+ * returns loc + scale * u (pass loc = low, scale = high - low; or 0 / 1 for the unit draw the reference caches);
+ * _logprob_* take loc = LOW and scale = HIGH: -log(high - low) on [low, high), -inf outside
+ * (torch.distributions.Uniform.log_prob, :81), d/dlow = g/(high - low), d/dhigh = -g/(high - low), d/dx = 0. */
 int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_mode, const void* scale, int scale_mode,
                        const void* u_in, int64_t K, int64_t N, uint64_t seed, uint64_t offset, void* rng_state,
                        void* rng_snapshot, zs_stream_t stream);
@@ -240,6 +244,12 @@ int zs_reinforce_step(int dtype, void* cost, void* dlogp, void* dlogq, float* mo
                       const void* logp, const void* logq, int64_t N, double decay, double grad_scale,
                       zs_stream_t stream);
 
+/* out[0] = scale_a * sum(a[0..na)) + scale_b * sum(b[0..nb)), one launch, fixed summation order.  ELBO.sgvb with a flow
+ * (zhusuan/variational/elbo.py:155-161) returns -mean(logp - logq) - sum(log_det): with the per-column costs of
+ * zs_iw_objective(ZS_EST_ELBO) as `a` (scale_a = 1/B) and the flow's log-determinants as `b` (scale_b = -1) this is the
+ * whole reduction; d out / d a_i = scale_a, d out / d b_i = scale_b.                                    */
+int zs_combine_sums(int dtype, void* out, const void* a, int64_t na, double scale_a, const void* b, int64_t nb,
+                    double scale_b, zs_stream_t stream);
 /* log_mean_exp over the leading axis of [K,B] -> [B]   (zhusuan/utils.py:6-21)    */
 int zs_log_mean_exp(int dtype, void* out, const void* x, int64_t K, int64_t B, zs_stream_t stream);
 /* backward: dx[K,B] = g[B] * softmax_k(x)                                          */

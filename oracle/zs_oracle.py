@@ -185,13 +185,15 @@ def iw_bernoulli_logits_step(estimator, logits, x, logp_other, logq, grad_scale=
 
 
 # --------------------------------------------------------------------------- Logistic / Laplace (numpy restatement)
-LOGISTIC, LAPLACE = 1, 2
+LOGISTIC, LAPLACE, UNIFORM = 1, 2, 3
 
 
 def locscale_noise(family, u):
     """eps of z = loc + scale * eps.  Logistic: log u - log(1 - u), u ~ U(0,1) (zhusuan/distributions/logistic.py:66-67);
     Laplace: -sign(u) log1p(-|u|), u ~ U(-1,1) (torch.distributions.Laplace.sample, called by laplace.py:74)."""
     u = np.asarray(u)
+    if family == UNIFORM:  # Uniform draws u ~ U[0,1) itself (torch.rand; zhusuan/distributions/uniform.py:63-66)
+        return u
     if family == LOGISTIC:
         return (np.log(u) - np.log(1 - u)).astype(u.dtype)
     return (-np.sign(u) * np.log1p(-np.abs(u))).astype(u.dtype)
@@ -219,7 +221,10 @@ def _softplus(v):
 def locscale_logprob_fwd(family, x, loc, scale, K, M, E):
     dt = np.result_type(x, loc, scale).type
     x, loc, scale = (np.broadcast_to(np.asarray(a, dt).reshape((-1, M, E)), (K, M, E)) for a in (x, loc, scale))
-    if family == LOGISTIC:
+    if family == UNIFORM:  # loc = low, scale = high: torch.distributions.Uniform.log_prob (uniform.py:81)
+        with np.errstate(divide="ignore"):
+            lp = np.log(((loc <= x) & (x < scale)).astype(dt)) - np.log(scale - loc)
+    elif family == LOGISTIC:
         z = (x - loc) / scale                                          # logistic.py:81
         lp = -z - 2 * _softplus(-z) - np.log(scale)                    # logistic.py:82
     else:
@@ -234,6 +239,12 @@ def locscale_logprob_bwd(family, g, x, loc, scale, K, M, E):
     shapes = [np.asarray(a).reshape((-1, M, E)).shape for a in (x, loc, scale)]
     x, loc, scale = (np.broadcast_to(np.asarray(a, dt).reshape((-1, M, E)), (K, M, E)) for a in (x, loc, scale))
     g = np.asarray(g, dt).reshape(K, M, 1)
+    if family == UNIFORM:  # autograd sees only -log(high - low): (dx, dlow, dhigh) = (0, g/(high-low), -g/(high-low))
+        r = (g / (scale - loc)).astype(dt)
+        outs = []
+        for grad, shp in zip((np.zeros_like(r), r, -r), shapes):
+            outs.append(grad if shp[0] == K and K > 1 or shp == (K, M, E) else grad.sum(0, keepdims=True).astype(dt))
+        return tuple(o.reshape(s_) for o, s_ in zip(outs, shapes))
     if family == LOGISTIC:
         z = (x - loc) / scale
         with np.errstate(over="ignore"):

@@ -367,6 +367,48 @@ def gen_locscale():
     save("locscale", **out)
 
 
+# --------------------------------------------------------------------------- Uniform
+def gen_uniform():
+    """Uniform node: log_prob + gradients with parameters broadcast over particles (values on the boundaries included),
+    and both sampling branches with injected unit uniforms (torch.rand patched), INCLUDING what the reference leaves in
+    `sample_cache` and what `log_prob(None)` then evaluates -- the quirks of uniform.py:51-68."""
+    from zhusuan.distributions.uniform import Uniform
+    rng = np.random.RandomState(31)
+    K, M, E = 5, 6, 8
+    low64 = rng.standard_normal((M, E)) - 1.0
+    span64 = np.exp(0.5 * rng.standard_normal((M, E))) + 1.5      # > 1: the unscaled u of a draw stays inside [low, high]
+    low64 = np.minimum(low64, -0.05)                               # low < 0 < 1 < high  (u in [0,1) is in the support)
+    high64 = np.maximum(low64 + span64, 1.05)
+    t01 = rng.uniform(size=(K, M, E))
+    x64 = low64 + t01 * (high64 - low64)
+    x64.reshape(K, -1)[0, 0] = low64.reshape(-1)[0]                # x == low : inside  (-log(high - low))
+    x64.reshape(K, -1)[1, 1] = high64.reshape(-1)[1]               # x == high: -inf   (log(0))
+    g64 = rng.standard_normal((K, M))
+    u64 = rng.uniform(size=(K, M, E))
+    dz64 = rng.standard_normal((K, M, E))
+    out = dict(x=x64, low=low64, high=high64, g=g64, u=u64, dz=dz64)
+    for dn, dt in DT.items():
+        low, high = t(low64, dt, True), t(high64, dt, True)
+        d = Uniform(low=low, high=high, group_ndims=1)
+        lp = d.log_prob(t(x64, dt))
+        finite = torch.isfinite(lp)
+        gr = torch.autograd.grad(lp, [low, high], grad_outputs=t(g64, dt))
+        out.update({"%s_lp" % dn: npy(lp), "%s_dlow" % dn: npy(gr[0]), "%s_dhigh" % dn: npy(gr[1])})
+        assert not bool(finite.all())  # the x == high corner really is -inf in the reference
+        u = t(u64, dt)
+        for name, reparam in (("rep", True), ("norep", False)):
+            low, high = t(low64, dt, True), t(high64, dt, True)
+            d = Uniform(low=low, high=high, is_reparameterized=reparam)
+            with mock.patch("torch.rand", lambda *a, **k: u.clone()):
+                z = d.sample(K)
+            gr = torch.autograd.grad(z, [low, high], grad_outputs=t(dz64, dt))
+            out.update({"%s_%s_z" % (dn, name): npy(z), "%s_%s_cache" % (dn, name): npy(d.sample_cache),
+                        "%s_%s_dlow" % (dn, name): npy(gr[0]), "%s_%s_dhigh" % (dn, name): npy(gr[1])})
+            if reparam:
+                out["%s_rep_lp_cache" % dn] = npy(d.log_prob(None))  # evaluated at the UNSCALED draw
+    save("uniform", **out)
+
+
 # --------------------------------------------------------------------------- VAE ELBO (cfg 1 shapes, small)
 def gen_elbo_path():
     rng = np.random.RandomState(16)
@@ -409,6 +451,61 @@ def gen_elbo_path():
         dm, ds, dp = torch.autograd.grad(loss, [m, s, probs])
         out.update({dn + "_loss": npy(loss), dn + "_dmean": npy(dm), dn + "_dstd": npy(ds), dn + "_dprobs": npy(dp)})
     save("elbo_path", **out)
+
+
+# --------------------------------------------------------------------------- ELBO with a flow (elbo.py:90-119,155-161)
+def gen_elbo_flow():
+    """ELBO(transform=...) with K particles: the variational sample goes through an elementwise affine flow
+    z' = z * exp(s) + t whose log-determinant [K, B] enters the objective as  + sum(log_det)  (elbo.py:159-160)."""
+    rng = np.random.RandomState(17)
+    K, B, Z, X = 4, 5, 6, 8
+    mean64 = 0.5 * rng.standard_normal((B, Z))
+    std64 = np.exp(0.3 * rng.standard_normal((B, Z)))
+    s64 = 0.2 * rng.standard_normal((Z,))
+    t64 = 0.3 * rng.standard_normal((Z,))
+    w64 = 0.4 * rng.standard_normal((Z, X))
+    x64 = (rng.uniform(size=(B, X)) < 0.5).astype(np.float64)
+    eps64 = rng.standard_normal((K, B, Z))
+    out = dict(mean=mean64, std=std64, s=s64, t=t64, w=w64, x=x64, eps=eps64, K=np.int64(K))
+
+    class G(BayesianNet):
+        def __init__(self, w):
+            super().__init__()
+            self.w = w
+
+        def forward(self, observed):
+            self.observe(observed)
+            dt = self.w.dtype
+            z = self.normal("z", mean=torch.zeros([B, Z], dtype=dt), std=torch.ones([B, Z], dtype=dt), n_samples=K,
+                            reduce_sum_dims=[2])
+            self.bernoulli("x", probs=torch.sigmoid(torch.matmul(z, self.w)), reduce_sum_dims=[2])
+            return self
+
+    class V(BayesianNet):
+        def __init__(self, m, s):
+            super().__init__()
+            self.m, self.s = m, s
+
+        def forward(self, observed):
+            self.observe(observed)
+            self.normal("z", mean=self.m, std=self.s, n_samples=K, reduce_sum_dims=[2])
+            return self
+
+    for dn, dt in DT.items():
+        m, sd, sc, sh, w = (t(a, dt, True) for a in (mean64, std64, s64, t64, w64))
+        eps = t(eps64, dt)
+
+        def flow(inputs):
+            (z,) = inputs
+            return {"z": z * torch.exp(sc) + sh}, sc.sum().expand(z.shape[0], z.shape[1])
+
+        with mock.patch("torch.normal", lambda *a, **k: eps.clone()):
+            loss = ELBO(G(w), V(m, sd), transform=flow, transform_var=["z"])({"x": t(x64, dt)})
+        grads = torch.autograd.grad(loss, [m, sd, sc, sh, w])
+        out[dn + "_loss"] = npy(loss)
+        for name, gr in zip(("dmean", "dstd", "ds", "dt", "dw"), grads):
+            out[dn + "_" + name] = npy(gr)
+    save("elbo_flow", **out)
 
 
 # --------------------------------------------------------------------------- SG-MCMC
@@ -596,6 +693,8 @@ if __name__ == "__main__":
     gen_iw_path()
     gen_logits_path()
     gen_locscale()
+    gen_uniform()
     gen_elbo_path()
+    gen_elbo_flow()
     gen_sgmcmc()
     gen_bnn()

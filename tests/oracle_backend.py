@@ -178,6 +178,11 @@ def iw_objective(estimator, logp, logq, grad_scale, extra=None, need_grads=True)
     return _t(cost, logp), _t(dlp, logp), _t(dlq, logp)
 
 
+def combine_sums(a, scale_a, b, scale_b):
+    v = scale_a * _np(a).astype(np.float64).sum() + scale_b * _np(b).astype(np.float64).sum()
+    return torch.tensor([v], dtype=a.dtype)
+
+
 def log_mean_exp(x):
     return _t(O.log_mean_exp(_np(x)), x)
 
@@ -321,7 +326,7 @@ def install(monkeypatch):
                  "bernoulli_latent_fwd", "bernoulli_latent_bwd", "bernoulli_sample",
                  "bernoulli_logpmf_fwd", "bernoulli_logpmf_bwd", "locscale_sample", "locscale_sample_bwd",
                  "locscale_logprob_fwd", "locscale_logprob_bwd", "categorical_sample", "categorical_logpmf_fwd",
-                 "categorical_logpmf_bwd", "iw_objective", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
+                 "categorical_logpmf_bwd", "iw_objective", "combine_sums", "log_mean_exp", "log_mean_exp_bwd", "fused_supported",
                  "iw_bernoulli_fused", "reinforce_step", "scale_inplace", "philox_normal", "sgld_step", "psgld_step", "sghmc_pre",
                  "sghmc_post", "sgmcmc_multi_step"):
         monkeypatch.setattr(_backend, name, globals()[name])

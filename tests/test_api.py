@@ -584,6 +584,96 @@ def test_locscale_distributions_against_reference_golden(dev, golden, name):
             Logistic(loc=torch.zeros(3), scale=torch.tensor([1.0, 0.0, 2.0]))
 
 
+def test_uniform_distribution_against_reference_golden(dev, golden):
+    """zhusuan.distributions.Uniform incl. the reference's quirks (uniform.py:51-83): the reparameterised draw caches the
+    UNSCALED unit draw (so log_prob(None) is evaluated there), the non-reparameterised draw is scaled twice, x == high
+    is -inf, low >= high and out-of-support values raise ValueError (torch.distributions' argument validation)."""
+    from zhusuan.distributions import Uniform
+    g = golden("uniform")
+    K = g["x"].shape[0]
+    for dn, dt, rt in (("f32", torch.float32, 1e-5), ("f64", torch.float64, 1e-10)):
+        low, high = T(g["low"], dev, dt, True), T(g["high"], dev, dt, True)
+        d = Uniform(low=low, high=high, group_ndims=1)
+        assert d.is_reparameterized and tuple(d.batch_shape) == tuple(low.shape)
+        lp = d.log_prob(T(g["x"], dev, dt))
+        ref = g[dn + "_lp"]
+        got = lp.detach().cpu().numpy()
+        assert np.array_equal(np.isinf(got), np.isinf(ref))
+        close(got[np.isfinite(got)], ref[np.isfinite(ref)], rt)
+        gr = torch.autograd.grad(lp, [low, high], grad_outputs=T(g["g"], dev, dt))
+        close(gr[0], g[dn + "_dlow"], rt)
+        close(gr[1], g[dn + "_dhigh"], rt)
+        for name, reparam in (("rep", True), ("norep", False)):
+            low, high = T(g["low"], dev, dt, True), T(g["high"], dev, dt, True)
+            d = Uniform(low=low, high=high, is_reparameterized=reparam)
+            with _rng.inject(uniform=[T(g["u"], dev, dt)]):
+                z = d.sample(K)
+            p = "%s_%s_" % (dn, name)
+            close(z, g[p + "z"], rt)
+            close(d.sample_cache, g[p + "cache"], rt)
+            sg = torch.autograd.grad(z, [low, high], grad_outputs=T(g["dz"], dev, dt))
+            close(sg[0], g[p + "dlow"], rt)
+            close(sg[1], g[p + "dhigh"], rt)
+            if reparam:
+                close(d.log_prob(None), g[dn + "_rep_lp_cache"], rt)
+    z = Uniform(low=torch.zeros(4, 8, device=dev), high=torch.ones(4, 8, device=dev)).sample(3)
+    assert tuple(z.shape) == (3, 4, 8) and float(z.min()) >= 0.0 and float(z.max()) < 1.0
+    with pytest.raises(ValueError):  # reference test_uniform.py:74-76
+        Uniform(low=torch.tensor([10.0]), high=torch.tensor([2.0])).log_prob(torch.tensor([3.0]))
+    with pytest.raises(ValueError):
+        Uniform(low=torch.tensor([0.0]), high=torch.tensor([1.0])).log_prob(torch.tensor([1.5]))
+    with pytest.raises(TypeError, match="must have a dtype in"):
+        Uniform(2, 2, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        Uniform(torch.zeros([2, 1]), torch.zeros([2, 4, 3]))
+
+    class Net(BayesianNet):
+        def forward(self, observed):
+            self.observe(observed)
+            self.uniform("u", low=torch.zeros(3, device=dev), high=torch.ones(3, device=dev), n_samples=4)
+            self.stochastic_node("Uniform", "v", low=torch.zeros(3, device=dev), high=torch.ones(3, device=dev))
+            return self
+
+    net = Net(device=dev)({})
+    assert type(net.nodes["u"].dist).__name__ == "Uniform" and tuple(net.nodes["u"].tensor.shape) == (4, 3)
+
+
+def test_elbo_with_flow_against_reference_golden(dev, golden):
+    """ELBO(transform=...) (elbo.py:90-119): the flow's outputs replace the latents, its log-determinants enter the
+    objective as + sum(log_det) (:159-160) -- here folded into the objective's reduction (zs_combine_sums)."""
+    g = golden("elbo_flow")
+    K = int(g["K"])
+    B, Z = g["mean"].shape
+    for dn, dt, rt in (("f32", torch.float32, 2e-5), ("f64", torch.float64, 1e-10)):
+        m, sd, sc, sh, w = (T(g[k], dev, dt, True) for k in ("mean", "std", "s", "t", "w"))
+
+        class G(BayesianNet):
+            def forward(self, observed):
+                self.observe(observed)
+                z = self.normal("z", mean=torch.zeros(B, Z, dtype=dt, device=dev), std=torch.ones(B, Z, dtype=dt, device=dev),
+                                n_samples=K, reduce_sum_dims=[2])
+                self.bernoulli("x", probs=torch.sigmoid(torch.matmul(z, w)), reduce_sum_dims=[2])
+                return self
+
+        class V(BayesianNet):
+            def forward(self, observed):
+                self.observe(observed)
+                self.normal("z", mean=m, std=sd, n_samples=K, reduce_sum_dims=[2])
+                return self
+
+        def flow(inputs):
+            (z,) = inputs
+            return {"z": z * torch.exp(sc) + sh}, sc.sum().expand(z.shape[0], z.shape[1])
+
+        eps = T(g["eps"], dev, dt)
+        with _rng.inject(normal=[eps, eps]):
+            loss = ELBO(G(device=dev), V(device=dev), transform=flow, transform_var=["z"])({"x": T(g["x"], dev, dt)})
+        close(loss, g[dn + "_loss"], rt)
+        grads = torch.autograd.grad(loss, [m, sd, sc, sh, w])
+        for name, gr in zip(("dmean", "dstd", "ds", "dt", "dw"), grads):
+            close(gr, g[dn + "_" + name], rt * 5)
+
+
 def test_bn_logistic_builds_laplace_like_the_reference(dev):
     """framework/bn.py:336-352 of the reference: `bn.logistic` constructs a Laplace."""
     from zhusuan.distributions import Laplace

@@ -669,6 +669,34 @@ def test_normal_logprob_few_long_rows(oracle, dt, K, E):
     close(host(dmean), rdm.reshape(K, 1, E), rt)
 
 
+# ----------------------------------------------------------------------------- Uniform node
+@pytest.mark.parametrize("dn", ["f32", "f64"])
+def test_uniform_golden(golden, dn):
+    g = golden("uniform")
+    dt = np.float32 if dn == "f32" else np.float64
+    x, low, high, up = (g[k].astype(dt) for k in ("x", "low", "high", "g"))
+    K, M, E = x.shape
+    rt = 1e-5 if dn == "f32" else 1e-11
+    out = host(be.locscale_logprob_fwd(be.FAM_UNIFORM, dev(x), FULL, dev(low), KBCAST, dev(high), KBCAST, K, M, E))
+    ref = g[dn + "_lp"]
+    assert np.array_equal(np.isinf(out), np.isinf(ref)) and (out[np.isinf(out)] < 0).all()
+    close(out[np.isfinite(out)], ref[np.isfinite(ref)], rt)
+    dx, dlow, dhigh = be.locscale_logprob_bwd(be.FAM_UNIFORM, dev(up), dev(x), FULL, dev(low), KBCAST, dev(high), KBCAST,
+                                              K, M, E, True, True, True)
+    assert not host(dx).any()
+    close(host(dlow), g[dn + "_dlow"], rt)
+    close(host(dhigh), g[dn + "_dhigh"], rt)
+    N = M * E
+    u = g["u"].astype(dt)
+    z = be.locscale_sample(be.FAM_UNIFORM, dev(low.reshape(N)), KBCAST, dev((high - low).reshape(N)), KBCAST, K, N,
+                           u_in=dev(u.reshape(K, N)))
+    close(host(z).reshape(K, M, E), g[dn + "_rep_z"], rt)
+    # Philox draws are U[0,1) like torch.rand: the unit draw of the reference's reparameterised branch
+    unit = host(be.locscale_sample(be.FAM_UNIFORM, torch.zeros(N, device=DEV), KBCAST, torch.ones(N, device=DEV), KBCAST,
+                                   2000, N, seed=4, offset=8))
+    assert unit.min() >= 0.0 and unit.max() < 1.0 and abs(unit.mean() - 0.5) < 5e-3 and abs(unit.var() - 1 / 12) < 2e-3
+
+
 # ----------------------------------------------------------------------------- Logistic / Laplace nodes
 @pytest.mark.parametrize("dn", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["logistic", "laplace"])
@@ -945,6 +973,42 @@ def test_categorical(oracle, dt, K, M, C, lm):
     s = be.categorical_sample(dev(logits), lm, K, M, C, u_in=dev(u))
     so = oracle.categorical_sample(logits, u, K, M, C)
     assert (host(s) == so).mean() > 0.999  # ties at cumulative-sum boundaries may round differently
+
+
+@pytest.mark.parametrize("tdt", [torch.float32, torch.float64])
+def test_categorical_pinned_to_torch_distributions(tdt):
+    """Kernels against torch.distributions.Categorical on the device (the implementation a reference user would use;
+    the reference itself has no Categorical): log_prob and d/dlogits, KBCAST and FULL logits."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    for K, M, C, lm in ((50, 64, 10, KBCAST), (6, 40, 257, FULL), (1, 7, 2, FULL)):
+        shape = (M, C) if lm == KBCAST else (K, M, C)
+        logits = (3 * torch.randn(shape, device=DEV, generator=g)).to(tdt).requires_grad_()
+        x = torch.randint(0, C, (K, M), device=DEV, generator=g)
+        up = torch.randn(K, M, device=DEV, generator=g).to(tdt)
+        ref = torch.distributions.Categorical(logits=logits).log_prob(x)
+        (gref,) = torch.autograd.grad(ref, [logits], grad_outputs=up)
+        out = be.categorical_logpmf_fwd(x.to(tdt), FULL, logits.detach(), lm, K, M, C)
+        d = be.categorical_logpmf_bwd(up, x.to(tdt), FULL, logits.detach(), lm, K, M, C)
+        rt = 1e-5 if tdt == torch.float32 else 1e-11
+        close(host(out), host(ref), rt)
+        close(host(d), host(gref), rt * 3)
+
+
+def test_categorical_sampler_chi_square():
+    """Goodness of fit of the inverse-CDF sampler: Pearson chi-square of 200 000 Philox draws per row against
+    softmax(logits) (p > 1e-3 for every row), and successive particles are uncorrelated."""
+    from scipy import stats
+    M, C, K = 6, 12, 200000
+    logits = 1.5 * torch.randn(M, C, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    s = host(be.categorical_sample(logits, KBCAST, K, M, C, seed=9, offset=40)).astype(int)
+    p = torch.softmax(logits.double(), -1).cpu().numpy()
+    assert s.min() >= 0 and s.max() < C
+    for m in range(M):
+        obs = np.bincount(s[:, m], minlength=C)
+        chi2, pval = stats.chisquare(obs, p[m] * K)
+        assert pval > 1e-3, (m, chi2, pval)
+    a, b = s[:-1, 0].astype(np.float64), s[1:, 0].astype(np.float64)
+    assert abs(np.corrcoef(a, b)[0, 1]) < 0.01
 
 
 def test_categorical_sample_statistics():

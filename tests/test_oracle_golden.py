@@ -235,6 +235,31 @@ def test_locscale_nodes(oracle, golden, name, dn):
         close(ss.reshape(M, E), g[p + "sdscale"], dn, 30)
 
 
+def _close_inf(a, ref, dn):
+    """Compare arrays that may hold -inf (the x == high corner of the Uniform log-density)."""
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    assert np.array_equal(np.isinf(a), np.isinf(ref)) and np.array_equal(a[np.isinf(a)], ref[np.isinf(ref)])
+    close(a[np.isfinite(a)], ref[np.isfinite(ref)], dn)
+
+
+@pytest.mark.parametrize("dn", [F32, F64])
+def test_uniform_node(oracle, golden, dn):
+    """Uniform log_prob (values on both boundaries: x == low inside, x == high -inf) + gradients, and the unit draw
+    scaled by (high - low) (tests/golden/make_golden.py:gen_uniform; reference uniform.py:51-83)."""
+    g = golden("uniform")
+    dt = np.float32 if dn == F32 else np.float64
+    x, low, high, up = (g[k].astype(dt) for k in ("x", "low", "high", "g"))
+    K, M, E = x.shape
+    _close_inf(oracle.locscale_logprob_fwd(oracle.UNIFORM, x, low, high, K, M, E), g[dn + "_lp"], dn)
+    dx, dlow, dhigh = oracle.locscale_logprob_bwd(oracle.UNIFORM, up, x, low, high, K, M, E)
+    assert not dx.any()
+    close(dlow.reshape(M, E), g[dn + "_dlow"], dn, 30)
+    close(dhigh.reshape(M, E), g[dn + "_dhigh"], dn, 30)
+    u = g["u"].astype(dt)
+    z = oracle.locscale_sample(oracle.UNIFORM, low, high - low, u, K, M * E).reshape(K, M, E)
+    close(z, g[dn + "_rep_z"], dn)
+
+
 def test_reinforce_steps(oracle, golden):
     """ELBO.reinforce over three consecutive calls: cost, gradients and the in-place moving-mean state
     (tests/golden/make_golden.py:gen_reinforce, reference elbo.py:200-238)."""
@@ -294,6 +319,25 @@ def test_sgmcmc_trajectories(oracle, golden, name):
     traj = _replay_sgmcmc(oracle, g, name)
     # 4 chained fp32 updates; the quartic gradient amplifies 1-ulp differences slightly
     np.testing.assert_allclose(traj, g[name + "_f32_traj"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("dn", [F32, F64])
+def test_categorical_pinned_to_torch_distributions(oracle, dn):
+    """The reference has no Categorical (bn.py:8-19), so the pin is the implementation a reference user would reach for:
+    torch.distributions.Categorical -- log_prob values and the autograd gradient w.r.t. the logits, parameters broadcast
+    over particles and per particle."""
+    import torch
+    rng = np.random.RandomState(6)
+    dt, tdt = (np.float32, torch.float32) if dn == F32 else (np.float64, torch.float64)
+    for K, M, C, full in ((5, 33, 10, False), (4, 20, 100, True), (1, 9, 3, False)):
+        logits = (2 * rng.standard_normal((K, M, C) if full else (M, C))).astype(dt)
+        x = rng.randint(0, C, size=(K, M))
+        up = rng.standard_normal((K, M)).astype(dt)
+        lt = torch.tensor(logits, requires_grad=True)
+        lp = torch.distributions.Categorical(logits=lt).log_prob(torch.tensor(x))
+        (gl,) = torch.autograd.grad(lp, [lt], grad_outputs=torch.tensor(up))
+        close(oracle.categorical_logpmf_fwd(x.astype(dt), logits, K, M, C), lp.detach().numpy(), dn, 10)
+        close(oracle.categorical_logpmf_bwd(up, x.astype(dt), logits, K, M, C).reshape(logits.shape), gl.numpy(), dn, 30)
 
 
 def test_categorical_closed_form(oracle):

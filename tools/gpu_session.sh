@@ -7,9 +7,10 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -5 $OUT/${TAG}_pytest.log
+timeout 300 python tools/parity_budget.py > $OUT/${TAG}_parity.log 2>&1; echo "parity rc=$?"
 timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --graph 0 --no-e2e --no-cpu-baseline --no-secondary --no-strong > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_latent_fwd_packed|k_latent_bwd|k_iw_bernoulli_boxf' \
-    -s 12 -c 6 -o $OUT/${TAG}_hot -f python bench.py --steps 2 --warmup 3 --graph 0 --no-e2e --no-cpu-baseline --no-secondary --no-strong > $OUT/${TAG}_ncu_full.log 2>&1
+    -s 12 -c 9 -o $OUT/${TAG}_hot -f python bench.py --steps 2 --warmup 3 --graph 0 --no-e2e --no-cpu-baseline --no-secondary --no-strong > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | tail -12

@@ -27,8 +27,9 @@ struct PeerTable {
 //   barrier 0 publishes nothing (what the peers read was written by EARLIER kernels of this stream, complete and
 //             visible at the home L2 before this kernel started) and the data loads that follow are volatile, i.e. they
 //             are served by the owner's L2, never by a stale local cache line;
-//   barrier 1 every thread fences at system scope after its pushes (they must have landed before the flag does); what
-//             was pushed into this rank's buffer is read by LATER kernels of this stream.
+//   barrier 1 the signalling threads fence at system scope after the CTA barrier that follows the pushes (the pushes
+//             must have landed before the flag does); what was pushed into this rank's buffer is read by LATER
+//             kernels of this stream.
 __device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -103,10 +104,12 @@ __global__ void __launch_bounds__(ZS_PEER_THREADS)
             }
         }
     }
-    // ---- barrier 1: my pushes are visible everywhere; every peer's pushes into my buffer are too
-    __threadfence_system();
+    // ---- barrier 1: my pushes are visible everywhere; every peer's pushes into my buffer are too.  The CTA barrier
+    // orders every thread's pushes before the signalling threads' system-scope fence (fences are cumulative), so the
+    // other ~500 threads do not each pay for one.
     __syncthreads();
     if (tid < world && tid != rank) {
+        __threadfence_system();
         st_flag(tab.flags[tid] + flag_index(set, 1, cta, rank), e);
         while ((int)(ld_flag(mine + flag_index(set, 1, cta, tid)) - e) < 0) {}
     }

@@ -80,6 +80,25 @@ struct LaplaceOp {
     }
 };
 
+// Uniform(low, high): torch.distributions.Uniform.log_prob as the reference calls it (zhusuan/distributions/uniform.py:81):
+//   log(1[low <= x] * 1[x < high]) - log(high - low), i.e. -log(high - low) inside the support and -inf outside;
+// autograd sees only the second term: d/dlow = +g/(high - low), d/dhigh = -g/(high - low), d/dx = 0.
+template <typename T>
+struct UniformOp {
+    static __device__ __forceinline__ T term(T x, T low, T high) {
+        const T inside = (low <= x && x < high) ? T(0) : -INFINITY;
+        return inside - Real<T>::log(high - low);
+    }
+    static __device__ __forceinline__ T finish(T acc) { return acc; }
+    template <bool NEED_X>
+    static __device__ __forceinline__ void grad(T g, T x, T low, T high, T& dx, T& dlow, T& dhigh) {
+        const T r = g / (high - low);
+        dx = T(0);
+        dlow = r;
+        dhigh = -r;
+    }
+};
+
 // Logistic(loc, scale): zhusuan/distributions/logistic.py:81-82
 //   z = (x - loc) / scale ;  log p = -z - 2 softplus(-z) - log(scale)      (softplus: torch's, threshold 20)
 template <typename T>
@@ -557,7 +576,8 @@ __global__ void __launch_bounds__(KR_X* KR_Y) k_kreduce_bwd(T* __restrict__ dx, 
 //   NOISE_LOGISTIC log(u) - log(1 - u), u ~ U(0,1)                                     logistic.py:66-67
 //   NOISE_LAPLACE  -sign(u) log1p(-|u|), u ~ U(-1,1)      torch.distributions.Laplace.sample (laplace.py:74)
 // Injected noise (`eps_in`) is the family's UNIFORM for the last two, so the transform itself is under test.
-constexpr int NOISE_NORMAL = 0, NOISE_LOGISTIC = 1, NOISE_LAPLACE = 2;
+//   NOISE_UNIFORM  u ~ U[0,1) itself                      torch.rand, as Uniform.sample draws it (uniform.py:63-66)
+constexpr int NOISE_NORMAL = 0, NOISE_LOGISTIC = 1, NOISE_LAPLACE = 2, NOISE_UNIFORM = 3;
 
 template <typename T, int NOISE>
 __device__ __forceinline__ T noise_from_uniform(T u) {
@@ -578,8 +598,12 @@ __device__ __forceinline__ void philox_noise4(uint64_t q, uint64_t offset, uint6
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float u = u01_open(w[j]);  // (0,1)
-            out[j] = noise_from_uniform<float, NOISE>(NOISE == NOISE_LAPLACE ? 2.0f * u - 1.0f : u);
+            if (NOISE == NOISE_UNIFORM) {
+                out[j] = u01_closed_open(w[j]);  // [0,1), like torch.rand
+            } else {
+                const float u = u01_open(w[j]);  // (0,1)
+                out[j] = noise_from_uniform<float, NOISE>(NOISE == NOISE_LAPLACE ? 2.0f * u - 1.0f : u);
+            }
         }
     }
 }
@@ -1002,12 +1026,16 @@ int zs_locscale_sample(int dtype, int family, void* z, const void* loc, int loc_
     ZS_REQUIRE(z && loc && scale && K >= 0 && N >= 0, ZS_ERR_ARG);
     if (u_in) rng_state = rng_snapshot = nullptr;
     ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
-    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE || family == ZS_FAM_UNIFORM, ZS_ERR_ARG);
     if (K * N == 0) return ZS_OK;
     const int grid = grid_for((K * N + 3) / 4, 256);
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             k_normal_sample<T, false, NOISE_LOGISTIC><<<grid, 256, 0, as_stream(stream)>>>(
+                (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset,
+                rs_ptr(rng_state), rs_ptr(rng_snapshot));
+        else if (family == ZS_FAM_UNIFORM)
+            k_normal_sample<T, false, NOISE_UNIFORM><<<grid, 256, 0, as_stream(stream)>>>(
                 (T*)z, (const T*)loc, loc_mode, (const T*)scale, scale_mode, (const T*)u_in, (T*)nullptr, K, N, seed, offset,
                 rs_ptr(rng_state), rs_ptr(rng_snapshot));
         else
@@ -1024,7 +1052,7 @@ int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void
                            zs_stream_t stream) {
     ZS_REQUIRE(dz && K >= 0 && N >= 0, ZS_ERR_ARG);
     ZS_REQUIRE(valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
-    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE || family == ZS_FAM_UNIFORM, ZS_ERR_ARG);
     if ((dloc && loc_mode == ZS_SCALAR) || (dscale && scale_mode == ZS_SCALAR)) {
         set_last_error_msg("SCALAR-mode gradients are not produced by the kernels; expand the operand");
         return ZS_ERR_UNSUPPORTED;
@@ -1036,6 +1064,10 @@ int zs_locscale_sample_bwd(int dtype, int family, void* dloc, int loc_mode, void
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             k_normal_sample_bwd<T, NOISE_LOGISTIC><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
+                (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset,
+                u ? nullptr : rs_ptr(rng_state));
+        else if (family == ZS_FAM_UNIFORM)
+            k_normal_sample_bwd<T, NOISE_UNIFORM><<<(unsigned)grid, block, 0, as_stream(stream)>>>(
                 (T*)dloc, loc_mode, (T*)dscale, scale_mode, (const T*)dz, (const T*)u, K, N, seed, offset,
                 u ? nullptr : rs_ptr(rng_state));
         else
@@ -1051,12 +1083,16 @@ int zs_locscale_logprob_fwd(int dtype, int family, void* out, const void* x, int
                             const void* scale, int scale_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
     ZS_REQUIRE(out && x && loc && scale && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(valid_mode(x_mode) && valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
-    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE || family == ZS_FAM_UNIFORM, ZS_ERR_ARG);
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             return dispatch_rows_fwd<T, LogisticOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
                                                        Operand<T>{(const T*)loc, loc_mode},
                                                        Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
+        if (family == ZS_FAM_UNIFORM)  // loc = low, scale = high
+            return dispatch_rows_fwd<T, UniformOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
+                                                      Operand<T>{(const T*)loc, loc_mode},
+                                                      Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
         return dispatch_rows_fwd<T, LaplaceOp<T>>((T*)out, Operand<T>{(const T*)x, x_mode},
                                                   Operand<T>{(const T*)loc, loc_mode},
                                                   Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
@@ -1068,13 +1104,17 @@ int zs_locscale_logprob_bwd(int dtype, int family, void* dx, void* dloc, void* d
                             int64_t M, int64_t E, zs_stream_t stream) {
     ZS_REQUIRE(g && x && loc && scale && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(valid_mode(x_mode) && valid_mode(loc_mode) && valid_mode(scale_mode), ZS_ERR_ARG);
-    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE, ZS_ERR_ARG);
+    ZS_REQUIRE(family == ZS_FAM_LOGISTIC || family == ZS_FAM_LAPLACE || family == ZS_FAM_UNIFORM, ZS_ERR_ARG);
     if (!dx && !dloc && !dscale) return ZS_OK;
     ZS_DTYPE_SWITCH(dtype, {
         if (family == ZS_FAM_LOGISTIC)
             return dispatch_bwd<T, LogisticOp<T>>((T*)dx, (T*)dloc, (T*)dscale, (const T*)g, Operand<T>{(const T*)x, x_mode},
                                                   Operand<T>{(const T*)loc, loc_mode},
                                                   Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
+        if (family == ZS_FAM_UNIFORM)
+            return dispatch_bwd<T, UniformOp<T>>((T*)dx, (T*)dloc, (T*)dscale, (const T*)g, Operand<T>{(const T*)x, x_mode},
+                                                 Operand<T>{(const T*)loc, loc_mode},
+                                                 Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));
         return dispatch_bwd<T, LaplaceOp<T>>((T*)dx, (T*)dloc, (T*)dscale, (const T*)g, Operand<T>{(const T*)x, x_mode},
                                              Operand<T>{(const T*)loc, loc_mode},
                                              Operand<T>{(const T*)scale, scale_mode}, K, M, E, as_stream(stream));

@@ -315,6 +315,30 @@ __global__ void __cluster_dims__(RF_CLUSTER, 1, 1) __launch_bounds__(RF_THREADS)
     cluster.sync();  // no CTA may exit while CTA 0 still reads its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------
+// out[0] = sa * sum(a) + sb * sum(b): the scalar that ELBO.sgvb returns when a flow is attached
+// (zhusuan/variational/elbo.py:155-161: -mean(logp - logq) - sum(log_det)) from the per-column costs and the flow's
+// log-determinants, in ONE launch with a fixed summation order (thread t adds elements t, t + 1024, ...; the partials are
+// combined by a shuffle tree and a fixed loop over the warps) instead of a mean, a sum and a subtraction kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) k_combine_sums(T* __restrict__ out, const T* __restrict__ a, int64_t na, T sa,
+                                                       const T* __restrict__ b, int64_t nb, T sb) {
+    double acc_a = 0.0, acc_b = 0.0;
+    for (int64_t i = threadIdx.x; i < na; i += 1024) acc_a += (double)a[i];
+    for (int64_t i = threadIdx.x; i < nb; i += 1024) acc_b += (double)b[i];
+    double v = (double)sa * acc_a + (double)sb * acc_b;
+    v = warp_sum(v);
+    __shared__ double s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += s_part[w];
+        out[0] = (T)t;
+    }
+}
+
 }  // namespace zs
 
 using namespace zs;
@@ -424,6 +448,23 @@ int zs_scale_inplace(int dtype, void* buf0, int64_t n0, void* buf1, int64_t n1, 
         return ZS_ERR_DTYPE;
     }
     ZS_LAUNCH_CHECK("k_scale_inplace");
+    return ZS_OK;
+}
+
+int zs_combine_sums(int dtype, void* out, const void* a, int64_t na, double scale_a, const void* b, int64_t nb,
+                    double scale_b, zs_stream_t stream) {
+    ZS_REQUIRE(out && na >= 0 && nb >= 0 && (a || na == 0) && (b || nb == 0), ZS_ERR_ARG);
+    if (dtype == ZS_F32)
+        k_combine_sums<float><<<1, 1024, 0, as_stream(stream)>>>((float*)out, (const float*)a, na, (float)scale_a,
+                                                                   (const float*)b, nb, (float)scale_b);
+    else if (dtype == ZS_F64)
+        k_combine_sums<double><<<1, 1024, 0, as_stream(stream)>>>((double*)out, (const double*)a, na, scale_a,
+                                                                    (const double*)b, nb, scale_b);
+    else {
+        set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
+        return ZS_ERR_DTYPE;
+    }
+    ZS_LAUNCH_CHECK("k_combine_sums");
     return ZS_OK;
 }
 

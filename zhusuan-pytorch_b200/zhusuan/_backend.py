@@ -71,6 +71,7 @@ def _declare(lib):
         "zs_categorical_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_categorical_logpmf_bwd": (i32, [i32, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_iw_objective": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, i64, i64, dbl, vp]),
+        "zs_combine_sums": (i32, [i32, vp, vp, i64, dbl, vp, i64, dbl, vp]),
         "zs_log_mean_exp": (i32, [i32, vp, vp, i64, i64, vp]),
         "zs_log_mean_exp_bwd": (i32, [i32, vp, vp, vp, i64, i64, vp]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, i32, vp]),
@@ -348,7 +349,7 @@ def bernoulli_logpmf_bwd(g, x, xm, probs, pm, K, M, E, need_x, need_probs, logit
 
 
 # ----------------------------------------------------------------------------- Logistic / Laplace
-FAM_LOGISTIC, FAM_LAPLACE = 1, 2
+FAM_LOGISTIC, FAM_LAPLACE, FAM_UNIFORM = 1, 2, 3
 
 
 def locscale_sample(family, loc, loc_mode, scale, scale_mode, K, N, u_in=None, seed=0, offset=0, rng_state=None,
@@ -433,6 +434,16 @@ def iw_objective(estimator, logp, logq, grad_scale, extra=None, need_grads=True)
     _go("zs_iw_objective", dev, dtype_code(dt), estimator, _ptr(cost), _ptr(dlp), _ptr(dlq), _ptr(logp), _ptr(logq),
         _ptr(extra), K, B, float(grad_scale))
     return cost, dlp, dlq
+
+
+def combine_sums(a, scale_a, b, scale_b):
+    """scale_a * a.sum() + scale_b * b.sum() as a [1] tensor, one launch (zs_combine_sums)."""
+    dt, dev = a.dtype, a.device
+    _chk(dev, dt, a=a, b=b)
+    out = torch.empty(1, dtype=dt, device=dev)
+    _go("zs_combine_sums", dev, dtype_code(dt), _ptr(out), _ptr(a), a.numel(), float(scale_a), _ptr(b), b.numel(),
+        float(scale_b))
+    return out
 
 
 def log_mean_exp(x):

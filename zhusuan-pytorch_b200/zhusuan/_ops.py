@@ -57,6 +57,9 @@ def to_compute(t):
     uploading the bytes again -- unless the CPU tensor takes part in autograd itself (a user may ask for the gradient
     w.r.t. it, or hook it): then the op must stay connected to the CPU tensor."""
     if isinstance(t, LazyDraw):
+        dev_twin = getattr(t, "_zs_dev", None)
+        if dev_twin is not None:  # a result this package parked on the device (lazy_host_results): no copy at all
+            return dev_twin
         t = t._zs_materialize()
     if t.is_cuda:
         return t
@@ -148,14 +151,47 @@ class device_results(object):
         return False
 
 
+_lazy_host = [0]
+
+
+class lazy_host_results(object):
+    """Inside this context a LARGE result that belongs on the host (a latent sample of a host-resident model: 8 MB at
+    config 2) is handed back as a LazyDraw standing for the host copy: the device->host transfer and its
+    synchronisation happen only if host code actually touches the values (a CPU decoder does; a model whose only
+    consumers are this package's nodes never does).  Ops of this package recognise the object and read the device
+    original.  The objectives enter it for the duration of a step."""
+
+    def __enter__(self):
+        _lazy_host[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _lazy_host[0] -= 1
+        return False
+
+
 def back_home(t, home):
     """Return `t` on the caller's device; remember the device original for later ops."""
     if t.device == home or _keep_on_device[0]:
         return t
-    if home.type == "cpu" and t.is_cuda and t.numel() * t.element_size() >= (1 << 16):
+    big = home.type == "cpu" and t.is_cuda and t.numel() * t.element_size() >= (1 << 16)
+    if big and _lazy_host[0] and not _rng.has_injected():
+        lazy = LazyDraw(lambda self, t=t: _host_copy(t), t.shape, t.dtype, home)
+        lazy._zs_dev = t
+        return lazy
+    if big:
         out = _ToHostPinned.apply(t)
     else:
         out = t.to(home)
+    try:
+        out._zs_twin = (t, out._version)
+    except Exception:
+        pass
+    return out
+
+
+def _host_copy(t):
+    out = _ToHostPinned.apply(t)
     try:
         out._zs_twin = (t, out._version)
     except Exception:
@@ -703,6 +739,36 @@ def iw_objective(logp, logq, axis, estimator, reduce_mean):
     out = _IWObjective.apply(lp2, lq2, estimator, bool(reduce_mean))
     if not reduce_mean:
         out = out.reshape(rest)
+    return back_home(out, home)
+
+
+class _ElboWithLogDet(torch.autograd.Function):
+    """ELBO.sgvb with a flow (elbo.py:155-161): -mean_{k,b}(logp - logq) - sum(log_det) from ONE objective launch (the
+    per-column costs and both gradients) and ONE reduction launch that folds the log-determinants in."""
+
+    @staticmethod
+    def forward(ctx, logp, logq, log_det):
+        K, B = logp.shape
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        cost, dlp, dlq = be.iw_objective(be.ELBO, logp, logq, _mean_scale(B), need_grads=need)
+        ctx.save_for_backward(dlp, dlq)
+        ctx.ld_shape = log_det.shape
+        return be.combine_sums(cost, _mean_scale(B), log_det.reshape(-1), -1.0).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dlp, dlq = ctx.saved_tensors
+        return (dlp * g if ctx.needs_input_grad[0] else None, dlq * g if ctx.needs_input_grad[1] else None,
+                (-g).expand(ctx.ld_shape) if ctx.needs_input_grad[2] else None)
+
+
+def elbo_with_log_det(logp, logq, log_det):
+    """logp / logq [K, ...] broadcastable, log_det any shape -> the scalar ELBO cost with the flow term."""
+    home = logq.device
+    lp, lq = torch.broadcast_tensors(to_compute(logp), to_compute(logq))
+    K = int(lp.shape[0])
+    ld = to_compute(log_det).to(lq.dtype).contiguous()
+    out = _ElboWithLogDet.apply(lp.reshape(K, -1).contiguous(), lq.reshape(K, -1).contiguous(), ld)
     return back_home(out, home)
 
 

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from zhusuan.framework.stochastic_tensor import StochasticTensor
-from zhusuan.distributions import Distribution, Normal, Bernoulli, Categorical, Logistic, Laplace
+from zhusuan.distributions import Distribution, Normal, Bernoulli, Categorical, Logistic, Laplace, Uniform
 
 __all__ = ['BayesianNet']
 
@@ -20,9 +20,10 @@ name_mapping = {
     "Categorical": Categorical,
     "Logistic": Logistic,
     "Laplace": Laplace,
+    "Uniform": Uniform,
 }
 
-_OUT_OF_SCOPE = ("Beta", "Exponential", "Gamma", "Poisson", "StudentT", "Uniform")
+_OUT_OF_SCOPE = ("Beta", "Exponential", "Gamma", "Poisson", "StudentT")
 
 
 class BayesianNet(nn.Module):
@@ -122,6 +123,14 @@ class BayesianNet(nn.Module):
             raise ValueError("name of stochastic_node must be str")
         dist = Laplace(loc=loc, scale=scale, dtype=dtype, is_continuous=is_continuous, group_ndims=group_ndims,
                        device=self.device, **kwargs)
+        return self._register(name, dist, n_samples, kwargs)
+
+    def uniform(self, name, low, high, dtype=None, is_continuous=True, is_reparameterized=True, group_ndims=0,
+                n_samples=None, **kwargs):
+        if not isinstance(name, str):
+            raise ValueError("name of stochastic_node must be str")
+        dist = Uniform(low=low, high=high, dtype=dtype, is_continuous=is_continuous,
+                       is_reparameterized=is_reparameterized, group_ndims=group_ndims, device=self.device, **kwargs)
         return self._register(name, dist, n_samples, kwargs)
 
     def logistic(self, name, loc, scale, dtype=None, is_continuous=True, group_ndims=0, n_samples=None, **kwargs):

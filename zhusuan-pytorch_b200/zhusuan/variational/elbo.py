@@ -42,7 +42,8 @@ class ELBO(nn.Module):
         return total
 
     def forward(self, observed, reduce_mean=True, **kwargs):
-        with _ops.upload_memo():  # host-resident parameters cross PCIe once per step
+        # host-resident parameters cross PCIe once per step; large host-bound results are copied back lazily
+        with _ops.upload_memo(), _ops.lazy_host_results():
             return self._forward(observed, reduce_mean, **kwargs)
 
     def _forward(self, observed, reduce_mean=True, **kwargs):
@@ -80,6 +81,10 @@ class ELBO(nn.Module):
         The mean runs over ALL axes, particles included, as in the reference (:155-156)."""
         if torch.is_tensor(logqz) and logqz.dim() > 0 and reduce_mean:
             lp, lq = torch.broadcast_tensors(torch.as_tensor(logpxz, dtype=logqz.dtype, device=logqz.device), logqz)
+            if (log_det is not None and torch.is_tensor(log_det) and log_det.numel() > 0
+                    and lq.dtype in (torch.float32, torch.float64) and lq.numel() > 0):
+                # the flow's term folded into the objective's reduction (zs_combine_sums): two launches in all
+                return _ops.elbo_with_log_det(lp, lq, log_det)
             cost = _ops.iw_objective(lp.reshape(lp.shape[0], -1), lq.reshape(lq.shape[0], -1), 0, _be.ELBO, True)
         else:
             cost = -(logpxz - logqz)

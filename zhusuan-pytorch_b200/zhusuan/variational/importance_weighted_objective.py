@@ -132,7 +132,9 @@ class ImportanceWeightedObjective(nn.Module):
 
     # -- reference protocol ---------------------------------------------------------------------
     def forward(self, observed, reduce_mean=True):
-        with _ops.upload_memo():  # host-resident parameters cross PCIe once per step
+        # host-resident parameters cross PCIe once per step; large host-bound results (the latent samples of a
+        # host-resident model) are copied back only if host code reads them
+        with _ops.upload_memo(), _ops.lazy_host_results():
             return self._forward(observed, reduce_mean)
 
     def _forward(self, observed, reduce_mean=True):
