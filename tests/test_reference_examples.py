@@ -188,22 +188,25 @@ vimco = sys.argv[3] == "1"
 K, B = 50, 8
 iwae.device = torch.device("cpu")
 iwae.reparameterization = not vimco
-torch.manual_seed(0)
-gen, var = iwae.Generator(784, 40, K), iwae.Variational(784, 40, K)
-model = ImportanceWeightedObjective(gen, var, axis=0, estimator="vimco" if vimco else "sgvb")
 d = np.load(sys.argv[2])
-x, eps = torch.tensor(d["x"]), torch.tensor(d["eps"])
-def fake_normal(*a, **k):
-    if "size" in k:
-        return eps.clone()
-    return (a[0] + a[1] * eps).detach()
-with mock.patch("torch.normal", fake_normal):
-    loss = model({"x": x})
-loss.backward()
-out = {"loss": float(loss)}
-for n, p in model.named_parameters():
-    out[n] = float(p.grad.norm())
-print(json.dumps(out))
+res = {}
+for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+    torch.manual_seed(0)
+    gen, var = iwae.Generator(784, 40, K), iwae.Variational(784, 40, K)
+    model = ImportanceWeightedObjective(gen, var, axis=0, estimator="vimco" if vimco else "sgvb").to(dt)
+    x, eps = torch.tensor(d["x"]).to(dt), torch.tensor(d["eps"]).to(dt)
+    def fake_normal(*a, **k):
+        if "size" in k:
+            return eps.clone()
+        return (a[0] + a[1] * eps).detach()
+    with mock.patch("torch.normal", fake_normal):
+        loss = model({"x": x})
+    loss.backward()
+    out = {"loss": float(loss)}
+    for n, p in model.named_parameters():
+        out[n] = float(p.grad.norm())
+    res[tag] = out
+print(json.dumps(res))
 '''
 
 
@@ -212,7 +215,12 @@ print(json.dumps(out))
 @pytest.mark.parametrize("vimco", [False, True])
 def test_iwae_example_matches_the_reference_run(tmp_path, vimco):
     """Same example classes, same initial weights (seeded nn.Linear init), same injected noise: the reference on the CPU
-    (subprocess, its own `zhusuan`) and this package on the GPU agree on the loss and on every parameter-gradient norm."""
+    (subprocess, its own `zhusuan`, once in float32 and once with the same weights cast to float64) and this package on
+    the GPU agree on the loss and on every parameter-gradient norm. The yardstick is the float64 run; the budget is
+    north_star's 1e-5-class bound (2e-5 on the loss, 2e-4 on gradient norms that pass through exp(log w)) or 1.5 x the
+    distance of the reference's OWN float32 run from its float64 run, whichever is larger: VIMCO's value holds
+    sum_k log q_k * signal_k with the signal formed as a difference of two O(100) float32 numbers, which leaves the
+    float32 reference 3e-5 (loss) / 6e-4 (encoder gradients) away from float64 on these inputs."""
     from zhusuan import _rng
     from zhusuan.variational.importance_weighted_objective import ImportanceWeightedObjective
     K, B = 50, 8
@@ -225,7 +233,8 @@ def test_iwae_example_matches_the_reference_run(tmp_path, vimco):
     r = subprocess.run([sys.executable, "-c", _REF_SCRIPT, REF, f, "1" if vimco else "0"], stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=600, env=env, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-2000:]
-    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    both = json.loads(r.stdout.strip().splitlines()[-1])
+    ref, ref32 = both["f64"], both["f32"]
 
     iwae = _example("variational_autoencoder.iwae")
     iwae.device = torch.device("cuda")
@@ -238,7 +247,9 @@ def test_iwae_example_matches_the_reference_run(tmp_path, vimco):
     with _rng.inject(normal=[e, e]):
         loss = model({"x": torch.tensor(x, device="cuda")})
     loss.backward()
-    assert abs(float(loss) - ref["loss"]) <= 2e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
+    gap = {n: abs(ref32[n] - ref[n]) for n in ref}
+    got = float(loss.detach())
+    assert abs(got - ref["loss"]) <= max(2e-5 * abs(ref["loss"]), 1.5 * gap["loss"]), (got, ref["loss"], ref32["loss"])
     for n, p in model.named_parameters():
         got = float(p.grad.norm())
-        assert abs(got - ref[n]) <= 2e-3 * max(ref[n], 1e-6), (n, got, ref[n])
+        assert abs(got - ref[n]) <= max(2e-4 * max(ref[n], 1e-6), 1.5 * gap[n]), (n, got, ref[n], ref32[n])
