@@ -291,6 +291,18 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, int flags,
                           zs_stream_t stream);
 
+/* The same launch, which also writes the objective itself: loss_out[0] = sum_b cost[b] (with ZS_FUSED_COST_SCALED the
+ * mean objective of importance_weighted_objective.py:128-129 / :190-191, i.e. what the reference returns from
+ * forward()), without a reduction launch after it.  The last objective warp of the grid to finish adds up cost[0, B)
+ * in a fixed order (double accumulation; bit-reproducible, independent of which CTA finishes last) while the row warps
+ * are still writing the last columns of dprobs.  `ticket` points at ONE zero-initialised 32-bit word in device memory
+ * that the caller keeps per stream (the kernel re-arms it; two launches that may run concurrently need two words).
+ * `cost` must not be NULL.                                                                                         */
+int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* ticket, float* cost, float* dprobs, float* dlogp,
+                               float* dlogq, float* logpx_out, const float* probs, const float* x,
+                               const float* logp_other, const float* logq, int64_t K, int64_t B, int64_t X,
+                               double grad_scale, int flags, zs_stream_t stream);
+
 /* Debug hooks.  zs_debug_set_trace: device buffer (grid*40 int64) that the generic box / ring kernels fill with
  * clock64() phase timestamps of each CTA's first 8 columns; NULL (default) disables tracing.
  * zs_debug_set_fused_impl: 2 = ring, 3 = box (default order), 4 = generic box only, -1 = back to the default

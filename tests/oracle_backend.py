@@ -198,7 +198,7 @@ def fused_supported(K, X, dtype):
 
 
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False, out=None,
-                       logits=False, accumulate_cost=False, cost_scaled=False):
+                       logits=False, accumulate_cost=False, cost_scaled=False, want_loss=False):
     f = O.iw_bernoulli_logits_step if logits else O.iw_bernoulli_step
     r = f(estimator, _np(probs), _np(x), _np(logp_other), _np(logq), grad_scale, need_dprobs=need_dprobs)
     cost = r["cost"] * (np.float32(grad_scale) if cost_scaled else np.float32(1.0))

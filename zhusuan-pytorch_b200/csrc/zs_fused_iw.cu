@@ -207,6 +207,30 @@ __device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int
     if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc * cscale;
 }
 
+// The mean objective itself (sum_b cost[b]) without another launch: every objective warp takes a ticket when its last
+// column is written; the warp that draws the last of the 2 x gridDim.x tickets adds up cost[0, B) in a fixed order
+// (lane-strided double partial sums, shuffle tree: the result does not depend on which warp does it), stores the
+// float and re-arms the counter for the next launch on this stream.  It runs while the row warps still write the last
+// column's gradient, so it is hidden.  `ticket` is a zero-initialised word owned by the caller (one per stream).
+__device__ __forceinline__ void finish_loss(int lane, const float* cost, int64_t B, float* __restrict__ loss_out,
+                                            unsigned* __restrict__ ticket) {
+    if (loss_out == nullptr) return;
+    __threadfence();  // this warp's cost[b] stores (lane 0) before its ticket
+    __syncwarp();
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t != 2u * gridDim.x - 1u) return;
+    __threadfence();
+    double acc = 0.0;
+    for (int64_t b = lane; b < B; b += 32) acc += (double)__ldcg(cost + b);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        *loss_out = (float)acc;
+        *ticket = 0u;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ring variant (fallback for shapes the box kernels do not take): one persistent CTA per SM, warp-specialised.
 //   row warps      : warp w owns rows k = w, w+NW, ... of every column and a private mini-ring of D
@@ -448,7 +472,8 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
                         float* __restrict__ dlogq, float* __restrict__ logpx_out, const float* __restrict__ probs,
                         const float* __restrict__ x, const float* __restrict__ logp_other,
                         const float* __restrict__ logq, int K, int64_t B, int X, int R, float gscale,
-                        int stagger_groups, int stagger_cycles, int flags, long long* __restrict__ trace, int64_t ldkb) {
+                        int stagger_groups, int stagger_cycles, int flags, long long* __restrict__ trace, int64_t ldkb,
+                        float* __restrict__ loss_out, unsigned* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     stagger_start(stagger_groups, stagger_cycles);
     const RingLayout L(K, X, R);
@@ -550,6 +575,7 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
+        finish_loss(lane, cost, B, loss_out, ticket);
         return;
     }
 
@@ -714,7 +740,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                        float* __restrict__ logpx_out, const float* __restrict__ x,
                        const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B, int X,
                        int inner, int nslot, int l2_ahead, float gscale, int stagger_groups, int stagger_cycles,
-                       int flags, long long* __restrict__ trace, int64_t ldkb) {
+                       int flags, long long* __restrict__ trace, int64_t ldkb, float* __restrict__ loss_out,
+                       unsigned* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     const BoxLayout L(K, X, inner, nslot);
     const int Kpad = L.Kpad;
@@ -826,6 +853,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
+        finish_loss(lane, cost, B, loss_out, ticket);
         return;
     }
 
@@ -1077,7 +1105,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
                         float* __restrict__ dprobs, float* __restrict__ dlogp, float* __restrict__ dlogq,
                         float* __restrict__ logpx_out, const float* __restrict__ x,
                         const float* __restrict__ logp_other, const float* __restrict__ logq, int K, int64_t B,
-                        int nslot, float gscale, int stagger_groups, int stagger_cycles, int flags, int64_t ldkb) {
+                        int nslot, float gscale, int stagger_groups, int stagger_cycles, int flags, int64_t ldkb,
+                        float* __restrict__ loss_out, unsigned* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int INNER = INNER4 * 4, X = INNER * NBOX, X4 = X / 4;
     const BoxLayout L(K, X, INNER, nslot);
@@ -1169,6 +1198,7 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
             column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
                                 s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
         }
+        finish_loss(lane, cost, B, loss_out, ticket);
         return;
     }
 
@@ -1292,6 +1322,8 @@ struct FusedCall {
     int kflags;  // FUSED_ACCUMULATE | FUSED_EARLY_ISSUE, as the kernels read them
     bool logits;
     cudaStream_t st;
+    float* loss_out = nullptr;   // sum_b cost[b], written by the launch itself (finish_loss), or null
+    unsigned* ticket = nullptr;  // its zero-initialised counter word
 };
 
 // Tensor map of probs[K][B][X] with box {inner, 1, K}; the driver's encoder is looked up through the runtime.
@@ -1418,7 +1450,7 @@ int launch_fused_box(const FusedCall& c, bool generic_only) {
         ZS_CUDA_TRY(cudaFuncSetAttribute(fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fixed<<<(unsigned)grid, threads, smem, c.st>>>(map, c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.x,
                                                         c.logp_other, c.logq, (int)K, B, nslot, (float)c.grad_scale,
-                                                        stg.groups, stg.cycles, c.kflags, c.ldkb);
+                                                        stg.groups, stg.cycles, c.kflags, c.ldkb, c.loss_out, c.ticket);
         ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
         return ZS_OK;
     }
@@ -1431,7 +1463,8 @@ int launch_fused_box(const FusedCall& c, bool generic_only) {
     // boxes requested into L2 ahead of the shared-memory copies: measured no gain (0..4) to a loss (>= 7), off
     kern<<<(unsigned)grid, threads, smem, c.st>>>(map, c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.x, c.logp_other,
                                                   c.logq, (int)K, B, (int)X, inner, nslot, knobs().l2_ahead,
-                                                  (float)c.grad_scale, stg.groups, stg.cycles, c.kflags, g_trace, c.ldkb);
+                                                  (float)c.grad_scale, stg.groups, stg.cycles, c.kflags, g_trace, c.ldkb,
+                                                  c.loss_out, c.ticket);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_box");
     return ZS_OK;
 }
@@ -1474,7 +1507,8 @@ int launch_fused_ring(const FusedCall& c) {
     kern<<<(unsigned)grid, threads, smem, c.st>>>(c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.probs, c.x,
                                                   c.logp_other, c.logq, (int)K, B, (int)X, R, (float)c.grad_scale,
                                                   stg.groups, stg.cycles,
-                                                  c.kflags | (knobs().early ? FUSED_EARLY_ISSUE : 0), g_trace, c.ldkb);
+                                                  c.kflags | (knobs().early ? FUSED_EARLY_ISSUE : 0), g_trace, c.ldkb,
+                                                  c.loss_out, c.ticket);
     ZS_LAUNCH_CHECK("k_iw_bernoulli_ring");
     return ZS_OK;
 }
@@ -1515,6 +1549,24 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                     ((flags & ZS_FUSED_COST_SCALED) ? FUSED_COST_SCALED : 0),
                 (flags & ZS_FUSED_LOGITS) != 0,
                 as_stream(stream)};
+    return fused_launch(c);
+}
+
+int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* ticket, float* cost, float* dprobs, float* dlogp,
+                               float* dlogq, float* logpx_out, const float* probs, const float* x,
+                               const float* logp_other, const float* logq, int64_t K, int64_t B, int64_t X,
+                               double grad_scale, int flags, zs_stream_t stream) {
+    ZS_REQUIRE(probs && x && loss_out && ticket && cost && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
+    ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
+    ZS_REQUIRE((flags & ~(ZS_FUSED_ACCUMULATE_COST | ZS_FUSED_LOGITS | ZS_FUSED_COST_SCALED)) == 0, ZS_ERR_ARG);
+    FusedCall c{estimator, cost, dprobs, dlogp, dlogq, logpx_out, probs, x, logp_other, logq, K, B, X, B, grad_scale,
+                ((flags & ZS_FUSED_ACCUMULATE_COST) ? FUSED_ACCUMULATE : 0) |
+                    ((flags & ZS_FUSED_COST_SCALED) ? FUSED_COST_SCALED : 0),
+                (flags & ZS_FUSED_LOGITS) != 0,
+                as_stream(stream)};
+    c.loss_out = loss_out;
+    c.ticket = (unsigned*)ticket;
     return fused_launch(c);
 }
 

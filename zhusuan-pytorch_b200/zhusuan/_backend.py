@@ -75,6 +75,7 @@ def _declare(lib):
         "zs_log_mean_exp": (i32, [i32, vp, vp, i64, i64, vp]),
         "zs_log_mean_exp_bwd": (i32, [i32, vp, vp, vp, i64, i64, vp]),
         "zs_iw_bernoulli_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, i32, vp]),
+        "zs_iw_bernoulli_fused_loss": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, dbl, i32, vp]),
         "zs_scale_inplace": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp]),
         "zs_debug_set_trace": (i32, [vp]),
         "zs_debug_set_fused_impl": (i32, [i32]),
@@ -487,13 +488,37 @@ def set_fused_impl(impl):
     check(load().zs_debug_set_fused_impl(int(impl)), "zs_debug_set_fused_impl")
 
 
+# zs_iw_bernoulli_fused_loss needs one zero-initialised counter word per stream that may run the launch: a small
+# per-device pool, handed out by stream id (host bookkeeping only, so it also works while a graph is being captured)
+_TICKET_WORDS = 256
+_tickets = {}
+
+
+def _ticket_ptr(dev):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ent = _tickets.get(idx)
+    if ent is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # no allocation + memset inside a capture: the caller reduces cost[B] itself this once
+        ent = _tickets[idx] = (torch.zeros(_TICKET_WORDS, dtype=torch.int32, device=dev), {})
+    words, slots = ent
+    sid = torch.cuda.current_stream(dev).cuda_stream
+    k = slots.get(sid)
+    if k is None:
+        if len(slots) >= _TICKET_WORDS:
+            return None
+        k = slots[sid] = len(slots)
+    return ctypes.c_void_p(words.data_ptr() + 4 * k)
+
+
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False,
-                       out=None, logits=False, accumulate_cost=False, cost_scaled=False):
+                       out=None, logits=False, accumulate_cost=False, cost_scaled=False, want_loss=False):
     """probs [K,B,X], x [B,X], logp_other/logq [K,B] or None.  `logits=True`: `probs` holds logits and "dprobs" is
     the gradient w.r.t. them (ZS_FUSED_LOGITS).  `accumulate_cost=True` (needs out["cost"]): the per-column
     objectives are ADDED to out["cost"] (ZS_FUSED_ACCUMULATE_COST).  `cost_scaled=True`: cost[b] already carries
-    grad_scale, so cost.sum() is the mean objective (ZS_FUSED_COST_SCALED).
-    Returns dict(cost[B], dprobs, dlogp, dlogq, logpx) or None when the shape is not supported."""
+    grad_scale, so cost.sum() is the mean objective (ZS_FUSED_COST_SCALED).  `want_loss=True`: the launch also writes
+    sum_b cost[b] into "loss" [1] (zs_iw_bernoulli_fused_loss); "loss" is None when no counter word is available.
+    Returns dict(cost[B], dprobs, dlogp, dlogq, logpx, loss) or None when the shape is not supported."""
     dev = probs.device
     _chk(dev, torch.float32, probs=probs, x=x, logp_other=logp_other, logq=logq)
     K, B, X = probs.shape
@@ -506,12 +531,22 @@ def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_d
     _chk(dev, torch.float32, cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx)
     flags = ((FUSED_LOGITS if logits else 0) | (FUSED_ACCUMULATE_COST if accumulate_cost else 0) |
              (FUSED_COST_SCALED if cost_scaled else 0))
-    rc = _run("zs_iw_bernoulli_fused", dev, estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx),
-              _ptr(probs), _ptr(x), _ptr(logp_other), _ptr(logq), K, B, X, float(grad_scale), flags)
+    ticket = _ticket_ptr(dev) if (want_loss and B >= 1 and cost is not None) else None
+    loss = None
+    if ticket is not None:
+        loss = o.get("loss") if "loss" in o else torch.empty(1, dtype=torch.float32, device=dev)
+        _chk(dev, torch.float32, loss=loss)
+        name = "zs_iw_bernoulli_fused_loss"
+        rc = _run(name, dev, estimator, _ptr(loss), ticket, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx),
+                  _ptr(probs), _ptr(x), _ptr(logp_other), _ptr(logq), K, B, X, float(grad_scale), flags)
+    else:
+        name = "zs_iw_bernoulli_fused"
+        rc = _run(name, dev, estimator, _ptr(cost), _ptr(dprobs), _ptr(dlp), _ptr(dlq), _ptr(lpx),
+                  _ptr(probs), _ptr(x), _ptr(logp_other), _ptr(logq), K, B, X, float(grad_scale), flags)
     if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
         return None
-    check(rc, "zs_iw_bernoulli_fused")
-    return dict(cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx)
+    check(rc, name)
+    return dict(cost=cost, dprobs=dprobs, dlogp=dlp, dlogq=dlq, logpx=lpx, loss=loss)
 
 
 def reinforce_step(logp, logq, moving_mean, local_step, decay, need_grads=True):

@@ -841,12 +841,14 @@ class _IWBernoulliFused(torch.autograd.Function):
         K, B, X = probs.shape
         # per-column costs come out already scaled by 1 / (columns of the local or global batch): the mean objective
         # is ONE reduction over them
+        # ... which the launch does itself (zs_iw_bernoulli_fused_loss): no reduction kernel after it
         r = be.iw_bernoulli_fused(estimator, probs, x, logp_other, logq, _mean_scale(B),
-                                  need_dprobs=ctx.needs_input_grad[0], logits=logits, cost_scaled=True)
+                                  need_dprobs=ctx.needs_input_grad[0], logits=logits, cost_scaled=True, want_loss=True)
         if r is None:
             raise be.BackendError("fused IW kernel refused a shape fused_supported() accepted")
         ctx.grads = (r["dprobs"], r["dlogp"], r["dlogq"])
-        return r["cost"].sum()
+        loss = r.get("loss")
+        return loss.reshape(()) if loss is not None else r["cost"].sum()
 
     @staticmethod
     def backward(ctx, g):
