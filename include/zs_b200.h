@@ -291,15 +291,18 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
                           const float* logq, int64_t K, int64_t B, int64_t X, double grad_scale, int flags,
                           zs_stream_t stream);
 
-/* The same launch, which also writes the objective itself: loss_out[0] = sum_b cost[b] (with ZS_FUSED_COST_SCALED the
- * mean objective of importance_weighted_objective.py:128-129 / :190-191, i.e. what the reference returns from
- * forward()), without a reduction launch after it.  The last objective warp of the grid to finish adds up cost[0, B)
- * in a fixed order (double accumulation; bit-reproducible, independent of which CTA finishes last) while the row warps
- * are still writing the last columns of dprobs.  `ticket` points at ONE zero-initialised 32-bit word in device memory
- * that the caller keeps per stream (the kernel re-arms it; two launches that may run concurrently need two words).
- * `cost` must not be NULL.                                                                                         */
-int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* ticket, float* cost, float* dprobs, float* dlogp,
-                               float* dlogq, float* logpx_out, const float* probs, const float* x,
+/* The same launch, which also writes the objective itself: loss_out[0] = sum_b cost_b of THIS launch (with
+ * ZS_FUSED_COST_SCALED the mean objective of importance_weighted_objective.py:128-129 / :190-191, i.e. what the
+ * reference returns from forward()), without a reduction launch after it.  Each of the grid's objective warps keeps
+ * the double sum of the float-rounded column costs it wrote; the last one to finish adds the per-warp sums in a fixed
+ * order while the row warps are still writing the last columns of dprobs.  Bit-reproducible from launch to launch on
+ * one device (the order depends only on the grid size).  `workspace`: ZS_FUSED_LOSS_WS_BYTES of device memory,
+ * zero-initialised ONCE by the caller and kept per stream (the kernel re-arms it; two launches that may run
+ * concurrently need two workspaces).  `cost` must not be NULL.                                                    */
+#define ZS_FUSED_LOSS_MAX_GRID 160
+#define ZS_FUSED_LOSS_WS_BYTES (8 + 2 * ZS_FUSED_LOSS_MAX_GRID * 8)
+int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* workspace, float* cost, float* dprobs,
+                               float* dlogp, float* dlogq, float* logpx_out, const float* probs, const float* x,
                                const float* logp_other, const float* logq, int64_t K, int64_t B, int64_t X,
                                double grad_scale, int flags, zs_stream_t stream);
 
@@ -372,6 +375,9 @@ int zs_sgmcmc_multi_step(int dtype, int algorithm, const zs_chain_tensor* tensor
  *   [first, first + count) : the floats to reduce (multiples of 4); every rank passes the same values
  *   flag_set      : 0 .. ZS_PEER_FLAG_SETS-1; calls that may be in flight at the same time use different sets
  *   ctas          : CTAs of the launch, the same on every rank (0 = default)
+ *   extra_src, extra_index : optional device scalar (the step's objective) that this rank's kernel stores into its own
+ *                   buffer at float index extra_index (inside [first, first + count)) before the exchange, so the
+ *                   caller needs no copy launch to put it there; NULL = nothing
  * Rank r reduces slice r in rank order and stores the sums into every rank's buffer: results are bit-identical on all
  * ranks.  Enqueued on `stream`; every rank must enqueue the matching call (a CTA waits for its counterpart on every
  * peer).  The per-CTA epochs live in the flag area, so the launch can be captured in a CUDA graph and replayed. */
@@ -381,7 +387,17 @@ int zs_sgmcmc_multi_step(int dtype, int algorithm, const zs_chain_tensor* tensor
 #define ZS_PEER_THREADS 512
 int64_t zs_allreduce_peer_flag_bytes(void);
 int zs_allreduce_sum_peer(float* const* bufs_host, void* const* flags_host, int rank, int world, int64_t first,
-                          int64_t count, int flag_set, int ctas, zs_stream_t stream);
+                          int64_t count, int flag_set, int ctas, const float* extra_src, int64_t extra_index,
+                          zs_stream_t stream);
+/* The same exchange through an NVSwitch multicast mapping (NVLS): `multicast_buf` is ONE address that names the buffer
+ * in every rank's memory (cuMulticast* / torch symmetric memory's multicast_ptr).  Rank r reads slice r with
+ * multimem.ld_reduce (the switch returns the SUM over the ranks) and writes it back with multimem.st (the switch
+ * stores into every rank's copy): 2/N of the buffer crosses each GPU's links instead of 2(N-1)/N.  Flags as above
+ * (unicast peer pointers); `local_buf` is this rank's ordinary pointer to its own buffer (for extra_src).  All ranks
+ * receive the same bits; the switch's summation order is its own.                                                */
+int zs_allreduce_sum_nvls(float* multicast_buf, float* local_buf, void* const* flags_host, int rank, int world,
+                          int64_t first, int64_t count, int flag_set, int ctas, const float* extra_src,
+                          int64_t extra_index, zs_stream_t stream);
 
 /* ---- host-buffer step (end-to-end measurement) ----
  * One importance-weighted step of the Bernoulli-likelihood path with HOST buffers for the big

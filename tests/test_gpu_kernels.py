@@ -488,9 +488,10 @@ def test_fused_accumulate_cost(monkeypatch, impl):
 @pytest.mark.parametrize("impl", ["ring", "box", "boxg"])
 @pytest.mark.parametrize("K,B,X", [(50, 333, 784), (50, 1024, 784), (6, 5, 128), (25, 1, 256), (50, 149, 784)])
 def test_fused_loss_in_launch(monkeypatch, impl, K, B, X):
-    """zs_iw_bernoulli_fused_loss: the launch's own sum_b cost[b] (last objective warp, fixed order, double
-    accumulation) equals the float64 sum of the per-column costs it wrote, launch after launch (the counter word
-    re-arms itself), bit-identically from run to run, and leaves every other output unchanged."""
+    """zs_iw_bernoulli_fused_loss: the launch's own sum_b cost[b] (per-warp double partial sums, added in a fixed
+    order by the last objective warp) equals the float64 sum of the per-column costs it wrote to float32 rounding,
+    launch after launch (the workspace re-arms itself), bit-identically from run to run, and leaves every other
+    output unchanged."""
     _set_impl(monkeypatch, impl)
     probs, x, other, logq = _fused_inputs(K, B, X, seed=21)
     dp, dx, do, dq = dev(probs), dev(x), dev(other), dev(logq)
@@ -499,8 +500,8 @@ def test_fused_loss_in_launch(monkeypatch, impl, K, B, X):
     for _ in range(4):
         r = be.iw_bernoulli_fused(be.VIMCO, dp, dx, do, dq, 1.0 / B, cost_scaled=True, want_loss=True)
         assert r["loss"] is not None and r["loss"].shape == (1,)
-        want = np.float32(host(r["cost"]).astype(np.float64).sum())
-        assert float(r["loss"]) == float(want), (float(r["loss"]), float(want))
+        want = host(r["cost"]).astype(np.float64).sum()
+        assert abs(float(r["loss"]) - want) <= 1.5e-7 * abs(want), (float(r["loss"]), float(want))
         seen.append(float(r["loss"]))
         assert torch.equal(r["cost"], base["cost"]) and torch.equal(r["dprobs"], base["dprobs"])
         assert torch.equal(r["dlogp"], base["dlogp"]) and torch.equal(r["dlogq"], base["dlogq"])

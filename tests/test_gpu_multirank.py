@@ -83,6 +83,9 @@ def _worker(rank, world, port, vimco, backend, out):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if backend == "peer-p2p":  # the peer loads / stores kernel even where the fabric offers a multicast mapping
+        os.environ["ZS_PEER_NVLS"] = "0"
+        backend = "peer"
     try:
         lo, hi = zd.shard_range(B)
         try:
@@ -95,6 +98,7 @@ def _worker(rank, world, port, vimco, backend, out):
             return
         torch.cuda.synchronize()
         res = {"loss": float(bucket.loss()), "backend": bucket.backend, "local_loss": float(loss), "lo": lo, "hi": hi,
+               "variant": getattr(bucket._peer, "variant", None),
                "dec": [p.grad.detach().cpu().numpy() for p in dec.parameters()],
                "a": a.grad.detach().cpu().numpy(), "b": None if b is None else b.grad.detach().cpu().numpy(),
                "views": all(p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr()
@@ -106,15 +110,17 @@ def _worker(rank, world, port, vimco, backend, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("backend", ["peer", "nccl"])
+@pytest.mark.parametrize("backend", ["peer", "peer-p2p", "nccl"])
 @pytest.mark.parametrize("vimco", [False, True])
 def test_two_ranks_equal_one_gpu(vimco, backend):
-    """backend "peer": the exchange is this library's NVLink peer-memory kernel (zs_allreduce_sum_peer);
-    "nccl": torch.distributed.all_reduce on the same bucket."""
+    """backend "peer": the exchange is this library's kernel over NVLink peer memory -- the NVSwitch multicast form
+    (zs_allreduce_sum_nvls) where the fabric offers a multicast mapping, else peer loads / stores
+    (zs_allreduce_sum_peer), which "peer-p2p" forces; "nccl": torch.distributed.all_reduce on the same bucket.
+    The objective reaches the bucket's slot through the kernel's `extra_src` (no copy launch)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29650 + (1 if vimco else 0) + (2 if backend == "peer" else 0)
+    port = 29650 + (1 if vimco else 0) + {"peer": 2, "peer-p2p": 4, "nccl": 0}[backend]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, vimco, backend, out)) for r in range(2)]
     for p in procs:
         p.start()
@@ -124,7 +130,10 @@ def test_two_ranks_equal_one_gpu(vimco, backend):
         assert p.exitcode == 0
     if "unavailable" in got[0]:
         pytest.skip("peer-mapped memory not available on this box: " + got[0]["unavailable"])
-    assert got[0]["backend"] == backend and got[1]["backend"] == backend
+    assert got[0]["backend"] == backend.split("-")[0] and got[1]["backend"] == backend.split("-")[0]
+    if backend == "peer-p2p":
+        assert got[0]["variant"] == "p2p"
+    print("peer variant:", got[0]["variant"])
     # the whole batch on one GPU, no process group: global_batch(B) is then the plain batch mean
     dev = torch.device("cuda", 0)
     loss, dec, (a, b), _ = _step(dev, slice(0, B), B, vimco, False)

@@ -38,7 +38,20 @@ for n in (4, 663784, 1346868):
     peer.all_reduce(0, (n + 3) // 4 * 4)
     torch.cuda.synchronize()
     ok = bool((peer.flat == world * (world + 1) / 2).all())
-    res = {"floats": n, "world": world, "peer_correct": ok}
+    res = {"floats": n, "world": world, "peer_correct": ok, "variant": peer.variant}
+    if peer.mc_ptr:  # also the peer loads / stores form on the same buffer
+        mc, peer.mc_ptr = peer.mc_ptr, 0
+        peer.flat.fill_(float(rank + 1))
+        torch.cuda.synchronize(); dist.barrier()
+        peer.all_reduce(0, (n + 3) // 4 * 4)
+        torch.cuda.synchronize()
+        res["p2p_correct"] = bool((peer.flat == world * (world + 1) / 2).all())
+        res["p2p_us"] = round(timed(lambda: peer.all_reduce(0, (n + 3) // 4 * 4)), 2)
+        peer.mc_ptr = mc
+        res["nvls_us"] = round(timed(lambda: peer.all_reduce(0, (n + 3) // 4 * 4)), 2)
+        for ctas in (8, 16, 32, 64):
+            import zhusuan._backend as be
+            res["nvls_us_ctas%d" % ctas] = round(timed(lambda: be.allreduce_sum_nvls(peer.mc_ptr, peer.buf_ptrs[peer.rank], peer.flag_ptrs, peer.rank, 0, (n + 3) // 4 * 4, 0, dev, ctas)), 2)
     for ctas in (16, 32, 64):
         import zhusuan._backend as be
         res["peer_us_ctas%d" % ctas] = round(timed(lambda: be.allreduce_sum_peer(peer.buf_ptrs, peer.flag_ptrs, peer.rank, 0,
@@ -50,7 +63,7 @@ for n in (4, 663784, 1346868):
     with torch.cuda.stream(sp):
         with torch.cuda.graph(gp, stream=sp):
             for _ in range(10):
-                be.allreduce_sum_peer(peer.buf_ptrs, peer.flag_ptrs, peer.rank, 0, (n + 3) // 4 * 4, 1, dev, 64)
+                peer.all_reduce(0, (n + 3) // 4 * 4, flag_set=1)
     torch.cuda.current_stream().wait_stream(sp)
     res["peer_us_in_graph"] = round(timed(gp.replay, reps=30, warm=3) / 10, 2)
     t = torch.ones(n, device=dev)

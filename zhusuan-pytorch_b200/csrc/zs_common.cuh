@@ -44,6 +44,38 @@ inline cudaStream_t as_stream(zs_stream_t s) { return reinterpret_cast<cudaStrea
 
 int sm_count();  // of the current device (cached per device)
 
+// ---- programmatic dependent launch ------------------------------------------------
+// The step is a chain of short launches around one long one, and in a replayed CUDA graph every kernel -> kernel edge
+// costs ~1.2 us of drain + launch latency (profiles/r2_notes.md).  The chain's own kernels are therefore launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled while the previous kernel of the
+// stream is still running and park at pdl_wait() (griddepcontrol.wait: returns once every prerequisite grid has
+// completed and its memory is visible), which every such kernel executes BEFORE its first global-memory access.
+// pdl_trigger() (griddepcontrol.launch_dependents) lets the NEXT kernel do the same.  Both are no-ops for a kernel
+// launched the ordinary way, so the kernels behave identically behind a plain <<<>>> launch.  ZS_PDL=0 disables it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ZS_PDL is a bit mask over the launch sites (PDL_* below).  Default: all but the latent backward -- measured with
+// tools/step_breakdown.py (profiles/r2_notes.md): a programmatic latent backward directly behind the fused kernel
+// costs the step 2 us (its CTAs take over SMs that the fused kernel's tail frees and then sit in front of nothing),
+// the other three sites are worth 3 us together.
+enum { PDL_LATENT_FWD = 1, PDL_FUSED = 2, PDL_SCALE = 4, PDL_LATENT_BWD = 8 };
+int pdl_mask();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int site, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mask() & site) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- 16-byte packs ---------------------------------------------------------
 template <typename T>
 struct alignas(16) Pack {

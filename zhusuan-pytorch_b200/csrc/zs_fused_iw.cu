@@ -122,7 +122,7 @@ __device__ __forceinline__ float4 dprobs4(const float4& p, const float4& xx, flo
 // Objective warp: turns the K log-weights of a column into cost, dlogp, dlogq (global) — off the
 // critical path of the row warps.  Same math as k_iw_objective; reciprocal instead of IEEE division.
 template <int EST>
-__device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
+__device__ __forceinline__ float column_objective(int lane, int K, int64_t B, int64_t b, const float* s_lpx,
                                                const float* s_other, const float* s_lq, double* s_xw, float gscale,
                                                float* __restrict__ cost, float* __restrict__ dlogp,
                                                float* __restrict__ dlogq, float* __restrict__ logpx_out,
@@ -204,30 +204,46 @@ __device__ __forceinline__ void column_objective(int lane, int K, int64_t B, int
     }
     c_acc = warp_sum(c_acc);
     // accumulate: running sum of the column's objective over launches (one writer per column: deterministic)
-    if (lane == 0 && cost) cost[b] = prev_cost + (float)c_acc * cscale;
+    const float cval = (float)c_acc * cscale;  // every lane holds the column's total
+    if (lane == 0 && cost) cost[b] = prev_cost + cval;
+    return cval;
 }
 
-// The mean objective itself (sum_b cost[b]) without another launch: every objective warp takes a ticket when its last
-// column is written; the warp that draws the last of the 2 x gridDim.x tickets adds up cost[0, B) in a fixed order
-// (lane-strided double partial sums, shuffle tree: the result does not depend on which warp does it), stores the
-// float and re-arms the counter for the next launch on this stream.  It runs while the row warps still write the last
-// column's gradient, so it is hidden.  `ticket` is a zero-initialised word owned by the caller (one per stream).
-__device__ __forceinline__ void finish_loss(int lane, const float* cost, int64_t B, float* __restrict__ loss_out,
-                                            unsigned* __restrict__ ticket) {
+// The mean objective itself (sum_b cost_b) without another launch.  Every objective warp keeps the double sum of the
+// (float-rounded) column costs it wrote -- its columns and their order are fixed by the grid -- and, when its last
+// column is done, stores that partial sum into its slot of the caller's workspace and takes a ticket.  The warp that
+// draws the last of the 2 x gridDim.x tickets adds the 2 x gridDim.x partial sums in slot order (lane-strided, shuffle
+// tree: the result does not depend on which warp does it), stores the float and re-arms the counter for the next launch
+// on this stream.  One batch of <= 10 loads per lane, issued while the row warps still write the last column's
+// gradient.  Workspace (ZS_FUSED_LOSS_WS_BYTES, zero-initialised once, one per stream): word 0 = ticket, then from
+// byte 8 the double partial sums.
+__device__ __forceinline__ void finish_loss(int lane, int p, double part, float* __restrict__ loss_out,
+                                            unsigned* __restrict__ ws) {
     if (loss_out == nullptr) return;
-    __threadfence();  // this warp's cost[b] stores (lane 0) before its ticket
-    __syncwarp();
+    double* partial = reinterpret_cast<double*>(ws + 2);
     unsigned t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1u);
+    if (lane == 0) {
+        __stcg(partial + 2 * blockIdx.x + p, part);
+        __threadfence();
+        t = atomicAdd(ws, 1u);
+    }
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t != 2u * gridDim.x - 1u) return;
+    const unsigned n = 2u * gridDim.x;
+    if (t != n - 1u) return;
     __threadfence();
+    double v[ZS_FUSED_LOSS_MAX_GRID * 2 / 32];
+#pragma unroll
+    for (int i = 0; i < ZS_FUSED_LOSS_MAX_GRID * 2 / 32; ++i) {
+        const unsigned idx = (unsigned)lane + 32u * i;
+        v[i] = idx < n ? __ldcg(partial + idx) : 0.0;
+    }
     double acc = 0.0;
-    for (int64_t b = lane; b < B; b += 32) acc += (double)__ldcg(cost + b);
+#pragma unroll
+    for (int i = 0; i < ZS_FUSED_LOSS_MAX_GRID * 2 / 32; ++i) acc += v[i];
     acc = warp_sum(acc);
     if (lane == 0) {
         *loss_out = (float)acc;
-        *ticket = 0u;
+        *ws = 0u;
     }
 }
 
@@ -569,13 +585,15 @@ __global__ void __launch_bounds__((ZS_RING_MAX_ROW_WARPS + 3) * 32, 1)
         // ---- objective warps: cost / dlogp / dlogq of every other column ----------------------------
         const int p = warp - NW - 1;
         int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        double part = 0.0;
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
+            part += (double)column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad,
+                                                  s_lq + buf * Kpad, s_xw + p * Kpad, gscale, cost, dlogp, dlogq,
+                                                  logpx_out, flags);
         }
-        finish_loss(lane, cost, B, loss_out, ticket);
+        finish_loss(lane, p, part, loss_out, ticket);
         return;
     }
 
@@ -847,13 +865,15 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     if (is_obj) {
         const int p = warp - NW - 1;
         int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        double part = 0.0;
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);  // lpx of column c complete
-            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
+            part += (double)column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad,
+                                                  s_lq + buf * Kpad, s_xw + p * Kpad, gscale, cost, dlogp, dlogq,
+                                                  logpx_out, flags);
         }
-        finish_loss(lane, cost, B, loss_out, ticket);
+        finish_loss(lane, p, part, loss_out, ticket);
         return;
     }
 
@@ -1140,6 +1160,8 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     auto stage_scalars = [&](int64_t b, int buf) { stage_scalars_batched(s_other + buf * Kpad, s_lq + buf * Kpad, logp_other, logq, K, ldkb, b, lane); };
     auto stage_x = [&](int64_t b, int slot) { stage_x_batched(s_x + (size_t)slot * 2 * X, s_bin + slot, x + b * X, X4, lane); };
     const bool is_stager = warp == NW, is_obj = warp == NW + 1 || warp == NW + 2, is_producer = warp == NW + 3;
+    pdl_wait();  // everything above touched shared memory only; probs / x / the [K,B] terms may come from the kernel before
+    pdl_trigger();
     stagger_start(stagger_groups, stagger_cycles);
     // Column 0 only: column 1 is staged while column 0 is being read.  The first tensor copies are issued AFTER
     // this staging on purpose: issuing them first (measured here and in the ring kernel: +4 and +7 us per launch)
@@ -1192,13 +1214,15 @@ __global__ void __launch_bounds__((BOX_MAX_ROW_WARPS + 4) * 32, 1)
     if (is_obj) {
         const int p = warp - NW - 1;
         int64_t b = (int64_t)blockIdx.x + (int64_t)p * gridDim.x;
+        double part = 0.0;
         for (int64_t c = p; c < ncols; c += 2, b += 2 * (int64_t)gridDim.x) {
             const int buf = (int)(c & 3);
             named_bar_sync(1 + p, sync_threads);
-            column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad, s_lq + buf * Kpad,
-                                s_xw + p * Kpad, gscale, cost, dlogp, dlogq, logpx_out, flags);
+            part += (double)column_objective<EST>(lane, K, ldkb, b, s_lpx + buf * Kpad, s_other + buf * Kpad,
+                                                  s_lq + buf * Kpad, s_xw + p * Kpad, gscale, cost, dlogp, dlogq,
+                                                  logpx_out, flags);
         }
-        finish_loss(lane, cost, B, loss_out, ticket);
+        finish_loss(lane, p, part, loss_out, ticket);
         return;
     }
 
@@ -1323,7 +1347,7 @@ struct FusedCall {
     bool logits;
     cudaStream_t st;
     float* loss_out = nullptr;   // sum_b cost[b], written by the launch itself (finish_loss), or null
-    unsigned* ticket = nullptr;  // its zero-initialised counter word
+    unsigned* ticket = nullptr;  // its workspace: counter word + per-warp partial sums (finish_loss)
 };
 
 // Tensor map of probs[K][B][X] with box {inner, 1, K}; the driver's encoder is looked up through the runtime.
@@ -1448,9 +1472,9 @@ int launch_fused_box(const FusedCall& c, bool generic_only) {
     }
     if (fixed != nullptr) {
         ZS_CUDA_TRY(cudaFuncSetAttribute(fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fixed<<<(unsigned)grid, threads, smem, c.st>>>(map, c.cost, c.dprobs, c.dlogp, c.dlogq, c.logpx_out, c.x,
-                                                        c.logp_other, c.logq, (int)K, B, nslot, (float)c.grad_scale,
-                                                        stg.groups, stg.cycles, c.kflags, c.ldkb, c.loss_out, c.ticket);
+        launch_pdl(PDL_FUSED, fixed, dim3((unsigned)grid), dim3(threads), smem, c.st, map, c.cost, c.dprobs, c.dlogp, c.dlogq,
+                   c.logpx_out, c.x, c.logp_other, c.logq, (int)K, B, nslot, (float)c.grad_scale, stg.groups, stg.cycles,
+                   c.kflags, c.ldkb, c.loss_out, c.ticket);
         ZS_LAUNCH_CHECK("k_iw_bernoulli_boxf");
         return ZS_OK;
     }
@@ -1552,11 +1576,11 @@ int zs_iw_bernoulli_fused(int estimator, float* cost, float* dprobs, float* dlog
     return fused_launch(c);
 }
 
-int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* ticket, float* cost, float* dprobs, float* dlogp,
+int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* workspace, float* cost, float* dprobs, float* dlogp,
                                float* dlogq, float* logpx_out, const float* probs, const float* x,
                                const float* logp_other, const float* logq, int64_t K, int64_t B, int64_t X,
                                double grad_scale, int flags, zs_stream_t stream) {
-    ZS_REQUIRE(probs && x && loss_out && ticket && cost && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(probs && x && loss_out && workspace && cost && K >= 1 && B >= 1 && X >= 1, ZS_ERR_ARG);
     ZS_REQUIRE(estimator == ZS_EST_SGVB || estimator == ZS_EST_VIMCO, ZS_ERR_ARG);
     ZS_REQUIRE(!(estimator == ZS_EST_VIMCO && (K < 2 || logq == nullptr)), ZS_ERR_ARG);
     ZS_REQUIRE((flags & ~(ZS_FUSED_ACCUMULATE_COST | ZS_FUSED_LOGITS | ZS_FUSED_COST_SCALED)) == 0, ZS_ERR_ARG);
@@ -1565,8 +1589,9 @@ int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* ticket, flo
                     ((flags & ZS_FUSED_COST_SCALED) ? FUSED_COST_SCALED : 0),
                 (flags & ZS_FUSED_LOGITS) != 0,
                 as_stream(stream)};
+    ZS_REQUIRE(persistent_grid(B) <= ZS_FUSED_LOSS_MAX_GRID, ZS_ERR_UNSUPPORTED);
     c.loss_out = loss_out;
-    c.ticket = (unsigned*)ticket;
+    c.ticket = (unsigned*)workspace;
     return fused_launch(c);
 }
 

@@ -310,6 +310,8 @@ __global__ void __launch_bounds__(LF_WARPS * 32, 8)
                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
                       const float* __restrict__ pb, const float* __restrict__ noise_in, int K, int M, int E4, int RW,
                       int KS, unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    pdl_wait();     // the parameters may come from the kernel before this one
+    pdl_trigger();  // the next kernel's CTAs may be scheduled as this grid drains
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rl = (int)(((unsigned)lane * inv_e4) >> 16), j = lane - rl * E4;  // lane / E4, lane % E4
     const int m = ((int)blockIdx.x * LF_WARPS + warp) * RW + rl;
@@ -570,6 +572,191 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, sizeof(T) == 4 ? 4 : 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward, row-per-thread form of the hot configuration (float, KBCAST parameters, E/4 <= 16).  k_latent_fwd_fast
+// above maps lanes to the float4 units of a row, so every row sum is a segmented shuffle reduction and every slice of
+// four particles redoes the row's parameter transform: ncu round 2 counted 4.5 M warp instructions (~280 per float4 of
+// latents, of which the noise is ~75) at 58 % issue utilisation -- 9.3 us for 8 MB.  Here
+//   * a CTA owns 32 consecutive batch rows; their parameter-only terms (mean, std, 0.5/std^2 | probs and the log-odds
+//     term; the prior's unless it is the standard one) are transformed ONCE per CTA into shared memory, and the per-row
+//     constant sum_e (c - log std_e) is reduced there too;
+//   * a lane owns ONE (particle, row) pair: it walks the row's E/4 units, two Philox / Box-Muller chains in flight,
+//     and keeps log q and log p in registers -- no shuffles at all;
+//   * the 32 rows of a particle are one contiguous 32*E-float block of z: the warp stages it in shared memory (row
+//     pitch E + 4 floats: conflict-free 128-bit accesses) and writes it out with fully coalesced 128-bit stores.
+// Element (k, m, e) still draws word e%4 of Philox counter (k*M*E + m*E + e)/4: the stream is identical to every other
+// sampling kernel's.  Sums are re-associated (sequential over the row) against the reference's order: 1e-7 relative.
+// ---------------------------------------------------------------------------------------------
+constexpr int LR_WARPS = 4;
+
+template <int FAM, bool STDP>
+__global__ void __launch_bounds__(LR_WARPS * 32)
+    k_latent_fwd_rows(float* __restrict__ z, float* __restrict__ logq, float* __restrict__ logp,
+                      const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
+                      const float* __restrict__ pb, const float* __restrict__ noise_in, int K, int M, int E4, int KS,
+                      unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs) {
+    extern __shared__ __align__(16) float lr_smem[];
+    pdl_wait();
+    pdl_trigger();
+    constexpr int NP = FAM == FAM_NORMAL ? (STDP ? 3 : 5) : (STDP ? 2 : 3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int E = 4 * E4, EP = E + 4, QP = E4 + 1;
+    const int m0 = (int)blockIdx.x * 32;
+    const int rows = M - m0 < 32 ? M - m0 : 32;
+    float* P = lr_smem;                          // [NP][32][EP]
+    float* s_q = P + NP * 32 * EP;               // [32][QP] per-unit parts of the row constant of log q
+    float* s_p = s_q + 32 * QP;                  // [32][QP] ... of log p
+    float* stage = s_p + 32 * QP + warp * 32 * EP;  // this warp's z block [32][EP]
+    const float c = normal_c<float>();
+    // ---- the CTA's parameter transform, once
+    for (int u = threadIdx.x; u < rows * E4; u += LR_WARPS * 32) {
+        const int r = (int)(((unsigned)u * inv_e4) >> 16), j = u - r * E4;
+        const size_t g = 4 * ((size_t)m0 * E4 + u);
+        const float4 av = *reinterpret_cast<const float4*>(a + g);
+        float4* dst = reinterpret_cast<float4*>(P + r * EP + 4 * j);
+        const int PS = 32 * EP / 4;  // float4 stride between parameter arrays
+        float uq, up = 0.f;
+        if (FAM == FAM_NORMAL) {
+            const float4 bv = *reinterpret_cast<const float4*>(b + g);
+            dst[0] = av;
+            dst[PS] = bv;
+            dst[2 * PS] = make_float4(0.5f * lat_rcp(bv.x * bv.x), 0.5f * lat_rcp(bv.y * bv.y),
+                                      0.5f * lat_rcp(bv.z * bv.z), 0.5f * lat_rcp(bv.w * bv.w));
+            uq = (c - lat_log(bv.x)) + (c - lat_log(bv.y)) + (c - lat_log(bv.z)) + (c - lat_log(bv.w));
+            if (!STDP) {
+                float4 pm = make_float4(0.f, 0.f, 0.f, 0.f), ps = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (pa) pm = *reinterpret_cast<const float4*>(pa + g);
+                if (pb) ps = *reinterpret_cast<const float4*>(pb + g);
+                dst[3 * PS] = pm;
+                dst[4 * PS] = make_float4(0.5f * lat_rcp(ps.x * ps.x), 0.5f * lat_rcp(ps.y * ps.y),
+                                          0.5f * lat_rcp(ps.z * ps.z), 0.5f * lat_rcp(ps.w * ps.w));
+                up = (c - lat_log(ps.x)) + (c - lat_log(ps.y)) + (c - lat_log(ps.z)) + (c - lat_log(ps.w));
+            }
+        } else {
+            // log(p + 1e-8), log((1-p) + 1e-8) of bernoulli.py:94: l1 + z (l0 - l1) per element
+            const float4 l1 = make_float4(lat_log((1.f - av.x) + 1e-8f), lat_log((1.f - av.y) + 1e-8f),
+                                          lat_log((1.f - av.z) + 1e-8f), lat_log((1.f - av.w) + 1e-8f));
+            dst[0] = av;
+            dst[PS] = make_float4(lat_log(av.x + 1e-8f) - l1.x, lat_log(av.y + 1e-8f) - l1.y,
+                                  lat_log(av.z + 1e-8f) - l1.z, lat_log(av.w + 1e-8f) - l1.w);
+            uq = (l1.x + l1.y) + (l1.z + l1.w);
+            if (!STDP) {
+                const float4 pp = *reinterpret_cast<const float4*>(pa + g);
+                const float4 h1 = make_float4(lat_log((1.f - pp.x) + 1e-8f), lat_log((1.f - pp.y) + 1e-8f),
+                                              lat_log((1.f - pp.z) + 1e-8f), lat_log((1.f - pp.w) + 1e-8f));
+                dst[2 * PS] = make_float4(lat_log(pp.x + 1e-8f) - h1.x, lat_log(pp.y + 1e-8f) - h1.y,
+                                          lat_log(pp.z + 1e-8f) - h1.z, lat_log(pp.w + 1e-8f) - h1.w);
+                up = (h1.x + h1.y) + (h1.z + h1.w);
+            }
+        }
+        s_q[r * QP + j] = uq;
+        s_p[r * QP + j] = up;
+    }
+    // the stream position is read by the CTA's leader meanwhile; its barrier also publishes the transform
+    offset = rng_acquire(offset, rs, nullptr, true);
+    __syncthreads();
+    const bool active = lane < rows;
+    float cq = 0.f, cp = 0.f;
+    if (active) {
+        for (int j = 0; j < E4; ++j) {
+            cq += s_q[lane * QP + j];
+            cp += s_p[lane * QP + j];
+        }
+        if (STDP) cp = FAM == FAM_NORMAL ? (float)E * c : (float)E * lat_log(0.5f + 1e-8f);
+    }
+    const unsigned ME4 = (unsigned)M * (unsigned)E4;
+    const float* prow = P + lane * EP;
+    const int PSF = 32 * EP;  // float stride between parameter arrays
+    for (int k = (int)blockIdx.y + KS * warp; k < K; k += KS * LR_WARPS) {  // uniform over the warp
+        float accq = cq, accp = cp;
+        const unsigned unit0 = (unsigned)k * ME4 + (unsigned)(m0 + lane) * (unsigned)E4;
+        if (active) {
+#pragma unroll 2
+            for (int j = 0; j < E4; ++j) {
+                float n4[4];
+                if (noise_in) {
+                    const float4 t = *reinterpret_cast<const float4*>(noise_in + 4 * (size_t)(unit0 + j));
+                    n4[0] = t.x; n4[1] = t.y; n4[2] = t.z; n4[3] = t.w;
+                } else if (FAM == FAM_NORMAL) {
+                    philox_normal4((uint64_t)(unit0 + j), offset, seed, n4);
+                } else {
+                    philox_uniform4((uint64_t)(unit0 + j), offset, seed, n4);
+                }
+                const float4 av = *reinterpret_cast<const float4*>(prow + 4 * j);
+                float4 zv;
+                if (FAM == FAM_NORMAL) {
+                    const float4 bv = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
+                    const float4 h = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
+                    zv = make_float4(fmaf(bv.x, n4[0], av.x), fmaf(bv.y, n4[1], av.y), fmaf(bv.z, n4[2], av.z),
+                                     fmaf(bv.w, n4[3], av.w));  // normal.py:105
+                    const float d0 = zv.x - av.x, d1 = zv.y - av.y, d2 = zv.z - av.z, d3 = zv.w - av.w;  // :121-124
+                    accq -= (h.x * (d0 * d0) + h.y * (d1 * d1)) + (h.z * (d2 * d2) + h.w * (d3 * d3));
+                    if (STDP) {
+                        accp -= 0.5f * ((zv.x * zv.x + zv.y * zv.y) + (zv.z * zv.z + zv.w * zv.w));
+                    } else {
+                        const float4 pm = *reinterpret_cast<const float4*>(prow + 3 * PSF + 4 * j);
+                        const float4 hp = *reinterpret_cast<const float4*>(prow + 4 * PSF + 4 * j);
+                        const float e0 = zv.x - pm.x, e1 = zv.y - pm.y, e2 = zv.z - pm.z, e3 = zv.w - pm.w;
+                        accp -= (hp.x * (e0 * e0) + hp.y * (e1 * e1)) + (hp.z * (e2 * e2) + hp.w * (e3 * e3));
+                    }
+                } else {
+                    const float4 l0 = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
+                    zv = make_float4(n4[0] < av.x ? 1.f : 0.f, n4[1] < av.y ? 1.f : 0.f, n4[2] < av.z ? 1.f : 0.f,
+                                     n4[3] < av.w ? 1.f : 0.f);  // bernoulli.py:79
+                    accq += (zv.x * l0.x + zv.y * l0.y) + (zv.z * l0.z + zv.w * l0.w);
+                    if (!STDP) {
+                        const float4 pm = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
+                        accp += (zv.x * pm.x + zv.y * pm.y) + (zv.z * pm.z + zv.w * pm.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(stage + lane * EP + 4 * j) = zv;
+            }
+            if (logq) logq[(size_t)k * M + m0 + lane] = accq;
+            if (logp) logp[(size_t)k * M + m0 + lane] = accp;
+        }
+        __syncwarp();
+        // the particle's 32-row block of z, coalesced
+        float* zblk = z + 4 * ((size_t)k * ME4 + (size_t)m0 * E4);
+        for (int u = lane; u < rows * E4; u += 32) {
+            const int r = (int)(((unsigned)u * inv_e4) >> 16), j = u - r * E4;
+            *reinterpret_cast<float4*>(zblk + 4 * (size_t)u) = *reinterpret_cast<const float4*>(stage + r * EP + 4 * j);
+        }
+        __syncwarp();
+    }
+}
+
+template <int FAM>
+static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float* a, int a_mode, const float* b,
+                                const float* pa, const float* pb, const float* noise_in, int64_t K, int64_t M,
+                                int64_t E4, uint64_t seed, uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+    static const bool enabled = [] {  // developer knob: ZS_LATENT_FWD_ROWS=0 keeps the lane-per-unit kernel
+        const char* e = getenv("ZS_LATENT_FWD_ROWS");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled || a_mode != ZS_KBCAST || E4 > 16 || E4 < 1 || K < 1 || M < 1 || K * M * E4 >= ((int64_t)1 << 31))
+        return false;
+    const int E = (int)(4 * E4), EP = E + 4, QP = (int)E4 + 1;
+    const bool stdp = FAM == FAM_NORMAL ? (pa == nullptr && pb == nullptr) : pa == nullptr;
+    const int np = FAM == FAM_NORMAL ? (stdp ? 3 : 5) : (stdp ? 2 : 3);
+    const size_t smem = (size_t)(np * 32 * EP + 2 * 32 * QP + LR_WARPS * 32 * EP) * sizeof(float);
+    // one particle per warp unless that takes more CTAs than the machine holds a few times over
+    const int64_t tiles = (M + 31) / 32;
+    int64_t per_warp = 1;
+    while (tiles * ((K + LR_WARPS * per_warp - 1) / (LR_WARPS * per_warp)) > (int64_t)sm_count() * 16 && per_warp < K)
+        per_warp *= 2;
+    int64_t KS = (K + LR_WARPS * per_warp - 1) / (LR_WARPS * per_warp);
+    if (KS > 65535 || tiles >= (int64_t)2147483647) return false;
+    const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
+    auto kern = stdp ? k_latent_fwd_rows<FAM, true> : k_latent_fwd_rows<FAM, false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    launch_pdl(PDL_LATENT_FWD, kern, dim3((unsigned)tiles, (unsigned)KS), dim3(LR_WARPS * 32), smem, st, z, logq, logp, a,
+               b, pa, pb, noise_in, (int)K, (int)M, (int)E4, (int)KS, inv, seed, offset, rs);
+    return true;
+}
+
 // float / KBCAST / 32-bit indexable shapes go to k_latent_fwd_fast; returns false when the shape does not qualify
 template <typename T, int FAM>
 static bool launch_latent_fwd_fast(dim3, T*, T*, T*, const T*, int, const T*, const T*, const T*, const T*, int64_t,
@@ -583,15 +770,15 @@ bool launch_latent_fwd_fast<float, FAM_NORMAL>(dim3 grid, float* z, float* logq,
                                                int64_t K, int64_t M, int64_t E4, int RW, int64_t KS, uint64_t seed,
                                                uint64_t offset, unsigned long long* rs, cudaStream_t st) {
     if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
+    if (latent_fwd_rows_f32<FAM_NORMAL>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st))
+        return true;
     const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
     if (pa == nullptr && pb == nullptr)
-        k_latent_fwd_fast<FAM_NORMAL, true><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in, (int)K,
-                                                                            (int)M, (int)E4, RW, (int)KS, inv, seed,
-                                                                            offset, rs);
+        launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_NORMAL, true>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
     else
-        k_latent_fwd_fast<FAM_NORMAL, false><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in, (int)K,
-                                                                             (int)M, (int)E4, RW, (int)KS, inv, seed,
-                                                                             offset, rs);
+        launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_NORMAL, false>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
     return true;
 }
 template <>
@@ -601,15 +788,15 @@ bool launch_latent_fwd_fast<float, FAM_BERNOULLI>(dim3 grid, float* z, float* lo
                                                   int64_t KS, uint64_t seed, uint64_t offset, unsigned long long* rs,
                                                   cudaStream_t st) {
     if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
+    if (latent_fwd_rows_f32<FAM_BERNOULLI>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st))
+        return true;
     const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
     if (pa == nullptr)
-        k_latent_fwd_fast<FAM_BERNOULLI, true><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in,
-                                                                               (int)K, (int)M, (int)E4, RW, (int)KS, inv,
-                                                                               seed, offset, rs);
+        launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_BERNOULLI, true>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
     else
-        k_latent_fwd_fast<FAM_BERNOULLI, false><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, b, pa, pb, noise_in,
-                                                                                (int)K, (int)M, (int)E4, RW, (int)KS, inv,
-                                                                                seed, offset, rs);
+        launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_BERNOULLI, false>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
     return true;
 }
 
@@ -701,14 +888,20 @@ static int latent_args_ok(const void* a, int a_mode, const void* b, int b_mode, 
 // closer of the two to the float64 reference run) and ~8 instructions per element.  Four particles per thread, all
 // eight 128-bit loads issued before the first use.
 // ---------------------------------------------------------------------------------------------
-constexpr int LBF_U = 4;  // particles in flight per thread
+constexpr int LBF_U = 4;  // particles in flight per thread (default)
 
-template <int FAM, bool STDP>
-__global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, 4)
+// LBF_U > 4: the one-wave block shape of config 2 (8 x 8 threads, 17 warps per SM) walked K = 50 particles in TWO
+// dependent rounds of loads (4 + 3 per thread) and was latency-bound on them (ncu round 2: long_scoreboard 10 of 13
+// stall cycles per issue, 2 TB/s).  With ceil(K / slices) <= 8 particles per thread ALL loads of the thread are issued
+// before the first use -- one memory round trip per CTA -- at ~100 registers, which 17 warps per SM can afford.
+template <int FAM, bool STDP, int LBF_U>
+__global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, LBF_U > 4 ? 2 : 4)
     k_latent_bwd_fast(float* __restrict__ da, float* __restrict__ db, const float* __restrict__ gq,
                       const float* __restrict__ gp, const float* __restrict__ dz_up, const float* __restrict__ z,
                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
                       const float* __restrict__ pb, int reparam, int K, int M, int E) {
+    pdl_wait();
+    pdl_trigger();
     const int LBX = blockDim.x, LBY = blockDim.y;
     const unsigned ME4 = ((unsigned)M * (unsigned)E) >> 2;
     const unsigned u = blockIdx.x * LBX + threadIdx.x;
@@ -829,10 +1022,26 @@ static bool latent_bwd_fast_f32(void* da, void* db, const void* gq, const void* 
     }
     dim3 block(lbx, lby);
     const bool stdp = pa == nullptr && pb == nullptr;
-    auto kern = stdp ? k_latent_bwd_fast<FAM, true> : k_latent_bwd_fast<FAM, false>;
-    kern<<<grid, block, 0, st>>>((float*)da, (float*)db, (const float*)gq, (const float*)gp, (const float*)dz_up,
-                                 (const float*)z, (const float*)a, (const float*)b, (const float*)pa, (const float*)pb,
-                                 reparam, (int)K, (int)M, (int)E);
+    auto kern = stdp ? k_latent_bwd_fast<FAM, true, LBF_U> : k_latent_bwd_fast<FAM, false, LBF_U>;
+    // every particle of a thread in flight at once where that takes at most 8 (and the CTAs stay small enough for the
+    // register budget: 2 x 256 threads per SM are guaranteed, the one-wave shape needs 17 warps)
+    const int per_thread = (int)((K + lby - 1) / lby);
+    static const bool all_in_flight = [] {  // developer knob: ZS_LATENT_BWD_DEEP=0 keeps four particles in flight
+        const char* e = getenv("ZS_LATENT_BWD_DEEP");
+        return !(e && e[0] == '0');
+    }();
+    if (lbx * lby <= 128 && all_in_flight) {
+#define ZS_LBF_PICK(U) \
+    if (per_thread == (U)) kern = stdp ? k_latent_bwd_fast<FAM, true, U> : k_latent_bwd_fast<FAM, false, U>
+        ZS_LBF_PICK(5);
+        ZS_LBF_PICK(6);
+        ZS_LBF_PICK(7);
+        ZS_LBF_PICK(8);
+#undef ZS_LBF_PICK
+    }
+    launch_pdl(PDL_LATENT_BWD, kern, dim3(grid), block, 0, st, (float*)da, (float*)db, (const float*)gq, (const float*)gp,
+               (const float*)dz_up, (const float*)z, (const float*)a, (const float*)b, (const float*)pa,
+               (const float*)pb, reparam, (int)K, (int)M, (int)E);
     return true;
 }
 template <>

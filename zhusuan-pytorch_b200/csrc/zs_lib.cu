@@ -1,5 +1,6 @@
 // Library plumbing: version, error strings, device info.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "zs_common.cuh"
@@ -28,6 +29,14 @@ int sm_count() {
     }
     if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
+}
+
+int pdl_mask() {
+    static const int mask = [] {
+        const char* e = getenv("ZS_PDL");
+        return e ? atoi(e) : (PDL_LATENT_FWD | PDL_FUSED | PDL_SCALE);
+    }();
+    return mask;
 }
 
 }  // namespace zs

@@ -222,6 +222,8 @@ __device__ __forceinline__ void scale_buffer(T* __restrict__ buf, int64_t n, T s
 template <typename T>
 __global__ void __launch_bounds__(256) k_scale_inplace(T* __restrict__ b0, int64_t n0, T* __restrict__ b1, int64_t n1,
                                                        T* __restrict__ b2, int64_t n2, const T* __restrict__ scale) {
+    pdl_wait();
+    pdl_trigger();
     const T s = *scale;
     if (s == T(1)) return;
     scale_buffer(b0, n0, s);
@@ -438,11 +440,11 @@ int zs_scale_inplace(int dtype, void* buf0, int64_t n0, void* buf1, int64_t n1, 
     if (n == 0) return ZS_OK;
     const int grid = grid_for(n / 4 + 1, 256, 8);
     if (dtype == ZS_F32)
-        k_scale_inplace<float><<<grid, 256, 0, as_stream(stream)>>>((float*)buf0, n0, (float*)buf1, n1, (float*)buf2, n2,
-                                                                      (const float*)scale_dev);
+        launch_pdl(PDL_SCALE, k_scale_inplace<float>, dim3(grid), dim3(256), 0, as_stream(stream), (float*)buf0, n0, (float*)buf1, n1,
+                   (float*)buf2, n2, (const float*)scale_dev);
     else if (dtype == ZS_F64)
-        k_scale_inplace<double><<<grid, 256, 0, as_stream(stream)>>>((double*)buf0, n0, (double*)buf1, n1, (double*)buf2,
-                                                                       n2, (const double*)scale_dev);
+        launch_pdl(PDL_SCALE, k_scale_inplace<double>, dim3(grid), dim3(256), 0, as_stream(stream), (double*)buf0, n0, (double*)buf1,
+                   n1, (double*)buf2, n2, (const double*)scale_dev);
     else {
         set_last_error_msg("dtype must be ZS_F32 or ZS_F64");
         return ZS_ERR_DTYPE;

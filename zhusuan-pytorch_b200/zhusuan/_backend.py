@@ -86,7 +86,8 @@ def _declare(lib):
         "zs_sgmcmc_multi_step": (i32, [i32, i32, c.POINTER(ChainTensor), i32, dbl, dbl, dbl, i32, i32, u64, u64, vp, vp]),
         "zs_reinforce_step": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, vp]),
         "zs_allreduce_peer_flag_bytes": (i64, []),
-        "zs_allreduce_sum_peer": (i32, [c.POINTER(vp), c.POINTER(vp), i32, i32, i64, i64, i32, i32, vp]),
+        "zs_allreduce_sum_peer": (i32, [c.POINTER(vp), c.POINTER(vp), i32, i32, i64, i64, i32, i32, vp, i64, vp]),
+        "zs_allreduce_sum_nvls": (i32, [vp, vp, c.POINTER(vp), i32, i32, i64, i64, i32, i32, vp, i64, vp]),
         "zs_host_step_create": (i32, [c.POINTER(vp)]),
         "zs_host_step_destroy": (i32, [vp]),
         "zs_iw_step_host_workspace": (i64, [i64, i64, i64]),
@@ -488,9 +489,10 @@ def set_fused_impl(impl):
     check(load().zs_debug_set_fused_impl(int(impl)), "zs_debug_set_fused_impl")
 
 
-# zs_iw_bernoulli_fused_loss needs one zero-initialised counter word per stream that may run the launch: a small
+# zs_iw_bernoulli_fused_loss needs one zero-initialised workspace per stream that may run the launch: a small
 # per-device pool, handed out by stream id (host bookkeeping only, so it also works while a graph is being captured)
-_TICKET_WORDS = 256
+_LOSS_WS_BYTES = 8 + 2 * 160 * 8  # ZS_FUSED_LOSS_WS_BYTES
+_LOSS_WS_SLOTS = 64
 _tickets = {}
 
 
@@ -500,15 +502,15 @@ def _ticket_ptr(dev):
     if ent is None:
         if torch.cuda.is_current_stream_capturing():
             return None  # no allocation + memset inside a capture: the caller reduces cost[B] itself this once
-        ent = _tickets[idx] = (torch.zeros(_TICKET_WORDS, dtype=torch.int32, device=dev), {})
+        ent = _tickets[idx] = (torch.zeros(_LOSS_WS_SLOTS * _LOSS_WS_BYTES // 8, dtype=torch.int64, device=dev), {})
     words, slots = ent
     sid = torch.cuda.current_stream(dev).cuda_stream
     k = slots.get(sid)
     if k is None:
-        if len(slots) >= _TICKET_WORDS:
+        if len(slots) >= _LOSS_WS_SLOTS:
             return None
         k = slots[sid] = len(slots)
-    return ctypes.c_void_p(words.data_ptr() + 4 * k)
+    return ctypes.c_void_p(words.data_ptr() + _LOSS_WS_BYTES * k)
 
 
 def iw_bernoulli_fused(estimator, probs, x, logp_other, logq, grad_scale, need_dprobs=True, want_logpx=False,
@@ -673,13 +675,24 @@ def allreduce_peer_flag_bytes():
     return int(load().zs_allreduce_peer_flag_bytes())
 
 
-def allreduce_sum_peer(buf_ptrs, flag_ptrs, rank, first, count, flag_set, device, ctas=0):
+def allreduce_sum_peer(buf_ptrs, flag_ptrs, rank, first, count, flag_set, device, ctas=0, extra=None, extra_index=0):
     """SUM-all-reduce floats [first, first + count) of the ranks' peer-mapped buffers (zs_allreduce_sum_peer) on
-    torch's current stream of `device`.  buf_ptrs / flag_ptrs: per-rank base addresses (ints) as mapped here."""
+    torch's current stream of `device`.  buf_ptrs / flag_ptrs: per-rank base addresses (ints) as mapped here.
+    `extra` (a 1-element float32 CUDA tensor) is stored at float index `extra_index` of this rank's buffer first."""
     world = len(buf_ptrs)
     bufs = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in buf_ptrs])
     flags = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
-    _go("zs_allreduce_sum_peer", device, bufs, flags, int(rank), world, int(first), int(count), int(flag_set), int(ctas))
+    _go("zs_allreduce_sum_peer", device, bufs, flags, int(rank), world, int(first), int(count), int(flag_set), int(ctas),
+        _ptr(extra), int(extra_index))
+
+
+def allreduce_sum_nvls(mc_ptr, local_ptr, flag_ptrs, rank, first, count, flag_set, device, ctas=0, extra=None,
+                       extra_index=0):
+    """The same exchange through the NVSwitch multicast mapping `mc_ptr` of the buffer (zs_allreduce_sum_nvls)."""
+    world = len(flag_ptrs)
+    flags = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+    _go("zs_allreduce_sum_nvls", device, ctypes.c_void_p(int(mc_ptr)), ctypes.c_void_p(int(local_ptr)), flags, int(rank),
+        world, int(first), int(count), int(flag_set), int(ctas), _ptr(extra), int(extra_index))
 
 
 # ----------------------------------------------------------------------------- host-buffer step (e2e)

@@ -18,6 +18,7 @@ How a data-parallel step is put together:
 `all_reduce_gradients` keeps the round-1 call signature on top of the same machinery.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -125,11 +126,13 @@ class GradientBucket(object):
                     self._peer_error = repr(e)
         self.flat = self._peer.flat if self._peer is not None else torch.zeros(total, dtype=self.dtype,
                                                                                   device=self.device)
+        self._slot_index = starts[-1] + sizes[-1] - 1  # the objective's slot: last element of the last segment
         self.segments, self._ranges = [], []
         for st, n in zip(starts, sizes):
             self.segments.append(self.flat[st:st + n])
             self._ranges.append((st, (n + 3) // 4 * 4))
         self._comm_stream = None
+        self._zero_pending = False
         self._views, self._seg_of, self._pending, self._works = {}, {}, [], []
         for si, g in enumerate(groups):
             off = starts[si]
@@ -143,16 +146,39 @@ class GradientBucket(object):
                 off += p.numel()
                 if hasattr(p, "register_post_accumulate_grad_hook"):
                     p.register_post_accumulate_grad_hook(self._on_grad)
+                if self.flat.is_cuda:
+                    p.register_hook(self._join_zero)
         self._sizes = [len(g) for g in groups] or [0]
         self.zero_grad()
 
     # -- per step ---------------------------------------------------------------------------------
-    def zero_grad(self):
+    def zero_grad(self, overlap=True):
         """Zero every gradient (one memset of the flat buffer) and re-arm the segment counters.  Use this instead
-        of optimizer.zero_grad(set_to_none=True), which would detach the parameters from the buffer."""
-        self.flat.zero_()
+        of optimizer.zero_grad(set_to_none=True), which would detach the parameters from the buffer.
+        `overlap` (CUDA buffers): the memset runs on the bucket's side stream, ordered after everything the current
+        stream has enqueued so far (the optimizer's reads of the gradients); the current stream joins it right before
+        the first gradient is accumulated into the buffer (a tensor hook on every parameter) or before the first
+        collective of the step, whichever comes first -- so zeroing overlaps the forward pass instead of delaying it."""
         self._pending = list(self._sizes)
         self._works = []
+        if not (overlap and self.flat.is_cuda):
+            self.flat.zero_()
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self.flat.zero_()
+        self._zero_pending = True
+
+    def _join_zero(self, grad=None):
+        """The current stream waits for an overlapped zero_grad() (no host blocking).  Doubles as the parameters'
+        tensor hook, which autograd runs BEFORE it accumulates the gradient into the buffer."""
+        if self._zero_pending:
+            self._zero_pending = False
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        return None
 
     @property
     def loss_slot(self):
@@ -171,10 +197,15 @@ class GradientBucket(object):
         if self._pending[si] == 0 and si < len(self.segments) - 1:
             self._launch(si)
 
-    def _launch(self, si):
+    def _launch(self, si, extra=None):
+        self._join_zero()
         if not (is_initialized() and dist.get_world_size(self.group) > 1):
+            if extra is not None:
+                self.loss_slot.copy_(extra)
             return
         if self._peer is None:
+            if extra is not None:
+                self.loss_slot.copy_(extra)
             self._works.append(dist.all_reduce(self.segments[si], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             return
         # this library's kernel, on a side stream ordered after what the compute stream has enqueued so far: the
@@ -184,8 +215,12 @@ class GradientBucket(object):
             self._comm_stream = torch.cuda.Stream(device=self.device)
         self._comm_stream.wait_stream(cur)
         first, count = self._ranges[si]
+        slot = self._slot_index
+        if extra is not None and not (extra.is_cuda and extra.dtype == torch.float32 and extra.is_contiguous()):
+            self.loss_slot.copy_(extra)
+            extra = None
         with torch.cuda.stream(self._comm_stream):
-            self._peer.all_reduce(first, count, flag_set=si % _be.PEER_FLAG_SETS)
+            self._peer.all_reduce(first, count, flag_set=si % _be.PEER_FLAG_SETS, extra=extra, extra_index=slot)
         self._works.append(_StreamJoin(self._comm_stream, self.device))
 
     def reduce_segment(self, si):
@@ -195,9 +230,8 @@ class GradientBucket(object):
     def finish(self, loss=None):
         """Store this rank's share of the objective in its slot, launch the last segment's all-reduce and make the
         current stream wait for every collective of the step."""
-        if loss is not None:
-            self.loss_slot.copy_(loss.detach().reshape(1))
-        self._launch(len(self.segments) - 1)
+        # the peer kernels store the scalar into the slot themselves (no copy launch); other backends copy it
+        self._launch(len(self.segments) - 1, extra=None if loss is None else loss.detach().reshape(1))
         for w in self._works:
             w.wait()  # stream-level wait: the host does not block
         self._works = []
@@ -238,13 +272,30 @@ class _PeerBuffer(object):
         self.rank = self.handle.rank
         self.buf_ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.flag_ptrs = [p + 4 * n_pad for p in self.buf_ptrs]
+        # NVSwitch multicast mapping of the same allocation (0 when the fabric has none): the NVLS kernel
+        mc = 0
+        try:
+            mc = int(self.handle.multicast_ptr)
+        except Exception:
+            mc = 0
+        if os.environ.get("ZS_PEER_NVLS", "1") == "0" or self.storage.data_ptr() != self.buf_ptrs[self.handle.rank]:
+            mc = 0
+        self.mc_ptr = mc
+        self.variant = "nvls" if mc else "p2p"
         self.flat = self.storage[:n]
         self.device = self.storage.device
         torch.cuda.synchronize(self.device)
         dist.barrier(group=pg)  # every rank's flags are zero before anyone's first kernel signals
 
-    def all_reduce(self, first, count, flag_set=0):
-        _be.allreduce_sum_peer(self.buf_ptrs, self.flag_ptrs, self.rank, first, count, flag_set, self.device)
+    def all_reduce(self, first, count, flag_set=0, extra=None, extra_index=0):
+        """`extra`: a 1-element float32 tensor on this device that the kernel stores at float index `extra_index` of
+        this rank's buffer before the exchange (the objective's slot: no copy launch)."""
+        if self.mc_ptr:
+            _be.allreduce_sum_nvls(self.mc_ptr, self.buf_ptrs[self.rank], self.flag_ptrs, self.rank, first, count,
+                                   flag_set, self.device, extra=extra, extra_index=extra_index)
+        else:
+            _be.allreduce_sum_peer(self.buf_ptrs, self.flag_ptrs, self.rank, first, count, flag_set, self.device,
+                                   extra=extra, extra_index=extra_index)
 
 
 _legacy_buckets = {}
