@@ -588,6 +588,11 @@ def measure_api(torch, dist, zd, be, vimco, dev, B, world, rank, steps, warm, us
                 "backend_is": "peer = zs_allreduce_sum_peer, this library's kernel over NVLink peer memory; "
                               "nccl = torch.distributed.all_reduce",
                 "peer_unavailable": getattr(bucket, "_peer_error", None),
+                "peer_variant": getattr(bucket._peer, "variant", None),
+                "peer_variant_is": "nvls = zs_allreduce_sum_nvls (NVSwitch multicast: multimem.ld_reduce / multimem.st), "
+                                   "p2p = zs_allreduce_sum_peer (peer loads / stores); the bucket times both once at "
+                                   "construction and keeps the faster one for this world size",
+                "peer_tuned_us": getattr(bucket._peer, "tuned_us", None),
                 "what": "every step: SUM all-reduce of the example VAE's %d decoder + %d encoder parameter gradients and "
                         "the scalar objective, one bucket (what a 25 MB DDP bucket would hold), launched when backward "
                         "is done; zhusuan.distributed.GradientBucket.  ZS_BENCH_SEGMENTS=2: decoder segment launched "

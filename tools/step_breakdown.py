@@ -35,9 +35,13 @@ def seq(n):
     return fn
 
 
-def timed(fn, reps=300):
-    run, how, _ = bench.capture(torch, fn, dev, True)
-    for _ in range(20):
+PER_GRAPH = 8  # repetitions captured into one graph: a replay then lasts long enough that the host's graph-launch
+               # rate (~8 us per replay from Python) is not what the events measure
+
+
+def timed(fn, reps=100):
+    run, how, _ = bench.capture(torch, lambda: [fn() for _ in range(PER_GRAPH)], dev, True)
+    for _ in range(5):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,11 +50,12 @@ def timed(fn, reps=300):
         run()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3
+    return e0.elapsed_time(e1) / (reps * PER_GRAPH) * 1e3
 
 
 names = {1: "fwd", 2: "fwd+fused", 3: "fwd+fused+bwd", 4: "fwd+fused+fill+scale+bwd", 5: "same, loss written by the fused launch"}
-res = {"pdl": os.environ.get("ZS_PDL", "15"), "bwd_deep": os.environ.get("ZS_LATENT_BWD_DEEP", "1"), "B": B}
+res = {"pdl": os.environ.get("ZS_PDL", "7"), "bwd_deep": os.environ.get("ZS_LATENT_BWD_DEEP", "1"),
+       "fwd_rows": os.environ.get("ZS_LATENT_FWD_ROWS", "1"), "B": B}
 for n in (1, 2, 3, 4, 5):
     res[names[n]] = round(timed(seq(n)), 2)
 fused_only = lambda: ks.fused_only(torch.zeros(K, B, device=dev), torch.zeros(K, B, device=dev))

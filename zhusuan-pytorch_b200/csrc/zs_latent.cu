@@ -588,6 +588,7 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, sizeof(T) == 4 ? 4 : 1)
 // sampling kernel's.  Sums are re-associated (sequential over the row) against the reference's order: 1e-7 relative.
 // ---------------------------------------------------------------------------------------------
 constexpr int LR_WARPS = 4;
+constexpr int LR_ILP = 5;  // units of a row in flight per lane
 
 template <int FAM, bool STDP>
 __global__ void __launch_bounds__(LR_WARPS * 32)
@@ -608,6 +609,9 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
     float* s_p = s_q + 32 * QP;                  // [32][QP] ... of log p
     float* stage = s_p + 32 * QP + warp * 32 * EP;  // this warp's z block [32][EP]
     const float c = normal_c<float>();
+    // the stream position: the leader's load is issued now and consumed after the transform (rng_acquire_peeked)
+    unsigned long long rng_base = 0ull;
+    if (rs != nullptr && threadIdx.x == 0) rng_base = *reinterpret_cast<volatile unsigned long long*>(rs);
     // ---- the CTA's parameter transform, once
     for (int u = threadIdx.x; u < rows * E4; u += LR_WARPS * 32) {
         const int r = (int)(((unsigned)u * inv_e4) >> 16), j = u - r * E4;
@@ -652,9 +656,8 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
         s_q[r * QP + j] = uq;
         s_p[r * QP + j] = up;
     }
-    // the stream position is read by the CTA's leader meanwhile; its barrier also publishes the transform
-    offset = rng_acquire(offset, rs, nullptr, true);
-    __syncthreads();
+    // its barrier also publishes the transform
+    offset = rng_acquire_peeked(offset, rs, rng_base);
     const bool active = lane < rows;
     float cq = 0.f, cp = 0.f;
     if (active) {
@@ -671,45 +674,55 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
         float accq = cq, accp = cp;
         const unsigned unit0 = (unsigned)k * ME4 + (unsigned)(m0 + lane) * (unsigned)E4;
         if (active) {
-#pragma unroll 2
-            for (int j = 0; j < E4; ++j) {
-                float n4[4];
-                if (noise_in) {
-                    const float4 t = *reinterpret_cast<const float4*>(noise_in + 4 * (size_t)(unit0 + j));
-                    n4[0] = t.x; n4[1] = t.y; n4[2] = t.z; n4[3] = t.w;
-                } else if (FAM == FAM_NORMAL) {
-                    philox_normal4((uint64_t)(unit0 + j), offset, seed, n4);
-                } else {
-                    philox_uniform4((uint64_t)(unit0 + j), offset, seed, n4);
-                }
-                const float4 av = *reinterpret_cast<const float4*>(prow + 4 * j);
-                float4 zv;
-                if (FAM == FAM_NORMAL) {
-                    const float4 bv = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
-                    const float4 h = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
-                    zv = make_float4(fmaf(bv.x, n4[0], av.x), fmaf(bv.y, n4[1], av.y), fmaf(bv.z, n4[2], av.z),
-                                     fmaf(bv.w, n4[3], av.w));  // normal.py:105
-                    const float d0 = zv.x - av.x, d1 = zv.y - av.y, d2 = zv.z - av.z, d3 = zv.w - av.w;  // :121-124
-                    accq -= (h.x * (d0 * d0) + h.y * (d1 * d1)) + (h.z * (d2 * d2) + h.w * (d3 * d3));
-                    if (STDP) {
-                        accp -= 0.5f * ((zv.x * zv.x + zv.y * zv.y) + (zv.z * zv.z + zv.w * zv.w));
+            // LR_ILP units at a time: their Philox / Box-Muller chains are independent and the kernel runs at ~11 warps
+            // per SM, so the instruction-level parallelism is what hides the chains' latency
+            for (int j0 = 0; j0 < E4; j0 += LR_ILP) {
+                float n4[LR_ILP][4];
+#pragma unroll
+                for (int i = 0; i < LR_ILP; ++i) {
+                    const int j = j0 + i < E4 ? j0 + i : E4 - 1;  // the tail recomputes the last unit (discarded below)
+                    if (noise_in) {
+                        const float4 t = *reinterpret_cast<const float4*>(noise_in + 4 * (size_t)(unit0 + j));
+                        n4[i][0] = t.x; n4[i][1] = t.y; n4[i][2] = t.z; n4[i][3] = t.w;
+                    } else if (FAM == FAM_NORMAL) {
+                        philox_normal4((uint64_t)(unit0 + j), offset, seed, n4[i]);
                     } else {
-                        const float4 pm = *reinterpret_cast<const float4*>(prow + 3 * PSF + 4 * j);
-                        const float4 hp = *reinterpret_cast<const float4*>(prow + 4 * PSF + 4 * j);
-                        const float e0 = zv.x - pm.x, e1 = zv.y - pm.y, e2 = zv.z - pm.z, e3 = zv.w - pm.w;
-                        accp -= (hp.x * (e0 * e0) + hp.y * (e1 * e1)) + (hp.z * (e2 * e2) + hp.w * (e3 * e3));
-                    }
-                } else {
-                    const float4 l0 = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
-                    zv = make_float4(n4[0] < av.x ? 1.f : 0.f, n4[1] < av.y ? 1.f : 0.f, n4[2] < av.z ? 1.f : 0.f,
-                                     n4[3] < av.w ? 1.f : 0.f);  // bernoulli.py:79
-                    accq += (zv.x * l0.x + zv.y * l0.y) + (zv.z * l0.z + zv.w * l0.w);
-                    if (!STDP) {
-                        const float4 pm = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
-                        accp += (zv.x * pm.x + zv.y * pm.y) + (zv.z * pm.z + zv.w * pm.w);
+                        philox_uniform4((uint64_t)(unit0 + j), offset, seed, n4[i]);
                     }
                 }
-                *reinterpret_cast<float4*>(stage + lane * EP + 4 * j) = zv;
+#pragma unroll
+                for (int i = 0; i < LR_ILP; ++i) {
+                    const int j = j0 + i;
+                    if (j >= E4) break;
+                    const float4 av = *reinterpret_cast<const float4*>(prow + 4 * j);
+                    float4 zv;
+                    if (FAM == FAM_NORMAL) {
+                        const float4 bv = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
+                        const float4 h = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
+                        zv = make_float4(fmaf(bv.x, n4[i][0], av.x), fmaf(bv.y, n4[i][1], av.y), fmaf(bv.z, n4[i][2], av.z),
+                                         fmaf(bv.w, n4[i][3], av.w));  // normal.py:105
+                        const float d0 = zv.x - av.x, d1 = zv.y - av.y, d2 = zv.z - av.z, d3 = zv.w - av.w;  // :121-124
+                        accq -= (h.x * (d0 * d0) + h.y * (d1 * d1)) + (h.z * (d2 * d2) + h.w * (d3 * d3));
+                        if (STDP) {
+                            accp -= 0.5f * ((zv.x * zv.x + zv.y * zv.y) + (zv.z * zv.z + zv.w * zv.w));
+                        } else {
+                            const float4 pm = *reinterpret_cast<const float4*>(prow + 3 * PSF + 4 * j);
+                            const float4 hp = *reinterpret_cast<const float4*>(prow + 4 * PSF + 4 * j);
+                            const float e0 = zv.x - pm.x, e1 = zv.y - pm.y, e2 = zv.z - pm.z, e3 = zv.w - pm.w;
+                            accp -= (hp.x * (e0 * e0) + hp.y * (e1 * e1)) + (hp.z * (e2 * e2) + hp.w * (e3 * e3));
+                        }
+                    } else {
+                        const float4 l0 = *reinterpret_cast<const float4*>(prow + PSF + 4 * j);
+                        zv = make_float4(n4[i][0] < av.x ? 1.f : 0.f, n4[i][1] < av.y ? 1.f : 0.f,
+                                         n4[i][2] < av.z ? 1.f : 0.f, n4[i][3] < av.w ? 1.f : 0.f);  // bernoulli.py:79
+                        accq += (zv.x * l0.x + zv.y * l0.y) + (zv.z * l0.z + zv.w * l0.w);
+                        if (!STDP) {
+                            const float4 pm = *reinterpret_cast<const float4*>(prow + 2 * PSF + 4 * j);
+                            accp += (zv.x * pm.x + zv.y * pm.y) + (zv.z * pm.z + zv.w * pm.w);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(stage + lane * EP + 4 * j) = zv;
+                }
             }
             if (logq) logq[(size_t)k * M + m0 + lane] = accq;
             if (logp) logp[(size_t)k * M + m0 + lane] = accp;

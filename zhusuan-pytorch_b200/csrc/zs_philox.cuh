@@ -84,6 +84,27 @@ __device__ __forceinline__ uint64_t rng_acquire(uint64_t offset, unsigned long l
     return eff;
 }
 
+// The same protocol for a kernel that has work to do between the leader's read of the state and its first draw: the
+// leader loads state[0] early (`base`, any time after the kernel started) and every thread calls this afterwards.
+// Always advances; contains the CTA barrier (which also publishes whatever the CTA wrote to shared memory before it).
+__device__ __forceinline__ uint64_t rng_acquire_peeked(uint64_t offset, unsigned long long* state, unsigned long long base) {
+    __shared__ unsigned long long s_rng_base2;
+    const bool leader = threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0;
+    if (leader) s_rng_base2 = state ? base : 0ull;
+    __syncthreads();
+    const uint64_t eff = offset + s_rng_base2;
+    if (leader && state != nullptr) {
+        __threadfence();
+        unsigned int* arrivals = reinterpret_cast<unsigned int*>(state + 1);
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(arrivals, 1u) == total - 1u) {
+            *reinterpret_cast<volatile unsigned int*>(arrivals) = 0u;
+            *reinterpret_cast<volatile unsigned long long*>(state) = base + ZS_RNG_TICK_DEV;
+        }
+    }
+    return eff;
+}
+
 // Box-Muller on two words -> two standard normals, written for instruction count: the sampling kernels are
 // issue-bound on the noise (ncu round 2: 350 instructions per float4 of latents, two thirds of them RNG), and libm's
 // logf / IEEE sqrtf with their range and denormal handling were ~45 of the ~110 Box-Muller instructions per pair.

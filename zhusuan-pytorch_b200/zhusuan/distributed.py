@@ -119,6 +119,7 @@ class GradientBucket(object):
             if backend in ("auto", "peer"):
                 try:
                     self._peer = _PeerBuffer(total, self.device, self.dtype, group)
+                    self._peer.tune(total, group)
                     self.backend = "peer"
                 except Exception as e:  # no peer access / symmetric memory: torch.distributed does the exchange
                     if backend == "peer":
@@ -152,13 +153,15 @@ class GradientBucket(object):
         self.zero_grad()
 
     # -- per step ---------------------------------------------------------------------------------
-    def zero_grad(self, overlap=True):
+    def zero_grad(self, overlap=False):
         """Zero every gradient (one memset of the flat buffer) and re-arm the segment counters.  Use this instead
         of optimizer.zero_grad(set_to_none=True), which would detach the parameters from the buffer.
-        `overlap` (CUDA buffers): the memset runs on the bucket's side stream, ordered after everything the current
+        `overlap=True` (CUDA buffers): the memset runs on the bucket's side stream, ordered after everything the current
         stream has enqueued so far (the optimizer's reads of the gradients); the current stream joins it right before
         the first gradient is accumulated into the buffer (a tensor hook on every parameter) or before the first
-        collective of the step, whichever comes first -- so zeroing overlaps the forward pass instead of delaying it."""
+        collective of the step, whichever comes first, so zeroing overlaps the forward pass.  Off by default: for a
+        5 MB bucket the memset is ~3 us, and inside a captured CUDA graph the fork / join around it measured 4.5 us
+        MORE than running it in line (N = 2: 113.8 against 109.3 us per step); it pays for buckets of 100s of MB."""
         self._pending = list(self._sizes)
         self._works = []
         if not (overlap and self.flat.is_cuda):
@@ -210,12 +213,21 @@ class GradientBucket(object):
             return
         # this library's kernel, on a side stream ordered after what the compute stream has enqueued so far: the
         # exchange overlaps whatever backward launches next; finish() joins the streams
+        first, count = self._ranges[si]
+        slot = self._slot_index
+        # The step's LAST segment has nothing left to overlap with (finish() makes the compute stream wait for it
+        # right away), so it is launched in the compute stream itself: a fork / join pair inside a captured graph
+        # costs more than it hides.  Earlier segments go to the side stream and overlap the rest of backward.
+        if si == len(self.segments) - 1 and os.environ.get("ZS_BUCKET_STREAM") != "side":
+            if extra is not None and not (extra.is_cuda and extra.dtype == torch.float32 and extra.is_contiguous()):
+                self.loss_slot.copy_(extra)
+                extra = None
+            self._peer.all_reduce(first, count, flag_set=si % _be.PEER_FLAG_SETS, extra=extra, extra_index=slot)
+            return
         cur = torch.cuda.current_stream(self.device)
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.device)
         self._comm_stream.wait_stream(cur)
-        first, count = self._ranges[si]
-        slot = self._slot_index
         if extra is not None and not (extra.is_cuda and extra.dtype == torch.float32 and extra.is_contiguous()):
             self.loss_slot.copy_(extra)
             extra = None
@@ -286,6 +298,38 @@ class _PeerBuffer(object):
         self.device = self.storage.device
         torch.cuda.synchronize(self.device)
         dist.barrier(group=pg)  # every rank's flags are zero before anyone's first kernel signals
+
+    def tune(self, count, group=None, iters=30):
+        """Pick the faster exchange kernel for THIS world size and bucket size by timing both on the buffer (its contents
+        are zero at construction, so summing them repeatedly changes nothing).  The multicast form moves ~(1 + 1/N)
+        buffer volumes over each GPU's links, peer loads / stores 2(N-1)/N: at N = 2 peer access wins (measured 20.6
+        against 27.8 us for the 5.4 MB bucket), from N = 4 on the switch should.  Every rank times both and the ranks
+        agree on the maxima, so they make the same choice.  ZS_PEER_NVLS=0 / 1 forces one."""
+        forced = os.environ.get("ZS_PEER_NVLS")
+        if not self.mc_ptr or forced in ("0", "1") or count <= 0:
+            return self.variant
+        mc = self.mc_ptr
+        times = []
+        for use_mc in (0, mc):
+            self.mc_ptr = use_mc
+            for _ in range(5):
+                self.all_reduce(0, count)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                self.all_reduce(0, count)
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            times.append(e0.elapsed_time(e1) / iters)
+        t = torch.tensor(times, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        t = [float(v) for v in t]
+        self.tuned_us = {"p2p": round(t[0] * 1e3, 2), "nvls": round(t[1] * 1e3, 2)}
+        self.mc_ptr = mc if t[1] < t[0] else 0
+        self.variant = "nvls" if self.mc_ptr else "p2p"
+        return self.variant
 
     def all_reduce(self, first, count, flag_set=0, extra=None, extra_index=0):
         """`extra`: a 1-element float32 tensor on this device that the kernel stores at float index `extra_index` of
