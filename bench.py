@@ -807,10 +807,8 @@ def cpu_baseline_subprocess(workload):
     return cb
 
 
-def e2e_block(torch, dist, be, zs, dev, world, rank, vimco, B, n_e2e):
-    """The same step through the PUBLIC Python API with pinned HOST tensors as leaves: the package uploads what the
-    kernels need, runs them, and returns the loss and the gradients in host memory.  For the host-resident likelihood
-    tensor the objective takes the chunk-pipelined route (zs_iw_step_host_begin)."""
+def e2e_setup(torch, vimco, B, rank=0):
+    """The step of e2e_block as a callable: step() -> float(loss), every leaf and result in (pinned) host memory."""
     from zhusuan.distributions import Bernoulli, Normal
     from zhusuan.framework import BayesianNet
     from zhusuan.variational import ImportanceWeightedObjective
@@ -863,6 +861,15 @@ def e2e_block(torch, dist, be, zs, dev, world, rank, vimco, B, n_e2e):
         assert probs.grad is not None and probs.grad.device.type == "cpu" and a.grad is not None
         return float(loss.detach())
 
+    return step
+
+
+def e2e_block(torch, dist, be, zs, dev, world, rank, vimco, B, n_e2e):
+    """The same step through the PUBLIC Python API with pinned HOST tensors as leaves: the package uploads what the
+    kernels need, runs them, and returns the loss and the gradients in host memory.  For the host-resident likelihood
+    tensor the objective takes the chunk-pipelined route (zs_iw_step_host_begin)."""
+    K, Z, X = K_PART, Z_DIM, X_DIM
+    step = e2e_setup(torch, vimco, B, rank)
     for _ in range(3):
         step()
     if world > 1:

@@ -312,6 +312,10 @@ int zs_iw_bernoulli_fused_loss(int estimator, float* loss_out, void* workspace, 
  * (the ZS_FUSED_IMPL environment variable, read once per process).  Process-wide; tests and tools only. */
 int zs_debug_set_trace(void* device_buffer);
 int zs_debug_set_fused_impl(int impl);
+/* zs_debug_set_latent_fwd: which float32 / KBCAST forward the latent entry points launch: -1 = by shape (default:
+ * the row-per-thread kernel for grids several waves deep, the lane-per-unit kernel otherwise), 0 = lane-per-unit,
+ * 1 = row-per-thread wherever the shape qualifies (E <= 64).  Process-wide; tests and tools only.          */
+int zs_debug_set_latent_fwd(int impl);
 
 /* ---- SG-MCMC updates across parallel chains (one pass) -----------------------
  * w_out receives the updated chain state and may alias w (in place); the reference

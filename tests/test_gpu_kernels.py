@@ -631,7 +631,7 @@ def test_iw_step_host_begin_wait_device_scalars(B):
     assert np.array_equal(dprobs.numpy(), host(r["dprobs"]))
 
 
-def test_latent_kernels_full_size_properties():
+def test_latent_kernels_full_size_properties(latent_fwd_impl):
     """BASELINE config 2 / 3 size (K=50, B=1024, Z=40): the fused latent kernels == the stand-alone kernels on the
     same Philox stream (sample, log q, log p, joint backward), and sample moments."""
     K, M, E = 50, 1024, 40
@@ -806,11 +806,21 @@ def test_reinforce_vs_oracle(oracle, dt, n):
 
 
 # ----------------------------------------------------------------------------- fused latent-node kernels
+@pytest.fixture(params=["auto", "rows", "lanes"])
+def latent_fwd_impl(request):
+    """zs_debug_set_latent_fwd is process-wide: every latent test runs with the shape-based choice, with the
+    row-per-thread forward forced (wherever the shape qualifies) and with the lane-per-unit forward forced."""
+    be.set_latent_fwd_impl({"auto": -1, "rows": 1, "lanes": 0}[request.param])
+    yield request.param
+    be.set_latent_fwd_impl(-1)
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("K,M,E,mode,prior", [(50, 64, 40, KBCAST, "std"), (50, 64, 40, KBCAST, "given"),
                                                (7, 5, 8, FULL, "std"), (3, 130, 132, KBCAST, "given"),
-                                               (1, 9, 4, KBCAST, "std")])
-def test_normal_latent_fused(oracle, dt, K, M, E, mode, prior):
+                                               (1, 9, 4, KBCAST, "std"), (9, 77, 64, KBCAST, "given"),
+                                               (50, 2500, 40, KBCAST, "std")])
+def test_normal_latent_fused(oracle, latent_fwd_impl, dt, K, M, E, mode, prior):
     """sample + log q + log p(z) in one launch and their joint backward == the composition of the
     per-stage oracle functions (normal.py:89-126 and its autograd)."""
     rng = np.random.RandomState(21)
@@ -864,8 +874,9 @@ def test_normal_latent_fused(oracle, dt, K, M, E, mode, prior):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("K,M,E,prior", [(50, 64, 40, None), (6, 7, 8, "given")])
-def test_bernoulli_latent_fused(oracle, dt, K, M, E, prior):
+@pytest.mark.parametrize("K,M,E,prior", [(50, 64, 40, None), (6, 7, 8, "given"), (11, 45, 24, "given"),
+                                         (50, 2500, 40, None)])
+def test_bernoulli_latent_fused(oracle, latent_fwd_impl, dt, K, M, E, prior):
     rng = np.random.RandomState(22)
     pq = rng.uniform(0.05, 0.95, size=(M, E)).astype(dt)
     pp = rng.uniform(0.2, 0.8, size=(M, E)).astype(dt) if prior else None

@@ -42,6 +42,5 @@ def api():
     return p.grad
 t("_ops.iw_bernoulli_fused_host + backward", api)
 import bench
-host = {"probs": probs_h, "x": x_h, "mean": (0.5*torch.randn(B,40)).pin_memory(), "std": torch.rand(B,40).add(0.5).pin_memory(), "zeros": torch.zeros(B,40).pin_memory(), "ones": torch.ones(B,40).pin_memory()}
-import zhusuan
-t("bench.api_step_host (full public API)", lambda: bench.api_step_host(torch, zhusuan, False, host))
+step = bench.e2e_setup(torch, False, B)
+t("bench.e2e_setup step (full public API)", step)

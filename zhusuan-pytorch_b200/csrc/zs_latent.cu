@@ -738,15 +738,21 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
     }
 }
 
+static int g_latent_fwd_override = -1;
+static bool g_latent_fwd_override_set = false;
+
 template <int FAM>
 static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float* a, int a_mode, const float* b,
                                 const float* pa, const float* pb, const float* noise_in, int64_t K, int64_t M,
                                 int64_t E4, uint64_t seed, uint64_t offset, unsigned long long* rs, cudaStream_t st) {
-    static const bool enabled = [] {  // developer knob: ZS_LATENT_FWD_ROWS=0 keeps the lane-per-unit kernel
+    // -1: by shape (below); 0: never (lane-per-unit kernel); 1: whenever the shape qualifies.  ZS_LATENT_FWD_ROWS sets
+    // the process default, zs_debug_set_latent_fwd overrides it at run time (tests run both kernels on every shape).
+    static const int env_choice = [] {
         const char* e = getenv("ZS_LATENT_FWD_ROWS");
-        return !(e && e[0] == '0');
+        return e ? (e[0] == '0' ? 0 : 1) : -1;
     }();
-    if (!enabled || a_mode != ZS_KBCAST || E4 > 16 || E4 < 1 || K < 1 || M < 1 || K * M * E4 >= ((int64_t)1 << 31))
+    const int choice = g_latent_fwd_override >= -1 && g_latent_fwd_override_set ? g_latent_fwd_override : env_choice;
+    if (choice == 0 || a_mode != ZS_KBCAST || E4 > 16 || E4 < 1 || K < 1 || M < 1 || K * M * E4 >= ((int64_t)1 << 31))
         return false;
     const int E = (int)(4 * E4), EP = E + 4, QP = (int)E4 + 1;
     const bool stdp = FAM == FAM_NORMAL ? (pa == nullptr && pb == nullptr) : pa == nullptr;
@@ -759,6 +765,11 @@ static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float*
         per_warp *= 2;
     int64_t KS = (K + LR_WARPS * per_warp - 1) / (LR_WARPS * per_warp);
     if (KS > 65535 || tiles >= (int64_t)2147483647) return false;
+    // Measured with tools/step_breakdown.py at K = 50, Z = 40 (profiles/r2_notes.md): the row form executes a third
+    // fewer instructions but runs few, fat warps, so it wins once the grid is several waves deep (B = 4096: 20.5
+    // against 27.1 us, B = 8192: 35.3 against 65.5 us), ties at B = 1024 (416 CTAs, 2.8 per SM) and loses below
+    // (B = 128: 5.4 against 3.6 us).  By default it takes grids of at least six CTAs per SM.
+    if (choice < 0 && tiles * KS < (int64_t)sm_count() * 6) return false;
     const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
     auto kern = stdp ? k_latent_fwd_rows<FAM, true> : k_latent_fwd_rows<FAM, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -1108,6 +1119,13 @@ static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp,
 }  // namespace zs
 
 using namespace zs;
+
+extern "C" int zs_debug_set_latent_fwd(int impl) {
+    ZS_REQUIRE(impl >= -1 && impl <= 1, ZS_ERR_ARG);
+    zs::g_latent_fwd_override = impl;
+    zs::g_latent_fwd_override_set = true;
+    return ZS_OK;
+}
 
 extern "C" {
 

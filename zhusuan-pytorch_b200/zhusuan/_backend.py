@@ -79,6 +79,7 @@ def _declare(lib):
         "zs_scale_inplace": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp]),
         "zs_debug_set_trace": (i32, [vp]),
         "zs_debug_set_fused_impl": (i32, [i32]),
+        "zs_debug_set_latent_fwd": (i32, [i32]),
         "zs_sgld_step": (i32, [i32, vp, vp, vp, vp, i64, dbl, u64, u64, vp, vp]),
         "zs_psgld_step": (i32, [i32, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, u64, u64, vp, vp]),
         "zs_sghmc_pre": (i32, [i32, vp, vp, vp, vp, i64, dbl, i32, i32, u64, u64, vp, vp]),
@@ -482,6 +483,11 @@ def fused_logits_supported(K, X, dtype):
     slot = (K * inner * 4 + 127) // 128 * 128
     fixed = 6 * X * 4 + 16 + 6 * kpad * 8 + 12 * kpad * 4 + 64
     return (nbox + 1) * (slot + 16) + fixed <= 227 * 1024
+
+
+def set_latent_fwd_impl(impl):
+    """Developer hook: -1 = by shape, 0 = lane-per-unit forward, 1 = row-per-thread forward (zs_debug_set_latent_fwd)."""
+    check(load().zs_debug_set_latent_fwd(int(impl)), "zs_debug_set_latent_fwd")
 
 
 def set_fused_impl(impl):
