@@ -41,7 +41,9 @@
 extern "C" {
 #endif
 
-#define ZS_ABI_VERSION 2
+/* 3: zs_allreduce_sum_peer takes (extra_src, extra_index); new: zs_allreduce_sum_nvls, zs_iw_bernoulli_fused_loss,
+ *    zs_debug_set_latent_fwd.  2: device-side Philox state, handle-based host step, flags argument of the fused kernel. */
+#define ZS_ABI_VERSION 3
 
 typedef void* zs_stream_t; /* cudaStream_t */
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in _declared() if not hasattr(lib, n)]
     assert not missing, missing
     lib.zs_abi_version.restype = ctypes.c_int
-    assert lib.zs_abi_version() == _backend.ABI_VERSION == 2
+    assert lib.zs_abi_version() == _backend.ABI_VERSION == 3
     lib.zs_strerror.restype = ctypes.c_char_p
     assert lib.zs_strerror(0) == b"ok" and b"dtype" in lib.zs_strerror(-2)
 

@@ -22,7 +22,7 @@ FUSED_ACCUMULATE_COST, FUSED_LOGITS, FUSED_COST_SCALED = 1, 2, 4
 ALG_SGLD, ALG_PSGLD, ALG_SGHMC_PRE, ALG_SGHMC_POST = 0, 1, 2, 3
 CHAIN_MAX_TENSORS = 32
 IMPL_DEFAULT, IMPL_RING, IMPL_BOX, IMPL_BOXG = -1, 2, 3, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 launch_count = 0  # kernels launched through this binding (bench.py's gpu_launches)
