@@ -1,25 +1,33 @@
 #!/bin/bash
-# Multi-GPU session (gpurun --gpus N): the 2-rank correctness test, the data-parallel bench at N ranks, and the
-# N = 1 diagnosis of the per-step overhead an initialised NCCL communicator adds.
-# Usage: bash tools/gpu_session_multi.sh TAG N
+# Multi-GPU session (gpurun --gpus N): the 2-rank correctness test (three exchange backends), the exchange microbench
+# (both kernels of this library against NCCL, with a correctness check) and the data-parallel bench at N ranks.
+# Usage: bash tools/gpu_session_multi.sh TAG N [variants]
+#   variants: also time the N-rank step with the exchange / bucket-zeroing placements of profiles/r2_notes.md
 TAG=${1:-r2n}; N=${2:-2}
 OUT=gpurun_out; mkdir -p $OUT
-nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
+nvidia-smi topo -m > $OUT/${TAG}_topo_n$N.txt 2>&1
 timeout 400 python -m pytest tests/test_gpu_multirank.py tests/test_gpu_round2.py -m gpu -q -k "two_ranks or non_current_device" > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -4 $OUT/${TAG}_pytest.log
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 \
-    tools/allreduce_bench.py > $OUT/${TAG}_allreduce_n$N.jsonl 2> $OUT/${TAG}_allreduce_n$N.err; echo "allreduce bench rc=$?"; cat $OUT/${TAG}_allreduce_n$N.jsonl
+    tools/allreduce_bench.py > $OUT/${TAG}_allreduce_n$N.jsonl 2> $OUT/${TAG}_allreduce_n$N.err; echo "allreduce bench rc=$?"; grep '^{' $OUT/${TAG}_allreduce_n$N.jsonl
 QUICK="--no-e2e --no-secondary --no-cpu-baseline"
-for n in $(seq 2 $N | awk -v N=$N '$1==2||$1==4||$1==8'); do
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29611 \
-      bench.py --gpus $n --steps 1000 --warmup 100 $QUICK > $OUT/${TAG}_bench_n$n.json 2> $OUT/${TAG}_bench_n$n.err; echo "bench n=$n rc=$?"
-done
-if [ "${3:-}" != "diag" ]; then ls -la $OUT | grep ${TAG}; exit 0; fi
-# N = 1 with and without a 1-rank NCCL communicator: step time and per-kernel durations
-timeout 300 python bench.py --steps 1000 --warmup 100 $QUICK --no-strong > $OUT/${TAG}_n1_nopg.json 2> $OUT/${TAG}_n1_nopg.err
-ZS_BENCH_FORCE_PG=1 timeout 300 python bench.py --steps 1000 --warmup 100 $QUICK --no-strong > $OUT/${TAG}_n1_pg.json 2> $OUT/${TAG}_n1_pg.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_n1_nopg_launches.csv \
-    python bench.py --steps 20 --warmup 5 --graph 0 $QUICK --no-strong > /dev/null 2>&1
-ZS_BENCH_FORCE_PG=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_n1_pg_launches.csv \
-    python bench.py --steps 20 --warmup 5 --graph 0 $QUICK --no-strong > /dev/null 2>&1
-ls -la $OUT | grep ${TAG}
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+    bench.py --gpus $N --steps 1000 --warmup 100 $QUICK > $OUT/${TAG}_${name}_n$N.json 2> $OUT/${TAG}_${name}_n$N.err
+  python - <<PY
+import json
+for l in open("$OUT/${TAG}_${name}_n$N.json"):
+    if l.startswith("{"):
+        b=json.loads(l); c=b["comm"] or {}
+        print("$name: step %.2f us value %.0f M/s  variant %s tuned %s launches %s strong %s" % (b["ms_per_step"]*1e3, b["value"]/1e6, c.get("peer_variant"), c.get("peer_tuned_us"), b["launches_per_step"], [(x["B_global"], round(x["ms_per_step"]*1e3,2)) for x in b.get("strong_scaling", [])]))
+PY
+}
+run bench A=1
+if [ "${3:-}" = "variants" ]; then
+  QUICK="$QUICK --no-strong"
+  run side ZS_BUCKET_STREAM=side
+  run nccl ZS_BENCH_COMM=nccl
+  run pdl0 ZS_PDL=0
+fi
+ls -la $OUT | grep ${TAG}_
