@@ -22,6 +22,11 @@ for K, B, X in ((50, 9, 784), (7, 5, 128), (25, 160, 256), (33, 20, 512), (20, 6
         be.set_fused_impl(be.IMPL_DEFAULT)
         acc = torch.zeros(B, device=dev)
         be.iw_bernoulli_fused(est, probs, x, other, logq, 1.0 / B, out={"cost": acc}, accumulate_cost=True)
+        for impl in (be.IMPL_BOX, be.IMPL_BOXG, be.IMPL_RING):  # the objective written by the launch itself
+            be.set_fused_impl(impl)
+            for _ in range(2):
+                be.iw_bernoulli_fused(est, probs, x, other, logq, 1.0 / B, cost_scaled=True, want_loss=True)
+        be.set_fused_impl(be.IMPL_DEFAULT)
         if be.fused_logits_supported(K, X, torch.float32):
             be.iw_bernoulli_fused(est, torch.randn(K, B, X, device=dev), x, other, logq, 1.0 / B, logits=True)
     l = torch.randn(K, B, X, device=dev)
@@ -30,8 +35,15 @@ for K, B, X in ((50, 9, 784), (7, 5, 128), (25, 160, 256), (33, 20, 512), (20, 6
 for n in (1, 7, 4097, 51200):
     mm, ls = torch.zeros(1, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
     be.reinforce_step(torch.randn(n, device=dev), torch.randn(n, device=dev), mm, ls, 0.8)
-for K, M, E in ((50, 37, 40), (3, 5, 8), (1, 9, 4), (6, 2, 132), (4, 3, 4600)):
+state = torch.zeros(2, dtype=torch.int64, device=dev)  # device-side Philox position
+for K, M, E in ((50, 37, 40), (3, 5, 8), (1, 9, 4), (6, 2, 132), (4, 3, 4600), (9, 77, 64)):
     mean, std = torch.randn(M, E, device=dev), torch.rand(M, E, device=dev) + 0.5
+    for impl in (0, 1):  # lane-per-unit / row-per-thread forward
+        be.set_latent_fwd_impl(impl)
+        be.normal_latent_fwd(mean, std, KBCAST if K > 1 else FULL, K, M, E, seed=1, offset=4)
+        be.normal_latent_fwd(mean, std, KBCAST if K > 1 else FULL, K, M, E, seed=1, rng_state=state, prior_mean=mean, prior_std=std)
+        be.bernoulli_latent_fwd(torch.rand(M, E, device=dev).clamp(0.05, 0.95), KBCAST if K > 1 else FULL, K, M, E, seed=1, rng_state=state)
+    be.set_latent_fwd_impl(-1)
     z, lq, lp = be.normal_latent_fwd(mean, std, KBCAST if K > 1 else FULL, K, M, E, seed=1, offset=4)
     be.normal_latent_bwd(lq, lp, torch.randn_like(z), z, mean, std, KBCAST if K > 1 else FULL, K, M, E, reparameterized=True)
     p = torch.rand(M, E, device=dev).clamp(0.05, 0.95)
