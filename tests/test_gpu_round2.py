@@ -523,6 +523,30 @@ def test_cpu_sample_keeps_its_autograd_connection():
     torch.testing.assert_close(gz, -z.detach())
 
 
+def test_gradient_bucket_zeroing_in_line_and_overlapped():
+    """GradientBucket on one GPU (no process group: the collectives are local no-ops): `.grad` tensors are views of the
+    flat buffer, zero_grad() in line and zero_grad(overlap=True) (memset on the side stream, joined by the parameters'
+    tensor hook before the first accumulation) both leave exactly this step's gradients in the buffer, step after step;
+    finish(loss) puts the objective into the bucket's last slot."""
+    import zhusuan.distributed as zd
+    torch.manual_seed(3)
+    lin = torch.nn.Sequential(torch.nn.Linear(64, 48), torch.nn.Tanh(), torch.nn.Linear(48, 7)).to(DEV)
+    bucket = zd.GradientBucket([lin.parameters()])
+    assert bucket.backend == "local"
+    assert all(p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr() for p in lin.parameters())
+    for step, overlap in enumerate((True, False, True, True)):
+        x = torch.randn(16, 64, device=DEV)
+        bucket.zero_grad(overlap=overlap)
+        loss = lin(x).square().mean()
+        loss.backward()
+        bucket.finish(loss)
+        torch.cuda.synchronize()
+        ref = torch.autograd.grad(lin(x).square().mean(), list(lin.parameters()))
+        for p, r in zip(lin.parameters(), ref):
+            torch.testing.assert_close(p.grad, r, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(bucket.loss(), loss.detach(), rtol=0, atol=0)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_operands_on_a_non_current_device():
     """tensors on cuda:1 while cuda:0 is current launch on cuda:1's stream."""
