@@ -376,7 +376,9 @@ class KernelSequence(object):
         kbx, kbz, kb, bz, bx = 4 * K * B * X, 4 * K * B * Z, 4 * K * B, 4 * B * Z, 4 * B * X
         fused = 2 * kbx + bx + 4 * kb + 4 * B          # probs R, dprobs W, x R, other/logq R, dlogp/dlogq W, cost W
         if self.vimco:
-            small = (bz + kbz + 2 * kb) + (kb + kbz + 2 * bz)            # latent fwd (W z, logq, logp), latent bwd
+            # latent fwd: R pq, W z, its packed copy (one byte per float4 unit), logq, logp; latent bwd: R dlogq, the
+            # packed sample, pq, W dpq
+            small = (bz + kbz + kbz // 16 + 2 * kb) + (kb + kbz // 16 + 2 * bz)
         else:
             small = (2 * bz + kbz + 2 * kb) + (2 * kb + 2 * kbz + 4 * bz)  # fwd: R mean,std W z,logq,logp; bwd: R g's,z,dz_up
         return fused, fused + small
@@ -386,9 +388,10 @@ class KernelSequence(object):
         K, B, Z = K_PART, self.B, Z_DIM
         n0 = be.launch_count
         if self.vimco:
-            z, logq, logpz = be.bernoulli_latent_fwd(self.pq, be.KBCAST, K, B, Z, seed=self.seed, rng_state=self.state)
+            z, logq, logpz, zbits = be.bernoulli_latent_fwd(self.pq, be.KBCAST, K, B, Z, seed=self.seed,
+                                                            rng_state=self.state, want_bits=True)
             r = be.iw_bernoulli_fused(be.VIMCO, self.probs, self.x, logpz, logq, 1.0 / B)
-            dpq = be.bernoulli_latent_bwd(r["dlogq"], z, self.pq, be.KBCAST, K, B, Z)
+            dpq = be.bernoulli_latent_bwd(r["dlogq"], z, self.pq, be.KBCAST, K, B, Z, zbits=zbits)
             self.out = (r["cost"], r["dprobs"], dpq)
         else:
             z, logq, logpz = be.normal_latent_fwd(self.mean, self.std, be.KBCAST, K, B, Z, seed=self.seed,

@@ -190,9 +190,12 @@ int zs_bernoulli_logits_logpmf_bwd(int dtype, void* dx, void* dlogits, const voi
 int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* mean, int mean_mode, const void* std,
                          int std_mode, const void* prior_mean, const void* prior_std, const void* eps_in, int64_t K,
                          int64_t M, int64_t E, uint64_t seed, uint64_t offset, void* rng_state, zs_stream_t stream);
+/* zbits (may be NULL; float32 / KBCAST only, else ZS_ERR_UNSUPPORTED): the sample once more as bits -- one byte per
+ * float4 unit of z ([K, M, E/4] bytes, bit q of byte (k, m, j) = z[k, m, 4j+q]).  zs_bernoulli_latent_bwd reads it
+ * instead of z when given: 0.5 MB instead of 8 MB at config 3, behind a kernel whose write-back is still draining. */
 int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
                             const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                            uint64_t offset, void* rng_state, zs_stream_t stream);
+                            uint64_t offset, void* rng_state, void* zbits, zs_stream_t stream);
 /* Backward in ONE launch: gradient of  <dlogq, log q> + <dlogp, log p> + <dz_up, z>  wrt the variational
  * parameters: autograd of both log-densities, the decoder's upstream gradient dz_up [K,M,E] (may be
  * NULL) and, if reparameterized, the pathwise backward of the sample (eps recovered as (z-mean)/std),
@@ -202,7 +205,7 @@ int zs_normal_latent_bwd(int dtype, void* dmean, void* dstd, const void* dlogq, 
                          const void* prior_mean, const void* prior_std, int reparameterized, int64_t K, int64_t M,
                          int64_t E, zs_stream_t stream);
 int zs_bernoulli_latent_bwd(int dtype, void* dprobs, const void* dlogq, const void* z, const void* probs,
-                            int probs_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream);
+                            int probs_mode, int64_t K, int64_t M, int64_t E, const void* zbits, zs_stream_t stream);
 
 /* ---- Categorical stochastic node (absent from the reference: parity unpinned;
  * API modelled on bernoulli.py) --------------------------------

@@ -85,8 +85,15 @@ def normal_latent_bwd(dlogq, dlogp, dz_up, z, mean, std, mode, K, M, E, prior_me
     return _t(dm, z), _t(ds, z)
 
 
+def _pack_bits(z):
+    """[K,M,E] 0/1 -> [K,M,E/4] uint8, bit q of a byte = element 4j+q (the kernels' packed-sample layout)."""
+    K, M, E = z.shape
+    b = (z.reshape(K, M, E // 4, 4) != 0).astype(np.uint8)
+    return (b[..., 0] | (b[..., 1] << 1) | (b[..., 2] << 2) | (b[..., 3] << 3)).astype(np.uint8)
+
+
 def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want_logq=True, want_logp=True, seed=0,
-                         offset=0, rng_state=None):
+                         offset=0, rng_state=None, want_bits=False):
     dt = _np(probs).dtype
     u = (O.philox_uniform(K * M * E, seed, offset).astype(dt) if u_in is None else _np(u_in)).reshape(K, M * E)
     z = O.bernoulli_sample(_np(probs), u, K, M * E).reshape(K, M, E)
@@ -95,10 +102,14 @@ def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want
     if want_logp:
         pp = np.full((M, E), 0.5, dt) if prior_probs is None else _np(prior_probs)
         logp = O.bernoulli_logpmf_fwd(z, pp, K, M, E)
-    return _t(z, probs), None if logq is None else _t(logq, probs), None if logp is None else _t(logp, probs)
+    out = (_t(z, probs), None if logq is None else _t(logq, probs), None if logp is None else _t(logp, probs))
+    if want_bits:
+        ok = dt == np.float32 and mode == KBCAST and E % 4 == 0 and E <= 128
+        out = out + ((torch.from_numpy(_pack_bits(z)) if ok else None),)
+    return out
 
 
-def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E):
+def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E, zbits=None):
     dp = O.bernoulli_logpmf_bwd(_np(dlogq).reshape(K, M), _np(z).reshape(K, M, E), _np(probs), K, M, E)
     return _t(dp.reshape(probs.shape), probs)
 

@@ -892,6 +892,17 @@ def test_bernoulli_latent_fused(oracle, latent_fwd_impl, dt, K, M, E, prior):
     g = rng.standard_normal((K, M)).astype(dt)
     dpq = be.bernoulli_latent_bwd(dev(g), z, dev(pq), KBCAST, K, M, E)
     close(host(dpq), oracle.bernoulli_logpmf_bwd(f64(g), f64(zo), f64(pq), K, M, E), rt)
+    # the forward's packed copy of the sample (one byte per float4 unit) and the backward that reads it instead of z
+    zb, _, _, bits = be.bernoulli_latent_fwd(dev(pq), KBCAST, K, M, E, prior_probs=None if pp is None else dev(pp),
+                                             u_in=dev(u), want_bits=True)
+    assert torch.equal(zb, z)
+    if dt == np.float32:
+        assert bits is not None and bits.dtype == torch.uint8 and bits.shape == (K, M, E // 4)
+        zh = host(z).reshape(K, M, E // 4, 4) != 0
+        assert np.array_equal(host(bits), (zh[..., 0] * 1 + zh[..., 1] * 2 + zh[..., 2] * 4 + zh[..., 3] * 8).astype(np.uint8))
+        assert torch.equal(be.bernoulli_latent_bwd(dev(g), z, dev(pq), KBCAST, K, M, E, zbits=bits), dpq)
+    else:
+        assert bits is None
     z2, _, _ = be.bernoulli_latent_fwd(dev(pq), KBCAST, K, M, E, seed=3, offset=4)
     assert torch.equal(z2.reshape(K, -1), be.bernoulli_sample(dev(pq).reshape(-1), KBCAST, K, M * E, seed=3, offset=4))
 

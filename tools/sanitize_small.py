@@ -47,8 +47,9 @@ for K, M, E in ((50, 37, 40), (3, 5, 8), (1, 9, 4), (6, 2, 132), (4, 3, 4600), (
     z, lq, lp = be.normal_latent_fwd(mean, std, KBCAST if K > 1 else FULL, K, M, E, seed=1, offset=4)
     be.normal_latent_bwd(lq, lp, torch.randn_like(z), z, mean, std, KBCAST if K > 1 else FULL, K, M, E, reparameterized=True)
     p = torch.rand(M, E, device=dev).clamp(0.05, 0.95)
-    zb, lqb, lpb = be.bernoulli_latent_fwd(p, KBCAST if K > 1 else FULL, K, M, E, seed=1, offset=8)
+    zb, lqb, lpb, bits = be.bernoulli_latent_fwd(p, KBCAST if K > 1 else FULL, K, M, E, seed=1, offset=8, want_bits=True)
     be.bernoulli_latent_bwd(lqb, zb, p, KBCAST if K > 1 else FULL, K, M, E)
+    be.bernoulli_latent_bwd(lqb, zb, p, KBCAST if K > 1 else FULL, K, M, E, zbits=bits)
 for K, E in ((5, 2048), (3, 4601), (2, 100003)):
     mean, y = torch.randn(K, 1, E, device=dev), torch.randn(1, E, device=dev)
     std = torch.full((1,), 0.3, device=dev)

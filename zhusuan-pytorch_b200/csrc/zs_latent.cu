@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(LF_WARPS * 32, 8)
     k_latent_fwd_fast(float* __restrict__ z, float* __restrict__ logq, float* __restrict__ logp,
                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
                       const float* __restrict__ pb, const float* __restrict__ noise_in, int K, int M, int E4, int RW,
-                      int KS, unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs) {
+                      int KS, unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs,
+                      unsigned char* __restrict__ zbits) {
     pdl_wait();     // the parameters may come from the kernel before this one
     pdl_trigger();  // the next kernel's CTAs may be scheduled as this grid drains
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -394,6 +395,11 @@ __global__ void __launch_bounds__(LF_WARPS * 32, 8)
             else accp = cp + ((zv.x * pm.x + zv.y * pm.y) + (zv.z * pm.z + zv.w * pm.w));
         }
         *reinterpret_cast<float4*>(z + 4 * (size_t)unit) = zv;
+        // Bernoulli samples are 0 / 1: four of them as one byte per float4 unit, for consumers that only need the
+        // pattern (zs_iw_bernoulli_fused_vimco_latent reads 0.5 MB of these instead of 8 MB of floats at config 3)
+        if (FAM == FAM_BERNOULLI && zbits)
+            zbits[unit] = (unsigned char)((zv.x != 0.f ? 1 : 0) | (zv.y != 0.f ? 2 : 0) | (zv.z != 0.f ? 4 : 0) |
+                                          (zv.w != 0.f ? 8 : 0));
     };
     // sum over the E4 consecutive lanes of a row (valid in the row's first lane); levels wider than a row are skipped
     auto row_sum = [&](float v) {
@@ -595,7 +601,8 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
     k_latent_fwd_rows(float* __restrict__ z, float* __restrict__ logq, float* __restrict__ logp,
                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
                       const float* __restrict__ pb, const float* __restrict__ noise_in, int K, int M, int E4, int KS,
-                      unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs) {
+                      unsigned inv_e4, uint64_t seed, uint64_t offset, unsigned long long* rs,
+                      unsigned char* __restrict__ zbits) {
     extern __shared__ __align__(16) float lr_smem[];
     pdl_wait();
     pdl_trigger();
@@ -722,6 +729,9 @@ __global__ void __launch_bounds__(LR_WARPS * 32)
                         }
                     }
                     *reinterpret_cast<float4*>(stage + lane * EP + 4 * j) = zv;
+                    if (FAM == FAM_BERNOULLI && zbits)
+                        zbits[unit0 + j] = (unsigned char)((zv.x != 0.f ? 1 : 0) | (zv.y != 0.f ? 2 : 0) |
+                                                           (zv.z != 0.f ? 4 : 0) | (zv.w != 0.f ? 8 : 0));
                 }
             }
             if (logq) logq[(size_t)k * M + m0 + lane] = accq;
@@ -744,7 +754,8 @@ static bool g_latent_fwd_override_set = false;
 template <int FAM>
 static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float* a, int a_mode, const float* b,
                                 const float* pa, const float* pb, const float* noise_in, int64_t K, int64_t M,
-                                int64_t E4, uint64_t seed, uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+                                int64_t E4, uint64_t seed, uint64_t offset, unsigned long long* rs, cudaStream_t st,
+                                unsigned char* zbits) {
     // -1: by shape (below); 0: never (lane-per-unit kernel); 1: whenever the shape qualifies.  ZS_LATENT_FWD_ROWS sets
     // the process default, zs_debug_set_latent_fwd overrides it at run time (tests run both kernels on every shape).
     static const int env_choice = [] {
@@ -777,7 +788,7 @@ static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float*
         return false;
     }
     launch_pdl(PDL_LATENT_FWD, kern, dim3((unsigned)tiles, (unsigned)KS), dim3(LR_WARPS * 32), smem, st, z, logq, logp, a,
-               b, pa, pb, noise_in, (int)K, (int)M, (int)E4, (int)KS, inv, seed, offset, rs);
+               b, pa, pb, noise_in, (int)K, (int)M, (int)E4, (int)KS, inv, seed, offset, rs, zbits);
     return true;
 }
 
@@ -785,24 +796,26 @@ static bool latent_fwd_rows_f32(float* z, float* logq, float* logp, const float*
 template <typename T, int FAM>
 static bool launch_latent_fwd_fast(dim3, T*, T*, T*, const T*, int, const T*, const T*, const T*, const T*, int64_t,
                                    int64_t, int64_t, int, int64_t, uint64_t, uint64_t, unsigned long long*,
-                                   cudaStream_t) {
+                                   cudaStream_t, unsigned char*) {
     return false;
 }
 template <>
 bool launch_latent_fwd_fast<float, FAM_NORMAL>(dim3 grid, float* z, float* logq, float* logp, const float* a, int a_mode,
                                                const float* b, const float* pa, const float* pb, const float* noise_in,
                                                int64_t K, int64_t M, int64_t E4, int RW, int64_t KS, uint64_t seed,
-                                               uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+                                               uint64_t offset, unsigned long long* rs, cudaStream_t st,
+                                               unsigned char* zbits) {
     if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
-    if (latent_fwd_rows_f32<FAM_NORMAL>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st))
+    if (latent_fwd_rows_f32<FAM_NORMAL>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st,
+                                        zbits))
         return true;
     const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
     if (pa == nullptr && pb == nullptr)
         launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_NORMAL, true>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
-                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs, zbits);
     else
         launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_NORMAL, false>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
-                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs, zbits);
     return true;
 }
 template <>
@@ -810,24 +823,25 @@ bool launch_latent_fwd_fast<float, FAM_BERNOULLI>(dim3 grid, float* z, float* lo
                                                   int a_mode, const float* b, const float* pa, const float* pb,
                                                   const float* noise_in, int64_t K, int64_t M, int64_t E4, int RW,
                                                   int64_t KS, uint64_t seed, uint64_t offset, unsigned long long* rs,
-                                                  cudaStream_t st) {
+                                                  cudaStream_t st, unsigned char* zbits) {
     if (a_mode != ZS_KBCAST || K * M * E4 >= ((int64_t)1 << 31) || K * M >= ((int64_t)1 << 31)) return false;
-    if (latent_fwd_rows_f32<FAM_BERNOULLI>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st))
+    if (latent_fwd_rows_f32<FAM_BERNOULLI>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, seed, offset, rs, st,
+                                           zbits))
         return true;
     const unsigned inv = (unsigned)((65536 + E4 - 1) / E4);
     if (pa == nullptr)
         launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_BERNOULLI, true>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
-                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs, zbits);
     else
         launch_pdl(PDL_LATENT_FWD, k_latent_fwd_fast<FAM_BERNOULLI, false>, grid, dim3(LF_WARPS * 32), 0, st, z, logq, logp, a, b, pa, pb,
-                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs);
+                   noise_in, (int)K, (int)M, (int)E4, RW, (int)KS, inv, seed, offset, rs, zbits);
     return true;
 }
 
 template <typename T, int FAM>
 static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, const T* b, int b_mode, const T* pa,
                              const T* pb, const T* noise_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                             uint64_t offset, unsigned long long* rs, cudaStream_t st) {
+                             uint64_t offset, unsigned long long* rs, cudaStream_t st, unsigned char* zbits = nullptr) {
     if (noise_in) rs = nullptr;  // injected noise: no draw, the stream position stays
     const int64_t E4 = E >> 2;
     if (E4 <= 32 && K < ((int64_t)1 << 30)) {
@@ -848,14 +862,22 @@ static int launch_latent_fwd(T* z, T* logq, T* logp, const T* a, int a_mode, con
         ZS_REQUIRE(gx < (int64_t)2147483647, ZS_ERR_UNSUPPORTED);
         dim3 grid((unsigned)gx, (unsigned)KS);
         if (launch_latent_fwd_fast<T, FAM>(grid, z, logq, logp, a, a_mode, b, pa, pb, noise_in, K, M, E4, RW, KS, seed,
-                                           offset, rs, st)) {
+                                           offset, rs, st, zbits)) {
             ZS_LAUNCH_CHECK("k_latent_fwd_fast");
             return ZS_OK;
+        }
+        if (zbits) {
+            set_last_error_msg("the packed sample (zbits) is produced by the float32 / KBCAST forward kernels only");
+            return ZS_ERR_UNSUPPORTED;
         }
         k_latent_fwd_packed<T, FAM><<<grid, LF_WARPS * 32, 0, st>>>(z, logq, logp, a, a_mode, b, pa, pb, noise_in, (int)K, M,
                                                                     (int)E4, RW, (int)KS, seed, offset, rs);
         ZS_LAUNCH_CHECK("k_latent_fwd_packed");
         return ZS_OK;
+    }
+    if (zbits) {
+        set_last_error_msg("the packed sample (zbits) is produced by the float32 / KBCAST forward kernels only");
+        return ZS_ERR_UNSUPPORTED;
     }
     // k-slices per batch row: enough groups to fill the machine, each slice reusing its parameters
 #define ZS_LATENT_FWD(G)                                                                                          \
@@ -923,7 +945,8 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, LBF_U > 4 ? 2 : 4)
     k_latent_bwd_fast(float* __restrict__ da, float* __restrict__ db, const float* __restrict__ gq,
                       const float* __restrict__ gp, const float* __restrict__ dz_up, const float* __restrict__ z,
                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ pa,
-                      const float* __restrict__ pb, int reparam, int K, int M, int E) {
+                      const float* __restrict__ pb, int reparam, int K, int M, int E,
+                      const unsigned char* __restrict__ zbits) {
     pdl_wait();
     pdl_trigger();
     const int LBX = blockDim.x, LBY = blockDim.y;
@@ -965,7 +988,15 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, LBF_U > 4 ? 2 : 4)
                 const size_t fe = 4 * ((size_t)kc * ME4 + u);
                 g_q[i] = gq ? __ldg(gq + r) : 0.f;
                 g_p[i] = has_gp ? __ldg(gp + r) : 0.f;
-                zv[i] = *reinterpret_cast<const float4*>(z + fe);
+                if (FAM == FAM_BERNOULLI && zbits != nullptr) {
+                    // the forward's packed copy of the sample (one byte per float4 unit): 1/16 of the bytes, which
+                    // matters behind the fused kernel, whose write-back is still draining when this kernel reads
+                    const unsigned bb = zbits[(size_t)kc * ME4 + u];
+                    zv[i] = make_float4((bb & 1u) ? 1.f : 0.f, (bb & 2u) ? 1.f : 0.f, (bb & 4u) ? 1.f : 0.f,
+                                        (bb & 8u) ? 1.f : 0.f);
+                } else {
+                    zv[i] = *reinterpret_cast<const float4*>(z + fe);
+                }
                 du[i] = has_du ? *reinterpret_cast<const float4*>(dz_up + fe) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
@@ -1021,13 +1052,14 @@ __global__ void __launch_bounds__(LB_X_MAX* LB_Y_MAX, LBF_U > 4 ? 2 : 4)
 
 template <typename T, int FAM>
 static bool launch_latent_bwd_fast(void*, void*, const void*, const void*, const void*, const void*, const void*, int,
-                                   const void*, const void*, const void*, int, int64_t, int64_t, int64_t, cudaStream_t) {
+                                   const void*, const void*, const void*, int, int64_t, int64_t, int64_t, cudaStream_t,
+                                   const void*) {
     return false;
 }
 template <int FAM>
 static bool latent_bwd_fast_f32(void* da, void* db, const void* gq, const void* gp, const void* dz_up, const void* z,
                                 const void* a, int a_mode, const void* b, const void* pa, const void* pb, int reparam,
-                                int64_t K, int64_t M, int64_t E, cudaStream_t st) {
+                                int64_t K, int64_t M, int64_t E, cudaStream_t st, const void* zbits) {
     if (a_mode != ZS_KBCAST || K * M * E >= ((int64_t)1 << 31) || da == nullptr || (FAM == FAM_NORMAL && db == nullptr))
         return false;
     const int64_t ME4 = (M * E) >> 2;
@@ -1065,30 +1097,31 @@ static bool latent_bwd_fast_f32(void* da, void* db, const void* gq, const void* 
     }
     launch_pdl(PDL_LATENT_BWD, kern, dim3(grid), block, 0, st, (float*)da, (float*)db, (const float*)gq, (const float*)gp,
                (const float*)dz_up, (const float*)z, (const float*)a, (const float*)b, (const float*)pa,
-               (const float*)pb, reparam, (int)K, (int)M, (int)E);
+               (const float*)pb, reparam, (int)K, (int)M, (int)E, (const unsigned char*)zbits);
     return true;
 }
 template <>
 bool launch_latent_bwd_fast<float, FAM_NORMAL>(void* da, void* db, const void* gq, const void* gp, const void* dz_up,
                                                const void* z, const void* a, int a_mode, const void* b, const void* pa,
                                                const void* pb, int reparam, int64_t K, int64_t M, int64_t E,
-                                               cudaStream_t st) {
-    return latent_bwd_fast_f32<FAM_NORMAL>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st);
+                                               cudaStream_t st, const void* zbits) {
+    return latent_bwd_fast_f32<FAM_NORMAL>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st, zbits);
 }
 template <>
 bool launch_latent_bwd_fast<float, FAM_BERNOULLI>(void* da, void* db, const void* gq, const void* gp, const void* dz_up,
                                                   const void* z, const void* a, int a_mode, const void* b,
                                                   const void* pa, const void* pb, int reparam, int64_t K, int64_t M,
-                                                  int64_t E, cudaStream_t st) {
-    return latent_bwd_fast_f32<FAM_BERNOULLI>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st);
+                                                  int64_t E, cudaStream_t st, const void* zbits) {
+    return latent_bwd_fast_f32<FAM_BERNOULLI>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E, st, zbits);
 }
 
 template <typename T, int FAM>
 static int launch_latent_bwd(void* da, void* db, const void* gq, const void* gp, const void* dz_up, const void* z,
                              const void* a, int a_mode, const void* b, int b_mode, const void* pa, const void* pb,
-                             int reparam, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+                             int reparam, int64_t K, int64_t M, int64_t E, zs_stream_t stream,
+                             const void* zbits = nullptr) {
     if (launch_latent_bwd_fast<T, FAM>(da, db, gq, gp, dz_up, z, a, a_mode, b, pa, pb, reparam, K, M, E,
-                                       as_stream(stream))) {
+                                       as_stream(stream), zbits)) {
         ZS_LAUNCH_CHECK("k_latent_bwd_fast");
         return ZS_OK;
     }
@@ -1153,8 +1186,9 @@ int zs_normal_latent_fwd(int dtype, void* z, void* logq, void* logp, const void*
 
 int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const void* probs, int probs_mode,
                             const void* prior_probs, const void* u_in, int64_t K, int64_t M, int64_t E, uint64_t seed,
-                            uint64_t offset, void* rng_state, zs_stream_t stream) {
+                            uint64_t offset, void* rng_state, void* zbits, zs_stream_t stream) {
     ZS_REQUIRE(z && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
+    ZS_REQUIRE(zbits == nullptr || dtype == ZS_F32, ZS_ERR_UNSUPPORTED);
     int rc = latent_args_ok(probs, probs_mode, nullptr, probs_mode, FAM_BERNOULLI, E, {z, probs, prior_probs, u_in});
     if (rc != ZS_OK) return rc;
     if (K * M == 0) return ZS_OK;
@@ -1162,7 +1196,8 @@ int zs_bernoulli_latent_fwd(int dtype, void* z, void* logq, void* logp, const vo
         return launch_latent_fwd<float, FAM_BERNOULLI>((float*)z, (float*)logq, (float*)logp, (const float*)probs,
                                                        probs_mode, nullptr, probs_mode, (const float*)prior_probs,
                                                        nullptr, (const float*)u_in, K, M, E, seed, offset,
-                                                       (unsigned long long*)rng_state, as_stream(stream));
+                                                       (unsigned long long*)rng_state, as_stream(stream),
+                                                       (unsigned char*)zbits);
     if (dtype == ZS_F64)
         return launch_latent_fwd<double, FAM_BERNOULLI>((double*)z, (double*)logq, (double*)logp,
                                                         (const double*)probs, probs_mode, nullptr, probs_mode,
@@ -1194,14 +1229,14 @@ int zs_normal_latent_bwd(int dtype, void* dmean, void* dstd, const void* dlogq, 
 }
 
 int zs_bernoulli_latent_bwd(int dtype, void* dprobs, const void* dlogq, const void* z, const void* probs,
-                            int probs_mode, int64_t K, int64_t M, int64_t E, zs_stream_t stream) {
+                            int probs_mode, int64_t K, int64_t M, int64_t E, const void* zbits, zs_stream_t stream) {
     ZS_REQUIRE(dprobs && dlogq && z && probs && K >= 0 && M >= 0 && E >= 1, ZS_ERR_ARG);
     int rc = latent_args_ok(probs, probs_mode, nullptr, probs_mode, FAM_BERNOULLI, E, {dprobs, z, probs});
     if (rc != ZS_OK) return rc;
     if (K * M == 0) return ZS_OK;
     if (dtype == ZS_F32)
         return launch_latent_bwd<float, FAM_BERNOULLI>(dprobs, nullptr, dlogq, nullptr, nullptr, z, probs, probs_mode,
-                                                       nullptr, probs_mode, nullptr, nullptr, 0, K, M, E, stream);
+                                                       nullptr, probs_mode, nullptr, nullptr, 0, K, M, E, stream, zbits);
     if (dtype == ZS_F64)
         return launch_latent_bwd<double, FAM_BERNOULLI>(dprobs, nullptr, dlogq, nullptr, nullptr, z, probs,
                                                         probs_mode, nullptr, probs_mode, nullptr, nullptr, 0, K, M, E,

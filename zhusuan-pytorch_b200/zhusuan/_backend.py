@@ -55,9 +55,9 @@ def _declare(lib):
         "zs_normal_logprob_fwd": (i32, [i32, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_normal_logprob_bwd": (i32, [i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_normal_latent_fwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, i64, i64, i64, u64, u64, vp, vp]),
-        "zs_bernoulli_latent_fwd": (i32, [i32, vp, vp, vp, vp, i32, vp, vp, i64, i64, i64, u64, u64, vp, vp]),
+        "zs_bernoulli_latent_fwd": (i32, [i32, vp, vp, vp, vp, i32, vp, vp, i64, i64, i64, u64, u64, vp, vp, vp]),
         "zs_normal_latent_bwd": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i64, i64, i64, vp]),
-        "zs_bernoulli_latent_bwd": (i32, [i32, vp, vp, vp, vp, i32, i64, i64, i64, vp]),
+        "zs_bernoulli_latent_bwd": (i32, [i32, vp, vp, vp, vp, i32, i64, i64, i64, vp, vp]),
         "zs_bernoulli_sample": (i32, [i32, vp, vp, i32, vp, i64, i64, u64, u64, vp, vp]),
         "zs_bernoulli_logpmf_fwd": (i32, [i32, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
         "zs_bernoulli_logpmf_bwd": (i32, [i32, vp, vp, vp, vp, i32, vp, i32, i64, i64, i64, vp]),
@@ -297,26 +297,43 @@ def normal_latent_bwd(dlogq, dlogp, dz_up, z, mean, std, mode, K, M, E, prior_me
 
 
 def bernoulli_latent_fwd(probs, mode, K, M, E, prior_probs=None, u_in=None, want_logq=True, want_logp=True, seed=0,
-                         offset=0, rng_state=None):
+                         offset=0, rng_state=None, want_bits=False):
+    """-> (z [K,M,E], logq, logp), or None when the shape is not supported.  `want_bits=True`: a fourth element, the
+    sample packed as one byte per float4 unit ([K, M, E/4] uint8; bernoulli_latent_bwd reads it instead of z), or None
+    where the launch has no packed output (not float32 / KBCAST / E > 128)."""
     dt, dev = probs.dtype, probs.device
     _chk(dev, dt, probs=probs, prior_probs=prior_probs, u_in=u_in)
     _chk_state(dev, rng_state=rng_state)
     z = torch.empty((K, M, E), dtype=dt, device=dev)
     logq = torch.empty((K, M), dtype=dt, device=dev) if want_logq else None
     logp = torch.empty((K, M), dtype=dt, device=dev) if want_logp else None
+    bits = None
+    if want_bits and dt == torch.float32 and mode == KBCAST and E % 4 == 0 and E <= 128:
+        bits = torch.empty((K, M, E // 4), dtype=torch.uint8, device=dev)
     rc = _run("zs_bernoulli_latent_fwd", dev, dtype_code(dt), _ptr(z), _ptr(logq), _ptr(logp), _ptr(probs), mode,
-              _ptr(prior_probs), _ptr(u_in), K, M, E, seed, offset, _ptr(rng_state))
+              _ptr(prior_probs), _ptr(u_in), K, M, E, seed, offset, _ptr(rng_state), _ptr(bits))
+    if rc == ERR_UNSUPPORTED and bits is not None:  # this shape's forward kernel has no packed output
+        bits = None
+        rc = _run("zs_bernoulli_latent_fwd", dev, dtype_code(dt), _ptr(z), _ptr(logq), _ptr(logp), _ptr(probs), mode,
+                  _ptr(prior_probs), _ptr(u_in), K, M, E, seed, offset, _ptr(rng_state), None)
     if rc in (ERR_UNSUPPORTED, ERR_ALIGN):
         return None
     check(rc, "zs_bernoulli_latent_fwd")
-    return z, logq, logp
+    return (z, logq, logp, bits) if want_bits else (z, logq, logp)
 
 
-def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E):
+def bernoulli_latent_bwd(dlogq, z, probs, mode, K, M, E, zbits=None):
+    """`zbits`: the forward's packed copy of z (bernoulli_latent_fwd(want_bits=True)); read instead of z where the
+    float32 / KBCAST backward kernel runs."""
     dt, dev = z.dtype, z.device
     _chk(dev, dt, dlogq=dlogq, z=z, probs=probs)
+    if zbits is not None:
+        _chk(dev, torch.uint8, zbits=zbits)
+        if tuple(zbits.shape) != (K, M, E // 4) or dt != torch.float32 or mode != KBCAST:
+            zbits = None
     dprobs = torch.empty_like(probs)
-    _go("zs_bernoulli_latent_bwd", dev, dtype_code(dt), _ptr(dprobs), _ptr(dlogq), _ptr(z), _ptr(probs), mode, K, M, E)
+    _go("zs_bernoulli_latent_bwd", dev, dtype_code(dt), _ptr(dprobs), _ptr(dlogq), _ptr(z), _ptr(probs), mode, K, M, E,
+        _ptr(zbits))
     return dprobs
 
 

@@ -379,10 +379,11 @@ class _BernoulliLatent(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probs, mode, K, M, E, u_in):
         fwd_kw, _ = _draw_kwargs(probs.device, u_in)
-        r = be.bernoulli_latent_fwd(probs, mode, K, M, E, u_in=u_in, want_logp=True, **fwd_kw)
+        r = be.bernoulli_latent_fwd(probs, mode, K, M, E, u_in=u_in, want_logp=True, want_bits=True, **fwd_kw)
         if r is None:
             raise be.BackendError("latent kernel refused a shape latent_supported() accepted")
-        z, logq, logp = r
+        z, logq, logp, bits = r
+        ctx.bits = bits  # the sample packed as bits (or None): what the backward reads instead of the 16x larger z
         ctx.save_for_backward(z, probs)
         ctx.cfg = (mode, K, M, E)
         ctx.mark_non_differentiable(z, logp)
@@ -397,7 +398,8 @@ class _BernoulliLatent(torch.autograd.Function):
         mode, K, M, E = ctx.cfg
         if dlogq is None:
             return torch.zeros_like(probs), None, None, None, None, None
-        return be.bernoulli_latent_bwd(dlogq.contiguous(), z, probs, mode, K, M, E), None, None, None, None, None
+        return (be.bernoulli_latent_bwd(dlogq.contiguous(), z, probs, mode, K, M, E, zbits=ctx.bits), None, None, None,
+                None, None)
 
 
 # log-density of a fused draw under the standard prior of its family, keyed by the identity of the sample tensor the
