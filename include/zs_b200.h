@@ -401,7 +401,7 @@ int zs_allreduce_sum_peer(float* const* bufs_host, void* const* flags_host, int 
 /* The same exchange through an NVSwitch multicast mapping (NVLS): `multicast_buf` is ONE address that names the buffer
  * in every rank's memory (cuMulticast* / torch symmetric memory's multicast_ptr).  Rank r reads slice r with
  * multimem.ld_reduce (the switch returns the SUM over the ranks) and writes it back with multimem.st (the switch
- * stores into every rank's copy): 2/N of the buffer crosses each GPU's links instead of 2(N-1)/N.  Flags as above
+ * stores into every rank's copy): (1 + 1/N) buffer volumes per GPU and direction instead of 2(N-1)/N.  Flags as above
  * (unicast peer pointers); `local_buf` is this rank's ordinary pointer to its own buffer (for extra_src).  All ranks
  * receive the same bits; the switch's summation order is its own.                                                */
 int zs_allreduce_sum_nvls(float* multicast_buf, float* local_buf, void* const* flags_host, int rank, int world,

@@ -135,10 +135,13 @@ __global__ void __launch_bounds__(ZS_PEER_THREADS)
 // With the buffer bound to a multicast object (one address that names the same offset in EVERY rank's memory) the
 // switch does the work: multimem.ld_reduce makes the switch fetch an element from all ranks and return the SUM,
 // multimem.st writes a value into all ranks' copies.  Rank r still owns slice r, but per element it issues ONE load and
-// ONE store whatever the world size -- 2/N of the buffer crosses this GPU's links instead of 2(N-1)/N -- which is
-// what matters at N = 8 (4.7 MB in + 4.7 MB out per rank with peer loads / stores against 0.67 + 0.67 MB here for the
-// 5.4 MB gradient bucket).  Barriers, flags and epochs are the unicast ones above.  The switch adds in its own fixed
-// order, so every rank receives the same bits, but they may differ in the last place from the rank-order sum.
+// ONE store whatever the world size.  The switch still has to fetch every rank's copy of a slice and to deliver every
+// slice to every rank, so per GPU and direction (1 + 1/N) buffer volumes cross the links (the reduce phase mostly
+// outbound, the broadcast phase mostly inbound) against 2(N-1)/N for peer loads / stores: more traffic at N = 2, less
+// from N = 4 on.  Measured on the 5.4 MB gradient bucket: N = 2 27.8 us against 20.6 us for the peer kernel, N = 4
+// 25.4 against 25.1, N = 8 25.8 against 28.9 (tools/allreduce_bench.py); the caller times both and keeps the faster.
+// Barriers, flags and epochs are the unicast ones above.  The switch adds in its own fixed order, so every rank
+// receives the same bits, but they may differ in the last place from the rank-order sum.
 __device__ __forceinline__ float4 mc_ld_reduce(const float* mc) {
     float4 r;
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
